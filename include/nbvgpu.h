@@ -1,0 +1,190 @@
+/* nbvgpu.h -- C ABI of the B200-native viewpoint-gain path.
+ *
+ * Drop-in boundary for the three reference call sites that make up the hot path
+ * of RaccoonlabDev/nbv_exploration_planner (citations relative to the reference
+ * tree).  The reference has no plugin / FFI interface: the path is three C++
+ * member functions reached through concrete pointers, so each entry point below
+ * names the member function / call site it replaces.
+ *
+ *   RrtTree::optimized_gain(Pose&)        nbveplanner/src/rrt.cpp:351-479   -> nbvgpu_gain_eval*, nbvgpu_optimized_gain
+ *   RrtTree::gain(Pose&)                  nbveplanner/src/rrt.cpp:481-579   -> same, camera.sum_all_yaws = 1
+ *   HighResManager::checkMotion<T>        nbveplanner/include/nbveplanner/voxblox_manager.h:89-108
+ *                                                                           -> nbvgpu_check_segments*, nbvgpu_check_motion
+ *   VoxbloxManager::getVoxelStatusByIndex nbveplanner/src/voxblox_manager.cpp:14-33 (map read side)
+ *   voxblox::Layer<VoxelType> block hash  voxblox/voxblox/include/voxblox/core/layer.h:23-296,
+ *                                         core/block_hash.h:20-31           -> nbvgpu_layer_* (GPU mirror)
+ *   node scoring in RrtTree::iterate      nbveplanner/src/rrt.cpp:220-246   -> nbvgpu_gain_eval_best*
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer;
+ * the library owns device memory, pinned staging and its CUDA stream.  All
+ * functions return an nbvgpu_status (0 = OK, < 0 = error); nothing throws across
+ * the ABI and there is NO CPU fallback: without a usable CUDA device
+ * nbvgpu_create fails with NBVGPU_ERR_NO_DEVICE.
+ *
+ * Threading (mirrors the reference): gain_eval from the planner
+ * thread, check_segments from planner and history threads, layer_update/commit
+ * from the map (ROS spin) thread.  Every entry point is serialised on the
+ * context by a mutex; work is ordered on one CUDA stream, so an evaluation always
+ * sees the map as of the last nbvgpu_commit enqueued before it.
+ *
+ * "_device" variants take DEVICE pointers (inputs already resident in HBM, e.g.
+ * the result of an NCCL broadcast) and are asynchronous on the context stream.
+ */
+#ifndef NBVGPU_H_
+#define NBVGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct nbvgpu_ctx nbvgpu_ctx;
+
+typedef enum {
+  NBVGPU_OK = 0,
+  NBVGPU_ERR_INVALID = -1,   /* null pointer, bad enum, bad size                      */
+  NBVGPU_ERR_NO_DEVICE = -2, /* no CUDA device / not sm_100: there is no CPU fallback */
+  NBVGPU_ERR_CUDA = -3,      /* a CUDA runtime call failed (see nbvgpu_last_error)    */
+  NBVGPU_ERR_CAPACITY = -4,  /* layer block pool or hash table full                   */
+  NBVGPU_ERR_STATE = -5,     /* camera not set, wrong layer kind, ...                 */
+  NBVGPU_ERR_RANGE = -6      /* non-finite or out-of-range coordinate (|x/voxel| >= 2^22) */
+} nbvgpu_status;
+
+/* Layer kinds: TsdfVoxel {distance, weight} / EsdfVoxel {distance}  (voxblox core/voxel.h:12-37). */
+enum { NBVGPU_LAYER_TSDF = 0, NBVGPU_LAYER_ESDF = 1 };
+
+/* Payload packings accepted by nbvgpu_layer_update*:
+ *  PLANAR : TSDF float[n][vps^3][2] = (distance, weight); ESDF float[n][vps^3] = distance.
+ *  VOXBLOX: the reference's own block serialisation (voxblox/src/core/block.cc:159-183 TSDF =
+ *           3 x u32 per voxel: distance bits, weight bits, rgba; :203-234 ESDF = 2 x u32 per voxel:
+ *           distance bits, parent|flags), i.e. the body of voxblox_msgs/Block.data. */
+enum { NBVGPU_PACK_PLANAR = 0, NBVGPU_PACK_VOXBLOX = 1 };
+
+/* Camera + gain parameters: the inputs of CameraModel::setIntrinsicsFromFoV / setExtrinsics /
+ * setBoundingBox (nbveplanner/src/camera_model.cpp:25-96, nbvep.cpp:40-61) and Params::gain_*
+ * (nbveplanner/include/nbveplanner/params.h:57-62). */
+typedef struct {
+  double hfov_deg, vfov_deg; /* system/camera/hfov, vfov                         */
+  double near_m, far_m;      /* sensor_min_range, nbvep/gain/range               */
+  double q_CB[4];            /* extrinsic T_C_B rotation, (w, x, y, z)           */
+  double t_CB[3];            /* extrinsic T_C_B translation                      */
+  double bbx_min[3], bbx_max[3]; /* exploration box, bbx/min*, bbx/max*          */
+  double gain_free, gain_occupied, gain_unmapped;
+  int32_t sum_all_yaws;      /* 0: optimized_gain (best yaw window); 1: gain() (sum of all yaws, yaw = 0) */
+  int32_t reserved;
+} nbvgpu_camera;
+
+/* Counters since context creation (metrics row). */
+typedef struct {
+  uint64_t rays;             /* rays cast by gain kernels                         */
+  uint64_t voxel_steps;      /* executed voxel-steps of gain kernels              */
+  uint64_t collision_steps;  /* executed voxel-steps of collision kernels         */
+  uint64_t blocks_uploaded;  /* blocks written by layer updates                   */
+  uint64_t bytes_uploaded;   /* payload + key bytes copied host->device           */
+  uint64_t kernel_launches;  /* kernels launched by this library                  */
+} nbvgpu_stats;
+
+/* Best-node record of nbvgpu_gain_eval_best* (rrt.cpp:220-246). */
+typedef struct {
+  int64_t index;             /* candidate index, -1 if no score > zero_gain       */
+  double score;              /* Node::gain_ = num_unmapped / time_to_reach        */
+  double gain;               /* Node::num_unmapped_ (return value of optimized_gain) */
+  double yaw;                /* state[3], radians                                 */
+} nbvgpu_best;
+
+/* ---- context ---------------------------------------------------------------------------- */
+int nbvgpu_create(int device, nbvgpu_ctx** out);
+void nbvgpu_destroy(nbvgpu_ctx* ctx);
+/* Use the caller's cudaStream_t (passed as void*) for all subsequent work; NULL restores the
+ * library-owned stream. */
+int nbvgpu_set_stream(nbvgpu_ctx* ctx, void* cuda_stream);
+int nbvgpu_synchronize(nbvgpu_ctx* ctx);
+const char* nbvgpu_last_error(nbvgpu_ctx* ctx);
+const char* nbvgpu_version(void);
+
+/* ---- map mirror: voxblox::Layer<TsdfVoxel|EsdfVoxel> (core/layer.h) ---------------------- */
+/* Layer(voxel_size, voxels_per_side) (layer.h:34-44).  max_blocks sizes the tile pool and the
+ * open-addressing table (capacity = next pow2 >= 2 * max_blocks). */
+int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int voxels_per_side,
+                        size_t max_blocks, int* layer_out);
+/* Insert-or-overwrite n blocks (the blocks Layer::getAllUpdatedBlocks(Update::kMap) returns,
+ * layer.h:194-203).  Host buffers are copied before the call returns; the update becomes visible
+ * to evaluations at the next nbvgpu_commit. keys = BlockIndex[n] (int32 x 3). */
+int nbvgpu_layer_update(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32_t* keys,
+                        const void* payload, int packing);
+/* Same with device buffers (keys must be unique within the call); applied in stream order. */
+int nbvgpu_layer_update_device(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32_t* d_keys,
+                               const void* d_payload, int packing);
+/* Layer::removeBlock (layer.h:171-173) / removeAllBlocks (:175). */
+int nbvgpu_layer_remove(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32_t* keys);
+int nbvgpu_layer_clear(nbvgpu_ctx* ctx, int layer);
+/* Publish staged updates/removals to the device snapshot (one H2D copy + scatter kernels). */
+int nbvgpu_commit(nbvgpu_ctx* ctx);
+/* Layer::getNumberOfAllocatedBlocks (layer.h:205). */
+int nbvgpu_layer_num_blocks(nbvgpu_ctx* ctx, int layer, size_t* out);
+/* Layer::getVoxelPtrByGlobalIndex (layer.h:215-239) for n global voxel indices (int64 x 3):
+ * out_values[n][2] = (distance, weight) (ESDF: weight slot = 0); out_found[n] = 1 if the block is
+ * allocated; out_status[n] (may be NULL) = 0 unknown / 1 free / 2 occupied per
+ * getVoxelStatusByIndex (TSDF only). */
+int nbvgpu_layer_read_voxels(nbvgpu_ctx* ctx, int layer, size_t n, const int64_t* global_index,
+                             float* out_values, uint8_t* out_found, uint8_t* out_status);
+
+/* ---- gain evaluator --------------------------------------------------------------------- */
+int nbvgpu_set_camera(nbvgpu_ctx* ctx, const nbvgpu_camera* cam);
+/* Batched optimized_gain()/gain(): pos[n][3] = state[0..2].  Outputs (any may be NULL except gain):
+ * gain[n] = return value; yaw_deg[n] = state[3] in integer degrees (-180..175; 0 for gain());
+ * counts[n][3] = unknown/free/occupied voxel counts over the winning yaw window (all yaws for
+ * gain()); per_yaw_counts[n][360][3] = the per-yaw counts behind vertical_gain[] (rrt.cpp:447);
+ * steps[n] = executed voxel-steps. */
+int nbvgpu_gain_eval(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, const double* pos, double* gain,
+                     int32_t* yaw_deg, uint64_t* counts, uint32_t* per_yaw_counts, uint64_t* steps);
+int nbvgpu_gain_eval_device(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, const double* d_pos,
+                            double* d_gain, int32_t* d_yaw_deg, uint64_t* d_counts,
+                            uint32_t* d_per_yaw_counts, uint64_t* d_steps);
+/* n = 1 shim with the reference's signature semantics: state[3] is overwritten with the yaw in
+ * radians (max_gain_yaw * M_PI / 180), the gain is stored in *gain_out. */
+int nbvgpu_optimized_gain(nbvgpu_ctx* ctx, int tsdf_layer, double state[4], double* gain_out);
+
+/* Batched evaluation + node scoring (rrt.cpp:220-246): score = gain / max(dyaw / dyaw_max,
+ * distance / v_max) with dyaw = yaw - parent_yaw wrapped once into (-pi, pi] (not abs'd, as in the
+ * reference); best = first candidate with score > running best starting at zero_gain.
+ * edge_free (may be NULL) masks candidates whose edge failed checkMotion.
+ * gain / yaw_deg (may be NULL) receive the per-candidate results as in nbvgpu_gain_eval. */
+int nbvgpu_gain_eval_best(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, const double* pos,
+                          const double* parent_yaw, const double* distance, const uint8_t* edge_free,
+                          double v_max, double dyaw_max, double zero_gain, nbvgpu_best* best,
+                          double* gain, int32_t* yaw_deg);
+int nbvgpu_gain_eval_best_device(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, const double* d_pos,
+                                 const double* d_parent_yaw, const double* d_distance,
+                                 const uint8_t* d_edge_free, double v_max, double dyaw_max,
+                                 double zero_gain, nbvgpu_best* d_best, double* d_gain,
+                                 int32_t* d_yaw_deg);
+
+/* ---- segment collision check ------------------------------------------------------------ */
+/* Batched HighResManager::checkMotion: seg[n][6] = (start xyz, end xyz); is_free[n] = 1 when every
+ * traversed voxel is allocated and robot_radius < distance. */
+int nbvgpu_check_segments(nbvgpu_ctx* ctx, int esdf_layer, double robot_radius, size_t n,
+                          const double* seg, uint8_t* is_free);
+int nbvgpu_check_segments_device(nbvgpu_ctx* ctx, int esdf_layer, double robot_radius, size_t n,
+                                 const double* d_seg, uint8_t* d_is_free);
+/* n = 1 shim: *free_out = checkMotion(start, end). */
+int nbvgpu_check_motion(nbvgpu_ctx* ctx, int esdf_layer, double robot_radius, const double start[3],
+                        const double end[3], int* free_out);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+int nbvgpu_get_stats(nbvgpu_ctx* ctx, nbvgpu_stats* out);
+/* Selects the gain kernel variant (0 = default/fastest, 1 = plain exact FP64 frustum test with
+ * {distance,weight} tile loads); both produce identical counts.  For A/B measurement only. */
+int nbvgpu_set_kernel_variant(nbvgpu_ctx* ctx, int variant);
+/* Number of single-precision frustum-classifier decisions contradicted by the exact FP64 plane test,
+ * counted by kernel variant 2 (0 = default, 1 = FP64 planes on every step + {distance,weight} loads,
+ * 2 = variant 0 with every classifier decision cross-checked, 3 = classifier + {distance,weight}
+ * loads).  Must be 0; the tests assert it. */
+int nbvgpu_debug_classifier_mismatches(nbvgpu_ctx* ctx, uint64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NBVGPU_H_ */

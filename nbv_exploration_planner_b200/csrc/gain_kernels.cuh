@@ -1,0 +1,580 @@
+// gain_kernels.cuh -- sm_100a kernels for the viewpoint-gain evaluator and its satellites.
+//
+//   k_gain<VARIANT>    RrtTree::optimized_gain / gain ray sweep   nbveplanner/src/rrt.cpp:351-447, 481-571
+//                      + CameraModel planes / in-view test        nbveplanner/src/camera_model.cpp:5-23,98-164,191-201
+//                      + voxblox RayCaster                        voxblox/src/integrator/integrator_utils.cc:111-179
+//                      + getVoxelStatusByIndex                    nbveplanner/src/voxblox_manager.cpp:14-33
+//   k_best_yaw         best-yaw window scan                       nbveplanner/src/rrt.cpp:449-478
+//   k_score_best       node scoring / best node                   nbveplanner/src/rrt.cpp:220-246
+//   k_check_segments   HighResManager::checkMotion                nbveplanner/include/nbveplanner/voxblox_manager.h:89-108
+//
+// Work decomposition of k_gain: one CTA per (candidate position, chunk of `yc` consecutive
+// yaws).  The CTA prologue (a) probes the block hash once for every block the candidate can
+// reach and stores the tile slots in a dense shared-memory grid, so the ray walk never hashes,
+// and (b) builds, one thread per yaw, the six frustum planes and the ray column frame in FP64
+// with the reference's operation order (no FMA: __dmul_rn/__dadd_rn).  Rays are then walked one
+// per lane; the 32 lanes of a warp take 32 consecutive yaws of the same ray row u, i.e. rays one
+// degree apart that stay within a voxel or two of each other: near-identical trip counts (little
+// divergence) and loads that fall into the same sectors.  Per-yaw counts are accumulated with
+// shared-memory atomics and written once per CTA.
+//
+// Exactness: the DDA is a literal float transcription (IEEE division, inf/NaN semantics kept);
+// the exploration-box test is done on integer voxel thresholds (exactly equivalent, see
+// camera_host.cc); the six FP64 plane tests are preceded by a conservative single-precision
+// classifier in the camera frame that decides "surely inside" / "surely outside" with a margin
+// far above its rounding error and otherwise falls back to the exact FP64 planes.  All variants
+// therefore produce identical counts; VARIANT only selects how:
+//   0  fp32 classifier + 2-bit status tiles (default)
+//   1  FP64 plane tests on every step + {distance, weight} tile loads (plain transcription)
+//   2  variant 0 + cross-check of every classifier decision against the FP64 planes
+//      (mismatch counter must stay 0; used by the tests)
+//   3  fp32 classifier + {distance, weight} tile loads
+#ifndef NBVGPU_GAIN_KERNELS_CUH_
+#define NBVGPU_GAIN_KERNELS_CUH_
+
+#include "map_mirror.cuh"
+
+namespace nbvgpu {
+
+constexpr int kGainThreads = 256;
+constexpr int kMaxReachVox = 4096;
+
+struct FilterConst {
+  float R[9];  // camera <- body rotation (row major)
+  float t[3];  // t_CB
+  float th, tv, nearp, farp;
+  float m, mh, mv;  // margins (plain, scaled for the horizontal / vertical side planes)
+};
+
+struct GainArgs {
+  LayerView L;
+  const double* A;    // [360][24]
+  const double* B;    // [360][3]
+  const float* cs;    // [360][2]
+  const double* pos;  // [n][3]
+  uint32_t* per_yaw;  // [n][360][3]
+  unsigned long long* steps;   // [n] or null
+  unsigned long long* totals;  // [0] rays [1] voxel steps [3] classifier mismatches
+  double vs, vs_inv;
+  float vs_f;
+  int gmin[3];
+  unsigned gspan[3];
+  int reach_vox;
+  int gnx, gny, gnz;  // local block grid dimensions
+  int yc;             // yaws per CTA (divides 360)
+  int n;
+  FilterConst F;
+};
+
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+struct D3 {
+  double x, y, z;
+};
+__device__ __forceinline__ D3 d3sub(const D3& a, const D3& b) { return {dsub(a.x, b.x), dsub(a.y, b.y), dsub(a.z, b.z)}; }
+__device__ __forceinline__ D3 d3add(const D3& a, const D3& b) { return {dadd(a.x, b.x), dadd(a.y, b.y), dadd(a.z, b.z)}; }
+// Eigen 3-vector dot on SSE2: (x0*y0 + x1*y1) + x2*y2.
+__device__ __forceinline__ double d3dot(const D3& a, const D3& b) {
+  return dadd(dadd(dmul(a.x, b.x), dmul(a.y, b.y)), dmul(a.z, b.z));
+}
+__device__ __forceinline__ D3 d3cross(const D3& a, const D3& b) {
+  return {dsub(dmul(a.y, b.z), dmul(a.z, b.y)), dsub(dmul(a.z, b.x), dmul(a.x, b.z)),
+          dsub(dmul(a.x, b.y), dmul(a.y, b.x))};
+}
+__device__ __forceinline__ D3 d3normalized(const D3& a) {
+  const double z = d3dot(a, a);
+  if (z > 0.0) {
+    const double n = __dsqrt_rn(z);
+    return {__ddiv_rn(a.x, n), __ddiv_rn(a.y, n), __ddiv_rn(a.z, n)};
+  }
+  return a;
+}
+
+// Shared-memory carve-up (dynamic): doubles first, then 4-byte arrays.
+struct GainSmem {
+  double* pl;     // [24][yc]  plane k component c at pl[(4k+c)*yc + j]
+  double* rd;     // [9][yc]   pp1 (3), u_slope (3), v_center (3)
+  float* st;      // [3][yc]   scaled ray start
+  float* csf;     // [2][yc]
+  int* um;        // [yc]
+  unsigned* cnt;  // [3][yc]
+  int* grid;      // [gnz][gny][gnx]
+};
+__device__ __forceinline__ GainSmem carve(unsigned char* base, int yc) {
+  GainSmem s;
+  s.pl = reinterpret_cast<double*>(base);
+  s.rd = s.pl + 24 * yc;
+  s.st = reinterpret_cast<float*>(s.rd + 9 * yc);
+  s.csf = s.st + 3 * yc;
+  s.um = reinterpret_cast<int*>(s.csf + 2 * yc);
+  s.cnt = reinterpret_cast<unsigned*>(s.um + yc);
+  s.grid = reinterpret_cast<int*>(s.cnt + 3 * yc);
+  return s;
+}
+inline size_t gain_smem_bytes(int yc, int gn) { return (size_t)yc * (33 * 8 + 9 * 4) + (size_t)gn * 4 + 16; }
+
+// Plane::setFromPoints + store (camera_model.cpp:5-11).
+__device__ __forceinline__ void store_plane(double* pl, int yc, int j, int k, const D3& p1, const D3& p2, const D3& p3) {
+  const D3 n = d3normalized(d3cross(d3sub(p2, p1), d3sub(p3, p1)));
+  pl[(4 * k + 0) * yc + j] = n.x;
+  pl[(4 * k + 1) * yc + j] = n.y;
+  pl[(4 * k + 2) * yc + j] = n.z;
+  pl[(4 * k + 3) * yc + j] = d3dot(n, p1);
+}
+
+// CameraModel::isPointInView plane part (camera_model.cpp:194-199) on P = (double)g * vs.
+__device__ __forceinline__ bool exact_in_frustum(const double* pl, int yc, int j, int gx, int gy, int gz, double vs) {
+  const double px = dmul((double)gx, vs), py = dmul((double)gy, vs), pz = dmul((double)gz, vs);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double nx = pl[(4 * k + 0) * yc + j], ny = pl[(4 * k + 1) * yc + j], nz = pl[(4 * k + 2) * yc + j];
+    const double d = pl[(4 * k + 3) * yc + j];
+    if (!(dadd(dadd(dmul(px, nx), dmul(py, ny)), dmul(pz, nz)) >= d)) return false;
+  }
+  return true;
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kGainThreads) k_gain(const GainArgs a) {
+  constexpr bool kFilter = (VARIANT != 1);
+  constexpr bool kStatusBits = (VARIANT == 0 || VARIANT == 2);
+  constexpr bool kParanoid = (VARIANT == 2);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int yc = a.yc;
+  const GainSmem S = carve(smem_raw, yc);
+  __shared__ int s_umax;
+  __shared__ unsigned long long s_steps;
+  __shared__ unsigned int s_mismatch;
+  __shared__ int s_bad;
+
+  const int chunks = 360 / yc;
+  const int v = blockIdx.x / chunks;
+  const int chunk = blockIdx.x - v * chunks;
+  const int tid = threadIdx.x;
+  const int lv = a.L.log2vps;
+  const int vm = (1 << lv) - 1;
+
+  const double px = a.pos[3 * v], py = a.pos[3 * v + 1], pz = a.pos[3 * v + 2];
+  // Guard (the host entry points validate; device-resident inputs are caught here).
+  const double lim = 4194304.0 - (double)a.reach_vox - 2.0;
+  const bool bad = !(fabs(px * a.vs_inv) < lim) || !(fabs(py * a.vs_inv) < lim) || !(fabs(pz * a.vs_inv) < lim);
+  if (tid == 0) {
+    s_umax = 0;
+    s_steps = 0ull;
+    s_mismatch = 0u;
+    s_bad = bad ? 1 : 0;
+  }
+  if (bad) {
+    for (int j = tid; j < yc; j += blockDim.x)
+      for (int k = 0; k < 3; ++k) a.per_yaw[((size_t)v * 360 + chunk * yc + j) * 3 + k] = 0u;
+    return;
+  }
+  // Voxel containing the candidate position and the origin of the local block grid.
+  const int g0x = (int)floor(px * a.vs_inv), g0y = (int)floor(py * a.vs_inv), g0z = (int)floor(pz * a.vs_inv);
+  const int b0x = (g0x - a.reach_vox) >> lv, b0y = (g0y - a.reach_vox) >> lv, b0z = (g0z - a.reach_vox) >> lv;
+
+  // (a) local block-slot grid: one hash probe per reachable block.
+  const int gn = a.gnx * a.gny * a.gnz;
+  for (int i = tid; i < gn; i += blockDim.x) {
+    const int ix = i % a.gnx, iy = (i / a.gnx) % a.gny, iz = i / (a.gnx * a.gny);
+    S.grid[i] = probe_block(a.L, b0x + ix, b0y + iy, b0z + iz);
+  }
+  // (b) per-yaw frames (rrt.cpp:369-385, camera_model.cpp:87-94,119-160,280-289).
+  for (int j = tid; j < yc; j += blockDim.x) {
+    const int y = chunk * yc + j;
+    const double* A = a.A + (size_t)y * 24;
+    const D3 p{px, py, pz};
+    const D3 t = d3add(p, D3{a.B[3 * y], a.B[3 * y + 1], a.B[3 * y + 2]});  // camera position
+    D3 c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) c[k] = d3add(D3{A[3 * k], A[3 * k + 1], A[3 * k + 2]}, t);
+    store_plane(S.pl, yc, j, 0, c[0], c[2], c[1]);  // near
+    store_plane(S.pl, yc, j, 1, c[4], c[5], c[6]);  // far
+    store_plane(S.pl, yc, j, 2, c[3], c[6], c[2]);  // left
+    store_plane(S.pl, yc, j, 3, c[0], c[5], c[4]);  // right
+    store_plane(S.pl, yc, j, 4, c[3], c[4], c[7]);  // top
+    store_plane(S.pl, yc, j, 5, c[2], c[6], c[5]);  // bottom
+    const D3 ud = d3sub(c[4], c[5]);                 // rrt.cpp:382
+    const D3 us = d3normalized(ud);                  // :383
+    const int um = (int)ceil(dmul(__dsqrt_rn(d3dot(ud, ud)), a.vs_inv));  // :384
+    const D3 d21 = d3sub(c[6], c[5]);
+    const D3 vc{__ddiv_rn(d21.x, 2.0), __ddiv_rn(d21.y, 2.0), __ddiv_rn(d21.z, 2.0)};  // :385
+    S.rd[0 * yc + j] = c[5].x; S.rd[1 * yc + j] = c[5].y; S.rd[2 * yc + j] = c[5].z;
+    S.rd[3 * yc + j] = us.x;   S.rd[4 * yc + j] = us.y;   S.rd[5 * yc + j] = us.z;
+    S.rd[6 * yc + j] = vc.x;   S.rd[7 * yc + j] = vc.y;   S.rd[8 * yc + j] = vc.z;
+    S.st[0 * yc + j] = __double2float_rn(dmul(t.x, a.vs_inv));  // :408-409
+    S.st[1 * yc + j] = __double2float_rn(dmul(t.y, a.vs_inv));
+    S.st[2 * yc + j] = __double2float_rn(dmul(t.z, a.vs_inv));
+    S.csf[0 * yc + j] = a.cs[2 * y];
+    S.csf[1 * yc + j] = a.cs[2 * y + 1];
+    S.um[j] = um;
+    S.cnt[0 * yc + j] = 0u; S.cnt[1 * yc + j] = 0u; S.cnt[2 * yc + j] = 0u;
+  }
+  __syncthreads();
+  for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
+  __syncthreads();
+  const int umax = s_umax;
+  const int n_rays = umax * yc;
+
+  // Offset of the candidate inside its voxel (classifier works relative to g0).
+  const float noffx = -__double2float_rn(px - (double)g0x * a.vs);
+  const float noffy = -__double2float_rn(py - (double)g0y * a.vs);
+  const float noffz = -__double2float_rn(pz - (double)g0z * a.vs);
+  const FilterConst& F = a.F;
+
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  unsigned long long my_steps = 0ull;
+  unsigned int my_mismatch = 0u;
+
+  for (int base = warp * 32; base < n_rays; base += nwarps * 32) {
+    const int r = base + lane;
+    const int u = r / yc;
+    const int j = r - u * yc;
+    if (r >= n_rays || u >= S.um[j]) continue;
+
+    // ---- ray end point (rrt.cpp:396,410-411) and RayCaster setup (integrator_utils.cc:127-179)
+    float s[3], e[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      s[k] = S.st[k * yc + j];
+      const double pos = dadd(dadd(S.rd[k * yc + j], dmul(dmul((double)u, S.rd[(3 + k) * yc + j]), a.vs)), S.rd[(6 + k) * yc + j]);
+      e[k] = __double2float_rn(dmul(pos, a.vs_inv));
+    }
+    int g[3], sg[3];
+    float t[3], dt[3];
+    int len = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      g[k] = (int)floorf(__fadd_rn(s[k], 1e-6f));
+      const int ei = (int)floorf(__fadd_rn(e[k], 1e-6f));
+      len += abs(ei - g[k]);
+      const float rr = __fsub_rn(e[k], s[k]);
+      sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
+      const float shifted = __fsub_rn(s[k], (float)g[k]);
+      const float dist = __fsub_rn((float)max(0, sg[k]), shifted);
+      t[k] = __fdiv_rn(dist, rr);           // +-inf / NaN when rr == 0, as in the reference
+      dt[k] = __fdiv_rn((float)sg[k], rr);
+    }
+    float fd[3] = {(float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z)};
+    const float fs[3] = {(float)sg[0], (float)sg[1], (float)sg[2]};
+    const float cy = S.csf[j], sy = S.csf[yc + j];
+
+    unsigned nu = 0, nf = 0, no = 0;
+    int cbx = INT_MIN, cby = 0, cbz = 0, cslot = -1;
+    int step = 0;
+    for (; step <= len; ++step) {
+      // ---- in-view test (camera_model.cpp:191-201) on the voxel corner g * vs
+      bool inview = (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+                    (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
+      if (inview) {
+        if (kFilter) {
+          const float rx = fmaf(fd[0], a.vs_f, noffx), ry = fmaf(fd[1], a.vs_f, noffy), rz = fmaf(fd[2], a.vs_f, noffz);
+          const float x1 = fmaf(sy, ry, cy * rx);
+          const float y1 = fmaf(cy, ry, -(sy * rx));
+          const float xc = fmaf(F.R[0], x1, fmaf(F.R[1], y1, fmaf(F.R[2], rz, F.t[0])));
+          const float yk = fmaf(F.R[3], x1, fmaf(F.R[4], y1, fmaf(F.R[5], rz, F.t[1])));
+          const float zk = fmaf(F.R[6], x1, fmaf(F.R[7], y1, fmaf(F.R[8], rz, F.t[2])));
+          const float s0 = xc - F.nearp, s1 = F.farp - xc;
+          const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
+          const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
+          const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
+          if (kParanoid) {
+            const bool ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+            if ((sure_in && !ex) || (sure_out && ex)) ++my_mismatch;
+            inview = ex;
+          } else if (sure_in) {
+            inview = true;
+          } else if (sure_out) {
+            inview = false;
+          } else {
+            inview = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+          }
+        } else {
+          inview = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+        }
+      }
+      if (inview) {
+        // ---- voxel status (voxblox_manager.cpp:14-33) through the shared-memory slot grid
+        const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
+        if (bx != cbx || by != cby || bz != cbz) {
+          cbx = bx; cby = by; cbz = bz;
+          const int ix = bx - b0x, iy = by - b0y, iz = bz - b0z;
+          if ((unsigned)ix < (unsigned)a.gnx && (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz)
+            cslot = S.grid[(iz * a.gny + iy) * a.gnx + ix];
+          else
+            cslot = probe_block(a.L, bx, by, bz);
+        }
+        unsigned status = 0u;
+        if (cslot >= 0) {
+          const int lin = (g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv));
+          if (kStatusBits) {
+            const uint32_t w = __ldg(a.L.status + (size_t)cslot * (a.L.nvox >> 4) + (lin >> 4));
+            status = (w >> ((lin & 15) * 2)) & 3u;
+          } else {
+            const float2 vx = __ldg(reinterpret_cast<const float2*>(a.L.tiles) + (size_t)cslot * a.L.nvox + lin);
+            status = tsdf_status(vx.x, vx.y);
+          }
+        }
+        if (status == 0u) {
+          ++nu;
+        } else if (status == 2u) {
+          ++no;
+          ++step;  // this step was executed
+          break;
+        } else {
+          ++nf;
+        }
+      }
+      // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
+      const bool c1 = t[1] < t[0];
+      const float bm = c1 ? t[1] : t[0];
+      const bool c2 = t[2] < bm;
+      if (c2) {
+        g[2] += sg[2]; t[2] = __fadd_rn(t[2], dt[2]); fd[2] += fs[2];
+      } else if (c1) {
+        g[1] += sg[1]; t[1] = __fadd_rn(t[1], dt[1]); fd[1] += fs[1];
+      } else {
+        g[0] += sg[0]; t[0] = __fadd_rn(t[0], dt[0]); fd[0] += fs[0];
+      }
+    }
+    my_steps += (unsigned long long)step;
+    if (nu) atomicAdd(&S.cnt[0 * yc + j], nu);
+    if (nf) atomicAdd(&S.cnt[1 * yc + j], nf);
+    if (no) atomicAdd(&S.cnt[2 * yc + j], no);
+  }
+  // ---- CTA epilogue
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    my_mismatch += __shfl_xor_sync(0xffffffffu, my_mismatch, o);
+  }
+  if (lane == 0) {
+    atomicAdd(&s_steps, my_steps);
+    if (kParanoid) atomicAdd(&s_mismatch, my_mismatch);
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * yc; i += blockDim.x) {
+    const int k = i / yc, j = i - k * yc;
+    a.per_yaw[((size_t)v * 360 + chunk * yc + j) * 3 + k] = S.cnt[k * yc + j];
+  }
+  if (tid == 0) {
+    unsigned long long rays = 0ull;
+    for (int j = 0; j < yc; ++j) rays += (unsigned long long)S.um[j];
+    if (a.steps) atomicAdd(a.steps + v, s_steps);
+    atomicAdd(a.totals + 0, rays);
+    atomicAdd(a.totals + 1, s_steps);
+    if (kParanoid && s_mismatch) atomicAdd(a.totals + 3, (unsigned long long)s_mismatch);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Best yaw (rrt.cpp:449-478) / all-yaw sum (rrt.cpp:571-578).  One warp per candidate.
+// ---------------------------------------------------------------------------------------------
+struct BestYawArgs {
+  const uint32_t* per_yaw;  // [n][360][3]
+  double* gain;             // [n]
+  int32_t* yaw_deg;         // [n] or null
+  unsigned long long* counts;  // [n][3] or null
+  double g_unmapped, g_free, g_occupied;
+  double cube;
+  int half_hfov;
+  int sum_all;
+  int n;
+};
+
+__global__ void __launch_bounds__(128) k_best_yaw(const BestYawArgs a) {
+  __shared__ double vg_all[4][360];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x * 4 + warp;
+  if (v >= a.n) return;
+  double* vg = vg_all[warp];
+  const uint32_t* c = a.per_yaw + (size_t)v * 1080;
+  unsigned long long tu = 0, tf = 0, to = 0;
+  for (int j = lane; j < 360; j += 32) {
+    const uint32_t nu = c[3 * j], nf = c[3 * j + 1], no = c[3 * j + 2];
+    // vertical_gain[j]: the running sum of rrt.cpp:436-443 in count form.
+    vg[j] = dadd(dadd(dmul((double)nu, a.g_unmapped), dmul((double)no, a.g_occupied)), dmul((double)nf, a.g_free));
+    tu += nu; tf += nf; to += no;
+  }
+  __syncwarp();
+  if (a.sum_all) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tu += __shfl_xor_sync(0xffffffffu, tu, o);
+      tf += __shfl_xor_sync(0xffffffffu, tf, o);
+      to += __shfl_xor_sync(0xffffffffu, to, o);
+    }
+    if (lane == 0) {
+      const double g = dadd(dadd(dmul((double)tu, a.g_unmapped), dmul((double)to, a.g_occupied)), dmul((double)tf, a.g_free));
+      a.gain[v] = dmul(g, a.cube);
+      if (a.yaw_deg) a.yaw_deg[v] = 0;
+      if (a.counts) { a.counts[3 * v] = tu; a.counts[3 * v + 1] = tf; a.counts[3 * v + 2] = to; }
+    }
+    return;
+  }
+  // 72 window centres, 5 degrees apart; each lane sums its windows in the reference's order.
+  double best = 0.0;
+  int best_c = 1 << 20;  // candidate ordinal; "none" sorts last
+  for (int cidx = lane; cidx < 72; cidx += 32) {
+    const int i = -180 + 5 * cidx;
+    double cur = 0.0;
+    int left = (i + 180) - a.half_hfov;
+    if (left < 0) {
+      for (int j = 360 + left; j < 360; ++j) cur = dadd(cur, vg[j]);
+      left = 0;
+    }
+    int right = (i + 180) + a.half_hfov;
+    if (right >= 360) {
+      for (int j = 0; j < right - 359; ++j) cur = dadd(cur, vg[j]);
+      right = 359;
+    }
+    for (int j = left; j <= right; ++j) cur = dadd(cur, vg[j]);
+    if (cur > best) { best = cur; best_c = cidx; }  // strict: first maximum of this lane
+  }
+  // Warp arg-max, ties -> lowest ordinal (= first strict maximum of the sequential scan).
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+  }
+  const int yaw = (best_c < 72) ? (-180 + 5 * best_c) : 0;  // max_gain_yaw starts at 0 (rrt.cpp:450)
+  if (a.counts) {
+    unsigned long long wu = 0, wf = 0, wo = 0;
+    for (int d = -a.half_hfov + lane; d <= a.half_hfov; d += 32) {
+      const int j = (((yaw + 180 + d) % 360) + 360) % 360;
+      wu += c[3 * j]; wf += c[3 * j + 1]; wo += c[3 * j + 2];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wu += __shfl_xor_sync(0xffffffffu, wu, o);
+      wf += __shfl_xor_sync(0xffffffffu, wf, o);
+      wo += __shfl_xor_sync(0xffffffffu, wo, o);
+    }
+    if (lane == 0) { a.counts[3 * v] = wu; a.counts[3 * v + 1] = wf; a.counts[3 * v + 2] = wo; }
+  }
+  if (lane == 0) {
+    a.gain[v] = dmul(best, a.cube);  // rrt.cpp:478
+    if (a.yaw_deg) a.yaw_deg[v] = yaw;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Node scoring (rrt.cpp:220-246): single CTA arg-max with first-strict-maximum semantics.
+// ---------------------------------------------------------------------------------------------
+struct BestRecord {
+  long long index;
+  double score, gain, yaw;
+};
+
+__global__ void __launch_bounds__(1024) k_score_best(const double* __restrict__ gain, const int32_t* __restrict__ yaw_deg,
+                                                     const double* __restrict__ parent_yaw, const double* __restrict__ distance,
+                                                     const uint8_t* __restrict__ edge_free, int n, double v_max, double dyaw_max,
+                                                     double zero_gain, BestRecord* out) {
+  __shared__ double s_score[32];
+  __shared__ int s_idx[32];
+  double best = zero_gain;
+  int best_i = INT_MAX;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    if (edge_free && !edge_free[i]) continue;
+    const double yaw = __ddiv_rn(dmul((double)yaw_deg[i], 3.14159265358979323846), 180.0);  // rrt.cpp:477
+    double dy = dsub(yaw, parent_yaw[i]);                                                   // :225
+    if (dy > 3.14159265358979323846) dy = dsub(dy, dmul(2.0, 3.14159265358979323846));
+    if (dy < -3.14159265358979323846) dy = dadd(dy, dmul(2.0, 3.14159265358979323846));
+    const double ta = __ddiv_rn(dy, dyaw_max), tb = __ddiv_rn(distance[i], v_max);
+    const double time = (ta < tb) ? tb : ta;          // std::max (:232-233)
+    const double score = __ddiv_rn(gain[i], time);    // :234
+    if (score > best) { best = score; best_i = i; }   // ascending i per thread: first strict max
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  if (lane == 0) { s_score[warp] = best; s_idx[warp] = best_i; }
+  __syncthreads();
+  if (warp == 0) {
+    const int nw = blockDim.x >> 5;
+    best = lane < nw ? s_score[lane] : zero_gain;
+    best_i = lane < nw ? s_idx[lane] : INT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+      if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+    }
+    if (lane == 0) {
+      if (best_i == INT_MAX) {
+        out->index = -1; out->score = zero_gain; out->gain = 0.0; out->yaw = 0.0;
+      } else {
+        out->index = best_i; out->score = best; out->gain = gain[best_i];
+        out->yaw = __ddiv_rn(dmul((double)yaw_deg[best_i], 3.14159265358979323846), 180.0);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// HighResManager::checkMotion (voxblox_manager.h:89-108).  One thread per segment.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_check_segments(LayerView L, float voxel_size, double radius,
+                                                        const double* __restrict__ seg, int n, uint8_t* is_free,
+                                                        unsigned long long* totals) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long steps = 0ull;
+  if (i < n) {
+    const int lv = L.log2vps, vm = (1 << lv) - 1;
+    int g[3], sg[3];
+    float t[3], dt[3];
+    int len = 0;
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float s = __fdiv_rn(__double2float_rn(seg[6 * i + k]), voxel_size);      // :96-98 float division
+      const float e = __fdiv_rn(__double2float_rn(seg[6 * i + 3 + k]), voxel_size);
+      if (!(fabsf(s) < 4194304.0f) || !(fabsf(e) < 4194304.0f)) ok = false;          // non-finite / out of range
+      g[k] = (int)floorf(__fadd_rn(s, 1e-6f));
+      const int ei = (int)floorf(__fadd_rn(e, 1e-6f));
+      len += abs(ei - g[k]);
+      const float rr = __fsub_rn(e, s);
+      sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
+      const float shifted = __fsub_rn(s, (float)g[k]);
+      const float dist = __fsub_rn((float)max(0, sg[k]), shifted);
+      t[k] = __fdiv_rn(dist, rr);
+      dt[k] = __fdiv_rn((float)sg[k], rr);
+    }
+    bool free_seg = ok;
+    if (ok) {
+      int cbx = INT_MIN, cby = 0, cbz = 0, cslot = -1;
+      for (int step = 0; step <= len; ++step) {
+        ++steps;
+        const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
+        if (bx != cbx || by != cby || bz != cbz) {
+          cbx = bx; cby = by; cbz = bz;
+          cslot = probe_block(L, bx, by, bz);
+        }
+        if (cslot < 0) { free_seg = false; break; }  // voxel == nullptr -> collision (voxblox_manager.cpp:125-127)
+        const int lin = (g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv));
+        const float d = __ldg(reinterpret_cast<const float*>(L.tiles) + (size_t)cslot * L.nvox + lin);
+        if (radius >= (double)d) { free_seg = false; break; }  // :128
+        const bool c1 = t[1] < t[0];
+        const float bm = c1 ? t[1] : t[0];
+        const bool c2 = t[2] < bm;
+        if (c2) { g[2] += sg[2]; t[2] = __fadd_rn(t[2], dt[2]); }
+        else if (c1) { g[1] += sg[1]; t[1] = __fadd_rn(t[1], dt[1]); }
+        else { g[0] += sg[0]; t[0] = __fadd_rn(t[0], dt[0]); }
+      }
+    }
+    is_free[i] = free_seg ? 1 : 0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
+  if ((threadIdx.x & 31) == 0 && steps) atomicAdd(totals + 2, steps);
+}
+
+}  // namespace nbvgpu
+#endif

@@ -1,0 +1,901 @@
+// nbvgpu.cu -- implementation of the C ABI in include/nbvgpu.h (sm_100a).
+// Host side: context, layer bookkeeping, staging, launches.  Device side: map_mirror.cuh and
+// gain_kernels.cuh.  There is no CPU fallback anywhere in this file.
+#include "nbvgpu.h"
+
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "camera_host.h"
+#include "gain_kernels.cuh"
+#include "map_mirror.cuh"
+
+using namespace nbvgpu;
+
+namespace {
+
+struct DevBuf {  // grow-only device scratch
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {  // grow-only pinned host staging
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes, bool keep) {
+    if (bytes <= cap) return cudaSuccess;
+    size_t want = bytes + bytes / 2 + 4096;
+    void* q = nullptr;
+    cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocDefault);
+    if (e != cudaSuccess) return e;
+    if (p) {
+      if (keep) memcpy(q, p, cap);
+      cudaFreeHost(p);
+    }
+    p = q;
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct KeyH {
+  int32_t x, y, z;
+  bool operator==(const KeyH& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct KeyHHash {
+  size_t operator()(const KeyH& k) const { return (size_t)hash_key(k.x, k.y, k.z) ^ ((size_t)k.z << 32); }
+};
+
+struct LayerHost {
+  int kind = 0;
+  float voxel_size = 0.f;
+  int vps = 0, log2vps = 0, nvox = 0;
+  size_t max_blocks = 0;
+  uint32_t cap = 0, log2cap = 0;
+  HashEntry* d_table = nullptr;
+  void* d_tiles = nullptr;
+  uint32_t* d_status = nullptr;
+  int* d_free_list = nullptr;
+  int* d_free_top = nullptr;            // [0] free_top, [1] err
+  unsigned long long* d_nblocks = nullptr;
+  size_t n_blocks = 0;                  // as of the last commit
+  size_t tombstones = 0;
+  // staged (uncommitted) operations
+  PinBuf h_keys, h_payload;             // updates
+  int pending_packing = -1;
+  size_t pending = 0;
+  std::unordered_map<KeyH, size_t, KeyHHash> pending_index;
+  std::vector<int32_t> pending_remove;
+  DevBuf d_keys, d_payload, d_slots;
+  size_t payload_bytes_per_block(int packing) const {
+    if (kind == NBVGPU_LAYER_TSDF) return (size_t)nvox * (packing == NBVGPU_PACK_PLANAR ? 8 : 12);
+    return (size_t)nvox * (packing == NBVGPU_PACK_PLANAR ? 4 : 8);
+  }
+  LayerView view() const {
+    LayerView v;
+    v.table = d_table;
+    v.tiles = d_tiles;
+    v.status = d_status;
+    v.mask = cap - 1;
+    v.shift = 32 - log2cap;
+    v.log2vps = log2vps;
+    v.nvox = nvox;
+    return v;
+  }
+};
+
+}  // namespace
+
+struct nbvgpu_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  std::mutex mu;
+  std::string err;
+  std::vector<LayerHost*> layers;
+  bool cam_set = false;
+  nbvgpu_camera cam{};
+  nbvgpu_host::CameraTables tab{};
+  double* d_A = nullptr;
+  double* d_B = nullptr;
+  float* d_cs = nullptr;
+  unsigned long long* d_totals = nullptr;  // rays, voxel steps, collision steps, classifier mismatches
+  PinBuf h_io;                             // pinned staging for n-sized inputs / outputs
+  DevBuf d_pos, d_per_yaw, d_gain, d_yaw, d_counts, d_steps, d_seg, d_free, d_aux, d_best;
+  nbvgpu_stats stats{};
+  int variant = 0;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+};
+
+namespace {
+
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+      return NBVGPU_ERR_CUDA;                                                                      \
+    }                                                                                              \
+  } while (0)
+
+int fail(nbvgpu_ctx* ctx, int code, const char* msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int ilog2(uint64_t v) {
+  int l = 0;
+  while ((1ull << l) < v) ++l;
+  return l;
+}
+
+LayerHost* get_layer(nbvgpu_ctx* ctx, int layer, int kind) {
+  if (layer < 0 || layer >= (int)ctx->layers.size() || !ctx->layers[layer]) return nullptr;
+  if (kind >= 0 && ctx->layers[layer]->kind != kind) return nullptr;
+  return ctx->layers[layer];
+}
+
+void free_layer(LayerHost* L) {
+  if (!L) return;
+  cudaFree(L->d_table);
+  cudaFree(L->d_tiles);
+  cudaFree(L->d_status);
+  cudaFree(L->d_free_list);
+  cudaFree(L->d_free_top);
+  cudaFree(L->d_nblocks);
+  L->h_keys.release();
+  L->h_payload.release();
+  L->d_keys.release();
+  L->d_payload.release();
+  L->d_slots.release();
+  delete L;
+}
+
+// Apply n blocks whose keys / payload are already on the device (stream ordered).
+int apply_update_device(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const int32_t* d_keys, const void* d_payload, int packing) {
+  if (n == 0) return NBVGPU_OK;
+  CK(L->d_slots.reserve(n * sizeof(int)));
+  const int threads = 128;
+  k_insert_keys<<<(unsigned)((n + threads - 1) / threads), threads, 0, ctx->stream>>>(
+      L->d_table, L->cap - 1, 32 - L->log2cap, d_keys, (int)n, L->d_free_list, L->d_free_top, L->d_slots.as<int>(),
+      L->d_free_top + 1, L->d_nblocks);
+  ctx->stats.kernel_launches++;
+  if (L->kind == NBVGPU_LAYER_TSDF) {
+    const int per = L->nvox / 2;
+    const int tpb = per < 256 ? per : 256;
+    dim3 grid((per + tpb - 1) / tpb, (unsigned)n);
+    if (packing == NBVGPU_PACK_PLANAR)
+      k_scatter_tsdf<0><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float2*)L->d_tiles, L->d_status, L->nvox);
+    else
+      k_scatter_tsdf<1><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float2*)L->d_tiles, L->d_status, L->nvox);
+  } else {
+    const int per = L->nvox / 4;
+    const int tpb = per < 256 ? per : 256;
+    dim3 grid((per + tpb - 1) / tpb, (unsigned)n);
+    if (packing == NBVGPU_PACK_PLANAR)
+      k_scatter_esdf<0><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float*)L->d_tiles, L->nvox);
+    else
+      k_scatter_esdf<1><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float*)L->d_tiles, L->nvox);
+  }
+  ctx->stats.kernel_launches++;
+  ctx->stats.blocks_uploaded += n;
+  CK(cudaGetLastError());
+  return NBVGPU_OK;
+}
+
+// Read back {n_blocks, err} of a layer (synchronises the stream).
+int sync_layer_state(nbvgpu_ctx* ctx, LayerHost* L) {
+  CK(ctx->h_io.reserve(64, false));
+  unsigned long long* h = ctx->h_io.as<unsigned long long>();
+  CK(cudaMemcpyAsync(h, L->d_nblocks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h + 1, L->d_free_top, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  L->n_blocks = (size_t)h[0];
+  const int err = reinterpret_cast<int*>(h + 1)[1];
+  if (err) {
+    CK(cudaMemsetAsync(L->d_free_top + 1, 0, sizeof(int), ctx->stream));
+    return fail(ctx, NBVGPU_ERR_CAPACITY, (err & 1) ? "layer tile pool exhausted (max_blocks)" : "layer hash table full");
+  }
+  return NBVGPU_OK;
+}
+
+int rehash_if_needed(nbvgpu_ctx* ctx, LayerHost* L, size_t incoming) {
+  if (L->tombstones == 0 || (L->n_blocks + L->tombstones + incoming) * 4 < (size_t)L->cap * 3) return NBVGPU_OK;
+  HashEntry* fresh = nullptr;
+  CK(cudaMalloc(&fresh, (size_t)L->cap * sizeof(HashEntry)));
+  CK(cudaMemsetAsync(fresh, 0xFF, (size_t)L->cap * sizeof(HashEntry), ctx->stream));
+  k_rehash<<<(L->cap + 255) / 256, 256, 0, ctx->stream>>>(L->d_table, L->cap, fresh, L->cap - 1, 32 - L->log2cap);
+  ctx->stats.kernel_launches++;
+  CK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(L->d_table);
+  L->d_table = fresh;
+  L->tombstones = 0;
+  return NBVGPU_OK;
+}
+
+int check_position_range(const nbvgpu_ctx* ctx, const LayerHost* L, size_t n, const double* pos) {
+  const double vs_inv = 1.0 / (double)L->voxel_size;
+  const double reach = std::ceil(ctx->tab.reach_m * vs_inv) + 4.0;
+  const double lim = 4194304.0 - reach - 2.0;
+  for (size_t i = 0; i < 3 * n; ++i)
+    if (!(std::fabs(pos[i] * vs_inv) < lim)) return NBVGPU_ERR_RANGE;
+  return NBVGPU_OK;
+}
+
+template <int V>
+cudaError_t launch_gain(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(k_gain<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_gain<V><<<grid, kGainThreads, smem, s>>>(a);
+  return cudaGetLastError();
+}
+
+// Enqueue: ray sweep + best yaw for n resident positions.  d_per_yaw may be null (scratch used).
+int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, double* d_gain, int32_t* d_yaw_deg,
+                 uint64_t* d_counts, uint32_t* d_per_yaw, uint64_t* d_steps) {
+  if (n == 0) return NBVGPU_OK;
+  if (n > (size_t)INT_MAX / 1080) return fail(ctx, NBVGPU_ERR_INVALID, "too many candidates in one call");
+  if (!d_per_yaw) {
+    CK(ctx->d_per_yaw.reserve(n * 1080 * sizeof(uint32_t)));
+    d_per_yaw = ctx->d_per_yaw.as<uint32_t>();
+  }
+  if (d_steps) CK(cudaMemsetAsync(d_steps, 0, n * sizeof(uint64_t), ctx->stream));
+  GainArgs a;
+  a.L = L->view();
+  a.A = ctx->d_A;
+  a.B = ctx->d_B;
+  a.cs = ctx->d_cs;
+  a.pos = d_pos;
+  a.per_yaw = d_per_yaw;
+  a.steps = reinterpret_cast<unsigned long long*>(d_steps);
+  a.totals = ctx->d_totals;
+  a.vs = (double)L->voxel_size;  // rrt.cpp:352: float layer value widened
+  a.vs_inv = 1.0 / a.vs;
+  a.vs_f = L->voxel_size;
+  int gmin[3], gmax[3];
+  nbvgpu_host::box_thresholds(ctx->cam, a.vs, gmin, gmax);
+  for (int k = 0; k < 3; ++k) {
+    if (gmax[k] < gmin[k]) {
+      a.gmin[k] = 1 << 30;
+      a.gspan[k] = 0u;
+    } else {
+      a.gmin[k] = gmin[k];
+      a.gspan[k] = (unsigned)((long long)gmax[k] - (long long)gmin[k]);
+    }
+  }
+  const double reach = std::ceil(ctx->tab.reach_m * a.vs_inv) + 4.0;
+  if (!(reach < (double)kMaxReachVox)) return fail(ctx, NBVGPU_ERR_RANGE, "gain range / voxel size too large");
+  a.reach_vox = (int)reach;
+  int gdim = ((2 * a.reach_vox) >> L->log2vps) + 2;
+  // yaws per CTA: enough CTAs to fill the machine for small batches, bigger chunks otherwise.
+  static const int kYc[] = {40, 20, 10, 8, 4};
+  int yc = 40;
+  for (int c : kYc) {
+    yc = c;
+    if (n * (size_t)(360 / c) >= (size_t)ctx->sm_count * 6) break;
+  }
+  size_t gn = (size_t)gdim * gdim * gdim;
+  size_t smem = gain_smem_bytes(yc, (int)gn);
+  if (smem > (size_t)ctx->max_smem_optin || smem > 96 * 1024) {  // fall back to direct hash probes
+    gdim = 0;
+    gn = 0;
+    smem = gain_smem_bytes(yc, 0);
+  }
+  a.gnx = a.gny = a.gnz = gdim;
+  a.yc = yc;
+  a.n = (int)n;
+  const nbvgpu_host::CameraTables& T = ctx->tab;
+  for (int k = 0; k < 9; ++k) a.F.R[k] = T.R_CB[k];
+  for (int k = 0; k < 3; ++k) a.F.t[k] = T.t_CB[k];
+  a.F.th = T.th; a.F.tv = T.tv; a.F.nearp = T.near_f; a.F.farp = T.far_f;
+  a.F.m = T.margin; a.F.mh = T.margin_h; a.F.mv = T.margin_v;
+  int variant = ctx->variant;
+  if (!T.filter_ok) variant = 1;
+  const unsigned grid = (unsigned)(n * (size_t)(360 / yc));
+  cudaError_t e;
+  switch (variant) {
+    case 1: e = launch_gain<1>(a, smem, grid, ctx->stream); break;
+    case 2: e = launch_gain<2>(a, smem, grid, ctx->stream); break;
+    case 3: e = launch_gain<3>(a, smem, grid, ctx->stream); break;
+    default: e = launch_gain<0>(a, smem, grid, ctx->stream); break;
+  }
+  CK(e);
+  ctx->stats.kernel_launches++;
+  BestYawArgs b;
+  b.per_yaw = d_per_yaw;
+  b.gain = d_gain;
+  b.yaw_deg = d_yaw_deg;
+  b.counts = reinterpret_cast<unsigned long long*>(d_counts);
+  b.g_unmapped = ctx->cam.gain_unmapped;
+  b.g_free = ctx->cam.gain_free;
+  b.g_occupied = ctx->cam.gain_occupied;
+  b.cube = a.vs * a.vs * a.vs;  // CUBE(voxel_size), rrt.h:23
+  b.half_hfov = T.half_hfov;
+  b.sum_all = ctx->cam.sum_all_yaws ? 1 : 0;
+  b.n = (int)n;
+  k_best_yaw<<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(b);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return NBVGPU_OK;
+}
+
+int enqueue_segments(nbvgpu_ctx* ctx, LayerHost* L, double radius, size_t n, const double* d_seg, uint8_t* d_free) {
+  if (n == 0) return NBVGPU_OK;
+  k_check_segments<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(L->view(), L->voxel_size, radius, d_seg, (int)n,
+                                                                         d_free, ctx->d_totals);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return NBVGPU_OK;
+}
+
+int best_device_nolock(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_pos, const double* d_parent_yaw,
+                       const double* d_distance, const uint8_t* d_edge_free, double v_max, double dyaw_max, double zero_gain,
+                       nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg) {
+  if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
+  LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
+  DeviceGuard guard(ctx->device);
+  if (!d_gain) {
+    CK(ctx->d_gain.reserve(n * 8 + 8));
+    d_gain = ctx->d_gain.as<double>();
+  }
+  if (!d_yaw_deg) {
+    CK(ctx->d_yaw.reserve(n * 4 + 4));
+    d_yaw_deg = ctx->d_yaw.as<int32_t>();
+  }
+  const int rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  static_assert(sizeof(BestRecord) == sizeof(nbvgpu_best), "record layout");
+  k_score_best<<<1, 1024, 0, ctx->stream>>>(d_gain, d_yaw_deg, d_parent_yaw, d_distance, d_edge_free, (int)n, v_max, dyaw_max,
+                                            zero_gain, reinterpret_cast<BestRecord*>(d_best));
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return NBVGPU_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+const char* nbvgpu_version(void) { return "nbvgpu 0.1 (sm_100a)"; }
+
+int nbvgpu_create(int device, nbvgpu_ctx** out) {
+  if (!out) return NBVGPU_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return NBVGPU_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NBVGPU_ERR_NO_DEVICE;
+  if (prop.major != 10) return NBVGPU_ERR_NO_DEVICE;  // built for sm_100a only
+  nbvgpu_ctx* ctx = new nbvgpu_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  DeviceGuard guard(device);
+  bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ctx->stream = ctx->own_stream;
+  ok = ok && cudaMalloc(&ctx->d_A, sizeof(double) * 360 * 24) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_B, sizeof(double) * 360 * 3) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_cs, sizeof(float) * 360 * 2) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_totals, sizeof(unsigned long long) * 8) == cudaSuccess;
+  ok = ok && cudaMemset(ctx->d_totals, 0, sizeof(unsigned long long) * 8) == cudaSuccess;
+  if (!ok) {
+    nbvgpu_destroy(ctx);
+    return NBVGPU_ERR_CUDA;
+  }
+  *out = ctx;
+  return NBVGPU_OK;
+}
+
+void nbvgpu_destroy(nbvgpu_ctx* ctx) {
+  if (!ctx) return;
+  {
+    DeviceGuard guard(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    for (LayerHost* L : ctx->layers) free_layer(L);
+    cudaFree(ctx->d_A);
+    cudaFree(ctx->d_B);
+    cudaFree(ctx->d_cs);
+    cudaFree(ctx->d_totals);
+    ctx->h_io.release();
+    for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
+                      &ctx->d_free, &ctx->d_aux, &ctx->d_best})
+      b->release();
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  }
+  delete ctx;
+}
+
+int nbvgpu_set_stream(nbvgpu_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+  return NBVGPU_OK;
+}
+
+int nbvgpu_synchronize(nbvgpu_ctx* ctx) {
+  if (!ctx) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NBVGPU_OK;
+}
+
+const char* nbvgpu_last_error(nbvgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+// ---- layers --------------------------------------------------------------------------------
+int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, size_t max_blocks, int* layer_out) {
+  if (!ctx || !layer_out) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (kind != NBVGPU_LAYER_TSDF && kind != NBVGPU_LAYER_ESDF) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer kind");
+  if (!(voxel_size > 0.f) || !std::isfinite(voxel_size)) return fail(ctx, NBVGPU_ERR_INVALID, "bad voxel size");
+  if (vps < 4 || vps > 32 || (vps & (vps - 1))) return fail(ctx, NBVGPU_ERR_INVALID, "voxels_per_side must be 4, 8, 16 or 32");
+  if (max_blocks == 0 || max_blocks > (1u << 28)) return fail(ctx, NBVGPU_ERR_INVALID, "bad max_blocks");
+  DeviceGuard guard(ctx->device);
+  LayerHost* L = new LayerHost();
+  L->kind = kind;
+  L->voxel_size = voxel_size;
+  L->vps = vps;
+  L->log2vps = ilog2(vps);
+  L->nvox = vps * vps * vps;
+  L->max_blocks = max_blocks;
+  L->log2cap = (uint32_t)ilog2(2 * (uint64_t)max_blocks);
+  if (L->log2cap < 4) L->log2cap = 4;
+  L->cap = 1u << L->log2cap;
+  const size_t tile_bytes = (size_t)L->nvox * (kind == NBVGPU_LAYER_TSDF ? 8 : 4);
+  bool ok = cudaMalloc(&L->d_table, (size_t)L->cap * sizeof(HashEntry)) == cudaSuccess;
+  ok = ok && cudaMalloc(&L->d_tiles, tile_bytes * max_blocks) == cudaSuccess;
+  if (kind == NBVGPU_LAYER_TSDF) ok = ok && cudaMalloc(&L->d_status, (size_t)(L->nvox / 16) * 4 * max_blocks) == cudaSuccess;
+  ok = ok && cudaMalloc(&L->d_free_list, sizeof(int) * max_blocks) == cudaSuccess;
+  ok = ok && cudaMalloc(&L->d_free_top, sizeof(int) * 2) == cudaSuccess;
+  ok = ok && cudaMalloc(&L->d_nblocks, sizeof(unsigned long long)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync(L->d_free_top, 0, sizeof(int) * 2, ctx->stream) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    free_layer(L);
+    return fail(ctx, NBVGPU_ERR_CUDA, "layer allocation failed");
+  }
+  const uint32_t nthreads = L->cap > (uint32_t)max_blocks ? L->cap : (uint32_t)max_blocks;
+  k_reset_table<<<(nthreads + 255) / 256, 256, 0, ctx->stream>>>(L->d_table, L->cap, L->d_free_list, (int)max_blocks,
+                                                                 L->d_free_top, L->d_nblocks);
+  ctx->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  ctx->layers.push_back(L);
+  *layer_out = (int)ctx->layers.size() - 1;
+  return NBVGPU_OK;
+}
+
+int nbvgpu_layer_update(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* keys, const void* payload, int packing) {
+  if (!ctx || (n && (!keys || !payload))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, -1);
+  if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
+  if (packing != NBVGPU_PACK_PLANAR && packing != NBVGPU_PACK_VOXBLOX) return fail(ctx, NBVGPU_ERR_INVALID, "bad packing");
+  if (L->pending && L->pending_packing != packing)
+    return fail(ctx, NBVGPU_ERR_STATE, "mixed packings between commits (commit first)");
+  for (size_t i = 0; i < 3 * n; ++i)
+    if (keys[i] < -(1 << 20) || keys[i] >= (1 << 20)) return fail(ctx, NBVGPU_ERR_RANGE, "block index out of range");
+  DeviceGuard guard(ctx->device);
+  const size_t per = L->payload_bytes_per_block(packing);
+  L->pending_packing = packing;
+  CK(L->h_keys.reserve((L->pending + n) * 12, true));
+  CK(L->h_payload.reserve((L->pending + n) * per, true));
+  for (size_t i = 0; i < n; ++i) {
+    const KeyH k{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]};
+    size_t idx;
+    auto it = L->pending_index.find(k);
+    if (it != L->pending_index.end()) {
+      idx = it->second;  // last write wins
+    } else {
+      idx = L->pending++;
+      L->pending_index.emplace(k, idx);
+      memcpy(L->h_keys.as<int32_t>() + 3 * idx, keys + 3 * i, 12);
+    }
+    memcpy(L->h_payload.as<char>() + idx * per, reinterpret_cast<const char*>(payload) + i * per, per);
+    // an update after a staged removal of the same block supersedes the removal
+    for (size_t r = 0; r + 2 < L->pending_remove.size(); r += 3)
+      if (L->pending_remove[r] == k.x && L->pending_remove[r + 1] == k.y && L->pending_remove[r + 2] == k.z) {
+        L->pending_remove.erase(L->pending_remove.begin() + r, L->pending_remove.begin() + r + 3);
+        break;
+      }
+  }
+  return NBVGPU_OK;
+}
+
+int nbvgpu_layer_update_device(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* d_keys, const void* d_payload, int packing) {
+  if (!ctx || (n && (!d_keys || !d_payload))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, -1);
+  if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
+  if (packing != NBVGPU_PACK_PLANAR && packing != NBVGPU_PACK_VOXBLOX) return fail(ctx, NBVGPU_ERR_INVALID, "bad packing");
+  DeviceGuard guard(ctx->device);
+  int rc = rehash_if_needed(ctx, L, n);
+  if (rc) return rc;
+  rc = apply_update_device(ctx, L, n, d_keys, d_payload, packing);
+  if (rc) return rc;
+  return sync_layer_state(ctx, L);
+}
+
+int nbvgpu_layer_remove(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* keys) {
+  if (!ctx || (n && !keys)) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, -1);
+  if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
+  for (size_t i = 0; i < n; ++i) {
+    const KeyH k{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]};
+    auto it = L->pending_index.find(k);
+    if (it != L->pending_index.end()) {
+      // cancel the staged update: move the last staged block into its place
+      const size_t idx = it->second, last = L->pending - 1;
+      const size_t per = L->payload_bytes_per_block(L->pending_packing);
+      L->pending_index.erase(it);
+      if (idx != last) {
+        int32_t* hk = L->h_keys.as<int32_t>();
+        memcpy(hk + 3 * idx, hk + 3 * last, 12);
+        memcpy(L->h_payload.as<char>() + idx * per, L->h_payload.as<char>() + last * per, per);
+        L->pending_index[KeyH{hk[3 * idx], hk[3 * idx + 1], hk[3 * idx + 2]}] = idx;
+      }
+      L->pending--;
+    }
+    L->pending_remove.insert(L->pending_remove.end(), {k.x, k.y, k.z});
+  }
+  return NBVGPU_OK;
+}
+
+int nbvgpu_layer_clear(nbvgpu_ctx* ctx, int layer) {
+  if (!ctx) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, -1);
+  if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
+  DeviceGuard guard(ctx->device);
+  L->pending = 0;
+  L->pending_index.clear();
+  L->pending_remove.clear();
+  const uint32_t nthreads = L->cap > (uint32_t)L->max_blocks ? L->cap : (uint32_t)L->max_blocks;
+  k_reset_table<<<(nthreads + 255) / 256, 256, 0, ctx->stream>>>(L->d_table, L->cap, L->d_free_list, (int)L->max_blocks,
+                                                                 L->d_free_top, L->d_nblocks);
+  ctx->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  L->n_blocks = 0;
+  L->tombstones = 0;
+  return NBVGPU_OK;
+}
+
+int nbvgpu_commit(nbvgpu_ctx* ctx) {
+  if (!ctx) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  int rc_all = NBVGPU_OK;
+  for (LayerHost* L : ctx->layers) {
+    if (!L || (L->pending == 0 && L->pending_remove.empty())) continue;
+    const size_t nrem = L->pending_remove.size() / 3;
+    if (nrem) {
+      CK(L->d_keys.reserve(nrem * 12));
+      CK(cudaMemcpyAsync(L->d_keys.p, L->pending_remove.data(), nrem * 12, cudaMemcpyHostToDevice, ctx->stream));
+      k_remove_keys<<<(unsigned)((nrem + 127) / 128), 128, 0, ctx->stream>>>(L->d_table, L->cap - 1, 32 - L->log2cap,
+                                                                             L->d_keys.as<int32_t>(), (int)nrem, L->d_free_list,
+                                                                             L->d_free_top, L->d_nblocks);
+      ctx->stats.kernel_launches++;
+      CK(cudaStreamSynchronize(ctx->stream));  // pending_remove is pageable memory
+      L->tombstones += nrem;
+      L->pending_remove.clear();
+      ctx->stats.bytes_uploaded += nrem * 12;
+    }
+    if (L->pending) {
+      int rc = rehash_if_needed(ctx, L, L->pending);
+      if (rc) return rc;
+      const size_t per = L->payload_bytes_per_block(L->pending_packing);
+      CK(L->d_keys.reserve(L->pending * 12));
+      CK(L->d_payload.reserve(L->pending * per));
+      CK(cudaMemcpyAsync(L->d_keys.p, L->h_keys.p, L->pending * 12, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(L->d_payload.p, L->h_payload.p, L->pending * per, cudaMemcpyHostToDevice, ctx->stream));
+      ctx->stats.bytes_uploaded += L->pending * (12 + per);
+      rc = apply_update_device(ctx, L, L->pending, L->d_keys.as<int32_t>(), L->d_payload.p, L->pending_packing);
+      if (rc) return rc;
+      L->pending = 0;
+      L->pending_index.clear();
+    }
+    const int rc = sync_layer_state(ctx, L);  // also fences the pinned staging for reuse
+    if (rc) rc_all = rc;
+  }
+  return rc_all;
+}
+
+int nbvgpu_layer_num_blocks(nbvgpu_ctx* ctx, int layer, size_t* out) {
+  if (!ctx || !out) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, -1);
+  if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
+  DeviceGuard guard(ctx->device);
+  const int rc = sync_layer_state(ctx, L);
+  *out = L->n_blocks;
+  return rc;
+}
+
+int nbvgpu_layer_read_voxels(nbvgpu_ctx* ctx, int layer, size_t n, const int64_t* g, float* out_values, uint8_t* out_found,
+                             uint8_t* out_status) {
+  if (!ctx || (n && (!g || !out_values || !out_found))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, -1);
+  if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
+  if (n == 0) return NBVGPU_OK;
+  for (size_t i = 0; i < 3 * n; ++i)
+    if (g[i] < -(1ll << 22) || g[i] >= (1ll << 22)) return fail(ctx, NBVGPU_ERR_RANGE, "voxel index out of range");
+  DeviceGuard guard(ctx->device);
+  CK(ctx->d_aux.reserve(n * (24 + 8 + 2)));
+  char* base = ctx->d_aux.as<char>();
+  long long* d_g = reinterpret_cast<long long*>(base);
+  float* d_val = reinterpret_cast<float*>(base + n * 24);
+  uint8_t* d_found = reinterpret_cast<uint8_t*>(base + n * 32);
+  uint8_t* d_stat = d_found + n;
+  CK(cudaMemcpyAsync(d_g, g, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+  k_read_voxels<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(L->view(), L->kind, d_g, (int)n, d_val, d_found,
+                                                                      L->kind == NBVGPU_LAYER_TSDF ? d_stat : nullptr);
+  ctx->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_values, d_val, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(out_found, d_found, n, cudaMemcpyDeviceToHost, ctx->stream));
+  if (out_status) {
+    if (L->kind == NBVGPU_LAYER_TSDF) CK(cudaMemcpyAsync(out_status, d_stat, n, cudaMemcpyDeviceToHost, ctx->stream));
+    else memset(out_status, 0, n);
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NBVGPU_OK;
+}
+
+// ---- camera --------------------------------------------------------------------------------
+int nbvgpu_set_camera(nbvgpu_ctx* ctx, const nbvgpu_camera* cam) {
+  if (!ctx || !cam) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  nbvgpu_host::CameraTables tab;
+  if (!nbvgpu_host::build_camera_tables(*cam, &tab)) return fail(ctx, NBVGPU_ERR_INVALID, "invalid camera parameters");
+  DeviceGuard guard(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));  // tables may still be in use
+  ctx->cam = *cam;
+  ctx->tab = tab;
+  CK(cudaMemcpyAsync(ctx->d_A, ctx->tab.A, sizeof(ctx->tab.A), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_B, ctx->tab.B, sizeof(ctx->tab.B), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->d_cs, ctx->tab.cs, sizeof(ctx->tab.cs), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->cam_set = true;
+  return NBVGPU_OK;
+}
+
+// ---- gain ----------------------------------------------------------------------------------
+int nbvgpu_gain_eval_device(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_pos, double* d_gain, int32_t* d_yaw_deg,
+                            uint64_t* d_counts, uint32_t* d_per_yaw, uint64_t* d_steps) {
+  if (!ctx || (n && (!d_pos || !d_gain))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
+  LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
+  DeviceGuard guard(ctx->device);
+  return enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, d_counts, d_per_yaw, d_steps);
+}
+
+int nbvgpu_gain_eval(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, double* gain, int32_t* yaw_deg, uint64_t* counts,
+                     uint32_t* per_yaw, uint64_t* steps) {
+  if (!ctx || (n && (!pos || !gain))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
+  LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
+  if (n == 0) return NBVGPU_OK;
+  if (check_position_range(ctx, L, n, pos)) return fail(ctx, NBVGPU_ERR_RANGE, "position non-finite or out of range");
+  DeviceGuard guard(ctx->device);
+  // pinned staging: [pos | gain | yaw | counts | steps]
+  const size_t o_gain = n * 24, o_yaw = o_gain + n * 8, o_counts = o_yaw + n * 8, o_steps = o_counts + n * 24;
+  CK(ctx->h_io.reserve(o_steps + n * 8, false));
+  char* h = ctx->h_io.as<char>();
+  memcpy(h, pos, n * 24);
+  CK(ctx->d_pos.reserve(n * 24));
+  CK(ctx->d_gain.reserve(n * 8));
+  CK(ctx->d_yaw.reserve(n * 4));
+  CK(ctx->d_counts.reserve(n * 24));
+  CK(ctx->d_steps.reserve(n * 8));
+  if (per_yaw) CK(ctx->d_per_yaw.reserve(n * 1080 * sizeof(uint32_t)));
+  CK(cudaMemcpyAsync(ctx->d_pos.p, h, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = enqueue_gain(ctx, L, n, ctx->d_pos.as<double>(), ctx->d_gain.as<double>(), ctx->d_yaw.as<int32_t>(),
+                              counts ? ctx->d_counts.as<uint64_t>() : nullptr, nullptr, steps ? ctx->d_steps.as<uint64_t>() : nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h + o_gain, ctx->d_gain.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (yaw_deg) CK(cudaMemcpyAsync(h + o_yaw, ctx->d_yaw.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (counts) CK(cudaMemcpyAsync(h + o_counts, ctx->d_counts.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+  if (steps) CK(cudaMemcpyAsync(h + o_steps, ctx->d_steps.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (per_yaw) CK(cudaMemcpyAsync(per_yaw, ctx->d_per_yaw.p, n * 1080 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(gain, h + o_gain, n * 8);
+  if (yaw_deg) memcpy(yaw_deg, h + o_yaw, n * 4);
+  if (counts) memcpy(counts, h + o_counts, n * 24);
+  if (steps) memcpy(steps, h + o_steps, n * 8);
+  return NBVGPU_OK;
+}
+
+int nbvgpu_optimized_gain(nbvgpu_ctx* ctx, int layer, double state[4], double* gain_out) {
+  if (!state || !gain_out) return NBVGPU_ERR_INVALID;
+  int32_t yaw = 0;
+  const int rc = nbvgpu_gain_eval(ctx, layer, 1, state, gain_out, &yaw, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  state[3] = yaw * M_PI / 180.0;  // rrt.cpp:477 (0.0 for gain(), :577)
+  return NBVGPU_OK;
+}
+
+int nbvgpu_gain_eval_best_device(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_pos, const double* d_parent_yaw,
+                                 const double* d_distance, const uint8_t* d_edge_free, double v_max, double dyaw_max,
+                                 double zero_gain, nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg) {
+  if (!ctx || !d_best || (n && (!d_pos || !d_parent_yaw || !d_distance))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return best_device_nolock(ctx, layer, n, d_pos, d_parent_yaw, d_distance, d_edge_free, v_max, dyaw_max, zero_gain, d_best,
+                            d_gain, d_yaw_deg);
+}
+
+int nbvgpu_gain_eval_best(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, const double* parent_yaw, const double* distance,
+                          const uint8_t* edge_free, double v_max, double dyaw_max, double zero_gain, nbvgpu_best* best,
+                          double* gain, int32_t* yaw_deg) {
+  if (!ctx || !best || (n && (!pos || !parent_yaw || !distance))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
+  LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
+  if (check_position_range(ctx, L, n, pos)) return fail(ctx, NBVGPU_ERR_RANGE, "position non-finite or out of range");
+  DeviceGuard guard(ctx->device);
+  // staging: [pos n*24 | parent n*8 | dist n*8 | free n (padded)] then results
+  const size_t o_par = n * 24, o_dist = o_par + n * 8, o_free = o_dist + n * 8, total = o_free + ((n + 7) & ~(size_t)7);
+  CK(ctx->h_io.reserve(total + n * 16 + 64, false));
+  CK(ctx->d_pos.reserve(total + 8));
+  CK(ctx->d_best.reserve(sizeof(nbvgpu_best)));
+  CK(ctx->d_gain.reserve(n * 8 + 8));
+  CK(ctx->d_yaw.reserve(n * 4 + 4));
+  char* h = ctx->h_io.as<char>();
+  memcpy(h, pos, n * 24);
+  memcpy(h + o_par, parent_yaw, n * 8);
+  memcpy(h + o_dist, distance, n * 8);
+  if (edge_free) memcpy(h + o_free, edge_free, n);
+  if (total) CK(cudaMemcpyAsync(ctx->d_pos.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
+  char* d = ctx->d_pos.as<char>();
+  const int rc = best_device_nolock(ctx, layer, n, reinterpret_cast<double*>(d), reinterpret_cast<double*>(d + o_par),
+                                    reinterpret_cast<double*>(d + o_dist),
+                                    edge_free ? reinterpret_cast<uint8_t*>(d + o_free) : nullptr, v_max, dyaw_max, zero_gain,
+                                    ctx->d_best.as<nbvgpu_best>(), ctx->d_gain.as<double>(), ctx->d_yaw.as<int32_t>());
+  if (rc) return rc;
+  char* hr = h + total;  // results after the inputs
+  CK(cudaMemcpyAsync(hr, ctx->d_best.p, sizeof(nbvgpu_best), cudaMemcpyDeviceToHost, ctx->stream));
+  if (gain && n) CK(cudaMemcpyAsync(hr + 64, ctx->d_gain.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  if (yaw_deg && n) CK(cudaMemcpyAsync(hr + 64 + n * 8, ctx->d_yaw.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(best, hr, sizeof(nbvgpu_best));
+  if (gain) memcpy(gain, hr + 64, n * 8);
+  if (yaw_deg) memcpy(yaw_deg, hr + 64 + n * 8, n * 4);
+  return NBVGPU_OK;
+}
+
+// ---- collision -----------------------------------------------------------------------------
+int nbvgpu_check_segments_device(nbvgpu_ctx* ctx, int layer, double radius, size_t n, const double* d_seg, uint8_t* d_is_free) {
+  if (!ctx || (n && (!d_seg || !d_is_free))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_ESDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
+  DeviceGuard guard(ctx->device);
+  return enqueue_segments(ctx, L, radius, n, d_seg, d_is_free);
+}
+
+int nbvgpu_check_segments(nbvgpu_ctx* ctx, int layer, double radius, size_t n, const double* seg, uint8_t* is_free) {
+  if (!ctx || (n && (!seg || !is_free))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_ESDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
+  if (n == 0) return NBVGPU_OK;
+  const double vs_inv = 1.0 / (double)L->voxel_size;
+  for (size_t i = 0; i < 6 * n; ++i)
+    if (!(std::fabs(seg[i] * vs_inv) < 4194000.0)) return fail(ctx, NBVGPU_ERR_RANGE, "segment non-finite or out of range");
+  DeviceGuard guard(ctx->device);
+  CK(ctx->h_io.reserve(n * 48 + n + 64, false));
+  CK(ctx->d_seg.reserve(n * 48));
+  CK(ctx->d_free.reserve(n));
+  char* h = ctx->h_io.as<char>();
+  memcpy(h, seg, n * 48);
+  CK(cudaMemcpyAsync(ctx->d_seg.p, h, n * 48, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = enqueue_segments(ctx, L, radius, n, ctx->d_seg.as<double>(), ctx->d_free.as<uint8_t>());
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h + n * 48, ctx->d_free.p, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(is_free, h + n * 48, n);
+  return NBVGPU_OK;
+}
+
+int nbvgpu_check_motion(nbvgpu_ctx* ctx, int layer, double radius, const double start[3], const double end[3], int* free_out) {
+  if (!start || !end || !free_out) return NBVGPU_ERR_INVALID;
+  const double seg[6] = {start[0], start[1], start[2], end[0], end[1], end[2]};
+  uint8_t f = 0;
+  const int rc = nbvgpu_check_segments(ctx, layer, radius, 1, seg, &f);
+  if (rc) return rc;
+  *free_out = f;
+  return NBVGPU_OK;
+}
+
+// ---- introspection -------------------------------------------------------------------------
+int nbvgpu_get_stats(nbvgpu_ctx* ctx, nbvgpu_stats* out) {
+  if (!ctx || !out) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  unsigned long long t[8];
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(t, ctx->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
+  ctx->stats.rays = t[0];
+  ctx->stats.voxel_steps = t[1];
+  ctx->stats.collision_steps = t[2];
+  *out = ctx->stats;
+  return NBVGPU_OK;
+}
+
+// Classifier cross-check counter of kernel variant 2 (must stay 0); not part of nbvgpu_stats.
+int nbvgpu_debug_classifier_mismatches(nbvgpu_ctx* ctx, uint64_t* out) {
+  if (!ctx || !out) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  unsigned long long t[8];
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaMemcpy(t, ctx->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
+  *out = t[3];
+  return NBVGPU_OK;
+}
+
+int nbvgpu_set_kernel_variant(nbvgpu_ctx* ctx, int variant) {
+  if (!ctx || variant < 0 || variant > 3) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->variant = variant;
+  return NBVGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,623 @@
+// nbv_oracle.cc -- CPU ORACLE for the NBV viewpoint-gain hot path.
+//
+// *** TEST INFRASTRUCTURE, NOT PRODUCT CODE. ***
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+// reference legs may load this library.  The product (libnbvgpu.so, the CUDA
+// path behind include/nbvgpu.h) never links, loads or calls anything in here.
+//
+// What it is: a dependency-free C++17 restatement of the reference's CPU
+// algorithm for the path, following the reference line by line in arithmetic
+// (double frustum / float Voxblox RayCaster / int64 voxel indices, round to
+// nearest, NO fused multiply-add: build with -ffp-contract=off, no -march).
+// Every function cites the reference file:line (relative to /root/reference)
+// it restates.  Nothing is copied: the reference is Eigen/minkindr/ROS code,
+// this file is scalar C++ over plain structs.
+//
+// PARITY UNPINNED: the reference has no test, golden vector or fixture for
+// castRay / optimized_gain / checkMotion, and it cannot be built here (needs
+// ROS, Eigen, glog, minkindr, protobuf).  The only
+// reference known answers that apply are the index-math KATs of
+// voxblox/voxblox/test/test_tsdf_map.cc, which tests/test_oracle_kats.py
+// replays against the helpers below.  The Eigen / minkindr evaluation-order
+// choices that cannot be pinned are collected in the "Eigen semantics"
+// section and are single, switchable functions.
+//
+// Eigen / minkindr are third-party dependencies that are NOT vendored under
+// /root/reference (dependencies.rosinstall lists them as bare git URLs with
+// no version pin); their published algorithms are restated here.
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// Eigen semantics (assumed; unpinned -- see header).
+// ---------------------------------------------------------------------------
+struct V3 {
+  double x, y, z;
+};
+struct Quat {
+  double w, x, y, z;
+};
+
+inline V3 add(const V3& a, const V3& b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 sub(const V3& a, const V3& b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 scale(double s, const V3& a) { return {s * a.x, s * a.y, s * a.z}; }
+
+// Eigen 3.3 redux on a fixed 3-vector of double with SSE2: one 2-wide packet
+// (x,y) then the scalar tail z  =>  (x0*y0 + x1*y1) + x2*y2.
+inline double dot(const V3& a, const V3& b) {
+#ifdef NBVO_DOT_SCALAR_UNROLLER
+  return a.x * b.x + (a.y * b.y + a.z * b.z);
+#else
+  return (a.x * b.x + a.y * b.y) + a.z * b.z;
+#endif
+}
+inline V3 cross(const V3& a, const V3& b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+inline double squared_norm(const V3& a) { return dot(a, a); }
+inline double norm(const V3& a) { return std::sqrt(squared_norm(a)); }
+// MatrixBase::normalized(): z = squaredNorm(); z > 0 ? v / sqrt(z) : v
+// (coefficient-wise true division, Eigen >= 3.3).
+inline V3 normalized(const V3& a) {
+  const double z = squared_norm(a);
+  if (z > 0.0) {
+    const double n = std::sqrt(z);
+    return {a.x / n, a.y / n, a.z / n};
+  }
+  return a;
+}
+// QuaternionBase::_transformVector: uv = q.vec x v; uv += uv;
+// v + q.w*uv + q.vec x uv.
+inline V3 rotate(const Quat& q, const V3& v) {
+  const V3 qv{q.x, q.y, q.z};
+  V3 uv = cross(qv, v);
+  uv = add(uv, uv);
+  const V3 c = cross(qv, uv);
+  return {(v.x + q.w * uv.x) + c.x, (v.y + q.w * uv.y) + c.y, (v.z + q.w * uv.z) + c.z};
+}
+// Generic Eigen quaternion product (left to right sums).  With a yaw-only left
+// operand (x = y = 0) every component has two non-zero products, so the sum
+// order cannot change the rounding.
+inline Quat qmul(const Quat& a, const Quat& b) {
+  return {a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z,
+          a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
+          a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z,
+          a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x};
+}
+inline Quat conj(const Quat& q) { return {q.w, -q.x, -q.y, -q.z}; }
+
+// ---------------------------------------------------------------------------
+// Voxblox index math.
+// ---------------------------------------------------------------------------
+constexpr float kEpsilon = 1e-6f;  // voxblox/core/common.h:142
+
+// getGridIndexFromPoint(scaled) -- voxblox/core/common.h:166-171.
+inline int64_t grid_index_scaled(float v) { return (int64_t)std::floor(v + kEpsilon); }
+// getGridIndexFromPoint(point, inv) -- voxblox/core/common.h:151-158.
+inline int64_t grid_index(float v, float inv) { return (int64_t)std::floor(v * inv + kEpsilon); }
+// signum -- voxblox/core/common.h:258.
+inline int signum(float x) { return (x == 0) ? 0 : x < 0 ? -1 : 1; }
+// getBlockIndexFromGlobalVoxelIndex -- voxblox/core/common.h:215-224.
+inline int32_t block_from_global(int64_t g, float vps_inv) {
+  return (int32_t)std::floor(static_cast<float>(g) * vps_inv);
+}
+// getLocalFromGlobalVoxelIndex -- voxblox/core/common.h:233-243.
+inline int32_t local_from_global(int64_t g, int vps) {
+  constexpr int offset = 1 << (8 * sizeof(int) - 1);  // INT_MIN, as in the reference
+  return (int32_t)((g + offset) & (vps - 1));
+}
+// Block::computeLinearIndexFromVoxelIndex -- voxblox/core/block_inl.h:12-27.
+inline size_t linear_index(int vps, int x, int y, int z) {
+  return static_cast<size_t>(x + vps * (y + z * vps));
+}
+// AnyIndexHash -- voxblox/core/block_hash.h:20-31.
+struct Key {
+  int32_t x, y, z;
+  bool operator==(const Key& o) const { return x == o.x && y == o.y && z == o.z; }
+};
+struct KeyHash {
+  static constexpr size_t sl = 17191;
+  static constexpr size_t sl2 = sl * sl;
+  size_t operator()(const Key& k) const {
+    return static_cast<unsigned int>(k.x + k.y * sl + k.z * sl2);
+  }
+};
+
+// RayCaster -- voxblox/src/integrator/integrator_utils.cc:111-179.
+struct RayCaster {
+  int64_t cur[3];
+  int sgn[3];
+  float t[3], dt[3];
+  unsigned len, step;
+
+  RayCaster(const float s[3], const float e[3]) {
+    // integrator_utils.cc:129-134: NaN input returns early with current_step_
+    // uninitialised (UB in the reference); the ABI rejects non-finite input, the
+    // oracle emits nothing for it.
+    if (std::isnan(s[0]) || std::isnan(s[1]) || std::isnan(s[2]) || std::isnan(e[0]) ||
+        std::isnan(e[1]) || std::isnan(e[2])) {
+      len = 0;
+      step = 1;
+      for (int k = 0; k < 3; ++k) { cur[k] = 0; sgn[k] = 0; t[k] = dt[k] = 0.f; }
+      return;
+    }
+    int64_t diff[3];
+    for (int k = 0; k < 3; ++k) {
+      cur[k] = grid_index_scaled(s[k]);            // :136
+      diff[k] = grid_index_scaled(e[k]) - cur[k];  // :137-138
+    }
+    step = 0;                                                                  // :140
+    len = (unsigned)(std::abs(diff[0]) + std::abs(diff[1]) + std::abs(diff[2]));  // :142-143
+    for (int k = 0; k < 3; ++k) {
+      const float r = e[k] - s[k];                 // :145
+      sgn[k] = signum(r);                          // :147-148
+      const int cs = std::max(0, sgn[k]);          // :150-152
+      const float shifted = s[k] - (float)cur[k];  // :154-155
+      const float dist = (float)cs - shifted;      // :157-158
+      // :160-166 / :170-178 -- the `abs(r) < 0.0 ? 2.0 :` guard can never fire,
+      // so a zero component divides by zero (+-inf / NaN), as in the reference.
+      t[k] = (std::abs(r) < 0.0) ? 2.0 : dist / r;
+      dt[k] = (std::abs(r) < 0.0) ? 2.0 : sgn[k] / r;
+    }
+  }
+  // nextRayIndex -- integrator_utils.cc:111-125; minCoeff keeps the first
+  // minimum (`value < best`), NaN never wins unless it is element 0.
+  bool next(int64_t out[3]) {
+    if (step++ > len) return false;
+    out[0] = cur[0]; out[1] = cur[1]; out[2] = cur[2];
+    int m = 0;
+    float best = t[0];
+    if (t[1] < best) { best = t[1]; m = 1; }
+    if (t[2] < best) { best = t[2]; m = 2; }
+    cur[m] += sgn[m];
+    t[m] += dt[m];
+    return true;
+  }
+};
+
+// ---------------------------------------------------------------------------
+// Layers: unordered_map<BlockIndex, dense vps^3 tile>, voxblox/core/layer.h.
+// ---------------------------------------------------------------------------
+struct TsdfVoxel { float distance, weight; };  // voxel.h:12-16 (colour unused)
+struct Layer {
+  int kind;  // 0 TSDF, 1 ESDF
+  float voxel_size;
+  int vps;
+  float vps_inv;
+  size_t nvox;
+  std::unordered_map<Key, std::unique_ptr<float[]>, KeyHash> blocks;  // TSDF: 2 floats/voxel
+};
+
+struct Camera {
+  double hfov_deg, vfov_deg, near_m, far_m;
+  double q_CB[4];  // w x y z
+  double t_CB[3];
+  double bbx_min[3], bbx_max[3];
+  double gain_free, gain_occupied, gain_unmapped;
+  int32_t sum_all_yaws;
+  int32_t reserved;
+};
+
+struct Plane {  // camera_model.cpp:5-23
+  V3 n;
+  double d;
+  void set_from_points(const V3& p1, const V3& p2, const V3& p3) {
+    const V3 p1p2 = sub(p2, p1);
+    const V3 p1p3 = sub(p3, p1);
+    n = normalized(cross(p1p2, p1p3));
+    d = dot(n, p1);
+  }
+  bool correct_side(const V3& p) const { return dot(p, n) >= d; }
+};
+
+struct Ctx {
+  std::vector<std::unique_ptr<Layer>> layers;
+  Camera cam{};
+  bool cam_set = false;
+  V3 corners_C[8];
+  Quat q_BC;
+  V3 t_BC;
+};
+
+// CameraModel::setIntrinsicsFromFoV -- camera_model.cpp:25-83 (6-plane mode).
+void set_intrinsics(Ctx* c) {
+  const Camera& cam = c->cam;
+  // camera_model.cpp:35-42: hfov == 360 builds the first 8 corners for a 90 degree sector.
+  const double hfov = (cam.hfov_deg == 360.0 ? 90.0 : cam.hfov_deg) * M_PI / 180.0;
+  const double vfov = cam.vfov_deg * M_PI / 180.0;
+  const double th = std::tan(hfov / 2.0);
+  const double tv = std::tan(vfov / 2.0);
+  const double n = cam.near_m, f = cam.far_m;
+  c->corners_C[0] = {n, n * th, n * tv};
+  c->corners_C[1] = {n, n * th, -n * tv};
+  c->corners_C[2] = {n, -n * th, -n * tv};
+  c->corners_C[3] = {n, -n * th, n * tv};
+  c->corners_C[4] = {f, f * th, f * tv};
+  c->corners_C[5] = {f, f * th, -f * tv};
+  c->corners_C[6] = {f, -f * th, -f * tv};
+  c->corners_C[7] = {f, -f * th, f * tv};
+  // T_C_B.inverse() (camera_model.cpp:92-94): minkindr inverts a unit
+  // quaternion by conjugation and the translation as -(q^-1 . t).
+  const Quat q_CB{cam.q_CB[0], cam.q_CB[1], cam.q_CB[2], cam.q_CB[3]};
+  c->q_BC = conj(q_CB);
+  const V3 r = rotate(c->q_BC, V3{cam.t_CB[0], cam.t_CB[1], cam.t_CB[2]});
+  c->t_BC = {-r.x, -r.y, -r.z};
+}
+
+struct YawFrame {
+  V3 cam_pos;
+  Plane planes[6];
+  V3 pp0, pp1, pp2;
+};
+
+// rrt.cpp:369-377 + camera_model.cpp:87-94,98-164,280-289 for one yaw.
+void yaw_frame(const Ctx* c, const V3& p, int i, YawFrame* f) {
+  const double yaw = M_PI * i / 180.0;  // rrt.cpp:369
+  // Eigen::AngleAxisd(yaw, UnitZ) -> Quaterniond: w = cos(a/2), vec = sin(a/2)*axis.
+  const double ha = 0.5 * yaw;
+  const double s = std::sin(ha);
+  const Quat q_yaw{std::cos(ha), s * 0.0, s * 0.0, s * 1.0};
+  // T_G_C = T_G_B * T_B_C : (qa*qb, ta + qa.rotate(tb)).
+  const Quat q_GC = qmul(q_yaw, c->q_BC);
+  const V3 t_GC = add(p, rotate(q_yaw, c->t_BC));
+  f->cam_pos = t_GC;
+  V3 g[8];
+  for (int k = 0; k < 8; ++k) g[k] = add(rotate(q_GC, c->corners_C[k]), t_GC);  // :119-121
+  f->planes[0].set_from_points(g[0], g[2], g[1]);  // near   :125
+  f->planes[1].set_from_points(g[4], g[5], g[6]);  // far    :131
+  f->planes[2].set_from_points(g[3], g[6], g[2]);  // left   :138
+  f->planes[3].set_from_points(g[0], g[5], g[4]);  // right  :145
+  f->planes[4].set_from_points(g[3], g[4], g[7]);  // top    :152
+  f->planes[5].set_from_points(g[2], g[6], g[5]);  // bottom :159
+  f->pp0 = g[4]; f->pp1 = g[5]; f->pp2 = g[6];     // getFarPlanePoints :280-289
+}
+
+// isInsideBounds (nbveplanner/common.h:22-31) + CameraModel::isPointInView
+// (camera_model.cpp:191-201).
+inline bool in_view(const Camera& cam, const YawFrame& f, const V3& p) {
+  if (!(p.x >= cam.bbx_min[0] && p.x <= cam.bbx_max[0] && p.y >= cam.bbx_min[1] &&
+        p.y <= cam.bbx_max[1] && p.z >= cam.bbx_min[2] && p.z <= cam.bbx_max[2]))
+    return false;
+  for (int k = 0; k < 6; ++k)
+    if (!f.planes[k].correct_side(p)) return false;
+  return true;
+}
+
+enum Status { kUnknown = 0, kFree = 1, kOccupied = 2 };
+
+// VoxbloxManager::getVoxelStatusByIndex -- voxblox_manager.cpp:14-33.
+inline Status voxel_status(const Layer& L, const Key& b, int lx, int ly, int lz) {
+  auto it = L.blocks.find(b);
+  if (it == L.blocks.end()) return kUnknown;
+  const float* v = it->second.get() + 2 * linear_index(L.vps, lx, ly, lz);
+  if (v[1] <= 1e-1) return kUnknown;   // float widened to double vs double literal
+  if (v[0] <= 0.0) return kOccupied;
+  return kFree;
+}
+
+struct GainOut {
+  double gain;
+  double yaw;          // state[3]
+  int32_t yaw_deg;
+  uint64_t counts[3];  // unknown, free, occupied over the winning window (or all yaws)
+  uint64_t steps;      // executed voxel-steps (SURVEY.md 8d unit of work)
+  uint64_t rays;
+};
+
+// RrtTree::optimized_gain (rrt.cpp:351-479) and RrtTree::gain (rrt.cpp:481-579).
+void eval_gain(const Ctx* c, const Layer& L, const double pos[3], bool sum_all, GainOut* out,
+               uint32_t* per_yaw /* [360][3] or null */) {
+  const Camera& cam = c->cam;
+  const double vs = (double)L.voxel_size;  // rrt.cpp:352 (float layer value widened)
+  const double vs_inv = 1.0 / vs;
+  const double cube = vs * vs * vs;        // CUBE macro, rrt.h:23
+  const V3 p{pos[0], pos[1], pos[2]};
+  double vertical_gain[360];
+  uint32_t cnt[360][3];
+  double total_gain = 0.0;  // gain(): one accumulator over all yaws (rrt.cpp:497)
+  uint64_t steps = 0, rays = 0;
+  YawFrame f;
+  for (int i = -180; i < 180; ++i) {
+    yaw_frame(c, p, i, &f);
+    const V3 ud = sub(f.pp0, f.pp1);                      // :382
+    const V3 us = normalized(ud);                          // :383
+    const int u_max = (int)std::ceil(norm(ud) * vs_inv);   // :384
+    const V3 d21 = sub(f.pp2, f.pp1);
+    const V3 vc{d21.x / 2.0, d21.y / 2.0, d21.z / 2.0};    // :385
+    double gain = sum_all ? total_gain : 0.0;              // :388 (gain(): never reset, :497)
+    uint32_t* ct = cnt[i + 180];
+    ct[0] = ct[1] = ct[2] = 0;
+    const float start[3] = {(float)(f.cam_pos.x * vs_inv), (float)(f.cam_pos.y * vs_inv),
+                            (float)(f.cam_pos.z * vs_inv)};  // :408-409
+    for (int u = 0; u < u_max; ++u) {
+      // :396  pos = pp1 + u*u_slope*voxel_size + v_center
+      const V3 e{(f.pp1.x + ((double)u * us.x) * vs) + vc.x,
+                 (f.pp1.y + ((double)u * us.y) * vs) + vc.y,
+                 (f.pp1.z + ((double)u * us.z) * vs) + vc.z};
+      const float end[3] = {(float)(e.x * vs_inv), (float)(e.y * vs_inv),
+                            (float)(e.z * vs_inv)};  // :410-411
+      RayCaster rc(start, end);                       // :413-414
+      ++rays;
+      int64_t g[3];
+      while (rc.next(g)) {                            // :419
+        ++steps;
+        const Key b{block_from_global(g[0], L.vps_inv), block_from_global(g[1], L.vps_inv),
+                    block_from_global(g[2], L.vps_inv)};  // :421
+        const V3 rp{(double)g[0] * vs, (double)g[1] * vs, (double)g[2] * vs};  // :431
+        if (in_view(cam, f, rp)) {                    // :433
+          const Status st = voxel_status(L, b, local_from_global(g[0], L.vps),
+                                         local_from_global(g[1], L.vps),
+                                         local_from_global(g[2], L.vps));  // :435
+          if (st == kUnknown) {
+            gain += cam.gain_unmapped; ++ct[0];
+          } else if (st == kOccupied) {
+            gain += cam.gain_occupied; ++ct[2];
+            break;
+          } else {
+            gain += cam.gain_free; ++ct[1];
+          }
+        }
+      }
+    }
+    vertical_gain[i + 180] = gain;  // :447
+    if (sum_all) total_gain = gain;
+  }
+  out->steps = steps;
+  out->rays = rays;
+  if (per_yaw) std::memcpy(per_yaw, cnt, sizeof(cnt));
+  if (sum_all) {
+    // rrt.cpp:481-579: one running double sum over every step of every yaw,
+    // state[3] = 0, return gain * cube.
+    uint64_t n[3] = {0, 0, 0};
+    for (int y = 0; y < 360; ++y)
+      for (int k = 0; k < 3; ++k) n[k] += cnt[y][k];
+    out->gain = total_gain * cube;
+    out->yaw = 0.0;
+    out->yaw_deg = 0;
+    out->counts[0] = n[0]; out->counts[1] = n[1]; out->counts[2] = n[2];
+    return;
+  }
+  // Best yaw window -- rrt.cpp:449-478.
+  double max_gain = 0.0;
+  int max_gain_yaw = 0;
+  const int half_hfov = (int)std::floor(cam.hfov_deg / 2.0);
+  for (int i = -180; i < 180; i += 5) {
+    double current = 0.0;
+    int left = (i + 180) - half_hfov;
+    if (left < 0) {
+      for (int j = 360 + left; j < 360; ++j) current += vertical_gain[j];
+      left = 0;
+    }
+    int right = (i + 180) + half_hfov;
+    if (right >= 360) {
+      for (int j = 0; j < right - 359; ++j) current += vertical_gain[j];
+      right = 359;
+    }
+    for (int j = left; j <= right; ++j) current += vertical_gain[j];
+    if (current > max_gain) {
+      max_gain = current;
+      max_gain_yaw = i;
+    }
+  }
+  out->yaw_deg = max_gain_yaw;
+  out->yaw = max_gain_yaw * M_PI / 180.0;  // :477
+  out->gain = max_gain * cube;             // :478
+  // Counts over the winning window (diagnostic; same wrap rule as above).
+  uint64_t n[3] = {0, 0, 0};
+  for (int d = -half_hfov; d <= half_hfov; ++d) {
+    const int j = (((max_gain_yaw + 180 + d) % 360) + 360) % 360;
+    for (int k = 0; k < 3; ++k) n[k] += cnt[j][k];
+  }
+  out->counts[0] = n[0]; out->counts[1] = n[1]; out->counts[2] = n[2];
+}
+
+// HighResManager::checkMotion (voxblox_manager.h:89-108) +
+// checkCollisionWithRobotAtVoxel (voxblox_manager.cpp:121-129) +
+// Layer::getVoxelPtrByGlobalIndex (layer.h:215-239).
+bool check_motion(const Layer& L, double radius, const double seg[6], uint64_t* steps) {
+  float s[3], e[3];
+  for (int k = 0; k < 3; ++k) {
+    s[k] = (float)seg[k] / L.voxel_size;      // float division by the float voxel size
+    e[k] = (float)seg[3 + k] / L.voxel_size;
+  }
+  RayCaster rc(s, e);
+  int64_t g[3];
+  while (rc.next(g)) {
+    if (steps) ++*steps;
+    const Key b{block_from_global(g[0], L.vps_inv), block_from_global(g[1], L.vps_inv),
+                block_from_global(g[2], L.vps_inv)};
+    auto it = L.blocks.find(b);
+    if (it == L.blocks.end()) return false;  // nullptr voxel => collision
+    const float d = it->second.get()[linear_index(L.vps, local_from_global(g[0], L.vps),
+                                                  local_from_global(g[1], L.vps),
+                                                  local_from_global(g[2], L.vps))];
+    if (radius >= d) return false;           // double >= float widened
+  }
+  return true;
+}
+
+template <class F>
+void parallel_for(size_t n, int n_threads, F&& fn) {
+  if (n_threads <= 1 || n <= 1) {
+    for (size_t i = 0; i < n; ++i) fn(i);
+    return;
+  }
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> th;
+  const int nt = (int)std::min<size_t>((size_t)n_threads, n);
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&] {
+      for (;;) {
+        const size_t i = next.fetch_add(1);
+        if (i >= n) break;
+        fn(i);
+      }
+    });
+  for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C API (ctypes).
+// ---------------------------------------------------------------------------
+extern "C" {
+
+void* nbvo_create() { return new Ctx(); }
+void nbvo_destroy(void* c) { delete static_cast<Ctx*>(c); }
+
+int nbvo_layer_create(void* c_, int kind, float voxel_size, int vps) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  if ((vps & (vps - 1)) != 0 || vps <= 0) return -1;
+  auto L = std::make_unique<Layer>();
+  L->kind = kind;
+  L->voxel_size = voxel_size;
+  L->vps = vps;
+  L->vps_inv = 1.0f / (float)vps;  // layer.h:34-44
+  L->nvox = (size_t)vps * vps * vps;
+  c->layers.push_back(std::move(L));
+  return (int)c->layers.size() - 1;
+}
+
+// Planar payload: TSDF [n][nvox][2] float (distance, weight); ESDF [n][nvox] float.
+int nbvo_layer_update(void* c_, int layer, size_t n, const int32_t* keys, const float* data) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  Layer& L = *c->layers.at(layer);
+  const size_t per = L.nvox * (L.kind == 0 ? 2 : 1);
+  for (size_t i = 0; i < n; ++i) {
+    const Key k{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]};
+    auto& slot = L.blocks[k];
+    if (!slot) slot.reset(new float[per]);
+    std::memcpy(slot.get(), data + i * per, per * sizeof(float));
+  }
+  return 0;
+}
+int nbvo_layer_remove(void* c_, int layer, size_t n, const int32_t* keys) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  Layer& L = *c->layers.at(layer);
+  for (size_t i = 0; i < n; ++i) L.blocks.erase(Key{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]});
+  return 0;
+}
+int nbvo_layer_clear(void* c_, int layer) {
+  static_cast<Ctx*>(c_)->layers.at(layer)->blocks.clear();
+  return 0;
+}
+size_t nbvo_layer_num_blocks(void* c_, int layer) {
+  return static_cast<Ctx*>(c_)->layers.at(layer)->blocks.size();
+}
+
+int nbvo_set_camera(void* c_, const Camera* cam) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  c->cam = *cam;
+  c->cam_set = true;
+  set_intrinsics(c);
+  return 0;
+}
+
+// Batched gain. out arrays may be null except gain/yaw_deg.
+int nbvo_gain_eval(void* c_, int layer, size_t n, const double* pos, double* gain, int32_t* yaw_deg,
+                   double* yaw_rad, uint64_t* counts /*[n][3]*/, uint32_t* per_yaw /*[n][360][3]*/,
+                   uint64_t* steps /*[n]*/, uint64_t* rays /*[n]*/, int n_threads) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  if (!c->cam_set) return -2;
+  const Layer& L = *c->layers.at(layer);
+  if (L.kind != 0) return -3;
+  const bool sum_all = c->cam.sum_all_yaws != 0;
+  parallel_for(n, n_threads, [&](size_t i) {
+    GainOut o{};
+    eval_gain(c, L, pos + 3 * i, sum_all, &o, per_yaw ? per_yaw + i * 1080 : nullptr);
+    gain[i] = o.gain;
+    yaw_deg[i] = o.yaw_deg;
+    if (yaw_rad) yaw_rad[i] = o.yaw;
+    if (counts) { counts[3 * i] = o.counts[0]; counts[3 * i + 1] = o.counts[1]; counts[3 * i + 2] = o.counts[2]; }
+    if (steps) steps[i] = o.steps;
+    if (rays) rays[i] = o.rays;
+  });
+  return 0;
+}
+
+int nbvo_check_segments(void* c_, int layer, double radius, size_t n, const double* seg,
+                        uint8_t* is_free, uint64_t* steps /*[n] or null*/, int n_threads) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  const Layer& L = *c->layers.at(layer);
+  if (L.kind != 1) return -3;
+  parallel_for(n, n_threads, [&](size_t i) {
+    uint64_t st = 0;
+    is_free[i] = check_motion(L, radius, seg + 6 * i, &st) ? 1 : 0;
+    if (steps) steps[i] = st;
+  });
+  return 0;
+}
+
+// castRay (integrator_utils.h:133-143): returns the number of indices the
+// reference would emit; writes at most `cap` of them.
+size_t nbvo_cast_ray(const float* start, const float* end, int64_t* out, size_t cap) {
+  RayCaster rc(start, end);
+  int64_t g[3];
+  size_t n = 0;
+  while (rc.next(g)) {
+    if (n < cap) { out[3 * n] = g[0]; out[3 * n + 1] = g[1]; out[3 * n + 2] = g[2]; }
+    ++n;
+  }
+  return n;
+}
+
+// Per-yaw frame dump for tests: planes [6][4] (nx,ny,nz,d), cam[3], pp[3][3], u_max.
+int nbvo_yaw_frame(void* c_, int layer, const double* pos, int yaw_deg, double* planes, double* cam,
+                   double* pp, int32_t* u_max) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  const Layer& L = *c->layers.at(layer);
+  YawFrame f;
+  yaw_frame(c, V3{pos[0], pos[1], pos[2]}, yaw_deg, &f);
+  for (int k = 0; k < 6; ++k) {
+    planes[4 * k] = f.planes[k].n.x; planes[4 * k + 1] = f.planes[k].n.y;
+    planes[4 * k + 2] = f.planes[k].n.z; planes[4 * k + 3] = f.planes[k].d;
+  }
+  cam[0] = f.cam_pos.x; cam[1] = f.cam_pos.y; cam[2] = f.cam_pos.z;
+  const V3* P[3] = {&f.pp0, &f.pp1, &f.pp2};
+  for (int k = 0; k < 3; ++k) { pp[3 * k] = P[k]->x; pp[3 * k + 1] = P[k]->y; pp[3 * k + 2] = P[k]->z; }
+  const double vs_inv = 1.0 / (double)L.voxel_size;
+  *u_max = (int)std::ceil(norm(sub(f.pp0, f.pp1)) * vs_inv);
+  return 0;
+}
+
+// Index helpers for the test_tsdf_map.cc known answers.
+void nbvo_grid_index_from_point(const float* p, float grid_size_inv, int64_t* out) {
+  for (int k = 0; k < 3; ++k) out[k] = grid_index(p[k], grid_size_inv);
+}
+void nbvo_block_and_local(const int64_t* g, int vps, int32_t* block, int32_t* local) {
+  const float inv = 1.0f / (float)vps;
+  for (int k = 0; k < 3; ++k) { block[k] = block_from_global(g[k], inv); local[k] = local_from_global(g[k], vps); }
+}
+uint64_t nbvo_linear_index(int vps, int x, int y, int z) { return linear_index(vps, x, y, z); }
+uint64_t nbvo_block_hash(int x, int y, int z) { return KeyHash()(Key{x, y, z}); }
+// Voxel status of one global voxel index (0 unknown, 1 free, 2 occupied).
+int nbvo_voxel_status(void* c_, int layer, const int64_t* g) {
+  const Layer& L = *static_cast<Ctx*>(c_)->layers.at(layer);
+  const Key b{block_from_global(g[0], L.vps_inv), block_from_global(g[1], L.vps_inv),
+              block_from_global(g[2], L.vps_inv)};
+  return voxel_status(L, b, local_from_global(g[0], L.vps), local_from_global(g[1], L.vps),
+                      local_from_global(g[2], L.vps));
+}
+// ESDF voxel distance or NaN when the block is not allocated.
+float nbvo_esdf_distance(void* c_, int layer, const int64_t* g) {
+  const Layer& L = *static_cast<Ctx*>(c_)->layers.at(layer);
+  const Key b{block_from_global(g[0], L.vps_inv), block_from_global(g[1], L.vps_inv),
+              block_from_global(g[2], L.vps_inv)};
+  auto it = L.blocks.find(b);
+  if (it == L.blocks.end()) return NAN;
+  return it->second.get()[linear_index(L.vps, local_from_global(g[0], L.vps),
+                                       local_from_global(g[1], L.vps), local_from_global(g[2], L.vps))];
+}
+
+}  // extern "C"
