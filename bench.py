@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- viewpoint-gain hot path benchmark (BASELINE.json metric: candidate viewpoints/s).
+
+A "step" is one planning-step pass of the hot path over one batch of synthetic candidates:
+segment collision check of every tree edge (HighResManager::checkMotion), gain evaluation of every
+candidate (RrtTree::optimized_gain: 360-yaw ray sweep + best-yaw window), node scoring and
+best-candidate selection (rrt.cpp:220-246); with N > 1 ranks also the all-gather of the per-rank
+best records.  Workload at N = 1: BASELINE.json configs[1] ("cfg2": 20x20x5 m synthetic TSDF/ESDF,
+0.15 m voxels, 90x60 deg FOV, 5 m range, 1,000 candidates with their parent edges).  With N GPUs
+every rank evaluates its own 1,000 candidates on a replica of the map (weak scaling; the map is
+broadcast from rank 0 over NCCL during setup).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfgX]
+
+Prints ONE JSON line (rank 0).  `value` = candidates of all ranks / device time (CUDA events on the
+launching stream, max over ranks) with inputs resident in HBM; `e2e` = same through the host-buffer
+C ABI (H2D of the candidates and D2H of the results inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_STEP = 8.0  # one {distance, weight} pair per voxel-step
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU (default: the config's)")
+    ap.add_argument("--variant", type=int, default=0, help="gain kernel variant (A/B measurement)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the cpu_baseline sample (default 1000)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the ray-sweep kernel from the committed ncu
+    capture (profiles/ncu_traffic.json, written by profiles/summarize_ncu.py), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("k_gain_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def load_oracle_ctx(m, cam):
+    from oracle.binding import Oracle  # cpu_baseline / reference arm only
+    o = Oracle()
+    lt = o.layer_create(0, m.voxel_size, m.vps)
+    le = o.layer_create(1, m.voxel_size, m.vps)
+    o.layer_update(lt, m.keys, m.tsdf)
+    o.layer_update(le, m.keys, m.esdf)
+    o.set_camera(cam.as_dict())
+    return o, lt, le
+
+
+def time_oracle(o, lt, le, cfg, pos, seg, threads):
+    t0 = time.perf_counter()
+    o.check_segments(le, cfg.robot_radius, seg, threads=threads)
+    r = o.gain_eval(lt, pos, threads=threads)
+    dt = time.perf_counter() - t0
+    return dt, int(r["steps"].sum())
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    """Reference arm: the reference's CPU algorithm for the path (oracle port -- the reference itself
+    needs ROS/Eigen/glog/minkindr and cannot be built here) on the host cores, all threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from nbv_exploration_planner_b200 import synth
+    cfg = synth.CONFIGS[args.config]
+    m = synth.make_map(args.config)
+    cam = m.camera()
+    o, lt, le = load_oracle_ctx(m, cam)
+    cores = os.cpu_count() or 1
+    n_total = args.candidates or cfg.n_candidates
+    c = synth.make_candidates(cfg, n_total, lambda s: o.check_segments(le, cfg.robot_radius, s, threads=cores)["free"])
+    sample = min(n_total, max(cores * 4, 64))  # bounded per-step sample so that K steps end within minutes
+    pos, seg = c.positions[:sample], c.segments[:sample]
+    for _ in range(min(args.warmup, 2)):
+        time_oracle(o, lt, le, cfg, pos, seg, cores)
+    steps = max(1, min(args.steps, 20))
+    total, vsteps = 0.0, 0
+    for _ in range(steps):
+        dt, st = time_oracle(o, lt, le, cfg, pos, seg, cores)
+        total += dt
+        vsteps += st
+    value = sample * steps / total
+    out = {
+        "impl": "reference", "metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 frustum + f32 DDA + i64 voxel index", "data": "synthetic",
+        "voxel_steps_per_s": vsteps / total,
+        "config": {"workload": f"{args.config}: {cfg.bounds_max[0]}x{cfg.bounds_max[1]}x{cfg.bounds_max[2]} m synthetic TSDF+ESDF, "
+                               f"{cfg.voxel_size} m voxels, {cfg.hfov_deg}x{cfg.vfov_deg} deg, {cfg.far_m} m range, "
+                               f"{n_total} candidates with ESDF edge check", "candidates_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "viewpoints/s", "cores": cores, "kind": "port",
+                         "sample": f"first {sample} of {n_total} candidates per step, {steps} steps, all {cores} host threads"},
+        "e2e": {"value": value, "unit": "viewpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from nbv_exploration_planner_b200 import LAYER_ESDF, LAYER_TSDF, NbvGpu, synth
+    from nbv_exploration_planner_b200 import dist as nd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.CONFIGS[args.config]
+    n_per = args.candidates or cfg.n_candidates
+    g = NbvGpu(local)
+    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    g.set_kernel_variant(args.variant)
+
+    # ---- setup (untimed): map on rank 0 -> NCCL broadcast -> every replica; candidates ------------
+    t_setup = time.perf_counter()
+    m = synth.make_map(args.config) if rank == 0 else None
+    nvox = cfg.vps ** 3
+    nb_hdr = torch.tensor([len(m.keys) if rank == 0 else 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(nb_hdr, 0)
+    nb = int(nb_hdr.item())
+    lt = g.layer_create(LAYER_TSDF, cfg.voxel_size, cfg.vps, nb + 64)
+    le = g.layer_create(LAYER_ESDF, cfg.voxel_size, cfg.vps, nb + 64)
+    ev_b0, ev_b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev_b0.record()
+    n_t, dk, dp = nd.broadcast_blocks(m.keys if rank == 0 else None, m.tsdf if rank == 0 else None, 2 * nvox, dev)
+    g.layer_update_device(lt, n_t, dk, dp)
+    n_e, dk2, dp2 = nd.broadcast_blocks(m.keys if rank == 0 else None, m.esdf if rank == 0 else None, nvox, dev)
+    g.layer_update_device(le, n_e, dk2, dp2)
+    ev_b1.record()
+    torch.cuda.synchronize()
+    map_broadcast_ms = ev_b0.elapsed_time(ev_b1)
+    cam = synth.camera_for(cfg)
+    g.set_camera(cam)
+
+    # candidates: grown on rank 0 with the GPU collision check as the acceptance test, then shared
+    if rank == 0:
+        c = synth.make_candidates(cfg, n_per * world, lambda s: g.check_segments(le, cfg.robot_radius, s))
+        pack = np.concatenate([c.positions, c.segments, c.distance[:, None]], 1)
+    else:
+        pack = np.empty((n_per * world, 10))
+    pack_t = torch.from_numpy(pack).to(dev)
+    if world > 1:
+        dist.broadcast(pack_t, 0)
+    lo, hi = nd.shard_bounds(n_per * world, world, rank)
+    mine = pack_t[lo:hi].contiguous()
+    n = hi - lo
+    d_pos = mine[:, 0:3].contiguous()
+    d_seg = mine[:, 3:9].contiguous()
+    d_dist = mine[:, 9].contiguous()
+    d_pyaw = torch.zeros(n, dtype=torch.float64, device=dev)   # flat candidate set: parents face yaw 0
+    d_free = torch.empty(n, dtype=torch.uint8, device=dev)
+    d_gain = torch.empty(n, dtype=torch.float64, device=dev)
+    d_yaw = torch.empty(n, dtype=torch.int32, device=dev)
+    d_best = torch.empty(32, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    v_max, dyaw_max, zero_gain = 1.0, 0.5, 0.0
+    setup_s = time.perf_counter() - t_setup
+
+    def step_device():
+        g.check_segments_device(le, cfg.robot_radius, n, d_seg, d_free)
+        g.gain_eval_best_device(lt, n, d_pos, d_pyaw, d_dist, d_free, v_max, dyaw_max, zero_gain, d_best, d_gain, d_yaw)
+        if world > 1:
+            return nd.gather_best(nd.best_record_as_f64(d_best), lo)
+        return None
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+
+    # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps ------
+    sampler = ClockSampler(local)
+    st0 = g.stats()
+    g.set_profiling(True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    winner = None
+    for a, b in evs:
+        flush.zero_()
+        a.record()
+        winner = step_device()
+        b.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler.stop_flag = True
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    kern_ms, kern_launches = g.profile_collect()
+    g.set_profiling(False)
+    st1 = g.stats()
+    launches = st1["kernel_launches"] - st0["kernel_launches"]
+    vsteps = st1["voxel_steps"] - st0["voxel_steps"]
+    rays = st1["rays"] - st0["rays"]
+
+    # ---- e2e: same step through the host-buffer C ABI (H2D + D2H inside) ---------------------------
+    h = mine.cpu().numpy()
+    h_pos, h_seg, h_dist = np.ascontiguousarray(h[:, 0:3]), np.ascontiguousarray(h[:, 3:9]), np.ascontiguousarray(h[:, 9])
+    h_pyaw = np.zeros(n)
+    e2e_steps = max(3, min(args.steps, 30))
+
+    def step_host():
+        free = g.check_segments(le, cfg.robot_radius, h_seg)
+        r = g.gain_eval_best(lt, h_pos, h_pyaw, h_dist, free, v_max, dyaw_max, zero_gain)
+        if world > 1:
+            rec = torch.tensor([r["index"], r["score"], r["best_gain"], r["best_yaw"]], dtype=torch.float64, device=dev)
+            return nd.gather_best(rec, lo)
+        return r
+
+    for _ in range(2):
+        host_result = step_host()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_result = step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    h2d = n * (48 + 24 + 8 + 8 + 1)
+    d2h = n * (1 + 8 + 4) + 32
+
+    # ---- reduce over ranks (max time) -----------------------------------------------------------
+    red = torch.tensor([dev_ms, e2e_s, kern_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(vsteps), float(rays), float(launches), float(n)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_s_max, kern_ms_max = (float(x) for x in red.cpu())
+    vsteps_all, rays_all, launches_all, n_all = (float(x) for x in tot.cpu())
+    clocks = sampler.summary()
+
+    if rank == 0:
+        value = n_all * args.steps / (dev_ms_max * 1e-3)
+        peak, peak_src = measured_peaks()
+        # roofline of the dominant kernel (k_gain) on THIS rank: algorithmic bytes per launch / launch time
+        steps_per_launch = vsteps / max(1, kern_launches)
+        ach = steps_per_launch * ALGO_BYTES_PER_STEP / (kern_ms / max(1, kern_launches) * 1e-3) / 1e9
+        out = {
+            "metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 frustum planes + f32 DDA + i32 voxel index (bit-exact vs reference arithmetic)",
+            "data": "synthetic",
+            "config": {"workload": f"{args.config}: {cfg.bounds_max[0]}x{cfg.bounds_max[1]}x{cfg.bounds_max[2]} m synthetic TSDF+ESDF, "
+                                   f"{cfg.voxel_size} m voxels, {cfg.vps}^3 blocks, {cfg.hfov_deg}x{cfg.vfov_deg} deg FOV, "
+                                   f"{cfg.far_m} m range, {n_per} candidates per GPU with ESDF edge check "
+                                   f"(radius {cfg.robot_radius:.4f} m, overshoot {cfg.overshoot} m)",
+                       "candidates_total": int(n_all), "map_blocks": nb, "l2": "flushed between steps (256 MiB write)",
+                       "kernel_variant": args.variant, "parallelism": f"candidates sharded over {world} GPU(s), map replicated",
+                       "map_broadcast_ms_setup": map_broadcast_ms, "setup_s": setup_s},
+            "rays_per_s": rays_all / (dev_ms_max * 1e-3), "voxel_steps_per_s": vsteps_all / (dev_ms_max * 1e-3),
+            "voxel_steps_per_viewpoint": vsteps_all / max(1.0, n_all * args.steps),
+            "e2e": {"value": n_all * e2e_steps / e2e_s_max, "unit": "viewpoints/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "kernel": "k_gain (ray sweep)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": steps_per_launch * ALGO_BYTES_PER_STEP,
+                         "avg_launch_ms": kern_ms / max(1, kern_launches),
+                         "kernel_share_of_step": kern_ms / dev_ms if dev_ms > 0 else None,
+                         "note": "8 B per executed voxel-step (SURVEY.md 8d); the map is L2/L1 resident so real DRAM traffic is far lower"},
+            "clocks": clocks,
+            "best": winner if winner is not None else {"index": int(d_best.view(torch.int64)[0].item())},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, cfg, h_pos, h_seg)
+        print(json.dumps(out), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, cfg, h_pos, h_seg):
+    """Oracle (port of the reference arithmetic) timed on the host cores of this box, bounded sample."""
+    from nbv_exploration_planner_b200 import synth
+    m = synth.make_map(args.config)
+    o, lt, le = load_oracle_ctx(m, m.camera())
+    cores = os.cpu_count() or 1
+    sample = min(len(h_pos), args.cpu_sample or 1000)
+    one = min(len(h_pos), 24)
+    dt1, st1 = time_oracle(o, lt, le, cfg, h_pos[:one], h_seg[:one], 1)
+    best = None
+    for _ in range(2):
+        dt, st = time_oracle(o, lt, le, cfg, h_pos[:sample], h_seg[:sample], cores)
+        if best is None or dt < best[0]:
+            best = (dt, st)
+    return {"value": sample / best[0], "unit": "viewpoints/s", "cores": cores, "kind": "port",
+            "sample": f"first {sample} candidates of the same workload, all {cores} host threads, best of 2",
+            "voxel_steps_per_s": best[1] / best[0],
+            "single_thread": {"value": one / dt1, "voxel_steps_per_s": st1 / dt1, "sample": f"first {one} candidates, 1 thread"}}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

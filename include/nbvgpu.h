@@ -175,6 +175,11 @@ int nbvgpu_check_motion(nbvgpu_ctx* ctx, int esdf_layer, double robot_radius, co
 
 /* ---- introspection ---------------------------------------------------------------------- */
 int nbvgpu_get_stats(nbvgpu_ctx* ctx, nbvgpu_stats* out);
+/* CUDA-event timing of the ray-sweep kernel (the dominant kernel): when enabled every launch is
+ * bracketed by events on the context stream; nbvgpu_profile_collect synchronises, returns the summed
+ * device time in ms and the number of launches since the last collect, and resets the list. */
+int nbvgpu_set_profiling(nbvgpu_ctx* ctx, int enable);
+int nbvgpu_profile_collect(nbvgpu_ctx* ctx, double* gain_kernel_ms, uint64_t* launches);
 /* Selects the gain kernel variant (0 = default/fastest, 1 = plain exact FP64 frustum test with
  * {distance,weight} tile loads); both produce identical counts.  For A/B measurement only. */
 int nbvgpu_set_kernel_variant(nbvgpu_ctx* ctx, int variant);

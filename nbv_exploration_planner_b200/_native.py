@@ -124,6 +124,8 @@ def lib() -> C.CDLL:
     L.nbvgpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.nbvgpu_set_kernel_variant.argtypes = [vp, C.c_int]
     L.nbvgpu_debug_classifier_mismatches.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.nbvgpu_set_profiling.argtypes = [vp, C.c_int]
+    L.nbvgpu_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -147,5 +149,5 @@ ABI_SYMBOLS = [
     "nbvgpu_set_camera", "nbvgpu_gain_eval", "nbvgpu_gain_eval_device", "nbvgpu_optimized_gain",
     "nbvgpu_gain_eval_best", "nbvgpu_gain_eval_best_device", "nbvgpu_check_segments",
     "nbvgpu_check_segments_device", "nbvgpu_check_motion", "nbvgpu_get_stats", "nbvgpu_set_kernel_variant",
-    "nbvgpu_debug_classifier_mismatches",
+    "nbvgpu_debug_classifier_mismatches", "nbvgpu_set_profiling", "nbvgpu_profile_collect",
 ]

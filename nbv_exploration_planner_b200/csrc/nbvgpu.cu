@@ -136,6 +136,10 @@ struct nbvgpu_ctx {
   int variant = 0;
   int sm_count = 148;
   int max_smem_optin = 0;
+  // optional CUDA-event timing of the ray-sweep kernel (nbvgpu_set_profiling)
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+  size_t prof_used = 0;
 };
 
 namespace {
@@ -336,12 +340,26 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   if (!T.filter_ok) variant = 1;
   const unsigned grid = (unsigned)(n * (size_t)(360 / yc));
   cudaError_t e;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  if (ctx->profiling) {
+    if (ctx->prof_used == ctx->prof_events.size()) {
+      cudaEvent_t a0, a1;
+      CK(cudaEventCreate(&a0));
+      CK(cudaEventCreate(&a1));
+      ctx->prof_events.emplace_back(a0, a1);
+    }
+    ev0 = ctx->prof_events[ctx->prof_used].first;
+    ev1 = ctx->prof_events[ctx->prof_used].second;
+    ctx->prof_used++;
+    CK(cudaEventRecord(ev0, ctx->stream));
+  }
   switch (variant) {
     case 1: e = launch_gain<1>(a, smem, grid, ctx->stream); break;
     case 2: e = launch_gain<2>(a, smem, grid, ctx->stream); break;
     case 3: e = launch_gain<3>(a, smem, grid, ctx->stream); break;
     default: e = launch_gain<0>(a, smem, grid, ctx->stream); break;
   }
+  if (ev1) cudaEventRecord(ev1, ctx->stream);
   CK(e);
   ctx->stats.kernel_launches++;
   BestYawArgs b;
@@ -450,6 +468,10 @@ void nbvgpu_destroy(nbvgpu_ctx* ctx) {
     for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
                       &ctx->d_free, &ctx->d_aux, &ctx->d_best})
       b->release();
+    for (auto& pr : ctx->prof_events) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   }
   delete ctx;
@@ -888,6 +910,31 @@ int nbvgpu_debug_classifier_mismatches(nbvgpu_ctx* ctx, uint64_t* out) {
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaMemcpy(t, ctx->d_totals, sizeof(t), cudaMemcpyDeviceToHost));
   *out = t[3];
+  return NBVGPU_OK;
+}
+
+int nbvgpu_set_profiling(nbvgpu_ctx* ctx, int enable) {
+  if (!ctx) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  ctx->profiling = enable != 0;
+  ctx->prof_used = 0;
+  return NBVGPU_OK;
+}
+
+int nbvgpu_profile_collect(nbvgpu_ctx* ctx, double* gain_kernel_ms, uint64_t* launches) {
+  if (!ctx || !gain_kernel_ms || !launches) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  CK(cudaStreamSynchronize(ctx->stream));
+  double total = 0.0;
+  for (size_t i = 0; i < ctx->prof_used; ++i) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->prof_events[i].first, ctx->prof_events[i].second));
+    total += ms;
+  }
+  *gain_kernel_ms = total;
+  *launches = ctx->prof_used;
+  ctx->prof_used = 0;
   return NBVGPU_OK;
 }
 

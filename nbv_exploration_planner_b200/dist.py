@@ -1,0 +1,94 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the GPU box,
+gloo in the CPU tests).
+
+The path shards by *candidates* (SURVEY.md 8e): every rank holds a replica of the map mirror and
+evaluates a contiguous block of the candidate list; there is no collective on the data path of the
+evaluation itself.  Two small exchanges surround it:
+
+  * ``broadcast_blocks``  -- once per planning step rank 0 packs the changed blocks (keys + tile
+    payload) into one device buffer and broadcasts it; every rank applies it with the same
+    insert/scatter kernels (``nbvgpu_layer_update_device``), so the replicas stay identical.
+  * ``gather_best``       -- each rank reduces its shard to one {score, global index, gain, yaw}
+    record on the device (``nbvgpu_gain_eval_best_device``); the 32-byte records are all-gathered
+    and every rank picks the winner with the reference's tie-break (first strict maximum in
+    candidate order, rrt.cpp:243-246).
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous blocks of ceil(n / world) candidates per rank (keeps tree-order locality)."""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def broadcast_blocks(keys: Optional[np.ndarray], payload: Optional[np.ndarray], payload_words_per_block: int,
+                     device: torch.device, src: int = 0, group=None):
+    """Broadcast changed blocks from `src`.  Returns (n_blocks, d_keys int32[n][3], d_payload f32[n][words])."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if rank == src:
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        n = len(keys)
+    else:
+        n = 0
+    if world > 1:
+        hdr = torch.tensor([n], dtype=torch.int64, device=device)
+        dist.broadcast(hdr, src, group=group)
+        n = int(hdr.item())
+    if n == 0:
+        return 0, None, None
+    # one buffer: [keys as float32 bit patterns | payload] so a single collective moves everything
+    words = 3 + payload_words_per_block
+    if rank == src:
+        buf_h = np.empty((n, words), np.float32)
+        buf_h[:, :3] = keys.view(np.float32)
+        buf_h[:, 3:] = np.ascontiguousarray(payload, np.float32).reshape(n, payload_words_per_block)
+        buf = torch.from_numpy(buf_h)
+        buf = buf.pin_memory().to(device, non_blocking=True) if device.type == "cuda" else buf.clone()
+    else:
+        buf = torch.empty((n, words), dtype=torch.float32, device=device)
+    if world > 1:
+        dist.broadcast(buf, src, group=group)
+    d_keys = buf[:, :3].contiguous().view(torch.int32)
+    d_payload = buf[:, 3:].contiguous()
+    return n, d_keys, d_payload
+
+
+def gather_best(record: torch.Tensor, index_offset: int, group=None) -> dict:
+    """record: float64[4] = (local index or -1, score, gain, yaw) on this rank's device.
+    Returns the global winner: highest score, ties -> lowest global candidate index; index -1 if no
+    rank found a candidate above zero_gain."""
+    rec = record.clone()
+    if rec[0] >= 0:
+        rec[0] += index_offset
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        out = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(out, rec, group=group)
+        allr = torch.stack(out).cpu().numpy()
+    else:
+        allr = rec.cpu().numpy()[None]
+    best = {"index": -1, "score": None, "gain": 0.0, "yaw": 0.0}
+    for idx, score, gain, yaw in allr:
+        if idx < 0:
+            continue
+        if best["index"] < 0 or score > best["score"] or (score == best["score"] and idx < best["index"]):
+            best = {"index": int(idx), "score": float(score), "gain": float(gain), "yaw": float(yaw)}
+    return best
+
+
+def best_record_as_f64(d_best_bytes: torch.Tensor) -> torch.Tensor:
+    """View the 32-byte nbvgpu_best {int64 index, double score, gain, yaw} as float64[4] with the
+    index converted (exact for |index| < 2^53)."""
+    raw = d_best_bytes.view(torch.int64)
+    f = d_best_bytes.view(torch.float64).clone()
+    f[0] = raw[0].to(torch.float64)
+    return f

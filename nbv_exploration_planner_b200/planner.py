@@ -248,6 +248,15 @@ class NbvGpu:
     def set_kernel_variant(self, variant: int) -> None:
         self._ck(self._L.nbvgpu_set_kernel_variant(self._h, variant))
 
+    def set_profiling(self, enable: bool) -> None:
+        self._ck(self._L.nbvgpu_set_profiling(self._h, int(enable)))
+
+    def profile_collect(self):
+        """(summed ray-sweep kernel ms, launches) since the last collect (CUDA events on the context stream)."""
+        ms, n = C.c_double(0.0), C.c_uint64(0)
+        self._ck(self._L.nbvgpu_profile_collect(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def classifier_mismatches(self) -> int:
         out = C.c_uint64(0)
         self._ck(self._L.nbvgpu_debug_classifier_mismatches(self._h, C.byref(out)))

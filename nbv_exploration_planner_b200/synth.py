@@ -66,6 +66,13 @@ CONFIGS["tiny"] = SynthConfig("tiny", (0, 0, 0), (8, 8, 3), 0.2, 3.0, 16, "pilla
                               obs_radius=3.5, traj_points=4, traj_step=2.0, vicinity=2.5)
 
 
+def camera_for(c: SynthConfig, **kw) -> CameraParams:
+    """Camera of a configuration: README default mount (0.1 m forward, pitched about +y), exploration
+    box = map bounds, gains (free, occupied, unmapped) = (0, 0, 1) unless overridden."""
+    return CameraParams.mount(pitch_deg=c.pitch_deg, t_BC=(0.1, 0.0, 0.0), hfov_deg=c.hfov_deg, vfov_deg=c.vfov_deg,
+                              near_m=c.near_m, far_m=c.far_m, bbx_min=c.bounds_min, bbx_max=c.bounds_max, **kw)
+
+
 @dataclass
 class SynthMap:
     cfg: SynthConfig
@@ -78,9 +85,7 @@ class SynthMap:
     trajectory: np.ndarray           # [nt][3] float64
 
     def camera(self, **kw) -> CameraParams:
-        c = self.cfg
-        return CameraParams.mount(pitch_deg=c.pitch_deg, t_BC=(0.1, 0.0, 0.0), hfov_deg=c.hfov_deg, vfov_deg=c.vfov_deg,
-                                  near_m=c.near_m, far_m=c.far_m, bbx_min=c.bounds_min, bbx_max=c.bounds_max, **kw)
+        return camera_for(self.cfg, **kw)
 
     def sha256(self) -> str:
         h = hashlib.sha256()

@@ -1,0 +1,51 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/nbvgpu.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from nbv_exploration_planner_b200 import _native as N
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "nbvgpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(nbvgpu_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    N.build()
+    lib = ctypes.CDLL(N.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in nbvgpu.h but not exported"
+    assert sorted(N.ABI_SYMBOLS) == syms
+
+
+def test_version_string():
+    lib = N.lib()
+    assert b"sm_100a" in lib.nbvgpu_version()
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device the product path must fail loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from nbv_exploration_planner_b200 import NbvGpu, NbvGpuError
+    with pytest.raises(NbvGpuError) as e:
+        NbvGpu(0)
+    assert e.value.code == N.ERR_NO_DEVICE
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "nbv_exploration_planner_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "nbv_oracle" not in txt and "nbvo_" not in txt, f
