@@ -196,7 +196,10 @@ def run_ours(args):
     cfg = synth.CONFIGS[args.config]
     n_per = args.candidates or cfg.n_candidates
     g = NbvGpu(local)
-    g.set_stream(torch.cuda.current_stream().cuda_stream)
+    # one explicit stream for everything: torch events, NCCL collectives and the library's kernels
+    work_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(work_stream)
+    g.set_stream(work_stream.cuda_stream)
     g.set_kernel_variant(args.variant)
 
     # ---- setup (untimed): map on rank 0 -> NCCL broadcast -> every replica; candidates ------------

@@ -98,7 +98,7 @@ typedef struct {
 int nbvgpu_create(int device, nbvgpu_ctx** out);
 void nbvgpu_destroy(nbvgpu_ctx* ctx);
 /* Use the caller's cudaStream_t (passed as void*) for all subsequent work; NULL restores the
- * library-owned stream. */
+ * library-owned stream (pass cudaStreamLegacy / cudaStreamPerThread to name the default streams). */
 int nbvgpu_set_stream(nbvgpu_ctx* ctx, void* cuda_stream);
 int nbvgpu_synchronize(nbvgpu_ctx* ctx);
 const char* nbvgpu_last_error(nbvgpu_ctx* ctx);

@@ -136,8 +136,57 @@ __device__ __forceinline__ bool exact_in_frustum(const double* pl, int yc, int j
   return true;
 }
 
-template <int VARIANT>
-__global__ void __launch_bounds__(kGainThreads) k_gain(const GainArgs a) {
+// CTA prologue, part (b): per-yaw frames (rrt.cpp:369-385, camera_model.cpp:87-94,119-160,280-289).
+// Kept out of line so that its FP64 register appetite does not set the register budget of the
+// ray loop.
+__device__ __noinline__ void build_yaw_frame(const double* __restrict__ A, const double* __restrict__ B,
+                                             const float* __restrict__ cs, double vs_inv, double* s_pl, double* s_rd,
+                                             float* s_st, float* s_csf, int* s_um, unsigned* s_cnt, int yc, int j, double px,
+                                             double py, double pz) {
+  // A, B, cs already point at this yaw's table rows
+  const D3 p{px, py, pz};
+  const D3 t = d3add(p, D3{B[0], B[1], B[2]});  // camera position
+  D3 c[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k] = d3add(D3{A[3 * k], A[3 * k + 1], A[3 * k + 2]}, t);
+  store_plane(s_pl, yc, j, 0, c[0], c[2], c[1]);  // near
+  store_plane(s_pl, yc, j, 1, c[4], c[5], c[6]);  // far
+  store_plane(s_pl, yc, j, 2, c[3], c[6], c[2]);  // left
+  store_plane(s_pl, yc, j, 3, c[0], c[5], c[4]);  // right
+  store_plane(s_pl, yc, j, 4, c[3], c[4], c[7]);  // top
+  store_plane(s_pl, yc, j, 5, c[2], c[6], c[5]);  // bottom
+  const D3 ud = d3sub(c[4], c[5]);                 // rrt.cpp:382
+  const D3 us = d3normalized(ud);                  // :383
+  const int um = (int)ceil(dmul(__dsqrt_rn(d3dot(ud, ud)), vs_inv));  // :384
+  const D3 d21 = d3sub(c[6], c[5]);
+  const D3 vc{__ddiv_rn(d21.x, 2.0), __ddiv_rn(d21.y, 2.0), __ddiv_rn(d21.z, 2.0)};  // :385
+  s_rd[0 * yc + j] = c[5].x; s_rd[1 * yc + j] = c[5].y; s_rd[2 * yc + j] = c[5].z;
+  s_rd[3 * yc + j] = us.x;   s_rd[4 * yc + j] = us.y;   s_rd[5 * yc + j] = us.z;
+  s_rd[6 * yc + j] = vc.x;   s_rd[7 * yc + j] = vc.y;   s_rd[8 * yc + j] = vc.z;
+  s_st[0 * yc + j] = __double2float_rn(dmul(t.x, vs_inv));  // :408-409
+  s_st[1 * yc + j] = __double2float_rn(dmul(t.y, vs_inv));
+  s_st[2 * yc + j] = __double2float_rn(dmul(t.z, vs_inv));
+  s_csf[0 * yc + j] = cs[0];
+  s_csf[1 * yc + j] = cs[1];
+  s_um[j] = um;
+  s_cnt[0 * yc + j] = 0u; s_cnt[1 * yc + j] = 0u; s_cnt[2 * yc + j] = 0u;
+}
+
+// Camera-frame coordinates of a point given as (float) voxel offsets from g0 (classifier math).
+__device__ __forceinline__ void to_camera(const FilterConst& F, float vs_f, float dx, float dy, float dz, float noffx,
+                                          float noffy, float noffz, float cy, float sy, float& xc, float& yk, float& zk) {
+  const float rx = fmaf(dx, vs_f, noffx), ry = fmaf(dy, vs_f, noffy), rz = fmaf(dz, vs_f, noffz);
+  const float x1 = fmaf(sy, ry, cy * rx);
+  const float y1 = fmaf(cy, ry, -(sy * rx));
+  xc = fmaf(F.R[0], x1, fmaf(F.R[1], y1, fmaf(F.R[2], rz, F.t[0])));
+  yk = fmaf(F.R[3], x1, fmaf(F.R[4], y1, fmaf(F.R[5], rz, F.t[1])));
+  zk = fmaf(F.R[6], x1, fmaf(F.R[7], y1, fmaf(F.R[8], rz, F.t[2])));
+}
+
+// VARIANT: see the header comment.  LV: log2(voxels per side) as a compile-time constant (0 = take
+// it from the layer at run time).
+template <int VARIANT, int LV>
+__global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   constexpr bool kFilter = (VARIANT != 1);
   constexpr bool kStatusBits = (VARIANT == 0 || VARIANT == 2);
   constexpr bool kParanoid = (VARIANT == 2);
@@ -147,13 +196,12 @@ __global__ void __launch_bounds__(kGainThreads) k_gain(const GainArgs a) {
   __shared__ int s_umax;
   __shared__ unsigned long long s_steps;
   __shared__ unsigned int s_mismatch;
-  __shared__ int s_bad;
 
   const int chunks = 360 / yc;
   const int v = blockIdx.x / chunks;
   const int chunk = blockIdx.x - v * chunks;
   const int tid = threadIdx.x;
-  const int lv = a.L.log2vps;
+  const int lv = LV ? LV : a.L.log2vps;
   const int vm = (1 << lv) - 1;
 
   const double px = a.pos[3 * v], py = a.pos[3 * v + 1], pz = a.pos[3 * v + 2];
@@ -164,7 +212,6 @@ __global__ void __launch_bounds__(kGainThreads) k_gain(const GainArgs a) {
     s_umax = 0;
     s_steps = 0ull;
     s_mismatch = 0u;
-    s_bad = bad ? 1 : 0;
   }
   if (bad) {
     for (int j = tid; j < yc; j += blockDim.x)
@@ -181,48 +228,28 @@ __global__ void __launch_bounds__(kGainThreads) k_gain(const GainArgs a) {
     const int ix = i % a.gnx, iy = (i / a.gnx) % a.gny, iz = i / (a.gnx * a.gny);
     S.grid[i] = probe_block(a.L, b0x + ix, b0y + iy, b0z + iz);
   }
-  // (b) per-yaw frames (rrt.cpp:369-385, camera_model.cpp:87-94,119-160,280-289).
+  // (b) per-yaw frames.
   for (int j = tid; j < yc; j += blockDim.x) {
     const int y = chunk * yc + j;
-    const double* A = a.A + (size_t)y * 24;
-    const D3 p{px, py, pz};
-    const D3 t = d3add(p, D3{a.B[3 * y], a.B[3 * y + 1], a.B[3 * y + 2]});  // camera position
-    D3 c[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) c[k] = d3add(D3{A[3 * k], A[3 * k + 1], A[3 * k + 2]}, t);
-    store_plane(S.pl, yc, j, 0, c[0], c[2], c[1]);  // near
-    store_plane(S.pl, yc, j, 1, c[4], c[5], c[6]);  // far
-    store_plane(S.pl, yc, j, 2, c[3], c[6], c[2]);  // left
-    store_plane(S.pl, yc, j, 3, c[0], c[5], c[4]);  // right
-    store_plane(S.pl, yc, j, 4, c[3], c[4], c[7]);  // top
-    store_plane(S.pl, yc, j, 5, c[2], c[6], c[5]);  // bottom
-    const D3 ud = d3sub(c[4], c[5]);                 // rrt.cpp:382
-    const D3 us = d3normalized(ud);                  // :383
-    const int um = (int)ceil(dmul(__dsqrt_rn(d3dot(ud, ud)), a.vs_inv));  // :384
-    const D3 d21 = d3sub(c[6], c[5]);
-    const D3 vc{__ddiv_rn(d21.x, 2.0), __ddiv_rn(d21.y, 2.0), __ddiv_rn(d21.z, 2.0)};  // :385
-    S.rd[0 * yc + j] = c[5].x; S.rd[1 * yc + j] = c[5].y; S.rd[2 * yc + j] = c[5].z;
-    S.rd[3 * yc + j] = us.x;   S.rd[4 * yc + j] = us.y;   S.rd[5 * yc + j] = us.z;
-    S.rd[6 * yc + j] = vc.x;   S.rd[7 * yc + j] = vc.y;   S.rd[8 * yc + j] = vc.z;
-    S.st[0 * yc + j] = __double2float_rn(dmul(t.x, a.vs_inv));  // :408-409
-    S.st[1 * yc + j] = __double2float_rn(dmul(t.y, a.vs_inv));
-    S.st[2 * yc + j] = __double2float_rn(dmul(t.z, a.vs_inv));
-    S.csf[0 * yc + j] = a.cs[2 * y];
-    S.csf[1 * yc + j] = a.cs[2 * y + 1];
-    S.um[j] = um;
-    S.cnt[0 * yc + j] = 0u; S.cnt[1 * yc + j] = 0u; S.cnt[2 * yc + j] = 0u;
+    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, yc, j, px, py,
+                    pz);
   }
   __syncthreads();
   for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
   __syncthreads();
-  const int umax = s_umax;
-  const int n_rays = umax * yc;
+  const int n_rays = s_umax * yc;
+  const bool use_grid = gn > 0;
+  // grid index of block (bx,by,bz) = (bz*gny + by)*gnx + bx + gbase
+  const int gbase = -((b0z * a.gny + b0y) * a.gnx + b0x);
 
   // Offset of the candidate inside its voxel (classifier works relative to g0).
   const float noffx = -__double2float_rn(px - (double)g0x * a.vs);
   const float noffy = -__double2float_rn(py - (double)g0y * a.vs);
   const float noffz = -__double2float_rn(pz - (double)g0z * a.vs);
   const FilterConst& F = a.F;
+  // "Surely in view" slack: a voxel corner is within sqrt(3) voxels of the ray point at which the
+  // voxel is entered; 1.8 voxels + classifier margin + float slop of the start point.
+  const float slack = 1.8f * a.vs_f + F.m + 1e-4f;
 
   const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   unsigned long long my_steps = 0ull;
@@ -235,109 +262,141 @@ __global__ void __launch_bounds__(kGainThreads) k_gain(const GainArgs a) {
     if (r >= n_rays || u >= S.um[j]) continue;
 
     // ---- ray end point (rrt.cpp:396,410-411) and RayCaster setup (integrator_utils.cc:127-179)
-    float s[3], e[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      s[k] = S.st[k * yc + j];
-      const double pos = dadd(dadd(S.rd[k * yc + j], dmul(dmul((double)u, S.rd[(3 + k) * yc + j]), a.vs)), S.rd[(6 + k) * yc + j]);
-      e[k] = __double2float_rn(dmul(pos, a.vs_inv));
-    }
     int g[3], sg[3];
     float t[3], dt[3];
     int len = 0;
+    float tlo = 0.0f, thi = 3.0e38f;  // parameter interval in which the visited voxel is surely in view
+    float e3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      g[k] = (int)floorf(__fadd_rn(s[k], 1e-6f));
-      const int ei = (int)floorf(__fadd_rn(e[k], 1e-6f));
+      const float sk = S.st[k * yc + j];
+      const double pos = dadd(dadd(S.rd[k * yc + j], dmul(dmul((double)u, S.rd[(3 + k) * yc + j]), a.vs)), S.rd[(6 + k) * yc + j]);
+      const float ek = __double2float_rn(dmul(pos, a.vs_inv));
+      e3[k] = ek;
+      g[k] = (int)floorf(__fadd_rn(sk, 1e-6f));
+      const int ei = (int)floorf(__fadd_rn(ek, 1e-6f));
       len += abs(ei - g[k]);
-      const float rr = __fsub_rn(e[k], s[k]);
+      const float rr = __fsub_rn(ek, sk);
       sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
-      const float shifted = __fsub_rn(s[k], (float)g[k]);
+      const float shifted = __fsub_rn(sk, (float)g[k]);
       const float dist = __fsub_rn((float)max(0, sg[k]), shifted);
       t[k] = __fdiv_rn(dist, rr);           // +-inf / NaN when rr == 0, as in the reference
       dt[k] = __fdiv_rn((float)sg[k], rr);
+      if (kFilter) {
+        // exploration box: gmin <= g <= gmax is implied by  gmin + 1.01 <= s + t*r <= gmax - 0.01
+        const float lo = (float)a.gmin[k] + 1.01f - sk, hi = ((float)a.gmin[k] + (float)a.gspan[k]) - 0.01f - sk;
+        if (rr != 0.0f) {
+          const float qa = lo / rr, qb = hi / rr;
+          tlo = fmaxf(tlo, fminf(qa, qb));
+          thi = fminf(thi, fmaxf(qa, qb));
+        } else if (!(lo <= 0.0f && hi >= 0.0f)) {
+          thi = -1.0f;
+        }
+      }
     }
-    float fd[3] = {(float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z)};
-    const float fs[3] = {(float)sg[0], (float)sg[1], (float)sg[2]};
-    const float cy = S.csf[j], sy = S.csf[yc + j];
+    if (kFilter) {
+      // frustum: camera-frame coordinates grow linearly from ~0 at the camera to Pc(end) at t = 1
+      float xe, ye, ze;
+      to_camera(F, a.vs_f, e3[0] - (float)g0x, e3[1] - (float)g0y, e3[2] - (float)g0z, noffx, noffy, noffz, S.csf[j],
+                S.csf[yc + j], xe, ye, ze);
+      const float dh = fmaf(F.th, xe, -fabsf(ye)), dv = fmaf(F.tv, xe, -fabsf(ze));
+      if (xe > 0.0f && dh > 0.0f && dv > 0.0f) {
+        const float sc = slack / F.m;  // margins scale with the plane normalisation
+        tlo = fmaxf(tlo, (F.nearp + slack) / xe);
+        tlo = fmaxf(tlo, (F.mh * sc) / dh);
+        tlo = fmaxf(tlo, (F.mv * sc) / dv);
+        thi = fminf(thi, (F.farp - slack) / xe);
+      } else {
+        thi = -1.0f;
+      }
+      tlo = fmaf(fabsf(tlo), 1e-5f, tlo) + 1e-6f;
+      thi = fmaf(fabsf(thi), -1e-5f, thi) - 1e-6f;
+    }
 
     unsigned nu = 0, nf = 0, no = 0;
     int cbx = INT_MIN, cby = 0, cbz = 0, cslot = -1;
+    float tcur = 0.0f;
     int step = 0;
     for (; step <= len; ++step) {
       // ---- in-view test (camera_model.cpp:191-201) on the voxel corner g * vs
-      bool inview = (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
-                    (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
-      if (inview) {
-        if (kFilter) {
-          const float rx = fmaf(fd[0], a.vs_f, noffx), ry = fmaf(fd[1], a.vs_f, noffy), rz = fmaf(fd[2], a.vs_f, noffz);
-          const float x1 = fmaf(sy, ry, cy * rx);
-          const float y1 = fmaf(cy, ry, -(sy * rx));
-          const float xc = fmaf(F.R[0], x1, fmaf(F.R[1], y1, fmaf(F.R[2], rz, F.t[0])));
-          const float yk = fmaf(F.R[3], x1, fmaf(F.R[4], y1, fmaf(F.R[5], rz, F.t[1])));
-          const float zk = fmaf(F.R[6], x1, fmaf(F.R[7], y1, fmaf(F.R[8], rz, F.t[2])));
-          const float s0 = xc - F.nearp, s1 = F.farp - xc;
-          const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
-          const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
-          const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
-          if (kParanoid) {
-            const bool ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-            if ((sure_in && !ex) || (sure_out && ex)) ++my_mismatch;
-            inview = ex;
-          } else if (sure_in) {
-            inview = true;
-          } else if (sure_out) {
-            inview = false;
+      bool inview;
+      const bool sure = kFilter && (tcur > tlo) && (tcur < thi);
+      if (sure && !kParanoid) {
+        inview = true;
+      } else {
+        inview = (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+                 (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
+        if (kParanoid && sure && !inview) ++my_mismatch;
+        if (inview) {
+          if (kFilter) {
+            float xc, yk, zk;
+            to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
+                      S.csf[yc + j], xc, yk, zk);
+            const float s0 = xc - F.nearp, s1 = F.farp - xc;
+            const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
+            const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
+            const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
+            if (kParanoid) {
+              const bool ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+              if ((sure_in && !ex) || (sure_out && ex) || (sure && !ex)) ++my_mismatch;
+              inview = ex;
+            } else if (sure_in) {
+              inview = true;
+            } else if (sure_out) {
+              inview = false;
+            } else {
+              inview = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+            }
           } else {
             inview = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
           }
-        } else {
-          inview = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
         }
       }
       if (inview) {
         // ---- voxel status (voxblox_manager.cpp:14-33) through the shared-memory slot grid
         const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
-        if (bx != cbx || by != cby || bz != cbz) {
-          cbx = bx; cby = by; cbz = bz;
-          const int ix = bx - b0x, iy = by - b0y, iz = bz - b0z;
-          if ((unsigned)ix < (unsigned)a.gnx && (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz)
-            cslot = S.grid[(iz * a.gny + iy) * a.gnx + ix];
-          else
+        int slot;
+        if (use_grid) {
+          slot = S.grid[(bz * a.gny + by) * a.gnx + bx + gbase];
+        } else {
+          if (bx != cbx || by != cby || bz != cbz) {
+            cbx = bx; cby = by; cbz = bz;
             cslot = probe_block(a.L, bx, by, bz);
+          }
+          slot = cslot;
         }
         unsigned status = 0u;
-        if (cslot >= 0) {
-          const int lin = (g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv));
+        if (slot >= 0) {
+          const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
+          const unsigned nvox = LV ? (1u << (3 * LV)) : (unsigned)a.L.nvox;
           if (kStatusBits) {
-            const uint32_t w = __ldg(a.L.status + (size_t)cslot * (a.L.nvox >> 4) + (lin >> 4));
-            status = (w >> ((lin & 15) * 2)) & 3u;
+            const uint32_t w = __ldg(a.L.status + ((unsigned)slot * (nvox >> 4) + (lin >> 4)));
+            status = (w >> ((lin & 15u) * 2u)) & 3u;
           } else {
-            const float2 vx = __ldg(reinterpret_cast<const float2*>(a.L.tiles) + (size_t)cslot * a.L.nvox + lin);
+            const float2 vx = __ldg(reinterpret_cast<const float2*>(a.L.tiles) + ((size_t)slot * nvox + lin));
             status = tsdf_status(vx.x, vx.y);
           }
         }
-        if (status == 0u) {
-          ++nu;
-        } else if (status == 2u) {
-          ++no;
+        if (status == 2u) {
+          no = 1u;
           ++step;  // this step was executed
           break;
-        } else {
-          ++nf;
         }
+        nu += (status == 0u);
+        nf += (status == 1u);
       }
       // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
       const bool c1 = t[1] < t[0];
       const float bm = c1 ? t[1] : t[0];
       const bool c2 = t[2] < bm;
-      if (c2) {
-        g[2] += sg[2]; t[2] = __fadd_rn(t[2], dt[2]); fd[2] += fs[2];
-      } else if (c1) {
-        g[1] += sg[1]; t[1] = __fadd_rn(t[1], dt[1]); fd[1] += fs[1];
-      } else {
-        g[0] += sg[0]; t[0] = __fadd_rn(t[0], dt[0]); fd[0] += fs[0];
-      }
+      tcur = c2 ? t[2] : bm;  // ray parameter at which the next voxel is entered
+      const bool m0 = !c1 && !c2, m1 = c1 && !c2;
+      g[0] += m0 ? sg[0] : 0;
+      g[1] += m1 ? sg[1] : 0;
+      g[2] += c2 ? sg[2] : 0;
+      t[0] = m0 ? __fadd_rn(t[0], dt[0]) : t[0];
+      t[1] = m1 ? __fadd_rn(t[1], dt[1]) : t[1];
+      t[2] = c2 ? __fadd_rn(t[2], dt[2]) : t[2];
     }
     my_steps += (unsigned long long)step;
     if (nu) atomicAdd(&S.cnt[0 * yc + j], nu);

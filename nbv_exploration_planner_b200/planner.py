@@ -116,8 +116,13 @@ class NbvGpu:
             raise N.NbvGpuError(rc, (self._L.nbvgpu_last_error(self._h) or b"").decode())
 
     def set_stream(self, cuda_stream: Optional[int]) -> None:
-        """Run all subsequent work on ``cuda_stream`` (e.g. ``torch.cuda.current_stream().cuda_stream``)."""
-        self._ck(self._L.nbvgpu_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+        """Run all subsequent work on ``cuda_stream`` (e.g. ``torch.cuda.current_stream().cuda_stream``).
+        ``None`` restores the library-owned stream; handle 0 (torch's default stream) is passed as
+        ``cudaStreamLegacy`` (0x1), because a NULL pointer means "own stream" at the ABI."""
+        if cuda_stream is None:
+            self._ck(self._L.nbvgpu_set_stream(self._h, None))
+        else:
+            self._ck(self._L.nbvgpu_set_stream(self._h, C.c_void_p(cuda_stream if cuda_stream else 1)))
 
     def synchronize(self) -> None:
         self._ck(self._L.nbvgpu_synchronize(self._h))
