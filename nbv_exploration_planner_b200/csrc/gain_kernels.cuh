@@ -102,18 +102,19 @@ struct GainSmem {
   unsigned* cnt;  // [3][yc]
   int* grid;      // [gnz][gny][gnx]
 };
-__device__ __forceinline__ GainSmem carve(unsigned char* base, int yc) {
+// The slot grid sits at offset 0 so that its address is a compile-time constant in the ray loop.
+__device__ __forceinline__ GainSmem carve(unsigned char* base, int yc, int gn) {
   GainSmem s;
-  s.pl = reinterpret_cast<double*>(base);
+  s.grid = reinterpret_cast<int*>(base);
+  s.pl = reinterpret_cast<double*>(base + (((size_t)gn * 4 + 15) & ~(size_t)15));
   s.rd = s.pl + 24 * yc;
   s.st = reinterpret_cast<float*>(s.rd + 9 * yc);
   s.csf = s.st + 3 * yc;
   s.um = reinterpret_cast<int*>(s.csf + 2 * yc);
   s.cnt = reinterpret_cast<unsigned*>(s.um + yc);
-  s.grid = reinterpret_cast<int*>(s.cnt + 3 * yc);
   return s;
 }
-inline size_t gain_smem_bytes(int yc, int gn) { return (size_t)yc * (33 * 8 + 9 * 4) + (size_t)gn * 4 + 16; }
+inline size_t gain_smem_bytes(int yc, int gn) { return (size_t)yc * (33 * 8 + 9 * 4) + (((size_t)gn * 4 + 15) & ~(size_t)15) + 16; }
 
 // Plane::setFromPoints + store (camera_model.cpp:5-11).
 __device__ __forceinline__ void store_plane(double* pl, int yc, int j, int k, const D3& p1, const D3& p2, const D3& p3) {
@@ -184,15 +185,32 @@ __device__ __forceinline__ void to_camera(const FilterConst& F, float vs_f, floa
 }
 
 // VARIANT: see the header comment.  LV: log2(voxels per side) as a compile-time constant (0 = take
-// it from the layer at run time).
-template <int VARIANT, int LV>
+// it from the layer at run time).  GRID: the shared-memory slot grid is in use (false: the reach is
+// too large for shared memory and blocks are probed in the global table with a per-lane cache).
+//
+// In-view decision per step, cheapest first (all exactness-preserving; VARIANT 2 cross-checks every
+// shortcut against the exact test):
+//   * every voxel is entered at a known ray parameter tcur (the DDA's own t); a voxel corner lies
+//     within sqrt(3) voxels of that entry point, and along the ray the signed distance to every
+//     bounding plane is linear in t.  Per ray this gives an interval (tlo, thi) in which the voxel
+//     is surely inside the exploration box and inside every frustum plane except possibly the
+//     nearer of top/bottom, and a tighter bound tlo_v beyond which that plane is sure as well;
+//   * between tlo and tlo_v only that one plane is open: one single-precision plane evaluation
+//     against the FP64 plane's coefficients (margin >> rounding error) settles it;
+//   * past t_out the ray has left the (convex) exploration box for good: the remaining voxels can
+//     contribute nothing and cannot stop the ray, so they are accounted as executed and skipped;
+//   * everything else: integer box test, single-precision classifier in the camera frame, and the
+//     exact FP64 plane tests when the classifier is within its margin.
+template <int VARIANT, int LV, bool GRID>
 __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   constexpr bool kFilter = (VARIANT != 1);
   constexpr bool kStatusBits = (VARIANT == 0 || VARIANT == 2);
   constexpr bool kParanoid = (VARIANT == 2);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int yc = a.yc;
-  const GainSmem S = carve(smem_raw, yc);
+  const int gn = GRID ? a.gnx * a.gny * a.gnz : 0;
+  const GainSmem S = carve(smem_raw, yc, gn);
+  const int* const sgrid = reinterpret_cast<const int*>(smem_raw);
   __shared__ int s_umax;
   __shared__ unsigned long long s_steps;
   __shared__ unsigned int s_mismatch;
@@ -223,7 +241,6 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   const int b0x = (g0x - a.reach_vox) >> lv, b0y = (g0y - a.reach_vox) >> lv, b0z = (g0z - a.reach_vox) >> lv;
 
   // (a) local block-slot grid: one hash probe per reachable block.
-  const int gn = a.gnx * a.gny * a.gnz;
   for (int i = tid; i < gn; i += blockDim.x) {
     const int ix = i % a.gnx, iy = (i / a.gnx) % a.gny, iz = i / (a.gnx * a.gny);
     S.grid[i] = probe_block(a.L, b0x + ix, b0y + iy, b0z + iz);
@@ -238,7 +255,6 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
   __syncthreads();
   const int n_rays = s_umax * yc;
-  const bool use_grid = gn > 0;
   // grid index of block (bx,by,bz) = (bz*gny + by)*gnx + bx + gbase
   const int gbase = -((b0z * a.gny + b0y) * a.gnx + b0x);
 
@@ -265,7 +281,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     int g[3], sg[3];
     float t[3], dt[3];
     int len = 0;
-    float tlo = 0.0f, thi = 3.0e38f;  // parameter interval in which the visited voxel is surely in view
+    float tlo = 0.0f, thi = 3.0e38f, tlo_v = 0.0f, t_out = 3.0e38f;
+    float pa[3] = {0.f, 0.f, 0.f}, pc = 0.f;  // open top/bottom plane, single precision, relative to g0
     float e3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -283,12 +300,16 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       t[k] = __fdiv_rn(dist, rr);           // +-inf / NaN when rr == 0, as in the reference
       dt[k] = __fdiv_rn((float)sg[k], rr);
       if (kFilter) {
-        // exploration box: gmin <= g <= gmax is implied by  gmin + 1.01 <= s + t*r <= gmax - 0.01
-        const float lo = (float)a.gmin[k] + 1.01f - sk, hi = ((float)a.gmin[k] + (float)a.gspan[k]) - 0.01f - sk;
+        // exploration box: gmin <= g <= gmax is implied by  gmin + 1.01 <= s + t*r <= gmax - 0.01,
+        // and g is surely outside once s + t*r has passed the bound by 1.02 in the direction of travel
+        const float bmin = (float)a.gmin[k], bmax = (float)a.gmin[k] + (float)a.gspan[k];
+        const float lo = bmin + 1.01f - sk, hi = bmax - 0.01f - sk;
         if (rr != 0.0f) {
           const float qa = lo / rr, qb = hi / rr;
           tlo = fmaxf(tlo, fminf(qa, qb));
           thi = fminf(thi, fmaxf(qa, qb));
+          const float qo = (rr > 0.0f ? (bmax + 1.02f - sk) : (bmin - 0.02f - sk)) / rr;
+          t_out = fminf(t_out, qo);
         } else if (!(lo <= 0.0f && hi >= 0.0f)) {
           thi = -1.0f;
         }
@@ -299,18 +320,30 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       float xe, ye, ze;
       to_camera(F, a.vs_f, e3[0] - (float)g0x, e3[1] - (float)g0y, e3[2] - (float)g0z, noffx, noffy, noffz, S.csf[j],
                 S.csf[yc + j], xe, ye, ze);
-      const float dh = fmaf(F.th, xe, -fabsf(ye)), dv = fmaf(F.tv, xe, -fabsf(ze));
-      if (xe > 0.0f && dh > 0.0f && dv > 0.0f) {
+      const float dh = fmaf(F.th, xe, -fabsf(ye));
+      const float dv_near = fmaf(F.tv, xe, -fabsf(ze)), dv_far = fmaf(F.tv, xe, fabsf(ze));
+      if (xe > 0.0f && dh > 0.0f && dv_far > 0.0f) {
         const float sc = slack / F.m;  // margins scale with the plane normalisation
         tlo = fmaxf(tlo, (F.nearp + slack) / xe);
         tlo = fmaxf(tlo, (F.mh * sc) / dh);
-        tlo = fmaxf(tlo, (F.mv * sc) / dv);
+        tlo = fmaxf(tlo, (F.mv * sc) / dv_far);
         thi = fminf(thi, (F.farp - slack) / xe);
+        tlo_v = dv_near > 0.0f ? (F.mv * sc) / dv_near : 3.0e38f;
       } else {
         thi = -1.0f;
       }
       tlo = fmaf(fabsf(tlo), 1e-5f, tlo) + 1e-6f;
+      tlo_v = fmaf(fabsf(tlo_v), 1e-5f, tlo_v) + 1e-6f;
       thi = fmaf(fabsf(thi), -1e-5f, thi) - 1e-6f;
+      t_out = fmaf(fabsf(t_out), 1e-5f, t_out) + 1e-6f;
+      // the open plane: top (index 4) when the ray ends in the upper half of the frustum, else bottom
+      // (5); s(g) = n.(g*vs) - d = sum_k (n_k*vs)*(g_k - g0_k) + (n.(g0*vs) - d), from the FP64 plane.
+      const int kp = ze >= 0.0f ? 4 : 5;
+      const double nx = S.pl[(4 * kp + 0) * yc + j], ny = S.pl[(4 * kp + 1) * yc + j], nz = S.pl[(4 * kp + 2) * yc + j];
+      pa[0] = __double2float_rn(nx * a.vs);
+      pa[1] = __double2float_rn(ny * a.vs);
+      pa[2] = __double2float_rn(nz * a.vs);
+      pc = __double2float_rn((nx * (double)g0x + ny * (double)g0y + nz * (double)g0z) * a.vs - S.pl[(4 * kp + 3) * yc + j]);
     }
 
     unsigned nu = 0, nf = 0, no = 0;
@@ -319,14 +352,33 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     int step = 0;
     for (; step <= len; ++step) {
       // ---- in-view test (camera_model.cpp:191-201) on the voxel corner g * vs
-      bool inview;
-      const bool sure = kFilter && (tcur > tlo) && (tcur < thi);
-      if (sure && !kParanoid) {
-        inview = true;
-      } else {
+      bool inview = false, decided = false;
+      if (kFilter) {
+        if (tcur > tlo && tcur < thi) {
+          if (tcur > tlo_v) {
+            inview = true;
+            decided = true;
+          } else {
+            const float sv = fmaf(pa[0], (float)(g[0] - g0x), fmaf(pa[1], (float)(g[1] - g0y), fmaf(pa[2], (float)(g[2] - g0z), pc)));
+            if (sv > F.m) {
+              inview = true;
+              decided = true;
+            } else if (sv < -F.m) {
+              decided = true;
+            }
+          }
+        } else if (tcur > t_out) {
+          if (!kParanoid) {
+            step = len + 1;  // the reference walks the remaining voxels; none of them is in view
+            break;
+          }
+          decided = true;
+        }
+      }
+      if (!decided || kParanoid) {
+        const bool fast = inview;
         inview = (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
                  (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
-        if (kParanoid && sure && !inview) ++my_mismatch;
         if (inview) {
           if (kFilter) {
             float xc, yk, zk;
@@ -338,7 +390,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
             const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
             if (kParanoid) {
               const bool ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-              if ((sure_in && !ex) || (sure_out && ex) || (sure && !ex)) ++my_mismatch;
+              if ((sure_in && !ex) || (sure_out && ex)) ++my_mismatch;
               inview = ex;
             } else if (sure_in) {
               inview = true;
@@ -351,13 +403,14 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
             inview = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
           }
         }
+        if (kParanoid && decided && fast != inview) ++my_mismatch;
       }
       if (inview) {
         // ---- voxel status (voxblox_manager.cpp:14-33) through the shared-memory slot grid
         const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
         int slot;
-        if (use_grid) {
-          slot = S.grid[(bz * a.gny + by) * a.gnx + bx + gbase];
+        if (GRID) {
+          slot = sgrid[(bz * a.gny + by) * a.gnx + bx + gbase];
         } else {
           if (bx != cbx || by != cby || bz != cbz) {
             cbx = bx; cby = by; cbz = bz;

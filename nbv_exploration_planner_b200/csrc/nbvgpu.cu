@@ -269,17 +269,19 @@ int check_position_range(const nbvgpu_ctx* ctx, const LayerHost* L, size_t n, co
   return NBVGPU_OK;
 }
 
-template <int V, int LV>
+template <int V, int LV, bool GRID>
 cudaError_t launch_gain_lv(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_gain<V, LV><<<grid, kGainThreads, smem, s>>>(a);
+  k_gain<V, LV, GRID><<<grid, kGainThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
 template <int V>
 cudaError_t launch_gain(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
   // 16 voxels per side (the Voxblox default) gets compile-time index math
-  return a.L.log2vps == 4 ? launch_gain_lv<V, 4>(a, smem, grid, s) : launch_gain_lv<V, 0>(a, smem, grid, s);
+  if (a.gnx > 0)
+    return a.L.log2vps == 4 ? launch_gain_lv<V, 4, true>(a, smem, grid, s) : launch_gain_lv<V, 0, true>(a, smem, grid, s);
+  return a.L.log2vps == 4 ? launch_gain_lv<V, 4, false>(a, smem, grid, s) : launch_gain_lv<V, 0, false>(a, smem, grid, s);
 }
 
 // Enqueue: ray sweep + best yaw for n resident positions.  d_per_yaw may be null (scratch used).
