@@ -60,6 +60,7 @@ struct GainArgs {
   int gmin[3];
   unsigned gspan[3];
   int reach_vox;
+  int unknown_slot;   // tile index of the all-unknown / zero tile (== max_blocks)
   int gnx, gny, gnz;  // local block grid dimensions
   int yc;             // yaws per CTA (divides 360)
   int n;
@@ -243,7 +244,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   // (a) local block-slot grid: one hash probe per reachable block.
   for (int i = tid; i < gn; i += blockDim.x) {
     const int ix = i % a.gnx, iy = (i / a.gnx) % a.gny, iz = i / (a.gnx * a.gny);
-    S.grid[i] = probe_block(a.L, b0x + ix, b0y + iy, b0z + iz);
+    const int sl = probe_block(a.L, b0x + ix, b0y + iy, b0z + iz);
+    S.grid[i] = sl < 0 ? a.unknown_slot : sl;
   }
   // (b) per-yaw frames.
   for (int j = tid; j < yc; j += blockDim.x) {
@@ -300,18 +302,12 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       t[k] = __fdiv_rn(dist, rr);           // +-inf / NaN when rr == 0, as in the reference
       dt[k] = __fdiv_rn((float)sg[k], rr);
       if (kFilter) {
-        // exploration box: gmin <= g <= gmax is implied by  gmin + 1.01 <= s + t*r <= gmax - 0.01,
-        // and g is surely outside once s + t*r has passed the bound by 1.02 in the direction of travel
+        // g is surely outside the (convex) exploration box once s + t*r has passed a bound by
+        // 1.02 voxels in the direction of travel
         const float bmin = (float)a.gmin[k], bmax = (float)a.gmin[k] + (float)a.gspan[k];
-        const float lo = bmin + 1.01f - sk, hi = bmax - 0.01f - sk;
         if (rr != 0.0f) {
-          const float qa = lo / rr, qb = hi / rr;
-          tlo = fmaxf(tlo, fminf(qa, qb));
-          thi = fminf(thi, fmaxf(qa, qb));
           const float qo = (rr > 0.0f ? (bmax + 1.02f - sk) : (bmin - 0.02f - sk)) / rr;
           t_out = fminf(t_out, qo);
-        } else if (!(lo <= 0.0f && hi >= 0.0f)) {
-          thi = -1.0f;
         }
       }
     }
@@ -346,40 +342,39 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       pc = __double2float_rn((nx * (double)g0x + ny * (double)g0y + nz * (double)g0z) * a.vs - S.pl[(4 * kp + 3) * yc + j]);
     }
 
-    unsigned nu = 0, nf = 0, no = 0;
-    int cbx = INT_MIN, cby = 0, cbz = 0, cslot = -1;
+    unsigned acc = 0u, occ = 0u;  // acc: unknown count (bits 0-15) | free count (bits 16-31); < 65536 steps per ray
+    int cbx = INT_MIN, cby = 0, cbz = 0, cslot = a.unknown_slot;
     float tcur = 0.0f;
     int step = 0;
     for (; step <= len; ++step) {
       // ---- in-view test (camera_model.cpp:191-201) on the voxel corner g * vs
-      bool inview = false, decided = false;
-      if (kFilter) {
-        if (tcur > tlo && tcur < thi) {
+      // exploration box first (integer thresholds, exact) ...
+      bool inview = (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+                    (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
+      if (kFilter && !inview && tcur > t_out) {
+        if (kParanoid) {
+          // keep walking and verify that no later voxel re-enters the box
+        } else {
+          step = len + 1;  // the reference walks the remaining voxels; none of them can be in view
+          break;
+        }
+      }
+      if (kParanoid && inview && tcur > t_out) ++my_mismatch;
+      // ... then the frustum, cheapest decision first
+      if (inview) {
+        bool decided = false, fin = false;
+        if (kFilter && tcur > tlo && tcur < thi) {
           if (tcur > tlo_v) {
-            inview = true;
+            fin = true;
             decided = true;
           } else {
             const float sv = fmaf(pa[0], (float)(g[0] - g0x), fmaf(pa[1], (float)(g[1] - g0y), fmaf(pa[2], (float)(g[2] - g0z), pc)));
-            if (sv > F.m) {
-              inview = true;
-              decided = true;
-            } else if (sv < -F.m) {
-              decided = true;
-            }
+            fin = sv > F.m;
+            decided = fin || sv < -F.m;
           }
-        } else if (tcur > t_out) {
-          if (!kParanoid) {
-            step = len + 1;  // the reference walks the remaining voxels; none of them is in view
-            break;
-          }
-          decided = true;
         }
-      }
-      if (!decided || kParanoid) {
-        const bool fast = inview;
-        inview = (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
-                 (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
-        if (inview) {
+        if (!decided || kParanoid) {
+          bool ex;
           if (kFilter) {
             float xc, yk, zk;
             to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
@@ -389,24 +384,25 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
             const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
             const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
             if (kParanoid) {
-              const bool ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-              if ((sure_in && !ex) || (sure_out && ex)) ++my_mismatch;
-              inview = ex;
+              ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+              if ((sure_in && !ex) || (sure_out && ex) || (decided && fin != ex)) ++my_mismatch;
             } else if (sure_in) {
-              inview = true;
+              ex = true;
             } else if (sure_out) {
-              inview = false;
+              ex = false;
             } else {
-              inview = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+              ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
             }
           } else {
-            inview = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+            ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
           }
+          fin = ex;
         }
-        if (kParanoid && decided && fast != inview) ++my_mismatch;
+        inview = fin;
       }
       if (inview) {
-        // ---- voxel status (voxblox_manager.cpp:14-33) through the shared-memory slot grid
+        // ---- voxel status (voxblox_manager.cpp:14-33) through the shared-memory slot grid; blocks that
+        // are not allocated map to the all-unknown tile (slot == max_blocks)
         const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
         int slot;
         if (GRID) {
@@ -415,28 +411,26 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
           if (bx != cbx || by != cby || bz != cbz) {
             cbx = bx; cby = by; cbz = bz;
             cslot = probe_block(a.L, bx, by, bz);
+            if (cslot < 0) cslot = a.unknown_slot;
           }
           slot = cslot;
         }
-        unsigned status = 0u;
-        if (slot >= 0) {
-          const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
-          const unsigned nvox = LV ? (1u << (3 * LV)) : (unsigned)a.L.nvox;
-          if (kStatusBits) {
-            const uint32_t w = __ldg(a.L.status + ((unsigned)slot * (nvox >> 4) + (lin >> 4)));
-            status = (w >> ((lin & 15u) * 2u)) & 3u;
-          } else {
-            const float2 vx = __ldg(reinterpret_cast<const float2*>(a.L.tiles) + ((size_t)slot * nvox + lin));
-            status = tsdf_status(vx.x, vx.y);
-          }
+        const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
+        const unsigned nvox = LV ? (1u << (3 * LV)) : (unsigned)a.L.nvox;
+        unsigned status;
+        if (kStatusBits) {
+          const uint32_t w = __ldg(a.L.status + ((unsigned)slot * (nvox >> 4) + (lin >> 4)));
+          status = (w >> ((lin & 15u) * 2u)) & 3u;
+        } else {
+          const float2 vx = __ldg(reinterpret_cast<const float2*>(a.L.tiles) + ((size_t)slot * nvox + lin));
+          status = tsdf_status(vx.x, vx.y);
         }
         if (status == 2u) {
-          no = 1u;
+          occ = 1u;
           ++step;  // this step was executed
           break;
         }
-        nu += (status == 0u);
-        nf += (status == 1u);
+        acc += 1u << (status << 4);  // unknown in the low half, free in the high half
       }
       // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
       const bool c1 = t[1] < t[0];
@@ -452,9 +446,9 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       t[2] = c2 ? __fadd_rn(t[2], dt[2]) : t[2];
     }
     my_steps += (unsigned long long)step;
-    if (nu) atomicAdd(&S.cnt[0 * yc + j], nu);
-    if (nf) atomicAdd(&S.cnt[1 * yc + j], nf);
-    if (no) atomicAdd(&S.cnt[2 * yc + j], no);
+    if (acc & 0xFFFFu) atomicAdd(&S.cnt[0 * yc + j], acc & 0xFFFFu);
+    if (acc >> 16) atomicAdd(&S.cnt[1 * yc + j], acc >> 16);
+    if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);
   }
   // ---- CTA epilogue
 #pragma unroll

@@ -320,6 +320,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   const double reach = std::ceil(ctx->tab.reach_m * a.vs_inv) + 4.0;
   if (!(reach < (double)kMaxReachVox)) return fail(ctx, NBVGPU_ERR_RANGE, "gain range / voxel size too large");
   a.reach_vox = (int)reach;
+  a.unknown_slot = (int)L->max_blocks;
   int gdim = ((2 * a.reach_vox) >> L->log2vps) + 2;
   // yaws per CTA: enough CTAs to fill the machine for small batches, bigger chunks otherwise.
   static const int kYc[] = {40, 20, 10, 8, 4};
@@ -524,8 +525,15 @@ int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, si
   L->cap = 1u << L->log2cap;
   const size_t tile_bytes = (size_t)L->nvox * (kind == NBVGPU_LAYER_TSDF ? 8 : 4);
   bool ok = cudaMalloc(&L->d_table, (size_t)L->cap * sizeof(HashEntry)) == cudaSuccess;
-  ok = ok && cudaMalloc(&L->d_tiles, tile_bytes * max_blocks) == cudaSuccess;
-  if (kind == NBVGPU_LAYER_TSDF) ok = ok && cudaMalloc(&L->d_status, (size_t)(L->nvox / 16) * 4 * max_blocks) == cudaSuccess;
+  // one extra tile at index max_blocks stays zero: {distance 0, weight 0} / status "unknown", the
+  // value every unallocated block reads as (voxblox_manager.cpp:30-32)
+  ok = ok && cudaMalloc(&L->d_tiles, tile_bytes * (max_blocks + 1)) == cudaSuccess;
+  ok = ok && cudaMemsetAsync((char*)L->d_tiles + tile_bytes * max_blocks, 0, tile_bytes, ctx->stream) == cudaSuccess;
+  if (kind == NBVGPU_LAYER_TSDF) {
+    const size_t sbytes = (size_t)(L->nvox / 16) * 4;
+    ok = ok && cudaMalloc(&L->d_status, sbytes * (max_blocks + 1)) == cudaSuccess;
+    ok = ok && cudaMemsetAsync((char*)L->d_status + sbytes * max_blocks, 0, sbytes, ctx->stream) == cudaSuccess;
+  }
   ok = ok && cudaMalloc(&L->d_free_list, sizeof(int) * max_blocks) == cudaSuccess;
   ok = ok && cudaMalloc(&L->d_free_top, sizeof(int) * 2) == cudaSuccess;
   ok = ok && cudaMalloc(&L->d_nblocks, sizeof(unsigned long long)) == cudaSuccess;
