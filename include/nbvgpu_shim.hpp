@@ -1,0 +1,121 @@
+// nbvgpu_shim.hpp -- header-only C++ shims with the reference's own signatures, over the C ABI.
+//
+// Drop these next to the reference's classes: the planner keeps calling
+//   double RrtTree::optimized_gain(Pose& state)            nbveplanner/src/rrt.cpp:351
+//   double RrtTree::gain(Pose& state)                      nbveplanner/src/rrt.cpp:481
+//   bool   HighResManager::checkMotion<T>(start, end)      nbveplanner/include/nbveplanner/voxblox_manager.h:89
+// and the bodies become one-line calls into libnbvgpu.so.  No Eigen / ROS / Voxblox headers are
+// needed here: `Pose` is anything indexable with [0..3] (Eigen::Vector4d), `Point` anything with
+// x(), y(), z() (Eigen::Vector3d), `Layer`/`Block` anything with the Voxblox accessors used below.
+//
+// Error behaviour follows the reference's convention (glog CHECK aborts + bool returns): a failing
+// ABI call throws std::runtime_error from the shim, which a maintainer may turn into LOG(FATAL).
+#ifndef NBVGPU_SHIM_HPP_
+#define NBVGPU_SHIM_HPP_
+
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "nbvgpu.h"
+
+namespace nbvgpu_shim {
+
+inline void check(nbvgpu_ctx* ctx, int rc, const char* what) {
+  if (rc != NBVGPU_OK) throw std::runtime_error(std::string(what) + ": " + nbvgpu_last_error(ctx) + " (" + std::to_string(rc) + ")");
+}
+
+/// Owns the context and the two layers the planner reads: the low-resolution TSDF (gain) and the
+/// high-resolution ESDF (collision), nbvep.cpp:21-27.
+class GpuMap {
+ public:
+  GpuMap(int device, float lowres_voxel_size, int lowres_vps, size_t lowres_max_blocks, float hires_voxel_size, int hires_vps,
+         size_t hires_max_blocks) {
+    check(nullptr, nbvgpu_create(device, &ctx_), "nbvgpu_create");
+    check(ctx_, nbvgpu_layer_create(ctx_, NBVGPU_LAYER_TSDF, lowres_voxel_size, lowres_vps, lowres_max_blocks, &tsdf_), "layer_create");
+    check(ctx_, nbvgpu_layer_create(ctx_, NBVGPU_LAYER_ESDF, hires_voxel_size, hires_vps, hires_max_blocks, &esdf_), "layer_create");
+  }
+  ~GpuMap() { nbvgpu_destroy(ctx_); }
+  GpuMap(const GpuMap&) = delete;
+  GpuMap& operator=(const GpuMap&) = delete;
+
+  nbvgpu_ctx* ctx() const { return ctx_; }
+  int tsdf_layer() const { return tsdf_; }
+  int esdf_layer() const { return esdf_; }
+
+#ifdef NBVGPU_SHIM_WITH_VOXBLOX
+  /// Upload hook for the L0 -> L1 boundary (after TsdfServer::integratePointcloud, tsdf_server.cc:414,
+  /// and EsdfServer::updateEsdf, esdf_server.cc:196): send every block whose Update::kMap bit is set
+  /// (Layer::getAllUpdatedBlocks, layer.h:194-203) in the reference's own serialisation
+  /// (Block::serializeToIntegers, block.cc:159-234), clear the bit, commit.  Needs the Voxblox
+  /// headers, so it is only compiled inside the reference tree.
+  template <class VoxelType>
+  void uploadUpdatedBlocks(voxblox::Layer<VoxelType>* layer, int gpu_layer) {
+    voxblox::BlockIndexList updated;
+    layer->getAllUpdatedBlocks(voxblox::Update::kMap, &updated);
+    std::vector<int32_t> keys;
+    std::vector<uint32_t> payload, one;
+    for (const voxblox::BlockIndex& bi : updated) {
+      typename voxblox::Block<VoxelType>::Ptr block = layer->getBlockPtrByIndex(bi);
+      if (!block) continue;
+      block->serializeToIntegers(&one);
+      keys.insert(keys.end(), {bi.x(), bi.y(), bi.z()});
+      payload.insert(payload.end(), one.begin(), one.end());
+      block->updated().reset(voxblox::Update::kMap);
+    }
+    if (!keys.empty()) uploadSerialized(gpu_layer, keys.size() / 3, keys.data(), payload.data());
+  }
+#endif
+  /// Raw variant for callers that already hold serialised blocks (e.g. a voxblox_msgs/Layer message).
+  void uploadSerialized(int gpu_layer, size_t n_blocks, const int32_t* keys, const uint32_t* data) {
+    check(ctx_, nbvgpu_layer_update(ctx_, gpu_layer, n_blocks, keys, data, NBVGPU_PACK_VOXBLOX), "layer_update");
+    check(ctx_, nbvgpu_commit(ctx_), "commit");
+  }
+  void clear() {  // VoxbloxManager::clear, voxblox_manager.cpp:92-95,150-154
+    check(ctx_, nbvgpu_layer_clear(ctx_, tsdf_), "layer_clear");
+    check(ctx_, nbvgpu_layer_clear(ctx_, esdf_), "layer_clear");
+  }
+
+ private:
+  nbvgpu_ctx* ctx_ = nullptr;
+  int tsdf_ = -1, esdf_ = -1;
+};
+
+/// What nbvePlanner::setUpCamera (nbvep.cpp:40-61) configures, as plain numbers.
+inline void setUpCamera(GpuMap& map, double hfov_deg, double vfov_deg, double sensor_min_range, double gain_range,
+                        const double q_CB_wxyz[4], const double t_CB[3], const double bbx_min[3], const double bbx_max[3],
+                        double gain_free, double gain_occupied, double gain_unmapped) {
+  nbvgpu_camera c;
+  std::memset(&c, 0, sizeof(c));
+  c.hfov_deg = hfov_deg; c.vfov_deg = vfov_deg; c.near_m = sensor_min_range; c.far_m = gain_range;
+  for (int k = 0; k < 4; ++k) c.q_CB[k] = q_CB_wxyz[k];
+  for (int k = 0; k < 3; ++k) { c.t_CB[k] = t_CB[k]; c.bbx_min[k] = bbx_min[k]; c.bbx_max[k] = bbx_max[k]; }
+  c.gain_free = gain_free; c.gain_occupied = gain_occupied; c.gain_unmapped = gain_unmapped;
+  c.sum_all_yaws = (hfov_deg == 360.0) ? 1 : 0;  // CameraModel::hasHorizontalLimit(), rrt.cpp:215-219
+  check(map.ctx(), nbvgpu_set_camera(map.ctx(), &c), "set_camera");
+}
+
+/// double RrtTree::optimized_gain(Pose& state) / double RrtTree::gain(Pose& state): returns the gain and
+/// writes the chosen yaw into state[3] (0 for gain()), exactly as rrt.cpp:477-478 / :577-578.
+template <class Pose>
+inline double optimized_gain(GpuMap& map, Pose& state) {
+  double s[4] = {state[0], state[1], state[2], state[3]};
+  double g = 0.0;
+  check(map.ctx(), nbvgpu_optimized_gain(map.ctx(), map.tsdf_layer(), s, &g), "optimized_gain");
+  state[3] = s[3];
+  return g;
+}
+
+/// bool HighResManager::checkMotion<T>(const T& start, const T& end): true = free.
+template <class T>
+inline bool checkMotion(GpuMap& map, double robot_radius, const T& start, const T& end) {
+  const double a[3] = {start.x(), start.y(), start.z()}, b[3] = {end.x(), end.y(), end.z()};
+  int free_seg = 0;
+  check(map.ctx(), nbvgpu_check_motion(map.ctx(), map.esdf_layer(), robot_radius, a, b, &free_seg), "check_motion");
+  return free_seg != 0;
+}
+
+}  // namespace nbvgpu_shim
+#endif  // NBVGPU_SHIM_HPP_
