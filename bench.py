@@ -171,7 +171,13 @@ def run_reference(args):
                          "sample": f"first {sample} of {n_total} candidates per step, {steps} steps, all {cores} host threads"},
         "e2e": {"value": value, "unit": "viewpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+def emit(obj):
+    out = globals().get("_json_out") or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -251,9 +257,8 @@ def run_ours(args):
     def step_device():
         g.check_segments_device(le, cfg.robot_radius, n, d_seg, d_free)
         g.gain_eval_best_device(lt, n, d_pos, d_pyaw, d_dist, d_free, v_max, dyaw_max, zero_gain, d_best, d_gain, d_yaw)
-        if world > 1:
-            return nd.gather_best(nd.best_record_as_f64(d_best), lo)
-        return None
+        # every step ends with the winner known on the host (one 32 B record per rank)
+        return nd.gather_best_raw(d_best, n_per * world)
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -353,11 +358,11 @@ def run_ours(args):
                          "kernel_share_of_step": kern_ms / dev_ms if dev_ms > 0 else None,
                          "note": "8 B per executed voxel-step (SURVEY.md 8d); the map is L2/L1 resident so real DRAM traffic is far lower"},
             "clocks": clocks,
-            "best": winner if winner is not None else {"index": int(d_best.view(torch.int64)[0].item())},
+            "best": winner,
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, cfg, h_pos, h_seg)
-        print(json.dumps(out), flush=True)
+        emit(out)
     g.close()
     if world > 1:
         dist.destroy_process_group()
@@ -384,6 +389,11 @@ def cpu_baseline(args, cfg, h_pos, h_seg):
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: anything else written to fd 1 (NCCL banners, library
+    # chatter) is sent to stderr; the JSON goes to the saved copy of the original stdout.
+    _json_fd = os.dup(1)
+    os.dup2(2, 1)
+    _json_out = os.fdopen(_json_fd, "w")
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)

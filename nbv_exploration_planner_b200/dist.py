@@ -62,27 +62,53 @@ def broadcast_blocks(keys: Optional[np.ndarray], payload: Optional[np.ndarray], 
     return n, d_keys, d_payload
 
 
-def gather_best(record: torch.Tensor, index_offset: int, group=None) -> dict:
-    """record: float64[4] = (local index or -1, score, gain, yaw) on this rank's device.
-    Returns the global winner: highest score, ties -> lowest global candidate index; index -1 if no
-    rank found a candidate above zero_gain."""
-    rec = record.clone()
-    if rec[0] >= 0:
-        rec[0] += index_offset
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if world > 1:
-        out = [torch.empty_like(rec) for _ in range(world)]
-        dist.all_gather(out, rec, group=group)
-        allr = torch.stack(out).cpu().numpy()
-    else:
-        allr = rec.cpu().numpy()[None]
+def _pick(records) -> dict:
+    """records: iterable of (global index or -1, score, gain, yaw).  Highest score wins, ties -> lowest
+    global candidate index (= the reference's first strict maximum in candidate order)."""
     best = {"index": -1, "score": None, "gain": 0.0, "yaw": 0.0}
-    for idx, score, gain, yaw in allr:
+    for idx, score, gain, yaw in records:
         if idx < 0:
             continue
         if best["index"] < 0 or score > best["score"] or (score == best["score"] and idx < best["index"]):
             best = {"index": int(idx), "score": float(score), "gain": float(gain), "yaw": float(yaw)}
     return best
+
+
+def gather_best(record: torch.Tensor, index_offset: int, group=None) -> dict:
+    """record: float64[4] = (local index or -1, score, gain, yaw) on this rank's device.
+    Returns the global winner; index -1 if no rank found a candidate above zero_gain."""
+    rec = record.detach().cpu().clone()
+    if rec[0] >= 0:
+        rec[0] += index_offset
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        rec = rec.to(record.device)
+        out = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(out, rec, group=group)
+        allr = torch.stack(out).cpu().numpy()
+    else:
+        allr = rec.numpy()[None]
+    return _pick(allr)
+
+
+def gather_best_raw(d_best: torch.Tensor, n_total: int, group=None) -> dict:
+    """d_best: the 32-byte nbvgpu_best record {int64 local index, double score, gain, yaw} as a uint8[32]
+    device tensor, exactly as nbvgpu_gain_eval_best_device wrote it.  One all-gather of the raw records
+    (NCCL over NVLink), one device->host read, decode + shard offsets + tie-break on the host."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        out = torch.empty(world * 32, dtype=torch.uint8, device=d_best.device)
+        dist.all_gather_into_tensor(out, d_best, group=group)
+    else:
+        out = d_best
+    raw = out.cpu().numpy()
+    idx = raw.view(np.int64).reshape(world, 4)[:, 0]
+    val = raw.view(np.float64).reshape(world, 4)[:, 1:]
+    recs = []
+    for r in range(world):
+        lo, _ = shard_bounds(n_total, world, r)
+        recs.append((int(idx[r]) + lo if idx[r] >= 0 else -1, val[r, 0], val[r, 1], val[r, 2]))
+    return _pick(recs)
 
 
 def best_record_as_f64(d_best_bytes: torch.Tensor) -> torch.Tensor:

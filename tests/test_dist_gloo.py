@@ -80,6 +80,12 @@ def _worker(rank, world, port, q):
     tie = torch.tensor([0.0, 5.0, 1.0, 0.5], dtype=torch.float64)
     best_tie = nd.gather_best(tie, lo)
     none = nd.gather_best(torch.tensor([-1.0, 0.0, 0.0, 0.0], dtype=torch.float64), lo)
+    # raw 32-byte nbvgpu_best records (the form the GPU path gathers): same winner
+    raw = torch.zeros(32, dtype=torch.uint8)
+    raw.view(torch.int64)[0] = int(rec[0])
+    raw.view(torch.float64)[1:] = rec[1:]
+    best_raw = nd.gather_best_raw(raw, 23)
+    assert best_raw == best, (best_raw, best)
     q.put((rank, lo, hi, n_t, n_e, best, best_tie, none, o.num_blocks(lt)))
     dist.destroy_process_group()
 
