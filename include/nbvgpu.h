@@ -180,13 +180,15 @@ int nbvgpu_get_stats(nbvgpu_ctx* ctx, nbvgpu_stats* out);
  * device time in ms and the number of launches since the last collect, and resets the list. */
 int nbvgpu_set_profiling(nbvgpu_ctx* ctx, int enable);
 int nbvgpu_profile_collect(nbvgpu_ctx* ctx, double* gain_kernel_ms, uint64_t* launches);
-/* Selects the gain kernel variant (0 = default/fastest, 1 = plain exact FP64 frustum test with
- * {distance,weight} tile loads); both produce identical counts.  For A/B measurement only. */
+/* Selects the ray-sweep kernel variant; all produce identical counts (A/B measurement and tests):
+ *  0 default: dense shared-memory status volume when it fits (16^3 blocks), else slot-grid path
+ *  1 plain transcription: FP64 plane tests on every step + {distance, weight} tile loads
+ *  2 variant 0 with every shortcut cross-checked against the exact test (mismatch counter)
+ *  3 slot-grid path reading {distance, weight} tiles instead of the 2-bit status tiles
+ *  4 slot-grid path (never the dense volume);  5 = 4 with cross-checks */
 int nbvgpu_set_kernel_variant(nbvgpu_ctx* ctx, int variant);
 /* Number of single-precision frustum-classifier decisions contradicted by the exact FP64 plane test,
- * counted by kernel variant 2 (0 = default, 1 = FP64 planes on every step + {distance,weight} loads,
- * 2 = variant 0 with every classifier decision cross-checked, 3 = classifier + {distance,weight}
- * loads).  Must be 0; the tests assert it. */
+ * counted by kernel variants 2 and 5.  Must be 0; the tests assert it. */
 int nbvgpu_debug_classifier_mismatches(nbvgpu_ctx* ctx, uint64_t* out);
 
 #ifdef __cplusplus

@@ -122,4 +122,46 @@ void box_thresholds(const nbvgpu_camera& cam, double vs, int gmin[3], int gmax[3
   }
 }
 
+
+bool dense_volume_bounds(const CameraTables& tab, double vs, int yc, int vmin[][3], int dims[3]) {
+  // Every voxel a ray of yaw y visits lies in the box spanned by its start voxel and end voxel
+  // (+-1 for the DDA's rounding at the very end).  Relative to the candidate position p, the start is
+  // B[y] and the end points of the ray column are A[y][5] + v_center + B[y] + u * u_slope * vs,
+  // u in [0, u_max): a straight line, so its extremes are at the two ends.  index(p + rel) - index(p) is
+  // floor(rel / vs) or that + 1, hence the asymmetric padding.
+  const int chunks = 360 / yc;
+  int dmax[3] = {0, 0, 0};
+  for (int c = 0; c < chunks; ++c) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int y = c * yc; y < (c + 1) * yc; ++y) {
+      const double* a4 = tab.A[y][4];
+      const double* a5 = tab.A[y][5];
+      const double* a6 = tab.A[y][6];
+      double ud[3], n2 = 0.0;
+      for (int k = 0; k < 3; ++k) { ud[k] = a4[k] - a5[k]; n2 += ud[k] * ud[k]; }
+      const double n = std::sqrt(n2);
+      if (!(n > 0.0)) return false;
+      const double umax = std::ceil(n / vs) + 1.0;
+      for (int k = 0; k < 3; ++k) {
+        const double s = tab.B[y][k];
+        const double e0 = a5[k] + (a6[k] - a5[k]) / 2.0 + tab.B[y][k];
+        const double e1 = e0 + umax * (ud[k] / n) * vs;
+        lo[k] = std::fmin(lo[k], std::fmin(s, std::fmin(e0, e1)));
+        hi[k] = std::fmax(hi[k], std::fmax(s, std::fmax(e0, e1)));
+      }
+    }
+    for (int k = 0; k < 3; ++k) {
+      const double a = std::floor(lo[k] / vs) - 2.0, b = std::floor(hi[k] / vs) + 3.0;
+      if (!(std::fabs(a) < 1e6) || !(std::fabs(b) < 1e6)) return false;
+      vmin[c][k] = (int)a;
+      const int ext = (int)(b - a) + 1;
+      if (ext > dmax[k]) dmax[k] = ext;
+    }
+  }
+  dims[0] = (dmax[0] + 15) / 16 + 1;  // 16-voxel words along x, worst-case alignment
+  dims[1] = dmax[1];
+  dims[2] = dmax[2];
+  return true;
+}
+
 }  // namespace nbvgpu_host

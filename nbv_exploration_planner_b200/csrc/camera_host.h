@@ -25,5 +25,11 @@ bool build_camera_tables(const nbvgpu_camera& cam, CameraTables* out);
 // Integer voxel-index thresholds equivalent to the exploration-box test on (double)g * vs.
 void box_thresholds(const nbvgpu_camera& cam, double vs, int gmin[3], int gmax[3]);
 
+// Conservative extent of the voxels visited by the rays of each chunk of `yc` consecutive yaws,
+// relative to the voxel that contains the candidate position: vmin[chunk][3] (lower corner, padded)
+// and common dims = {16-voxel words along x, voxels along y, voxels along z}.  Used to size the dense
+// shared-memory status volume of k_gain_dense.  false if the camera geometry is degenerate.
+bool dense_volume_bounds(const CameraTables& tab, double vs, int yc, int vmin[][3], int dims[3]);
+
 }  // namespace nbvgpu_host
 #endif

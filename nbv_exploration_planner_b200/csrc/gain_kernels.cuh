@@ -64,6 +64,10 @@ struct GainArgs {
   int gnx, gny, gnz;  // local block grid dimensions
   int yc;             // yaws per CTA (divides 360)
   int n;
+  // dense shared-memory status volume (k_gain_dense): per-chunk lower corner relative to the
+  // candidate's voxel, and the common dimensions {16-voxel words along x, voxels along y, z}
+  const int* vmin;    // [360 / yc][3]
+  int vxw, vey, vez;
   FilterConst F;
 };
 
@@ -451,6 +455,289 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);
   }
   // ---- CTA epilogue
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    my_mismatch += __shfl_xor_sync(0xffffffffu, my_mismatch, o);
+  }
+  if (lane == 0) {
+    atomicAdd(&s_steps, my_steps);
+    if (kParanoid) atomicAdd(&s_mismatch, my_mismatch);
+  }
+  __syncthreads();
+  for (int i = tid; i < 3 * yc; i += blockDim.x) {
+    const int k = i / yc, j = i - k * yc;
+    a.per_yaw[((size_t)v * 360 + chunk * yc + j) * 3 + k] = S.cnt[k * yc + j];
+  }
+  if (tid == 0) {
+    unsigned long long rays = 0ull;
+    for (int j = 0; j < yc; ++j) rays += (unsigned long long)S.um[j];
+    if (a.steps) atomicAdd(a.steps + v, s_steps);
+    atomicAdd(a.totals + 0, rays);
+    atomicAdd(a.totals + 1, s_steps);
+    if (kParanoid && s_mismatch) atomicAdd(a.totals + 3, (unsigned long long)s_mismatch);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_gain_dense: same sweep, but the CTA first copies the 2-bit status of every voxel its rays can
+// reach into a dense shared-memory volume [vez][vey][vxw words] (x word-aligned to the 16-voxel
+// block rows, so whole status-tile words are copied), with the exploration box folded in as a 4th
+// value (3 = outside the box: neither counted nor able to stop the ray).  A lane addresses the volume
+// with ONE integer: the bit address P = ((z*vey + y)*vxw)*32 + 2*x; a DDA step along x/y/z adds
+// +-2 / +-32*vxw / +-32*vxw*vey (the x carry into the next word comes for free), and the status is
+// (vol[P >> 5] >> (P & 31)) & 3.  The ray loop therefore has no box test, no block lookup, no tile
+// address arithmetic and no global load.  Requires 16 voxels per side and a volume that fits the
+// shared-memory budget; otherwise k_gain (slot grid / hash probes) is used.  VARIANT 2 cross-checks
+// every fetched status against the direct (box test + status tile) path and every frustum shortcut
+// against the exact planes.
+// ---------------------------------------------------------------------------------------------
+inline size_t dense_smem_bytes(int yc, int gn, int nvol) {
+  return (((size_t)nvol * 4 + 15) & ~(size_t)15) + gain_smem_bytes(yc, gn);
+}
+
+template <int VARIANT>
+__global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a) {
+  constexpr bool kParanoid = (VARIANT == 2);
+  constexpr int lv = 4, vm = 15;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int yc = a.yc;
+  const int gn = a.gnx * a.gny * a.gnz;
+  const int vxw = a.vxw, vey = a.vey, vez = a.vez;
+  const int nvol = vxw * vey * vez;
+  uint32_t* const vol = reinterpret_cast<uint32_t*>(smem_raw);
+  const GainSmem S = carve(smem_raw + (((size_t)nvol * 4 + 15) & ~(size_t)15), yc, gn);
+  __shared__ int s_umax;
+  __shared__ unsigned long long s_steps;
+  __shared__ unsigned int s_mismatch;
+
+  const int chunks = 360 / yc;
+  const int v = blockIdx.x / chunks;
+  const int chunk = blockIdx.x - v * chunks;
+  const int tid = threadIdx.x;
+
+  const double px = a.pos[3 * v], py = a.pos[3 * v + 1], pz = a.pos[3 * v + 2];
+  const double lim = 4194304.0 - (double)a.reach_vox - 2.0;
+  const bool bad = !(fabs(px * a.vs_inv) < lim) || !(fabs(py * a.vs_inv) < lim) || !(fabs(pz * a.vs_inv) < lim);
+  if (tid == 0) {
+    s_umax = 0;
+    s_steps = 0ull;
+    s_mismatch = 0u;
+  }
+  if (bad) {
+    for (int j = tid; j < yc; j += blockDim.x)
+      for (int k = 0; k < 3; ++k) a.per_yaw[((size_t)v * 360 + chunk * yc + j) * 3 + k] = 0u;
+    return;
+  }
+  const int g0x = (int)floor(px * a.vs_inv), g0y = (int)floor(py * a.vs_inv), g0z = (int)floor(pz * a.vs_inv);
+  const int b0x = (g0x - a.reach_vox) >> lv, b0y = (g0y - a.reach_vox) >> lv, b0z = (g0z - a.reach_vox) >> lv;
+  // volume origin (global voxel index); x aligned down to a block row
+  const int x0 = ((g0x + a.vmin[3 * chunk]) >> lv) << lv;
+  const int y0 = g0y + a.vmin[3 * chunk + 1];
+  const int z0 = g0z + a.vmin[3 * chunk + 2];
+
+  // (a) block-slot grid, (b) per-yaw frames
+  for (int i = tid; i < gn; i += blockDim.x) {
+    const int ix = i % a.gnx, iy = (i / a.gnx) % a.gny, iz = i / (a.gnx * a.gny);
+    const int sl = probe_block(a.L, b0x + ix, b0y + iy, b0z + iz);
+    S.grid[i] = sl < 0 ? a.unknown_slot : sl;
+  }
+  for (int j = tid; j < yc; j += blockDim.x) {
+    const int y = chunk * yc + j;
+    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, yc, j, px, py,
+                    pz);
+  }
+  __syncthreads();
+  for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
+  // (c) dense status volume: one status-tile word (16 voxels along x) per thread and iteration
+  for (int w = tid; w < nvol; w += blockDim.x) {
+    const int wx = w % vxw, t2 = w / vxw;
+    const int gy = y0 + t2 % vey, gz = z0 + t2 / vey, gx = x0 + 16 * wx;
+    uint32_t word = 0xFFFFFFFFu;  // 3 = outside the exploration box
+    const long long lo = (long long)a.gmin[0] - gx, hi = lo + (long long)a.gspan[0];  // in-box x range inside the word
+    if ((unsigned)(gy - a.gmin[1]) <= a.gspan[1] && (unsigned)(gz - a.gmin[2]) <= a.gspan[2] && hi >= 0 && lo <= 15) {
+      const int bx = gx >> lv, by = gy >> lv, bz = gz >> lv;
+      const int ix = bx - b0x, iy = by - b0y, iz = bz - b0z;
+      int slot;
+      if ((unsigned)ix < (unsigned)a.gnx && (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz) {
+        slot = S.grid[(iz * a.gny + iy) * a.gnx + ix];
+      } else {
+        slot = probe_block(a.L, bx, by, bz);
+        if (slot < 0) slot = a.unknown_slot;
+      }
+      word = __ldg(a.L.status + ((unsigned)slot * 256u + (unsigned)(((gz & vm) << lv) | (gy & vm))));
+      const int l = lo > 0 ? (int)lo : 0, h = hi < 15 ? (int)hi : 15;
+      const uint32_t below = (1u << (2 * l)) - 1u;                         // voxels < l
+      const uint32_t upto = h == 15 ? 0xFFFFFFFFu : ((1u << (2 * (h + 1))) - 1u);  // voxels <= h
+      word |= below | ~upto;
+    }
+    vol[w] = word;
+  }
+  __syncthreads();
+  const int n_rays = s_umax * yc;
+
+  const float noffx = -__double2float_rn(px - (double)g0x * a.vs);
+  const float noffy = -__double2float_rn(py - (double)g0y * a.vs);
+  const float noffz = -__double2float_rn(pz - (double)g0z * a.vs);
+  const FilterConst& F = a.F;
+  const float slack = 1.8f * a.vs_f + F.m + 1e-4f;
+  const int stride_y = 32 * vxw, stride_z = 32 * vxw * vey;
+
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  unsigned long long my_steps = 0ull;
+  unsigned int my_mismatch = 0u;
+
+  for (int base = warp * 32; base < n_rays; base += nwarps * 32) {
+    const int r = base + lane;
+    const int u = r / yc;
+    const int j = r - u * yc;
+    if (r >= n_rays || u >= S.um[j]) continue;
+
+    int g[3], sg[3];
+    float t[3], dt[3];
+    int len = 0;
+    float tlo = 0.0f, thi = 3.0e38f, tlo_v = 0.0f, t_out = 3.0e38f;
+    float pa[3], pc;
+    float e3[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float sk = S.st[k * yc + j];
+      const double pos = dadd(dadd(S.rd[k * yc + j], dmul(dmul((double)u, S.rd[(3 + k) * yc + j]), a.vs)), S.rd[(6 + k) * yc + j]);
+      const float ek = __double2float_rn(dmul(pos, a.vs_inv));
+      e3[k] = ek;
+      g[k] = (int)floorf(__fadd_rn(sk, 1e-6f));
+      const int ei = (int)floorf(__fadd_rn(ek, 1e-6f));
+      len += abs(ei - g[k]);
+      const float rr = __fsub_rn(ek, sk);
+      sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
+      const float shifted = __fsub_rn(sk, (float)g[k]);
+      const float dist = __fsub_rn((float)max(0, sg[k]), shifted);
+      t[k] = __fdiv_rn(dist, rr);
+      dt[k] = __fdiv_rn((float)sg[k], rr);
+      const float bmin = (float)a.gmin[k], bmax = (float)a.gmin[k] + (float)a.gspan[k];
+      if (rr != 0.0f) {
+        const float qo = (rr > 0.0f ? (bmax + 1.02f - sk) : (bmin - 0.02f - sk)) / rr;
+        t_out = fminf(t_out, qo);
+      }
+    }
+    {
+      float xe, ye, ze;
+      to_camera(F, a.vs_f, e3[0] - (float)g0x, e3[1] - (float)g0y, e3[2] - (float)g0z, noffx, noffy, noffz, S.csf[j],
+                S.csf[yc + j], xe, ye, ze);
+      const float dh = fmaf(F.th, xe, -fabsf(ye));
+      const float dv_near = fmaf(F.tv, xe, -fabsf(ze)), dv_far = fmaf(F.tv, xe, fabsf(ze));
+      if (xe > 0.0f && dh > 0.0f && dv_far > 0.0f) {
+        const float sc = slack / F.m;
+        tlo = fmaxf(tlo, (F.nearp + slack) / xe);
+        tlo = fmaxf(tlo, (F.mh * sc) / dh);
+        tlo = fmaxf(tlo, (F.mv * sc) / dv_far);
+        thi = fminf(thi, (F.farp - slack) / xe);
+        tlo_v = dv_near > 0.0f ? (F.mv * sc) / dv_near : 3.0e38f;
+      } else {
+        thi = -1.0f;
+      }
+      tlo = fmaf(fabsf(tlo), 1e-5f, tlo) + 1e-6f;
+      tlo_v = fmaf(fabsf(tlo_v), 1e-5f, tlo_v) + 1e-6f;
+      thi = fmaf(fabsf(thi), -1e-5f, thi) - 1e-6f;
+      t_out = fmaf(fabsf(t_out), 1e-5f, t_out) + 1e-6f;
+      const int kp = ze >= 0.0f ? 4 : 5;
+      const double nx = S.pl[(4 * kp + 0) * yc + j], ny = S.pl[(4 * kp + 1) * yc + j], nz = S.pl[(4 * kp + 2) * yc + j];
+      pa[0] = __double2float_rn(nx * a.vs);
+      pa[1] = __double2float_rn(ny * a.vs);
+      pa[2] = __double2float_rn(nz * a.vs);
+      pc = __double2float_rn((nx * (double)g0x + ny * (double)g0y + nz * (double)g0z) * a.vs - S.pl[(4 * kp + 3) * yc + j]);
+    }
+    // bit address of the start voxel in the dense volume and the per-axis strides
+    int P = ((g[2] - z0) * vey + (g[1] - y0)) * stride_y + 2 * (g[0] - x0);
+    const int stx = 2 * sg[0], sty = stride_y * sg[1], stz = stride_z * sg[2];
+
+    unsigned acc = 0u, occ = 0u;
+    float tcur = 0.0f;
+    int step = 0;
+    for (; step <= len; ++step) {
+      if (tcur > t_out) {  // left the convex exploration box for good
+        if (!kParanoid) {
+          step = len + 1;
+          break;
+        }
+        if ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+            (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2])
+          ++my_mismatch;
+      }
+      // ---- frustum (camera_model.cpp:194-199), cheapest decision first
+      bool decided = false, fin = false;
+      if (tcur > tlo && tcur < thi) {
+        if (tcur > tlo_v) {
+          fin = true;
+          decided = true;
+        } else {
+          const float sv = fmaf(pa[0], (float)(g[0] - g0x), fmaf(pa[1], (float)(g[1] - g0y), fmaf(pa[2], (float)(g[2] - g0z), pc)));
+          fin = sv > F.m;
+          decided = fin || sv < -F.m;
+        }
+      }
+      if (!decided || kParanoid) {
+        float xc, yk, zk;
+        to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
+                  S.csf[yc + j], xc, yk, zk);
+        const float s0 = xc - F.nearp, s1 = F.farp - xc;
+        const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
+        const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
+        const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
+        bool ex;
+        if (kParanoid) {
+          ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+          if ((sure_in && !ex) || (sure_out && ex) || (decided && fin != ex)) ++my_mismatch;
+        } else if (sure_in) {
+          ex = true;
+        } else if (sure_out) {
+          ex = false;
+        } else {
+          ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+        }
+        fin = ex;
+      }
+      if (fin) {
+        // ---- exploration box + voxel status from the dense volume
+        const uint32_t w = vol[(unsigned)P >> 5];
+        const unsigned status = __funnelshift_r(w, 0u, (unsigned)P) & 3u;
+        if (kParanoid) {
+          unsigned want = 3u;
+          if ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+              (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2]) {
+            int slot = probe_block(a.L, g[0] >> lv, g[1] >> lv, g[2] >> lv);
+            if (slot < 0) slot = a.unknown_slot;
+            const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
+            want = (__ldg(a.L.status + ((unsigned)slot * 256u + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
+          }
+          if (((unsigned)P >> 5) >= (unsigned)nvol || want != status) ++my_mismatch;
+        }
+        if (status == 2u) {
+          occ = 1u;
+          ++step;  // this step was executed
+          break;
+        }
+        acc += (status == 3u) ? 0u : (1u << (status << 4));  // unknown: low half, free: high half
+      }
+      // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
+      const bool c1 = t[1] < t[0];
+      const float bm = c1 ? t[1] : t[0];
+      const bool c2 = t[2] < bm;
+      tcur = c2 ? t[2] : bm;
+      const bool m0 = !c1 && !c2, m1 = c1 && !c2;
+      P += c2 ? stz : (c1 ? sty : stx);
+      g[0] += m0 ? sg[0] : 0;
+      g[1] += m1 ? sg[1] : 0;
+      g[2] += c2 ? sg[2] : 0;
+      t[0] = m0 ? __fadd_rn(t[0], dt[0]) : t[0];
+      t[1] = m1 ? __fadd_rn(t[1], dt[1]) : t[1];
+      t[2] = c2 ? __fadd_rn(t[2], dt[2]) : t[2];
+    }
+    my_steps += (unsigned long long)step;
+    if (acc & 0xFFFFu) atomicAdd(&S.cnt[0 * yc + j], acc & 0xFFFFu);
+    if (acc >> 16) atomicAdd(&S.cnt[1 * yc + j], acc >> 16);
+    if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);

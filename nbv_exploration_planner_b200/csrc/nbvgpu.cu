@@ -8,6 +8,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -136,6 +137,14 @@ struct nbvgpu_ctx {
   int variant = 0;
   int sm_count = 148;
   int max_smem_optin = 0;
+  // dense-volume bounds cache (k_gain_dense): valid for (camera generation, voxel size, yc)
+  DevBuf d_vmin;
+  int vmin_yc = 0;
+  float vmin_vs = 0.f;
+  unsigned long long vmin_gen = ~0ull, cam_gen = 0;
+  int vdims[3] = {0, 0, 0};
+  bool vmin_ok = false;
+  int force_yc = 0;  // NBVGPU_YC environment override (experiments)
   // optional CUDA-event timing of the ray-sweep kernel (nbvgpu_set_profiling)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -277,6 +286,13 @@ cudaError_t launch_gain_lv(const GainArgs& a, size_t smem, unsigned grid, cudaSt
   return cudaGetLastError();
 }
 template <int V>
+cudaError_t launch_gain_dense(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(k_gain_dense<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  k_gain_dense<V><<<grid, kGainThreads, smem, s>>>(a);
+  return cudaGetLastError();
+}
+template <int V>
 cudaError_t launch_gain(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
   // 16 voxels per side (the Voxblox default) gets compile-time index math
   if (a.gnx > 0)
@@ -329,6 +345,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     yc = c;
     if (n * (size_t)(360 / c) >= (size_t)ctx->sm_count * 6) break;
   }
+  if (ctx->force_yc > 0 && 360 % ctx->force_yc == 0 && ctx->force_yc <= 120) yc = ctx->force_yc;
   size_t gn = (size_t)gdim * gdim * gdim;
   size_t smem = gain_smem_bytes(yc, (int)gn);
   if (smem > (size_t)ctx->max_smem_optin || smem > 96 * 1024) {  // fall back to direct hash probes
@@ -346,6 +363,37 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   a.F.m = T.margin; a.F.mh = T.margin_h; a.F.mv = T.margin_v;
   int variant = ctx->variant;
   if (!T.filter_ok) variant = 1;
+  // Dense shared-memory status volume (k_gain_dense) when the layer has 16^3 blocks and the volume of
+  // one yaw chunk fits the budget that still allows 4 CTAs per SM.
+  bool dense = false;
+  a.vmin = nullptr;
+  a.vxw = a.vey = a.vez = 0;
+  if ((variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0) {
+    if (ctx->vmin_gen != ctx->cam_gen || ctx->vmin_yc != yc || ctx->vmin_vs != L->voxel_size) {
+      std::vector<int> vmin((size_t)(360 / yc) * 3);
+      ctx->vmin_ok = nbvgpu_host::dense_volume_bounds(T, a.vs, yc, reinterpret_cast<int(*)[3]>(vmin.data()), ctx->vdims);
+      if (ctx->vmin_ok) {
+        CK(ctx->d_vmin.reserve(vmin.size() * sizeof(int)));
+        CK(cudaMemcpyAsync(ctx->d_vmin.p, vmin.data(), vmin.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));  // vmin is a local vector
+      }
+      ctx->vmin_gen = ctx->cam_gen;
+      ctx->vmin_yc = yc;
+      ctx->vmin_vs = L->voxel_size;
+    }
+    if (ctx->vmin_ok) {
+      const long long nvol = (long long)ctx->vdims[0] * ctx->vdims[1] * ctx->vdims[2];
+      const size_t need = nvol < (1 << 24) ? dense_smem_bytes(yc, (int)gn, (int)nvol) : (size_t)1 << 30;
+      if (need <= 56 * 1024 && need <= (size_t)ctx->max_smem_optin) {
+        dense = true;
+        smem = need;
+        a.vmin = ctx->d_vmin.as<int>();
+        a.vxw = ctx->vdims[0];
+        a.vey = ctx->vdims[1];
+        a.vez = ctx->vdims[2];
+      }
+    }
+  }
   const unsigned grid = (unsigned)(n * (size_t)(360 / yc));
   cudaError_t e;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -363,9 +411,11 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   }
   switch (variant) {
     case 1: e = launch_gain<1>(a, smem, grid, ctx->stream); break;
-    case 2: e = launch_gain<2>(a, smem, grid, ctx->stream); break;
+    case 2: e = dense ? launch_gain_dense<2>(a, smem, grid, ctx->stream) : launch_gain<2>(a, smem, grid, ctx->stream); break;
     case 3: e = launch_gain<3>(a, smem, grid, ctx->stream); break;
-    default: e = launch_gain<0>(a, smem, grid, ctx->stream); break;
+    case 4: e = launch_gain<0>(a, smem, grid, ctx->stream); break;
+    case 5: e = launch_gain<2>(a, smem, grid, ctx->stream); break;
+    default: e = dense ? launch_gain_dense<0>(a, smem, grid, ctx->stream) : launch_gain<0>(a, smem, grid, ctx->stream); break;
   }
   if (ev1) cudaEventRecord(ev1, ctx->stream);
   CK(e);
@@ -445,6 +495,7 @@ int nbvgpu_create(int device, nbvgpu_ctx** out) {
   nbvgpu_ctx* ctx = new nbvgpu_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = std::getenv("NBVGPU_YC")) ctx->force_yc = std::atoi(e);
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   DeviceGuard guard(device);
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -473,6 +524,7 @@ void nbvgpu_destroy(nbvgpu_ctx* ctx) {
     cudaFree(ctx->d_cs);
     cudaFree(ctx->d_totals);
     ctx->h_io.release();
+    ctx->d_vmin.release();
     for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
                       &ctx->d_free, &ctx->d_aux, &ctx->d_best})
       b->release();
@@ -741,6 +793,7 @@ int nbvgpu_set_camera(nbvgpu_ctx* ctx, const nbvgpu_camera* cam) {
   CK(cudaStreamSynchronize(ctx->stream));  // tables may still be in use
   ctx->cam = *cam;
   ctx->tab = tab;
+  ctx->cam_gen++;
   CK(cudaMemcpyAsync(ctx->d_A, ctx->tab.A, sizeof(ctx->tab.A), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_B, ctx->tab.B, sizeof(ctx->tab.B), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->d_cs, ctx->tab.cs, sizeof(ctx->tab.cs), cudaMemcpyHostToDevice, ctx->stream));
@@ -954,7 +1007,7 @@ int nbvgpu_profile_collect(nbvgpu_ctx* ctx, double* gain_kernel_ms, uint64_t* la
 }
 
 int nbvgpu_set_kernel_variant(nbvgpu_ctx* ctx, int variant) {
-  if (!ctx || variant < 0 || variant > 3) return NBVGPU_ERR_INVALID;
+  if (!ctx || variant < 0 || variant > 5) return NBVGPU_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->variant = variant;
   return NBVGPU_OK;

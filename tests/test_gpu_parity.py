@@ -27,7 +27,7 @@ def _compare_gain(o, lt_o, g, lt_g, pos, expect_exact_gain=True):
     return ro, rg
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 def test_tiny_map_all_kernel_variants(oracle_mod, tiny_map, variant):
     from nbv_exploration_planner_b200 import synth
     cam = tiny_map.camera()
@@ -35,12 +35,12 @@ def test_tiny_map_all_kernel_variants(oracle_mod, tiny_map, variant):
     g, lt_g, le_g = load_gpu(tiny_map, cam, variant)
     c = synth.make_candidates(tiny_map.cfg, 16, lambda s: o.check_segments(le_o, tiny_map.cfg.robot_radius, s)["free"])
     _compare_gain(o, lt_o, g, lt_g, c.positions)
-    if variant == 2:
+    if variant in (2, 5):
         assert g.classifier_mismatches() == 0
     g.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 4, 5])
 def test_cfg1_100_candidates(oracle_mod, cfg1_map, variant):
     """BASELINE config 1: 20x20x5 m, 0.15 m voxels, 90x60 deg, 5 m range, 100 candidates."""
     from nbv_exploration_planner_b200 import synth
@@ -51,7 +51,7 @@ def test_cfg1_100_candidates(oracle_mod, cfg1_map, variant):
     c = synth.make_candidates(cfg, 100, lambda s: o.check_segments(le_o, cfg.robot_radius, s)["free"])
     ro, rg = _compare_gain(o, lt_o, g, lt_g, c.positions)
     assert ro["rays"][0] == 360 * 39 and ro["steps"].sum() > 50e6
-    if variant == 2:
+    if variant in (2, 5):
         assert g.classifier_mismatches() == 0
     st = g.stats()
     assert st["voxel_steps"] == int(ro["steps"].sum()) and st["rays"] == int(ro["rays"].sum())
@@ -86,11 +86,11 @@ def test_camera_and_layer_parameter_sweep(oracle_mod, hfov, vfov, far, pitch, vs
     m = synth.make_map(cfg)   # negative coordinates: blocks with negative indices
     cam = m.camera()
     o, lt_o, _ = load_oracle(oracle_mod, m, cam)
-    for variant in (0, 2):
+    for variant in (0, 2, 5):
         g, lt_g, _ = load_gpu(m, cam, variant)
         c = synth.make_candidates(cfg, 12, None)
         _compare_gain(o, lt_o, g, lt_g, c.positions)
-        if variant == 2:
+        if variant in (2, 5):
             assert g.classifier_mismatches() == 0
         g.close()
 
