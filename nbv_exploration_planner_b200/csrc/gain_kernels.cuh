@@ -105,6 +105,7 @@ struct GainSmem {
   float* csf;     // [2][yc]
   int* um;        // [yc]
   unsigned* cnt;  // [3][yc]
+  float* fp;      // [12][yc]  far / top / bottom plane in single precision, relative to the candidate voxel
   int* grid;      // [gnz][gny][gnx]
 };
 // The slot grid sits at offset 0 so that its address is a compile-time constant in the ray loop.
@@ -117,9 +118,10 @@ __device__ __forceinline__ GainSmem carve(unsigned char* base, int yc, int gn) {
   s.csf = s.st + 3 * yc;
   s.um = reinterpret_cast<int*>(s.csf + 2 * yc);
   s.cnt = reinterpret_cast<unsigned*>(s.um + yc);
+  s.fp = reinterpret_cast<float*>(s.cnt + 3 * yc);
   return s;
 }
-inline size_t gain_smem_bytes(int yc, int gn) { return (size_t)yc * (33 * 8 + 9 * 4) + (((size_t)gn * 4 + 15) & ~(size_t)15) + 16; }
+inline size_t gain_smem_bytes(int yc, int gn) { return (size_t)yc * (33 * 8 + 21 * 4) + (((size_t)gn * 4 + 15) & ~(size_t)15) + 16; }
 
 // Plane::setFromPoints + store (camera_model.cpp:5-11).
 __device__ __forceinline__ void store_plane(double* pl, int yc, int j, int k, const D3& p1, const D3& p2, const D3& p3) {
@@ -147,8 +149,8 @@ __device__ __forceinline__ bool exact_in_frustum(const double* pl, int yc, int j
 // ray loop.
 __device__ __noinline__ void build_yaw_frame(const double* __restrict__ A, const double* __restrict__ B,
                                              const float* __restrict__ cs, double vs_inv, double* s_pl, double* s_rd,
-                                             float* s_st, float* s_csf, int* s_um, unsigned* s_cnt, int yc, int j, double px,
-                                             double py, double pz) {
+                                             float* s_st, float* s_csf, int* s_um, unsigned* s_cnt, float* s_fp, double vs,
+                                             int g0x, int g0y, int g0z, int yc, int j, double px, double py, double pz) {
   // A, B, cs already point at this yaw's table rows
   const D3 p{px, py, pz};
   const D3 t = d3add(p, D3{B[0], B[1], B[2]});  // camera position
@@ -176,6 +178,17 @@ __device__ __noinline__ void build_yaw_frame(const double* __restrict__ A, const
   s_csf[1 * yc + j] = cs[1];
   s_um[j] = um;
   s_cnt[0 * yc + j] = 0u; s_cnt[1 * yc + j] = 0u; s_cnt[2 * yc + j] = 0u;
+  // Single-precision copies of the far (1), top (4) and bottom (5) planes for the one-plane tests:
+  // s(g) = n.(g*vs) - d = sum_k (n_k*vs)*(g_k - g0_k) + (n.(g0*vs) - d); |error| ~ 3e-6 m << margin.
+  const int kp[3] = {1, 4, 5};
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    const double nx = s_pl[(4 * kp[q] + 0) * yc + j], ny = s_pl[(4 * kp[q] + 1) * yc + j], nz = s_pl[(4 * kp[q] + 2) * yc + j];
+    s_fp[(4 * q + 0) * yc + j] = __double2float_rn(nx * vs);
+    s_fp[(4 * q + 1) * yc + j] = __double2float_rn(ny * vs);
+    s_fp[(4 * q + 2) * yc + j] = __double2float_rn(nz * vs);
+    s_fp[(4 * q + 3) * yc + j] = __double2float_rn((nx * (double)g0x + ny * (double)g0y + nz * (double)g0z) * vs - s_pl[(4 * kp[q] + 3) * yc + j]);
+  }
 }
 
 // Camera-frame coordinates of a point given as (float) voxel offsets from g0 (classifier math).
@@ -254,8 +267,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   // (b) per-yaw frames.
   for (int j = tid; j < yc; j += blockDim.x) {
     const int y = chunk * yc + j;
-    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, yc, j, px, py,
-                    pz);
+    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, a.vs, g0x,
+                    g0y, g0z, yc, j, px, py, pz);
   }
   __syncthreads();
   for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
@@ -338,12 +351,11 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       t_out = fmaf(fabsf(t_out), 1e-5f, t_out) + 1e-6f;
       // the open plane: top (index 4) when the ray ends in the upper half of the frustum, else bottom
       // (5); s(g) = n.(g*vs) - d = sum_k (n_k*vs)*(g_k - g0_k) + (n.(g0*vs) - d), from the FP64 plane.
-      const int kp = ze >= 0.0f ? 4 : 5;
-      const double nx = S.pl[(4 * kp + 0) * yc + j], ny = S.pl[(4 * kp + 1) * yc + j], nz = S.pl[(4 * kp + 2) * yc + j];
-      pa[0] = __double2float_rn(nx * a.vs);
-      pa[1] = __double2float_rn(ny * a.vs);
-      pa[2] = __double2float_rn(nz * a.vs);
-      pc = __double2float_rn((nx * (double)g0x + ny * (double)g0y + nz * (double)g0z) * a.vs - S.pl[(4 * kp + 3) * yc + j]);
+      const int q = ze >= 0.0f ? 4 : 8;
+      pa[0] = S.fp[(q + 0) * yc + j];
+      pa[1] = S.fp[(q + 1) * yc + j];
+      pa[2] = S.fp[(q + 2) * yc + j];
+      pc = S.fp[(q + 3) * yc + j];
     }
 
     unsigned acc = 0u, occ = 0u;  // acc: unknown count (bits 0-15) | free count (bits 16-31); < 65536 steps per ray
@@ -544,34 +556,42 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
   }
   for (int j = tid; j < yc; j += blockDim.x) {
     const int y = chunk * yc + j;
-    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, yc, j, px, py,
-                    pz);
+    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, a.vs, g0x,
+                    g0y, g0z, yc, j, px, py, pz);
   }
   __syncthreads();
   for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
-  // (c) dense status volume: one status-tile word (16 voxels along x) per thread and iteration
-  for (int w = tid; w < nvol; w += blockDim.x) {
-    const int wx = w % vxw, t2 = w / vxw;
-    const int gy = y0 + t2 % vey, gz = z0 + t2 / vey, gx = x0 + 16 * wx;
-    uint32_t word = 0xFFFFFFFFu;  // 3 = outside the exploration box
-    const long long lo = (long long)a.gmin[0] - gx, hi = lo + (long long)a.gspan[0];  // in-box x range inside the word
-    if ((unsigned)(gy - a.gmin[1]) <= a.gspan[1] && (unsigned)(gz - a.gmin[2]) <= a.gspan[2] && hi >= 0 && lo <= 15) {
-      const int bx = gx >> lv, by = gy >> lv, bz = gz >> lv;
-      const int ix = bx - b0x, iy = by - b0y, iz = bz - b0z;
-      int slot;
-      if ((unsigned)ix < (unsigned)a.gnx && (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz) {
-        slot = S.grid[(iz * a.gny + iy) * a.gnx + ix];
-      } else {
-        slot = probe_block(a.L, bx, by, bz);
-        if (slot < 0) slot = a.unknown_slot;
+  // (c) dense status volume, one (y, z) row of vxw words per thread and iteration.  Volume codes:
+  // 0 unknown, 1 free, 2 skip (outside the exploration box), 3 occupied.
+  for (int row = tid; row < vey * vez; row += blockDim.x) {
+    const int gy = y0 + row % vey, gz = z0 + row / vey;
+    const bool row_in = (unsigned)(gy - a.gmin[1]) <= a.gspan[1] && (unsigned)(gz - a.gmin[2]) <= a.gspan[2];
+    const int iy = (gy >> lv) - b0y, iz = (gz >> lv) - b0z;
+    const bool row_grid = (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz;
+    const unsigned rowoff = (unsigned)(((gz & vm) << lv) | (gy & vm));
+    for (int wx = 0; wx < vxw; ++wx) {
+      const int gx = x0 + 16 * wx;
+      uint32_t word = 0xAAAAAAAAu;
+      const long long lo = (long long)a.gmin[0] - gx, hi = lo + (long long)a.gspan[0];  // in-box x range inside the word
+      if (row_in && hi >= 0 && lo <= 15) {
+        const int ix = (gx >> lv) - b0x;
+        int slot;
+        if (row_grid && (unsigned)ix < (unsigned)a.gnx) {
+          slot = S.grid[(iz * a.gny + iy) * a.gnx + ix];
+        } else {
+          slot = probe_block(a.L, gx >> lv, gy >> lv, gz >> lv);
+          if (slot < 0) slot = a.unknown_slot;
+        }
+        word = __ldg(a.L.status + ((unsigned)slot * 256u + rowoff));
+        word |= (word >> 1) & 0x55555555u;  // tile code 2 (occupied) -> volume code 3
+        const int l = lo > 0 ? (int)lo : 0, h = hi < 15 ? (int)hi : 15;
+        const uint32_t below = (1u << (2 * l)) - 1u;                                   // voxels < l
+        const uint32_t upto = h == 15 ? 0xFFFFFFFFu : ((1u << (2 * (h + 1))) - 1u);   // voxels <= h
+        const uint32_t outm = below | ~upto;
+        word = (word & ~outm) | (outm & 0xAAAAAAAAu);
       }
-      word = __ldg(a.L.status + ((unsigned)slot * 256u + (unsigned)(((gz & vm) << lv) | (gy & vm))));
-      const int l = lo > 0 ? (int)lo : 0, h = hi < 15 ? (int)hi : 15;
-      const uint32_t below = (1u << (2 * l)) - 1u;                         // voxels < l
-      const uint32_t upto = h == 15 ? 0xFFFFFFFFu : ((1u << (2 * (h + 1))) - 1u);  // voxels <= h
-      word |= below | ~upto;
+      vol[row * vxw + wx] = word;
     }
-    vol[w] = word;
   }
   __syncthreads();
   const int n_rays = s_umax * yc;
@@ -582,6 +602,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
   const FilterConst& F = a.F;
   const float slack = 1.8f * a.vs_f + F.m + 1e-4f;
   const int stride_y = 32 * vxw, stride_z = 32 * vxw * vey;
+  const uint32_t vol_s = (uint32_t)__cvta_generic_to_shared(vol);  // shared-window address kept in a register
 
   const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   unsigned long long my_steps = 0ull;
@@ -597,7 +618,6 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
     float t[3], dt[3];
     int len = 0;
     float tlo = 0.0f, thi = 3.0e38f, tlo_v = 0.0f, t_out = 3.0e38f;
-    float pa[3], pc;
     float e3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -612,14 +632,16 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
       const float shifted = __fsub_rn(sk, (float)g[k]);
       const float dist = __fsub_rn((float)max(0, sg[k]), shifted);
-      t[k] = __fdiv_rn(dist, rr);
+      t[k] = __fdiv_rn(dist, rr);  // exact IEEE division: part of the reference's arithmetic
       dt[k] = __fdiv_rn((float)sg[k], rr);
+      // conservative bounds below may use the fast division: they are padded by 1e-5 relative
       const float bmin = (float)a.gmin[k], bmax = (float)a.gmin[k] + (float)a.gspan[k];
       if (rr != 0.0f) {
-        const float qo = (rr > 0.0f ? (bmax + 1.02f - sk) : (bmin - 0.02f - sk)) / rr;
+        const float qo = __fdividef(rr > 0.0f ? (bmax + 1.02f - sk) : (bmin - 0.02f - sk), rr);
         t_out = fminf(t_out, qo);
       }
     }
+    float pa[3], pc;
     {
       float xe, ye, ze;
       to_camera(F, a.vs_f, e3[0] - (float)g0x, e3[1] - (float)g0y, e3[2] - (float)g0z, noffx, noffy, noffz, S.csf[j],
@@ -627,98 +649,114 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       const float dh = fmaf(F.th, xe, -fabsf(ye));
       const float dv_near = fmaf(F.tv, xe, -fabsf(ze)), dv_far = fmaf(F.tv, xe, fabsf(ze));
       if (xe > 0.0f && dh > 0.0f && dv_far > 0.0f) {
-        const float sc = slack / F.m;
-        tlo = fmaxf(tlo, (F.nearp + slack) / xe);
-        tlo = fmaxf(tlo, (F.mh * sc) / dh);
-        tlo = fmaxf(tlo, (F.mv * sc) / dv_far);
-        thi = fminf(thi, (F.farp - slack) / xe);
-        tlo_v = dv_near > 0.0f ? (F.mv * sc) / dv_near : 3.0e38f;
+        const float sc = __fdividef(slack, F.m);
+        const float rx = __fdividef(1.0f, xe);
+        tlo = fmaxf(tlo, (F.nearp + slack) * rx);
+        tlo = fmaxf(tlo, __fdividef(F.mh * sc, dh));
+        tlo = fmaxf(tlo, __fdividef(F.mv * sc, dv_far));
+        thi = (F.farp - slack) * rx;
+        tlo_v = dv_near > 0.0f ? __fdividef(F.mv * sc, dv_near) : 3.0e38f;
       } else {
-        thi = -1.0f;
+        tlo = 3.0e38f;  // degenerate frustum geometry for this ray: always use the classifier
       }
-      tlo = fmaf(fabsf(tlo), 1e-5f, tlo) + 1e-6f;
-      tlo_v = fmaf(fabsf(tlo_v), 1e-5f, tlo_v) + 1e-6f;
-      thi = fmaf(fabsf(thi), -1e-5f, thi) - 1e-6f;
-      t_out = fmaf(fabsf(t_out), 1e-5f, t_out) + 1e-6f;
-      const int kp = ze >= 0.0f ? 4 : 5;
-      const double nx = S.pl[(4 * kp + 0) * yc + j], ny = S.pl[(4 * kp + 1) * yc + j], nz = S.pl[(4 * kp + 2) * yc + j];
-      pa[0] = __double2float_rn(nx * a.vs);
-      pa[1] = __double2float_rn(ny * a.vs);
-      pa[2] = __double2float_rn(nz * a.vs);
-      pc = __double2float_rn((nx * (double)g0x + ny * (double)g0y + nz * (double)g0z) * a.vs - S.pl[(4 * kp + 3) * yc + j]);
+      tlo = fmaf(fabsf(tlo), 1e-4f, tlo) + 1e-5f;
+      tlo_v = fmaf(fabsf(tlo_v), 1e-4f, tlo_v) + 1e-5f;
+      thi = fmaf(fabsf(thi), -1e-4f, thi) - 1e-5f;
+      t_out = fmaf(fabsf(t_out), 1e-4f, t_out) + 1e-5f;
+      const int q = ze >= 0.0f ? 4 : 8;  // open vertical plane: top when the ray ends in the upper half
+      pa[0] = S.fp[(q + 0) * yc + j];
+      pa[1] = S.fp[(q + 1) * yc + j];
+      pa[2] = S.fp[(q + 2) * yc + j];
+      pc = S.fp[(q + 3) * yc + j];
     }
+    const float tA = fmaxf(tlo, tlo_v), tB = fminf(thi, t_out);  // window in which every test is sure
     // bit address of the start voxel in the dense volume and the per-axis strides
     int P = ((g[2] - z0) * vey + (g[1] - y0)) * stride_y + 2 * (g[0] - x0);
     const int stx = 2 * sg[0], sty = stride_y * sg[1], stz = stride_z * sg[2];
 
-    unsigned acc = 0u, occ = 0u;
+    unsigned acc = 0u, occ = 0u;  // acc: 10-bit fields, [0] unknown, [1] free, [2] skipped
     float tcur = 0.0f;
     int step = 0;
     for (; step <= len; ++step) {
-      if (tcur > t_out) {  // left the convex exploration box for good
-        if (!kParanoid) {
-          step = len + 1;
-          break;
-        }
-        if ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
-            (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2])
-          ++my_mismatch;
-      }
       // ---- frustum (camera_model.cpp:194-199), cheapest decision first
-      bool decided = false, fin = false;
-      if (tcur > tlo && tcur < thi) {
-        if (tcur > tlo_v) {
-          fin = true;
-          decided = true;
-        } else {
-          const float sv = fmaf(pa[0], (float)(g[0] - g0x), fmaf(pa[1], (float)(g[1] - g0y), fmaf(pa[2], (float)(g[2] - g0z), pc)));
-          fin = sv > F.m;
-          decided = fin || sv < -F.m;
-        }
-      }
-      if (!decided || kParanoid) {
-        float xc, yk, zk;
-        to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
-                  S.csf[yc + j], xc, yk, zk);
-        const float s0 = xc - F.nearp, s1 = F.farp - xc;
-        const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
-        const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
-        const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
-        bool ex;
-        if (kParanoid) {
-          ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-          if ((sure_in && !ex) || (sure_out && ex) || (decided && fin != ex)) ++my_mismatch;
-        } else if (sure_in) {
-          ex = true;
-        } else if (sure_out) {
-          ex = false;
-        } else {
-          ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-        }
-        fin = ex;
-      }
-      if (fin) {
-        // ---- exploration box + voxel status from the dense volume
-        const uint32_t w = vol[(unsigned)P >> 5];
-        const unsigned status = __funnelshift_r(w, 0u, (unsigned)P) & 3u;
-        if (kParanoid) {
-          unsigned want = 3u;
-          if ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
-              (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2]) {
-            int slot = probe_block(a.L, g[0] >> lv, g[1] >> lv, g[2] >> lv);
-            if (slot < 0) slot = a.unknown_slot;
-            const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
-            want = (__ldg(a.L.status + ((unsigned)slot * 256u + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
+      bool fin = true;
+      if (!(tcur > tA && tcur < tB) || kParanoid) {
+        if (tcur > t_out) {  // left the convex exploration box for good
+          if (!kParanoid) {
+            step = len + 1;
+            break;
           }
-          if (((unsigned)P >> 5) >= (unsigned)nvol || want != status) ++my_mismatch;
+          if ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+              (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2])
+            ++my_mismatch;
         }
-        if (status == 2u) {
-          occ = 1u;
-          ++step;  // this step was executed
-          break;
+        bool decided = false;
+        fin = false;
+        if (tcur > tlo) {
+          // near, left/right and the farther of top/bottom are sure; open: the far plane once tcur >= thi,
+          // the nearer of top/bottom while tcur <= tlo_v -> one single-precision plane evaluation each
+          const float dx = (float)(g[0] - g0x), dy = (float)(g[1] - g0y), dz = (float)(g[2] - g0z);
+          bool any_out = false, any_und = false;
+          if (!(tcur < thi)) {
+            const float sf = fmaf(S.fp[0 * yc + j], dx, fmaf(S.fp[1 * yc + j], dy, fmaf(S.fp[2 * yc + j], dz, S.fp[3 * yc + j])));
+            any_out = sf < -F.m;
+            any_und = !any_out && !(sf > F.m);
+          }
+          if (!(tcur > tlo_v)) {
+            const float sv = fmaf(pa[0], dx, fmaf(pa[1], dy, fmaf(pa[2], dz, pc)));
+            any_out = any_out || sv < -F.m;
+            any_und = any_und || (!(sv < -F.m) && !(sv > F.m));
+          }
+          // one plane surely out settles it; otherwise a plane within its margin needs the exact test
+          decided = any_out || !any_und;
+          fin = !any_out && !any_und;
         }
-        acc += (status == 3u) ? 0u : (1u << (status << 4));  // unknown: low half, free: high half
+        if (!decided || kParanoid) {
+          float xc, yk, zk;
+          to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
+                    S.csf[yc + j], xc, yk, zk);
+          const float s0 = xc - F.nearp, s1 = F.farp - xc;
+          const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
+          const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
+          const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
+          bool ex;
+          if (kParanoid) {
+            ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+            const bool fast_all = tcur > tA && tcur < tB;
+            if ((sure_in && !ex) || (sure_out && ex) || (decided && fin != ex) || (fast_all && !ex)) ++my_mismatch;
+          } else if (sure_in) {
+            ex = true;
+          } else if (sure_out) {
+            ex = false;
+          } else {
+            ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+          }
+          fin = ex;
+        }
       }
+      // ---- exploration box + voxel status: one word of the dense volume (always in range)
+      uint32_t w;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(vol_s + (((unsigned)P >> 3) & ~3u)));
+      unsigned code = __funnelshift_r(w, 0u, (unsigned)P) & 3u;
+      if (kParanoid) {
+        unsigned want = 2u;
+        if ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+            (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2]) {
+          int slot = probe_block(a.L, g[0] >> lv, g[1] >> lv, g[2] >> lv);
+          if (slot < 0) slot = a.unknown_slot;
+          const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
+          const unsigned st = (__ldg(a.L.status + ((unsigned)slot * 256u + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
+          want = st == 2u ? 3u : st;
+        }
+        if (((unsigned)P >> 5) >= (unsigned)nvol || want != code) ++my_mismatch;
+      }
+      code = fin ? code : 2u;
+      if (code == 3u) {
+        occ = 1u;
+        ++step;  // this step was executed
+        break;
+      }
+      acc += 1u << (code * 10u);
       // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
       const bool c1 = t[1] < t[0];
       const float bm = c1 ? t[1] : t[0];
@@ -734,8 +772,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       t[2] = c2 ? __fadd_rn(t[2], dt[2]) : t[2];
     }
     my_steps += (unsigned long long)step;
-    if (acc & 0xFFFFu) atomicAdd(&S.cnt[0 * yc + j], acc & 0xFFFFu);
-    if (acc >> 16) atomicAdd(&S.cnt[1 * yc + j], acc >> 16);
+    if (acc & 1023u) atomicAdd(&S.cnt[0 * yc + j], acc & 1023u);
+    if ((acc >> 10) & 1023u) atomicAdd(&S.cnt[1 * yc + j], (acc >> 10) & 1023u);
     if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);
   }
 #pragma unroll
