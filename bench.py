@@ -45,6 +45,9 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="gain kernel variant (A/B measurement)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the cpu_baseline sample (default 1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="", choices=["", "weak", "strong"], help="default: weak for cfg1/2, strong otherwise")
+    ap.add_argument("--selfcheck", action="store_true", help="re-run one step with the plain FP64 kernel and compare")
+    ap.add_argument("--traj-prefix", type=int, default=0, help="use only the first N trajectory points for the map")
     return ap.parse_args()
 
 
@@ -181,6 +184,33 @@ def emit(obj):
 
 
 # ---------------------------------------------------------------------------------------------
+def replicate_map(g, lt, le, m, cfg, rank, world, dev, chunk_blocks=4096):
+    """Rank 0 holds the map on the host; every rank ends up with the same device replica: per chunk one
+    pinned H2D copy on rank 0, one NCCL broadcast of {keys | payload}, insert + scatter kernels on every
+    rank (nbvgpu_layer_update_device).  Returns (#blocks, device ms including H2D and broadcast)."""
+    import torch
+    import torch.distributed as dist
+
+    from nbv_exploration_planner_b200 import dist as nd
+    nvox = cfg.vps ** 3
+    hdr = torch.tensor([len(m.keys) if rank == 0 else 0], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.broadcast(hdr, 0)
+    nb = int(hdr.item())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(0, nb, chunk_blocks):
+        j = min(nb, i + chunk_blocks)
+        n_t, dk, dp = nd.broadcast_blocks(m.keys[i:j] if rank == 0 else None, m.tsdf[i:j] if rank == 0 else None, 2 * nvox, dev)
+        g.layer_update_device(lt, n_t, dk, dp)
+        n_e, dk2, dp2 = nd.broadcast_blocks(m.keys[i:j] if rank == 0 else None, m.esdf[i:j] if rank == 0 else None, nvox, dev)
+        g.layer_update_device(le, n_e, dk2, dp2)
+    e1.record()
+    torch.cuda.synchronize()
+    return nb, e0.elapsed_time(e1)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -200,7 +230,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = synth.CONFIGS[args.config]
-    n_per = args.candidates or cfg.n_candidates
+    strong = (args.scaling or ("weak" if args.config in ("cfg1", "cfg2") else "strong")) == "strong"
+    n_total = (args.candidates or cfg.n_candidates) * (1 if strong else world)
     g = NbvGpu(local)
     # one explicit stream for everything: torch events, NCCL collectives and the library's kernels
     work_stream = torch.cuda.Stream(device=dev)
@@ -208,38 +239,29 @@ def run_ours(args):
     g.set_stream(work_stream.cuda_stream)
     g.set_kernel_variant(args.variant)
 
-    # ---- setup (untimed): map on rank 0 -> NCCL broadcast -> every replica; candidates ------------
+    # ---- setup (untimed unless the config says otherwise): map on rank 0 -> NCCL broadcast -> replicas ----
     t_setup = time.perf_counter()
-    m = synth.make_map(args.config) if rank == 0 else None
-    nvox = cfg.vps ** 3
-    nb_hdr = torch.tensor([len(m.keys) if rank == 0 else 0], dtype=torch.int64, device=dev)
+    m = synth.make_map(args.config, traj_prefix=args.traj_prefix or None) if rank == 0 else None
+    hdr = torch.tensor([len(m.keys) if rank == 0 else 0], dtype=torch.int64, device=dev)
     if world > 1:
-        dist.broadcast(nb_hdr, 0)
-    nb = int(nb_hdr.item())
-    lt = g.layer_create(LAYER_TSDF, cfg.voxel_size, cfg.vps, nb + 64)
-    le = g.layer_create(LAYER_ESDF, cfg.voxel_size, cfg.vps, nb + 64)
-    ev_b0, ev_b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev_b0.record()
-    n_t, dk, dp = nd.broadcast_blocks(m.keys if rank == 0 else None, m.tsdf if rank == 0 else None, 2 * nvox, dev)
-    g.layer_update_device(lt, n_t, dk, dp)
-    n_e, dk2, dp2 = nd.broadcast_blocks(m.keys if rank == 0 else None, m.esdf if rank == 0 else None, nvox, dev)
-    g.layer_update_device(le, n_e, dk2, dp2)
-    ev_b1.record()
-    torch.cuda.synchronize()
-    map_broadcast_ms = ev_b0.elapsed_time(ev_b1)
+        dist.broadcast(hdr, 0)
+    nb_alloc = int(hdr.item())
+    lt = g.layer_create(LAYER_TSDF, cfg.voxel_size, cfg.vps, nb_alloc + 64)
+    le = g.layer_create(LAYER_ESDF, cfg.voxel_size, cfg.vps, nb_alloc + 64)
+    nb, map_broadcast_ms = replicate_map(g, lt, le, m, cfg, rank, world, dev)
     cam = synth.camera_for(cfg)
     g.set_camera(cam)
 
     # candidates: grown on rank 0 with the GPU collision check as the acceptance test, then shared
     if rank == 0:
-        c = synth.make_candidates(cfg, n_per * world, lambda s: g.check_segments(le, cfg.robot_radius, s))
+        c = synth.make_candidates(cfg, n_total, lambda s: g.check_segments(le, cfg.robot_radius, s))
         pack = np.concatenate([c.positions, c.segments, c.distance[:, None]], 1)
     else:
-        pack = np.empty((n_per * world, 10))
+        pack = np.empty((n_total, 10))
     pack_t = torch.from_numpy(pack).to(dev)
     if world > 1:
         dist.broadcast(pack_t, 0)
-    lo, hi = nd.shard_bounds(n_per * world, world, rank)
+    lo, hi = nd.shard_bounds(n_total, world, rank)
     mine = pack_t[lo:hi].contiguous()
     n = hi - lo
     d_pos = mine[:, 0:3].contiguous()
@@ -258,7 +280,7 @@ def run_ours(args):
         g.check_segments_device(le, cfg.robot_radius, n, d_seg, d_free)
         g.gain_eval_best_device(lt, n, d_pos, d_pyaw, d_dist, d_free, v_max, dyaw_max, zero_gain, d_best, d_gain, d_yaw)
         # every step ends with the winner known on the host (one 32 B record per rank)
-        return nd.gather_best_raw(d_best, n_per * world)
+        return nd.gather_best_raw(d_best, n_total)
 
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -306,25 +328,35 @@ def run_ours(args):
         return r
 
     for _ in range(2):
-        host_result = step_host()
+        step_host()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        host_result = step_host()
+        step_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     h2d = n * (48 + 24 + 8 + 8 + 1)
     d2h = n * (1 + 8 + 4) + 32
 
+    # ---- optional full-size self-check: the plain FP64 transcription kernel must give the same result
+    selfcheck = None
+    if args.selfcheck:
+        ref_gain, ref_yaw = d_gain.clone(), d_yaw.clone()
+        g.set_kernel_variant(1)
+        step_device()
+        torch.cuda.synchronize()
+        selfcheck = {"variant_1_equals_default": bool(torch.equal(ref_gain, d_gain) and torch.equal(ref_yaw, d_yaw)), "candidates": n}
+        g.set_kernel_variant(args.variant)
+
     # ---- reduce over ranks (max time) -----------------------------------------------------------
-    red = torch.tensor([dev_ms, e2e_s, kern_ms], dtype=torch.float64, device=dev)
+    red = torch.tensor([dev_ms, e2e_s, kern_ms, map_broadcast_ms], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(vsteps), float(rays), float(launches), float(n)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max, kern_ms_max = (float(x) for x in red.cpu())
+    dev_ms_max, e2e_s_max, kern_ms_max, bcast_ms_max = (float(x) for x in red.cpu())
     vsteps_all, rays_all, launches_all, n_all = (float(x) for x in tot.cpu())
     clocks = sampler.summary()
 
@@ -336,18 +368,20 @@ def run_ours(args):
         ach = steps_per_launch * ALGO_BYTES_PER_STEP / (kern_ms / max(1, kern_launches) * 1e-3) / 1e9
         out = {
             "metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64 frustum planes + f32 DDA + i32 voxel index (bit-exact vs reference arithmetic)",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {cfg.bounds_max[0]}x{cfg.bounds_max[1]}x{cfg.bounds_max[2]} m synthetic TSDF+ESDF, "
                                    f"{cfg.voxel_size} m voxels, {cfg.vps}^3 blocks, {cfg.hfov_deg}x{cfg.vfov_deg} deg FOV, "
-                                   f"{cfg.far_m} m range, {n_per} candidates per GPU with ESDF edge check "
+                                   f"{cfg.far_m} m range, {int(n_all)} candidates ({n} per GPU) with ESDF edge check "
                                    f"(radius {cfg.robot_radius:.4f} m, overshoot {cfg.overshoot} m)",
                        "candidates_total": int(n_all), "map_blocks": nb, "l2": "flushed between steps (256 MiB write)",
                        "kernel_variant": args.variant, "parallelism": f"candidates sharded over {world} GPU(s), map replicated",
-                       "map_broadcast_ms_setup": map_broadcast_ms, "setup_s": setup_s},
+                       "map_broadcast_ms_setup": bcast_ms_max, "setup_s": setup_s},
             "rays_per_s": rays_all / (dev_ms_max * 1e-3), "voxel_steps_per_s": vsteps_all / (dev_ms_max * 1e-3),
             "voxel_steps_per_viewpoint": vsteps_all / max(1.0, n_all * args.steps),
+            "value_including_map_broadcast": n_all / ((dev_ms_max / args.steps + bcast_ms_max) * 1e-3),
             "e2e": {"value": n_all * e2e_steps / e2e_s_max, "unit": "viewpoints/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
             "gpu_launches": int(launches_all),
@@ -360,9 +394,125 @@ def run_ours(args):
             "clocks": clocks,
             "best": winner,
         }
+        if selfcheck is not None:
+            out["selfcheck"] = selfcheck
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, cfg, h_pos, h_seg)
         emit(out)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------
+def run_replay(args):
+    """BASELINE config 5: incremental exploration replay.  Each planning step marks the blocks that
+    intersect the observation sphere around the next trajectory point as changed, uploads them (rank 0
+    host -> device -> NCCL broadcast -> insert/scatter kernels on every rank), then checks and scores a
+    fresh set of candidates around the new position.  Everything per step is inside the timed region."""
+    import torch
+    import torch.distributed as dist
+
+    from nbv_exploration_planner_b200 import LAYER_ESDF, LAYER_TSDF, NbvGpu, synth
+    from nbv_exploration_planner_b200 import dist as nd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = synth.CONFIGS[args.config]
+    n_total = args.candidates or cfg.n_candidates
+    n_steps = min(args.steps, cfg.traj_points - 1)
+    g = NbvGpu(local)
+    ws = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(ws)
+    g.set_stream(ws.cuda_stream)
+    nvox = cfg.vps ** 3
+    rng = np.random.Generator(np.random.MT19937(cfg.seed_map))
+    objects = synth._world_objects(cfg, rng)
+    traj = synth._trajectory(cfg, rng)
+    all_keys = synth.blocks_touching(cfg.voxel_size, cfg.vps, traj, cfg.obs_radius, cfg.bounds_min, cfg.bounds_max)
+    lt = g.layer_create(LAYER_TSDF, cfg.voxel_size, cfg.vps, len(all_keys) + 64)
+    le = g.layer_create(LAYER_ESDF, cfg.voxel_size, cfg.vps, len(all_keys) + 64)
+    g.set_camera(synth.camera_for(cfg))
+    # per-step changed blocks, generated up front on rank 0 (map *writing* is not the path being measured)
+    updates = []
+    if rank == 0:
+        for k in range(n_steps + 1):
+            keys = synth.blocks_touching(cfg.voxel_size, cfg.vps, traj[k:k + 1], cfg.obs_radius, cfg.bounds_min, cfg.bounds_max)
+            tsdf, esdf = synth.generate_blocks(cfg, keys, objects, traj[:k + 1])
+            updates.append((keys, tsdf, esdf))
+    # candidate offsets around the current position (star-shaped expansion from the current pose)
+    crng = np.random.Generator(np.random.MT19937(cfg.seed_cand))
+    off = 2.0 * cfg.vicinity * (crng.random((4 * n_total, 3)) - 0.5)
+    off = off[(off ** 2).sum(1) <= cfg.vicinity ** 2][:n_total]
+    lo_b, hi_b = np.array(cfg.bounds_min, float) + 0.3, np.array(cfg.bounds_max, float) - 0.3
+    lo, hi = nd.shard_bounds(n_total, world, rank)
+
+    def apply_update(k):
+        keys, tsdf, esdf = updates[k] if rank == 0 else (None, None, None)
+        n_t, dk, dp = nd.broadcast_blocks(keys, tsdf, 2 * nvox, dev)
+        g.layer_update_device(lt, n_t, dk, dp)
+        n_e, dk2, dp2 = nd.broadcast_blocks(keys, esdf, nvox, dev)
+        g.layer_update_device(le, n_e, dk2, dp2)
+        return n_t
+
+    def plan(k):
+        p = traj[k]
+        pos = np.clip(p + off[lo:hi], lo_b, hi_b)
+        d = pos - p
+        nrm = np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-9)
+        seg = np.concatenate([np.broadcast_to(p, pos.shape), pos + d / nrm * cfg.overshoot], 1)
+        free = g.check_segments(le, cfg.robot_radius, seg)
+        r = g.gain_eval_best(lt, pos, np.zeros(len(pos)), nrm[:, 0], free, 1.0, 0.5, 0.0)
+        rec = torch.tensor([r["index"], r["score"], r["best_gain"], r["best_yaw"]], dtype=torch.float64, device=dev)
+        return nd.gather_best(rec, lo), int(free.sum())
+
+    apply_update(0)
+    plan(0)                                   # warm-up on the first pose
+    st0 = g.stats()
+    sampler = ClockSampler(local)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    t0 = time.perf_counter()
+    up_ms, blocks, nfree = 0.0, 0, 0
+    for k in range(1, n_steps + 1):
+        tu = time.perf_counter()
+        blocks += apply_update(k)
+        torch.cuda.synchronize()
+        up_ms += (time.perf_counter() - tu) * 1e3
+        best, nf = plan(k)
+        nfree += nf
+    torch.cuda.synchronize()
+    total_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    st1 = g.stats()
+    red = torch.tensor([total_s, up_ms], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(st1["voxel_steps"] - st0["voxel_steps"]), float(st1["kernel_launches"] - st0["kernel_launches"])],
+                       dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        total_s, up_ms = (float(x) for x in red.cpu())
+        vsteps, launches = (float(x) for x in tot.cpu())
+        value = n_total * n_steps / total_s
+        emit({"metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": world, "steps": n_steps,
+              "warmup": 1, "ms_per_step": 1e3 * total_s / n_steps, "higher_is_better": True, "scaling": "strong",
+              "vs_baseline": None, "dtype": "f64 frustum planes + f32 DDA + i32 voxel index", "data": "synthetic",
+              "config": {"workload": f"{args.config}: incremental exploration replay, {n_steps} planning steps, per-step changed-block "
+                                     f"upload + {n_total} candidates, {cfg.voxel_size} m voxels, {cfg.far_m} m range",
+                         "blocks_uploaded_per_step": blocks / n_steps, "map_update_ms_per_step": up_ms / n_steps,
+                         "free_edges_per_step": nfree / n_steps, "timing": "wall clock over the whole replay, host buffers"},
+              "voxel_steps_per_s": vsteps / total_s, "gpu_launches": int(launches), "clocks": sampler.summary(),
+              "e2e": {"value": value, "unit": "viewpoints/s", "h2d_bytes_per_step": (hi - lo) * 89 + int(blocks / n_steps) * nvox * 12,
+                      "d2h_bytes_per_step": (hi - lo) * 13 + 32}, "best": best})
     g.close()
     if world > 1:
         dist.destroy_process_group()
@@ -397,5 +547,7 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.config == "cfg5":
+        run_replay(a)
     else:
         run_ours(a)

@@ -123,14 +123,16 @@ void box_thresholds(const nbvgpu_camera& cam, double vs, int gmin[3], int gmax[3
 }
 
 
-bool dense_volume_bounds(const CameraTables& tab, double vs, int yc, int vmin[][3], int dims[3]) {
+bool dense_volume_bounds(const CameraTables& tab, double vs, int yc, int* chunk_info, int* ez_out, long long* max_words) {
   // Every voxel a ray of yaw y visits lies in the box spanned by its start voxel and end voxel
   // (+-1 for the DDA's rounding at the very end).  Relative to the candidate position p, the start is
   // B[y] and the end points of the ray column are A[y][5] + v_center + B[y] + u * u_slope * vs,
   // u in [0, u_max): a straight line, so its extremes are at the two ends.  index(p + rel) - index(p) is
   // floor(rel / vs) or that + 1, hence the asymmetric padding.
+  // chunk_info[c] = {min x, min y, min z, words along x (worst-case 16-alignment), voxels along y}.
   const int chunks = 360 / yc;
-  int dmax[3] = {0, 0, 0};
+  int ez = 0;
+  long long words = 0;
   for (int c = 0; c < chunks; ++c) {
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     for (int y = c * yc; y < (c + 1) * yc; ++y) {
@@ -150,17 +152,21 @@ bool dense_volume_bounds(const CameraTables& tab, double vs, int yc, int vmin[][
         hi[k] = std::fmax(hi[k], std::fmax(s, std::fmax(e0, e1)));
       }
     }
+    int ext[3];
     for (int k = 0; k < 3; ++k) {
       const double a = std::floor(lo[k] / vs) - 2.0, b = std::floor(hi[k] / vs) + 3.0;
       if (!(std::fabs(a) < 1e6) || !(std::fabs(b) < 1e6)) return false;
-      vmin[c][k] = (int)a;
-      const int ext = (int)(b - a) + 1;
-      if (ext > dmax[k]) dmax[k] = ext;
+      chunk_info[5 * c + k] = (int)a;
+      ext[k] = (int)(b - a) + 1;
     }
+    chunk_info[5 * c + 3] = (ext[0] + 15) / 16 + 1;
+    chunk_info[5 * c + 4] = ext[1];
+    if (ext[2] > ez) ez = ext[2];
+    const long long w = (long long)chunk_info[5 * c + 3] * ext[1];
+    if (w > words) words = w;
   }
-  dims[0] = (dmax[0] + 15) / 16 + 1;  // 16-voxel words along x, worst-case alignment
-  dims[1] = dmax[1];
-  dims[2] = dmax[2];
+  *ez_out = ez;
+  *max_words = words * ez;
   return true;
 }
 

@@ -26,10 +26,11 @@ bool build_camera_tables(const nbvgpu_camera& cam, CameraTables* out);
 void box_thresholds(const nbvgpu_camera& cam, double vs, int gmin[3], int gmax[3]);
 
 // Conservative extent of the voxels visited by the rays of each chunk of `yc` consecutive yaws,
-// relative to the voxel that contains the candidate position: vmin[chunk][3] (lower corner, padded)
-// and common dims = {16-voxel words along x, voxels along y, voxels along z}.  Used to size the dense
-// shared-memory status volume of k_gain_dense.  false if the camera geometry is degenerate.
-bool dense_volume_bounds(const CameraTables& tab, double vs, int yc, int vmin[][3], int dims[3]);
+// relative to the voxel that contains the candidate position: chunk_info[chunk][5] = {lower corner
+// x, y, z (padded), 16-voxel words along x, voxels along y}; *ez = voxels along z (common);
+// *max_words = largest volume in 32-bit words over the chunks.  Sizes the dense shared-memory status
+// volume of k_gain_dense.  false if the camera geometry is degenerate.
+bool dense_volume_bounds(const CameraTables& tab, double vs, int yc, int* chunk_info, int* ez, long long* max_words);
 
 }  // namespace nbvgpu_host
 #endif

@@ -66,8 +66,8 @@ struct GainArgs {
   int n;
   // dense shared-memory status volume (k_gain_dense): per-chunk lower corner relative to the
   // candidate's voxel, and the common dimensions {16-voxel words along x, voxels along y, z}
-  const int* vmin;    // [360 / yc][3]
-  int vxw, vey, vez;
+  const int* vmin;    // [360 / yc][5]: lower corner x, y, z; words along x; voxels along y
+  int vez, vwords;    // voxels along z (common); shared-memory words reserved for the volume
   FilterConst F;
 };
 
@@ -515,10 +515,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int yc = a.yc;
   const int gn = a.gnx * a.gny * a.gnz;
-  const int vxw = a.vxw, vey = a.vey, vez = a.vez;
-  const int nvol = vxw * vey * vez;
   uint32_t* const vol = reinterpret_cast<uint32_t*>(smem_raw);
-  const GainSmem S = carve(smem_raw + (((size_t)nvol * 4 + 15) & ~(size_t)15), yc, gn);
+  const GainSmem S = carve(smem_raw + (((size_t)a.vwords * 4 + 15) & ~(size_t)15), yc, gn);
   __shared__ int s_umax;
   __shared__ unsigned long long s_steps;
   __shared__ unsigned int s_mismatch;
@@ -543,10 +541,12 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
   }
   const int g0x = (int)floor(px * a.vs_inv), g0y = (int)floor(py * a.vs_inv), g0z = (int)floor(pz * a.vs_inv);
   const int b0x = (g0x - a.reach_vox) >> lv, b0y = (g0y - a.reach_vox) >> lv, b0z = (g0z - a.reach_vox) >> lv;
-  // volume origin (global voxel index); x aligned down to a block row
-  const int x0 = ((g0x + a.vmin[3 * chunk]) >> lv) << lv;
-  const int y0 = g0y + a.vmin[3 * chunk + 1];
-  const int z0 = g0z + a.vmin[3 * chunk + 2];
+  // volume origin (global voxel index; x aligned down to a block row) and this chunk's dimensions
+  const int x0 = ((g0x + a.vmin[5 * chunk]) >> lv) << lv;
+  const int y0 = g0y + a.vmin[5 * chunk + 1];
+  const int z0 = g0z + a.vmin[5 * chunk + 2];
+  const int vxw = a.vmin[5 * chunk + 3], vey = a.vmin[5 * chunk + 4], vez = a.vez;
+  const int nvol = vxw * vey * vez;
 
   // (a) block-slot grid, (b) per-yaw frames
   for (int i = tid; i < gn; i += blockDim.x) {

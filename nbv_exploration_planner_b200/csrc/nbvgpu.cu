@@ -142,9 +142,11 @@ struct nbvgpu_ctx {
   int vmin_yc = 0;
   float vmin_vs = 0.f;
   unsigned long long vmin_gen = ~0ull, cam_gen = 0;
-  int vdims[3] = {0, 0, 0};
+  int vez = 0;
+  long long vwords = 0;
   bool vmin_ok = false;
   int force_yc = 0;  // NBVGPU_YC environment override (experiments)
+  int dense_budget = 56 * 1024;  // shared memory per CTA the dense volume path may use (NBVGPU_DENSE_KB)
   // optional CUDA-event timing of the ray-sweep kernel (nbvgpu_set_profiling)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -367,11 +369,11 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   // one yaw chunk fits the budget that still allows 4 CTAs per SM.
   bool dense = false;
   a.vmin = nullptr;
-  a.vxw = a.vey = a.vez = 0;
+  a.vez = a.vwords = 0;
   if ((variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0) {
     if (ctx->vmin_gen != ctx->cam_gen || ctx->vmin_yc != yc || ctx->vmin_vs != L->voxel_size) {
-      std::vector<int> vmin((size_t)(360 / yc) * 3);
-      ctx->vmin_ok = nbvgpu_host::dense_volume_bounds(T, a.vs, yc, reinterpret_cast<int(*)[3]>(vmin.data()), ctx->vdims);
+      std::vector<int> vmin((size_t)(360 / yc) * 5);
+      ctx->vmin_ok = nbvgpu_host::dense_volume_bounds(T, a.vs, yc, vmin.data(), &ctx->vez, &ctx->vwords);
       if (ctx->vmin_ok) {
         CK(ctx->d_vmin.reserve(vmin.size() * sizeof(int)));
         CK(cudaMemcpyAsync(ctx->d_vmin.p, vmin.data(), vmin.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
@@ -382,15 +384,14 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
       ctx->vmin_vs = L->voxel_size;
     }
     if (ctx->vmin_ok) {
-      const long long nvol = (long long)ctx->vdims[0] * ctx->vdims[1] * ctx->vdims[2];
+      const long long nvol = ctx->vwords;
       const size_t need = nvol < (1 << 24) ? dense_smem_bytes(yc, (int)gn, (int)nvol) : (size_t)1 << 30;
-      if (need <= 56 * 1024 && need <= (size_t)ctx->max_smem_optin) {
+      if (need <= (size_t)ctx->dense_budget && need <= (size_t)ctx->max_smem_optin) {
         dense = true;
         smem = need;
         a.vmin = ctx->d_vmin.as<int>();
-        a.vxw = ctx->vdims[0];
-        a.vey = ctx->vdims[1];
-        a.vez = ctx->vdims[2];
+        a.vez = ctx->vez;
+        a.vwords = (int)nvol;
       }
     }
   }
@@ -496,6 +497,7 @@ int nbvgpu_create(int device, nbvgpu_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("NBVGPU_YC")) ctx->force_yc = std::atoi(e);
+  if (const char* e = std::getenv("NBVGPU_DENSE_KB")) ctx->dense_budget = std::atoi(e) * 1024;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   DeviceGuard guard(device);
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
