@@ -29,6 +29,19 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n, lo + per)
 
 
+_PINNED = {}
+
+
+def _pinned_staging(n: int, words: int) -> torch.Tensor:
+    """One reusable pinned host buffer per row width (allocating pinned memory per call costs more than
+    the copy itself for large maps)."""
+    buf = _PINNED.get(words)
+    if buf is None or buf.shape[0] < n:
+        buf = torch.empty((max(n, 64), words), dtype=torch.float32).pin_memory()
+        _PINNED[words] = buf
+    return buf[:n]
+
+
 def broadcast_blocks(keys: Optional[np.ndarray], payload: Optional[np.ndarray], payload_words_per_block: int,
                      device: torch.device, src: int = 0, group=None):
     """Broadcast changed blocks from `src`.  Returns (n_blocks, d_keys int32[n][3], d_payload f32[n][words])."""
@@ -48,11 +61,18 @@ def broadcast_blocks(keys: Optional[np.ndarray], payload: Optional[np.ndarray], 
     # one buffer: [keys as float32 bit patterns | payload] so a single collective moves everything
     words = 3 + payload_words_per_block
     if rank == src:
-        buf_h = np.empty((n, words), np.float32)
-        buf_h[:, :3] = keys.view(np.float32)
-        buf_h[:, 3:] = np.ascontiguousarray(payload, np.float32).reshape(n, payload_words_per_block)
-        buf = torch.from_numpy(buf_h)
-        buf = buf.pin_memory().to(device, non_blocking=True) if device.type == "cuda" else buf.clone()
+        if device.type == "cuda":
+            stage = _pinned_staging(n, words)
+            buf_h = stage.numpy()
+            buf_h[:, :3] = keys.view(np.float32)
+            buf_h[:, 3:] = np.asarray(payload, np.float32).reshape(n, payload_words_per_block)
+            buf = stage.to(device, non_blocking=True)
+            torch.cuda.current_stream(device).synchronize()  # the staging buffer is reused by the next call
+        else:
+            buf_h = np.empty((n, words), np.float32)
+            buf_h[:, :3] = keys.view(np.float32)
+            buf_h[:, 3:] = np.asarray(payload, np.float32).reshape(n, payload_words_per_block)
+            buf = torch.from_numpy(buf_h)
     else:
         buf = torch.empty((n, words), dtype=torch.float32, device=device)
     if world > 1:
