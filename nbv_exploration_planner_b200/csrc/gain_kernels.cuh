@@ -106,6 +106,7 @@ struct GainSmem {
   int* um;        // [yc]
   unsigned* cnt;  // [3][yc]
   float* fp;      // [12][yc]  far / top / bottom plane in single precision, relative to the candidate voxel
+  float* sl;      // [6][yc]   per-plane corner slack: vs * sum_i max(n_i, 0)
   int* grid;      // [gnz][gny][gnx]
 };
 // The slot grid sits at offset 0 so that its address is a compile-time constant in the ray loop.
@@ -119,9 +120,10 @@ __device__ __forceinline__ GainSmem carve(unsigned char* base, int yc, int gn) {
   s.um = reinterpret_cast<int*>(s.csf + 2 * yc);
   s.cnt = reinterpret_cast<unsigned*>(s.um + yc);
   s.fp = reinterpret_cast<float*>(s.cnt + 3 * yc);
+  s.sl = s.fp + 12 * yc;
   return s;
 }
-inline size_t gain_smem_bytes(int yc, int gn) { return (size_t)yc * (33 * 8 + 21 * 4) + (((size_t)gn * 4 + 15) & ~(size_t)15) + 16; }
+inline size_t gain_smem_bytes(int yc, int gn) { return (size_t)yc * (33 * 8 + 27 * 4) + (((size_t)gn * 4 + 15) & ~(size_t)15) + 16; }
 
 // Plane::setFromPoints + store (camera_model.cpp:5-11).
 __device__ __forceinline__ void store_plane(double* pl, int yc, int j, int k, const D3& p1, const D3& p2, const D3& p3) {
@@ -149,8 +151,9 @@ __device__ __forceinline__ bool exact_in_frustum(const double* pl, int yc, int j
 // ray loop.
 __device__ __noinline__ void build_yaw_frame(const double* __restrict__ A, const double* __restrict__ B,
                                              const float* __restrict__ cs, double vs_inv, double* s_pl, double* s_rd,
-                                             float* s_st, float* s_csf, int* s_um, unsigned* s_cnt, float* s_fp, double vs,
-                                             int g0x, int g0y, int g0z, int yc, int j, double px, double py, double pz) {
+                                             float* s_st, float* s_csf, int* s_um, unsigned* s_cnt, float* s_fp, float* s_sl,
+                                             double vs, int g0x, int g0y, int g0z, int yc, int j, double px, double py,
+                                             double pz) {
   // A, B, cs already point at this yaw's table rows
   const D3 p{px, py, pz};
   const D3 t = d3add(p, D3{B[0], B[1], B[2]});  // camera position
@@ -188,6 +191,13 @@ __device__ __noinline__ void build_yaw_frame(const double* __restrict__ A, const
     s_fp[(4 * q + 1) * yc + j] = __double2float_rn(ny * vs);
     s_fp[(4 * q + 2) * yc + j] = __double2float_rn(nz * vs);
     s_fp[(4 * q + 3) * yc + j] = __double2float_rn((nx * (double)g0x + ny * (double)g0y + nz * (double)g0z) * vs - s_pl[(4 * kp[q] + 3) * yc + j]);
+  }
+  // Corner slack per plane: the tested point is the MIN corner of the voxel that contains the ray
+  // point X (g <= X/vs <= g+1), so n.(g*vs) >= n.X - vs * sum_i max(n_i, 0); rounded up.
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double sx = fmax(s_pl[(4 * k + 0) * yc + j], 0.0), sy = fmax(s_pl[(4 * k + 1) * yc + j], 0.0), sz = fmax(s_pl[(4 * k + 2) * yc + j], 0.0);
+    s_sl[k * yc + j] = __double2float_ru((sx + sy + sz) * vs * 1.001);
   }
 }
 
@@ -267,8 +277,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   // (b) per-yaw frames.
   for (int j = tid; j < yc; j += blockDim.x) {
     const int y = chunk * yc + j;
-    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, a.vs, g0x,
-                    g0y, g0z, yc, j, px, py, pz);
+    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, S.sl, a.vs,
+                    g0x, g0y, g0z, yc, j, px, py, pz);
   }
   __syncthreads();
   for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
@@ -556,8 +566,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
   }
   for (int j = tid; j < yc; j += blockDim.x) {
     const int y = chunk * yc + j;
-    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, a.vs, g0x,
-                    g0y, g0z, yc, j, px, py, pz);
+    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, S.sl, a.vs,
+                    g0x, g0y, g0z, yc, j, px, py, pz);
   }
   __syncthreads();
   for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
@@ -600,9 +610,9 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
   const float noffy = -__double2float_rn(py - (double)g0y * a.vs);
   const float noffz = -__double2float_rn(pz - (double)g0z * a.vs);
   const FilterConst& F = a.F;
-  const float slack = 1.8f * a.vs_f + F.m + 1e-4f;
   const int stride_y = 32 * vxw, stride_z = 32 * vxw * vey;
-  const uint32_t vol_s = (uint32_t)__cvta_generic_to_shared(vol);  // shared-window address kept in a register
+  uint32_t vol_s = (uint32_t)__cvta_generic_to_shared(vol);
+  asm volatile("mov.u32 %0, %0;" : "+r"(vol_s));  // opaque: keep the shared-window address in a register
 
   const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   unsigned long long my_steps = 0ull;
@@ -646,16 +656,26 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       float xe, ye, ze;
       to_camera(F, a.vs_f, e3[0] - (float)g0x, e3[1] - (float)g0y, e3[2] - (float)g0z, noffx, noffy, noffz, S.csf[j],
                 S.csf[yc + j], xe, ye, ze);
-      const float dh = fmaf(F.th, xe, -fabsf(ye));
-      const float dv_near = fmaf(F.tv, xe, -fabsf(ze)), dv_far = fmaf(F.tv, xe, fabsf(ze));
-      if (xe > 0.0f && dh > 0.0f && dv_far > 0.0f) {
-        const float sc = __fdividef(slack, F.m);
+      // Signed distances of the ray point to the six planes grow linearly from ~0 at the camera to
+      // these values at t = 1 (unnormalised for the side planes): near/far use xe, "left" (plane 2)
+      // th*x + y, "right" (3) th*x - y, top (4) tv*x - z, bottom (5) tv*x + z.
+      const float dL = fmaf(F.th, xe, ye), dR = fmaf(F.th, xe, -ye);
+      const float dT = fmaf(F.tv, xe, -ze), dB = fmaf(F.tv, xe, ze);
+      // classifier margin + float slop of the start point + 0.01 voxel for the drift of the DDA's own
+      // float t against the exact crossing parameter (<= ~5e-4 voxel over a ray)
+      const float m1 = F.m + 1e-4f + 0.01f * a.vs_f;
+      const float nh = __fdividef(F.mh, F.m), nv = __fdividef(F.mv, F.m);  // sqrt(1+th^2), sqrt(1+tv^2)
+      const bool up = ze >= 0.0f;                           // ray ends in the upper half: top is the nearer plane
+      const float d_nearv = up ? dT : dB, d_farv = up ? dB : dT;
+      const float sl_nearv = S.sl[(up ? 4 : 5) * yc + j], sl_farv = S.sl[(up ? 5 : 4) * yc + j];
+      if (xe > 0.0f && dL > 0.0f && dR > 0.0f && d_farv > 0.0f) {
         const float rx = __fdividef(1.0f, xe);
-        tlo = fmaxf(tlo, (F.nearp + slack) * rx);
-        tlo = fmaxf(tlo, __fdividef(F.mh * sc, dh));
-        tlo = fmaxf(tlo, __fdividef(F.mv * sc, dv_far));
-        thi = (F.farp - slack) * rx;
-        tlo_v = dv_near > 0.0f ? __fdividef(F.mv * sc, dv_near) : 3.0e38f;
+        tlo = fmaxf(tlo, (F.nearp + S.sl[0 * yc + j] + m1) * rx);
+        tlo = fmaxf(tlo, __fdividef((S.sl[2 * yc + j] + m1) * nh, dL));
+        tlo = fmaxf(tlo, __fdividef((S.sl[3 * yc + j] + m1) * nh, dR));
+        tlo = fmaxf(tlo, __fdividef((sl_farv + m1) * nv, d_farv));
+        thi = (F.farp - S.sl[1 * yc + j] - m1) * rx;
+        tlo_v = d_nearv > 0.0f ? __fdividef((sl_nearv + m1) * nv, d_nearv) : 3.0e38f;
       } else {
         tlo = 3.0e38f;  // degenerate frustum geometry for this ray: always use the classifier
       }
@@ -663,7 +683,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       tlo_v = fmaf(fabsf(tlo_v), 1e-4f, tlo_v) + 1e-5f;
       thi = fmaf(fabsf(thi), -1e-4f, thi) - 1e-5f;
       t_out = fmaf(fabsf(t_out), 1e-4f, t_out) + 1e-5f;
-      const int q = ze >= 0.0f ? 4 : 8;  // open vertical plane: top when the ray ends in the upper half
+      const int q = up ? 4 : 8;  // open vertical plane
       pa[0] = S.fp[(q + 0) * yc + j];
       pa[1] = S.fp[(q + 1) * yc + j];
       pa[2] = S.fp[(q + 2) * yc + j];
@@ -674,7 +694,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
     int P = ((g[2] - z0) * vey + (g[1] - y0)) * stride_y + 2 * (g[0] - x0);
     const int stx = 2 * sg[0], sty = stride_y * sg[1], stz = stride_z * sg[2];
 
-    unsigned acc = 0u, occ = 0u;  // acc: 10-bit fields, [0] unknown, [1] free, [2] skipped
+    unsigned acc = 0u, occ = 0u;  // acc: byte fields [0] unknown, [1] free, [2] skipped (rays have < 255 steps here)
     float tcur = 0.0f;
     int step = 0;
     for (; step <= len; ++step) {
@@ -696,20 +716,12 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
           // near, left/right and the farther of top/bottom are sure; open: the far plane once tcur >= thi,
           // the nearer of top/bottom while tcur <= tlo_v -> one single-precision plane evaluation each
           const float dx = (float)(g[0] - g0x), dy = (float)(g[1] - g0y), dz = (float)(g[2] - g0z);
-          bool any_out = false, any_und = false;
-          if (!(tcur < thi)) {
-            const float sf = fmaf(S.fp[0 * yc + j], dx, fmaf(S.fp[1 * yc + j], dy, fmaf(S.fp[2 * yc + j], dz, S.fp[3 * yc + j])));
-            any_out = sf < -F.m;
-            any_und = !any_out && !(sf > F.m);
-          }
-          if (!(tcur > tlo_v)) {
-            const float sv = fmaf(pa[0], dx, fmaf(pa[1], dy, fmaf(pa[2], dz, pc)));
-            any_out = any_out || sv < -F.m;
-            any_und = any_und || (!(sv < -F.m) && !(sv > F.m));
-          }
-          // one plane surely out settles it; otherwise a plane within its margin needs the exact test
-          decided = any_out || !any_und;
-          fin = !any_out && !any_und;
+          const float sf = fmaf(S.fp[0 * yc + j], dx, fmaf(S.fp[1 * yc + j], dy, fmaf(S.fp[2 * yc + j], dz, S.fp[3 * yc + j])));
+          const float sv = fmaf(pa[0], dx, fmaf(pa[1], dy, fmaf(pa[2], dz, pc)));
+          // the smaller of the open planes' signed distances decides: > m in, < -m out, else exact test
+          const float smin = fminf(tcur < thi ? 3.0e38f : sf, tcur > tlo_v ? 3.0e38f : sv);
+          fin = smin > F.m;
+          decided = fin || smin < -F.m;
         }
         if (!decided || kParanoid) {
           float xc, yk, zk;
@@ -756,7 +768,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
         ++step;  // this step was executed
         break;
       }
-      acc += 1u << (code * 10u);
+      acc += 1u << (code << 3);
       // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
       const bool c1 = t[1] < t[0];
       const float bm = c1 ? t[1] : t[0];
@@ -772,8 +784,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       t[2] = c2 ? __fadd_rn(t[2], dt[2]) : t[2];
     }
     my_steps += (unsigned long long)step;
-    if (acc & 1023u) atomicAdd(&S.cnt[0 * yc + j], acc & 1023u);
-    if ((acc >> 10) & 1023u) atomicAdd(&S.cnt[1 * yc + j], (acc >> 10) & 1023u);
+    if (acc & 255u) atomicAdd(&S.cnt[0 * yc + j], acc & 255u);
+    if ((acc >> 8) & 255u) atomicAdd(&S.cnt[1 * yc + j], (acc >> 8) & 255u);
     if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);
   }
 #pragma unroll

@@ -370,7 +370,8 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   bool dense = false;
   a.vmin = nullptr;
   a.vez = a.vwords = 0;
-  if ((variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0) {
+  // (byte-wide per-ray counters in that kernel: a ray has at most 3 * (reach + 2) + 1 < 255 steps)
+  if ((variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0 && 3 * (a.reach_vox + 2) + 1 < 255) {
     if (ctx->vmin_gen != ctx->cam_gen || ctx->vmin_yc != yc || ctx->vmin_vs != L->voxel_size) {
       std::vector<int> vmin((size_t)(360 / yc) * 5);
       ctx->vmin_ok = nbvgpu_host::dense_volume_bounds(T, a.vs, yc, vmin.data(), &ctx->vez, &ctx->vwords);
