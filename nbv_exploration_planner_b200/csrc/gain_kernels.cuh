@@ -691,7 +691,9 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
     }
     const float tA = fmaxf(tlo, tlo_v), tB = fminf(thi, t_out);  // window in which every test is sure
     // bit address of the start voxel in the dense volume and the per-axis strides
-    int P = ((g[2] - z0) * vey + (g[1] - y0)) * stride_y + 2 * (g[0] - x0);
+    // (the shared-window byte address of the volume is folded in: P = 8 * vol_s + bit offset, so the
+    // word address is (P >> 3) & ~3 and the bit position P & 31 -- vol_s is 16-byte aligned)
+    unsigned P = (unsigned)(((g[2] - z0) * vey + (g[1] - y0)) * stride_y + 2 * (g[0] - x0)) + 8u * vol_s;
     const int stx = 2 * sg[0], sty = stride_y * sg[1], stz = stride_z * sg[2];
 
     unsigned acc = 0u, occ = 0u;  // acc: byte fields [0] unknown, [1] free, [2] skipped (rays have < 255 steps here)
@@ -716,10 +718,11 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
           // near, left/right and the farther of top/bottom are sure; open: the far plane once tcur >= thi,
           // the nearer of top/bottom while tcur <= tlo_v -> one single-precision plane evaluation each
           const float dx = (float)(g[0] - g0x), dy = (float)(g[1] - g0y), dz = (float)(g[2] - g0z);
-          const float sf = fmaf(S.fp[0 * yc + j], dx, fmaf(S.fp[1 * yc + j], dy, fmaf(S.fp[2 * yc + j], dz, S.fp[3 * yc + j])));
+          float sf = 3.0e38f;
+          if (!(tcur < thi)) sf = fmaf(S.fp[0 * yc + j], dx, fmaf(S.fp[1 * yc + j], dy, fmaf(S.fp[2 * yc + j], dz, S.fp[3 * yc + j])));
           const float sv = fmaf(pa[0], dx, fmaf(pa[1], dy, fmaf(pa[2], dz, pc)));
           // the smaller of the open planes' signed distances decides: > m in, < -m out, else exact test
-          const float smin = fminf(tcur < thi ? 3.0e38f : sf, tcur > tlo_v ? 3.0e38f : sv);
+          const float smin = fminf(sf, tcur > tlo_v ? 3.0e38f : sv);
           fin = smin > F.m;
           decided = fin || smin < -F.m;
         }
@@ -748,8 +751,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       }
       // ---- exploration box + voxel status: one word of the dense volume (always in range)
       uint32_t w;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(vol_s + (((unsigned)P >> 3) & ~3u)));
-      unsigned code = __funnelshift_r(w, 0u, (unsigned)P) & 3u;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((P >> 3) & ~3u));
+      unsigned code = __funnelshift_r(w, 0u, P) & 3u;
       if (kParanoid) {
         unsigned want = 2u;
         if ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
@@ -760,7 +763,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
           const unsigned st = (__ldg(a.L.status + ((unsigned)slot * 256u + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
           want = st == 2u ? 3u : st;
         }
-        if (((unsigned)P >> 5) >= (unsigned)nvol || want != code) ++my_mismatch;
+        if (((P - 8u * vol_s) >> 5) >= (unsigned)nvol || want != code) ++my_mismatch;
       }
       code = fin ? code : 2u;
       if (code == 3u) {
@@ -775,7 +778,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       const bool c2 = t[2] < bm;
       tcur = c2 ? t[2] : bm;
       const bool m0 = !c1 && !c2, m1 = c1 && !c2;
-      P += c2 ? stz : (c1 ? sty : stx);
+      P += (unsigned)(c2 ? stz : (c1 ? sty : stx));
       g[0] += m0 ? sg[0] : 0;
       g[1] += m1 ? sg[1] : 0;
       g[2] += c2 ? sg[2] : 0;

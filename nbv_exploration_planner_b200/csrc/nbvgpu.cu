@@ -147,6 +147,7 @@ struct nbvgpu_ctx {
   bool vmin_ok = false;
   int force_yc = 0;  // NBVGPU_YC environment override (experiments)
   int dense_budget = 56 * 1024;  // shared memory per CTA the dense volume path may use (NBVGPU_DENSE_KB)
+  int smem_pad = 0;              // extra dynamic shared memory per CTA (NBVGPU_SMEM_PAD_KB; occupancy experiments)
   // optional CUDA-event timing of the ray-sweep kernel (nbvgpu_set_profiling)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -397,6 +398,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     }
   }
   const unsigned grid = (unsigned)(n * (size_t)(360 / yc));
+  smem += (size_t)ctx->smem_pad;
   cudaError_t e;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   if (ctx->profiling) {
@@ -499,6 +501,7 @@ int nbvgpu_create(int device, nbvgpu_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = std::getenv("NBVGPU_YC")) ctx->force_yc = std::atoi(e);
   if (const char* e = std::getenv("NBVGPU_DENSE_KB")) ctx->dense_budget = std::atoi(e) * 1024;
+  if (const char* e = std::getenv("NBVGPU_SMEM_PAD_KB")) ctx->smem_pad = std::atoi(e) * 1024;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   DeviceGuard guard(device);
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
