@@ -22,13 +22,8 @@
 // the exploration-box test is done on integer voxel thresholds (exactly equivalent, see
 // camera_host.cc); the six FP64 plane tests are preceded by a conservative single-precision
 // classifier in the camera frame that decides "surely inside" / "surely outside" with a margin
-// far above its rounding error and otherwise falls back to the exact FP64 planes.  All variants
-// therefore produce identical counts; VARIANT only selects how:
-//   0  fp32 classifier + 2-bit status tiles (default)
-//   1  FP64 plane tests on every step + {distance, weight} tile loads (plain transcription)
-//   2  variant 0 + cross-check of every classifier decision against the FP64 planes
-//      (mismatch counter must stay 0; used by the tests)
-//   3  fp32 classifier + {distance, weight} tile loads
+// far above its rounding error and otherwise falls back to the exact FP64 planes.  All variants and
+// modes therefore produce identical counts (see the comment above k_gain).
 #ifndef NBVGPU_GAIN_KERNELS_CUH_
 #define NBVGPU_GAIN_KERNELS_CUH_
 
@@ -212,33 +207,59 @@ __device__ __forceinline__ void to_camera(const FilterConst& F, float vs_f, floa
   zk = fmaf(F.R[6], x1, fmaf(F.R[7], y1, fmaf(F.R[8], rz, F.t[2])));
 }
 
-// VARIANT: see the header comment.  LV: log2(voxels per side) as a compile-time constant (0 = take
-// it from the layer at run time).  GRID: the shared-memory slot grid is in use (false: the reach is
-// too large for shared memory and blocks are probed in the global table with a per-lane cache).
+// ---------------------------------------------------------------------------------------------
+// k_gain<VARIANT, LV, MODE> -- the ray sweep.
 //
-// In-view decision per step, cheapest first (all exactness-preserving; VARIANT 2 cross-checks every
-// shortcut against the exact test):
-//   * every voxel is entered at a known ray parameter tcur (the DDA's own t); a voxel corner lies
-//     within sqrt(3) voxels of that entry point, and along the ray the signed distance to every
-//     bounding plane is linear in t.  Per ray this gives an interval (tlo, thi) in which the voxel
-//     is surely inside the exploration box and inside every frustum plane except possibly the
-//     nearer of top/bottom, and a tighter bound tlo_v beyond which that plane is sure as well;
-//   * between tlo and tlo_v only that one plane is open: one single-precision plane evaluation
-//     against the FP64 plane's coefficients (margin >> rounding error) settles it;
-//   * past t_out the ray has left the (convex) exploration box for good: the remaining voxels can
-//     contribute nothing and cannot stop the ray, so they are accounted as executed and skipped;
-//   * everything else: integer box test, single-precision classifier in the camera frame, and the
-//     exact FP64 plane tests when the classifier is within its margin.
-template <int VARIANT, int LV, bool GRID>
+// MODE selects how a step reads the map:
+//   kDense  the CTA first copies the 2-bit status of every voxel its rays can reach into a dense
+//           shared-memory volume [z][y][x words] (x word-aligned to the 16-voxel block rows, so whole
+//           status-tile words are copied), with the exploration box folded in as a 4th value.  A lane
+//           addresses it with ONE integer, the bit address P = 8*smem_base + ((z*Y + y)*Xw)*32 + 2*x:
+//           a DDA step along x/y/z adds +-2 / +-32*Xw / +-32*Xw*Y (the x carry into the next word is
+//           free) and the status is (lds[(P>>3)&~3] >> (P&31)) & 3 -- no box test, block lookup, tile
+//           address arithmetic or global load in the ray loop.  Needs 16^3 blocks, a volume that fits
+//           the shared-memory budget and rays shorter than 255 steps (byte-wide counters).
+//   kGrid   integer box test, tile slot from the shared-memory slot grid (one hash probe per reachable
+//           block in the prologue), one word of the status tile (or the {distance, weight} tile) through
+//           the read-only path.
+//   kProbe  as kGrid but the reach is too large for a shared-memory grid: global hash probes with a
+//           per-lane last-block cache.
+// VARIANT: 0 default; 1 plain transcription (FP64 planes on every step, {distance, weight} tiles);
+//   2 default with every shortcut cross-checked against the exact test (mismatch counter);
+//   3 default decisions but {distance, weight} tile loads.  LV: log2(voxels per side), 0 = run time.
+//
+// Voxel codes inside the loop: 0 unknown, 1 free, 2 skip (not in view), 3 occupied (stops the ray).
+//
+// In-view decision per step, cheapest first (all exactness-preserving):
+//   * every voxel is entered at a known ray parameter tcur (the DDA's own t).  The tested point is the
+//     MIN corner of the voxel that contains the ray point X, so n.corner >= n.X - vs*sum_i max(n_i,0),
+//     and n.X is linear in t.  Per ray: tlo (near, left, right and the farther of top/bottom are sure
+//     beyond it), tlo_v (the nearer of top/bottom is sure beyond it), thi (the far plane is sure before
+//     it), t_out (past it the ray has left the convex exploration box for good: the remaining voxels
+//     can neither count nor stop the ray -- they are accounted as executed and skipped);
+//   * between tlo and the all-sure window only the far plane and/or the nearer of top/bottom are open:
+//     one single-precision plane evaluation each, decided by the smaller signed distance;
+//   * else the single-precision classifier in the camera frame, and the exact FP64 planes when that
+//     is within its margin.
+// ---------------------------------------------------------------------------------------------
+enum { kDense = 0, kGrid = 1, kProbe = 2 };
+
+inline size_t dense_smem_bytes(int yc, int gn, int nvol) {
+  return (((size_t)nvol * 4 + 15) & ~(size_t)15) + gain_smem_bytes(yc, gn);
+}
+
+template <int VARIANT, int LV, int MODE>
 __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   constexpr bool kFilter = (VARIANT != 1);
   constexpr bool kStatusBits = (VARIANT == 0 || VARIANT == 2);
   constexpr bool kParanoid = (VARIANT == 2);
+  constexpr bool kIsDense = (MODE == kDense);
+  static_assert(!kIsDense || (LV == 4 && kStatusBits), "the dense volume copies 16-voxel status-tile words");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int yc = a.yc;
-  const int gn = GRID ? a.gnx * a.gny * a.gnz : 0;
-  const GainSmem S = carve(smem_raw, yc, gn);
-  const int* const sgrid = reinterpret_cast<const int*>(smem_raw);
+  const int gn = (MODE == kProbe) ? 0 : a.gnx * a.gny * a.gnz;
+  uint32_t* const vol = reinterpret_cast<uint32_t*>(smem_raw);
+  const GainSmem S = carve(smem_raw + (kIsDense ? (((size_t)a.vwords * 4 + 15) & ~(size_t)15) : 0), yc, gn);
   __shared__ int s_umax;
   __shared__ unsigned long long s_steps;
   __shared__ unsigned int s_mismatch;
@@ -249,6 +270,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   const int tid = threadIdx.x;
   const int lv = LV ? LV : a.L.log2vps;
   const int vm = (1 << lv) - 1;
+  const unsigned nvox = LV ? (1u << (3 * LV)) : (unsigned)a.L.nvox;
 
   const double px = a.pos[3 * v], py = a.pos[3 * v + 1], pz = a.pos[3 * v + 2];
   // Guard (the host entry points validate; device-resident inputs are caught here).
@@ -268,13 +290,12 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   const int g0x = (int)floor(px * a.vs_inv), g0y = (int)floor(py * a.vs_inv), g0z = (int)floor(pz * a.vs_inv);
   const int b0x = (g0x - a.reach_vox) >> lv, b0y = (g0y - a.reach_vox) >> lv, b0z = (g0z - a.reach_vox) >> lv;
 
-  // (a) local block-slot grid: one hash probe per reachable block.
+  // (a) block-slot grid: one hash probe per reachable block; (b) per-yaw frames
   for (int i = tid; i < gn; i += blockDim.x) {
     const int ix = i % a.gnx, iy = (i / a.gnx) % a.gny, iz = i / (a.gnx * a.gny);
     const int sl = probe_block(a.L, b0x + ix, b0y + iy, b0z + iz);
     S.grid[i] = sl < 0 ? a.unknown_slot : sl;
   }
-  // (b) per-yaw frames.
   for (int j = tid; j < yc; j += blockDim.x) {
     const int y = chunk * yc + j;
     build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, S.sl, a.vs,
@@ -282,19 +303,61 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   }
   __syncthreads();
   for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
+
+  // (c) dense status volume, one (y, z) row of Xw words per thread and iteration
+  int x0 = 0, y0 = 0, z0 = 0, vxw = 0, vey = 0, nvol = 0;
+  if (kIsDense) {
+    x0 = ((g0x + a.vmin[5 * chunk]) >> 4) << 4;  // origin: global voxel index, x aligned down to a block row
+    y0 = g0y + a.vmin[5 * chunk + 1];
+    z0 = g0z + a.vmin[5 * chunk + 2];
+    vxw = a.vmin[5 * chunk + 3];
+    vey = a.vmin[5 * chunk + 4];
+    nvol = vxw * vey * a.vez;
+    for (int row = tid; row < vey * a.vez; row += blockDim.x) {
+      const int gy = y0 + row % vey, gz = z0 + row / vey;
+      const bool row_in = (unsigned)(gy - a.gmin[1]) <= a.gspan[1] && (unsigned)(gz - a.gmin[2]) <= a.gspan[2];
+      const int iy = (gy >> 4) - b0y, iz = (gz >> 4) - b0z;
+      const bool row_grid = (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz;
+      const unsigned rowoff = (unsigned)(((gz & 15) << 4) | (gy & 15));
+      for (int wx = 0; wx < vxw; ++wx) {
+        const int gx = x0 + 16 * wx;
+        uint32_t word = 0xAAAAAAAAu;  // 16 x "skip"
+        const long long lo = (long long)a.gmin[0] - gx, hi = lo + (long long)a.gspan[0];  // in-box x range inside the word
+        if (row_in && hi >= 0 && lo <= 15) {
+          const int ix = (gx >> 4) - b0x;
+          int slot;
+          if (row_grid && (unsigned)ix < (unsigned)a.gnx) {
+            slot = S.grid[(iz * a.gny + iy) * a.gnx + ix];
+          } else {
+            slot = probe_block(a.L, gx >> 4, gy >> 4, gz >> 4);
+            if (slot < 0) slot = a.unknown_slot;
+          }
+          word = __ldg(a.L.status + ((unsigned)slot * 256u + rowoff));
+          word |= (word >> 1) & 0x55555555u;  // tile status 2 (occupied) -> code 3
+          const int l = lo > 0 ? (int)lo : 0, h = hi < 15 ? (int)hi : 15;
+          const uint32_t below = (1u << (2 * l)) - 1u;                                  // voxels < l
+          const uint32_t upto = h == 15 ? 0xFFFFFFFFu : ((1u << (2 * (h + 1))) - 1u);  // voxels <= h
+          const uint32_t outm = below | ~upto;
+          word = (word & ~outm) | (outm & 0xAAAAAAAAu);
+        }
+        vol[row * vxw + wx] = word;
+      }
+    }
+  }
   __syncthreads();
   const int n_rays = s_umax * yc;
-  // grid index of block (bx,by,bz) = (bz*gny + by)*gnx + bx + gbase
-  const int gbase = -((b0z * a.gny + b0y) * a.gnx + b0x);
+  const int gbase = -((b0z * a.gny + b0y) * a.gnx + b0x);  // grid index of block (bx,by,bz) = (bz*gny + by)*gnx + bx + gbase
+  const int* const sgrid = S.grid;
 
   // Offset of the candidate inside its voxel (classifier works relative to g0).
   const float noffx = -__double2float_rn(px - (double)g0x * a.vs);
   const float noffy = -__double2float_rn(py - (double)g0y * a.vs);
   const float noffz = -__double2float_rn(pz - (double)g0z * a.vs);
   const FilterConst& F = a.F;
-  // "Surely in view" slack: a voxel corner is within sqrt(3) voxels of the ray point at which the
-  // voxel is entered; 1.8 voxels + classifier margin + float slop of the start point.
-  const float slack = 1.8f * a.vs_f + F.m + 1e-4f;
+  const int stride_y = 32 * vxw, stride_z = 32 * vxw * vey;
+  uint32_t vol_s = (uint32_t)__cvta_generic_to_shared(vol);
+  asm volatile("mov.u32 %0, %0;" : "+r"(vol_s));  // opaque: keep the shared-window address in a register
+  constexpr unsigned kCountShift = kIsDense ? 3u : 4u;  // per-ray counter fields: bytes (dense) or 16-bit halves
 
   const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   unsigned long long my_steps = 0ull;
@@ -311,7 +374,6 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     float t[3], dt[3];
     int len = 0;
     float tlo = 0.0f, thi = 3.0e38f, tlo_v = 0.0f, t_out = 3.0e38f;
-    float pa[3] = {0.f, 0.f, 0.f}, pc = 0.f;  // open top/bottom plane, single precision, relative to g0
     float e3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -326,333 +388,17 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
       const float shifted = __fsub_rn(sk, (float)g[k]);
       const float dist = __fsub_rn((float)max(0, sg[k]), shifted);
-      t[k] = __fdiv_rn(dist, rr);           // +-inf / NaN when rr == 0, as in the reference
+      t[k] = __fdiv_rn(dist, rr);  // exact IEEE division (+-inf / NaN when rr == 0): the reference's arithmetic
       dt[k] = __fdiv_rn((float)sg[k], rr);
       if (kFilter) {
-        // g is surely outside the (convex) exploration box once s + t*r has passed a bound by
-        // 1.02 voxels in the direction of travel
+        // g is surely outside the (convex) exploration box once s + t*r has passed a bound by 1.02 voxels in
+        // the direction of travel.  Conservative bounds may use the fast division: padded by 1e-4 relative.
         const float bmin = (float)a.gmin[k], bmax = (float)a.gmin[k] + (float)a.gspan[k];
-        if (rr != 0.0f) {
-          const float qo = (rr > 0.0f ? (bmax + 1.02f - sk) : (bmin - 0.02f - sk)) / rr;
-          t_out = fminf(t_out, qo);
-        }
+        if (rr != 0.0f) t_out = fminf(t_out, __fdividef(rr > 0.0f ? (bmax + 1.02f - sk) : (bmin - 0.02f - sk), rr));
       }
     }
+    float pa[3] = {0.f, 0.f, 0.f}, pc = 0.f;  // the open one of top/bottom, single precision, relative to g0
     if (kFilter) {
-      // frustum: camera-frame coordinates grow linearly from ~0 at the camera to Pc(end) at t = 1
-      float xe, ye, ze;
-      to_camera(F, a.vs_f, e3[0] - (float)g0x, e3[1] - (float)g0y, e3[2] - (float)g0z, noffx, noffy, noffz, S.csf[j],
-                S.csf[yc + j], xe, ye, ze);
-      const float dh = fmaf(F.th, xe, -fabsf(ye));
-      const float dv_near = fmaf(F.tv, xe, -fabsf(ze)), dv_far = fmaf(F.tv, xe, fabsf(ze));
-      if (xe > 0.0f && dh > 0.0f && dv_far > 0.0f) {
-        const float sc = slack / F.m;  // margins scale with the plane normalisation
-        tlo = fmaxf(tlo, (F.nearp + slack) / xe);
-        tlo = fmaxf(tlo, (F.mh * sc) / dh);
-        tlo = fmaxf(tlo, (F.mv * sc) / dv_far);
-        thi = fminf(thi, (F.farp - slack) / xe);
-        tlo_v = dv_near > 0.0f ? (F.mv * sc) / dv_near : 3.0e38f;
-      } else {
-        thi = -1.0f;
-      }
-      tlo = fmaf(fabsf(tlo), 1e-5f, tlo) + 1e-6f;
-      tlo_v = fmaf(fabsf(tlo_v), 1e-5f, tlo_v) + 1e-6f;
-      thi = fmaf(fabsf(thi), -1e-5f, thi) - 1e-6f;
-      t_out = fmaf(fabsf(t_out), 1e-5f, t_out) + 1e-6f;
-      // the open plane: top (index 4) when the ray ends in the upper half of the frustum, else bottom
-      // (5); s(g) = n.(g*vs) - d = sum_k (n_k*vs)*(g_k - g0_k) + (n.(g0*vs) - d), from the FP64 plane.
-      const int q = ze >= 0.0f ? 4 : 8;
-      pa[0] = S.fp[(q + 0) * yc + j];
-      pa[1] = S.fp[(q + 1) * yc + j];
-      pa[2] = S.fp[(q + 2) * yc + j];
-      pc = S.fp[(q + 3) * yc + j];
-    }
-
-    unsigned acc = 0u, occ = 0u;  // acc: unknown count (bits 0-15) | free count (bits 16-31); < 65536 steps per ray
-    int cbx = INT_MIN, cby = 0, cbz = 0, cslot = a.unknown_slot;
-    float tcur = 0.0f;
-    int step = 0;
-    for (; step <= len; ++step) {
-      // ---- in-view test (camera_model.cpp:191-201) on the voxel corner g * vs
-      // exploration box first (integer thresholds, exact) ...
-      bool inview = (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
-                    (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
-      if (kFilter && !inview && tcur > t_out) {
-        if (kParanoid) {
-          // keep walking and verify that no later voxel re-enters the box
-        } else {
-          step = len + 1;  // the reference walks the remaining voxels; none of them can be in view
-          break;
-        }
-      }
-      if (kParanoid && inview && tcur > t_out) ++my_mismatch;
-      // ... then the frustum, cheapest decision first
-      if (inview) {
-        bool decided = false, fin = false;
-        if (kFilter && tcur > tlo && tcur < thi) {
-          if (tcur > tlo_v) {
-            fin = true;
-            decided = true;
-          } else {
-            const float sv = fmaf(pa[0], (float)(g[0] - g0x), fmaf(pa[1], (float)(g[1] - g0y), fmaf(pa[2], (float)(g[2] - g0z), pc)));
-            fin = sv > F.m;
-            decided = fin || sv < -F.m;
-          }
-        }
-        if (!decided || kParanoid) {
-          bool ex;
-          if (kFilter) {
-            float xc, yk, zk;
-            to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
-                      S.csf[yc + j], xc, yk, zk);
-            const float s0 = xc - F.nearp, s1 = F.farp - xc;
-            const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
-            const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
-            const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
-            if (kParanoid) {
-              ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-              if ((sure_in && !ex) || (sure_out && ex) || (decided && fin != ex)) ++my_mismatch;
-            } else if (sure_in) {
-              ex = true;
-            } else if (sure_out) {
-              ex = false;
-            } else {
-              ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-            }
-          } else {
-            ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-          }
-          fin = ex;
-        }
-        inview = fin;
-      }
-      if (inview) {
-        // ---- voxel status (voxblox_manager.cpp:14-33) through the shared-memory slot grid; blocks that
-        // are not allocated map to the all-unknown tile (slot == max_blocks)
-        const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
-        int slot;
-        if (GRID) {
-          slot = sgrid[(bz * a.gny + by) * a.gnx + bx + gbase];
-        } else {
-          if (bx != cbx || by != cby || bz != cbz) {
-            cbx = bx; cby = by; cbz = bz;
-            cslot = probe_block(a.L, bx, by, bz);
-            if (cslot < 0) cslot = a.unknown_slot;
-          }
-          slot = cslot;
-        }
-        const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
-        const unsigned nvox = LV ? (1u << (3 * LV)) : (unsigned)a.L.nvox;
-        unsigned status;
-        if (kStatusBits) {
-          const uint32_t w = __ldg(a.L.status + ((unsigned)slot * (nvox >> 4) + (lin >> 4)));
-          status = (w >> ((lin & 15u) * 2u)) & 3u;
-        } else {
-          const float2 vx = __ldg(reinterpret_cast<const float2*>(a.L.tiles) + ((size_t)slot * nvox + lin));
-          status = tsdf_status(vx.x, vx.y);
-        }
-        if (status == 2u) {
-          occ = 1u;
-          ++step;  // this step was executed
-          break;
-        }
-        acc += 1u << (status << 4);  // unknown in the low half, free in the high half
-      }
-      // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
-      const bool c1 = t[1] < t[0];
-      const float bm = c1 ? t[1] : t[0];
-      const bool c2 = t[2] < bm;
-      tcur = c2 ? t[2] : bm;  // ray parameter at which the next voxel is entered
-      const bool m0 = !c1 && !c2, m1 = c1 && !c2;
-      g[0] += m0 ? sg[0] : 0;
-      g[1] += m1 ? sg[1] : 0;
-      g[2] += c2 ? sg[2] : 0;
-      t[0] = m0 ? __fadd_rn(t[0], dt[0]) : t[0];
-      t[1] = m1 ? __fadd_rn(t[1], dt[1]) : t[1];
-      t[2] = c2 ? __fadd_rn(t[2], dt[2]) : t[2];
-    }
-    my_steps += (unsigned long long)step;
-    if (acc & 0xFFFFu) atomicAdd(&S.cnt[0 * yc + j], acc & 0xFFFFu);
-    if (acc >> 16) atomicAdd(&S.cnt[1 * yc + j], acc >> 16);
-    if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);
-  }
-  // ---- CTA epilogue
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
-    my_mismatch += __shfl_xor_sync(0xffffffffu, my_mismatch, o);
-  }
-  if (lane == 0) {
-    atomicAdd(&s_steps, my_steps);
-    if (kParanoid) atomicAdd(&s_mismatch, my_mismatch);
-  }
-  __syncthreads();
-  for (int i = tid; i < 3 * yc; i += blockDim.x) {
-    const int k = i / yc, j = i - k * yc;
-    a.per_yaw[((size_t)v * 360 + chunk * yc + j) * 3 + k] = S.cnt[k * yc + j];
-  }
-  if (tid == 0) {
-    unsigned long long rays = 0ull;
-    for (int j = 0; j < yc; ++j) rays += (unsigned long long)S.um[j];
-    if (a.steps) atomicAdd(a.steps + v, s_steps);
-    atomicAdd(a.totals + 0, rays);
-    atomicAdd(a.totals + 1, s_steps);
-    if (kParanoid && s_mismatch) atomicAdd(a.totals + 3, (unsigned long long)s_mismatch);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// k_gain_dense: same sweep, but the CTA first copies the 2-bit status of every voxel its rays can
-// reach into a dense shared-memory volume [vez][vey][vxw words] (x word-aligned to the 16-voxel
-// block rows, so whole status-tile words are copied), with the exploration box folded in as a 4th
-// value (3 = outside the box: neither counted nor able to stop the ray).  A lane addresses the volume
-// with ONE integer: the bit address P = ((z*vey + y)*vxw)*32 + 2*x; a DDA step along x/y/z adds
-// +-2 / +-32*vxw / +-32*vxw*vey (the x carry into the next word comes for free), and the status is
-// (vol[P >> 5] >> (P & 31)) & 3.  The ray loop therefore has no box test, no block lookup, no tile
-// address arithmetic and no global load.  Requires 16 voxels per side and a volume that fits the
-// shared-memory budget; otherwise k_gain (slot grid / hash probes) is used.  VARIANT 2 cross-checks
-// every fetched status against the direct (box test + status tile) path and every frustum shortcut
-// against the exact planes.
-// ---------------------------------------------------------------------------------------------
-inline size_t dense_smem_bytes(int yc, int gn, int nvol) {
-  return (((size_t)nvol * 4 + 15) & ~(size_t)15) + gain_smem_bytes(yc, gn);
-}
-
-template <int VARIANT>
-__global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a) {
-  constexpr bool kParanoid = (VARIANT == 2);
-  constexpr int lv = 4, vm = 15;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int yc = a.yc;
-  const int gn = a.gnx * a.gny * a.gnz;
-  uint32_t* const vol = reinterpret_cast<uint32_t*>(smem_raw);
-  const GainSmem S = carve(smem_raw + (((size_t)a.vwords * 4 + 15) & ~(size_t)15), yc, gn);
-  __shared__ int s_umax;
-  __shared__ unsigned long long s_steps;
-  __shared__ unsigned int s_mismatch;
-
-  const int chunks = 360 / yc;
-  const int v = blockIdx.x / chunks;
-  const int chunk = blockIdx.x - v * chunks;
-  const int tid = threadIdx.x;
-
-  const double px = a.pos[3 * v], py = a.pos[3 * v + 1], pz = a.pos[3 * v + 2];
-  const double lim = 4194304.0 - (double)a.reach_vox - 2.0;
-  const bool bad = !(fabs(px * a.vs_inv) < lim) || !(fabs(py * a.vs_inv) < lim) || !(fabs(pz * a.vs_inv) < lim);
-  if (tid == 0) {
-    s_umax = 0;
-    s_steps = 0ull;
-    s_mismatch = 0u;
-  }
-  if (bad) {
-    for (int j = tid; j < yc; j += blockDim.x)
-      for (int k = 0; k < 3; ++k) a.per_yaw[((size_t)v * 360 + chunk * yc + j) * 3 + k] = 0u;
-    return;
-  }
-  const int g0x = (int)floor(px * a.vs_inv), g0y = (int)floor(py * a.vs_inv), g0z = (int)floor(pz * a.vs_inv);
-  const int b0x = (g0x - a.reach_vox) >> lv, b0y = (g0y - a.reach_vox) >> lv, b0z = (g0z - a.reach_vox) >> lv;
-  // volume origin (global voxel index; x aligned down to a block row) and this chunk's dimensions
-  const int x0 = ((g0x + a.vmin[5 * chunk]) >> lv) << lv;
-  const int y0 = g0y + a.vmin[5 * chunk + 1];
-  const int z0 = g0z + a.vmin[5 * chunk + 2];
-  const int vxw = a.vmin[5 * chunk + 3], vey = a.vmin[5 * chunk + 4], vez = a.vez;
-  const int nvol = vxw * vey * vez;
-
-  // (a) block-slot grid, (b) per-yaw frames
-  for (int i = tid; i < gn; i += blockDim.x) {
-    const int ix = i % a.gnx, iy = (i / a.gnx) % a.gny, iz = i / (a.gnx * a.gny);
-    const int sl = probe_block(a.L, b0x + ix, b0y + iy, b0z + iz);
-    S.grid[i] = sl < 0 ? a.unknown_slot : sl;
-  }
-  for (int j = tid; j < yc; j += blockDim.x) {
-    const int y = chunk * yc + j;
-    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, S.sl, a.vs,
-                    g0x, g0y, g0z, yc, j, px, py, pz);
-  }
-  __syncthreads();
-  for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
-  // (c) dense status volume, one (y, z) row of vxw words per thread and iteration.  Volume codes:
-  // 0 unknown, 1 free, 2 skip (outside the exploration box), 3 occupied.
-  for (int row = tid; row < vey * vez; row += blockDim.x) {
-    const int gy = y0 + row % vey, gz = z0 + row / vey;
-    const bool row_in = (unsigned)(gy - a.gmin[1]) <= a.gspan[1] && (unsigned)(gz - a.gmin[2]) <= a.gspan[2];
-    const int iy = (gy >> lv) - b0y, iz = (gz >> lv) - b0z;
-    const bool row_grid = (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz;
-    const unsigned rowoff = (unsigned)(((gz & vm) << lv) | (gy & vm));
-    for (int wx = 0; wx < vxw; ++wx) {
-      const int gx = x0 + 16 * wx;
-      uint32_t word = 0xAAAAAAAAu;
-      const long long lo = (long long)a.gmin[0] - gx, hi = lo + (long long)a.gspan[0];  // in-box x range inside the word
-      if (row_in && hi >= 0 && lo <= 15) {
-        const int ix = (gx >> lv) - b0x;
-        int slot;
-        if (row_grid && (unsigned)ix < (unsigned)a.gnx) {
-          slot = S.grid[(iz * a.gny + iy) * a.gnx + ix];
-        } else {
-          slot = probe_block(a.L, gx >> lv, gy >> lv, gz >> lv);
-          if (slot < 0) slot = a.unknown_slot;
-        }
-        word = __ldg(a.L.status + ((unsigned)slot * 256u + rowoff));
-        word |= (word >> 1) & 0x55555555u;  // tile code 2 (occupied) -> volume code 3
-        const int l = lo > 0 ? (int)lo : 0, h = hi < 15 ? (int)hi : 15;
-        const uint32_t below = (1u << (2 * l)) - 1u;                                   // voxels < l
-        const uint32_t upto = h == 15 ? 0xFFFFFFFFu : ((1u << (2 * (h + 1))) - 1u);   // voxels <= h
-        const uint32_t outm = below | ~upto;
-        word = (word & ~outm) | (outm & 0xAAAAAAAAu);
-      }
-      vol[row * vxw + wx] = word;
-    }
-  }
-  __syncthreads();
-  const int n_rays = s_umax * yc;
-
-  const float noffx = -__double2float_rn(px - (double)g0x * a.vs);
-  const float noffy = -__double2float_rn(py - (double)g0y * a.vs);
-  const float noffz = -__double2float_rn(pz - (double)g0z * a.vs);
-  const FilterConst& F = a.F;
-  const int stride_y = 32 * vxw, stride_z = 32 * vxw * vey;
-  uint32_t vol_s = (uint32_t)__cvta_generic_to_shared(vol);
-  asm volatile("mov.u32 %0, %0;" : "+r"(vol_s));  // opaque: keep the shared-window address in a register
-
-  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  unsigned long long my_steps = 0ull;
-  unsigned int my_mismatch = 0u;
-
-  for (int base = warp * 32; base < n_rays; base += nwarps * 32) {
-    const int r = base + lane;
-    const int u = r / yc;
-    const int j = r - u * yc;
-    if (r >= n_rays || u >= S.um[j]) continue;
-
-    int g[3], sg[3];
-    float t[3], dt[3];
-    int len = 0;
-    float tlo = 0.0f, thi = 3.0e38f, tlo_v = 0.0f, t_out = 3.0e38f;
-    float e3[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float sk = S.st[k * yc + j];
-      const double pos = dadd(dadd(S.rd[k * yc + j], dmul(dmul((double)u, S.rd[(3 + k) * yc + j]), a.vs)), S.rd[(6 + k) * yc + j]);
-      const float ek = __double2float_rn(dmul(pos, a.vs_inv));
-      e3[k] = ek;
-      g[k] = (int)floorf(__fadd_rn(sk, 1e-6f));
-      const int ei = (int)floorf(__fadd_rn(ek, 1e-6f));
-      len += abs(ei - g[k]);
-      const float rr = __fsub_rn(ek, sk);
-      sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
-      const float shifted = __fsub_rn(sk, (float)g[k]);
-      const float dist = __fsub_rn((float)max(0, sg[k]), shifted);
-      t[k] = __fdiv_rn(dist, rr);  // exact IEEE division: part of the reference's arithmetic
-      dt[k] = __fdiv_rn((float)sg[k], rr);
-      // conservative bounds below may use the fast division: they are padded by 1e-5 relative
-      const float bmin = (float)a.gmin[k], bmax = (float)a.gmin[k] + (float)a.gspan[k];
-      if (rr != 0.0f) {
-        const float qo = __fdividef(rr > 0.0f ? (bmax + 1.02f - sk) : (bmin - 0.02f - sk), rr);
-        t_out = fminf(t_out, qo);
-      }
-    }
-    float pa[3], pc;
-    {
       float xe, ye, ze;
       to_camera(F, a.vs_f, e3[0] - (float)g0x, e3[1] - (float)g0y, e3[2] - (float)g0z, noffx, noffy, noffz, S.csf[j],
                 S.csf[yc + j], xe, ye, ze);
@@ -665,7 +411,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       // float t against the exact crossing parameter (<= ~5e-4 voxel over a ray)
       const float m1 = F.m + 1e-4f + 0.01f * a.vs_f;
       const float nh = __fdividef(F.mh, F.m), nv = __fdividef(F.mv, F.m);  // sqrt(1+th^2), sqrt(1+tv^2)
-      const bool up = ze >= 0.0f;                           // ray ends in the upper half: top is the nearer plane
+      const bool up = ze >= 0.0f;  // the ray ends in the upper half: top is the nearer plane
       const float d_nearv = up ? dT : dB, d_farv = up ? dB : dT;
       const float sl_nearv = S.sl[(up ? 4 : 5) * yc + j], sl_farv = S.sl[(up ? 5 : 4) * yc + j];
       if (xe > 0.0f && dL > 0.0f && dR > 0.0f && d_farv > 0.0f) {
@@ -683,102 +429,143 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       tlo_v = fmaf(fabsf(tlo_v), 1e-4f, tlo_v) + 1e-5f;
       thi = fmaf(fabsf(thi), -1e-4f, thi) - 1e-5f;
       t_out = fmaf(fabsf(t_out), 1e-4f, t_out) + 1e-5f;
-      const int q = up ? 4 : 8;  // open vertical plane
+      const int q = up ? 4 : 8;
       pa[0] = S.fp[(q + 0) * yc + j];
       pa[1] = S.fp[(q + 1) * yc + j];
       pa[2] = S.fp[(q + 2) * yc + j];
       pc = S.fp[(q + 3) * yc + j];
     }
     const float tA = fmaxf(tlo, tlo_v), tB = fminf(thi, t_out);  // window in which every test is sure
-    // bit address of the start voxel in the dense volume and the per-axis strides
-    // (the shared-window byte address of the volume is folded in: P = 8 * vol_s + bit offset, so the
-    // word address is (P >> 3) & ~3 and the bit position P & 31 -- vol_s is 16-byte aligned)
-    unsigned P = (unsigned)(((g[2] - z0) * vey + (g[1] - y0)) * stride_y + 2 * (g[0] - x0)) + 8u * vol_s;
-    const int stx = 2 * sg[0], sty = stride_y * sg[1], stz = stride_z * sg[2];
+    // dense volume: bit address of the start voxel (the shared-window byte address of the volume is folded
+    // in: word address (P >> 3) & ~3, bit position P & 31; vol_s is 16-byte aligned) and per-axis strides
+    unsigned P = 0u;
+    int stx = 0, sty = 0, stz = 0;
+    if (kIsDense) {
+      P = (unsigned)(((g[2] - z0) * vey + (g[1] - y0)) * stride_y + 2 * (g[0] - x0)) + 8u * vol_s;
+      stx = 2 * sg[0];
+      sty = stride_y * sg[1];
+      stz = stride_z * sg[2];
+    }
 
-    unsigned acc = 0u, occ = 0u;  // acc: byte fields [0] unknown, [1] free, [2] skipped (rays have < 255 steps here)
+    unsigned acc = 0u, occ = 0u;  // acc: per-code counter fields (kCountShift bits apart)
+    int cbx = INT_MIN, cby = 0, cbz = 0, cslot = a.unknown_slot;
     float tcur = 0.0f;
     int step = 0;
     for (; step <= len; ++step) {
+      // ---- exploration box (integer thresholds, exact); folded into the volume in dense mode
+      bool inbox = true;
+      if (!kIsDense || kParanoid)
+        inbox = (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+                (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
       // ---- frustum (camera_model.cpp:194-199), cheapest decision first
       bool fin = true;
-      if (!(tcur > tA && tcur < tB) || kParanoid) {
+      if (!kFilter) {
+        fin = inbox && exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+      } else if (!(tcur > tA && tcur < tB) || kParanoid) {
         if (tcur > t_out) {  // left the convex exploration box for good
           if (!kParanoid) {
             step = len + 1;
             break;
           }
-          if ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
-              (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2])
-            ++my_mismatch;
+          if (inbox) ++my_mismatch;
         }
         bool decided = false;
         fin = false;
-        if (tcur > tlo) {
-          // near, left/right and the farther of top/bottom are sure; open: the far plane once tcur >= thi,
-          // the nearer of top/bottom while tcur <= tlo_v -> one single-precision plane evaluation each
-          const float dx = (float)(g[0] - g0x), dy = (float)(g[1] - g0y), dz = (float)(g[2] - g0z);
-          float sf = 3.0e38f;
-          if (!(tcur < thi)) sf = fmaf(S.fp[0 * yc + j], dx, fmaf(S.fp[1 * yc + j], dy, fmaf(S.fp[2 * yc + j], dz, S.fp[3 * yc + j])));
-          const float sv = fmaf(pa[0], dx, fmaf(pa[1], dy, fmaf(pa[2], dz, pc)));
-          // the smaller of the open planes' signed distances decides: > m in, < -m out, else exact test
-          const float smin = fminf(sf, tcur > tlo_v ? 3.0e38f : sv);
-          fin = smin > F.m;
-          decided = fin || smin < -F.m;
-        }
-        if (!decided || kParanoid) {
-          float xc, yk, zk;
-          to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
-                    S.csf[yc + j], xc, yk, zk);
-          const float s0 = xc - F.nearp, s1 = F.farp - xc;
-          const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
-          const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
-          const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
-          bool ex;
-          if (kParanoid) {
-            ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-            const bool fast_all = tcur > tA && tcur < tB;
-            if ((sure_in && !ex) || (sure_out && ex) || (decided && fin != ex) || (fast_all && !ex)) ++my_mismatch;
-          } else if (sure_in) {
-            ex = true;
-          } else if (sure_out) {
-            ex = false;
-          } else {
-            ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+        if (kIsDense || inbox) {
+          if (tcur > tlo) {
+            // near, left/right and the farther of top/bottom are sure; open: the far plane once tcur >= thi,
+            // the nearer of top/bottom while tcur <= tlo_v -> one single-precision plane evaluation each
+            const float dx = (float)(g[0] - g0x), dy = (float)(g[1] - g0y), dz = (float)(g[2] - g0z);
+            float sf = 3.0e38f;
+            if (!(tcur < thi)) sf = fmaf(S.fp[0 * yc + j], dx, fmaf(S.fp[1 * yc + j], dy, fmaf(S.fp[2 * yc + j], dz, S.fp[3 * yc + j])));
+            const float sv = fmaf(pa[0], dx, fmaf(pa[1], dy, fmaf(pa[2], dz, pc)));
+            // the smaller of the open planes' signed distances decides: > m in, < -m out, else exact test
+            const float smin = fminf(sf, tcur > tlo_v ? 3.0e38f : sv);
+            fin = smin > F.m;
+            decided = fin || smin < -F.m;
           }
-          fin = ex;
+          if (!decided || kParanoid) {
+            float xc, yk, zk;
+            to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
+                      S.csf[yc + j], xc, yk, zk);
+            const float s0 = xc - F.nearp, s1 = F.farp - xc;
+            const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
+            const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
+            const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
+            bool ex;
+            if (kParanoid) {
+              ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+              const bool fast_all = tcur > tA && tcur < tB;
+              if ((sure_in && !ex) || (sure_out && ex) || (decided && fin != ex) || (fast_all && !ex)) ++my_mismatch;
+            } else if (sure_in) {
+              ex = true;
+            } else if (sure_out) {
+              ex = false;
+            } else {
+              ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+            }
+            fin = ex;
+          }
         }
+      } else if (!kIsDense) {
+        fin = inbox;  // inside the all-sure window the box is sure as well only up to t_out, which tB includes;
+                      // the integer test is kept as the authority (cheap) -- and cross-checked in variant 2
       }
-      // ---- exploration box + voxel status: one word of the dense volume (always in range)
-      uint32_t w;
-      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((P >> 3) & ~3u));
-      unsigned code = __funnelshift_r(w, 0u, P) & 3u;
-      if (kParanoid) {
-        unsigned want = 2u;
-        if ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
-            (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2]) {
-          int slot = probe_block(a.L, g[0] >> lv, g[1] >> lv, g[2] >> lv);
-          if (slot < 0) slot = a.unknown_slot;
-          const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
-          const unsigned st = (__ldg(a.L.status + ((unsigned)slot * 256u + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
-          want = st == 2u ? 3u : st;
+      // ---- voxel code: 0 unknown, 1 free, 2 skip, 3 occupied (voxblox_manager.cpp:14-33)
+      unsigned code = 2u;
+      if (kIsDense) {
+        uint32_t w;  // one word of the dense volume (always in range)
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((P >> 3) & ~3u));
+        code = __funnelshift_r(w, 0u, P) & 3u;
+        if (kParanoid) {
+          unsigned want = 2u;
+          if (inbox) {
+            int slot = probe_block(a.L, g[0] >> lv, g[1] >> lv, g[2] >> lv);
+            if (slot < 0) slot = a.unknown_slot;
+            const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
+            const unsigned st = (__ldg(a.L.status + ((unsigned)slot * (nvox >> 4) + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
+            want = st == 2u ? 3u : st;
+          }
+          if (((P - 8u * vol_s) >> 5) >= (unsigned)nvol || want != code) ++my_mismatch;
         }
-        if (((P - 8u * vol_s) >> 5) >= (unsigned)nvol || want != code) ++my_mismatch;
+        code = fin ? code : 2u;
+      } else if (fin) {
+        const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
+        int slot;
+        if (MODE == kGrid) {
+          slot = sgrid[(bz * a.gny + by) * a.gnx + bx + gbase];
+        } else {
+          if (bx != cbx || by != cby || bz != cbz) {
+            cbx = bx; cby = by; cbz = bz;
+            cslot = probe_block(a.L, bx, by, bz);
+            if (cslot < 0) cslot = a.unknown_slot;  // all-unknown tile
+          }
+          slot = cslot;
+        }
+        const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
+        unsigned st;
+        if (kStatusBits) {
+          st = (__ldg(a.L.status + ((unsigned)slot * (nvox >> 4) + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
+        } else {
+          const float2 vx = __ldg(reinterpret_cast<const float2*>(a.L.tiles) + ((size_t)slot * nvox + lin));
+          st = tsdf_status(vx.x, vx.y);
+        }
+        code = st | (st >> 1);  // 2 (occupied) -> 3
       }
-      code = fin ? code : 2u;
       if (code == 3u) {
         occ = 1u;
         ++step;  // this step was executed
         break;
       }
-      acc += 1u << (code << 3);
+      if (kIsDense) acc += 1u << (code << kCountShift);
+      else acc += (code == 2u) ? 0u : (1u << (code << kCountShift));
       // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
       const bool c1 = t[1] < t[0];
       const float bm = c1 ? t[1] : t[0];
       const bool c2 = t[2] < bm;
-      tcur = c2 ? t[2] : bm;
+      tcur = c2 ? t[2] : bm;  // ray parameter at which the next voxel is entered
       const bool m0 = !c1 && !c2, m1 = c1 && !c2;
-      P += (unsigned)(c2 ? stz : (c1 ? sty : stx));
+      if (kIsDense) P += (unsigned)(c2 ? stz : (c1 ? sty : stx));
       g[0] += m0 ? sg[0] : 0;
       g[1] += m1 ? sg[1] : 0;
       g[2] += c2 ? sg[2] : 0;
@@ -787,10 +574,13 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain_dense(const GainArgs a
       t[2] = c2 ? __fadd_rn(t[2], dt[2]) : t[2];
     }
     my_steps += (unsigned long long)step;
-    if (acc & 255u) atomicAdd(&S.cnt[0 * yc + j], acc & 255u);
-    if ((acc >> 8) & 255u) atomicAdd(&S.cnt[1 * yc + j], (acc >> 8) & 255u);
+    const unsigned fmask = (1u << (1u << kCountShift)) - 1u;
+    const unsigned nu = acc & fmask, nf = (acc >> (1u << kCountShift)) & fmask;
+    if (nu) atomicAdd(&S.cnt[0 * yc + j], nu);
+    if (nf) atomicAdd(&S.cnt[1 * yc + j], nf);
     if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);
   }
+  // ---- CTA epilogue
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -138,15 +139,17 @@ struct nbvgpu_ctx {
   int sm_count = 148;
   int max_smem_optin = 0;
   // dense-volume bounds cache (k_gain_dense): valid for (camera generation, voxel size, yc)
-  DevBuf d_vmin;
-  int vmin_yc = 0;
-  float vmin_vs = 0.f;
-  unsigned long long vmin_gen = ~0ull, cam_gen = 0;
-  int vez = 0;
-  long long vwords = 0;
-  bool vmin_ok = false;
+  struct DenseInfo {
+    bool ok = false;
+    int vez = 0;
+    long long vwords = 0;
+    DevBuf d_vmin;
+  };
+  std::map<int, DenseInfo> dense_info;  // per yaws-per-CTA, valid for (dense_gen, dense_vs)
+  float dense_vs = 0.f;
+  unsigned long long dense_gen = ~0ull, cam_gen = 0;
   int force_yc = 0;  // NBVGPU_YC environment override (experiments)
-  int dense_budget = 56 * 1024;  // shared memory per CTA the dense volume path may use (NBVGPU_DENSE_KB)
+  int dense_budget = 55 * 1024;  // shared memory per CTA the dense volume path may use (NBVGPU_DENSE_KB)
   int smem_pad = 0;              // extra dynamic shared memory per CTA (NBVGPU_SMEM_PAD_KB; occupancy experiments)
   // optional CUDA-event timing of the ray-sweep kernel (nbvgpu_set_profiling)
   bool profiling = false;
@@ -281,26 +284,19 @@ int check_position_range(const nbvgpu_ctx* ctx, const LayerHost* L, size_t n, co
   return NBVGPU_OK;
 }
 
-template <int V, int LV, bool GRID>
-cudaError_t launch_gain_lv(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV, GRID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int V, int LV, int MODE>
+cudaError_t launch_gain_as(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k_gain<V, LV, GRID><<<grid, kGainThreads, smem, s>>>(a);
+  k_gain<V, LV, MODE><<<grid, kGainThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
+// mode: kDense / kGrid / kProbe (gain_kernels.cuh).  16 voxels per side (the Voxblox default) gets
+// compile-time index math; the dense volume exists only for that size and the status-bit variants.
 template <int V>
-cudaError_t launch_gain_dense(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_gain_dense<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  k_gain_dense<V><<<grid, kGainThreads, smem, s>>>(a);
-  return cudaGetLastError();
-}
-template <int V>
-cudaError_t launch_gain(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
-  // 16 voxels per side (the Voxblox default) gets compile-time index math
-  if (a.gnx > 0)
-    return a.L.log2vps == 4 ? launch_gain_lv<V, 4, true>(a, smem, grid, s) : launch_gain_lv<V, 0, true>(a, smem, grid, s);
-  return a.L.log2vps == 4 ? launch_gain_lv<V, 4, false>(a, smem, grid, s) : launch_gain_lv<V, 0, false>(a, smem, grid, s);
+cudaError_t launch_gain(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s, int mode) {
+  if (mode == kProbe) return a.L.log2vps == 4 ? launch_gain_as<V, 4, kProbe>(a, smem, grid, s) : launch_gain_as<V, 0, kProbe>(a, smem, grid, s);
+  return a.L.log2vps == 4 ? launch_gain_as<V, 4, kGrid>(a, smem, grid, s) : launch_gain_as<V, 0, kGrid>(a, smem, grid, s);
 }
 
 // Enqueue: ray sweep + best yaw for n resident positions.  d_per_yaw may be null (scratch used).
@@ -366,34 +362,47 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   a.F.m = T.margin; a.F.mh = T.margin_h; a.F.mv = T.margin_v;
   int variant = ctx->variant;
   if (!T.filter_ok) variant = 1;
-  // Dense shared-memory status volume (k_gain_dense) when the layer has 16^3 blocks and the volume of
-  // one yaw chunk fits the budget that still allows 4 CTAs per SM.
+  // Dense shared-memory status volume (MODE kDense) when the layer has 16^3 blocks and the volume of one
+  // yaw chunk fits the budget that still allows 4 CTAs per SM: take the widest chunk that fits (narrower
+  // chunks have smaller volumes), starting from the width chosen above.
+  // (byte-wide per-ray counters in that mode: a ray has at most 3 * (reach + 2) + 1 < 255 steps)
   bool dense = false;
   a.vmin = nullptr;
   a.vez = a.vwords = 0;
-  // (byte-wide per-ray counters in that kernel: a ray has at most 3 * (reach + 2) + 1 < 255 steps)
   if ((variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0 && 3 * (a.reach_vox + 2) + 1 < 255) {
-    if (ctx->vmin_gen != ctx->cam_gen || ctx->vmin_yc != yc || ctx->vmin_vs != L->voxel_size) {
-      std::vector<int> vmin((size_t)(360 / yc) * 5);
-      ctx->vmin_ok = nbvgpu_host::dense_volume_bounds(T, a.vs, yc, vmin.data(), &ctx->vez, &ctx->vwords);
-      if (ctx->vmin_ok) {
-        CK(ctx->d_vmin.reserve(vmin.size() * sizeof(int)));
-        CK(cudaMemcpyAsync(ctx->d_vmin.p, vmin.data(), vmin.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));  // vmin is a local vector
-      }
-      ctx->vmin_gen = ctx->cam_gen;
-      ctx->vmin_yc = yc;
-      ctx->vmin_vs = L->voxel_size;
+    if (ctx->dense_gen != ctx->cam_gen || ctx->dense_vs != L->voxel_size) {
+      CK(cudaStreamSynchronize(ctx->stream));  // cached tables may still be in use
+      for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
+      ctx->dense_info.clear();
+      ctx->dense_gen = ctx->cam_gen;
+      ctx->dense_vs = L->voxel_size;
     }
-    if (ctx->vmin_ok) {
-      const long long nvol = ctx->vwords;
-      const size_t need = nvol < (1 << 24) ? dense_smem_bytes(yc, (int)gn, (int)nvol) : (size_t)1 << 30;
+    for (int c : kYc) {
+      if (c > yc) continue;
+      auto it = ctx->dense_info.find(c);
+      if (it == ctx->dense_info.end()) {
+        nbvgpu_ctx::DenseInfo info;
+        std::vector<int> vmin((size_t)(360 / c) * 5);
+        info.ok = nbvgpu_host::dense_volume_bounds(T, a.vs, c, vmin.data(), &info.vez, &info.vwords);
+        if (info.ok) {
+          CK(info.d_vmin.reserve(vmin.size() * sizeof(int)));
+          CK(cudaMemcpyAsync(info.d_vmin.p, vmin.data(), vmin.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+          CK(cudaStreamSynchronize(ctx->stream));  // vmin is a local vector
+        }
+        it = ctx->dense_info.emplace(c, std::move(info)).first;
+      }
+      const nbvgpu_ctx::DenseInfo& di = it->second;
+      if (!di.ok || di.vwords >= (1 << 24)) continue;
+      const size_t need = dense_smem_bytes(c, (int)gn, (int)di.vwords);
       if (need <= (size_t)ctx->dense_budget && need <= (size_t)ctx->max_smem_optin) {
         dense = true;
+        yc = c;
+        a.yc = c;
         smem = need;
-        a.vmin = ctx->d_vmin.as<int>();
-        a.vez = ctx->vez;
-        a.vwords = (int)nvol;
+        a.vmin = di.d_vmin.as<int>();
+        a.vez = di.vez;
+        a.vwords = (int)di.vwords;
+        break;
       }
     }
   }
@@ -413,13 +422,14 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     ctx->prof_used++;
     CK(cudaEventRecord(ev0, ctx->stream));
   }
+  const int mode = gdim > 0 ? kGrid : kProbe;
   switch (variant) {
-    case 1: e = launch_gain<1>(a, smem, grid, ctx->stream); break;
-    case 2: e = dense ? launch_gain_dense<2>(a, smem, grid, ctx->stream) : launch_gain<2>(a, smem, grid, ctx->stream); break;
-    case 3: e = launch_gain<3>(a, smem, grid, ctx->stream); break;
-    case 4: e = launch_gain<0>(a, smem, grid, ctx->stream); break;
-    case 5: e = launch_gain<2>(a, smem, grid, ctx->stream); break;
-    default: e = dense ? launch_gain_dense<0>(a, smem, grid, ctx->stream) : launch_gain<0>(a, smem, grid, ctx->stream); break;
+    case 1: e = launch_gain<1>(a, smem, grid, ctx->stream, mode); break;
+    case 2: e = dense ? launch_gain_as<2, 4, kDense>(a, smem, grid, ctx->stream) : launch_gain<2>(a, smem, grid, ctx->stream, mode); break;
+    case 3: e = launch_gain<3>(a, smem, grid, ctx->stream, mode); break;
+    case 4: e = launch_gain<0>(a, smem, grid, ctx->stream, mode); break;
+    case 5: e = launch_gain<2>(a, smem, grid, ctx->stream, mode); break;
+    default: e = dense ? launch_gain_as<0, 4, kDense>(a, smem, grid, ctx->stream) : launch_gain<0>(a, smem, grid, ctx->stream, mode); break;
   }
   if (ev1) cudaEventRecord(ev1, ctx->stream);
   CK(e);
@@ -530,7 +540,7 @@ void nbvgpu_destroy(nbvgpu_ctx* ctx) {
     cudaFree(ctx->d_cs);
     cudaFree(ctx->d_totals);
     ctx->h_io.release();
-    ctx->d_vmin.release();
+    for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
     for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
                       &ctx->d_free, &ctx->d_aux, &ctx->d_best})
       b->release();
