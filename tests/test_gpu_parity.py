@@ -110,6 +110,23 @@ def test_axis_aligned_and_grid_aligned_positions(oracle_mod, tiny_map):
     g.close()
 
 
+@pytest.mark.parametrize("variant", [0, 2, 3])
+def test_very_long_range_uses_global_probes(oracle_mod, tiny_map, variant):
+    """A reach too large for the shared-memory slot grid (60 m range on 0.2 m voxels: 346 ray rows,
+    ~125 k rays per viewpoint) takes the global-probe path (MODE kProbe); rays leave the map and the
+    exploration box long before they end."""
+    cam = tiny_map.camera()
+    cam.far_m = 60.0
+    o, lt_o, _ = load_oracle(oracle_mod, tiny_map, cam)
+    g, lt_g, _ = load_gpu(tiny_map, cam, variant)
+    pos = np.array([[4.0, 4.0, 1.2], [2.3, 5.1, 0.9]])
+    ro, rg = _compare_gain(o, lt_o, g, lt_g, pos)
+    assert ro["rays"][0] == 360 * 347 or ro["rays"][0] > 100000
+    if variant == 2:
+        assert g.classifier_mismatches() == 0
+    g.close()
+
+
 def test_sum_all_yaws_mode_is_reference_gain(oracle_mod, tiny_map):
     """camera.sum_all_yaws = 1 == RrtTree::gain (rrt.cpp:481-579): total over every yaw, yaw = 0."""
     from nbv_exploration_planner_b200 import synth
