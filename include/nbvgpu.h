@@ -131,6 +131,24 @@ int nbvgpu_layer_num_blocks(nbvgpu_ctx* ctx, int layer, size_t* out);
 int nbvgpu_layer_read_voxels(nbvgpu_ctx* ctx, int layer, size_t n, const int64_t* global_index,
                              float* out_values, uint8_t* out_found, uint8_t* out_status);
 
+/* ---- ingest in the reference's own formats ------------------------------------ */
+/* voxblox::io::LoadBlocksFromFile (voxblox/io/layer_io_inl.h:14-127, kReplace, multiple-layer files
+ * supported): reads a .voxblox file (varint-framed LayerProto + BlockProto messages), keeps the blocks of
+ * the first layer compatible with `layer` (voxel size, voxels per side, "tsdf"/"esdf"), uploads them
+ * and commits.  *n_blocks_out (may be NULL) = blocks loaded. */
+int nbvgpu_layer_load_voxblox_file(nbvgpu_ctx* ctx, int layer, const char* path, size_t* n_blocks_out);
+/* voxblox::deserializeMsgToLayer (voxblox_ros/conversions_inl.h:43-115) on a voxblox_msgs/Layer message
+ * in ROS 1 wire serialisation: ACTION_UPDATE (0) overwrites/inserts the blocks, ACTION_RESET (2) clears
+ * the layer first; ACTION_MERGE (1) needs the integrators' voxel merge and returns NBVGPU_ERR_INVALID. */
+int nbvgpu_layer_apply_layer_msg(nbvgpu_ctx* ctx, int layer, const uint8_t* msg, size_t len, size_t* n_blocks_out);
+/* Host-only parsers behind the two calls above (no device needed): kind = NBVGPU_LAYER_*; on success
+ * *n_blocks is the number of blocks found; keys_out[n][3] / words_out[n][words per block] are filled when
+ * non-NULL and capacity_blocks >= *n_blocks.  format: 0 = .voxblox bytes, 1 = Layer message bytes;
+ * *action_out (may be NULL) = the message's action. */
+int nbvgpu_parse_blocks(int format, const uint8_t* buf, size_t len, int kind, float voxel_size, int voxels_per_side,
+                        size_t* n_blocks, int32_t* keys_out, uint32_t* words_out, size_t capacity_blocks,
+                        int* action_out);
+
 /* ---- gain evaluator --------------------------------------------------------------------- */
 int nbvgpu_set_camera(nbvgpu_ctx* ctx, const nbvgpu_camera* cam);
 /* Batched optimized_gain()/gain(): pos[n][3] = state[0..2].  Outputs (any may be NULL except gain):

@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> None:
     """Compile libnbvgpu.so / libnbvsynth.so in-tree (nvcc -gencode arch=compute_100a,code=sm_100a)."""
     hdr = os.path.join(_HERE, "..", "include", "nbvgpu.h")
     gpu_stale = _sources_newer(LIB_PATH, ["nbvgpu.cu", "gain_kernels.cuh", "map_mirror.cuh", "camera_host.cc",
-                                          "camera_host.h", hdr])
+                                          "camera_host.h", "voxblox_io.cc", "voxblox_io.h", hdr])
     synth_stale = _sources_newer(SYNTH_PATH, ["synth_gen.cc"])
     if not (force or gpu_stale or synth_stale):
         return
@@ -124,6 +124,10 @@ def lib() -> C.CDLL:
     L.nbvgpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.nbvgpu_set_kernel_variant.argtypes = [vp, C.c_int]
     L.nbvgpu_debug_classifier_mismatches.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.nbvgpu_layer_load_voxblox_file.argtypes = [vp, C.c_int, C.c_char_p, C.POINTER(C.c_size_t)]
+    L.nbvgpu_layer_apply_layer_msg.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
+    L.nbvgpu_parse_blocks.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_size_t), vp, vp,
+                                      C.c_size_t, C.POINTER(C.c_int)]
     L.nbvgpu_set_profiling.argtypes = [vp, C.c_int]
     L.nbvgpu_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     _lib = L
@@ -150,4 +154,5 @@ ABI_SYMBOLS = [
     "nbvgpu_gain_eval_best", "nbvgpu_gain_eval_best_device", "nbvgpu_check_segments",
     "nbvgpu_check_segments_device", "nbvgpu_check_motion", "nbvgpu_get_stats", "nbvgpu_set_kernel_variant",
     "nbvgpu_debug_classifier_mismatches", "nbvgpu_set_profiling", "nbvgpu_profile_collect",
+    "nbvgpu_layer_load_voxblox_file", "nbvgpu_layer_apply_layer_msg", "nbvgpu_parse_blocks",
 ]

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -19,6 +20,7 @@
 #include "camera_host.h"
 #include "gain_kernels.cuh"
 #include "map_mirror.cuh"
+#include "voxblox_io.h"
 
 using namespace nbvgpu;
 
@@ -796,6 +798,80 @@ int nbvgpu_layer_read_voxels(nbvgpu_ctx* ctx, int layer, size_t n, const int64_t
     else memset(out_status, 0, n);
   }
   CK(cudaStreamSynchronize(ctx->stream));
+  return NBVGPU_OK;
+}
+
+// ---- ingest in the reference's formats ------------------------------------------------------
+static int upload_parsed(nbvgpu_ctx* ctx, int layer, const nbvgpu_io::ParsedBlocks& pb, size_t* n_out) {
+  if (n_out) *n_out = pb.n_blocks;
+  if (pb.n_blocks == 0) return NBVGPU_OK;
+  const size_t per = pb.words.size() / pb.n_blocks;
+  const size_t batch = 2048;  // bounds the pinned staging for large files
+  for (size_t i = 0; i < pb.n_blocks; i += batch) {
+    const size_t n = std::min(batch, pb.n_blocks - i);
+    int rc = nbvgpu_layer_update(ctx, layer, n, pb.keys.data() + 3 * i, pb.words.data() + per * i, NBVGPU_PACK_VOXBLOX);
+    if (rc) return rc;
+    rc = nbvgpu_commit(ctx);
+    if (rc) return rc;
+  }
+  return NBVGPU_OK;
+}
+
+int nbvgpu_layer_load_voxblox_file(nbvgpu_ctx* ctx, int layer, const char* path, size_t* n_blocks_out) {
+  if (!ctx || !path) return NBVGPU_ERR_INVALID;
+  int kind, vps;
+  float vs;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    LayerHost* L = get_layer(ctx, layer, -1);
+    if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
+    kind = L->kind; vps = L->vps; vs = L->voxel_size;
+  }
+  nbvgpu_io::ParsedBlocks pb;
+  if (!nbvgpu_io::parse_voxblox_file(path, kind, vs, vps, &pb)) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err = pb.error;
+    return NBVGPU_ERR_INVALID;
+  }
+  return upload_parsed(ctx, layer, pb, n_blocks_out);
+}
+
+int nbvgpu_layer_apply_layer_msg(nbvgpu_ctx* ctx, int layer, const uint8_t* msg, size_t len, size_t* n_blocks_out) {
+  if (!ctx || !msg) return NBVGPU_ERR_INVALID;
+  int kind, vps;
+  float vs;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    LayerHost* L = get_layer(ctx, layer, -1);
+    if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
+    kind = L->kind; vps = L->vps; vs = L->voxel_size;
+  }
+  nbvgpu_io::ParsedBlocks pb;
+  if (!nbvgpu_io::parse_layer_msg(msg, len, kind, vs, vps, &pb) || pb.action == 1 || pb.action > 2) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->err = pb.error.empty() ? "ACTION_MERGE is not supported by the mirror" : pb.error;
+    return NBVGPU_ERR_INVALID;
+  }
+  if (pb.action == 2) {  // MapDerializationAction::kReset -> removeAllBlocks
+    const int rc = nbvgpu_layer_clear(ctx, layer);
+    if (rc) return rc;
+  }
+  return upload_parsed(ctx, layer, pb, n_blocks_out);
+}
+
+int nbvgpu_parse_blocks(int format, const uint8_t* buf, size_t len, int kind, float voxel_size, int vps, size_t* n_blocks,
+                        int32_t* keys_out, uint32_t* words_out, size_t capacity_blocks, int* action_out) {
+  if (!buf || !n_blocks || (kind != NBVGPU_LAYER_TSDF && kind != NBVGPU_LAYER_ESDF) || vps <= 0) return NBVGPU_ERR_INVALID;
+  nbvgpu_io::ParsedBlocks pb;
+  const bool ok = format == 0 ? nbvgpu_io::parse_voxblox_bytes(buf, len, kind, voxel_size, vps, &pb)
+                              : nbvgpu_io::parse_layer_msg(buf, len, kind, voxel_size, vps, &pb);
+  if (!ok) return NBVGPU_ERR_INVALID;
+  *n_blocks = pb.n_blocks;
+  if (action_out) *action_out = pb.action;
+  if (keys_out && words_out && capacity_blocks >= pb.n_blocks) {
+    memcpy(keys_out, pb.keys.data(), pb.keys.size() * sizeof(int32_t));
+    memcpy(words_out, pb.words.data(), pb.words.size() * sizeof(uint32_t));
+  }
   return NBVGPU_OK;
 }
 

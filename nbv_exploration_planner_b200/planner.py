@@ -175,6 +175,20 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_layer_read_voxels(self._h, layer, n, _vp(g), _vp(vals), _vp(found), _vp(status)))
         return vals, found, status
 
+    # -- ingest in the reference's own formats ---------------------------------
+    def layer_load_voxblox_file(self, layer: int, path: str) -> int:
+        """voxblox::io::LoadBlocksFromFile: load a .voxblox file into `layer`; returns #blocks."""
+        n = C.c_size_t(0)
+        self._ck(self._L.nbvgpu_layer_load_voxblox_file(self._h, layer, str(path).encode(), C.byref(n)))
+        return n.value
+
+    def layer_apply_layer_msg(self, layer: int, msg: bytes) -> int:
+        """voxblox::deserializeMsgToLayer on a ROS-1-serialised voxblox_msgs/Layer; returns #blocks."""
+        buf = np.frombuffer(msg, np.uint8)
+        n = C.c_size_t(0)
+        self._ck(self._L.nbvgpu_layer_apply_layer_msg(self._h, layer, _vp(buf), len(buf), C.byref(n)))
+        return n.value
+
     # -- camera ------------------------------------------------------------------------------
     def set_camera(self, cam: CameraParams) -> None:
         s = cam.as_struct()
@@ -266,6 +280,27 @@ class NbvGpu:
         out = C.c_uint64(0)
         self._ck(self._L.nbvgpu_debug_classifier_mismatches(self._h, C.byref(out)))
         return out.value
+
+
+def parse_blocks(data: bytes, kind: int, voxel_size: float, voxels_per_side: int, fmt: str = "voxblox"):
+    """Host-only parse of a .voxblox byte string (fmt="voxblox") or a ROS-1-serialised voxblox_msgs/Layer
+    (fmt="msg") into (keys int32[n][3], words uint32[n][words per block], action).  No GPU needed."""
+    L = N.lib()
+    buf = np.frombuffer(data, np.uint8)
+    f = 0 if fmt == "voxblox" else 1
+    n, act = C.c_size_t(0), C.c_int(0)
+    rc = L.nbvgpu_parse_blocks(f, _vp(buf), len(buf), kind, np.float32(voxel_size), voxels_per_side, C.byref(n), None, None, 0,
+                               C.byref(act))
+    if rc != 0:
+        raise N.NbvGpuError(rc, "could not parse blocks")
+    per = voxels_per_side ** 3 * (3 if kind == N.LAYER_TSDF else 2)
+    keys = np.zeros((n.value, 3), np.int32)
+    words = np.zeros((n.value, per), np.uint32)
+    rc = L.nbvgpu_parse_blocks(f, _vp(buf), len(buf), kind, np.float32(voxel_size), voxels_per_side, C.byref(n), _vp(keys),
+                               _vp(words), n.value, C.byref(act))
+    if rc != 0:
+        raise N.NbvGpuError(rc, "could not parse blocks")
+    return keys, words, act.value
 
 
 # ---------------------------------------------------------------------------------------------

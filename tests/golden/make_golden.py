@@ -52,7 +52,19 @@ def golden_rays(out):
                         indices=np.concatenate(seqs, 0))
 
 
+def golden_voxblox_file(out):
+    """A 3-block TSDF + ESDF .voxblox file encoded by the protobuf library (tests/voxblox_fixture.py)."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    import voxblox_fixture as vf
+    m = synth.make_map("tiny")
+    data = vf.voxblox_file_bytes([("tsdf", m.voxel_size, m.vps, m.keys[:3], vf.tsdf_words(m.tsdf[:3])),
+                                  ("esdf", m.voxel_size, m.vps, m.keys[:3], vf.esdf_words(m.esdf[:3]))])
+    open(out, "wb").write(data)
+    print("voxblox fixture", len(data), "bytes")
+
+
 if __name__ == "__main__":
     golden_cfg("cfg1", 100, os.path.join(HERE, "cfg1_golden.npz"))
     golden_cfg("tiny", 16, os.path.join(HERE, "tiny_golden.npz"))
     golden_rays(os.path.join(HERE, "rays_golden.npz"))
+    golden_voxblox_file(os.path.join(HERE, "tiny_tsdf_esdf.voxblox"))
