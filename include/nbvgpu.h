@@ -180,6 +180,31 @@ int nbvgpu_gain_eval_best_device(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, cons
                                  double zero_gain, nbvgpu_best* d_best, double* d_gain,
                                  int32_t* d_yaw_deg);
 
+/* ---- batched tree expansion ------------------------------------------------- */
+/* Parameters of RrtTree::iterate that are not in nbvgpu_camera (params.h:26-35,93,103; rrt.cpp:175). */
+typedef struct {
+  double root[3];          /* rootNode_->state_ xyz: centre of the sampling sphere                 */
+  double vicinity;         /* root_vicinity_                                                        */
+  double extension_range;  /* nbvep/tree/extension_range                                            */
+  double overshoot;        /* system/overshoot                                                      */
+  double robot_radius;     /* system/robot_radius                                                   */
+  double v_max, dyaw_max;  /* system/v_max, system/dyaw_max                                         */
+  double zero_gain;        /* nbvep/gain/zero                                                       */
+} nbvgpu_expand_params;
+/* One batched pass of the body of RrtTree::iterate (rrt.cpp:172-246) over n uniform triples u[n][3] in
+ * [0,1) (the caller's RNG replaces the reference's clock-seeded mt19937): sample in the vicinity sphere,
+ * reject outside it or outside the exploration box; nearest of the n_nodes existing tree nodes
+ * (node_state[n_nodes][4] = x y z yaw, node_distance[n_nodes]) as parent; clip to extension_range; edge +
+ * overshoot through checkMotion; gain (optimized_gain / gain per the camera) for free edges; node score
+ * against the parent's yaw and distance; best = first strict maximum over zero_gain in sample order.
+ * Parents are existing nodes only: samples of one batch do not see each other (with n = 1 this is exactly
+ * one iterate() call).  Per-sample outputs (any may be NULL): status 0 = sample rejected, 1 = edge collides,
+ * 2 = node created; pos[n][3]; parent[n]; gain[n]; yaw[n] (radians); distance[n]; score[n]. */
+int nbvgpu_expand_tree(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, const nbvgpu_expand_params* params,
+                       size_t n_nodes, const double* node_state, const double* node_distance, size_t n,
+                       const double* uniforms, uint8_t* status, double* pos, int32_t* parent, double* gain, double* yaw,
+                       double* distance, double* score, nbvgpu_best* best);
+
 /* ---- segment collision check ------------------------------------------------------------ */
 /* Batched HighResManager::checkMotion: seg[n][6] = (start xyz, end xyz); is_free[n] = 1 when every
  * traversed voxel is allocated and robot_radius < distance. */

@@ -45,6 +45,13 @@ class Stats(C.Structure):
                 ("rays", "voxel_steps", "collision_steps", "blocks_uploaded", "bytes_uploaded", "kernel_launches")]
 
 
+class ExpandParams(C.Structure):
+    """nbvgpu_expand_params."""
+
+    _fields_ = [("root", C.c_double * 3), ("vicinity", C.c_double), ("extension_range", C.c_double), ("overshoot", C.c_double),
+                ("robot_radius", C.c_double), ("v_max", C.c_double), ("dyaw_max", C.c_double), ("zero_gain", C.c_double)]
+
+
 class Best(C.Structure):
     """nbvgpu_best."""
 
@@ -128,6 +135,8 @@ def lib() -> C.CDLL:
     L.nbvgpu_layer_apply_layer_msg.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
     L.nbvgpu_parse_blocks.argtypes = [C.c_int, vp, C.c_size_t, C.c_int, C.c_float, C.c_int, C.POINTER(C.c_size_t), vp, vp,
                                       C.c_size_t, C.POINTER(C.c_int)]
+    L.nbvgpu_expand_tree.argtypes = [vp, C.c_int, C.c_int, C.POINTER(ExpandParams), C.c_size_t, vp, vp, C.c_size_t, vp, vp, vp, vp,
+                                     vp, vp, vp, vp, C.POINTER(Best)]
     L.nbvgpu_set_profiling.argtypes = [vp, C.c_int]
     L.nbvgpu_profile_collect.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     _lib = L
@@ -154,5 +163,5 @@ ABI_SYMBOLS = [
     "nbvgpu_gain_eval_best", "nbvgpu_gain_eval_best_device", "nbvgpu_check_segments",
     "nbvgpu_check_segments_device", "nbvgpu_check_motion", "nbvgpu_get_stats", "nbvgpu_set_kernel_variant",
     "nbvgpu_debug_classifier_mismatches", "nbvgpu_set_profiling", "nbvgpu_profile_collect",
-    "nbvgpu_layer_load_voxblox_file", "nbvgpu_layer_apply_layer_msg", "nbvgpu_parse_blocks",
+    "nbvgpu_layer_load_voxblox_file", "nbvgpu_layer_apply_layer_msg", "nbvgpu_parse_blocks", "nbvgpu_expand_tree",
 ]

@@ -47,6 +47,7 @@ struct GainArgs {
   const double* B;    // [360][3]
   const float* cs;    // [360][2]
   const double* pos;  // [n][3]
+  const uint8_t* valid;  // [n] or null: candidates with valid == 0 are skipped (counts 0)
   uint32_t* per_yaw;  // [n][360][3]
   unsigned long long* steps;   // [n] or null
   unsigned long long* totals;  // [0] rays [1] voxel steps [3] classifier mismatches
@@ -275,7 +276,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   const double px = a.pos[3 * v], py = a.pos[3 * v + 1], pz = a.pos[3 * v + 2];
   // Guard (the host entry points validate; device-resident inputs are caught here).
   const double lim = 4194304.0 - (double)a.reach_vox - 2.0;
-  const bool bad = !(fabs(px * a.vs_inv) < lim) || !(fabs(py * a.vs_inv) < lim) || !(fabs(pz * a.vs_inv) < lim);
+  const bool bad = !(fabs(px * a.vs_inv) < lim) || !(fabs(py * a.vs_inv) < lim) || !(fabs(pz * a.vs_inv) < lim) ||
+                   (a.valid != nullptr && a.valid[v] == 0);
   if (tid == 0) {
     s_umax = 0;
     s_steps = 0ull;
@@ -708,13 +710,16 @@ struct BestRecord {
 __global__ void __launch_bounds__(1024) k_score_best(const double* __restrict__ gain, const int32_t* __restrict__ yaw_deg,
                                                      const double* __restrict__ parent_yaw, const double* __restrict__ distance,
                                                      const uint8_t* __restrict__ edge_free, int n, double v_max, double dyaw_max,
-                                                     double zero_gain, BestRecord* out) {
+                                                     double zero_gain, BestRecord* out, double* score_out = nullptr) {
   __shared__ double s_score[32];
   __shared__ int s_idx[32];
   double best = zero_gain;
   int best_i = INT_MAX;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    if (edge_free && !edge_free[i]) continue;
+    if (edge_free && !edge_free[i]) {
+      if (score_out) score_out[i] = 0.0;
+      continue;
+    }
     const double yaw = __ddiv_rn(dmul((double)yaw_deg[i], 3.14159265358979323846), 180.0);  // rrt.cpp:477
     double dy = dsub(yaw, parent_yaw[i]);                                                   // :225
     if (dy > 3.14159265358979323846) dy = dsub(dy, dmul(2.0, 3.14159265358979323846));
@@ -722,6 +727,7 @@ __global__ void __launch_bounds__(1024) k_score_best(const double* __restrict__ 
     const double ta = __ddiv_rn(dy, dyaw_max), tb = __ddiv_rn(distance[i], v_max);
     const double time = (ta < tb) ? tb : ta;          // std::max (:232-233)
     const double score = __ddiv_rn(gain[i], time);    // :234
+    if (score_out) score_out[i] = score;
     if (score > best) { best = score; best_i = i; }   // ascending i per thread: first strict max
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -752,6 +758,81 @@ __global__ void __launch_bounds__(1024) k_score_best(const double* __restrict__ 
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Batched RrtTree::iterate front half (rrt.cpp:172-212,223): sample -> reject -> nearest parent ->
+// clip -> edge with overshoot.  One thread per uniform triple; FP64 in the reference's operation order.
+// status: 0 = sample rejected, 1 = candidate produced (collision check and gain follow).
+// ---------------------------------------------------------------------------------------------
+struct ExpandArgs {
+  double root[3];
+  double vicinity, extension_range, overshoot;
+  double bbx_min[3], bbx_max[3];
+  const double* node_state;     // [n_nodes][4] x y z yaw
+  const double* node_distance;  // [n_nodes]
+  const double* uniforms;       // [n][3]
+  int n_nodes, n;
+  uint8_t* status;              // [n]
+  double* pos;                  // [n][3]
+  double* seg;                  // [n][6]
+  int32_t* parent;              // [n]
+  double* parent_yaw;           // [n]
+  double* distance;             // [n]
+};
+
+__global__ void __launch_bounds__(128) k_expand_sample(const ExpandArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  double s[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) s[k] = dmul(dmul(2.0, a.vicinity), dsub(a.uniforms[3 * i + k], 0.5));  // :176-178
+  bool ok = !(dadd(dadd(dmul(s[0], s[0]), dmul(s[1], s[1])), dmul(s[2], s[2])) > dmul(a.vicinity, a.vicinity));  // :179
+#pragma unroll
+  for (int k = 0; k < 3; ++k) s[k] = dadd(s[k], a.root[k]);                                           // :182
+  ok = ok && s[0] >= a.bbx_min[0] && s[0] <= a.bbx_max[0] && s[1] >= a.bbx_min[1] && s[1] <= a.bbx_max[1] &&
+       s[2] >= a.bbx_min[2] && s[2] <= a.bbx_max[2];                                                  // :183-185
+  a.status[i] = ok ? 1 : 0;
+  if (!ok) {
+    for (int k = 0; k < 3; ++k) a.pos[3 * i + k] = 0.0;
+    for (int k = 0; k < 6; ++k) a.seg[6 * i + k] = 0.0;
+    a.parent[i] = -1;
+    a.parent_yaw[i] = 0.0;
+    a.distance[i] = 0.0;
+    return;
+  }
+  // kd_nearest3 (kdtree.c): squared distance accumulated x, y, z; first minimum
+  int best = 0;
+  double best_d = 0.0;
+  for (int j = 0; j < a.n_nodes; ++j) {
+    const double dx = dsub(a.node_state[4 * j], s[0]), dy = dsub(a.node_state[4 * j + 1], s[1]), dz = dsub(a.node_state[4 * j + 2], s[2]);
+    const double d = dadd(dadd(dadd(0.0, dmul(dx, dx)), dmul(dy, dy)), dmul(dz, dz));
+    if (j == 0 || d < best_d) { best_d = d; best = j; }
+  }
+  const D3 origin{a.node_state[4 * best], a.node_state[4 * best + 1], a.node_state[4 * best + 2]};
+  D3 dir = d3sub(D3{s[0], s[1], s[2]}, origin);                                                       // :202-203
+  if (__dsqrt_rn(d3dot(dir, dir)) > a.extension_range) {                                              // :204-206
+    const D3 un = d3normalized(dir);
+    dir = D3{dmul(a.extension_range, un.x), dmul(a.extension_range, un.y), dmul(a.extension_range, un.z)};
+  }
+  const D3 ns = d3add(origin, dir);                                                                   // :207-209
+  const D3 un = d3normalized(dir);
+  const D3 end = d3add(d3add(dir, origin), D3{dmul(un.x, a.overshoot), dmul(un.y, a.overshoot), dmul(un.z, a.overshoot)});  // :210-212
+  a.pos[3 * i] = ns.x; a.pos[3 * i + 1] = ns.y; a.pos[3 * i + 2] = ns.z;
+  a.seg[6 * i] = origin.x; a.seg[6 * i + 1] = origin.y; a.seg[6 * i + 2] = origin.z;
+  a.seg[6 * i + 3] = end.x; a.seg[6 * i + 4] = end.y; a.seg[6 * i + 5] = end.z;
+  a.parent[i] = best;
+  a.parent_yaw[i] = a.node_state[4 * best + 3];
+  a.distance[i] = dadd(a.node_distance[best], __dsqrt_rn(d3dot(dir, dir)));                           // :223
+}
+
+// status 1 + free edge -> 2 (node created); valid[i] = (status == 2) for the gain / scoring kernels.
+__global__ void k_expand_status(uint8_t* status, const uint8_t* __restrict__ edge_free, uint8_t* valid, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t st = status[i] ? (edge_free[i] ? 2 : 1) : 0;
+  status[i] = st;
+  valid[i] = st == 2 ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------

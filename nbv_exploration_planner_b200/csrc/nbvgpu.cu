@@ -303,7 +303,7 @@ cudaError_t launch_gain(const GainArgs& a, size_t smem, unsigned grid, cudaStrea
 
 // Enqueue: ray sweep + best yaw for n resident positions.  d_per_yaw may be null (scratch used).
 int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, double* d_gain, int32_t* d_yaw_deg,
-                 uint64_t* d_counts, uint32_t* d_per_yaw, uint64_t* d_steps) {
+                 uint64_t* d_counts, uint32_t* d_per_yaw, uint64_t* d_steps, const uint8_t* d_valid = nullptr) {
   if (n == 0) return NBVGPU_OK;
   if (n > (size_t)INT_MAX / 1080) return fail(ctx, NBVGPU_ERR_INVALID, "too many candidates in one call");
   if (!d_per_yaw) {
@@ -317,6 +317,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   a.B = ctx->d_B;
   a.cs = ctx->d_cs;
   a.pos = d_pos;
+  a.valid = d_valid;
   a.per_yaw = d_per_yaw;
   a.steps = reinterpret_cast<unsigned long long*>(d_steps);
   a.totals = ctx->d_totals;
@@ -999,6 +1000,89 @@ int nbvgpu_gain_eval_best(nbvgpu_ctx* ctx, int layer, size_t n, const double* po
   memcpy(best, hr, sizeof(nbvgpu_best));
   if (gain) memcpy(gain, hr + 64, n * 8);
   if (yaw_deg) memcpy(yaw_deg, hr + 64 + n * 8, n * 4);
+  return NBVGPU_OK;
+}
+
+// ---- batched tree expansion ----------------------------------------------------------------
+int nbvgpu_expand_tree(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, const nbvgpu_expand_params* P, size_t n_nodes,
+                       const double* node_state, const double* node_distance, size_t n, const double* uniforms, uint8_t* status,
+                       double* pos, int32_t* parent, double* gain, double* yaw, double* distance, double* score, nbvgpu_best* best) {
+  if (!ctx || !P || !best || !node_state || !node_distance || n_nodes == 0 || (n && !uniforms)) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
+  LayerHost* LT = get_layer(ctx, tsdf_layer, NBVGPU_LAYER_TSDF);
+  LayerHost* LE = get_layer(ctx, esdf_layer, NBVGPU_LAYER_ESDF);
+  if (!LT || !LE) return fail(ctx, NBVGPU_ERR_STATE, "need a TSDF and an ESDF layer");
+  if (n_nodes > (size_t)INT_MAX / 4 || n > (size_t)INT_MAX / 1080) return fail(ctx, NBVGPU_ERR_INVALID, "batch too large");
+  if (check_position_range(ctx, LT, 1, P->root) || !(P->vicinity >= 0.0) || !(P->vicinity < 1e6) || !(P->extension_range < 1e6) ||
+      !(P->overshoot < 1e6))
+    return fail(ctx, NBVGPU_ERR_RANGE, "root / ranges non-finite or out of range");
+  for (size_t i = 0; i < n_nodes; ++i)
+    for (int k = 0; k < 3; ++k)
+      if (!(std::fabs(node_state[4 * i + k]) < 1e6)) return fail(ctx, NBVGPU_ERR_RANGE, "tree node non-finite or out of range");
+  DeviceGuard guard(ctx->device);
+  if (n == 0) {
+    best->index = -1; best->score = P->zero_gain; best->gain = 0.0; best->yaw = 0.0;
+    return NBVGPU_OK;
+  }
+  // device layout (doubles first): nodes [nn*4] | node_dist [nn] | u [n*3] | pos [n*3] | seg [n*6] | pyaw [n] | dist [n] |
+  //                                gain [n] | score [n] | best [4] | parent i32 [n] | yaw_deg i32 [n] | status [n] | free [n] | valid [n]
+  const size_t nn = n_nodes;
+  const size_t o_nd = nn * 4, o_u = o_nd + nn, o_pos = o_u + n * 3, o_seg = o_pos + n * 3, o_py = o_seg + n * 6, o_di = o_py + n,
+               o_ga = o_di + n, o_sc = o_ga + n, o_be = o_sc + n, n_dbl = o_be + 4;
+  const size_t b_par = n_dbl * 8, b_yd = b_par + n * 4, b_st = b_yd + n * 4, b_fr = b_st + n, b_va = b_fr + n, total = b_va + n;
+  CK(ctx->d_aux.reserve(total + 64));
+  CK(ctx->h_io.reserve(total + 64, false));
+  char* d = ctx->d_aux.as<char>();
+  char* h = ctx->h_io.as<char>();
+  double* dd = reinterpret_cast<double*>(d);
+  memcpy(h, node_state, nn * 32);
+  memcpy(h + o_nd * 8, node_distance, nn * 8);
+  memcpy(h + o_u * 8, uniforms, n * 24);
+  CK(cudaMemcpyAsync(d, h, o_pos * 8, cudaMemcpyHostToDevice, ctx->stream));
+  ExpandArgs a;
+  for (int k = 0; k < 3; ++k) { a.root[k] = P->root[k]; a.bbx_min[k] = ctx->cam.bbx_min[k]; a.bbx_max[k] = ctx->cam.bbx_max[k]; }
+  a.vicinity = P->vicinity; a.extension_range = P->extension_range; a.overshoot = P->overshoot;
+  a.node_state = dd; a.node_distance = dd + o_nd; a.uniforms = dd + o_u;
+  a.n_nodes = (int)nn; a.n = (int)n;
+  a.status = reinterpret_cast<uint8_t*>(d + b_st);
+  a.pos = dd + o_pos; a.seg = dd + o_seg; a.parent = reinterpret_cast<int32_t*>(d + b_par);
+  a.parent_yaw = dd + o_py; a.distance = dd + o_di;
+  k_expand_sample<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  uint8_t* d_free = reinterpret_cast<uint8_t*>(d + b_fr);
+  uint8_t* d_valid = reinterpret_cast<uint8_t*>(d + b_va);
+  int rc = enqueue_segments(ctx, LE, P->robot_radius, n, a.seg, d_free);
+  if (rc) return rc;
+  k_expand_status<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a.status, d_free, d_valid, (int)n);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  int32_t* d_yd = reinterpret_cast<int32_t*>(d + b_yd);
+  rc = enqueue_gain(ctx, LT, n, a.pos, dd + o_ga, d_yd, nullptr, nullptr, nullptr, d_valid);
+  if (rc) return rc;
+  static_assert(sizeof(BestRecord) == sizeof(nbvgpu_best), "record layout");
+  k_score_best<<<1, 1024, 0, ctx->stream>>>(dd + o_ga, d_yd, a.parent_yaw, a.distance, d_valid, (int)n, P->v_max, P->dyaw_max,
+                                            P->zero_gain, reinterpret_cast<BestRecord*>(dd + o_be), dd + o_sc);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(h + o_pos * 8, d + o_pos * 8, total - o_pos * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  const double* hd = reinterpret_cast<const double*>(h);
+  memcpy(best, hd + o_be, sizeof(nbvgpu_best));
+  const uint8_t* hs = reinterpret_cast<const uint8_t*>(h + b_st);
+  const int32_t* hyd = reinterpret_cast<const int32_t*>(h + b_yd);
+  if (status) memcpy(status, hs, n);
+  if (pos) memcpy(pos, hd + o_pos, n * 24);
+  if (parent) memcpy(parent, h + b_par, n * 4);
+  for (size_t i = 0; i < n; ++i) {
+    const bool ok = hs[i] == 2;
+    if (gain) gain[i] = ok ? hd[o_ga + i] : 0.0;
+    if (yaw) yaw[i] = ok ? hyd[i] * M_PI / 180.0 : 0.0;
+    if (distance) distance[i] = ok ? hd[o_di + i] : 0.0;
+    if (score) score[i] = ok ? hd[o_sc + i] : 0.0;
+    if (!hs[i] && parent) parent[i] = -1;
+  }
   return NBVGPU_OK;
 }
 

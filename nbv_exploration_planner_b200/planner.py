@@ -241,6 +241,27 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_optimized_gain(self._h, layer, state.ctypes.data_as(C.POINTER(C.c_double)), C.byref(g)))
         return g.value
 
+    # -- batched tree expansion --------------------------------------------------
+    def expand_tree(self, tsdf_layer: int, esdf_layer: int, params: dict, node_state, node_distance, uniforms) -> dict:
+        """One batched pass of the body of ``RrtTree::iterate`` (rrt.cpp:172-246) over uniform triples."""
+        P = N.ExpandParams()
+        P.root[:] = [float(v) for v in params["root"]]
+        for k in ("vicinity", "extension_range", "overshoot", "robot_radius", "v_max", "dyaw_max", "zero_gain"):
+            setattr(P, k, float(params[k]))
+        ns = np.ascontiguousarray(node_state, np.float64).reshape(-1, 4)
+        nd = np.ascontiguousarray(node_distance, np.float64)
+        u = np.ascontiguousarray(uniforms, np.float64).reshape(-1, 3)
+        n = len(u)
+        out = {"status": np.zeros(n, np.uint8), "pos": np.zeros((n, 3)), "parent": np.zeros(n, np.int32), "gain": np.zeros(n),
+               "yaw": np.zeros(n), "distance": np.zeros(n), "score": np.zeros(n)}
+        best = N.Best()
+        self._ck(self._L.nbvgpu_expand_tree(self._h, tsdf_layer, esdf_layer, C.byref(P), len(ns), _vp(ns), _vp(nd), n, _vp(u),
+                                            _vp(out["status"]), _vp(out["pos"]), _vp(out["parent"]), _vp(out["gain"]),
+                                            _vp(out["yaw"]), _vp(out["distance"]), _vp(out["score"]), C.byref(best)))
+        out["best_index"] = best.index
+        out["best_score"] = best.score
+        return out
+
     # -- collision ---------------------------------------------------------------------------
     def check_segments(self, layer: int, robot_radius: float, seg: np.ndarray) -> np.ndarray:
         seg = np.ascontiguousarray(seg, np.float64).reshape(-1, 6)

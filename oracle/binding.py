@@ -37,6 +37,11 @@ class OracleCamera(C.Structure):
     ]
 
 
+class OracleExpandParams(C.Structure):
+    _fields_ = [("root", C.c_double * 3), ("vicinity", C.c_double), ("extension_range", C.c_double), ("overshoot", C.c_double),
+                ("robot_radius", C.c_double), ("v_max", C.c_double), ("dyaw_max", C.c_double), ("zero_gain", C.c_double)]
+
+
 def _ptr(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
 
@@ -63,6 +68,10 @@ def lib():
                                      C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
         L.nbvo_check_segments.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.POINTER(C.c_double),
                                           C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_int]
+        L.nbvo_expand_tree.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(OracleExpandParams), C.c_size_t, C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_uint8),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]
         L.nbvo_cast_ray.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64), C.c_size_t]
         L.nbvo_cast_ray.restype = C.c_size_t
         L.nbvo_yaw_frame.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
@@ -155,6 +164,27 @@ class Oracle:
         if r != 0:
             raise RuntimeError(f"oracle check_segments failed: {r}")
         return {"free": free, "steps": steps}
+
+    def expand_tree(self, tsdf_layer: int, esdf_layer: int, params: dict, node_state, node_distance, uniforms, threads: int = 1) -> dict:
+        P = OracleExpandParams()
+        P.root[:] = [float(v) for v in params["root"]]
+        for k in ("vicinity", "extension_range", "overshoot", "robot_radius", "v_max", "dyaw_max", "zero_gain"):
+            setattr(P, k, float(params[k]))
+        ns = np.ascontiguousarray(node_state, np.float64).reshape(-1, 4)
+        nd = np.ascontiguousarray(node_distance, np.float64)
+        u = np.ascontiguousarray(uniforms, np.float64).reshape(-1, 3)
+        n = len(u)
+        out = {"status": np.zeros(n, np.uint8), "pos": np.zeros((n, 3)), "parent": np.zeros(n, np.int32), "gain": np.zeros(n),
+               "yaw": np.zeros(n), "distance": np.zeros(n), "score": np.zeros(n)}
+        best = C.c_int64(-1)
+        r = self._l.nbvo_expand_tree(self._c, tsdf_layer, esdf_layer, C.byref(P), len(ns), _ptr(ns, C.c_double), _ptr(nd, C.c_double),
+                                     n, _ptr(u, C.c_double), _ptr(out["status"], C.c_uint8), _ptr(out["pos"], C.c_double),
+                                     _ptr(out["parent"], C.c_int32), _ptr(out["gain"], C.c_double), _ptr(out["yaw"], C.c_double),
+                                     _ptr(out["distance"], C.c_double), _ptr(out["score"], C.c_double), C.byref(best), threads)
+        if r != 0:
+            raise RuntimeError(f"oracle expand_tree failed: {r}")
+        out["best_index"] = best.value
+        return out
 
     def yaw_frame(self, layer: int, pos, yaw_deg: int) -> dict:
         pos = np.ascontiguousarray(pos, np.float64)

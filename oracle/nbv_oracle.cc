@@ -559,6 +559,72 @@ int nbvo_check_segments(void* c_, int layer, double radius, size_t n, const doub
   return 0;
 }
 
+// Batched restatement of the body of RrtTree::iterate (rrt.cpp:172-246) for given uniform triples:
+// status 0 = sample rejected (outside the vicinity sphere / exploration box), 1 = edge collides,
+// 2 = node created.  Parents are the n_nodes existing nodes only (kd_nearest3 by brute force, squared
+// distance accumulated x, y, z as kdtree.c does; lowest index on ties).
+struct ExpandParams {
+  double root[3];
+  double vicinity, extension_range, overshoot, robot_radius, v_max, dyaw_max, zero_gain;
+};
+int nbvo_expand_tree(void* c_, int tsdf_layer, int esdf_layer, const ExpandParams* P, size_t n_nodes, const double* node_state,
+                     const double* node_distance, size_t n, const double* uniforms, uint8_t* status, double* pos,
+                     int32_t* parent, double* gain, double* yaw, double* distance, double* score, int64_t* best_index,
+                     int n_threads) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  if (!c->cam_set || n_nodes == 0) return -2;
+  const Layer& LT = *c->layers.at(tsdf_layer);
+  const Layer& LE = *c->layers.at(esdf_layer);
+  const Camera& cam = c->cam;
+  const bool sum_all = cam.sum_all_yaws != 0;
+  parallel_for(n, n_threads, [&](size_t i) {
+    status[i] = 0; parent[i] = -1; gain[i] = 0.0; yaw[i] = 0.0; distance[i] = 0.0; score[i] = 0.0;
+    double s[3];
+    for (int k = 0; k < 3; ++k) s[k] = 2.0 * P->vicinity * (uniforms[3 * i + k] - 0.5);          // :176-178
+    pos[3 * i] = pos[3 * i + 1] = pos[3 * i + 2] = 0.0;
+    if (s[0] * s[0] + s[1] * s[1] + s[2] * s[2] > P->vicinity * P->vicinity) return;           // :179-180
+    for (int k = 0; k < 3; ++k) s[k] += P->root[k];                                             // :182
+    if (!(s[0] >= cam.bbx_min[0] && s[0] <= cam.bbx_max[0] && s[1] >= cam.bbx_min[1] && s[1] <= cam.bbx_max[1] &&
+          s[2] >= cam.bbx_min[2] && s[2] <= cam.bbx_max[2])) return;                             // :183-185
+    size_t best = 0;                                                                            // :190-197
+    double best_d = 0.0;
+    for (size_t j = 0; j < n_nodes; ++j) {
+      double d = 0.0;
+      for (int k = 0; k < 3; ++k) { const double df = node_state[4 * j + k] - s[k]; d += df * df; }
+      if (j == 0 || d < best_d) { best_d = d; best = j; }
+    }
+    const V3 origin{node_state[4 * best], node_state[4 * best + 1], node_state[4 * best + 2]};
+    V3 dir{s[0] - origin.x, s[1] - origin.y, s[2] - origin.z};                                   // :202-203
+    if (norm(dir) > P->extension_range) dir = scale(P->extension_range, normalized(dir));       // :204-206
+    const V3 ns = add(origin, dir);                                                             // :207-209
+    const V3 un = normalized(dir);
+    const V3 end = add(add(dir, origin), V3{un.x * P->overshoot, un.y * P->overshoot, un.z * P->overshoot});  // :210-212
+    pos[3 * i] = ns.x; pos[3 * i + 1] = ns.y; pos[3 * i + 2] = ns.z;
+    parent[i] = (int32_t)best;
+    const double seg[6] = {origin.x, origin.y, origin.z, end.x, end.y, end.z};
+    status[i] = 1;
+    if (!check_motion(LE, P->robot_radius, seg, nullptr)) return;
+    status[i] = 2;
+    GainOut o{};
+    const double p3[3] = {ns.x, ns.y, ns.z};
+    eval_gain(c, LT, p3, sum_all, &o, nullptr);                                                 // :214-219
+    gain[i] = o.gain;
+    yaw[i] = o.yaw;
+    distance[i] = node_distance[best] + norm(dir);                                              // :223
+    double dy = o.yaw - node_state[4 * best + 3];                                               // :225
+    if (dy > M_PI) dy -= 2.0 * M_PI;
+    if (dy < -M_PI) dy += 2.0 * M_PI;
+    const double ttr = std::max(dy / P->dyaw_max, distance[i] / P->v_max);                      // :232-233
+    score[i] = o.gain / ttr;                                                                    // :234
+  });
+  double bg = P->zero_gain;                                                                     // :243-246, in sample order
+  int64_t bi = -1;
+  for (size_t i = 0; i < n; ++i)
+    if (status[i] == 2 && score[i] > bg) { bg = score[i]; bi = (int64_t)i; }
+  *best_index = bi;
+  return 0;
+}
+
 // castRay (integrator_utils.h:133-143): returns the number of indices the
 // reference would emit; writes at most `cap` of them.
 size_t nbvo_cast_ray(const float* start, const float* end, int64_t* out, size_t cap) {
