@@ -29,7 +29,7 @@ void box_thresholds(const nbvgpu_camera& cam, double vs, int gmin[3], int gmax[3
 // relative to the voxel that contains the candidate position: chunk_info[chunk][5] = {lower corner
 // x, y, z (padded), 16-voxel words along x, voxels along y}; *ez = voxels along z (common);
 // *max_words = largest volume in 32-bit words over the chunks.  Sizes the dense shared-memory status
-// volume of k_gain_dense.  false if the camera geometry is degenerate.
+// volume of k_gain's kDense mode.  false if the camera geometry is degenerate.
 bool dense_volume_bounds(const CameraTables& tab, double vs, int yc, int* chunk_info, int* ez, long long* max_words);
 
 }  // namespace nbvgpu_host

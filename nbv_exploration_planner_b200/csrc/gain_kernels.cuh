@@ -1,12 +1,13 @@
 // gain_kernels.cuh -- sm_100a kernels for the viewpoint-gain evaluator and its satellites.
 //
-//   k_gain<VARIANT>    RrtTree::optimized_gain / gain ray sweep   nbveplanner/src/rrt.cpp:351-447, 481-571
+//   k_gain<V,LV,MODE>  RrtTree::optimized_gain / gain ray sweep   nbveplanner/src/rrt.cpp:351-447, 481-571
 //                      + CameraModel planes / in-view test        nbveplanner/src/camera_model.cpp:5-23,98-164,191-201
 //                      + voxblox RayCaster                        voxblox/src/integrator/integrator_utils.cc:111-179
 //                      + getVoxelStatusByIndex                    nbveplanner/src/voxblox_manager.cpp:14-33
 //   k_best_yaw         best-yaw window scan                       nbveplanner/src/rrt.cpp:449-478
 //   k_score_best       node scoring / best node                   nbveplanner/src/rrt.cpp:220-246
 //   k_check_segments   HighResManager::checkMotion                nbveplanner/include/nbveplanner/voxblox_manager.h:89-108
+//   k_expand_sample    RrtTree::iterate front half (batched)      nbveplanner/src/rrt.cpp:172-212,223
 //
 // Work decomposition of k_gain: one CTA per (candidate position, chunk of `yc` consecutive
 // yaws).  The CTA prologue (a) probes the block hash once for every block the candidate can
@@ -60,7 +61,7 @@ struct GainArgs {
   int gnx, gny, gnz;  // local block grid dimensions
   int yc;             // yaws per CTA (divides 360)
   int n;
-  // dense shared-memory status volume (k_gain_dense): per-chunk lower corner relative to the
+  // dense shared-memory status volume (MODE kDense): per-chunk lower corner relative to the
   // candidate's voxel, and the common dimensions {16-voxel words along x, voxels along y, z}
   const int* vmin;    // [360 / yc][5]: lower corner x, y, z; words along x; voxels along y
   int vez, vwords;    // voxels along z (common); shared-memory words reserved for the volume

@@ -140,7 +140,7 @@ struct nbvgpu_ctx {
   int variant = 0;
   int sm_count = 148;
   int max_smem_optin = 0;
-  // dense-volume bounds cache (k_gain_dense): valid for (camera generation, voxel size, yc)
+  // dense-volume bounds cache (k_gain MODE kDense): valid for (camera generation, voxel size)
   struct DenseInfo {
     bool ok = false;
     int vez = 0;
