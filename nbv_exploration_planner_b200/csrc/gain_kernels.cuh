@@ -360,7 +360,6 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   const int stride_y = 32 * vxw, stride_z = 32 * vxw * vey;
   uint32_t vol_s = (uint32_t)__cvta_generic_to_shared(vol);
   asm volatile("mov.u32 %0, %0;" : "+r"(vol_s));  // opaque: keep the shared-window address in a register
-  constexpr unsigned kCountShift = kIsDense ? 3u : 4u;  // per-ray counter fields: bytes (dense) or 16-bit halves
 
   const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   unsigned long long my_steps = 0ull;
@@ -450,7 +449,11 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       stz = stride_z * sg[2];
     }
 
-    unsigned acc = 0u, occ = 0u;  // acc: per-code counter fields (kCountShift bits apart)
+    // Per-ray counts by power sums: every walked voxel adds its code c in {0 unknown, 1 free, 2 skip} to
+    // S1 = sum c and S2 = sum c^2; with n_acc walked voxels, n_skip = (S2 - S1) / 2, n_free = S1 - 2 n_skip,
+    // n_unknown = n_acc - n_free - n_skip (two cheap instructions per step instead of a shift-and-add).
+    unsigned S1 = 0u, S2 = 0u, occ = 0u;
+    int n_acc = -1;  // set when the walk stops early; else derived from the step counter
     int cbx = INT_MIN, cby = 0, cbz = 0, cslot = a.unknown_slot;
     float tcur = 0.0f;
     int step = 0;
@@ -467,6 +470,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       } else if (!(tcur > tA && tcur < tB) || kParanoid) {
         if (tcur > t_out) {  // left the convex exploration box for good
           if (!kParanoid) {
+            n_acc = step;    // voxels walked so far; the rest are accounted as executed but contribute nothing
             step = len + 1;
             break;
           }
@@ -557,11 +561,12 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       }
       if (code == 3u) {
         occ = 1u;
+        n_acc = step;
         ++step;  // this step was executed
         break;
       }
-      if (kIsDense) acc += 1u << (code << kCountShift);
-      else acc += (code == 2u) ? 0u : (1u << (code << kCountShift));
+      S1 += code;
+      S2 = code * code + S2;
       // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
       const bool c1 = t[1] < t[0];
       const float bm = c1 ? t[1] : t[0];
@@ -577,8 +582,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       t[2] = c2 ? __fadd_rn(t[2], dt[2]) : t[2];
     }
     my_steps += (unsigned long long)step;
-    const unsigned fmask = (1u << (1u << kCountShift)) - 1u;
-    const unsigned nu = acc & fmask, nf = (acc >> (1u << kCountShift)) & fmask;
+    if (n_acc < 0) n_acc = step;  // the walk ran to the end of the ray: len + 1 voxels
+    const unsigned n_skip = (S2 - S1) >> 1, nf = S1 - 2u * n_skip, nu = (unsigned)n_acc - nf - n_skip;
     if (nu) atomicAdd(&S.cnt[0 * yc + j], nu);
     if (nf) atomicAdd(&S.cnt[1 * yc + j], nf);
     if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);

@@ -368,11 +368,10 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   // Dense shared-memory status volume (MODE kDense) when the layer has 16^3 blocks and the volume of one
   // yaw chunk fits the budget that still allows 4 CTAs per SM: take the widest chunk that fits (narrower
   // chunks have smaller volumes), starting from the width chosen above.
-  // (byte-wide per-ray counters in that mode: a ray has at most 3 * (reach + 2) + 1 < 255 steps)
   bool dense = false;
   a.vmin = nullptr;
   a.vez = a.vwords = 0;
-  if ((variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0 && 3 * (a.reach_vox + 2) + 1 < 255) {
+  if ((variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0) {
     if (ctx->dense_gen != ctx->cam_gen || ctx->dense_vs != L->voxel_size) {
       CK(cudaStreamSynchronize(ctx->stream));  // cached tables may still be in use
       for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
