@@ -13,18 +13,24 @@
 // it restates.  Nothing is copied: the reference is Eigen/minkindr/ROS code,
 // this file is scalar C++ over plain structs.
 //
-// PARITY UNPINNED: the reference has no test, golden vector or fixture for
-// castRay / optimized_gain / checkMotion, and it cannot be built here (needs
-// ROS, Eigen, glog, minkindr, protobuf).  The only
-// reference known answers that apply are the index-math KATs of
-// voxblox/voxblox/test/test_tsdf_map.cc, which tests/test_oracle_kats.py
-// replays against the helpers below.  The Eigen / minkindr evaluation-order
-// choices that cannot be pinned are collected in the "Eigen semantics"
-// section and are single, switchable functions.
+// PINNING.  The reference holds no test, golden vector or fixture for castRay / optimized_gain /
+// checkMotion (its only applicable known answers are the index-math KATs of
+// voxblox/voxblox/test/test_tsdf_map.cc, replayed in tests/test_oracle_kats.py), and it cannot be built as
+// it is (ROS, Eigen, glog, minkindr, protobuf are absent).  The oracle is therefore pinned against the
+// reference's OWN SOURCE instead: oracle/_ref/libnbv_ref.so (oracle/Makefile `ref`, oracle/ref_wrap.cc)
+// compiles the reference's integrator_utils.cc and camera_model.cpp verbatim, its Voxblox core headers,
+// and the bodies of RrtTree::optimized_gain / gain, getVoxelStatusByIndex, checkCollisionWithRobotAtVoxel
+// and checkMotion cut out of rrt.cpp / voxblox_manager.{h,cpp} by line range, against stand-ins for the
+// third-party headers only (oracle/ref_shim/).  tests/test_ref_pinning.py compares this file with that
+// library bit for bit (ray index sequences incl. the degenerate ones, index math, hash, per-yaw planes /
+// camera positions / far-plane points, gains and yaws, edge verdicts, voxel status, the cfg-1 goldens).
+// What stays an assumption is the arithmetic of the un-vendored, un-pinned third-party libraries (Eigen's
+// dot / normalized / quaternion evaluation order, minkindr's compose / inverse): it is restated once in
+// the stand-ins and once in the "Eigen semantics" section below, as single switchable functions.
 //
-// Eigen / minkindr are third-party dependencies that are NOT vendored under
-// /root/reference (dependencies.rosinstall lists them as bare git URLs with
-// no version pin); their published algorithms are restated here.
+// Eigen / minkindr are third-party dependencies that are NOT vendored under /root/reference
+// (dependencies.rosinstall lists them as bare git URLs with no version pin); their published
+// algorithms are restated here.
 
 #include <algorithm>
 #include <atomic>

@@ -1,0 +1,216 @@
+// ref_wrap.cc -- C API over the REFERENCE'S OWN hot-path sources, compiled where they lie under
+// /root/reference into oracle/_ref/libnbv_ref.so (recipe: oracle/Makefile target `ref`).
+// TEST INFRASTRUCTURE: used only to pin the oracle restatement (tests/test_ref_pinning.py).
+//
+// What is the reference's and what is not:
+//   * verbatim reference translation units, compiled as files: voxblox/src/integrator/integrator_utils.cc
+//     (RayCaster, castRay) and nbveplanner/src/camera_model.cpp (frustum planes, isPointInView);
+//   * verbatim reference headers: voxblox/core/{common,block,block_inl,layer,layer_inl,block_hash,voxel,
+//     color}.h, voxblox/integrator/integrator_utils.h, voxblox/utils/timing.h, nbveplanner/{camera_model,
+//     common}.h;
+//   * function bodies that live in files which also include ROS headers are cut out BY LINE RANGE at
+//     build time (sed into oracle/_ref/extract/, deleted after the compile; the Makefile checks the first
+//     line of each range) and #included below inside class skeletons that only declare the members
+//     those bodies use: RrtTree::optimized_gain (rrt.cpp:351-479), RrtTree::gain (:481-579),
+//     VoxbloxManager::getVoxelStatusByIndex (voxblox_manager.cpp:14-33),
+//     HighResManager::checkCollisionWithRobotAtVoxel (:121-129), getResolution / getVoxelsPerSide
+//     (voxblox_manager.h:35-37), HighResManager::checkMotion<T> (voxblox_manager.h:89-108);
+//   * NOT the reference's: the third-party headers it needs (Eigen, minkindr, glog, protoc output) --
+//     stand-ins under oracle/ref_shim/ restating their published semantics -- and this C glue.
+// Nothing from /root/reference is copied into the repository.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+
+#include "nbveplanner/camera_model.h"
+#include "voxblox/core/layer.h"
+#include "voxblox/integrator/integrator_utils.h"
+
+#define SQ(x) ((x) * (x))            // nbveplanner/include/nbveplanner/rrt.h:22
+#define CUBE(x) ((x) * (x) * (x))    // nbveplanner/include/nbveplanner/rrt.h:23
+
+namespace nbveplanner {
+
+enum VoxelStatus { kUnknown, kOccupied, kFree };  // voxblox_manager.h:18
+
+struct Params {  // the members of nbveplanner/params.h that the extracted bodies read
+  CameraModel camera_model_;
+  double camera_hfov_ = 90.0;
+  double gain_free_ = 0.0, gain_occupied_ = 0.0, gain_unmapped_ = 1.0;
+  double robot_radius_ = 0.5;
+};
+
+class VoxbloxManager {
+ public:
+  VoxelStatus getVoxelStatusByIndex(const voxblox::BlockIndex& block_idx, const voxblox::VoxelIndex& voxel_idx) const;
+#include "extract/voxblox_manager_h_35_37.inc"
+  Params* params_ = nullptr;
+  voxblox::Layer<voxblox::TsdfVoxel>* tsdf_layer_ = nullptr;
+  double voxel_size_ = 0.0;
+};
+
+class HighResManager : public VoxbloxManager {
+ public:
+  bool checkCollisionWithRobotAtVoxel(const voxblox::GlobalIndex& global_index) const;
+#include "extract/voxblox_manager_h_89_108.inc"
+  voxblox::Layer<voxblox::EsdfVoxel>* esdf_layer_ = nullptr;
+};
+
+class RrtTree {
+ public:
+  double optimized_gain(Pose& state);
+  double gain(Pose& state);
+  VoxbloxManager* manager_lowres_ = nullptr;
+  Params* params_ = nullptr;
+};
+
+#include "extract/voxblox_manager_cpp_14_33.inc"
+#include "extract/voxblox_manager_cpp_121_129.inc"
+#include "extract/rrt_cpp_351_479.inc"
+#include "extract/rrt_cpp_481_579.inc"
+
+}  // namespace nbveplanner
+
+namespace {
+struct RefCtx {
+  std::unique_ptr<voxblox::Layer<voxblox::TsdfVoxel>> tsdf;
+  std::unique_ptr<voxblox::Layer<voxblox::EsdfVoxel>> esdf;
+  std::unique_ptr<voxblox::Layer<voxblox::TsdfVoxel>> hires_tsdf;
+  nbveplanner::Params params;
+  nbveplanner::VoxbloxManager low;
+  nbveplanner::HighResManager high;
+  nbveplanner::RrtTree tree;
+};
+}  // namespace
+
+extern "C" {
+
+void* nbvr_create(float tsdf_voxel_size, int tsdf_vps, float esdf_voxel_size, int esdf_vps) {
+  RefCtx* c = new RefCtx();
+  c->tsdf.reset(new voxblox::Layer<voxblox::TsdfVoxel>(tsdf_voxel_size, tsdf_vps));
+  c->esdf.reset(new voxblox::Layer<voxblox::EsdfVoxel>(esdf_voxel_size, esdf_vps));
+  c->low.params_ = &c->params;
+  c->low.tsdf_layer_ = c->tsdf.get();
+  c->low.voxel_size_ = c->tsdf->voxel_size();
+  c->high.params_ = &c->params;
+  c->high.esdf_layer_ = c->esdf.get();
+  // HighResManager::checkMotion scales by tsdf_layer_->voxel_size() of the HIGH-RES server's TSDF layer,
+  // which has the ESDF's voxel size: an (empty) TSDF layer object of that size stands in for it.
+  c->hires_tsdf.reset(new voxblox::Layer<voxblox::TsdfVoxel>(esdf_voxel_size, esdf_vps));
+  c->high.tsdf_layer_ = c->hires_tsdf.get();
+  c->tree.manager_lowres_ = &c->low;
+  c->tree.params_ = &c->params;
+  return c;
+}
+void nbvr_destroy(void* c_) {
+  delete static_cast<RefCtx*>(c_);
+}
+
+// planar payloads as in the oracle: TSDF [n][nvox][2] = (distance, weight), ESDF [n][nvox] = distance
+void nbvr_tsdf_update(void* c_, size_t n, const int32_t* keys, const float* data) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  const size_t nvox = c->tsdf->voxels_per_side() * c->tsdf->voxels_per_side() * c->tsdf->voxels_per_side();
+  for (size_t i = 0; i < n; ++i) {
+    auto block = c->tsdf->allocateBlockPtrByIndex(voxblox::BlockIndex(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]));
+    for (size_t v = 0; v < nvox; ++v) {
+      voxblox::TsdfVoxel& vox = block->getVoxelByLinearIndex(v);
+      vox.distance = data[(i * nvox + v) * 2];
+      vox.weight = data[(i * nvox + v) * 2 + 1];
+    }
+  }
+}
+void nbvr_esdf_update(void* c_, size_t n, const int32_t* keys, const float* data) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  const size_t nvox = c->esdf->voxels_per_side() * c->esdf->voxels_per_side() * c->esdf->voxels_per_side();
+  for (size_t i = 0; i < n; ++i) {
+    auto block = c->esdf->allocateBlockPtrByIndex(voxblox::BlockIndex(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]));
+    for (size_t v = 0; v < nvox; ++v) block->getVoxelByLinearIndex(v).distance = data[i * nvox + v];
+  }
+}
+void nbvr_tsdf_remove(void* c_, size_t n, const int32_t* keys) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  for (size_t i = 0; i < n; ++i) c->tsdf->removeBlock(voxblox::BlockIndex(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]));
+}
+
+// nbvePlanner::setUpCamera (nbvep.cpp:40-61) with the TF lookup replaced by the given T_C_B
+void nbvr_set_camera(void* c_, double hfov, double vfov, double near_m, double far_m, const double* q_CB_wxyz, const double* t_CB,
+                     const double* bbx_min, const double* bbx_max, double g_free, double g_occ, double g_unmapped, double robot_radius) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  nbveplanner::Params& p = c->params;
+  p.camera_hfov_ = hfov;
+  p.gain_free_ = g_free; p.gain_occupied_ = g_occ; p.gain_unmapped_ = g_unmapped;
+  p.robot_radius_ = robot_radius;
+  p.camera_model_.setIntrinsicsFromFoV(hfov, vfov, near_m, far_m);
+  nbveplanner::Point lo(bbx_min[0], bbx_min[1], bbx_min[2]), hi(bbx_max[0], bbx_max[1], bbx_max[2]);
+  p.camera_model_.setBoundingBox(lo, hi);
+  const nbveplanner::Transformation T_C_B(nbveplanner::Point(t_CB[0], t_CB[1], t_CB[2]),
+                                          Eigen::Quaterniond(q_CB_wxyz[0], q_CB_wxyz[1], q_CB_wxyz[2], q_CB_wxyz[3]));
+  p.camera_model_.setExtrinsics(T_C_B);
+}
+
+// RrtTree::optimized_gain / gain exactly as the planner calls them (rrt.cpp:215-219)
+void nbvr_gain_eval(void* c_, size_t n, const double* pos, int sum_all, double* gain, double* yaw) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  for (size_t i = 0; i < n; ++i) {
+    nbveplanner::Pose state(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], 123.0);
+    gain[i] = sum_all ? c->tree.gain(state) : c->tree.optimized_gain(state);
+    yaw[i] = state[3];
+  }
+}
+void nbvr_check_segments(void* c_, size_t n, const double* seg, uint8_t* is_free) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  for (size_t i = 0; i < n; ++i) {
+    const nbveplanner::Point a(seg[6 * i], seg[6 * i + 1], seg[6 * i + 2]), b(seg[6 * i + 3], seg[6 * i + 4], seg[6 * i + 5]);
+    is_free[i] = c->high.checkMotion<nbveplanner::Point>(a, b) ? 1 : 0;
+  }
+}
+// voxblox::castRay (integrator_utils.h:133-143)
+size_t nbvr_cast_ray(const float* s, const float* e, int64_t* out, size_t cap) {
+  voxblox::AlignedVector<voxblox::GlobalIndex> idx;
+  voxblox::castRay(voxblox::Point(s[0], s[1], s[2]), voxblox::Point(e[0], e[1], e[2]), &idx);
+  for (size_t i = 0; i < idx.size() && i < cap; ++i) { out[3 * i] = idx[i].x(); out[3 * i + 1] = idx[i].y(); out[3 * i + 2] = idx[i].z(); }
+  return idx.size();
+}
+// per-yaw planes / far-plane points of the real CameraModel for one body pose (rrt.cpp:369-377)
+void nbvr_yaw_frame(void* c_, const double* pos, int yaw_deg, double* planes /*[6][4]*/, double* cam /*[3]*/, double* pp /*[3][3]*/) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  const double yaw = M_PI * yaw_deg / 180.0;
+  Eigen::Quaterniond orientation;
+  orientation = Eigen::AngleAxisd(yaw, nbveplanner::Point::UnitZ());
+  const nbveplanner::Transformation T_G_B(nbveplanner::Point(pos[0], pos[1], pos[2]), orientation);
+  c->params.camera_model_.setBodyPose(T_G_B);
+  const auto& bp = c->params.camera_model_.getBoundingPlanes();
+  for (int k = 0; k < 6; ++k) {
+    const nbveplanner::Point nrm = bp[k].normal();
+    planes[4 * k] = nrm.x(); planes[4 * k + 1] = nrm.y(); planes[4 * k + 2] = nrm.z(); planes[4 * k + 3] = bp[k].distance();
+  }
+  const nbveplanner::Point cp = c->params.camera_model_.getCameraPose().getPosition();
+  cam[0] = cp.x(); cam[1] = cp.y(); cam[2] = cp.z();
+  nbveplanner::AlignedVector<nbveplanner::Point> pts;
+  c->params.camera_model_.getFarPlanePoints(0, &pts);
+  for (int k = 0; k < 3; ++k) { pp[3 * k] = pts[k].x(); pp[3 * k + 1] = pts[k].y(); pp[3 * k + 2] = pts[k].z(); }
+}
+int nbvr_in_view(void* c_, const double* p) {
+  return static_cast<RefCtx*>(c_)->params.camera_model_.isPointInView(nbveplanner::Point(p[0], p[1], p[2])) ? 1 : 0;
+}
+// index helpers (voxblox/core/common.h, block_hash.h, block_inl.h) for the KAT comparison
+void nbvr_block_and_local(const int64_t* g, int vps, int32_t* block, int32_t* local) {
+  const voxblox::GlobalIndex gi(g[0], g[1], g[2]);
+  const voxblox::BlockIndex b = voxblox::getBlockIndexFromGlobalVoxelIndex(gi, 1.0 / vps);
+  const voxblox::VoxelIndex l = voxblox::getLocalFromGlobalVoxelIndex(gi, vps);
+  for (int k = 0; k < 3; ++k) { block[k] = b[k]; local[k] = l[k]; }
+}
+void nbvr_grid_index_from_point(const float* p, float inv, int64_t* out) {
+  const voxblox::GlobalIndex g = voxblox::getGridIndexFromPoint<voxblox::GlobalIndex>(voxblox::Point(p[0], p[1], p[2]), inv);
+  for (int k = 0; k < 3; ++k) out[k] = g[k];
+}
+uint64_t nbvr_block_hash(int x, int y, int z) { return voxblox::AnyIndexHash()(voxblox::AnyIndex(x, y, z)); }
+int nbvr_voxel_status(void* c_, const int32_t* block, const int32_t* voxel) {
+  // oracle codes: 0 unknown, 1 free, 2 occupied
+  const nbveplanner::VoxelStatus s = static_cast<RefCtx*>(c_)->low.getVoxelStatusByIndex(
+      voxblox::BlockIndex(block[0], block[1], block[2]), voxblox::VoxelIndex(voxel[0], voxel[1], voxel[2]));
+  return s == nbveplanner::kUnknown ? 0 : (s == nbveplanner::kFree ? 1 : 2);
+}
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+"""Pins the oracle restatement against the REFERENCE'S OWN SOURCE: oracle/_ref/libnbv_ref.so is compiled
+from /root/reference's integrator_utils.cc, camera_model.cpp, the gain loops of rrt.cpp and the status /
+collision members of voxblox_manager.{h,cpp}, with the real Voxblox core headers, against stand-ins for the
+third-party headers only (oracle/ref_shim/).  Every comparison below is bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import binding as ob
+from oracle import ref_binding as rb
+
+pytestmark = pytest.mark.skipif(not rb.available(), reason="oracle/_ref/libnbv_ref.so not built (reference absent)")
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def reflib():
+    return rb.RefLib()
+
+
+def test_cast_ray_matches_reference_raycaster(reflib):
+    """voxblox::castRay / RayCaster (integrator_utils.cc:111-179) incl. the degenerate inf/NaN rays."""
+    g = np.load(os.path.join(GOLD, "rays_golden.npz"))
+    off = 0
+    for s, e, n in zip(g["starts"], g["ends"], g["lengths"]):
+        r = reflib.cast_ray(s, e)
+        assert len(r) == n and np.array_equal(r, g["indices"][off:off + n])
+        off += n
+    rng = np.random.default_rng(3)
+    for k in range(3000):
+        s = rng.uniform(-60, 60, 3).astype(np.float32)
+        e = (s + rng.uniform(-40, 40, 3)).astype(np.float32)
+        if k % 7 == 0:
+            e[rng.integers(0, 3)] = s[rng.integers(0, 3)] if k % 14 else e[0]   # zero / odd components
+        if k % 11 == 0:
+            ax = rng.integers(0, 3)
+            e[ax] = s[ax]
+        if k % 13 == 0:
+            s = np.round(s)                                                      # starts on voxel corners
+        assert np.array_equal(ob.cast_ray(s, e), reflib.cast_ray(s, e)), (s, e)
+
+
+def test_index_math_and_hash_match_reference_headers(reflib):
+    """voxblox/core/common.h:151-243 and block_hash.h:20-31 as compiled from the reference."""
+    rng = np.random.default_rng(4)
+    for vps in (8, 16, 32):
+        for g in rng.integers(-100000, 100000, (300, 3)):
+            bo, lo = ob.block_and_local(g.astype(np.int64), vps)
+            br, lr = reflib.block_and_local(g.astype(np.int64), vps)
+            assert np.array_equal(bo, br) and np.array_equal(lo, lr)
+    for p in rng.uniform(-50, 50, (500, 3)).astype(np.float32):
+        for inv in (np.float32(1 / 0.8), np.float32(10.0), np.float32(1 / 2.4)):
+            assert np.array_equal(ob.grid_index_from_point(p, inv), reflib.grid_index_from_point(p, inv))
+    for x, y, z in rng.integers(-5000, 5000, (500, 3)):
+        assert ob.block_hash(int(x), int(y), int(z)) == reflib.block_hash(int(x), int(y), int(z))
+
+
+def _both(m, cam, robot_radius):
+    o = ob.Oracle()
+    lt = o.layer_create(0, m.voxel_size, m.vps)
+    le = o.layer_create(1, m.voxel_size, m.vps)
+    o.layer_update(lt, m.keys, m.tsdf)
+    o.layer_update(le, m.keys, m.esdf)
+    o.set_camera(cam.as_dict())
+    r = rb.Reference(m.voxel_size, m.vps)
+    r.tsdf_update(m.keys, m.tsdf)
+    r.esdf_update(m.keys, m.esdf)
+    r.set_camera(cam.as_dict(), robot_radius)
+    return o, lt, le, r
+
+
+def test_camera_model_frames_match_reference(tiny_map):
+    """CameraModel::setBodyPose / calculateBoundingPlanes / getFarPlanePoints (camera_model.cpp) for every
+    yaw of several body positions: planes, camera position and far-plane points, bit for bit."""
+    from nbv_exploration_planner_b200.planner import CameraParams
+    cams = [tiny_map.camera(), CameraParams.mount(-20.0, (0.05, 0.02, -0.1), hfov_deg=69.0, vfov_deg=42.0, near_m=0.3, far_m=3.0,
+                                                 bbx_min=(-4, -1, 0), bbx_max=(10, 14, 3)),
+            CameraParams(hfov_deg=120, vfov_deg=90, near_m=0.1, far_m=7.5, bbx_min=(-50, -50, -5), bbx_max=(50, 50, 5))]
+    rng = np.random.default_rng(5)
+    for cam in cams:
+        o, lt, le, r = _both(tiny_map, cam, 0.4)
+        for pos in np.concatenate([rng.uniform(-30, 30, (6, 3)), [[0.0, 0.0, 0.0], [4.0, 4.0, 1.2]]]):
+            for yaw in list(range(-180, 180, 7)) + [-90, 0, 90, 179]:
+                fo, fr = o.yaw_frame(lt, pos, yaw), r.yaw_frame(pos, yaw)
+                assert np.array_equal(fo["planes"], fr["planes"]) and np.array_equal(fo["cam"], fr["cam"])
+                assert np.array_equal(fo["pp"], fr["pp"])
+
+
+@pytest.mark.parametrize("sum_all", [0, 1])
+def test_gain_matches_reference_rrt_loops(tiny_map, sum_all):
+    """RrtTree::optimized_gain (rrt.cpp:351-479) / RrtTree::gain (:481-579), verbatim: gain and state[3]."""
+    from nbv_exploration_planner_b200 import synth
+    cam = tiny_map.camera(sum_all_yaws=sum_all)
+    o, lt, le, r = _both(tiny_map, cam, tiny_map.cfg.robot_radius)
+    c = synth.make_candidates(tiny_map.cfg, 16, None)
+    pos = np.concatenate([c.positions, [[4.0, 4.0, 1.2], [3.2, 3.2, 1.6], [0.0, 0.0, 0.0], [8.0, 8.0, 3.0]]])
+    ro, rr = o.gain_eval(lt, pos, threads=8), r.gain_eval(pos)
+    assert np.array_equal(ro["gain"], rr["gain"]) and np.array_equal(ro["yaw"], rr["yaw"])
+    assert ro["gain"].max() > 0
+
+
+def test_gain_matches_reference_other_geometry(tiny_map):
+    """The shipped yaml's camera (d435 69x42 deg, 3 m range) on a 0.3 m / 16^3 layer, non-default gains."""
+    from nbv_exploration_planner_b200 import synth
+    cfg = synth.SynthConfig("pin", (-6, -5, -1), (6, 7, 3), 0.3, 3.0, 10, "pillars", 77, 78, (0.5, 0.3, 0.9), obs_radius=4.0,
+                            traj_points=5, traj_step=2.0, vicinity=3.0, hfov_deg=69.0, vfov_deg=42.0, pitch_deg=0.0)
+    m = synth.make_map(cfg)
+    cam = m.camera(gain_free=0.25, gain_occupied=0.5, gain_unmapped=1.0)   # exactly representable weights
+    o, lt, le, r = _both(m, cam, 0.4)
+    c = synth.make_candidates(cfg, 10, None)
+    ro, rr = o.gain_eval(lt, c.positions, threads=8), r.gain_eval(c.positions)
+    assert np.array_equal(ro["gain"], rr["gain"]) and np.array_equal(ro["yaw"], rr["yaw"])
+
+
+def test_check_motion_and_voxel_status_match_reference(tiny_map):
+    """HighResManager::checkMotion (voxblox_manager.h:89-108, .cpp:121-129) and getVoxelStatusByIndex (:14-33)."""
+    from nbv_exploration_planner_b200 import synth
+    cfg = tiny_map.cfg
+    for radius in (0.0, 0.2, cfg.robot_radius, 1.0):
+        o, lt, le, r = _both(tiny_map, tiny_map.camera(), radius)
+        c = synth.make_candidates(cfg, 200, None)
+        rng = np.random.default_rng(6)
+        seg = np.concatenate([c.segments, np.concatenate([rng.uniform(-1, 9, (200, 2)), rng.uniform(-0.5, 3.5, (200, 1)),
+                                                          rng.uniform(-1, 9, (200, 2)), rng.uniform(-0.5, 3.5, (200, 1))], 1)])
+        assert np.array_equal(o.check_segments(le, radius, seg)["free"], r.check_segments(seg))
+    rng = np.random.default_rng(7)
+    for g in rng.integers(-10, 60, (400, 3)):
+        b, l = ob.block_and_local(g.astype(np.int64), 16)
+        assert o.voxel_status(lt, g) == r.voxel_status(b, l)
+
+
+def test_cfg1_golden_subset_against_reference(cfg1_map):
+    """BASELINE config 1 candidates: the committed golden gains / yaws / edge verdicts equal the reference's."""
+    g = np.load(os.path.join(GOLD, "cfg1_golden.npz"))
+    r = rb.Reference(cfg1_map.voxel_size, cfg1_map.vps)
+    r.tsdf_update(cfg1_map.keys, cfg1_map.tsdf)
+    r.esdf_update(cfg1_map.keys, cfg1_map.esdf)
+    r.set_camera(cfg1_map.camera().as_dict(), cfg1_map.cfg.robot_radius)
+    sel = np.arange(0, 100, 6)
+    rr = r.gain_eval(g["positions"][sel])
+    assert np.array_equal(rr["gain"], g["gain"][sel])
+    assert np.array_equal(rr["yaw"], g["yaw_deg"][sel] * np.pi / 180.0)
+    assert np.array_equal(r.check_segments(g["segments"]), g["seg_free"])
