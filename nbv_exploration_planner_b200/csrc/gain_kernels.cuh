@@ -209,6 +209,86 @@ __device__ __forceinline__ void to_camera(const FilterConst& F, float vs_f, floa
   zk = fmaf(F.R[6], x1, fmaf(F.R[7], y1, fmaf(F.R[8], rz, F.t[2])));
 }
 
+// RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): the axis with the FIRST minimum t steps
+// (compare + select, so a NaN in t[1] / t[2] never wins and a NaN in t[0] always does -- the order of the
+// reference's minCoeff), t of that axis grows by dt, the voxel index by the step sign.  `tcur` receives the
+// ray parameter at which the next voxel is entered.  Written as predicated PTX: 6 compare/select + one
+// predicated add per carried quantity (HASP: bit address of the dense volume; HASSV: signed distance to
+// the open top/bottom plane).
+template <bool HASP, bool HASSV>
+__device__ __forceinline__ void dda_advance(float (&t)[3], const float (&dt)[3], float& tcur, int (&g)[3], const int (&sg)[3],
+                                            unsigned& P, int stx, int sty, int stz, float& sv, float d0, float d1, float d2) {
+#define NBV_DDA_SELECT                       \
+  "{\n\t"                                    \
+  ".reg .pred c1, m0, m1, m2;\n\t"           \
+  ".reg .f32 bm;\n\t"                        \
+  "setp.lt.f32 c1, %1, %0;\n\t"              \
+  "selp.f32 bm, %1, %0, c1;\n\t"             \
+  "setp.lt.f32 m2, %2, bm;\n\t"              \
+  "selp.f32 %3, %2, bm, m2;\n\t"             \
+  "setp.geu.and.f32 m1, %2, bm, c1;\n\t"     \
+  "setp.geu.and.f32 m0, %2, bm, !c1;\n\t"
+  if (HASP && HASSV) {
+    asm(NBV_DDA_SELECT
+        "@m0 add.rn.f32 %0, %0, %9;\n\t"
+        "@m1 add.rn.f32 %1, %1, %10;\n\t"
+        "@m2 add.rn.f32 %2, %2, %11;\n\t"
+        "@m0 add.s32 %4, %4, %12;\n\t"
+        "@m1 add.s32 %5, %5, %13;\n\t"
+        "@m2 add.s32 %6, %6, %14;\n\t"
+        "@m0 add.s32 %7, %7, %15;\n\t"
+        "@m1 add.s32 %7, %7, %16;\n\t"
+        "@m2 add.s32 %7, %7, %17;\n\t"
+        "@m0 add.rn.f32 %8, %8, %18;\n\t"
+        "@m1 add.rn.f32 %8, %8, %19;\n\t"
+        "@m2 add.rn.f32 %8, %8, %20;\n\t"
+        "}"
+        : "+f"(t[0]), "+f"(t[1]), "+f"(t[2]), "=&f"(tcur), "+r"(g[0]), "+r"(g[1]), "+r"(g[2]), "+r"(P), "+f"(sv)
+        : "f"(dt[0]), "f"(dt[1]), "f"(dt[2]), "r"(sg[0]), "r"(sg[1]), "r"(sg[2]), "r"(stx), "r"(sty), "r"(stz), "f"(d0), "f"(d1),
+          "f"(d2));
+  } else if (HASP) {
+    asm(NBV_DDA_SELECT
+        "@m0 add.rn.f32 %0, %0, %8;\n\t"
+        "@m1 add.rn.f32 %1, %1, %9;\n\t"
+        "@m2 add.rn.f32 %2, %2, %10;\n\t"
+        "@m0 add.s32 %4, %4, %11;\n\t"
+        "@m1 add.s32 %5, %5, %12;\n\t"
+        "@m2 add.s32 %6, %6, %13;\n\t"
+        "@m0 add.s32 %7, %7, %14;\n\t"
+        "@m1 add.s32 %7, %7, %15;\n\t"
+        "@m2 add.s32 %7, %7, %16;\n\t"
+        "}"
+        : "+f"(t[0]), "+f"(t[1]), "+f"(t[2]), "=&f"(tcur), "+r"(g[0]), "+r"(g[1]), "+r"(g[2]), "+r"(P)
+        : "f"(dt[0]), "f"(dt[1]), "f"(dt[2]), "r"(sg[0]), "r"(sg[1]), "r"(sg[2]), "r"(stx), "r"(sty), "r"(stz));
+  } else if (HASSV) {
+    asm(NBV_DDA_SELECT
+        "@m0 add.rn.f32 %0, %0, %8;\n\t"
+        "@m1 add.rn.f32 %1, %1, %9;\n\t"
+        "@m2 add.rn.f32 %2, %2, %10;\n\t"
+        "@m0 add.s32 %4, %4, %11;\n\t"
+        "@m1 add.s32 %5, %5, %12;\n\t"
+        "@m2 add.s32 %6, %6, %13;\n\t"
+        "@m0 add.rn.f32 %7, %7, %14;\n\t"
+        "@m1 add.rn.f32 %7, %7, %15;\n\t"
+        "@m2 add.rn.f32 %7, %7, %16;\n\t"
+        "}"
+        : "+f"(t[0]), "+f"(t[1]), "+f"(t[2]), "=&f"(tcur), "+r"(g[0]), "+r"(g[1]), "+r"(g[2]), "+f"(sv)
+        : "f"(dt[0]), "f"(dt[1]), "f"(dt[2]), "r"(sg[0]), "r"(sg[1]), "r"(sg[2]), "f"(d0), "f"(d1), "f"(d2));
+  } else {
+    asm(NBV_DDA_SELECT
+        "@m0 add.rn.f32 %0, %0, %7;\n\t"
+        "@m1 add.rn.f32 %1, %1, %8;\n\t"
+        "@m2 add.rn.f32 %2, %2, %9;\n\t"
+        "@m0 add.s32 %4, %4, %10;\n\t"
+        "@m1 add.s32 %5, %5, %11;\n\t"
+        "@m2 add.s32 %6, %6, %12;\n\t"
+        "}"
+        : "+f"(t[0]), "+f"(t[1]), "+f"(t[2]), "=&f"(tcur), "+r"(g[0]), "+r"(g[1]), "+r"(g[2])
+        : "f"(dt[0]), "f"(dt[1]), "f"(dt[2]), "r"(sg[0]), "r"(sg[1]), "r"(sg[2]));
+  }
+#undef NBV_DDA_SELECT
+}
+
 // ---------------------------------------------------------------------------------------------
 // k_gain<VARIANT, LV, MODE> -- the ray sweep.
 //
@@ -369,7 +449,10 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     const int r = base + lane;
     const int u = r / yc;
     const int j = r - u * yc;
-    if (r >= n_rays || u >= S.um[j]) continue;
+    // The batch loop is warp-uniform; lanes without a ray (tail of the last batch, rows beyond this yaw's
+    // u_max) run the set-up on in-range table entries and never walk, so that the warp-level
+    // synchronisation between the stretches of the walk below always sees all 32 lanes.
+    const bool active = r < n_rays && u < S.um[j];
 
     // ---- ray end point (rrt.cpp:396,410-411) and RayCaster setup (integrator_utils.cc:127-179)
     int g[3], sg[3];
@@ -442,6 +525,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     // in: word address (P >> 3) & ~3, bit position P & 31; vol_s is 16-byte aligned) and per-axis strides
     unsigned P = 0u;
     int stx = 0, sty = 0, stz = 0;
+    float dummy_sv = 0.0f;
     if (kIsDense) {
       P = (unsigned)(((g[2] - z0) * vey + (g[1] - y0)) * stride_y + 2 * (g[0] - x0)) + 8u * vol_s;
       stx = 2 * sg[0];
@@ -450,143 +534,221 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     }
 
     // Per-ray counts by power sums: every walked voxel adds its code c in {0 unknown, 1 free, 2 skip} to
-    // S1 = sum c and S2 = sum c^2; with n_acc walked voxels, n_skip = (S2 - S1) / 2, n_free = S1 - 2 n_skip,
-    // n_unknown = n_acc - n_free - n_skip (two cheap instructions per step instead of a shift-and-add).
+    // S1 = sum c and S2 = sum c^2; with n_acc counted voxels, n_skip = (S2 - S1) / 2, n_free = S1 - 2 n_skip,
+    // n_unknown = n_acc - n_free - n_skip.  The high half of S1 counts the voxels walked (the RayCaster's
+    // step counter, integrator_utils.cc:111-117), so one add and one compare per step serve both.
     unsigned S1 = 0u, S2 = 0u, occ = 0u;
-    int n_acc = -1;  // set when the walk stops early; else derived from the step counter
+    const unsigned walk_end = (unsigned)(len + 1) << 16;  // the ray emits len + 1 voxels
+    int skipped = 0;  // voxels past t_out: accounted as executed, never looked at
     int cbx = INT_MIN, cby = 0, cbz = 0, cslot = a.unknown_slot;
     float tcur = 0.0f;
-    int step = 0;
-    for (; step <= len; ++step) {
-      // ---- exploration box (integer thresholds, exact); folded into the volume in dense mode
-      bool inbox = true;
-      if (!kIsDense || kParanoid)
-        inbox = (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
-                (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
-      // ---- frustum (camera_model.cpp:194-199), cheapest decision first
-      bool fin = true;
-      if (!kFilter) {
-        fin = inbox && exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-      } else if (!(tcur > tA && tcur < tB) || kParanoid) {
-        if (tcur > t_out) {  // left the convex exploration box for good
-          if (!kParanoid) {
-            n_acc = step;    // voxels walked so far; the rest are accounted as executed but contribute nothing
-            step = len + 1;
+    bool run = active;
+
+    // Exploration box on integer thresholds (exact); folded into the volume in dense mode.
+    auto in_box = [&]() -> bool {
+      return (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+             (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
+    };
+    // Voxel code of the current voxel as the map has it: 0 unknown, 1 free, 3 occupied (voxblox_manager.cpp:14-33);
+    // the dense volume also answers 2 for voxels outside the exploration box.
+    auto tile_code = [&]() -> unsigned {
+      const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
+      int slot;
+      if (MODE == kGrid) {
+        slot = sgrid[(bz * a.gny + by) * a.gnx + bx + gbase];
+      } else if (MODE == kProbe) {
+        if (bx != cbx || by != cby || bz != cbz) {
+          cbx = bx; cby = by; cbz = bz;
+          cslot = probe_block(a.L, bx, by, bz);
+          if (cslot < 0) cslot = a.unknown_slot;  // all-unknown tile
+        }
+        slot = cslot;
+      } else {  // dense mode asks the tiles only to cross-check the volume (variant 2)
+        slot = probe_block(a.L, bx, by, bz);
+        if (slot < 0) slot = a.unknown_slot;
+      }
+      const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
+      unsigned st;
+      if (kStatusBits) {
+        st = (__ldg(a.L.status + ((unsigned)slot * (nvox >> 4) + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
+      } else {
+        const float2 vx = __ldg(reinterpret_cast<const float2*>(a.L.tiles) + ((size_t)slot * nvox + lin));
+        st = tsdf_status(vx.x, vx.y);
+      }
+      return st | (st >> 1);  // 2 (occupied) -> 3
+    };
+    auto volume_code = [&]() -> unsigned {
+      uint32_t w;  // one word of the dense volume (always in range)
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((P >> 3) & ~3u));
+      const unsigned code = __funnelshift_r(w, 0u, P) & 3u;
+      if (kParanoid) {
+        const unsigned want = in_box() ? tile_code() : 2u;
+        if (((P - 8u * vol_s) >> 5) >= (unsigned)nvol || want != code) ++my_mismatch;
+      }
+      return code;
+    };
+
+    // A ray passes through up to three kinds of stretches, in this order: the general one (ray start; again at
+    // the very end, where the far plane is open), a stretch where only the nearer of top/bottom is open (whole
+    // rays in the rows that hug those planes), and the window in which every plane is sure.  One loop per
+    // kind, so that the lanes of a warp -- neighbouring yaws of the same row, with near-equal boundaries --
+    // run the same kind together instead of dragging each other through the general code: the warp is
+    // re-converged between the loops, and lanes that finished a stretch early wait for the others there.
+    while (__any_sync(0xffffffffu, run)) {
+      // ---- general loop (camera_model.cpp:194-199 decided cheapest first)
+      while (run && (!kFilter || !(tcur > tlo && tcur < tB))) {
+        const bool inbox = (!kIsDense || kParanoid) ? in_box() : true;
+        bool fin = true;
+        if (!kFilter) {
+          fin = inbox && exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+        } else {
+          if (tcur > t_out) {  // left the convex exploration box for good
+            if (!kParanoid) {
+              skipped = len + 1 - (int)(S1 >> 16);  // the rest is accounted as executed but contributes nothing
+              run = false;
+              break;
+            }
+            if (inbox) ++my_mismatch;
+          }
+          bool decided = false;
+          fin = false;
+          if (kIsDense || inbox) {
+            if (tcur > tlo) {
+              // near, left/right and the farther of top/bottom are sure; open: the far plane once tcur >= thi,
+              // the nearer of top/bottom while tcur <= tlo_v -> one single-precision plane evaluation each
+              const float dx = (float)(g[0] - g0x), dy = (float)(g[1] - g0y), dz = (float)(g[2] - g0z);
+              float sf = 3.0e38f;
+              if (!(tcur < thi)) sf = fmaf(S.fp[0 * yc + j], dx, fmaf(S.fp[1 * yc + j], dy, fmaf(S.fp[2 * yc + j], dz, S.fp[3 * yc + j])));
+              const float sv = fmaf(pa[0], dx, fmaf(pa[1], dy, fmaf(pa[2], dz, pc)));
+              // the smaller of the open planes' signed distances decides: > m in, < -m out, else exact test
+              const float smin = fminf(sf, tcur > tlo_v ? 3.0e38f : sv);
+              fin = smin > F.m;
+              decided = fin || smin < -F.m;
+            }
+            if (!decided || kParanoid) {
+              float xc, yk, zk;
+              to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
+                        S.csf[yc + j], xc, yk, zk);
+              const float s0 = xc - F.nearp, s1 = F.farp - xc;
+              const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
+              const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
+              const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
+              bool ex;
+              if (kParanoid) {
+                ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+                if ((sure_in && !ex) || (sure_out && ex) || (decided && fin != ex)) ++my_mismatch;
+              } else if (sure_in) {
+                ex = true;
+              } else if (sure_out) {
+                ex = false;
+              } else {
+                ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+              }
+              fin = ex;
+            }
+          }
+          if (!kIsDense) fin = fin && inbox;
+        }
+        unsigned code = 2u;
+        if (kIsDense) {
+          code = volume_code();
+          code = fin ? code : 2u;
+        } else if (fin) {
+          code = tile_code();
+        }
+        if (code == 3u) {
+          occ = 1u;
+          S1 += 0x10000u;  // this step was executed
+          run = false;
+          break;
+        }
+        if (tcur != tcur) {
+          // t[0] is NaN: the ray has no x component (integer yaws +-90 deg), its first x "crossing" was at
+          // -inf (or 0/0) and grew by dt = 0/0.  minCoeff then picks axis 0 for ever, whose step is 0: the
+          // RayCaster emits this same voxel for all remaining steps (integrator_utils.cc:119-123,165-179).
+          const unsigned rem = (unsigned)(len + 1) - (S1 >> 16);
+          S1 += rem * (code + 0x10000u);
+          S2 += rem * code * code;
+          run = false;
+          break;
+        }
+        S1 += code + 0x10000u;
+        S2 = code * code + S2;
+        if (kIsDense) dda_advance<true, false>(t, dt, tcur, g, sg, P, stx, sty, stz, dummy_sv, 0.f, 0.f, 0.f);
+        else dda_advance<false, false>(t, dt, tcur, g, sg, P, 0, 0, 0, dummy_sv, 0.f, 0.f, 0.f);
+        run = S1 < walk_end;
+      }
+      if (!kFilter) continue;
+      __syncwarp();
+      // ---- only the nearer of top/bottom is open (tlo < tcur <= tlo_v, before thi and t_out): its signed
+      //      distance is evaluated once on entry and then follows the walk with one add per step.  The n
+      //      roundings of that sum are covered by widening the decision margin (|sv| <= reach + 1 m, so each is
+      //      below 2^-24 * 1e5 * F.m); inside the margin the exact planes decide.
+      if (run && tcur < tB && !(tcur > tlo_v)) {
+        float sv = fmaf(pa[0], (float)(g[0] - g0x), fmaf(pa[1], (float)(g[1] - g0y), fmaf(pa[2], (float)(g[2] - g0z), pc)));
+        const float d0 = pa[0] * (float)sg[0], d1 = pa[1] * (float)sg[1], d2 = pa[2] * (float)sg[2];
+        const float mi = F.m * (1.0f + 0.01f * (float)(len + 1));
+        do {
+          bool fin = sv > mi;
+          if (!fin && !(sv < -mi)) fin = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+          if (kParanoid && fin != exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs) && (kIsDense || in_box())) ++my_mismatch;
+          unsigned code = 2u;
+          if (kIsDense) {
+            code = volume_code();
+            code = fin ? code : 2u;
+          } else if (fin && in_box()) {
+            code = tile_code();
+          }
+          if (code == 3u) {
+            occ = 1u;
+            S1 += 0x10000u;
+            run = false;
             break;
           }
-          if (inbox) ++my_mismatch;
-        }
-        bool decided = false;
-        fin = false;
-        if (kIsDense || inbox) {
-          if (tcur > tlo) {
-            // near, left/right and the farther of top/bottom are sure; open: the far plane once tcur >= thi,
-            // the nearer of top/bottom while tcur <= tlo_v -> one single-precision plane evaluation each
-            const float dx = (float)(g[0] - g0x), dy = (float)(g[1] - g0y), dz = (float)(g[2] - g0z);
-            float sf = 3.0e38f;
-            if (!(tcur < thi)) sf = fmaf(S.fp[0 * yc + j], dx, fmaf(S.fp[1 * yc + j], dy, fmaf(S.fp[2 * yc + j], dz, S.fp[3 * yc + j])));
-            const float sv = fmaf(pa[0], dx, fmaf(pa[1], dy, fmaf(pa[2], dz, pc)));
-            // the smaller of the open planes' signed distances decides: > m in, < -m out, else exact test
-            const float smin = fminf(sf, tcur > tlo_v ? 3.0e38f : sv);
-            fin = smin > F.m;
-            decided = fin || smin < -F.m;
-          }
-          if (!decided || kParanoid) {
-            float xc, yk, zk;
-            to_camera(F, a.vs_f, (float)(g[0] - g0x), (float)(g[1] - g0y), (float)(g[2] - g0z), noffx, noffy, noffz, S.csf[j],
-                      S.csf[yc + j], xc, yk, zk);
-            const float s0 = xc - F.nearp, s1 = F.farp - xc;
-            const float sh = fmaf(F.th, xc, -fabsf(yk)), sv = fmaf(F.tv, xc, -fabsf(zk));
-            const bool sure_in = s0 > F.m && s1 > F.m && sh > F.mh && sv > F.mv;
-            const bool sure_out = s0 < -F.m || s1 < -F.m || sh < -F.mh || sv < -F.mv;
-            bool ex;
-            if (kParanoid) {
-              ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-              const bool fast_all = tcur > tA && tcur < tB;
-              if ((sure_in && !ex) || (sure_out && ex) || (decided && fin != ex) || (fast_all && !ex)) ++my_mismatch;
-            } else if (sure_in) {
-              ex = true;
-            } else if (sure_out) {
-              ex = false;
-            } else {
-              ex = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
-            }
-            fin = ex;
-          }
-        }
-      } else if (!kIsDense) {
-        fin = inbox;  // inside the all-sure window the box is sure as well only up to t_out, which tB includes;
-                      // the integer test is kept as the authority (cheap) -- and cross-checked in variant 2
+          S1 += code + 0x10000u;
+          S2 = code * code + S2;
+          if (kIsDense) dda_advance<true, true>(t, dt, tcur, g, sg, P, stx, sty, stz, sv, d0, d1, d2);
+          else dda_advance<false, true>(t, dt, tcur, g, sg, P, 0, 0, 0, sv, d0, d1, d2);
+          run = S1 < walk_end;
+        } while (run && tcur < tB && !(tcur > tlo_v));
       }
-      // ---- voxel code: 0 unknown, 1 free, 2 skip, 3 occupied (voxblox_manager.cpp:14-33)
-      unsigned code = 2u;
-      if (kIsDense) {
-        uint32_t w;  // one word of the dense volume (always in range)
-        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((P >> 3) & ~3u));
-        code = __funnelshift_r(w, 0u, P) & 3u;
-        if (kParanoid) {
-          unsigned want = 2u;
-          if (inbox) {
-            int slot = probe_block(a.L, g[0] >> lv, g[1] >> lv, g[2] >> lv);
-            if (slot < 0) slot = a.unknown_slot;
-            const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
-            const unsigned st = (__ldg(a.L.status + ((unsigned)slot * (nvox >> 4) + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
-            want = st == 2u ? 3u : st;
+      __syncwarp();
+      // ---- window: every plane is sure, the voxel counts unless it is outside the exploration box
+      if (run && tcur > tA && tcur < tB) {
+        do {
+          if (kParanoid && (kIsDense || in_box()) && !exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs)) {
+            if (in_box()) ++my_mismatch;
           }
-          if (((P - 8u * vol_s) >> 5) >= (unsigned)nvol || want != code) ++my_mismatch;
-        }
-        code = fin ? code : 2u;
-      } else if (fin) {
-        const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
-        int slot;
-        if (MODE == kGrid) {
-          slot = sgrid[(bz * a.gny + by) * a.gnx + bx + gbase];
-        } else {
-          if (bx != cbx || by != cby || bz != cbz) {
-            cbx = bx; cby = by; cbz = bz;
-            cslot = probe_block(a.L, bx, by, bz);
-            if (cslot < 0) cslot = a.unknown_slot;  // all-unknown tile
+          unsigned code = 2u;
+          if (kIsDense) {
+            code = volume_code();
+          } else if (in_box()) {
+            code = tile_code();
           }
-          slot = cslot;
-        }
-        const unsigned lin = (unsigned)((g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv)));
-        unsigned st;
-        if (kStatusBits) {
-          st = (__ldg(a.L.status + ((unsigned)slot * (nvox >> 4) + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
-        } else {
-          const float2 vx = __ldg(reinterpret_cast<const float2*>(a.L.tiles) + ((size_t)slot * nvox + lin));
-          st = tsdf_status(vx.x, vx.y);
-        }
-        code = st | (st >> 1);  // 2 (occupied) -> 3
+          if (code == 3u) {
+            occ = 1u;
+            S1 += 0x10000u;
+            run = false;
+            break;
+          }
+          S1 += code + 0x10000u;
+          S2 = code * code + S2;
+          if (kIsDense) dda_advance<true, false>(t, dt, tcur, g, sg, P, stx, sty, stz, dummy_sv, 0.f, 0.f, 0.f);
+          else dda_advance<false, false>(t, dt, tcur, g, sg, P, 0, 0, 0, dummy_sv, 0.f, 0.f, 0.f);
+          run = S1 < walk_end;
+        } while (run && tcur < tB);
       }
-      if (code == 3u) {
-        occ = 1u;
-        n_acc = step;
-        ++step;  // this step was executed
-        break;
-      }
-      S1 += code;
-      S2 = code * code + S2;
-      // ---- RayCaster::nextRayIndex advance (integrator_utils.cc:119-123): first minimum wins
-      const bool c1 = t[1] < t[0];
-      const float bm = c1 ? t[1] : t[0];
-      const bool c2 = t[2] < bm;
-      tcur = c2 ? t[2] : bm;  // ray parameter at which the next voxel is entered
-      const bool m0 = !c1 && !c2, m1 = c1 && !c2;
-      if (kIsDense) P += (unsigned)(c2 ? stz : (c1 ? sty : stx));
-      g[0] += m0 ? sg[0] : 0;
-      g[1] += m1 ? sg[1] : 0;
-      g[2] += c2 ? sg[2] : 0;
-      t[0] = m0 ? __fadd_rn(t[0], dt[0]) : t[0];
-      t[1] = m1 ? __fadd_rn(t[1], dt[1]) : t[1];
-      t[2] = c2 ? __fadd_rn(t[2], dt[2]) : t[2];
     }
-    my_steps += (unsigned long long)step;
-    if (n_acc < 0) n_acc = step;  // the walk ran to the end of the ray: len + 1 voxels
-    const unsigned n_skip = (S2 - S1) >> 1, nf = S1 - 2u * n_skip, nu = (unsigned)n_acc - nf - n_skip;
-    if (nu) atomicAdd(&S.cnt[0 * yc + j], nu);
-    if (nf) atomicAdd(&S.cnt[1 * yc + j], nf);
-    if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);
+    const unsigned walked = S1 >> 16;  // includes the occupied voxel that stopped the ray
+    S1 &= 0xFFFFu;
+    my_steps += (unsigned long long)(walked + (unsigned)skipped);
+    const unsigned n_acc = walked - occ;
+    const unsigned n_skip = (S2 - S1) >> 1, nf = S1 - 2u * n_skip, nu = n_acc - nf - n_skip;
+    if (active) {
+      if (nu) atomicAdd(&S.cnt[0 * yc + j], nu);
+      if (nf) atomicAdd(&S.cnt[1 * yc + j], nf);
+      if (occ) atomicAdd(&S.cnt[2 * yc + j], occ);
+    }
   }
   // ---- CTA epilogue
 #pragma unroll
