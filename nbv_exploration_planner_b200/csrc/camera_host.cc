@@ -160,6 +160,7 @@ bool dense_volume_bounds(const CameraTables& tab, double vs, int yc, int* chunk_
       ext[k] = (int)(b - a) + 1;
     }
     chunk_info[5 * c + 3] = (ext[0] + 15) / 16 + 1;
+    if (chunk_info[5 * c + 3] > 32) return false;  // kMaxDenseWordsX: the kernel keeps one box mask per x word
     chunk_info[5 * c + 4] = ext[1];
     if (ext[2] > ez) ez = ext[2];
     const long long w = (long long)chunk_info[5 * c + 3] * ext[1];

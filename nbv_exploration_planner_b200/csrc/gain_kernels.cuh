@@ -34,6 +34,7 @@ namespace nbvgpu {
 
 constexpr int kGainThreads = 256;
 constexpr int kMaxReachVox = 4096;
+constexpr int kMaxDenseWordsX = 32;  // 16-voxel words along x of the dense shared-memory volume
 
 struct FilterConst {
   float R[9];  // camera <- body rotation (row major)
@@ -345,6 +346,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   __shared__ int s_umax;
   __shared__ unsigned long long s_steps;
   __shared__ unsigned int s_mismatch;
+  __shared__ uint32_t s_outm[kMaxDenseWordsX];
 
   const int chunks = 360 / yc;
   const int v = blockIdx.x / chunks;
@@ -379,6 +381,21 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     const int sl = probe_block(a.L, b0x + ix, b0y + iy, b0z + iz);
     S.grid[i] = sl < 0 ? a.unknown_slot : sl;
   }
+  // dense volume: origin along x (global voxel index aligned down to a block row) and, per 16-voxel word,
+  // the mask of voxels outside the exploration box along x
+  const int dense_x0 = kIsDense ? (((g0x + a.vmin[5 * chunk]) >> 4) << 4) : 0;
+  if (kIsDense && tid < kMaxDenseWordsX) {
+    const int lo = a.gmin[0] - (dense_x0 + 16 * tid);  // in-box voxels of word `tid`: lo .. lo + gspan
+    const long long hi = (long long)lo + (long long)a.gspan[0];
+    uint32_t om = 0xFFFFFFFFu;
+    if (hi >= 0 && lo <= 15) {
+      const int l = lo > 0 ? lo : 0, h = hi < 15 ? (int)hi : 15;
+      const uint32_t below = (1u << (2 * l)) - 1u;                                  // voxels < l
+      const uint32_t upto = h == 15 ? 0xFFFFFFFFu : ((1u << (2 * (h + 1))) - 1u);  // voxels <= h
+      om = below | ~upto;
+    }
+    s_outm[tid] = om;
+  }
   for (int j = tid; j < yc; j += blockDim.x) {
     const int y = chunk * yc + j;
     build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, S.sl, a.vs,
@@ -390,41 +407,45 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   // (c) dense status volume, one (y, z) row of Xw words per thread and iteration
   int x0 = 0, y0 = 0, z0 = 0, vxw = 0, vey = 0, nvol = 0;
   if (kIsDense) {
-    x0 = ((g0x + a.vmin[5 * chunk]) >> 4) << 4;  // origin: global voxel index, x aligned down to a block row
     y0 = g0y + a.vmin[5 * chunk + 1];
     z0 = g0z + a.vmin[5 * chunk + 2];
+    x0 = dense_x0;
     vxw = a.vmin[5 * chunk + 3];
     vey = a.vmin[5 * chunk + 4];
     nvol = vxw * vey * a.vez;
-    for (int row = tid; row < vey * a.vez; row += blockDim.x) {
-      const int gy = y0 + row % vey, gz = z0 + row / vey;
+    const int nrows = vey * a.vez;
+    int ry = tid % vey, rz = tid / vey;                             // row = rz * vey + ry
+    const int dy = (int)blockDim.x % vey, dz = (int)blockDim.x / vey;  // row += blockDim.x
+    for (int row = tid; row < nrows; row += blockDim.x) {
+      const int gy = y0 + ry, gz = z0 + rz;
       const bool row_in = (unsigned)(gy - a.gmin[1]) <= a.gspan[1] && (unsigned)(gz - a.gmin[2]) <= a.gspan[2];
       const int iy = (gy >> 4) - b0y, iz = (gz >> 4) - b0z;
       const bool row_grid = (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz;
       const unsigned rowoff = (unsigned)(((gz & 15) << 4) | (gy & 15));
+      const int ix0 = (x0 >> 4) - b0x;
+      const int* const grow = S.grid + (iz * a.gny + iy) * a.gnx;
+      uint32_t* const vrow = vol + row * vxw;
       for (int wx = 0; wx < vxw; ++wx) {
-        const int gx = x0 + 16 * wx;
-        uint32_t word = 0xAAAAAAAAu;  // 16 x "skip"
-        const long long lo = (long long)a.gmin[0] - gx, hi = lo + (long long)a.gspan[0];  // in-box x range inside the word
-        if (row_in && hi >= 0 && lo <= 15) {
-          const int ix = (gx >> 4) - b0x;
+        const uint32_t om = s_outm[wx];  // voxels of this word outside the exploration box along x
+        uint32_t word = 0xAAAAAAAAu;     // 16 x "skip"
+        if (row_in && om != 0xFFFFFFFFu) {
+          const int ix = ix0 + wx;
           int slot;
           if (row_grid && (unsigned)ix < (unsigned)a.gnx) {
-            slot = S.grid[(iz * a.gny + iy) * a.gnx + ix];
+            slot = grow[ix];
           } else {
-            slot = probe_block(a.L, gx >> 4, gy >> 4, gz >> 4);
+            slot = probe_block(a.L, (x0 >> 4) + wx, gy >> 4, gz >> 4);
             if (slot < 0) slot = a.unknown_slot;
           }
           word = __ldg(a.L.status + ((unsigned)slot * 256u + rowoff));
           word |= (word >> 1) & 0x55555555u;  // tile status 2 (occupied) -> code 3
-          const int l = lo > 0 ? (int)lo : 0, h = hi < 15 ? (int)hi : 15;
-          const uint32_t below = (1u << (2 * l)) - 1u;                                  // voxels < l
-          const uint32_t upto = h == 15 ? 0xFFFFFFFFu : ((1u << (2 * (h + 1))) - 1u);  // voxels <= h
-          const uint32_t outm = below | ~upto;
-          word = (word & ~outm) | (outm & 0xAAAAAAAAu);
+          word = (word & ~om) | (om & 0xAAAAAAAAu);
         }
-        vol[row * vxw + wx] = word;
+        vrow[wx] = word;
       }
+      ry += dy;
+      rz += dz;
+      if (ry >= vey) { ry -= vey; ++rz; }
     }
   }
   __syncthreads();
@@ -531,6 +552,9 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       stx = 2 * sg[0];
       sty = stride_y * sg[1];
       stz = stride_z * sg[2];
+      // opaque: keep the three strides in registers (ptxas otherwise re-derives them from the step signs
+      // inside the loops, on the integer pipe that bounds the kernel)
+      asm volatile("" : "+r"(stx), "+r"(sty), "+r"(stz));
     }
 
     // Per-ray counts by power sums: every walked voxel adds its code c in {0 unknown, 1 free, 2 skip} to
@@ -689,24 +713,24 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
         const float d0 = pa[0] * (float)sg[0], d1 = pa[1] * (float)sg[1], d2 = pa[2] * (float)sg[2];
         const float mi = F.m * (1.0f + 0.01f * (float)(len + 1));
         do {
-          bool fin = sv > mi;
-          if (!fin && !(sv < -mi)) fin = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+          bool fin = sv > 0.0f;
+          if (!(fabsf(sv) > mi)) fin = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);  // inside the margin (rare)
           if (kParanoid && fin != exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs) && (kIsDense || in_box())) ++my_mismatch;
-          unsigned code = 2u;
+          unsigned c = 0x10002u;  // code + 2^16, as in the window loop below
           if (kIsDense) {
-            code = volume_code();
-            code = fin ? code : 2u;
+            c = volume_code() | 0x10000u;
+            c = fin ? c : 0x10002u;
           } else if (fin && in_box()) {
-            code = tile_code();
+            c = tile_code() | 0x10000u;
           }
-          if (code == 3u) {
+          if (c == 0x10003u) {
             occ = 1u;
             S1 += 0x10000u;
             run = false;
             break;
           }
-          S1 += code + 0x10000u;
-          S2 = code * code + S2;
+          S1 += c;
+          S2 = c * c + S2;
           if (kIsDense) dda_advance<true, true>(t, dt, tcur, g, sg, P, stx, sty, stz, sv, d0, d1, d2);
           else dda_advance<false, true>(t, dt, tcur, g, sg, P, 0, 0, 0, sv, d0, d1, d2);
           run = S1 < walk_end;
@@ -719,20 +743,26 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
           if (kParanoid && (kIsDense || in_box()) && !exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs)) {
             if (in_box()) ++my_mismatch;
           }
-          unsigned code = 2u;
+          // c = code + 2^16 (the walk counter's bit) in one logic op
+          unsigned c = 0x10002u;
           if (kIsDense) {
-            code = volume_code();
+            uint32_t w;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((P >> 3) & ~3u));
+            asm("lop3.b32 %0, %1, 3, 0x10000, 0xEA;" : "=r"(c) : "r"(__funnelshift_r(w, 0u, P)));  // (x & 3) | 2^16
+            if (kParanoid && (c & 3u) != volume_code()) ++my_mismatch;  // volume_code() cross-checks against the tiles
           } else if (in_box()) {
-            code = tile_code();
+            c = tile_code() | 0x10000u;
           }
-          if (code == 3u) {
+          if (c == 0x10003u) {
             occ = 1u;
             S1 += 0x10000u;
             run = false;
             break;
           }
-          S1 += code + 0x10000u;
-          S2 = code * code + S2;
+          // c^2 = code^2 + code * 2^17 (mod 2^32): the low 17 bits of S2 stay the sum of squares, the rest is
+          // masked off after the walk
+          S1 += c;
+          S2 = c * c + S2;
           if (kIsDense) dda_advance<true, false>(t, dt, tcur, g, sg, P, stx, sty, stz, dummy_sv, 0.f, 0.f, 0.f);
           else dda_advance<false, false>(t, dt, tcur, g, sg, P, 0, 0, 0, dummy_sv, 0.f, 0.f, 0.f);
           run = S1 < walk_end;
@@ -741,6 +771,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     }
     const unsigned walked = S1 >> 16;  // includes the occupied voxel that stopped the ray
     S1 &= 0xFFFFu;
+    S2 &= 0x1FFFFu;
     my_steps += (unsigned long long)(walked + (unsigned)skipped);
     const unsigned n_acc = walked - occ;
     const unsigned n_skip = (S2 - S1) >> 1, nf = S1 - 2u * n_skip, nu = n_acc - nf - n_skip;
