@@ -123,15 +123,6 @@ __device__ __forceinline__ GainSmem carve(unsigned char* base, int yc, int gn) {
 }
 inline size_t gain_smem_bytes(int yc, int gn) { return (size_t)yc * (33 * 8 + 27 * 4) + (((size_t)gn * 4 + 15) & ~(size_t)15) + 16; }
 
-// Plane::setFromPoints + store (camera_model.cpp:5-11).
-__device__ __forceinline__ void store_plane(double* pl, int yc, int j, int k, const D3& p1, const D3& p2, const D3& p3) {
-  const D3 n = d3normalized(d3cross(d3sub(p2, p1), d3sub(p3, p1)));
-  pl[(4 * k + 0) * yc + j] = n.x;
-  pl[(4 * k + 1) * yc + j] = n.y;
-  pl[(4 * k + 2) * yc + j] = n.z;
-  pl[(4 * k + 3) * yc + j] = d3dot(n, p1);
-}
-
 // CameraModel::isPointInView plane part (camera_model.cpp:194-199) on P = (double)g * vs.
 __device__ __forceinline__ bool exact_in_frustum(const double* pl, int yc, int j, int gx, int gy, int gz, double vs) {
   const double px = dmul((double)gx, vs), py = dmul((double)gy, vs), pz = dmul((double)gz, vs);
@@ -144,34 +135,59 @@ __device__ __forceinline__ bool exact_in_frustum(const double* pl, int yc, int j
   return true;
 }
 
-// CTA prologue, part (b): per-yaw frames (rrt.cpp:369-385, camera_model.cpp:87-94,119-160,280-289).
-// Kept out of line so that its FP64 register appetite does not set the register budget of the
-// ray loop.
-__device__ __noinline__ void build_yaw_frame(const double* __restrict__ A, const double* __restrict__ B,
-                                             const float* __restrict__ cs, double vs_inv, double* s_pl, double* s_rd,
-                                             float* s_st, float* s_csf, int* s_um, unsigned* s_cnt, float* s_fp, float* s_sl,
-                                             double vs, int g0x, int g0y, int g0z, int yc, int j, double px, double py,
-                                             double pz) {
-  // A, B, cs already point at this yaw's table rows
-  const D3 p{px, py, pz};
-  const D3 t = d3add(p, D3{B[0], B[1], B[2]});  // camera position
-  D3 c[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) c[k] = d3add(D3{A[3 * k], A[3 * k + 1], A[3 * k + 2]}, t);
-  store_plane(s_pl, yc, j, 0, c[0], c[2], c[1]);  // near
-  store_plane(s_pl, yc, j, 1, c[4], c[5], c[6]);  // far
-  store_plane(s_pl, yc, j, 2, c[3], c[6], c[2]);  // left
-  store_plane(s_pl, yc, j, 3, c[0], c[5], c[4]);  // right
-  store_plane(s_pl, yc, j, 4, c[3], c[4], c[7]);  // top
-  store_plane(s_pl, yc, j, 5, c[2], c[6], c[5]);  // bottom
-  const D3 ud = d3sub(c[4], c[5]);                 // rrt.cpp:382
-  const D3 us = d3normalized(ud);                  // :383
+// CTA prologue, part (b): per-yaw frames (rrt.cpp:369-385, camera_model.cpp:87-94,119-160,280-289), one
+// thread per (yaw, plane) plus one per yaw for the ray column, so that the FP64 dependency chains of a
+// chunk's 40 yaws run side by side on all warps instead of on two.  Kept out of line so that their FP64
+// register appetite does not set the register budget of the ray loop.
+//
+// Plane k of a yaw: Plane::setFromPoints(c[i1], c[i2], c[i3]) with the corner triples of
+// CameraModel::calculateBoundingPlanes (near 0,2,1; far 4,5,6; left 3,6,2; right 0,5,4; top 3,4,7;
+// bottom 2,6,5), c[i] = A[i] + (p + B).
+__device__ __noinline__ void build_yaw_plane(const double* __restrict__ A, const double* __restrict__ B, int k, double* s_pl,
+                                             float* s_fp, float* s_sl, double vs, int g0x, int g0y, int g0z, int yc, int j,
+                                             double px, double py, double pz) {
+  const D3 t = d3add(D3{px, py, pz}, D3{B[0], B[1], B[2]});  // camera position
+  const int i1 = (0x230340 >> (4 * k)) & 15, i2 = (0x645652 >> (4 * k)) & 15, i3 = (0x574261 >> (4 * k)) & 15;
+  const D3 p1 = d3add(D3{A[3 * i1], A[3 * i1 + 1], A[3 * i1 + 2]}, t);
+  const D3 p2 = d3add(D3{A[3 * i2], A[3 * i2 + 1], A[3 * i2 + 2]}, t);
+  const D3 p3 = d3add(D3{A[3 * i3], A[3 * i3 + 1], A[3 * i3 + 2]}, t);
+  // Plane::setFromPoints (camera_model.cpp:5-11)
+  const D3 n = d3normalized(d3cross(d3sub(p2, p1), d3sub(p3, p1)));
+  const double d = d3dot(n, p1);
+  s_pl[(4 * k + 0) * yc + j] = n.x;
+  s_pl[(4 * k + 1) * yc + j] = n.y;
+  s_pl[(4 * k + 2) * yc + j] = n.z;
+  s_pl[(4 * k + 3) * yc + j] = d;
+  // Single-precision copies of the far (1), top (4) and bottom (5) planes for the one-plane tests:
+  // s(g) = n.(g*vs) - d = sum_k (n_k*vs)*(g_k - g0_k) + (n.(g0*vs) - d); |error| ~ 3e-6 m << margin.
+  if (k == 1 || k >= 4) {
+    const int q = k == 1 ? 0 : k - 3;
+    s_fp[(4 * q + 0) * yc + j] = __double2float_rn(n.x * vs);
+    s_fp[(4 * q + 1) * yc + j] = __double2float_rn(n.y * vs);
+    s_fp[(4 * q + 2) * yc + j] = __double2float_rn(n.z * vs);
+    s_fp[(4 * q + 3) * yc + j] = __double2float_rn((n.x * (double)g0x + n.y * (double)g0y + n.z * (double)g0z) * vs - d);
+  }
+  // Corner slack: the tested point is the MIN corner of the voxel that contains the ray point X
+  // (g <= X/vs <= g+1), so n.(g*vs) >= n.X - vs * sum_i max(n_i, 0); rounded up.
+  const double sx = fmax(n.x, 0.0), sy = fmax(n.y, 0.0), sz = fmax(n.z, 0.0);
+  s_sl[k * yc + j] = __double2float_ru((sx + sy + sz) * vs * 1.001);
+}
+
+// Ray column of a yaw (rrt.cpp:382-385,408-409, camera_model.cpp:280-289) and the per-yaw counters.
+__device__ __noinline__ void build_yaw_rays(const double* __restrict__ A, const double* __restrict__ B,
+                                            const float* __restrict__ cs, double vs_inv, double* s_rd, float* s_st,
+                                            float* s_csf, int* s_um, unsigned* s_cnt, int yc, int j, double px, double py,
+                                            double pz) {
+  const D3 t = d3add(D3{px, py, pz}, D3{B[0], B[1], B[2]});  // camera position
+  const D3 c4 = d3add(D3{A[12], A[13], A[14]}, t), c5 = d3add(D3{A[15], A[16], A[17]}, t), c6 = d3add(D3{A[18], A[19], A[20]}, t);
+  const D3 ud = d3sub(c4, c5);                                         // rrt.cpp:382
+  const D3 us = d3normalized(ud);                                      // :383
   const int um = (int)ceil(dmul(__dsqrt_rn(d3dot(ud, ud)), vs_inv));  // :384
-  const D3 d21 = d3sub(c[6], c[5]);
+  const D3 d21 = d3sub(c6, c5);
   const D3 vc{__ddiv_rn(d21.x, 2.0), __ddiv_rn(d21.y, 2.0), __ddiv_rn(d21.z, 2.0)};  // :385
-  s_rd[0 * yc + j] = c[5].x; s_rd[1 * yc + j] = c[5].y; s_rd[2 * yc + j] = c[5].z;
-  s_rd[3 * yc + j] = us.x;   s_rd[4 * yc + j] = us.y;   s_rd[5 * yc + j] = us.z;
-  s_rd[6 * yc + j] = vc.x;   s_rd[7 * yc + j] = vc.y;   s_rd[8 * yc + j] = vc.z;
+  s_rd[0 * yc + j] = c5.x; s_rd[1 * yc + j] = c5.y; s_rd[2 * yc + j] = c5.z;
+  s_rd[3 * yc + j] = us.x; s_rd[4 * yc + j] = us.y; s_rd[5 * yc + j] = us.z;
+  s_rd[6 * yc + j] = vc.x; s_rd[7 * yc + j] = vc.y; s_rd[8 * yc + j] = vc.z;
   s_st[0 * yc + j] = __double2float_rn(dmul(t.x, vs_inv));  // :408-409
   s_st[1 * yc + j] = __double2float_rn(dmul(t.y, vs_inv));
   s_st[2 * yc + j] = __double2float_rn(dmul(t.z, vs_inv));
@@ -179,24 +195,6 @@ __device__ __noinline__ void build_yaw_frame(const double* __restrict__ A, const
   s_csf[1 * yc + j] = cs[1];
   s_um[j] = um;
   s_cnt[0 * yc + j] = 0u; s_cnt[1 * yc + j] = 0u; s_cnt[2 * yc + j] = 0u;
-  // Single-precision copies of the far (1), top (4) and bottom (5) planes for the one-plane tests:
-  // s(g) = n.(g*vs) - d = sum_k (n_k*vs)*(g_k - g0_k) + (n.(g0*vs) - d); |error| ~ 3e-6 m << margin.
-  const int kp[3] = {1, 4, 5};
-#pragma unroll
-  for (int q = 0; q < 3; ++q) {
-    const double nx = s_pl[(4 * kp[q] + 0) * yc + j], ny = s_pl[(4 * kp[q] + 1) * yc + j], nz = s_pl[(4 * kp[q] + 2) * yc + j];
-    s_fp[(4 * q + 0) * yc + j] = __double2float_rn(nx * vs);
-    s_fp[(4 * q + 1) * yc + j] = __double2float_rn(ny * vs);
-    s_fp[(4 * q + 2) * yc + j] = __double2float_rn(nz * vs);
-    s_fp[(4 * q + 3) * yc + j] = __double2float_rn((nx * (double)g0x + ny * (double)g0y + nz * (double)g0z) * vs - s_pl[(4 * kp[q] + 3) * yc + j]);
-  }
-  // Corner slack per plane: the tested point is the MIN corner of the voxel that contains the ray
-  // point X (g <= X/vs <= g+1), so n.(g*vs) >= n.X - vs * sum_i max(n_i, 0); rounded up.
-#pragma unroll
-  for (int k = 0; k < 6; ++k) {
-    const double sx = fmax(s_pl[(4 * k + 0) * yc + j], 0.0), sy = fmax(s_pl[(4 * k + 1) * yc + j], 0.0), sz = fmax(s_pl[(4 * k + 2) * yc + j], 0.0);
-    s_sl[k * yc + j] = __double2float_ru((sx + sy + sz) * vs * 1.001);
-  }
 }
 
 // Camera-frame coordinates of a point given as (float) voxel offsets from g0 (classifier math).
@@ -343,7 +341,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   const int gn = (MODE == kProbe) ? 0 : a.gnx * a.gny * a.gnz;
   uint32_t* const vol = reinterpret_cast<uint32_t*>(smem_raw);
   const GainSmem S = carve(smem_raw + (kIsDense ? (((size_t)a.vwords * 4 + 15) & ~(size_t)15) : 0), yc, gn);
-  __shared__ int s_umax;
+  __shared__ int s_umax, s_next;
   __shared__ unsigned long long s_steps;
   __shared__ unsigned int s_mismatch;
   __shared__ uint32_t s_outm[kMaxDenseWordsX];
@@ -363,6 +361,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
                    (a.valid != nullptr && a.valid[v] == 0);
   if (tid == 0) {
     s_umax = 0;
+    s_next = 0;
     s_steps = 0ull;
     s_mismatch = 0u;
   }
@@ -396,10 +395,13 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     }
     s_outm[tid] = om;
   }
-  for (int j = tid; j < yc; j += blockDim.x) {
+  for (int i = tid; i < 6 * yc; i += blockDim.x) {
+    const int k = i / yc, j = i - k * yc, y = chunk * yc + j;
+    build_yaw_plane(a.A + (size_t)y * 24, a.B + 3 * y, k, S.pl, S.fp, S.sl, a.vs, g0x, g0y, g0z, yc, j, px, py, pz);
+  }
+  for (int j = (int)blockDim.x - 1 - tid; j < yc; j += blockDim.x) {  // from the far end: those warps have less plane work
     const int y = chunk * yc + j;
-    build_yaw_frame(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.pl, S.rd, S.st, S.csf, S.um, S.cnt, S.fp, S.sl, a.vs,
-                    g0x, g0y, g0z, yc, j, px, py, pz);
+    build_yaw_rays(a.A + (size_t)y * 24, a.B + 3 * y, a.cs + 2 * y, a.vs_inv, S.rd, S.st, S.csf, S.um, S.cnt, yc, j, px, py, pz);
   }
   __syncthreads();
   for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
@@ -425,23 +427,35 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       const int ix0 = (x0 >> 4) - b0x;
       const int* const grow = S.grid + (iz * a.gny + iy) * a.gnx;
       uint32_t* const vrow = vol + row * vxw;
-      for (int wx = 0; wx < vxw; ++wx) {
-        const uint32_t om = s_outm[wx];  // voxels of this word outside the exploration box along x
-        uint32_t word = 0xAAAAAAAAu;     // 16 x "skip"
-        if (row_in && om != 0xFFFFFFFFu) {
-          const int ix = ix0 + wx;
-          int slot;
-          if (row_grid && (unsigned)ix < (unsigned)a.gnx) {
-            slot = grow[ix];
-          } else {
-            slot = probe_block(a.L, (x0 >> 4) + wx, gy >> 4, gz >> 4);
-            if (slot < 0) slot = a.unknown_slot;
+      // four words at a time: the status-tile loads of a group are issued before any is used
+      for (int wx0 = 0; wx0 < vxw; wx0 += 4) {
+        uint32_t om[4], word[4];
+        bool use[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int wx = wx0 + q;
+          om[q] = wx < vxw ? s_outm[wx] : 0xFFFFFFFFu;  // voxels of this word outside the exploration box along x
+          use[q] = row_in && om[q] != 0xFFFFFFFFu;
+          word[q] = 0u;
+          if (use[q]) {
+            const int ix = ix0 + wx;
+            int slot;
+            if (row_grid && (unsigned)ix < (unsigned)a.gnx) {
+              slot = grow[ix];
+            } else {
+              slot = probe_block(a.L, (x0 >> 4) + wx, gy >> 4, gz >> 4);
+              if (slot < 0) slot = a.unknown_slot;
+            }
+            word[q] = __ldg(a.L.status + ((unsigned)slot * 256u + rowoff));
           }
-          word = __ldg(a.L.status + ((unsigned)slot * 256u + rowoff));
-          word |= (word >> 1) & 0x55555555u;  // tile status 2 (occupied) -> code 3
-          word = (word & ~om) | (om & 0xAAAAAAAAu);
         }
-        vrow[wx] = word;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint32_t w = word[q];
+          w |= (w >> 1) & 0x55555555u;  // tile status 2 (occupied) -> code 3
+          w = use[q] ? ((w & ~om[q]) | (om[q] & 0xAAAAAAAAu)) : 0xAAAAAAAAu;  // "skip" outside the box
+          if (wx0 + q < vxw) vrow[wx0 + q] = w;
+        }
       }
       ry += dy;
       rz += dz;
@@ -462,11 +476,17 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   uint32_t vol_s = (uint32_t)__cvta_generic_to_shared(vol);
   asm volatile("mov.u32 %0, %0;" : "+r"(vol_s));  // opaque: keep the shared-window address in a register
 
-  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int lane = tid & 31;
   unsigned long long my_steps = 0ull;
   unsigned int my_mismatch = 0u;
 
-  for (int base = warp * 32; base < n_rays; base += nwarps * 32) {
+  // Batches of 32 rays are handed out dynamically (rows differ in ray length by up to 2x, and 8 warps rarely
+  // divide the batch count): a warp takes the next batch when it is done with its last.
+  for (;;) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&s_next, 32);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= n_rays) break;
     const int r = base + lane;
     const int u = r / yc;
     const int j = r - u * yc;
