@@ -487,7 +487,9 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     if (lane == 0) base = atomicAdd(&s_next, 32);
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= n_rays) break;
-    const int r = base + lane;
+    // top rows first: with a floor-bounded exploration box the downward rows leave the box early, so the
+    // short batches come last and the warps of a CTA finish closer together (order only; any order is exact)
+    const int r = (((n_rays + 31) >> 5) << 5) - 32 - base + lane;
     const int u = r / yc;
     const int j = r - u * yc;
     // The batch loop is warp-uniform; lanes without a ray (tail of the last batch, rows beyond this yaw's
