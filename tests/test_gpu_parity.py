@@ -110,6 +110,52 @@ def test_axis_aligned_and_grid_aligned_positions(oracle_mod, tiny_map):
     g.close()
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 4])
+@pytest.mark.parametrize("state", ["unknown", "free", "occupied"])
+def test_rays_stuck_at_yaw_plus_minus_90(oracle_mod, state, variant):
+    """Integer yaws +-90 deg give rays with no x component: the reference's RayCaster divides by that zero
+    (t = -inf or 0/0, dt = 0/0), minCoeff then picks the axis for ever and the SAME voxel -- the one under the
+    camera -- is emitted len + 1 times (integrator_utils.cc:119-123,165-179).  The kernel evaluates that in
+    closed form.  Here that voxel is unknown / free / occupied; its min corner lies inside the frustum for
+    yaw -90 (camera near the +y face of the voxel, looking along -y) and behind the camera for yaw +90."""
+    from nbv_exploration_planner_b200 import LAYER_TSDF, NbvGpu
+    from nbv_exploration_planner_b200.planner import CameraParams
+    vs, vps = 0.2, 16
+    cam = CameraParams(hfov_deg=90, vfov_deg=60, near_m=0.01, far_m=2.0, bbx_min=(-4, -4, -4), bbx_max=(8, 8, 8))  # identity T_C_B
+    keys = np.array([[0, 0, 0]], np.int32)
+    tsdf = np.zeros((1, vps ** 3, 2), np.float32)  # weight 0: unknown
+    lin = 5 + 5 * vps + 5 * vps * vps
+    if state == "free":
+        tsdf[0, lin] = (0.4, 1.0)
+    elif state == "occupied":
+        tsdf[0, lin] = (-0.05, 1.0)
+    pos = np.array([[(5 + 0.02) * vs, (5 + 0.9) * vs, (5 + 0.03) * vs]])
+    o = oracle_mod.Oracle()
+    lt_o = o.layer_create(0, vs, vps)
+    o.layer_update(lt_o, keys, tsdf)
+    o.set_camera(cam.as_dict())
+    g = NbvGpu(0)
+    lt_g = g.layer_create(LAYER_TSDF, vs, vps, 8)
+    g.layer_update(lt_g, keys, tsdf)
+    g.commit()
+    g.set_camera(cam)
+    g.set_kernel_variant(variant)
+    ro, rg = _compare_gain(o, lt_o, g, lt_g, pos)
+    if variant == 2:
+        assert g.classifier_mismatches() == 0
+    # the signature of a stuck ray, so that the test cannot pass without exercising it
+    looking_minus_y, looking_plus_y = ro["per_yaw"][0, 90], ro["per_yaw"][0, 270]
+    assert tuple(looking_plus_y) == (0, 0, 0)            # the voxel's corner is behind the camera: skipped every time
+    u_max = int(ro["rays"][0]) // 360
+    if state == "unknown":
+        assert looking_minus_y[0] > u_max and looking_minus_y[1] == 0 and looking_minus_y[2] == 0
+    elif state == "free":
+        assert looking_minus_y[0] == 0 and looking_minus_y[1] > u_max and looking_minus_y[2] == 0
+    else:
+        assert tuple(looking_minus_y) == (0, 0, u_max)   # every ray of the column stops on its first voxel
+    g.close()
+
+
 @pytest.mark.parametrize("variant", [0, 2, 3])
 def test_very_long_range_uses_global_probes(oracle_mod, tiny_map, variant):
     """A reach too large for the shared-memory slot grid (60 m range on 0.2 m voxels: 346 ray rows,

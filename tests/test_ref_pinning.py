@@ -113,6 +113,43 @@ def test_gain_matches_reference_other_geometry(tiny_map):
     assert np.array_equal(ro["gain"], rr["gain"]) and np.array_equal(ro["yaw"], rr["yaw"])
 
 
+@pytest.mark.parametrize("sum_all", [0, 1])
+@pytest.mark.parametrize("state", ["unknown", "free", "occupied"])
+def test_rays_stuck_at_yaw_plus_minus_90_match_reference(state, sum_all):
+    """At the integer yaws +-90 deg the ray has no x component; the reference's RayCaster then emits the voxel
+    under the camera len + 1 times (integrator_utils.cc:119-123,165-179: t = -inf or 0/0, dt = 0/0, minCoeff
+    picks that axis for ever).  The reference only returns gain and yaw, so the repeated voxel is pinned
+    through totals: exactly representable weights make an unknown / free / occupied start voxel show up in the
+    gain of both RrtTree::gain (all-yaw sum) and RrtTree::optimized_gain (best window)."""
+    from nbv_exploration_planner_b200.planner import CameraParams
+    vs, vps = 0.2, 16
+    cam = CameraParams(hfov_deg=90, vfov_deg=60, near_m=0.01, far_m=2.0, bbx_min=(-4, -4, -4), bbx_max=(8, 8, 8),
+                       gain_free=0.25, gain_occupied=0.5, gain_unmapped=1.0, sum_all_yaws=sum_all)  # identity T_C_B
+    keys = np.array([[0, 0, 0]], np.int32)
+    tsdf = np.zeros((1, vps ** 3, 2), np.float32)
+    lin = 5 + 5 * vps + 5 * vps * vps
+    if state == "free":
+        tsdf[0, lin] = (0.4, 1.0)
+    elif state == "occupied":
+        tsdf[0, lin] = (-0.05, 1.0)
+    # camera near the +y face of voxel (5,5,5): its min corner is in view looking along -y, behind the camera along +y
+    pos = np.array([[(5 + 0.02) * vs, (5 + 0.9) * vs, (5 + 0.03) * vs], [(5 + 0.5) * vs, (5 + 0.5) * vs, (5 + 0.5) * vs]])
+    o = ob.Oracle()
+    lt = o.layer_create(0, vs, vps)
+    o.layer_update(lt, keys, tsdf)
+    o.set_camera(cam.as_dict())
+    r = rb.Reference(vs, vps)
+    r.tsdf_update(keys, tsdf)
+    r.set_camera(cam.as_dict(), 0.4)
+    ro, rr = o.gain_eval(lt, pos, per_yaw=True, threads=2), r.gain_eval(pos)
+    assert np.array_equal(ro["gain"], rr["gain"]) and np.array_equal(ro["yaw"], rr["yaw"])
+    # and the oracle's own per-yaw view of it: the voxel is counted once per step of every ray of the column
+    u_max = int(ro["rays"][0]) // 360
+    want = {"unknown": 0, "free": 1, "occupied": 2}[state]
+    col = ro["per_yaw"][0, 90]
+    assert col[want] >= u_max and col.sum() == col[want] and tuple(ro["per_yaw"][0, 270]) == (0, 0, 0)
+
+
 def test_check_motion_and_voxel_status_match_reference(tiny_map):
     """HighResManager::checkMotion (voxblox_manager.h:89-108, .cpp:121-129) and getVoxelStatusByIndex (:14-33)."""
     from nbv_exploration_planner_b200 import synth
