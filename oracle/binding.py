@@ -193,6 +193,24 @@ class Oracle:
                                _ptr(cam, C.c_double), _ptr(pp, C.c_double), C.byref(um))
         return {"planes": planes, "cam": cam, "pp": pp, "u_max": um.value}
 
+    def frontier_potential(self, layer: int, points, max_distance: float = 6.0, threads: int = 1) -> dict:
+        """History::bfs (history.cpp:103-137) per vertex: potential gain, frontier-voxel count, visited cells."""
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+        n = len(pts)
+        gain = np.zeros(n); fv = np.zeros(n, np.uint64); vis = np.zeros(n, np.uint64)
+        self._l.nbvo_frontier_potential.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_double), C.c_double,
+                                                    C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+        rc = self._l.nbvo_frontier_potential(self._c, layer, n, _ptr(pts, C.c_double), float(max_distance), _ptr(gain, C.c_double),
+                                             _ptr(fv, C.c_uint64), _ptr(vis, C.c_uint64), threads)
+        if rc != 0:
+            raise RuntimeError(f"nbvo_frontier_potential -> {rc}")
+        return {"gain": gain, "frontier_voxels": fv, "visited": vis}
+
+    def voxel_status_at(self, layer: int, p) -> int:
+        p = np.ascontiguousarray(p, np.float64)
+        self._l.nbvo_voxel_status_at.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        return self._l.nbvo_voxel_status_at(self._c, layer, _ptr(p, C.c_double))
+
     def voxel_status(self, layer: int, g) -> int:
         g = np.ascontiguousarray(g, np.int64)
         return self._l.nbvo_voxel_status(self._c, layer, _ptr(g, C.c_int64))

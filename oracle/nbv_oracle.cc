@@ -33,6 +33,10 @@
 // algorithms are restated here.
 
 #include <algorithm>
+#include <cstdio>
+#include <queue>
+#include <string>
+#include <unordered_set>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
@@ -563,6 +567,89 @@ int nbvo_check_segments(void* c_, int layer, double radius, size_t n, const doub
     if (steps) steps[i] = st;
   });
   return 0;
+}
+
+// LowResManager::getVoxelStatus(position) -- voxblox_manager.cpp:73-90: the position is cast to float, the
+// block comes from Layer::computeBlockIndexFromCoordinates (layer.h:128-131: getGridIndexFromPoint with
+// block_size_inv), the voxel from Block::computeTruncatedVoxelIndexFromCoordinates (block_inl.h:30-40:
+// getGridIndexFromPoint(coords - origin, voxel_size_inv) clamped to the block), origin = float(index) *
+// block_size (common.h:196-201, layer.h:137).  All in float, as the reference.
+inline Status voxel_status_at(const Layer& L, const V3& position) {
+  const float block_size = (float)L.vps * L.voxel_size;  // layer.h:32  block_size_ = voxel_size_ * voxels_per_side_
+  const float block_size_inv = 1.0f / block_size;
+  const float voxel_size_inv = 1.0f / L.voxel_size;
+  const float pf[3] = {(float)position.x, (float)position.y, (float)position.z};
+  int b[3], l[3];
+  for (int k = 0; k < 3; ++k) {
+    b[k] = (int)grid_index(pf[k], block_size_inv);
+    const float origin = (float)b[k] * block_size;
+    const int64_t v = grid_index(pf[k] - origin, voxel_size_inv);
+    l[k] = (int)std::max<int64_t>(std::min<int64_t>(v, L.vps - 1), 0);
+  }
+  return voxel_status(L, Key{b[0], b[1], b[2]}, l[0], l[1], l[2]);
+}
+
+// History::bfs -- history.cpp:96-137, literally: cells are identified by std::to_string (= "%f", six
+// decimals) of their ACCUMULATED double coordinates, kept in FIFO order; a neighbour that is not yet
+// visited, within max_distance (6.0 in the reference) of the start and inside the exploration bounds is
+// looked up by coordinates: free -> visited + queued, unknown -> counted (once per encounter, i.e. per
+// free-cell face), occupied -> nothing.  The start point is expanded whatever its own status.
+inline std::string bfs_key(const V3& v) {
+  char buf[3 * 400];  // "%f" of a double has at most 1 + 309 + 1 + 6 characters
+  std::snprintf(buf, sizeof buf, "%f/%f/%f", v.x, v.y, v.z);
+  return std::string(buf);
+}
+inline uint64_t frontier_bfs(const Ctx* c, const Layer& L, const V3& point, double max_distance, uint64_t* visited_out) {
+  const double vs = (double)L.voxel_size;  // getResolution(): the float voxel size widened (voxblox_manager.h:35)
+  const V3 conn[6] = {{vs, 0, 0}, {-vs, 0, 0}, {0, vs, 0}, {0, -vs, 0}, {0, 0, vs}, {0, 0, -vs}};
+  std::unordered_set<std::string> visited;
+  visited.insert(bfs_key(point));
+  std::queue<V3> queue;
+  queue.push(point);
+  uint64_t frontier = 0;
+  while (!queue.empty()) {
+    const V3 cur = queue.front();
+    queue.pop();
+    for (const V3& d : conn) {
+      const V3 cand = add(cur, d);
+      if (visited.find(bfs_key(cand)) != visited.end()) continue;
+      if (!(norm(sub(cand, point)) <= max_distance)) continue;
+      if (!(cand.x >= c->cam.bbx_min[0] && cand.x <= c->cam.bbx_max[0] && cand.y >= c->cam.bbx_min[1] &&
+            cand.y <= c->cam.bbx_max[1] && cand.z >= c->cam.bbx_min[2] && cand.z <= c->cam.bbx_max[2]))
+        continue;  // nbveplanner/common.h:22-31
+      const Status st = voxel_status_at(L, cand);
+      if (st == kFree) {
+        visited.insert(bfs_key(cand));
+        queue.push(cand);
+      } else if (st == kUnknown) {
+        ++frontier;
+      }
+    }
+  }
+  if (visited_out) *visited_out = visited.size();
+  return frontier;
+}
+
+// History::recalculatePotential's input: potential_gain = frontierVoxels * pow(voxel_size, 3.0) per vertex.
+int nbvo_frontier_potential(void* c_, int layer, size_t n, const double* points, double max_distance, double* gain,
+                            uint64_t* frontier_voxels /*[n] or null*/, uint64_t* visited /*[n] or null*/, int n_threads) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  if (!c->cam_set) return -2;
+  const Layer& L = *c->layers.at(layer);
+  if (L.kind != 0) return -3;
+  const double cube = std::pow((double)L.voxel_size, 3.0);
+  parallel_for(n, n_threads, [&](size_t i) {
+    uint64_t vis = 0;
+    const uint64_t f = frontier_bfs(c, L, V3{points[3 * i], points[3 * i + 1], points[3 * i + 2]}, max_distance, &vis);
+    gain[i] = (double)(int)f * cube;  // int frontierVoxels * pow(...) (history.cpp:136)
+    if (frontier_voxels) frontier_voxels[i] = f;
+    if (visited) visited[i] = vis;
+  });
+  return 0;
+}
+int nbvo_voxel_status_at(void* c_, int layer, const double* p) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  return voxel_status_at(*c->layers.at(layer), V3{p[0], p[1], p[2]});
 }
 
 // Batched restatement of the body of RrtTree::iterate (rrt.cpp:172-246) for given uniform triples:

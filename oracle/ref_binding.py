@@ -135,6 +135,20 @@ class Reference:
         self.L.nbvr_yaw_frame(self._c, _p(pos, C.c_double), yaw_deg, _p(planes, C.c_double), _p(cam, C.c_double), _p(pp, C.c_double))
         return {"planes": planes, "cam": cam, "pp": pp}
 
+    def frontier_potential(self, points):
+        """The reference's own History::bfs (history.cpp:103-137; 6.0 m hard-coded there)."""
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+        gain = np.zeros(len(pts))
+        self.L.nbvr_frontier_potential.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        self.L.nbvr_frontier_potential.restype = None
+        self.L.nbvr_frontier_potential(self._c, len(pts), _p(pts, C.c_double), _p(gain, C.c_double))
+        return gain
+
+    def voxel_status_at(self, p) -> int:
+        p = np.ascontiguousarray(p, np.float64)
+        self.L.nbvr_voxel_status_at.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        return self.L.nbvr_voxel_status_at(self._c, _p(p, C.c_double))
+
     def voxel_status(self, block, voxel) -> int:
         b = np.ascontiguousarray(block, np.int32); v = np.ascontiguousarray(voxel, np.int32)
         return self.L.nbvr_voxel_status(self._c, _p(b, C.c_int32), _p(v, C.c_int32))

@@ -18,3 +18,5 @@ cut nbveplanner/src/voxblox_manager.cpp 14 33 voxblox_manager_cpp_14_33.inc 'Vox
 cut nbveplanner/src/voxblox_manager.cpp 121 129 voxblox_manager_cpp_121_129.inc 'bool HighResManager::checkCollisionWithRobotAtVoxel('
 cut nbveplanner/include/nbveplanner/voxblox_manager.h 35 37 voxblox_manager_h_35_37.inc 'double getResolution() const'
 cut nbveplanner/include/nbveplanner/voxblox_manager.h 89 108 voxblox_manager_h_89_108.inc 'template <typename T>'
+cut nbveplanner/src/voxblox_manager.cpp 73 90 voxblox_manager_cpp_73_90.inc 'VoxelStatus LowResManager::getVoxelStatus(const Point &position) const {'
+cut nbveplanner/src/history.cpp 96 137 history_cpp_96_137.inc 'std::string convertToString(const Eigen::Vector3d &vec) {'

@@ -14,7 +14,9 @@
 //     those bodies use: RrtTree::optimized_gain (rrt.cpp:351-479), RrtTree::gain (:481-579),
 //     VoxbloxManager::getVoxelStatusByIndex (voxblox_manager.cpp:14-33),
 //     HighResManager::checkCollisionWithRobotAtVoxel (:121-129), getResolution / getVoxelsPerSide
-//     (voxblox_manager.h:35-37), HighResManager::checkMotion<T> (voxblox_manager.h:89-108);
+//     (voxblox_manager.h:35-37), HighResManager::checkMotion<T> (voxblox_manager.h:89-108),
+//     LowResManager::getVoxelStatus (voxblox_manager.cpp:73-90), convertToString + History::bfs
+//     (history.cpp:96-137);
 //   * NOT the reference's: the third-party headers it needs (Eigen, minkindr, glog, protoc output) --
 //     stand-ins under oracle/ref_shim/ restating their published semantics -- and this C glue.
 // Nothing from /root/reference is copied into the repository.
@@ -22,6 +24,11 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
+#include <queue>
+#include <sstream>
+#include <string>
+#include <unordered_set>
+#include <vector>
 
 #include "nbveplanner/camera_model.h"
 #include "voxblox/core/layer.h"
@@ -39,6 +46,7 @@ struct Params {  // the members of nbveplanner/params.h that the extracted bodie
   double camera_hfov_ = 90.0;
   double gain_free_ = 0.0, gain_occupied_ = 0.0, gain_unmapped_ = 1.0;
   double robot_radius_ = 0.5;
+  Point bbx_min_, bbx_max_;  // params.h: the exploration bounds History::bfs tests against
 };
 
 class VoxbloxManager {
@@ -57,6 +65,18 @@ class HighResManager : public VoxbloxManager {
   voxblox::Layer<voxblox::EsdfVoxel>* esdf_layer_ = nullptr;
 };
 
+class LowResManager : public VoxbloxManager {
+ public:
+  VoxelStatus getVoxelStatus(const Point& position) const;
+};
+
+class History {
+ public:
+  double bfs(const Eigen::Vector3d& point);
+  LowResManager* manager_lowres_ = nullptr;
+  Params* params_ = nullptr;
+};
+
 class RrtTree {
  public:
   double optimized_gain(Pose& state);
@@ -69,6 +89,8 @@ class RrtTree {
 #include "extract/voxblox_manager_cpp_121_129.inc"
 #include "extract/rrt_cpp_351_479.inc"
 #include "extract/rrt_cpp_481_579.inc"
+#include "extract/voxblox_manager_cpp_73_90.inc"
+#include "extract/history_cpp_96_137.inc"
 
 }  // namespace nbveplanner
 
@@ -78,7 +100,8 @@ struct RefCtx {
   std::unique_ptr<voxblox::Layer<voxblox::EsdfVoxel>> esdf;
   std::unique_ptr<voxblox::Layer<voxblox::TsdfVoxel>> hires_tsdf;
   nbveplanner::Params params;
-  nbveplanner::VoxbloxManager low;
+  nbveplanner::LowResManager low;
+  nbveplanner::History history;
   nbveplanner::HighResManager high;
   nbveplanner::RrtTree tree;
 };
@@ -101,6 +124,8 @@ void* nbvr_create(float tsdf_voxel_size, int tsdf_vps, float esdf_voxel_size, in
   c->high.tsdf_layer_ = c->hires_tsdf.get();
   c->tree.manager_lowres_ = &c->low;
   c->tree.params_ = &c->params;
+  c->history.manager_lowres_ = &c->low;
+  c->history.params_ = &c->params;
   return c;
 }
 void nbvr_destroy(void* c_) {
@@ -144,6 +169,8 @@ void nbvr_set_camera(void* c_, double hfov, double vfov, double near_m, double f
   p.camera_model_.setIntrinsicsFromFoV(hfov, vfov, near_m, far_m);
   nbveplanner::Point lo(bbx_min[0], bbx_min[1], bbx_min[2]), hi(bbx_max[0], bbx_max[1], bbx_max[2]);
   p.camera_model_.setBoundingBox(lo, hi);
+  p.bbx_min_ = lo;  // the same Params::bbx_min_/bbx_max_ that nbvep.cpp:45 hands to the camera model
+  p.bbx_max_ = hi;
   const nbveplanner::Transformation T_C_B(nbveplanner::Point(t_CB[0], t_CB[1], t_CB[2]),
                                           Eigen::Quaterniond(q_CB_wxyz[0], q_CB_wxyz[1], q_CB_wxyz[2], q_CB_wxyz[3]));
   p.camera_model_.setExtrinsics(T_C_B);
@@ -213,4 +240,14 @@ int nbvr_voxel_status(void* c_, const int32_t* block, const int32_t* voxel) {
   return s == nbveplanner::kUnknown ? 0 : (s == nbveplanner::kFree ? 1 : 2);
 }
 
+// History::bfs (history.cpp:103-137) for each vertex position; the reference hard-codes 6.0 m.
+void nbvr_frontier_potential(void* c_, size_t n, const double* points, double* gain) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  for (size_t i = 0; i < n; ++i) gain[i] = c->history.bfs(Eigen::Vector3d(points[3 * i], points[3 * i + 1], points[3 * i + 2]));
+}
+// LowResManager::getVoxelStatus (voxblox_manager.cpp:73-90); oracle codes: 0 unknown, 1 free, 2 occupied
+int nbvr_voxel_status_at(void* c_, const double* p) {
+  const nbveplanner::VoxelStatus s = static_cast<RefCtx*>(c_)->low.getVoxelStatus(nbveplanner::Point(p[0], p[1], p[2]));
+  return s == nbveplanner::kUnknown ? 0 : (s == nbveplanner::kFree ? 1 : 2);
+}
 }  // extern "C"

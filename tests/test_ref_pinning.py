@@ -179,3 +179,48 @@ def test_cfg1_golden_subset_against_reference(cfg1_map):
     assert np.array_equal(rr["gain"], g["gain"][sel])
     assert np.array_equal(rr["yaw"], g["yaw_deg"][sel] * np.pi / 180.0)
     assert np.array_equal(r.check_segments(g["segments"]), g["seg_free"])
+
+
+def test_voxel_status_by_coordinates_matches_reference(tiny_map):
+    """LowResManager::getVoxelStatus(position) (voxblox_manager.cpp:73-90): float cast, block by coordinates,
+    truncated voxel index -- on random points, points on voxel / block faces and points outside the map."""
+    cam = tiny_map.camera()
+    o, lt, le, r = _both(tiny_map, cam, 0.4)
+    vs = float(tiny_map.voxel_size)
+    rng = np.random.default_rng(11)
+    pts = np.concatenate([rng.uniform(-2, 10, (3000, 3)),
+                          rng.integers(-10, 50, (1500, 3)) * vs,                      # exactly on voxel faces (as doubles)
+                          rng.integers(-2, 4, (300, 3)) * (16 * vs) + rng.choice([-1e-7, 0.0, 1e-7, 1e-6], (300, 3)),  # block faces
+                          rng.integers(-10, 50, (1500, 3)) * np.float64(np.float32(vs))])  # accumulated-float-step lattice
+    seen = set()
+    for q in pts:
+        a, b = o.voxel_status_at(lt, q), r.voxel_status_at(q)
+        assert a == b, q
+        seen.add(a)
+    assert seen == {0, 1, 2}
+
+
+@pytest.mark.parametrize("which", ["tiny", "quarter"])
+def test_frontier_bfs_matches_reference_history(tiny_map, which):
+    """History::bfs (history.cpp:96-137), verbatim: cells keyed by std::to_string of accumulated doubles, FIFO
+    order, unknown neighbours counted per encounter, 6.0 m radius, exploration bounds.  Vertices in free,
+    unknown and occupied space, near and outside the bounds; `quarter` uses a voxel size of exactly 0.25 m,
+    where 24 steps reach 6.0 m exactly and the `<= 6.0` test sits on accumulated roundings."""
+    from nbv_exploration_planner_b200 import synth
+    if which == "tiny":
+        m, cfg = tiny_map, tiny_map.cfg
+    else:
+        cfg = synth.SynthConfig("quarter", (-3, -2, 0), (9, 10, 3), 0.25, 3.0, 8, "pillars", 91, 92, (3.0, 4.0, 1.0), obs_radius=4.0,
+                                traj_points=4, traj_step=2.5, vicinity=3.0)
+        m = synth.make_map(cfg)
+    cam = m.camera()
+    o, lt, le, r = _both(m, cam, 0.4)
+    c = synth.make_candidates(cfg, 6, None)
+    lo, hi = np.array(cfg.bounds_min, float), np.array(cfg.bounds_max, float)
+    extra = np.array([lo + 0.01, hi - 0.01, lo - 0.5, [lo[0], 0.5 * (lo[1] + hi[1]), 1.0],      # corners, outside, on a face
+                      0.5 * (lo + hi), [cfg.root[0], cfg.root[1], cfg.root[2]], [1.0, 2.0, 0.5], [3.0, 4.0, 1.0]])
+    pts = np.concatenate([c.positions, extra])
+    ro, rr = o.frontier_potential(lt, pts, 6.0, threads=8), r.frontier_potential(pts)
+    assert np.array_equal(ro["gain"], rr), (ro["gain"], rr)
+    assert ro["frontier_voxels"].max() > 100 and ro["visited"].max() > 1000   # the fill really spreads
+
