@@ -10,6 +10,7 @@
  *   RrtTree::gain(Pose&)                  nbveplanner/src/rrt.cpp:481-579   -> same, camera.sum_all_yaws = 1
  *   HighResManager::checkMotion<T>        nbveplanner/include/nbveplanner/voxblox_manager.h:89-108
  *                                                                           -> nbvgpu_check_segments*, nbvgpu_check_motion
+ *   History::bfs(point)                   nbveplanner/src/history.cpp:96-137 -> nbvgpu_frontier_potential
  *   VoxbloxManager::getVoxelStatusByIndex nbveplanner/src/voxblox_manager.cpp:14-33 (map read side)
  *   voxblox::Layer<VoxelType> block hash  voxblox/voxblox/include/voxblox/core/layer.h:23-296,
  *                                         core/block_hash.h:20-31           -> nbvgpu_layer_* (GPU mirror)
@@ -215,6 +216,26 @@ int nbvgpu_check_segments_device(nbvgpu_ctx* ctx, int esdf_layer, double robot_r
 /* n = 1 shim: *free_out = checkMotion(start, end). */
 int nbvgpu_check_motion(nbvgpu_ctx* ctx, int esdf_layer, double robot_radius, const double start[3],
                         const double end[3], int* free_out);
+
+/* ---- history-graph frontier potential ----------------------------------
+ * History::bfs(point) (nbveplanner/src/history.cpp:96-137) as History::recalculatePotential calls it per
+ * vertex (:211-222): 6-connected flood fill from `point` over free cells -- cells being accumulated double
+ * coordinates identified by their std::to_string, FIFO order --, bounded by `max_distance` (the reference
+ * hard-codes 6.0) and by the exploration bounds (Params::bbx_min_/bbx_max_: the camera's bounding box here,
+ * nbvep.cpp:45), status from LowResManager::getVoxelStatus(position) (voxblox_manager.cpp:73-90) on the
+ * TSDF layer.  potential_gain[i] = frontierVoxels * pow(voxel_size, 3.0), frontierVoxels = number of
+ * (visited free cell, unknown neighbour) encounters; visited_cells[i] = size of the reference's `visited` set
+ * at the end (the start included) and cells_checksum[i] = an order-independent sum over those cells of a
+ * 64-bit mix of the bit patterns of their three doubles: diagnostics the reference does not return, used by
+ * the parity tests to show that every cell carries the doubles of the reference's first arrival.  Host
+ * buffers. */
+int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, const double* points /* [n][3] */,
+                              double max_distance, double* potential_gain /* [n] */,
+                              uint64_t* frontier_voxels /* [n] or NULL */, uint64_t* visited_cells /* [n] or NULL */,
+                              uint64_t* cells_checksum /* [n] or NULL */);
+/* Host-only helper for tests: round-half-even of |x| * 10^6, the integer behind "%f" / std::to_string(double),
+ * exactly as the flood fill's cell keys compute it.  NBVGPU_ERR_RANGE for non-finite x or |x| >= 2^21. */
+int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude);
 
 /* ---- introspection ---------------------------------------------------------------------- */
 int nbvgpu_get_stats(nbvgpu_ctx* ctx, nbvgpu_stats* out);

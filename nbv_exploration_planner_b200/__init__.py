@@ -5,7 +5,7 @@
 CPU implementation in this package: constructing ``NbvGpu`` without a B200 raises.
 """
 from ._native import (LAYER_ESDF, LAYER_TSDF, PACK_PLANAR, PACK_VOXBLOX, NbvGpuError, build)
-from .planner import CameraParams, HighResManager, LowResManager, NbvGpu, RrtGain, kFree, kOccupied, kUnknown
+from .planner import CameraParams, HighResManager, History, LowResManager, NbvGpu, RrtGain, kFree, kOccupied, kUnknown
 
-__all__ = ["NbvGpu", "RrtGain", "LowResManager", "HighResManager", "CameraParams", "NbvGpuError", "build",
+__all__ = ["NbvGpu", "RrtGain", "LowResManager", "HighResManager", "History", "CameraParams", "NbvGpuError", "build",
            "LAYER_TSDF", "LAYER_ESDF", "PACK_PLANAR", "PACK_VOXBLOX", "kUnknown", "kFree", "kOccupied"]

@@ -1,0 +1,393 @@
+// frontier_kernels.cuh -- History::bfs (nbveplanner/src/history.cpp:96-137) on the GPU map mirror:
+// the frontier "potential" of a history-graph vertex = number of (visited free cell, unknown neighbour)
+// faces within max_distance (6.0 m in the reference) and inside the exploration bounds, times voxel_size^3.
+//
+// What the reference does, and what therefore has to be reproduced for an identical count:
+//   * cells are NOT voxels: a cell is a triple of ACCUMULATED doubles, new = parent + (+-vs, 0, 0) etc. (all
+//     three components are added, so a -0.0 turns into +0.0), and two cells are the same iff their
+//     std::to_string ("%f": six decimals, correctly rounded, ties to even, "-0.000000" for tiny negatives)
+//     agree on all three coordinates;
+//   * FIFO order with the neighbour order +x -x +y -y +z -z decides which arrival creates a cell and with
+//     which doubles; the later tests (norm <= max_distance, bounds, status) are made on those doubles;
+//   * the status comes from LowResManager::getVoxelStatus(position) (voxblox_manager.cpp:73-90): cast to
+//     float, block by coordinates, voxel by coordinates truncated into the block;
+//   * a free neighbour is inserted and queued, an unknown one is counted -- every time it is met --, the
+//     start point is expanded whatever its own status.
+//
+// Device formulation: one CTA per vertex, level-synchronous.  A level's frontier is an array in FIFO order;
+// its 6 * |frontier| (entry, direction) slots are evaluated in parallel.  The sequential order is kept by
+// construction: a free cell reached by several slots of one level belongs to the smallest slot index
+// (atomicMin on the arrival stamp), the next frontier is written in slot order (block scan), and an
+// unknown neighbour is not counted when a smaller slot of the same level inserted that very key (what the
+// sequential code would have seen as visited).  The string identity is a 64-bit key: lattice index (i, j, k)
+// relative to the start (16 bits each), per axis the difference between the exactly rounded x * 10^6 of the
+// accumulated double and of the canonical fma(i, vs, x0) (3 bits: paths differ by a few ulps, i.e. by at most
+// one unit and only next to a rounding boundary), and per axis the "-0.000000" flag.
+#ifndef NBVGPU_FRONTIER_KERNELS_CUH_
+#define NBVGPU_FRONTIER_KERNELS_CUH_
+
+#include <cstdint>
+#include <cstring>
+
+#include "map_mirror.cuh"
+
+namespace nbvgpu {
+
+// round_half_even(|x| * 10^6), exactly: |x| = m * 2^(e-1075), 10^6 = 15625 * 2^6, so |x| * 10^6 is the 67-bit
+// integer m * 15625 shifted right by 1069 - e.  ~0 for non-finite or |x| >= 2^21 (callers validate).
+__host__ __device__ inline unsigned long long dec6_magnitude(double x) {
+  unsigned long long bits;
+#ifdef __CUDA_ARCH__
+  bits = (unsigned long long)__double_as_longlong(x);
+#else
+  std::memcpy(&bits, &x, sizeof bits);
+#endif
+  const int e = (int)((bits >> 52) & 0x7ffu);
+  if (e == 0) return 0ull;  // zero or subnormal
+  const int sh = 1069 - e;
+  if (e == 0x7ff || sh < 26) return ~0ull;
+  if (sh >= 128) return 0ull;
+  const unsigned long long m = (bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
+  unsigned long long lo, hi;
+#ifdef __CUDA_ARCH__
+  lo = m * 15625ull;
+  hi = __umul64hi(m, 15625ull);
+#else
+  const unsigned __int128 p = (unsigned __int128)m * 15625u;
+  lo = (unsigned long long)p;
+  hi = (unsigned long long)(p >> 64);
+#endif
+  unsigned long long q;
+  bool gt, eq;  // discarded part greater than / equal to one half
+  if (sh < 64) {
+    q = (lo >> sh) | (hi << (64 - sh));
+    const unsigned long long rem = lo & ((1ull << sh) - 1ull), half = 1ull << (sh - 1);
+    gt = rem > half;
+    eq = rem == half;
+  } else if (sh == 64) {
+    q = hi;
+    gt = lo > (1ull << 63);
+    eq = lo == (1ull << 63);
+  } else {
+    const int s2 = sh - 64;  // 1 .. 63
+    q = hi >> s2;
+    const unsigned long long rem_hi = hi & ((1ull << s2) - 1ull), half_hi = 1ull << (s2 - 1);
+    gt = rem_hi > half_hi || (rem_hi == half_hi && lo != 0ull);
+    eq = rem_hi == half_hi && lo == 0ull;
+  }
+  if (gt || (eq && (q & 1ull))) ++q;
+  return q;
+}
+
+struct FrontierEntry {  // one queued cell: the doubles of its first arrival and its key
+  double x, y, z;
+  unsigned long long key;
+};
+struct FrontierCell {  // hash set of visited cells
+  unsigned long long key;      // kFrontierEmpty = free
+  unsigned long long arrival;  // (level << 32) | slot of the arrival that created it; smaller = earlier
+};
+constexpr unsigned long long kFrontierEmpty = ~0ull;
+
+struct FrontierArgs {
+  LayerView L;
+  const double* points;  // [n][3]
+  unsigned long long* frontier_voxels;  // [n]
+  unsigned long long* visited;          // [n] or null
+  unsigned long long* checksum;         // [n] or null: sum of cell_fingerprint over the visited cells
+  int* status;                          // [n]: 0 ok, 1 workspace exhausted, 2 coordinate out of range
+  // workspace of CTA b: cells + b * cell_cap, cur/next + b * frontier_cap, slot_eval + b * 6 * frontier_cap
+  FrontierCell* cells;
+  FrontierEntry* cur;
+  FrontierEntry* next;
+  int* slot_eval;
+  unsigned cell_cap;      // power of two
+  unsigned frontier_cap;
+  double vs;              // float voxel size widened (LowResManager::getResolution)
+  double max_distance;
+  double bmin[3], bmax[3];
+  float block_size, block_size_inv, voxel_size_inv;
+  int vps;
+  int n;
+};
+
+// Order-independent fingerprint of a visited cell (the bit patterns of its three doubles); summed per vertex
+// as a diagnostic: equal sums mean the same doubles in every cell, i.e. the same first arrivals as the
+// sequential code (the oracle computes the same function).
+__device__ __forceinline__ unsigned long long cell_fingerprint(double x, double y, double z) {
+  const unsigned long long b[3] = {(unsigned long long)__double_as_longlong(x), (unsigned long long)__double_as_longlong(y),
+                                   (unsigned long long)__double_as_longlong(z)};
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    h ^= b[k] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 31;
+  }
+  return h;
+}
+
+__device__ __forceinline__ unsigned frontier_hash(unsigned long long k) {
+  k ^= k >> 29;
+  k *= 0xBF58476D1CE4E5B9ull;
+  k ^= k >> 32;
+  return (unsigned)k;
+}
+
+// Key fields.  Lattice index per axis biased by 32768 in bits 16a..16a+15, rounding variant + 4 in bits
+// 48+3a..50+3a, "-0.000000" flag in bit 57+a.
+__device__ __forceinline__ unsigned long long key_axis_fields(int a, int lattice, int variant, bool negzero) {
+  return ((unsigned long long)(unsigned)(lattice + 32768) << (16 * a)) | ((unsigned long long)(unsigned)(variant + 4) << (48 + 3 * a)) |
+         ((unsigned long long)(negzero ? 1u : 0u) << (57 + a));
+}
+__device__ __forceinline__ unsigned long long key_axis_mask(int a) {
+  return (0xFFFFull << (16 * a)) | (7ull << (48 + 3 * a)) | (1ull << (57 + a));
+}
+__device__ __forceinline__ int key_lattice(unsigned long long key, int a) { return (int)((key >> (16 * a)) & 0xFFFFu) - 32768; }
+
+// Fields of one axis for the accumulated coordinate v with lattice index i; false if the variant does not fit
+// (cannot happen for |i| < 2^15 additions; reported, never ignored).
+__device__ __forceinline__ bool axis_fields(int a, double v, int lattice, double v0, double vs, unsigned long long* out) {
+  const unsigned long long mag = dec6_magnitude(v);
+  const double canon = fma((double)lattice, vs, v0);
+  const unsigned long long cmag = dec6_magnitude(canon);
+  if (mag == ~0ull || cmag == ~0ull) return false;
+  const bool neg = v < 0.0 || (v == 0.0 && (__double_as_longlong(v) < 0));
+  const bool cneg = canon < 0.0;
+  const long long s = neg ? -(long long)mag : (long long)mag, cs = cneg ? -(long long)cmag : (long long)cmag;
+  const long long variant = s - cs;
+  if (variant < -3 || variant > 3) return false;
+  *out = key_axis_fields(a, lattice, (int)variant, neg && mag == 0ull);
+  return true;
+}
+
+// LowResManager::getVoxelStatus(position) (voxblox_manager.cpp:73-90) on the mirror: 0 unknown, 1 free, 2 occupied.
+__device__ __forceinline__ unsigned status_at(const FrontierArgs& a, double x, double y, double z) {
+  const double p[3] = {x, y, z};
+  int b[3], l[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float pf = __double2float_rn(p[k]);                                                   // position.cast<float>()
+    b[k] = (int)floorf(__fadd_rn(__fmul_rn(pf, a.block_size_inv), 1e-6f));                      // common.h: getGridIndexFromPoint
+    const float origin = __fmul_rn((float)b[k], a.block_size);                                  // common.h:196-201
+    const int v = (int)floorf(__fadd_rn(__fmul_rn(__fsub_rn(pf, origin), a.voxel_size_inv), 1e-6f));
+    l[k] = max(min(v, a.vps - 1), 0);                                                           // block_inl.h:30-40
+  }
+  const int slot = probe_block(a.L, b[0], b[1], b[2]);
+  if (slot < 0) return 0u;
+  const unsigned lin = (unsigned)(l[0] + a.vps * (l[1] + a.vps * l[2]));
+  return (__ldg(a.L.status + ((size_t)slot * (a.L.nvox >> 4) + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
+}
+
+constexpr int kFrontierThreads = 1024;
+// slot_eval codes
+constexpr int kSlotNone = -1, kSlotUnknown = -2;
+
+__global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const FrontierArgs a) {
+  __shared__ unsigned s_warp[32];
+  __shared__ unsigned s_run, s_total;
+  __shared__ int s_err;
+  __shared__ unsigned long long s_count, s_sum;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  FrontierCell* const cells = a.cells + (size_t)blockIdx.x * a.cell_cap;
+  FrontierEntry* cur = a.cur + (size_t)blockIdx.x * a.frontier_cap;
+  FrontierEntry* next = a.next + (size_t)blockIdx.x * a.frontier_cap;
+  int* const slot_eval = a.slot_eval + (size_t)blockIdx.x * 6 * a.frontier_cap;
+  const unsigned mask = a.cell_cap - 1;
+
+  for (int v = blockIdx.x; v < a.n; v += gridDim.x) {
+    const double x0 = a.points[3 * v], y0 = a.points[3 * v + 1], z0 = a.points[3 * v + 2];
+    for (unsigned i = tid; i < a.cell_cap; i += blockDim.x) cells[i] = FrontierCell{kFrontierEmpty, ~0ull};
+    if (tid == 0) {
+      s_err = 0;
+      s_count = 0ull;
+      s_sum = cell_fingerprint(x0, y0, z0);
+    }
+    __syncthreads();
+    unsigned n_cur = 1, n_visited = 1;
+    if (tid == 0) {
+      unsigned long long fx = 0, fy = 0, fz = 0;
+      const bool ok = axis_fields(0, x0, 0, x0, a.vs, &fx) && axis_fields(1, y0, 0, y0, a.vs, &fy) && axis_fields(2, z0, 0, z0, a.vs, &fz);
+      if (!ok) {
+        s_err = 2;
+      } else {
+        const unsigned long long key = fx | fy | fz;
+        cur[0] = FrontierEntry{x0, y0, z0, key};
+        cells[frontier_hash(key) & mask] = FrontierCell{key, 0ull};  // visited.insert(convertToString(point))
+      }
+    }
+    __syncthreads();
+    unsigned long long my_count = 0ull, my_sum = 0ull;
+    for (unsigned level = 1; n_cur > 0 && s_err == 0; ++level) {
+      const unsigned n_slots = 6u * n_cur;
+      const unsigned long long stamp0 = (unsigned long long)level << 32;
+      // ---- expand: every (entry, direction) of this level
+      for (unsigned s = tid; s < n_slots; s += blockDim.x) {
+        const FrontierEntry e = cur[s / 6u];
+        const unsigned d = s % 6u;
+        const int axis = (int)(d >> 1);
+        const double step = (d & 1u) ? -a.vs : a.vs;
+        // candidate = new_pos + c: all three components are added (Eigen), the idle ones with +0.0
+        const double cx = __dadd_rn(e.x, axis == 0 ? step : 0.0), cy = __dadd_rn(e.y, axis == 1 ? step : 0.0),
+                     cz = __dadd_rn(e.z, axis == 2 ? step : 0.0);
+        int ev = kSlotNone;
+        // key: the moved axis is recomputed; an idle axis keeps its fields unless it was -0.0 (now +0.0)
+        unsigned long long key = e.key;
+        const double cv = axis == 0 ? cx : (axis == 1 ? cy : cz), v0 = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
+        const int lattice = key_lattice(key, axis) + ((d & 1u) ? -1 : 1);
+        unsigned long long f = 0;
+        bool ok = lattice > -32768 && lattice < 32767 && axis_fields(axis, cv, lattice, v0, a.vs, &f);
+        key = (key & ~key_axis_mask(axis)) | f;
+        if (axis != 0 && e.x == 0.0) key &= ~(1ull << 57);
+        if (axis != 1 && e.y == 0.0) key &= ~(1ull << 58);
+        if (axis != 2 && e.z == 0.0) key &= ~(1ull << 59);
+        if (!ok) {
+          s_err = 2;
+        } else {
+          // visited.find(...) as of the previous levels (same-level arrivals are arbitrated below)
+          bool seen = false;
+          unsigned h = frontier_hash(key) & mask;
+          for (unsigned n = 0; n <= mask; ++n) {
+            const unsigned long long k = cells[h].key;
+            if (k == key) {
+              seen = cells[h].arrival < stamp0;
+              break;
+            }
+            if (k == kFrontierEmpty) break;
+            h = (h + 1) & mask;
+          }
+          if (!seen) {
+            const double dx = __dsub_rn(cx, x0), dy = __dsub_rn(cy, y0), dz = __dsub_rn(cz, z0);
+            const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
+            if (nrm <= a.max_distance && cx >= a.bmin[0] && cx <= a.bmax[0] && cy >= a.bmin[1] && cy <= a.bmax[1] &&
+                cz >= a.bmin[2] && cz <= a.bmax[2]) {
+              const unsigned st = status_at(a, cx, cy, cz);
+              if (st == 0u) {
+                ev = kSlotUnknown;
+              } else if (st == 1u) {
+                // insert or find, earliest arrival wins
+                unsigned hh = frontier_hash(key) & mask;
+                bool placed = false;
+                for (unsigned n = 0; n <= mask; ++n) {
+                  unsigned long long k = cells[hh].key;
+                  if (k == kFrontierEmpty) k = atomicCAS(&cells[hh].key, kFrontierEmpty, key);
+                  if (k == kFrontierEmpty || k == key) {
+                    atomicMin(&cells[hh].arrival, stamp0 | s);
+                    ev = (int)hh;
+                    placed = true;
+                    break;
+                  }
+                  hh = (hh + 1) & mask;
+                }
+                if (!placed) s_err = 1;
+              }
+            }
+          }
+        }
+        slot_eval[s] = ev;
+      }
+      __syncthreads();
+      // ---- resolve in slot order: winners form the next frontier, unknown neighbours are counted
+      if (tid == 0) s_run = 0u;
+      __syncthreads();
+      for (unsigned base = 0; base < n_slots; base += blockDim.x) {
+        const unsigned s = base + tid;
+        bool win = false;
+        double cx = 0, cy = 0, cz = 0;
+        unsigned long long key = 0;
+        if (s < n_slots) {
+          const int ev = slot_eval[s];
+          if (ev != kSlotNone) {
+            const FrontierEntry e = cur[s / 6u];
+            const unsigned d = s % 6u;
+            const int axis = (int)(d >> 1);
+            const double step = (d & 1u) ? -a.vs : a.vs;
+            cx = __dadd_rn(e.x, axis == 0 ? step : 0.0);
+            cy = __dadd_rn(e.y, axis == 1 ? step : 0.0);
+            cz = __dadd_rn(e.z, axis == 2 ? step : 0.0);
+            if (ev >= 0) {
+              win = cells[ev].arrival == (stamp0 | s);
+              key = cells[ev].key;
+            } else {
+              // unknown neighbour: counted unless an earlier slot of this level inserted this very key
+              key = e.key;
+              const double cv = axis == 0 ? cx : (axis == 1 ? cy : cz), v0 = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
+              unsigned long long f = 0;
+              axis_fields(axis, cv, key_lattice(key, axis) + ((d & 1u) ? -1 : 1), v0, a.vs, &f);
+              key = (key & ~key_axis_mask(axis)) | f;
+              if (axis != 0 && e.x == 0.0) key &= ~(1ull << 57);
+              if (axis != 1 && e.y == 0.0) key &= ~(1ull << 58);
+              if (axis != 2 && e.z == 0.0) key &= ~(1ull << 59);
+              bool earlier = false;
+              unsigned h = frontier_hash(key) & mask;
+              for (unsigned n = 0; n <= mask; ++n) {
+                const unsigned long long k = cells[h].key;
+                if (k == key) {
+                  earlier = cells[h].arrival < (stamp0 | s);
+                  break;
+                }
+                if (k == kFrontierEmpty) break;
+                h = (h + 1) & mask;
+              }
+              if (!earlier) ++my_count;
+            }
+          }
+        }
+        // exclusive scan of `win` over the chunk, in slot order
+        const unsigned ballot = __ballot_sync(0xffffffffu, win);
+        if (lane == 0) s_warp[warp] = __popc(ballot);
+        __syncthreads();
+        if (warp == 0) {
+          unsigned w = s_warp[lane];
+          unsigned incl = w;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          s_warp[lane] = incl - w;
+          if (lane == 31) s_total = incl;
+        }
+        __syncthreads();
+        if (win) {
+          const unsigned pos = s_run + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
+          if (pos < a.frontier_cap) next[pos] = FrontierEntry{cx, cy, cz, key};
+          my_sum += cell_fingerprint(cx, cy, cz);
+        }
+        __syncthreads();
+        if (tid == 0) s_run += s_total;
+        __syncthreads();
+      }
+      const unsigned n_next = s_run;
+      if (n_next > a.frontier_cap) {
+        if (tid == 0) s_err = 1;
+      }
+      __syncthreads();
+      n_visited += n_next;
+      n_cur = n_next;
+      FrontierEntry* t = cur;
+      cur = next;
+      next = t;
+    }
+    // ---- vertex result
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      my_count += __shfl_xor_sync(0xffffffffu, my_count, o);
+      my_sum += __shfl_xor_sync(0xffffffffu, my_sum, o);
+    }
+    if (lane == 0 && my_count) atomicAdd(&s_count, my_count);
+    if (lane == 0 && my_sum) atomicAdd(&s_sum, my_sum);
+    __syncthreads();
+    if (tid == 0) {
+      a.frontier_voxels[v] = s_count;
+      if (a.visited) a.visited[v] = n_visited;
+      if (a.checksum) a.checksum[v] = s_sum;
+      a.status[v] = s_err;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace nbvgpu
+
+#endif  // NBVGPU_FRONTIER_KERNELS_CUH_

@@ -19,6 +19,7 @@
 
 #include "camera_host.h"
 #include "gain_kernels.cuh"
+#include "frontier_kernels.cuh"
 #include "map_mirror.cuh"
 #include "voxblox_io.h"
 
@@ -136,6 +137,7 @@ struct nbvgpu_ctx {
   unsigned long long* d_totals = nullptr;  // rays, voxel steps, collision steps, classifier mismatches
   PinBuf h_io;                             // pinned staging for n-sized inputs / outputs
   DevBuf d_pos, d_per_yaw, d_gain, d_yaw, d_counts, d_steps, d_seg, d_free, d_aux, d_best;
+  DevBuf d_fr_cells, d_fr_cur, d_fr_next, d_fr_slots, d_fr_io;  // History::bfs workspaces (nbvgpu_frontier_potential)
   nbvgpu_stats stats{};
   int variant = 0;
   int sm_count = 148;
@@ -1127,6 +1129,103 @@ int nbvgpu_check_motion(nbvgpu_ctx* ctx, int layer, double radius, const double 
   if (rc) return rc;
   *free_out = f;
   return NBVGPU_OK;
+}
+
+// ---- History::bfs (history.cpp:96-137): frontier potential of history-graph vertices ---------
+int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double* points, double max_distance, double* potential_gain,
+                              uint64_t* frontier_voxels, uint64_t* visited_cells, uint64_t* cells_checksum) {
+  if (!ctx || (n && (!points || !potential_gain))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
+  if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "set the camera first: its bounding box is the exploration bounds the flood fill respects");
+  if (n == 0) return NBVGPU_OK;
+  const double vs = (double)L->voxel_size;  // LowResManager::getResolution(): the float voxel size widened
+  if (!(max_distance >= 0.0) || !(max_distance / vs < 30000.0)) return fail(ctx, NBVGPU_ERR_RANGE, "max_distance out of range");
+  for (size_t i = 0; i < 3 * n; ++i)
+    if (!(std::fabs(points[i]) + max_distance + vs < 1048576.0)) return fail(ctx, NBVGPU_ERR_RANGE, "vertex non-finite or out of range");
+  DeviceGuard guard(ctx->device);
+  // workspace per CTA: every lattice cell within max_distance can be visited once (+ slack for split keys)
+  const double R = std::floor(max_distance / vs) + 2.0;
+  const size_t cells_bound = (size_t)std::ceil(4.18879 * (R + 1.0) * (R + 1.0) * (R + 1.0)) + 64;
+  size_t cell_cap = 1024;
+  while (cell_cap < 2 * cells_bound) cell_cap <<= 1;
+  if (cell_cap > (1ull << 30)) return fail(ctx, NBVGPU_ERR_CAPACITY, "max_distance / voxel_size too large for the visited set");
+  const size_t n_ctas = std::min<size_t>(n, (size_t)ctx->sm_count);
+  std::vector<int> h_status(n);
+  std::vector<unsigned long long> h_count(n), h_visited(n), h_sum(n);
+  // a level of the fill is a surface: 16 (R + 2)^2 entries cover it with a wide margin; a fill that needs
+  // more reports it and the call is repeated once with room for every cell
+  size_t frontier_cap = std::min<size_t>(cells_bound, std::max<size_t>(4096, (size_t)(16.0 * (R + 2.0) * (R + 2.0))));
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CK(ctx->d_fr_cells.reserve(n_ctas * cell_cap * sizeof(FrontierCell)));
+    CK(ctx->d_fr_cur.reserve(n_ctas * frontier_cap * sizeof(FrontierEntry)));
+    CK(ctx->d_fr_next.reserve(n_ctas * frontier_cap * sizeof(FrontierEntry)));
+    CK(ctx->d_fr_slots.reserve(n_ctas * frontier_cap * 6 * sizeof(int)));
+    CK(ctx->d_fr_io.reserve(n * (24 + 8 + 8 + 8 + 4) + 64));
+    CK(ctx->h_io.reserve(n * (24 + 8 + 8 + 8 + 4) + 64, false));
+    char* h = ctx->h_io.as<char>();
+    memcpy(h, points, n * 24);
+    char* d = ctx->d_fr_io.as<char>();
+    CK(cudaMemcpyAsync(d, h, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+    FrontierArgs a;
+    a.L = L->view();
+    a.points = reinterpret_cast<const double*>(d);
+    a.frontier_voxels = reinterpret_cast<unsigned long long*>(d + n * 24);
+    a.visited = reinterpret_cast<unsigned long long*>(d + n * 32);
+    a.checksum = reinterpret_cast<unsigned long long*>(d + n * 40);
+    a.status = reinterpret_cast<int*>(d + n * 48);
+    a.cells = ctx->d_fr_cells.as<FrontierCell>();
+    a.cur = ctx->d_fr_cur.as<FrontierEntry>();
+    a.next = ctx->d_fr_next.as<FrontierEntry>();
+    a.slot_eval = ctx->d_fr_slots.as<int>();
+    a.cell_cap = (unsigned)cell_cap;
+    a.frontier_cap = (unsigned)frontier_cap;
+    a.vs = vs;
+    a.max_distance = max_distance;
+    for (int k = 0; k < 3; ++k) {
+      a.bmin[k] = ctx->cam.bbx_min[k];
+      a.bmax[k] = ctx->cam.bbx_max[k];
+    }
+    // layer.h:34-42: block_size_ = voxel_size_ * voxels_per_side_ (float), the inverses are 1.0 / x rounded to float
+    a.block_size = L->voxel_size * (float)L->vps;
+    a.block_size_inv = (float)(1.0 / (double)a.block_size);
+    a.voxel_size_inv = (float)(1.0 / (double)L->voxel_size);
+    a.vps = L->vps;
+    a.n = (int)n;
+    k_frontier_bfs<<<(unsigned)n_ctas, kFrontierThreads, 0, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(h + n * 24, d + n * 24, n * 28, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(h_count.data(), h + n * 24, n * 8);
+    memcpy(h_visited.data(), h + n * 32, n * 8);
+    memcpy(h_sum.data(), h + n * 40, n * 8);
+    memcpy(h_status.data(), h + n * 48, n * 4);
+    bool overflow = false;
+    for (size_t i = 0; i < n; ++i) {
+      if (h_status[i] == 2) return fail(ctx, NBVGPU_ERR_RANGE, "flood fill left the representable key range");
+      if (h_status[i] == 1) overflow = true;
+    }
+    if (!overflow) break;
+    if (attempt == 1 || frontier_cap == cells_bound) return fail(ctx, NBVGPU_ERR_CAPACITY, "flood-fill workspace exhausted");
+    frontier_cap = cells_bound;
+  }
+  const double cube = std::pow(vs, 3.0);  // history.cpp:136
+  for (size_t i = 0; i < n; ++i) {
+    potential_gain[i] = (double)(int)h_count[i] * cube;
+    if (frontier_voxels) frontier_voxels[i] = h_count[i];
+    if (visited_cells) visited_cells[i] = h_visited[i];
+    if (cells_checksum) cells_checksum[i] = h_sum[i];
+  }
+  return NBVGPU_OK;
+}
+
+// Host-only: round_half_even(|x| * 10^6) as the flood fill's cell keys compute it (what "%f" prints); for tests.
+int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude) {
+  if (!magnitude) return NBVGPU_ERR_INVALID;
+  *magnitude = dec6_magnitude(x);
+  return *magnitude == ~0ull ? NBVGPU_ERR_RANGE : NBVGPU_OK;
 }
 
 // ---- introspection -------------------------------------------------------------------------

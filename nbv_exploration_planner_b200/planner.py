@@ -279,6 +279,18 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_check_motion(self._h, layer, float(robot_radius), s, e, C.byref(out)))
         return bool(out.value)
 
+    # -- history-graph frontier potential (History::bfs, history.cpp:96-137) -----------------
+    def frontier_potential(self, tsdf_layer: int, points, max_distance: float = 6.0) -> dict:
+        """potential gain and frontier-voxel count of each vertex position (the reference hard-codes 6.0 m)."""
+        pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+        gain = np.zeros(len(pts))
+        fv = np.zeros(len(pts), np.uint64)
+        vis = np.zeros(len(pts), np.uint64)
+        chk = np.zeros(len(pts), np.uint64)
+        self._ck(self._L.nbvgpu_frontier_potential(self._h, tsdf_layer, len(pts), _vp(pts), float(max_distance), _vp(gain), _vp(fv),
+                                                   _vp(vis), _vp(chk)))
+        return {"gain": gain, "frontier_voxels": fv, "visited": vis, "cells_checksum": chk}
+
     # -- introspection -----------------------------------------------------------------------
     def stats(self) -> dict:
         s = N.Stats()
@@ -380,6 +392,23 @@ class HighResManager:
 
     def checkMotionBatch(self, segments: np.ndarray) -> np.ndarray:
         return self.gpu.check_segments(self.layer, self.robot_radius, segments)
+
+
+class History:
+    """The map-reading part of ``nbveplanner::History`` (history.h): ``bfs`` / ``recalculatePotential``."""
+
+    def __init__(self, gpu: NbvGpu, manager_lowres: "LowResManager", zero_frontier_voxels: float = 10.0):
+        self.gpu = gpu
+        self.manager_lowres = manager_lowres
+        # params.h:42,105-106: nbvep/graph/zero_frontier_voxels, default 10.0; a vertex whose potential is not
+        # above it is retired (history.cpp:213) -- that decision stays with the caller
+        self.zero_frontier_voxels = float(zero_frontier_voxels)
+
+    def bfs(self, point) -> float:  # history.cpp:103-137
+        return float(self.gpu.frontier_potential(self.manager_lowres.layer, np.asarray(point, float).reshape(1, 3))["gain"][0])
+
+    def recalculatePotential(self, positions) -> np.ndarray:  # history.cpp:211-222, all vertices of a pass at once
+        return self.gpu.frontier_potential(self.manager_lowres.layer, positions)["gain"]
 
 
 @dataclass

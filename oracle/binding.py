@@ -197,14 +197,15 @@ class Oracle:
         """History::bfs (history.cpp:103-137) per vertex: potential gain, frontier-voxel count, visited cells."""
         pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
         n = len(pts)
-        gain = np.zeros(n); fv = np.zeros(n, np.uint64); vis = np.zeros(n, np.uint64)
+        gain = np.zeros(n); fv = np.zeros(n, np.uint64); vis = np.zeros(n, np.uint64); chk = np.zeros(n, np.uint64)
         self._l.nbvo_frontier_potential.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_double), C.c_double,
-                                                    C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]
+                                                    C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64),
+                                                    C.POINTER(C.c_uint64), C.c_int]
         rc = self._l.nbvo_frontier_potential(self._c, layer, n, _ptr(pts, C.c_double), float(max_distance), _ptr(gain, C.c_double),
-                                             _ptr(fv, C.c_uint64), _ptr(vis, C.c_uint64), threads)
+                                             _ptr(fv, C.c_uint64), _ptr(vis, C.c_uint64), _ptr(chk, C.c_uint64), threads)
         if rc != 0:
             raise RuntimeError(f"nbvo_frontier_potential -> {rc}")
-        return {"gain": gain, "frontier_voxels": fv, "visited": vis}
+        return {"gain": gain, "frontier_voxels": fv, "visited": vis, "cells_checksum": chk}
 
     def voxel_status_at(self, layer: int, p) -> int:
         p = np.ascontiguousarray(p, np.float64)

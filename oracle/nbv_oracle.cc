@@ -576,8 +576,10 @@ int nbvo_check_segments(void* c_, int layer, double radius, size_t n, const doub
 // block_size (common.h:196-201, layer.h:137).  All in float, as the reference.
 inline Status voxel_status_at(const Layer& L, const V3& position) {
   const float block_size = (float)L.vps * L.voxel_size;  // layer.h:32  block_size_ = voxel_size_ * voxels_per_side_
-  const float block_size_inv = 1.0f / block_size;
-  const float voxel_size_inv = 1.0f / L.voxel_size;
+  // layer.h:37,41 / block.h:38,40: `1.0 / x` -- a double division rounded to float on assignment (identical to
+  // the float quotient: 53 >= 2 * 24 + 2 bits makes the double rounding innocuous; written the reference's way)
+  const float block_size_inv = (float)(1.0 / (double)block_size);
+  const float voxel_size_inv = (float)(1.0 / (double)L.voxel_size);
   const float pf[3] = {(float)position.x, (float)position.y, (float)position.z};
   int b[3], l[3];
   for (int k = 0; k < 3; ++k) {
@@ -599,14 +601,29 @@ inline std::string bfs_key(const V3& v) {
   std::snprintf(buf, sizeof buf, "%f/%f/%f", v.x, v.y, v.z);
   return std::string(buf);
 }
-inline uint64_t frontier_bfs(const Ctx* c, const Layer& L, const V3& point, double max_distance, uint64_t* visited_out) {
+// Order-independent fingerprint of a visited cell: a 64-bit mix of the bit patterns of its three doubles (the
+// same function in csrc/frontier_kernels.cuh); the sum over all visited cells tells whether two
+// implementations hold the same doubles for every cell, i.e. made the same first arrivals.
+inline uint64_t cell_fingerprint(const V3& v) {
+  uint64_t b[3];
+  std::memcpy(&b[0], &v.x, 8); std::memcpy(&b[1], &v.y, 8); std::memcpy(&b[2], &v.z, 8);
+  uint64_t h = 0x9E3779B97F4A7C15ull;
+  for (int k = 0; k < 3; ++k) {
+    h ^= b[k] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h *= 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 31;
+  }
+  return h;
+}
+inline uint64_t frontier_bfs(const Ctx* c, const Layer& L, const V3& point, double max_distance, uint64_t* visited_out,
+                             uint64_t* checksum_out = nullptr) {
   const double vs = (double)L.voxel_size;  // getResolution(): the float voxel size widened (voxblox_manager.h:35)
   const V3 conn[6] = {{vs, 0, 0}, {-vs, 0, 0}, {0, vs, 0}, {0, -vs, 0}, {0, 0, vs}, {0, 0, -vs}};
   std::unordered_set<std::string> visited;
   visited.insert(bfs_key(point));
   std::queue<V3> queue;
   queue.push(point);
-  uint64_t frontier = 0;
+  uint64_t frontier = 0, checksum = cell_fingerprint(point);
   while (!queue.empty()) {
     const V3 cur = queue.front();
     queue.pop();
@@ -621,26 +638,30 @@ inline uint64_t frontier_bfs(const Ctx* c, const Layer& L, const V3& point, doub
       if (st == kFree) {
         visited.insert(bfs_key(cand));
         queue.push(cand);
+        checksum += cell_fingerprint(cand);
       } else if (st == kUnknown) {
         ++frontier;
       }
     }
   }
   if (visited_out) *visited_out = visited.size();
+  if (checksum_out) *checksum_out = checksum;
   return frontier;
 }
 
 // History::recalculatePotential's input: potential_gain = frontierVoxels * pow(voxel_size, 3.0) per vertex.
 int nbvo_frontier_potential(void* c_, int layer, size_t n, const double* points, double max_distance, double* gain,
-                            uint64_t* frontier_voxels /*[n] or null*/, uint64_t* visited /*[n] or null*/, int n_threads) {
+                            uint64_t* frontier_voxels /*[n] or null*/, uint64_t* visited /*[n] or null*/,
+                            uint64_t* checksum /*[n] or null*/, int n_threads) {
   Ctx* c = static_cast<Ctx*>(c_);
   if (!c->cam_set) return -2;
   const Layer& L = *c->layers.at(layer);
   if (L.kind != 0) return -3;
   const double cube = std::pow((double)L.voxel_size, 3.0);
   parallel_for(n, n_threads, [&](size_t i) {
-    uint64_t vis = 0;
-    const uint64_t f = frontier_bfs(c, L, V3{points[3 * i], points[3 * i + 1], points[3 * i + 2]}, max_distance, &vis);
+    uint64_t vis = 0, sum = 0;
+    const uint64_t f = frontier_bfs(c, L, V3{points[3 * i], points[3 * i + 1], points[3 * i + 2]}, max_distance, &vis, &sum);
+    if (checksum) checksum[i] = sum;
     gain[i] = (double)(int)f * cube;  // int frontierVoxels * pow(...) (history.cpp:136)
     if (frontier_voxels) frontier_voxels[i] = f;
     if (visited) visited[i] = vis;

@@ -1,0 +1,129 @@
+"""GPU parity for the history-graph frontier potential: nbvgpu_frontier_potential vs the
+oracle's literal restatement of History::bfs (history.cpp:96-137; itself pinned against the reference's own
+lines in tests/test_ref_pinning.py).  Bar: the frontier-voxel count and the potential gain bit-exact."""
+import numpy as np
+import pytest
+
+from conftest import load_gpu, load_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(o, lt_o, g, lt_g, pts, max_distance=6.0):
+    ro = o.frontier_potential(lt_o, pts, max_distance, threads=8)
+    rg = g.frontier_potential(lt_g, pts, max_distance)
+    assert np.array_equal(rg["frontier_voxels"], ro["frontier_voxels"]), (rg["frontier_voxels"], ro["frontier_voxels"])
+    assert np.array_equal(rg["gain"], ro["gain"])
+    assert np.array_equal(rg["visited"], ro["visited"]), (rg["visited"], ro["visited"])   # size of the reference's visited set
+    # every visited cell holds the same three doubles as in the sequential FIFO order (sum of per-cell fingerprints)
+    assert np.array_equal(rg["cells_checksum"], ro["cells_checksum"])
+    return ro, rg
+
+
+def _special_points(cfg):
+    lo, hi = np.array(cfg.bounds_min, float), np.array(cfg.bounds_max, float)
+    return np.array([lo + 0.01, hi - 0.01, lo - 0.5, [lo[0], 0.5 * (lo[1] + hi[1]), 1.0], 0.5 * (lo + hi),
+                     [cfg.root[0], cfg.root[1], cfg.root[2]], [1.0, 2.0, 0.5], [3.0, 4.0, 1.0], hi, lo])
+
+
+def test_tiny_map_vertices_everywhere(oracle_mod, tiny_map):
+    """Vertices in free, unknown and occupied space, on and outside the exploration bounds."""
+    from nbv_exploration_planner_b200 import synth
+    cam = tiny_map.camera()
+    o, lt_o, _ = load_oracle(oracle_mod, tiny_map, cam)
+    g, lt_g, _ = load_gpu(tiny_map, cam)
+    c = synth.make_candidates(tiny_map.cfg, 12, None)
+    ro, rg = _compare(o, lt_o, g, lt_g, np.concatenate([c.positions, _special_points(tiny_map.cfg)]))
+    assert ro["frontier_voxels"].max() > 100 and ro["visited"].max() > 1000
+    for d in (0.0, 0.19, 1.0, 2.5):
+        _compare(o, lt_o, g, lt_g, c.positions[:4], d)
+    g.close()
+
+
+def test_cfg1_map_full_radius(oracle_mod, cfg1_map):
+    """BASELINE config 1 map (0.15 m voxels): ~150 k visited cells per vertex at the reference's 6.0 m."""
+    from nbv_exploration_planner_b200 import synth
+    cam = cfg1_map.camera()
+    o, lt_o, _ = load_oracle(oracle_mod, cfg1_map, cam)
+    g, lt_g, _ = load_gpu(cfg1_map, cam)
+    c = synth.make_candidates(cfg1_map.cfg, 6, None)
+    ro, rg = _compare(o, lt_o, g, lt_g, c.positions)
+    assert ro["visited"].min() > 50000
+    g.close()
+
+
+def test_quarter_metre_voxels_knife_edge(oracle_mod):
+    """A voxel size of exactly 0.25 m: 24 steps reach 6.0 m exactly, so `norm <= 6.0` is decided by the
+    roundings of the accumulated doubles, which differ between paths."""
+    from nbv_exploration_planner_b200 import synth
+    cfg = synth.SynthConfig("quarter", (-3, -2, 0), (9, 10, 3), 0.25, 3.0, 8, "pillars", 91, 92, (3.0, 4.0, 1.0), obs_radius=4.0,
+                            traj_points=4, traj_step=2.5, vicinity=3.0)
+    m = synth.make_map(cfg)
+    cam = m.camera()
+    o, lt_o, _ = load_oracle(oracle_mod, m, cam)
+    g, lt_g, _ = load_gpu(m, cam)
+    c = synth.make_candidates(cfg, 6, None)
+    _compare(o, lt_o, g, lt_g, np.concatenate([c.positions, _special_points(cfg), [[3.0, 4.0, 1.0], [0.25, 0.5, 0.75]]]))
+    g.close()
+
+
+def test_negative_zero_and_tiny_negative_coordinates(oracle_mod):
+    """std::to_string(-0.0) is "-0.000000" but -0.0 + 0.0 is +0.0, and -1e-9 prints "-0.000000" for ever: the
+    start cell and the cell the fill comes back to are different strings, so the reference visits it again."""
+    from nbv_exploration_planner_b200 import LAYER_TSDF, NbvGpu
+    from nbv_exploration_planner_b200.planner import CameraParams
+    vs, vps = 0.2, 16
+    keys = np.array([[bx, by, bz] for bx in (-1, 0) for by in (-1, 0) for bz in (-1, 0)], np.int32)
+    tsdf = np.zeros((len(keys), vps ** 3, 2), np.float32)
+    tsdf[..., 0] = 0.4
+    tsdf[..., 1] = 1.0          # everything observed free; outside these blocks unknown
+    rng = np.random.default_rng(2)
+    hole = rng.random(tsdf.shape[:2]) < 0.03
+    tsdf[hole, 1] = 0.0         # a few unknown voxels inside
+    wall = rng.random(tsdf.shape[:2]) < 0.03
+    tsdf[wall, 0] = -0.1        # and a few occupied ones
+    tsdf[3, 15, 1] = 0.0        # block (-1,0,0) voxel (15,0,0): the -x neighbour of the cell at the origin is unknown,
+    tsdf[7, 0, :] = (0.4, 1.0)  # the cell at the origin (block (0,0,0) voxel (0,0,0)) is free
+    cam = CameraParams(hfov_deg=90, vfov_deg=60, near_m=0.1, far_m=2.0, bbx_min=(-2.5, -2.5, -2.5), bbx_max=(2.5, 2.5, 2.5))
+    o = oracle_mod.Oracle()
+    lt_o = o.layer_create(0, vs, vps)
+    o.layer_update(lt_o, keys, tsdf)
+    o.set_camera(cam.as_dict())
+    g = NbvGpu(0)
+    lt_g = g.layer_create(LAYER_TSDF, vs, vps, 16)
+    g.layer_update(lt_g, keys, tsdf)
+    g.commit()
+    g.set_camera(cam)
+    pts = np.array([[-0.0, 0.1, 0.1], [0.0, 0.1, 0.1], [0.1, -0.0, -0.0], [-1e-9, 0.1, 0.1], [1e-9, -1e-9, 0.1], [-0.0, -0.0, -0.0],
+                    [0.0078125, 0.0234375, 0.1], [-0.0078125, 0.3, -0.0234375]])
+    ro, rg = _compare(o, lt_o, g, lt_g, pts, 2.0)
+    assert ro["visited"].min() > 1000
+    # the quirk is observable here: from -0.0 the origin cell is entered twice and its unknown neighbour counted twice
+    assert ro["frontier_voxels"][0] == ro["frontier_voxels"][1] + 1 and ro["visited"][0] == ro["visited"][1] + 1
+    g.close()
+
+
+def test_empty_map_and_errors(oracle_mod):
+    from nbv_exploration_planner_b200 import LAYER_ESDF, LAYER_TSDF, NbvGpu, NbvGpuError
+    from nbv_exploration_planner_b200.planner import CameraParams
+    cam = CameraParams(hfov_deg=90, vfov_deg=60, near_m=0.1, far_m=2.0, bbx_min=(-5, -5, -5), bbx_max=(5, 5, 5))
+    o = oracle_mod.Oracle()
+    lt_o = o.layer_create(0, 0.15, 16)
+    o.set_camera(cam.as_dict())
+    g = NbvGpu(0)
+    lt_g = g.layer_create(LAYER_TSDF, 0.15, 16, 8)
+    le_g = g.layer_create(LAYER_ESDF, 0.15, 16, 8)
+    with pytest.raises(NbvGpuError):     # the exploration bounds come with the camera
+        g.frontier_potential(lt_g, [[0.0, 0.0, 0.0]])
+    g.set_camera(cam)
+    ro, rg = _compare(o, lt_o, g, lt_g, np.array([[0.1, 0.2, 0.3], [4.95, 0.0, 0.0], [7.0, 0.0, 0.0]]))
+    assert list(rg["frontier_voxels"]) == [6, 5, 0]   # all six neighbours unknown; one outside the bounds; all outside
+    assert g.frontier_potential(lt_g, np.zeros((0, 3)))["gain"].shape == (0,)
+    for bad in ([[float("nan"), 0, 0]], [[1e7, 0, 0]]):
+        with pytest.raises(NbvGpuError):
+            g.frontier_potential(lt_g, bad)
+    with pytest.raises(NbvGpuError):
+        g.frontier_potential(le_g, [[0.0, 0.0, 0.0]])
+    with pytest.raises(NbvGpuError):
+        g.frontier_potential(lt_g, [[0.0, 0.0, 0.0]], max_distance=1e6)
+    g.close()

@@ -224,3 +224,36 @@ def test_frontier_bfs_matches_reference_history(tiny_map, which):
     assert np.array_equal(ro["gain"], rr), (ro["gain"], rr)
     assert ro["frontier_voxels"].max() > 100 and ro["visited"].max() > 1000   # the fill really spreads
 
+
+def test_frontier_bfs_negative_zero_coordinates_match_reference():
+    """std::to_string(-0.0) == "-0.000000" while -0.0 + 0.0 == +0.0, and -1e-9 prints "-0.000000" for ever: start
+    points with such coordinates make the reference's string keys split a cell.  Same map and points as
+    tests/test_gpu_frontier.py::test_negative_zero_and_tiny_negative_coordinates (the reference hard-codes 6.0 m;
+    the blocks only reach 3.2 m, so the fill is bounded by the unknown space around them)."""
+    from nbv_exploration_planner_b200.planner import CameraParams
+    vs, vps = 0.2, 16
+    keys = np.array([[bx, by, bz] for bx in (-1, 0) for by in (-1, 0) for bz in (-1, 0)], np.int32)
+    tsdf = np.zeros((len(keys), vps ** 3, 2), np.float32)
+    tsdf[..., 0] = 0.4
+    tsdf[..., 1] = 1.0
+    rng = np.random.default_rng(2)
+    tsdf[rng.random(tsdf.shape[:2]) < 0.03, 1] = 0.0
+    tsdf[rng.random(tsdf.shape[:2]) < 0.03, 0] = -0.1
+    tsdf[3, 15, 1] = 0.0        # the -x neighbour of the cell at the origin is unknown,
+    tsdf[7, 0, :] = (0.4, 1.0)  # the cell at the origin is free
+    cam = CameraParams(hfov_deg=90, vfov_deg=60, near_m=0.1, far_m=2.0, bbx_min=(-2.5, -2.5, -2.5), bbx_max=(2.5, 2.5, 2.5))
+    o = ob.Oracle()
+    lt = o.layer_create(0, vs, vps)
+    o.layer_update(lt, keys, tsdf)
+    o.set_camera(cam.as_dict())
+    r = rb.Reference(vs, vps)
+    r.tsdf_update(keys, tsdf)
+    r.set_camera(cam.as_dict(), 0.4)
+    pts = np.array([[-0.0, 0.1, 0.1], [0.0, 0.1, 0.1], [0.1, -0.0, -0.0], [-1e-9, 0.1, 0.1], [1e-9, -1e-9, 0.1], [-0.0, -0.0, -0.0],
+                    [0.0078125, 0.0234375, 0.1], [-0.0078125, 0.3, -0.0234375]])
+    ro, rr = o.frontier_potential(lt, pts, 6.0, threads=8), r.frontier_potential(pts)
+    assert np.array_equal(ro["gain"], rr), (ro["gain"], rr)
+    assert ro["visited"].min() > 1000
+    # observable in the reference's own result: the -0.0 start counts the unknown neighbour of the origin cell twice
+    assert rr[0] != rr[1] and ro["frontier_voxels"][0] == ro["frontier_voxels"][1] + 1
+
