@@ -1149,7 +1149,7 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double
   const double R = std::floor(max_distance / vs) + 2.0;
   const size_t cells_bound = (size_t)std::ceil(4.18879 * (R + 1.0) * (R + 1.0) * (R + 1.0)) + 64;
   size_t cell_cap = 1024;
-  while (cell_cap < 2 * cells_bound) cell_cap <<= 1;
+  while (cell_cap < cells_bound + cells_bound / 2) cell_cap <<= 1;  // load factor <= 2/3 even if every cell of the sphere is visited
   if (cell_cap > (1ull << 30)) return fail(ctx, NBVGPU_ERR_CAPACITY, "max_distance / voxel_size too large for the visited set");
   const size_t n_ctas = std::min<size_t>(n, (size_t)ctx->sm_count);
   std::vector<int> h_status(n);
