@@ -233,6 +233,10 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, const d
                               double max_distance, double* potential_gain /* [n] */,
                               uint64_t* frontier_voxels /* [n] or NULL */, uint64_t* visited_cells /* [n] or NULL */,
                               uint64_t* cells_checksum /* [n] or NULL */);
+/* Vertices, since the context was created, whose flood fill met one lattice cell under two different strings (next
+ * to a "%f" rounding boundary, or -0.0 against +0.0) and was therefore redone with the exact hash-keyed visited set
+ * instead of the dense one; for tests (NBVGPU_FRONTIER_HASH=1 in the environment forces the hash set for all). */
+int nbvgpu_debug_frontier_hash_redo(nbvgpu_ctx* ctx, uint64_t* count);
 /* Host-only helper for tests: round-half-even of |x| * 10^6, the integer behind "%f" / std::to_string(double),
  * exactly as the flood fill's cell keys compute it.  NBVGPU_ERR_RANGE for non-finite x or |x| >= 2^21. */
 int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude);

@@ -28,6 +28,7 @@
 
 #include <cstdint>
 #include <cstring>
+#include <type_traits>
 
 #include "map_mirror.cuh"
 
@@ -95,13 +96,17 @@ struct FrontierArgs {
   unsigned long long* frontier_voxels;  // [n]
   unsigned long long* visited;          // [n] or null
   unsigned long long* checksum;         // [n] or null: sum of cell_fingerprint over the visited cells
-  int* status;                          // [n]: 0 ok, 1 workspace exhausted, 2 coordinate out of range
+  int* status;                          // [n]: 0 ok, 1 workspace exhausted, 2 coordinate out of range,
+                                        //      3 dense set met a split key: redo this vertex with the hash set
+  const int* todo;                      // null, or [n]: the vertices this launch has to do (the others are left alone)
   // workspace of CTA b: cells + b * cell_cap, cur/next + b * frontier_cap, slot_eval + b * 6 * frontier_cap
   FrontierCell* cells;
   FrontierEntry* cur;
   FrontierEntry* next;
   int* slot_eval;
-  unsigned cell_cap;      // power of two
+  unsigned cell_cap;      // power of two (hash set)
+  unsigned long long* grid;  // dense visited set: workspace of CTA b at grid + b * grid_dim^3
+  int grid_r;                // lattice radius covered: indices -grid_r .. grid_r per axis
   unsigned frontier_cap;
   double vs;              // float voxel size widened (LowResManager::getResolution)
   double max_distance;
@@ -179,27 +184,122 @@ __device__ __forceinline__ unsigned status_at(const FrontierArgs& a, double x, d
   return (__ldg(a.L.status + ((size_t)slot * (a.L.nvox >> 4) + (lin >> 4))) >> ((lin & 15u) * 2u)) & 3u;
 }
 
+// ---- visited set ------------------------------------------------------------------------------
+// Two implementations with one interface.  `stamp` = (level << kStampSlotBits) | slot orders arrivals; an entry created in
+// an earlier level has a smaller stamp than any stamp of the current one.
+//   (stamp = (level << 26) | slot)
+//   seen_before(key, level_stamp)  was this key inserted in an earlier level (or is it the start)?
+//   insert(key, stamp)             create the entry or lower its stamp; returns a handle (< 0: no room)
+//   owner(handle) / key_of(handle) after the level's barrier: the winning stamp and the key
+//   earlier(key, stamp)            after the barrier: was this key inserted with a smaller stamp?
+// VisitedHash: open addressing on the full 64-bit key -- exact in every case.
+// VisitedDense: one 8-byte word per lattice cell of the cube |i|,|j|,|k| <= R: (stamp << 12) | the key's 12
+// rounding / zero-sign bits; one access, no probing, and a wavefront only touches a shell of the cube.  A
+// lattice cell can hold one key only: meeting an entry whose 12 bits differ (the same lattice cell under two
+// different strings -- next to a "%f" rounding boundary, or -0.0 against +0.0) raises `split`, and the vertex
+// is redone with VisitedHash.
+constexpr int kStampSlotBits = 26;  // slots per level < 2^26; the dense word keeps 64 - 12 - 26 bits for the level
+
+struct VisitedHash {
+  FrontierCell* cells;
+  unsigned mask;
+  int* split;  // unused
+  __device__ void clear(int tid, int nthreads) const {
+    for (unsigned i = tid; i <= mask; i += nthreads) cells[i] = FrontierCell{kFrontierEmpty, ~0ull};
+  }
+  __device__ void insert_start(unsigned long long key) const { cells[frontier_hash(key) & mask] = FrontierCell{key, 0ull}; }
+  __device__ bool seen_before(unsigned long long key, unsigned long long level_stamp) const {
+    unsigned h = frontier_hash(key) & mask;
+    for (unsigned n = 0; n <= mask; ++n) {
+      const unsigned long long k = cells[h].key;
+      if (k == key) return cells[h].arrival < level_stamp;
+      if (k == kFrontierEmpty) return false;
+      h = (h + 1) & mask;
+    }
+    return false;
+  }
+  __device__ int insert(unsigned long long key, unsigned long long stamp) const {
+    unsigned h = frontier_hash(key) & mask;
+    for (unsigned n = 0; n <= mask; ++n) {
+      unsigned long long k = cells[h].key;
+      if (k == kFrontierEmpty) k = atomicCAS(&cells[h].key, kFrontierEmpty, key);
+      if (k == kFrontierEmpty || k == key) {
+        atomicMin(&cells[h].arrival, stamp);
+        return (int)h;
+      }
+      h = (h + 1) & mask;
+    }
+    return -1;
+  }
+  __device__ bool wins(int handle, unsigned long long, unsigned long long stamp) const { return cells[handle].arrival == stamp; }
+  __device__ bool earlier(unsigned long long key, unsigned long long stamp) const { return seen_before(key, stamp); }
+};
+
+struct VisitedDense {
+  unsigned long long* grid;
+  int r, d;    // radius, edge = 2 r + 1
+  int* split;  // shared flag
+  __device__ void clear(int tid, int nthreads) const {
+    const unsigned n = (unsigned)d * d * d;
+    for (unsigned i = tid; i < n; i += nthreads) grid[i] = ~0ull;
+  }
+  __device__ int index(unsigned long long key) const {
+    return ((key_lattice(key, 2) + r) * d + (key_lattice(key, 1) + r)) * d + (key_lattice(key, 0) + r);
+  }
+  __device__ static unsigned long long pack(unsigned long long stamp, unsigned long long key) { return (stamp << 12) | ((key >> 48) & 0xFFFull); }
+  __device__ void insert_start(unsigned long long key) const { grid[index(key)] = pack(0ull, key); }
+  __device__ bool seen_before(unsigned long long key, unsigned long long level_stamp) const {
+    const unsigned long long e = grid[index(key)];
+    if (e == ~0ull) return false;
+    if ((e & 0xFFFull) != ((key >> 48) & 0xFFFull)) {
+      *split = 1;
+      return false;
+    }
+    return (e >> 12) < level_stamp;
+  }
+  __device__ int insert(unsigned long long key, unsigned long long stamp) const {
+    const int i = index(key);
+    atomicMin(&grid[i], pack(stamp, key));
+    return i;
+  }
+  __device__ bool wins(int handle, unsigned long long key, unsigned long long stamp) const {
+    const unsigned long long e = grid[handle];
+    if ((e & 0xFFFull) != ((key >> 48) & 0xFFFull)) *split = 1;  // another string took this lattice cell in this level
+    return e == pack(stamp, key);
+  }
+  __device__ bool earlier(unsigned long long key, unsigned long long stamp) const { return seen_before(key, stamp); }
+};
+
 constexpr int kFrontierThreads = 1024;
 // slot_eval codes
 constexpr int kSlotNone = -1, kSlotUnknown = -2;
 
+template <bool DENSE>
 __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const FrontierArgs a) {
   __shared__ unsigned s_warp[32];
   __shared__ unsigned s_run, s_total;
-  __shared__ int s_err;
+  __shared__ int s_err, s_split;
   __shared__ unsigned long long s_count, s_sum;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  FrontierCell* const cells = a.cells + (size_t)blockIdx.x * a.cell_cap;
+  typedef typename std::conditional<DENSE, VisitedDense, VisitedHash>::type Visited;
+  Visited vis;
+  if constexpr (DENSE) {
+    const int d = 2 * a.grid_r + 1;
+    vis = VisitedDense{a.grid + (size_t)blockIdx.x * d * d * d, a.grid_r, d, &s_split};
+  } else {
+    vis = VisitedHash{a.cells + (size_t)blockIdx.x * a.cell_cap, a.cell_cap - 1, &s_split};
+  }
   FrontierEntry* cur = a.cur + (size_t)blockIdx.x * a.frontier_cap;
   FrontierEntry* next = a.next + (size_t)blockIdx.x * a.frontier_cap;
   int* const slot_eval = a.slot_eval + (size_t)blockIdx.x * 6 * a.frontier_cap;
-  const unsigned mask = a.cell_cap - 1;
 
   for (int v = blockIdx.x; v < a.n; v += gridDim.x) {
+    if (a.todo && !a.todo[v]) continue;
     const double x0 = a.points[3 * v], y0 = a.points[3 * v + 1], z0 = a.points[3 * v + 2];
-    for (unsigned i = tid; i < a.cell_cap; i += blockDim.x) cells[i] = FrontierCell{kFrontierEmpty, ~0ull};
+    vis.clear(tid, blockDim.x);
     if (tid == 0) {
       s_err = 0;
+      s_split = 0;
       s_count = 0ull;
       s_sum = cell_fingerprint(x0, y0, z0);
     }
@@ -213,14 +313,14 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
       } else {
         const unsigned long long key = fx | fy | fz;
         cur[0] = FrontierEntry{x0, y0, z0, key};
-        cells[frontier_hash(key) & mask] = FrontierCell{key, 0ull};  // visited.insert(convertToString(point))
+        vis.insert_start(key);  // visited.insert(convertToString(point))
       }
     }
     __syncthreads();
     unsigned long long my_count = 0ull, my_sum = 0ull;
-    for (unsigned level = 1; n_cur > 0 && s_err == 0; ++level) {
+    for (unsigned level = 1; n_cur > 0 && s_err == 0 && s_split == 0; ++level) {
       const unsigned n_slots = 6u * n_cur;
-      const unsigned long long stamp0 = (unsigned long long)level << 32;
+      const unsigned long long stamp0 = (unsigned long long)level << kStampSlotBits;
       // ---- expand: every (entry, direction) of this level
       for (unsigned s = tid; s < n_slots; s += blockDim.x) {
         const FrontierEntry e = cur[s / 6u];
@@ -237,25 +337,19 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
         const int lattice = key_lattice(key, axis) + ((d & 1u) ? -1 : 1);
         unsigned long long f = 0;
         bool ok = lattice > -32768 && lattice < 32767 && axis_fields(axis, cv, lattice, v0, a.vs, &f);
+        if (DENSE && ok && (lattice < -a.grid_r || lattice > a.grid_r)) {
+          s_split = 1;  // outside the cube (cannot happen for R = floor(max_distance / vs) + 2): let the hash set do this vertex
+          ok = false;
+        }
         key = (key & ~key_axis_mask(axis)) | f;
         if (axis != 0 && e.x == 0.0) key &= ~(1ull << 57);
         if (axis != 1 && e.y == 0.0) key &= ~(1ull << 58);
         if (axis != 2 && e.z == 0.0) key &= ~(1ull << 59);
         if (!ok) {
-          s_err = 2;
+          if (!(DENSE && s_split)) s_err = 2;
         } else {
           // visited.find(...) as of the previous levels (same-level arrivals are arbitrated below)
-          bool seen = false;
-          unsigned h = frontier_hash(key) & mask;
-          for (unsigned n = 0; n <= mask; ++n) {
-            const unsigned long long k = cells[h].key;
-            if (k == key) {
-              seen = cells[h].arrival < stamp0;
-              break;
-            }
-            if (k == kFrontierEmpty) break;
-            h = (h + 1) & mask;
-          }
+          const bool seen = vis.seen_before(key, stamp0);
           if (!seen) {
             const double dx = __dsub_rn(cx, x0), dy = __dsub_rn(cy, y0), dz = __dsub_rn(cz, z0);
             const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
@@ -266,20 +360,11 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
                 ev = kSlotUnknown;
               } else if (st == 1u) {
                 // insert or find, earliest arrival wins
-                unsigned hh = frontier_hash(key) & mask;
-                bool placed = false;
-                for (unsigned n = 0; n <= mask; ++n) {
-                  unsigned long long k = cells[hh].key;
-                  if (k == kFrontierEmpty) k = atomicCAS(&cells[hh].key, kFrontierEmpty, key);
-                  if (k == kFrontierEmpty || k == key) {
-                    atomicMin(&cells[hh].arrival, stamp0 | s);
-                    ev = (int)hh;
-                    placed = true;
-                    break;
-                  }
-                  hh = (hh + 1) & mask;
+                ev = vis.insert(key, stamp0 | s);
+                if (ev < 0) {
+                  ev = kSlotNone;
+                  s_err = 1;
                 }
-                if (!placed) s_err = 1;
               }
             }
           }
@@ -305,31 +390,19 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
             cx = __dadd_rn(e.x, axis == 0 ? step : 0.0);
             cy = __dadd_rn(e.y, axis == 1 ? step : 0.0);
             cz = __dadd_rn(e.z, axis == 2 ? step : 0.0);
+            // the candidate's key, as in the expand pass
+            key = e.key;
+            const double cv = axis == 0 ? cx : (axis == 1 ? cy : cz), v0 = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
+            unsigned long long f = 0;
+            axis_fields(axis, cv, key_lattice(key, axis) + ((d & 1u) ? -1 : 1), v0, a.vs, &f);
+            key = (key & ~key_axis_mask(axis)) | f;
+            if (axis != 0 && e.x == 0.0) key &= ~(1ull << 57);
+            if (axis != 1 && e.y == 0.0) key &= ~(1ull << 58);
+            if (axis != 2 && e.z == 0.0) key &= ~(1ull << 59);
             if (ev >= 0) {
-              win = cells[ev].arrival == (stamp0 | s);
-              key = cells[ev].key;
-            } else {
-              // unknown neighbour: counted unless an earlier slot of this level inserted this very key
-              key = e.key;
-              const double cv = axis == 0 ? cx : (axis == 1 ? cy : cz), v0 = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
-              unsigned long long f = 0;
-              axis_fields(axis, cv, key_lattice(key, axis) + ((d & 1u) ? -1 : 1), v0, a.vs, &f);
-              key = (key & ~key_axis_mask(axis)) | f;
-              if (axis != 0 && e.x == 0.0) key &= ~(1ull << 57);
-              if (axis != 1 && e.y == 0.0) key &= ~(1ull << 58);
-              if (axis != 2 && e.z == 0.0) key &= ~(1ull << 59);
-              bool earlier = false;
-              unsigned h = frontier_hash(key) & mask;
-              for (unsigned n = 0; n <= mask; ++n) {
-                const unsigned long long k = cells[h].key;
-                if (k == key) {
-                  earlier = cells[h].arrival < (stamp0 | s);
-                  break;
-                }
-                if (k == kFrontierEmpty) break;
-                h = (h + 1) & mask;
-              }
-              if (!earlier) ++my_count;
+              win = vis.wins(ev, key, stamp0 | s);
+            } else if (!vis.earlier(key, stamp0 | s)) {
+              ++my_count;  // unknown neighbour: counted unless an earlier slot of this level inserted this very key
             }
           }
         }
@@ -382,7 +455,7 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
       a.frontier_voxels[v] = s_count;
       if (a.visited) a.visited[v] = n_visited;
       if (a.checksum) a.checksum[v] = s_sum;
-      a.status[v] = s_err;
+      a.status[v] = s_err ? s_err : (s_split ? 3 : 0);
     }
     __syncthreads();
   }

@@ -138,6 +138,7 @@ struct nbvgpu_ctx {
   PinBuf h_io;                             // pinned staging for n-sized inputs / outputs
   DevBuf d_pos, d_per_yaw, d_gain, d_yaw, d_counts, d_steps, d_seg, d_free, d_aux, d_best;
   DevBuf d_fr_cells, d_fr_cur, d_fr_next, d_fr_slots, d_fr_io;  // History::bfs workspaces (nbvgpu_frontier_potential)
+  unsigned long long stats_frontier_hash_redo = 0;              // vertices the dense visited set handed to the hash set
   nbvgpu_stats stats{};
   int variant = 0;
   int sm_count = 148;
@@ -1151,23 +1152,28 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double
   size_t cell_cap = 1024;
   while (cell_cap < cells_bound + cells_bound / 2) cell_cap <<= 1;  // load factor <= 2/3 even if every cell of the sphere is visited
   if (cell_cap > (1ull << 30)) return fail(ctx, NBVGPU_ERR_CAPACITY, "max_distance / voxel_size too large for the visited set");
-  const size_t n_ctas = std::min<size_t>(n, (size_t)ctx->sm_count);
-  std::vector<int> h_status(n);
-  std::vector<unsigned long long> h_count(n), h_visited(n), h_sum(n);
+  // dense visited set: one 8-byte word per lattice cell of the cube of radius R (the default; a vertex that meets a
+  // split key is redone with the hash set)
+  const int grid_r = (int)R;
+  const size_t grid_d = 2 * (size_t)grid_r + 1, grid_words = grid_d * grid_d * grid_d;
+  const bool use_dense = grid_words * 8 <= (64ull << 20) && getenv("NBVGPU_FRONTIER_HASH") == nullptr;
+  size_t n_ctas = std::min<size_t>(n, (size_t)ctx->sm_count);
+  if (use_dense) n_ctas = std::max<size_t>(1, std::min<size_t>(n_ctas, (4ull << 30) / (grid_words * 8)));
+  std::vector<int> h_status(n, 0), h_todo(n, 1);
+  std::vector<unsigned long long> h_count(n, 0), h_visited(n, 0), h_sum(n, 0);
   // a level of the fill is a surface: 16 (R + 2)^2 entries cover it with a wide margin; a fill that needs
-  // more reports it and the call is repeated once with room for every cell
+  // more reports it and is repeated once with room for every cell
   size_t frontier_cap = std::min<size_t>(cells_bound, std::max<size_t>(4096, (size_t)(16.0 * (R + 2.0) * (R + 2.0))));
+  const size_t io_bytes = n * (24 + 8 + 8 + 8 + 4 + 4) + 64;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    CK(ctx->d_fr_cells.reserve(n_ctas * cell_cap * sizeof(FrontierCell)));
+    if (6 * frontier_cap >= (1ull << kStampSlotBits)) return fail(ctx, NBVGPU_ERR_CAPACITY, "max_distance / voxel_size too large for the flood fill");
     CK(ctx->d_fr_cur.reserve(n_ctas * frontier_cap * sizeof(FrontierEntry)));
     CK(ctx->d_fr_next.reserve(n_ctas * frontier_cap * sizeof(FrontierEntry)));
     CK(ctx->d_fr_slots.reserve(n_ctas * frontier_cap * 6 * sizeof(int)));
-    CK(ctx->d_fr_io.reserve(n * (24 + 8 + 8 + 8 + 4) + 64));
-    CK(ctx->h_io.reserve(n * (24 + 8 + 8 + 8 + 4) + 64, false));
+    CK(ctx->d_fr_io.reserve(io_bytes));
+    CK(ctx->h_io.reserve(io_bytes, false));
     char* h = ctx->h_io.as<char>();
-    memcpy(h, points, n * 24);
     char* d = ctx->d_fr_io.as<char>();
-    CK(cudaMemcpyAsync(d, h, n * 24, cudaMemcpyHostToDevice, ctx->stream));
     FrontierArgs a;
     a.L = L->view();
     a.points = reinterpret_cast<const double*>(d);
@@ -1175,11 +1181,14 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double
     a.visited = reinterpret_cast<unsigned long long*>(d + n * 32);
     a.checksum = reinterpret_cast<unsigned long long*>(d + n * 40);
     a.status = reinterpret_cast<int*>(d + n * 48);
-    a.cells = ctx->d_fr_cells.as<FrontierCell>();
+    a.todo = reinterpret_cast<const int*>(d + n * 52);
+    a.cells = nullptr;
+    a.grid = nullptr;
     a.cur = ctx->d_fr_cur.as<FrontierEntry>();
     a.next = ctx->d_fr_next.as<FrontierEntry>();
     a.slot_eval = ctx->d_fr_slots.as<int>();
     a.cell_cap = (unsigned)cell_cap;
+    a.grid_r = grid_r;
     a.frontier_cap = (unsigned)frontier_cap;
     a.vs = vs;
     a.max_distance = max_distance;
@@ -1193,19 +1202,54 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double
     a.voxel_size_inv = (float)(1.0 / (double)L->voxel_size);
     a.vps = L->vps;
     a.n = (int)n;
-    k_frontier_bfs<<<(unsigned)n_ctas, kFrontierThreads, 0, ctx->stream>>>(a);
-    CK(cudaGetLastError());
-    ctx->stats.kernel_launches++;
-    CK(cudaMemcpyAsync(h + n * 24, d + n * 24, n * 28, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    memcpy(h_count.data(), h + n * 24, n * 8);
-    memcpy(h_visited.data(), h + n * 32, n * 8);
-    memcpy(h_sum.data(), h + n * 40, n * 8);
-    memcpy(h_status.data(), h + n * 48, n * 4);
+    // pass 0: dense set on everything still to do; pass 1: hash set on what the dense pass handed back (status 3)
+    for (int pass = use_dense ? 0 : 1; pass < 2; ++pass) {
+      bool any = false;
+      for (size_t i = 0; i < n; ++i) any = any || h_todo[i];
+      if (!any) break;
+      memcpy(h, points, n * 24);
+      memcpy(h + n * 52, h_todo.data(), n * 4);
+      CK(cudaMemcpyAsync(d, h, n * 24, cudaMemcpyHostToDevice, ctx->stream));
+      CK(cudaMemcpyAsync(d + n * 52, h + n * 52, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+      if (pass == 0) {
+        CK(ctx->d_fr_cells.reserve(n_ctas * grid_words * 8));
+        a.grid = ctx->d_fr_cells.as<unsigned long long>();
+        k_frontier_bfs<true><<<(unsigned)n_ctas, kFrontierThreads, 0, ctx->stream>>>(a);
+      } else {
+        CK(ctx->d_fr_cells.reserve(n_ctas * cell_cap * sizeof(FrontierCell)));
+        a.cells = ctx->d_fr_cells.as<FrontierCell>();
+        k_frontier_bfs<false><<<(unsigned)n_ctas, kFrontierThreads, 0, ctx->stream>>>(a);
+      }
+      CK(cudaGetLastError());
+      ctx->stats.kernel_launches++;
+      CK(cudaMemcpyAsync(h + n * 24, d + n * 24, n * 28, cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      const unsigned long long* r_count = reinterpret_cast<const unsigned long long*>(h + n * 24);
+      const unsigned long long* r_vis = reinterpret_cast<const unsigned long long*>(h + n * 32);
+      const unsigned long long* r_sum = reinterpret_cast<const unsigned long long*>(h + n * 40);
+      const int* r_status = reinterpret_cast<const int*>(h + n * 48);
+      for (size_t i = 0; i < n; ++i) {
+        if (!h_todo[i]) continue;
+        h_status[i] = r_status[i];
+        if (r_status[i] == 2) return fail(ctx, NBVGPU_ERR_RANGE, "flood fill left the representable key range");
+        if (r_status[i] == 0) {
+          h_count[i] = r_count[i];
+          h_visited[i] = r_vis[i];
+          h_sum[i] = r_sum[i];
+          h_todo[i] = 0;
+        } else if (r_status[i] == 3 && pass == 0) {
+          ctx->stats_frontier_hash_redo++;
+        }
+      }
+      if (pass == 0) {  // the hash pass takes the split vertices only; overflowed ones wait for the next attempt
+        for (size_t i = 0; i < n; ++i) h_todo[i] = h_todo[i] && h_status[i] == 3;
+      }
+    }
+    // what is left overflowed its frontier arrays
     bool overflow = false;
     for (size_t i = 0; i < n; ++i) {
-      if (h_status[i] == 2) return fail(ctx, NBVGPU_ERR_RANGE, "flood fill left the representable key range");
-      if (h_status[i] == 1) overflow = true;
+      h_todo[i] = h_status[i] == 1;
+      overflow = overflow || h_todo[i];
     }
     if (!overflow) break;
     if (attempt == 1 || frontier_cap == cells_bound) return fail(ctx, NBVGPU_ERR_CAPACITY, "flood-fill workspace exhausted");
@@ -1218,6 +1262,15 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double
     if (visited_cells) visited_cells[i] = h_visited[i];
     if (cells_checksum) cells_checksum[i] = h_sum[i];
   }
+  return NBVGPU_OK;
+}
+
+// Number of vertices (since context creation) that the dense visited set handed back to the hash set because a
+// lattice cell appeared under two different strings; for tests.
+int nbvgpu_debug_frontier_hash_redo(nbvgpu_ctx* ctx, uint64_t* out) {
+  if (!ctx || !out) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  *out = ctx->stats_frontier_hash_redo;
   return NBVGPU_OK;
 }
 

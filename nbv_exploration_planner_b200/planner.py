@@ -291,6 +291,12 @@ class NbvGpu:
                                                    _vp(vis), _vp(chk)))
         return {"gain": gain, "frontier_voxels": fv, "visited": vis, "cells_checksum": chk}
 
+    def frontier_hash_redo(self) -> int:
+        """vertices the dense visited set of the flood fill handed back to the hash-keyed one (tests)."""
+        out = C.c_uint64(0)
+        self._ck(self._L.nbvgpu_debug_frontier_hash_redo(self._h, C.byref(out)))
+        return int(out.value)
+
     # -- introspection -----------------------------------------------------------------------
     def stats(self) -> dict:
         s = N.Stats()

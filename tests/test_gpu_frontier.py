@@ -49,6 +49,7 @@ def test_cfg1_map_full_radius(oracle_mod, cfg1_map):
     c = synth.make_candidates(cfg1_map.cfg, 6, None)
     ro, rg = _compare(o, lt_o, g, lt_g, c.positions)
     assert ro["visited"].min() > 50000
+    assert g.frontier_hash_redo() == 0        # ordinary vertices stay on the dense visited set
     g.close()
 
 
@@ -100,6 +101,8 @@ def test_negative_zero_and_tiny_negative_coordinates(oracle_mod):
     assert ro["visited"].min() > 1000
     # the quirk is observable here: from -0.0 the origin cell is entered twice and its unknown neighbour counted twice
     assert ro["frontier_voxels"][0] == ro["frontier_voxels"][1] + 1 and ro["visited"][0] == ro["visited"][1] + 1
+    # ... and those starts really took the exact hash-keyed path: one lattice cell under two strings
+    assert g.frontier_hash_redo() >= 3
     g.close()
 
 
@@ -127,3 +130,19 @@ def test_empty_map_and_errors(oracle_mod):
     with pytest.raises(NbvGpuError):
         g.frontier_potential(lt_g, [[0.0, 0.0, 0.0]], max_distance=1e6)
     g.close()
+
+
+def test_hash_and_dense_visited_sets_agree(oracle_mod, tiny_map, monkeypatch):
+    """NBVGPU_FRONTIER_HASH=1 forces the hash-keyed visited set for every vertex: same results as the default."""
+    from nbv_exploration_planner_b200 import synth
+    cam = tiny_map.camera()
+    o, lt_o, _ = load_oracle(oracle_mod, tiny_map, cam)
+    g, lt_g, _ = load_gpu(tiny_map, cam)
+    pts = np.concatenate([synth.make_candidates(tiny_map.cfg, 8, None).positions, _special_points(tiny_map.cfg)])
+    _, dense = _compare(o, lt_o, g, lt_g, pts)
+    monkeypatch.setenv("NBVGPU_FRONTIER_HASH", "1")
+    _, hashed = _compare(o, lt_o, g, lt_g, pts)
+    for k in ("gain", "frontier_voxels", "visited", "cells_checksum"):
+        assert np.array_equal(dense[k], hashed[k])
+    g.close()
+
