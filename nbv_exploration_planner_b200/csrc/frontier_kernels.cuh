@@ -106,7 +106,7 @@ struct FrontierArgs {
   int* slot_eval;
   unsigned cell_cap;      // power of two (hash set)
   unsigned long long* grid;  // dense visited set: workspace of CTA b at grid + b * grid_dim^3
-  int grid_r;                // lattice radius covered: indices -grid_r .. grid_r per axis
+  int grid_r;                // lattice radius covered: indices -grid_r .. grid_r per axis (dense set and canon tables)
   unsigned frontier_cap;
   double vs;              // float voxel size widened (LowResManager::getResolution)
   double max_distance;
@@ -150,18 +150,32 @@ __device__ __forceinline__ unsigned long long key_axis_mask(int a) {
 }
 __device__ __forceinline__ int key_lattice(unsigned long long key, int a) { return (int)((key >> (16 * a)) & 0xFFFFu) - 32768; }
 
-// Fields of one axis for the accumulated coordinate v with lattice index i; false if the variant does not fit
-// (cannot happen for |i| < 2^15 additions; reported, never ignored).
-__device__ __forceinline__ bool axis_fields(int a, double v, int lattice, double v0, double vs, unsigned long long* out) {
-  const unsigned long long mag = dec6_magnitude(v);
-  const double canon = fma((double)lattice, vs, v0);
-  const unsigned long long cmag = dec6_magnitude(canon);
-  if (mag == ~0ull || cmag == ~0ull) return false;
-  const bool neg = v < 0.0 || (v == 0.0 && (__double_as_longlong(v) < 0));
-  const bool cneg = canon < 0.0;
-  const long long s = neg ? -(long long)mag : (long long)mag, cs = cneg ? -(long long)cmag : (long long)cmag;
-  const long long variant = s - cs;
-  if (variant < -3 || variant > 3) return false;
+// Canonical value of lattice index i on one axis: the double an axis-monotone path arrives with, x0 + vs + vs + ...
+// (or + (-vs) ...), i.e. what almost every first arrival holds, and its rounded decimal.  One table per vertex and
+// axis in shared memory, indices -r .. r.
+struct AxisCanon {
+  double value;
+  unsigned long long mag;  // dec6_magnitude(value)
+};
+
+// Fields of one axis for the accumulated coordinate v with lattice index i: the rounding variant is the difference
+// between the exactly rounded v * 10^6 and the canonical one -- zero without any arithmetic when v IS the canonical
+// double (bitwise), computed exactly otherwise.  false if it does not fit (cannot happen: reported, never ignored).
+__device__ __forceinline__ bool axis_fields(int a, double v, int lattice, const AxisCanon* canon, int r, unsigned long long* out) {
+  if (lattice < -r || lattice > r) return false;
+  const AxisCanon c = canon[(size_t)a * (2 * r + 1) + (lattice + r)];
+  const long long vb = __double_as_longlong(v), cb = __double_as_longlong(c.value);
+  const bool neg = vb < 0;  // sign bit: "-0.000000" also for -0.0 and tiny negatives
+  unsigned long long mag = c.mag;
+  long long variant = 0;
+  if (vb != cb) {
+    mag = dec6_magnitude(v);
+    if (mag == ~0ull) return false;
+    const long long sv = neg ? -(long long)mag : (long long)mag, sc = cb < 0 ? -(long long)c.mag : (long long)c.mag;
+    variant = sv - sc;
+    if (variant < -3 || variant > 3) return false;
+  }
+  if (c.mag == ~0ull) return false;
   *out = key_axis_fields(a, lattice, (int)variant, neg && mag == 0ull);
   return true;
 }
@@ -280,6 +294,9 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
   __shared__ unsigned s_run, s_total;
   __shared__ int s_err, s_split;
   __shared__ unsigned long long s_count, s_sum;
+  extern __shared__ __align__(16) unsigned char s_dyn[];
+  AxisCanon* const canon = reinterpret_cast<AxisCanon*>(s_dyn);  // [3][2 r + 1]
+  const int cr = a.grid_r, cd = 2 * a.grid_r + 1;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   typedef typename std::conditional<DENSE, VisitedDense, VisitedHash>::type Visited;
   Visited vis;
@@ -305,9 +322,25 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
     }
     __syncthreads();
     unsigned n_cur = 1, n_visited = 1;
+    // canonical tables: six threads accumulate outwards from the start (sequential adds, as a monotone path does),
+    // then everybody rounds
+    if (tid < 6) {
+      const int axis = tid >> 1;
+      const double step = (tid & 1) ? -a.vs : a.vs;
+      double v = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
+      AxisCanon* t = canon + (size_t)axis * cd + cr;
+      if ((tid & 1) == 0) t[0].value = v;
+      for (int i = 1; i <= cr; ++i) {
+        v = __dadd_rn(v, step);
+        t[(tid & 1) ? -i : i].value = v;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < 3 * cd; i += blockDim.x) canon[i].mag = dec6_magnitude(canon[i].value);
+    __syncthreads();
     if (tid == 0) {
       unsigned long long fx = 0, fy = 0, fz = 0;
-      const bool ok = axis_fields(0, x0, 0, x0, a.vs, &fx) && axis_fields(1, y0, 0, y0, a.vs, &fy) && axis_fields(2, z0, 0, z0, a.vs, &fz);
+      const bool ok = axis_fields(0, x0, 0, canon, cr, &fx) && axis_fields(1, y0, 0, canon, cr, &fy) && axis_fields(2, z0, 0, canon, cr, &fz);
       if (!ok) {
         s_err = 2;
       } else {
@@ -333,10 +366,10 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
         int ev = kSlotNone;
         // key: the moved axis is recomputed; an idle axis keeps its fields unless it was -0.0 (now +0.0)
         unsigned long long key = e.key;
-        const double cv = axis == 0 ? cx : (axis == 1 ? cy : cz), v0 = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
+        const double cv = axis == 0 ? cx : (axis == 1 ? cy : cz);
         const int lattice = key_lattice(key, axis) + ((d & 1u) ? -1 : 1);
         unsigned long long f = 0;
-        bool ok = lattice > -32768 && lattice < 32767 && axis_fields(axis, cv, lattice, v0, a.vs, &f);
+        bool ok = axis_fields(axis, cv, lattice, canon, cr, &f);
         if (DENSE && ok && (lattice < -a.grid_r || lattice > a.grid_r)) {
           s_split = 1;  // outside the cube (cannot happen for R = floor(max_distance / vs) + 2): let the hash set do this vertex
           ok = false;
@@ -392,9 +425,9 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
             cz = __dadd_rn(e.z, axis == 2 ? step : 0.0);
             // the candidate's key, as in the expand pass
             key = e.key;
-            const double cv = axis == 0 ? cx : (axis == 1 ? cy : cz), v0 = axis == 0 ? x0 : (axis == 1 ? y0 : z0);
+            const double cv = axis == 0 ? cx : (axis == 1 ? cy : cz);
             unsigned long long f = 0;
-            axis_fields(axis, cv, key_lattice(key, axis) + ((d & 1u) ? -1 : 1), v0, a.vs, &f);
+            axis_fields(axis, cv, key_lattice(key, axis) + ((d & 1u) ? -1 : 1), canon, cr, &f);
             key = (key & ~key_axis_mask(axis)) | f;
             if (axis != 0 && e.x == 0.0) key &= ~(1ull << 57);
             if (axis != 1 && e.y == 0.0) key &= ~(1ull << 58);

@@ -1156,6 +1156,8 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double
   // split key is redone with the hash set)
   const int grid_r = (int)R;
   const size_t grid_d = 2 * (size_t)grid_r + 1, grid_words = grid_d * grid_d * grid_d;
+  const size_t canon_bytes = 3 * grid_d * sizeof(AxisCanon);  // per-axis canonical values, shared memory
+  if (canon_bytes > (size_t)ctx->max_smem_optin - 1024) return fail(ctx, NBVGPU_ERR_CAPACITY, "max_distance / voxel_size too large for the flood fill");
   const bool use_dense = grid_words * 8 <= (64ull << 20) && getenv("NBVGPU_FRONTIER_HASH") == nullptr;
   size_t n_ctas = std::min<size_t>(n, (size_t)ctx->sm_count);
   if (use_dense) n_ctas = std::max<size_t>(1, std::min<size_t>(n_ctas, (4ull << 30) / (grid_words * 8)));
@@ -1214,11 +1216,13 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double
       if (pass == 0) {
         CK(ctx->d_fr_cells.reserve(n_ctas * grid_words * 8));
         a.grid = ctx->d_fr_cells.as<unsigned long long>();
-        k_frontier_bfs<true><<<(unsigned)n_ctas, kFrontierThreads, 0, ctx->stream>>>(a);
+        if (canon_bytes > 48 * 1024) CK(cudaFuncSetAttribute(k_frontier_bfs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)canon_bytes));
+        k_frontier_bfs<true><<<(unsigned)n_ctas, kFrontierThreads, canon_bytes, ctx->stream>>>(a);
       } else {
         CK(ctx->d_fr_cells.reserve(n_ctas * cell_cap * sizeof(FrontierCell)));
         a.cells = ctx->d_fr_cells.as<FrontierCell>();
-        k_frontier_bfs<false><<<(unsigned)n_ctas, kFrontierThreads, 0, ctx->stream>>>(a);
+        if (canon_bytes > 48 * 1024) CK(cudaFuncSetAttribute(k_frontier_bfs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)canon_bytes));
+        k_frontier_bfs<false><<<(unsigned)n_ctas, kFrontierThreads, canon_bytes, ctx->stream>>>(a);
       }
       CK(cudaGetLastError());
       ctx->stats.kernel_launches++;
