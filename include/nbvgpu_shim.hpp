@@ -4,6 +4,7 @@
 //   double RrtTree::optimized_gain(Pose& state)            nbveplanner/src/rrt.cpp:351
 //   double RrtTree::gain(Pose& state)                      nbveplanner/src/rrt.cpp:481
 //   bool   HighResManager::checkMotion<T>(start, end)      nbveplanner/include/nbveplanner/voxblox_manager.h:89
+//   double History::bfs(const Eigen::Vector3d& point)      nbveplanner/src/history.cpp:103
 // and the bodies become one-line calls into libnbvgpu.so.  No Eigen / ROS / Voxblox headers are
 // needed here: `Pose` is anything indexable with [0..3] (Eigen::Vector4d), `Point` anything with
 // x(), y(), z() (Eigen::Vector3d), `Layer`/`Block` anything with the Voxblox accessors used below.
@@ -115,6 +116,23 @@ inline bool checkMotion(GpuMap& map, double robot_radius, const T& start, const 
   int free_seg = 0;
   check(map.ctx(), nbvgpu_check_motion(map.ctx(), map.esdf_layer(), robot_radius, a, b, &free_seg), "check_motion");
   return free_seg != 0;
+}
+
+/// double History::bfs(const Eigen::Vector3d& point) (history.cpp:103-137): the frontier potential of one vertex,
+/// frontierVoxels * pow(voxel_size, 3.0) on the low-resolution TSDF layer, 6.0 m radius as in the reference.
+template <class T>
+inline double bfs(GpuMap& map, const T& point) {
+  const double p[3] = {point.x(), point.y(), point.z()};
+  double gain = 0.0;
+  check(map.ctx(), nbvgpu_frontier_potential(map.ctx(), map.tsdf_layer(), 1, p, 6.0, &gain, nullptr, nullptr, nullptr), "frontier_potential");
+  return gain;
+}
+
+/// The batched form History::recalculatePotential wants when it sweeps the active vertices (history.cpp:196-222):
+/// potential_gain[i] for points[3 i .. 3 i + 2], one call.
+inline void bfs_batch(GpuMap& map, size_t n, const double* points_xyz, double* potential_gain) {
+  check(map.ctx(), nbvgpu_frontier_potential(map.ctx(), map.tsdf_layer(), n, points_xyz, 6.0, potential_gain, nullptr, nullptr, nullptr),
+        "frontier_potential");
 }
 
 }  // namespace nbvgpu_shim

@@ -25,8 +25,12 @@ int main() {
     Pose s{{1.0, 2.0, 1.0, 0.5}};
     const double g = nbvgpu_shim::optimized_gain(map, s);  // empty map: everything unknown
     const bool free_seg = nbvgpu_shim::checkMotion(map, 0.4, Point{{1, 2, 1}}, Point{{2, 2, 1}});  // unallocated -> collision
-    std::printf("gpu gain=%.9g yaw=%.9g free=%d\n", g, s[3], (int)free_seg);
-    return (g > 0.0 && !free_seg) ? 0 : 3;
+    const double potential = nbvgpu_shim::bfs(map, Point{{1, 2, 1}});  // empty map: the six neighbours are unknown
+    double batch[2] = {0, 0};
+    const double pts[6] = {1, 2, 1, 2, 2, 1};
+    nbvgpu_shim::bfs_batch(map, 2, pts, batch);
+    std::printf("gpu gain=%.9g yaw=%.9g free=%d potential=%.9g\n", g, s[3], (int)free_seg, potential);
+    return (g > 0.0 && !free_seg && potential > 0.0 && batch[0] == potential && batch[1] == potential) ? 0 : 3;
   } catch (const std::exception& e) {
     std::printf("no-device: %s\n", e.what());
     return 42;

@@ -1,9 +1,12 @@
-"""Generates the committed golden vectors under tests/golden/ from the CPU oracle.
+"""Generates the committed golden vectors under tests/golden/.
 
-The reference itself cannot be built or imported here, so the vectors are
-outputs of the oracle restatement (oracle/nbv_oracle.cc) on seeded synthetic inputs; they pin the
-oracle against silent regressions and give the GPU tests a fixture that does not need the oracle
-at run time.  Re-run:  python tests/golden/make_golden.py
+The reference has no build that works here (catkin / ROS) and holds no fixtures for this path (SURVEY.md section
+8c).  The vectors are outputs of the CPU oracle (oracle/nbv_oracle.cc) on seeded synthetic inputs -- the oracle
+itself is pinned bit for bit against the reference's own hot-path sources compiled into oracle/_ref
+(tests/test_ref_pinning.py) -- and, where the reference's own code returns the quantity, outputs of that code
+(`frontier_golden.npz`: `reference_gain` comes from the reference's History::bfs).  They guard the oracle against
+silent regressions and give the GPU tests fixtures that need neither the oracle nor /root/reference at run time.
+Re-run:  python tests/golden/make_golden.py [frontier]
 """
 import os
 import sys
@@ -63,8 +66,39 @@ def golden_voxblox_file(out):
     print("voxblox fixture", len(data), "bytes")
 
 
+def golden_frontier(out):
+    """History::bfs (history.cpp:96-137) on the tiny map: vertices in free / unknown / occupied space, on and outside
+    the bounds; oracle outputs plus the gains of the reference's own bfs (oracle/_ref) when it is built."""
+    from oracle import ref_binding as rb
+    m = synth.make_map("tiny")
+    cfg, cam = m.cfg, m.camera()
+    o = Oracle()
+    lt = o.layer_create(0, m.voxel_size, m.vps)
+    o.layer_update(lt, m.keys, m.tsdf)
+    o.set_camera(cam.as_dict())
+    lo, hi = np.array(cfg.bounds_min, float), np.array(cfg.bounds_max, float)
+    special = np.array([lo + 0.01, hi - 0.01, lo - 0.5, [lo[0], 0.5 * (lo[1] + hi[1]), 1.0], 0.5 * (lo + hi),
+                        [cfg.root[0], cfg.root[1], cfg.root[2]], [1.0, 2.0, 0.5], [3.0, 4.0, 1.0], hi, lo, [-0.0, 4.0, 1.0]])
+    pts = np.concatenate([synth.make_candidates(cfg, 12, None).positions, special])
+    r = o.frontier_potential(lt, pts, 6.0, threads=os.cpu_count())
+    ref_gain = np.zeros(0)
+    if rb.available():
+        ref = rb.Reference(m.voxel_size, m.vps)
+        ref.tsdf_update(m.keys, m.tsdf)
+        ref.set_camera(cam.as_dict(), 0.4)
+        ref_gain = ref.frontier_potential(pts)
+        assert np.array_equal(ref_gain, r["gain"]), "oracle and reference disagree: do not write a golden file"
+    np.savez_compressed(out, map_sha256=m.sha256(), points=pts, max_distance=6.0, gain=r["gain"], frontier_voxels=r["frontier_voxels"],
+                        visited=r["visited"], cells_checksum=r["cells_checksum"], reference_gain=ref_gain)
+    print("frontier golden:", len(pts), "vertices, frontier voxels", r["frontier_voxels"].tolist(), "reference gains recorded:", len(ref_gain) > 0)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "frontier":
+        golden_frontier(os.path.join(HERE, "frontier_golden.npz"))
+        sys.exit(0)
     golden_cfg("cfg1", 100, os.path.join(HERE, "cfg1_golden.npz"))
     golden_cfg("tiny", 16, os.path.join(HERE, "tiny_golden.npz"))
     golden_rays(os.path.join(HERE, "rays_golden.npz"))
     golden_voxblox_file(os.path.join(HERE, "tiny_tsdf_esdf.voxblox"))
+    golden_frontier(os.path.join(HERE, "frontier_golden.npz"))

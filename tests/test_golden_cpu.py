@@ -41,6 +41,18 @@ def test_cfg1_golden_subset(oracle_mod, cfg1_map):
     assert np.array_equal(f["free"], g["seg_free"]) and np.array_equal(f["steps"], g["seg_steps"])
 
 
+def test_frontier_golden(oracle_mod, tiny_map):
+    """History::bfs on the tiny map: the oracle reproduces the committed vectors, whose gains are also the outputs
+    of the reference's own bfs (recorded when oracle/_ref was built at generation time)."""
+    g = np.load(os.path.join(GOLD, "frontier_golden.npz"))
+    assert tiny_map.sha256() == str(g["map_sha256"])
+    o, lt, _ = load_oracle(oracle_mod, tiny_map, tiny_map.camera())
+    r = o.frontier_potential(lt, g["points"], float(g["max_distance"]), threads=4)
+    for k in ("gain", "frontier_voxels", "visited", "cells_checksum"):
+        assert np.array_equal(r[k], g[k]), k
+    assert len(g["reference_gain"]) == len(g["points"]) and np.array_equal(g["reference_gain"], g["gain"])
+
+
 def test_threaded_oracle_equals_single_thread(oracle_mod, tiny_map):
     o, lt, _ = load_oracle(oracle_mod, tiny_map, tiny_map.camera())
     pos = np.load(os.path.join(GOLD, "tiny_golden.npz"))["positions"]

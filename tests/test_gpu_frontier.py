@@ -40,6 +40,20 @@ def test_tiny_map_vertices_everywhere(oracle_mod, tiny_map):
     g.close()
 
 
+def test_against_committed_golden_vectors(tiny_map):
+    """No oracle at run time: tests/golden/frontier_golden.npz (oracle outputs; `reference_gain` = the reference's own
+    History::bfs run when the file was generated)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frontier_golden.npz"))
+    assert tiny_map.sha256() == str(g["map_sha256"])
+    gpu, lt, _ = load_gpu(tiny_map, tiny_map.camera())
+    r = gpu.frontier_potential(lt, g["points"], float(g["max_distance"]))
+    for k in ("gain", "frontier_voxels", "visited", "cells_checksum"):
+        assert np.array_equal(r[k], g[k]), k
+    assert np.array_equal(r["gain"], g["reference_gain"])
+    gpu.close()
+
+
 def test_cfg1_map_full_radius(oracle_mod, cfg1_map):
     """BASELINE config 1 map (0.15 m voxels): ~150 k visited cells per vertex at the reference's 6.0 m."""
     from nbv_exploration_planner_b200 import synth
