@@ -61,6 +61,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def l2_info(g, achieved_gbs):
+    """the same algorithmic bytes normalised by an L2 read peak measured on this box in this run
+    (nbvgpu_probe_l2_read_bandwidth: 128-bit ld.global.cg reads from every SM over a 64 MiB buffer, untimed warm-up
+    pass, 40 timed passes, CUDA events; best of 3).  None if the probe fails."""
+    try:
+        peak = max(g.probe_l2_read_bandwidth(64 << 20, 40) for _ in range(3))
+    except Exception as e:  # measurement extra, never fatal
+        print(f"bench: L2 probe failed: {e}", file=sys.stderr)
+        return None
+    return {"peak": peak, "unit": "GB/s", "frac": achieved_gbs / peak,
+            "peak_source": "measured in this run: 64 MiB buffer, 128-bit L1-bypassing reads, best of 3"}
+
+
 def ncu_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum of the ray-sweep kernel from the committed ncu
     capture (profiles/ncu_traffic.json, written by profiles/summarize_ncu.py), or None."""
@@ -448,6 +461,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": steps_per_launch * ALGO_BYTES_PER_STEP,
                          "avg_launch_ms": kern_ms / max(1, kern_launches),
                          "kernel_share_of_step": kern_ms / dev_ms if dev_ms > 0 else None,
+                         "l2": l2_info(g, ach),
                          "note": "8 B per executed voxel-step (SURVEY.md 8d); the map is L2/L1 resident so real DRAM traffic is far lower"},
             "clocks": clocks,
             "best": winner,

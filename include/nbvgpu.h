@@ -237,6 +237,11 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, const d
  * to a "%f" rounding boundary, or -0.0 against +0.0) and was therefore redone with the exact hash-keyed visited set
  * instead of the dense one; for tests (NBVGPU_FRONTIER_HASH=1 in the environment forces the hash set for all). */
 int nbvgpu_debug_frontier_hash_redo(nbvgpu_ctx* ctx, uint64_t* count);
+/* Measurement infrastructure (SURVEY.md 8 d): read bandwidth of this GPU's L2 in GB/s -- 128-bit ld.global.cg
+ * loads from every SM over a `bytes`-sized buffer (choose it well below the L2 capacity), `iters` timed passes
+ * after an untimed warm-up pass, CUDA events on the context's stream.  Used by bench.py for the L2-normalised
+ * roofline fraction; not part of the planner interface. */
+int nbvgpu_probe_l2_read_bandwidth(nbvgpu_ctx* ctx, size_t bytes, int iters, double* gb_per_s);
 /* Host-only helper for tests: round-half-even of |x| * 10^6, the integer behind "%f" / std::to_string(double),
  * exactly as the flood fill's cell keys compute it.  NBVGPU_ERR_RANGE for non-finite x or |x| >= 2^21. */
 int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude);

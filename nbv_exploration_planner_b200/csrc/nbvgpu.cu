@@ -1278,6 +1278,64 @@ int nbvgpu_debug_frontier_hash_redo(nbvgpu_ctx* ctx, uint64_t* out) {
   return NBVGPU_OK;
 }
 
+// ---- measurement infrastructure: L2 read bandwidth of this GPU -------------------------------
+// SURVEY.md 8(d) / BASELINE.md ask for an L2-normalised roofline fraction next to the HBM one, "using an L2 peak
+// measured on the box" (MEASURED_PEAKS.json has none).  Every thread streams 128-bit ld.global.cg loads (L1
+// bypassed) over a buffer that fits L2; the first pass pulls it in from HBM and is not timed.
+__global__ void __launch_bounds__(256) k_probe_l2_read(const uint4* __restrict__ p, size_t n_vec, int iters, unsigned* sink) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+  for (int it = 0; it < iters; ++it) {
+    size_t i = tid;
+    for (; i + 3 * stride < n_vec; i += 4 * stride) {  // four independent loads in flight per thread
+      const uint4 a = __ldcg(p + i), b = __ldcg(p + i + stride), c = __ldcg(p + i + 2 * stride), d = __ldcg(p + i + 3 * stride);
+      acc.x ^= a.x ^ b.x ^ c.x ^ d.x;
+      acc.y ^= a.y ^ b.y ^ c.y ^ d.y;
+      acc.z ^= a.z ^ b.z ^ c.z ^ d.z;
+      acc.w ^= a.w ^ b.w ^ c.w ^ d.w;
+    }
+    for (; i < n_vec; i += stride) {
+      const uint4 a = __ldcg(p + i);
+      acc.x ^= a.x; acc.y ^= a.y; acc.z ^= a.z; acc.w ^= a.w;
+    }
+  }
+  if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x9E3779B9u) *sink = 1u;  // keeps the loads alive
+}
+
+int nbvgpu_probe_l2_read_bandwidth(nbvgpu_ctx* ctx, size_t bytes, int iters, double* gb_per_s) {
+  if (!ctx || !gb_per_s || bytes < (1u << 20) || iters < 1) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  DeviceGuard guard(ctx->device);
+  const size_t n_vec = bytes / 16;
+  void* buf = nullptr;
+  unsigned* sink = nullptr;
+  CK(cudaMalloc(&buf, n_vec * 16));
+  if (cudaMalloc(&sink, 4) != cudaSuccess) {
+    cudaFree(buf);
+    return fail(ctx, NBVGPU_ERR_CUDA, "cudaMalloc");
+  }
+  cudaMemsetAsync(buf, 0x5A, n_vec * 16, ctx->stream);
+  cudaMemsetAsync(sink, 0, 4, ctx->stream);
+  const unsigned grid = (unsigned)ctx->sm_count * 8u;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_probe_l2_read<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(buf), n_vec, 2, sink);  // warm: HBM -> L2
+  cudaEventRecord(e0, ctx->stream);
+  k_probe_l2_read<<<grid, 256, 0, ctx->stream>>>(reinterpret_cast<const uint4*>(buf), n_vec, iters, sink);
+  cudaEventRecord(e1, ctx->stream);
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  float ms = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(sink);
+  if (e != cudaSuccess || !(ms > 0.f)) return fail(ctx, NBVGPU_ERR_CUDA, "L2 probe failed");
+  *gb_per_s = (double)n_vec * 16.0 * (double)iters / ((double)ms * 1e-3) / 1e9;
+  return NBVGPU_OK;
+}
+
 // Host-only: round_half_even(|x| * 10^6) as the flood fill's cell keys compute it (what "%f" prints); for tests.
 int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude) {
   if (!magnitude) return NBVGPU_ERR_INVALID;

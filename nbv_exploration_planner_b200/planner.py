@@ -291,6 +291,12 @@ class NbvGpu:
                                                    _vp(vis), _vp(chk)))
         return {"gain": gain, "frontier_voxels": fv, "visited": vis, "cells_checksum": chk}
 
+    def probe_l2_read_bandwidth(self, nbytes: int = 32 << 20, iters: int = 50) -> float:
+        """GB/s of 128-bit L1-bypassing reads over an L2-resident buffer (measurement infrastructure)."""
+        out = C.c_double(0.0)
+        self._ck(self._L.nbvgpu_probe_l2_read_bandwidth(self._h, int(nbytes), int(iters), C.byref(out)))
+        return float(out.value)
+
     def frontier_hash_redo(self) -> int:
         """vertices the dense visited set of the flood fill handed back to the hash-keyed one (tests)."""
         out = C.c_uint64(0)
