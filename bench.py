@@ -51,6 +51,17 @@ def parse_args():
     return ap.parse_args()
 
 
+def cpu_model() -> str:
+    """Model name of the host CPU the baseline legs run on (SURVEY.md 8d asks for it next to the core count)."""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -227,7 +238,7 @@ def run_reference(args):
         "config": {"workload": f"{args.config}: {cfg.bounds_max[0]}x{cfg.bounds_max[1]}x{cfg.bounds_max[2]} m synthetic TSDF+ESDF, "
                                f"{cfg.voxel_size} m voxels, {cfg.hfov_deg}x{cfg.vfov_deg} deg, {cfg.far_m} m range, "
                                f"{n_total} candidates with ESDF edge check", "candidates_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": "viewpoints/s", "cores": cores, "kind": ref.kind,
+        "cpu_baseline": {"value": value, "unit": "viewpoints/s", "cores": cores, "cpu_model": cpu_model(), "kind": ref.kind,
                          "sample": f"first {sample} of {n_total} candidates per step, {steps} steps, {cores} host threads "
                                    f"(one reference planner instance per thread)"},
         "e2e": {"value": value, "unit": "viewpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -316,6 +327,13 @@ def run_ours(args):
         pack = np.concatenate([c.positions, c.segments, c.distance[:, None]], 1)
     else:
         pack = np.empty((n_total, 10))
+    import hashlib
+    inputs_sha = None
+    if rank == 0:
+        map_bytes = sum(int(np.asarray(a).nbytes) for a in (m.keys, m.tsdf, m.esdf) if a is not None)
+        inputs_sha = {"candidates": hashlib.sha256(np.ascontiguousarray(pack).tobytes()).hexdigest(),
+                      "map": m.sha256() if map_bytes <= (1 << 30) else f"not hashed ({map_bytes >> 20} MiB)",
+                      "seeds": {"map": cfg.seed_map, "candidates": cfg.seed_cand}}
     pack_t = torch.from_numpy(pack).to(dev)
     if world > 1:
         dist.broadcast(pack_t, 0)
@@ -370,6 +388,7 @@ def run_ours(args):
     launches = st1["kernel_launches"] - st0["kernel_launches"]
     vsteps = st1["voxel_steps"] - st0["voxel_steps"]
     rays = st1["rays"] - st0["rays"]
+    csteps = st1["collision_steps"] - st0["collision_steps"]
 
     # ---- e2e: same step through the host-buffer C ABI (H2D + D2H inside) ---------------------------
     h = mine.cpu().numpy()
@@ -423,12 +442,12 @@ def run_ours(args):
 
     # ---- reduce over ranks (max time) -----------------------------------------------------------
     red = torch.tensor([dev_ms, e2e_s, kern_ms, map_broadcast_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(vsteps), float(rays), float(launches), float(n)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(vsteps), float(rays), float(launches), float(n), float(csteps)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     dev_ms_max, e2e_s_max, kern_ms_max, bcast_ms_max = (float(x) for x in red.cpu())
-    vsteps_all, rays_all, launches_all, n_all = (float(x) for x in tot.cpu())
+    vsteps_all, rays_all, launches_all, n_all, csteps_all = (float(x) for x in tot.cpu())
     clocks = sampler.summary()
 
     if rank == 0:
@@ -449,9 +468,11 @@ def run_ours(args):
                                    f"(radius {cfg.robot_radius:.4f} m, overshoot {cfg.overshoot} m)",
                        "candidates_total": int(n_all), "map_blocks": nb, "l2": "flushed between steps (256 MiB write)",
                        "kernel_variant": args.variant, "parallelism": f"candidates sharded over {world} GPU(s), map replicated",
-                       "map_broadcast_ms_setup": bcast_ms_max, "setup_s": setup_s},
+                       "map_broadcast_ms_setup": bcast_ms_max, "setup_s": setup_s, "inputs_sha256": inputs_sha},
             "rays_per_s": rays_all / (dev_ms_max * 1e-3), "voxel_steps_per_s": vsteps_all / (dev_ms_max * 1e-3),
             "voxel_steps_per_viewpoint": vsteps_all / max(1.0, n_all * args.steps),
+            # every candidate comes with its parent edge (edges/s for config 2); ESDF voxel-steps of checkMotion
+            "edges_per_s": n_all * args.steps / (dev_ms_max * 1e-3), "collision_steps_per_s": csteps_all / (dev_ms_max * 1e-3),
             "value_including_map_broadcast": n_all / ((dev_ms_max / args.steps + bcast_ms_max) * 1e-3),
             "e2e": {"value": n_all * e2e_steps / e2e_s_max, "unit": "viewpoints/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps},
@@ -607,7 +628,7 @@ def cpu_baseline(args, cfg, h_pos, h_seg):
     o, lt, le = load_oracle_ctx(m, cam)
     dtp, stp = time_oracle(o, lt, le, cfg, h_pos[:sample], h_seg[:sample], cores)
     dtp1, _ = time_oracle(o, lt, le, cfg, h_pos[:one], h_seg[:one], 1)
-    return {"value": sample / dta, "unit": "viewpoints/s", "cores": cores, "kind": ref.kind,
+    return {"value": sample / dta, "unit": "viewpoints/s", "cores": cores, "cpu_model": cpu_model(), "kind": ref.kind,
             "sample": f"first {sample} candidates of the same workload, {cores} host threads (one reference planner instance per "
                       f"thread), best of 2",
             "voxel_steps_per_s": (sample / dta) * stp / sample,
