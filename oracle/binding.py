@@ -207,6 +207,29 @@ class Oracle:
             raise RuntimeError(f"nbvo_frontier_potential -> {rc}")
         return {"gain": gain, "frontier_voxels": fv, "visited": vis, "cells_checksum": chk}
 
+    def layer_update_esdf_observed(self, layer: int, keys, dist, observed) -> None:
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        dist = np.ascontiguousarray(dist, np.float32)
+        observed = np.ascontiguousarray(observed, np.uint8)
+        self._l.nbvo_layer_update_esdf_observed.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_float),
+                                                            C.POINTER(C.c_uint8)]
+        rc = self._l.nbvo_layer_update_esdf_observed(self._c, layer, len(keys), _ptr(keys, C.c_int32), _ptr(dist, C.c_float), _ptr(observed, C.c_uint8))
+        if rc != 0:
+            raise RuntimeError(f"nbvo_layer_update_esdf_observed -> {rc}")
+
+    def distance_and_gradient(self, layer: int, positions, threads: int = 1) -> dict:
+        """EsdfMap::getDistanceAndGradientAtPosition (esdf_map.cc:22-52) per query."""
+        pos = np.ascontiguousarray(positions, np.float64).reshape(-1, 3)
+        n = len(pos)
+        ok = np.zeros(n, np.uint8); dist = np.zeros(n); grad = np.zeros((n, 3))
+        self._l.nbvo_distance_and_gradient.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_uint8),
+                                                       C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int]
+        rc = self._l.nbvo_distance_and_gradient(self._c, layer, n, _ptr(pos, C.c_double), _ptr(ok, C.c_uint8), _ptr(dist, C.c_double),
+                                                _ptr(grad, C.c_double), threads)
+        if rc != 0:
+            raise RuntimeError(f"nbvo_distance_and_gradient -> {rc}")
+        return {"ok": ok, "distance": dist, "gradient": grad}
+
     def voxel_status_at(self, layer: int, p) -> int:
         p = np.ascontiguousarray(p, np.float64)
         self._l.nbvo_voxel_status_at.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]

@@ -206,6 +206,7 @@ struct Layer {
   float vps_inv;
   size_t nvox;
   std::unordered_map<Key, std::unique_ptr<float[]>, KeyHash> blocks;  // TSDF: 2 floats/voxel
+  std::unordered_map<Key, std::unique_ptr<uint8_t[]>, KeyHash> observed;  // ESDF: EsdfVoxel::observed (voxel.h:21)
 };
 
 struct Camera {
@@ -509,17 +510,42 @@ int nbvo_layer_update(void* c_, int layer, size_t n, const int32_t* keys, const 
     auto& slot = L.blocks[k];
     if (!slot) slot.reset(new float[per]);
     std::memcpy(slot.get(), data + i * per, per * sizeof(float));
+    if (L.kind == 1) {  // planar ESDF payload carries no flags: a voxel is observed unless its distance is NaN
+      auto& ob = L.observed[k];
+      if (!ob) ob.reset(new uint8_t[L.nvox]);
+      for (size_t v = 0; v < L.nvox; ++v) ob[v] = std::isnan(data[i * per + v]) ? 0 : 1;
+    }
+  }
+  return 0;
+}
+// ESDF blocks with explicit EsdfVoxel::observed flags: dist [n][nvox] floats, obs [n][nvox] bytes
+int nbvo_layer_update_esdf_observed(void* c_, int layer, size_t n, const int32_t* keys, const float* dist, const uint8_t* obs) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  Layer& L = *c->layers.at(layer);
+  if (L.kind != 1) return -3;
+  for (size_t i = 0; i < n; ++i) {
+    const Key k{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]};
+    auto& slot = L.blocks[k];
+    if (!slot) slot.reset(new float[L.nvox]);
+    std::memcpy(slot.get(), dist + i * L.nvox, L.nvox * sizeof(float));
+    auto& ob = L.observed[k];
+    if (!ob) ob.reset(new uint8_t[L.nvox]);
+    for (size_t v = 0; v < L.nvox; ++v) ob[v] = obs[i * L.nvox + v] ? 1 : 0;
   }
   return 0;
 }
 int nbvo_layer_remove(void* c_, int layer, size_t n, const int32_t* keys) {
   Ctx* c = static_cast<Ctx*>(c_);
   Layer& L = *c->layers.at(layer);
-  for (size_t i = 0; i < n; ++i) L.blocks.erase(Key{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]});
+  for (size_t i = 0; i < n; ++i) {
+    L.blocks.erase(Key{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]});
+    L.observed.erase(Key{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]});
+  }
   return 0;
 }
 int nbvo_layer_clear(void* c_, int layer) {
   static_cast<Ctx*>(c_)->layers.at(layer)->blocks.clear();
+  static_cast<Ctx*>(c_)->layers.at(layer)->observed.clear();
   return 0;
 }
 size_t nbvo_layer_num_blocks(void* c_, int layer) {
@@ -567,6 +593,119 @@ int nbvo_check_segments(void* c_, int layer, double radius, size_t n, const doub
     if (steps) steps[i] = st;
   });
   return 0;
+}
+
+// ---- ESDF interpolated distance and gradient ------------------------------------------
+// EsdfMap::getDistanceAndGradientAtPosition (voxblox/src/core/esdf_map.cc:22-52) -> Interpolator<EsdfVoxel>
+// (voxblox/interpolator/interpolator_inl.h): getInterpDistance :318-330 (setIndexes :160-198, getVoxelsAndQVector
+// :224-272, getQVector :200-222, interpMember :447-474) and getGradient :47-77.  All in float.  The two products of
+// interpMember, q * (table * data^T), are summed over the inner index from left to right -- the evaluation order of
+// the Eigen stand-in the pinning build uses (oracle/ref_shim/Eigen/Core); a build against real Eigen may sum them in
+// another order, so values are claimed against the real library within float tolerance only, the success flag and the
+// choice of the eight voxels exactly.
+struct EsdfLookup {
+  const Layer& L;
+  float block_size, block_size_inv, voxel_size_inv;
+  explicit EsdfLookup(const Layer& l) : L(l) {
+    block_size = (float)L.vps * L.voxel_size;                  // layer.h:39 / block.h:39
+    block_size_inv = (float)(1.0 / (double)block_size);        // layer.h:41
+    voxel_size_inv = (float)(1.0 / (double)L.voxel_size);      // layer.h:37, block.h:38
+  }
+  // Block::computeCoordinatesFromVoxelIndex (block.h:90-92): origin_ + getCenterPointFromGridIndex(index, voxel_size_),
+  // the centre being (float(idx) + 0.5) * voxel_size evaluated in double and rounded to float (common.h:188-193)
+  float voxel_centre(int block, int voxel) const {
+    const float origin = (float)block * block_size;            // common.h:196-201
+    const float centre = (float)(((double)(float)voxel + 0.5) * (double)L.voxel_size);
+    return origin + centre;
+  }
+  // Interpolator::getInterpDistance
+  bool interp_distance(const float pos[3], float* distance) const {
+    int b[3], v[3];
+    for (int k = 0; k < 3; ++k) b[k] = (int)grid_index(pos[k], block_size_inv);  // layer.h:128-131
+    if (L.blocks.find(Key{b[0], b[1], b[2]}) == L.blocks.end()) return false;     // setIndexes :165-168
+    for (int k = 0; k < 3; ++k) {
+      const float origin = (float)b[k] * block_size;
+      const int64_t t = grid_index(pos[k] - origin, voxel_size_inv);              // block_inl.h:30-40
+      v[k] = (int)std::max<int64_t>(std::min<int64_t>(t, L.vps - 1), 0);
+      const float centre_offset = pos[k] - voxel_centre(b[k], v[k]);              // :171-172
+      if (centre_offset < 0) {                                                    // :176-184
+        v[k]--;
+        if (v[k] < 0) {
+          b[k]--;
+          v[k] += L.vps;
+        }
+      }
+    }
+    float q[8], data[8];
+    for (int i = 0; i < 8; ++i) {                                                 // getVoxelsAndQVector :232-270
+      if (L.blocks.find(Key{b[0], b[1], b[2]}) == L.blocks.end()) return false;   // the (shifted) home block itself
+      const int off[3] = {(i >> 2) & 1, (i >> 1) & 1, i & 1};                     // columns of the index table :190-195
+      int nb[3], nv[3];
+      for (int k = 0; k < 3; ++k) {
+        nb[k] = b[k];
+        nv[k] = v[k] + off[k];
+        if (nv[k] >= L.vps) {                                                     // :241-249
+          nb[k]++;
+          nv[k] -= L.vps;
+        }
+      }
+      auto it = L.blocks.find(Key{nb[0], nb[1], nb[2]});
+      if (it == L.blocks.end()) return false;
+      if (i == 0) {                                                               // getQVector :205-221
+        float o[3];
+        for (int k = 0; k < 3; ++k) o[k] = (pos[k] - voxel_centre(nb[k], nv[k])) * voxel_size_inv;
+        q[0] = 1.0f; q[1] = o[0]; q[2] = o[1]; q[3] = o[2];
+        q[4] = o[0] * o[1]; q[5] = o[1] * o[2]; q[6] = o[2] * o[0]; q[7] = o[0] * o[1] * o[2];
+      }
+      const size_t lin = (size_t)linear_index(L.vps, nv[0], nv[1], nv[2]);
+      data[i] = it->second.get()[lin];
+      auto ob = L.observed.find(Key{nb[0], nb[1], nb[2]});
+      if (ob == L.observed.end() || !ob->second.get()[lin]) return false;         // utils::isObservedVoxel :266-268
+    }
+    static const float table[8][8] = {{1, 0, 0, 0, 0, 0, 0, 0},  {-1, 0, 0, 0, 1, 0, 0, 0}, {-1, 0, 1, 0, 0, 0, 0, 0}, {-1, 1, 0, 0, 0, 0, 0, 0},
+                                      {1, 0, -1, 0, -1, 0, 1, 0}, {1, -1, -1, 1, 0, 0, 0, 0}, {1, -1, 0, 0, -1, 1, 0, 0},
+                                      {-1, 1, 1, -1, 1, -1, -1, 1}};                // interpMember :460-471
+    float y[8];
+    for (int r = 0; r < 8; ++r) {
+      float acc = table[r][0] * data[0];
+      for (int c = 1; c < 8; ++c) acc = acc + table[r][c] * data[c];
+      y[r] = acc;
+    }
+    float acc = q[0] * y[0];
+    for (int i = 1; i < 8; ++i) acc = acc + q[i] * y[i];
+    *distance = acc;
+    return true;
+  }
+  // Interpolator::getGradient(pos, grad, interpolate = true) :47-77: grad is left partially summed on an early failure
+  bool gradient(const float pos[3], float grad[3]) const {
+    int b[3];
+    for (int k = 0; k < 3; ++k) b[k] = (int)grid_index(pos[k], block_size_inv);
+    if (L.blocks.find(Key{b[0], b[1], b[2]}) == L.blocks.end()) return false;
+    grad[0] = grad[1] = grad[2] = 0.0f;
+    for (int i = 0; i < 3; ++i)
+      for (int sign = -1; sign <= 1; sign += 2) {
+        float p[3] = {pos[0] + 0.0f, pos[1] + 0.0f, pos[2] + 0.0f};                // pos + offset: all three components are added
+        p[i] = pos[i] + (float)sign * L.voxel_size;
+        float d;
+        if (!interp_distance(p, &d)) return false;
+        grad[i] += d * (float)sign;
+      }
+    const float denom = 2 * L.voxel_size;
+    for (int k = 0; k < 3; ++k) grad[k] = grad[k] / denom;
+    return true;
+  }
+};
+
+// one query of EsdfMap::getDistanceAndGradientAtPosition(position, &distance, &gradient), esdf_map.cc:31-52
+inline bool distance_and_gradient(const Layer& L, const double position[3], double* distance, double gradient[3]) {
+  const EsdfLookup E(L);
+  const float pos[3] = {(float)position[0], (float)position[1], (float)position[2]};
+  float d = 0.0f, g[3] = {0.0f, 0.0f, 0.0f};
+  bool success = E.interp_distance(pos, &d);
+  success &= E.gradient(pos, g);  // evaluated whatever the first call returned
+  *distance = (double)d;
+  for (int k = 0; k < 3; ++k) gradient[k] = (double)g[k];
+  return success;
 }
 
 // LowResManager::getVoxelStatus(position) -- voxblox_manager.cpp:73-90: the position is cast to float, the
@@ -666,6 +805,14 @@ int nbvo_frontier_potential(void* c_, int layer, size_t n, const double* points,
     if (frontier_voxels) frontier_voxels[i] = f;
     if (visited) visited[i] = vis;
   });
+  return 0;
+}
+int nbvo_distance_and_gradient(void* c_, int layer, size_t n, const double* positions, uint8_t* ok, double* distance, double* gradient,
+                               int n_threads) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  const Layer& L = *c->layers.at(layer);
+  if (L.kind != 1) return -3;
+  parallel_for(n, n_threads, [&](size_t i) { ok[i] = distance_and_gradient(L, positions + 3 * i, distance + i, gradient + 3 * i) ? 1 : 0; });
   return 0;
 }
 int nbvo_voxel_status_at(void* c_, int layer, const double* p) {

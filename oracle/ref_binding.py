@@ -149,6 +149,25 @@ class Reference:
         self.L.nbvr_voxel_status_at.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         return self.L.nbvr_voxel_status_at(self._c, _p(p, C.c_double))
 
+    def esdf_update_observed(self, keys, esdf, observed) -> None:
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        esdf = np.ascontiguousarray(esdf, np.float32)
+        observed = np.ascontiguousarray(observed, np.uint8)
+        self.L.nbvr_esdf_update_observed.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_uint8)]
+        self.L.nbvr_esdf_update_observed.restype = None
+        self.L.nbvr_esdf_update_observed(self._c, len(keys), _p(keys, C.c_int32), _p(esdf, C.c_float), _p(observed, C.c_uint8))
+
+    def distance_and_gradient(self, positions) -> dict:
+        """The reference's own EsdfMap::getDistanceAndGradientAtPosition (esdf_map.cc:22-52) per query."""
+        pos = np.ascontiguousarray(positions, np.float64).reshape(-1, 3)
+        n = len(pos)
+        ok = np.zeros(n, np.uint8); dist = np.zeros(n); grad = np.zeros((n, 3))
+        self.L.nbvr_distance_and_gradient.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_uint8),
+                                                      C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        self.L.nbvr_distance_and_gradient.restype = None
+        self.L.nbvr_distance_and_gradient(self._c, n, _p(pos, C.c_double), _p(ok, C.c_uint8), _p(dist, C.c_double), _p(grad, C.c_double))
+        return {"ok": ok, "distance": dist, "gradient": grad}
+
     def voxel_status(self, block, voxel) -> int:
         b = np.ascontiguousarray(block, np.int32); v = np.ascontiguousarray(voxel, np.int32)
         return self.L.nbvr_voxel_status(self._c, _p(b, C.c_int32), _p(v, C.c_int32))

@@ -20,3 +20,4 @@ cut nbveplanner/include/nbveplanner/voxblox_manager.h 35 37 voxblox_manager_h_35
 cut nbveplanner/include/nbveplanner/voxblox_manager.h 89 108 voxblox_manager_h_89_108.inc 'template <typename T>'
 cut nbveplanner/src/voxblox_manager.cpp 73 90 voxblox_manager_cpp_73_90.inc 'VoxelStatus LowResManager::getVoxelStatus(const Point &position) const {'
 cut nbveplanner/src/history.cpp 96 137 history_cpp_96_137.inc 'std::string convertToString(const Eigen::Vector3d &vec) {'
+cut voxblox/voxblox/src/core/esdf_map.cc 22 52 esdf_map_cc_22_52.inc 'bool EsdfMap::getDistanceAndGradientAtPosition('

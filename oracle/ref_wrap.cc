@@ -16,7 +16,9 @@
 //     HighResManager::checkCollisionWithRobotAtVoxel (:121-129), getResolution / getVoxelsPerSide
 //     (voxblox_manager.h:35-37), HighResManager::checkMotion<T> (voxblox_manager.h:89-108),
 //     LowResManager::getVoxelStatus (voxblox_manager.cpp:73-90), convertToString + History::bfs
-//     (history.cpp:96-137);
+//     (history.cpp:96-137), EsdfMap::getDistanceAndGradientAtPosition (voxblox/src/core/esdf_map.cc:22-52);
+//   * verbatim as well: voxblox/interpolator/interpolator{,_inl}.h (trilinear interpolation, central-difference
+//     gradient) and voxblox/src/utils/evaluation_utils.cc (isObservedVoxel);
 //   * NOT the reference's: the third-party headers it needs (Eigen, minkindr, glog, protoc output) --
 //     stand-ins under oracle/ref_shim/ restating their published semantics -- and this C glue.
 // Nothing from /root/reference is copied into the repository.
@@ -33,9 +35,24 @@
 #include "nbveplanner/camera_model.h"
 #include "voxblox/core/layer.h"
 #include "voxblox/integrator/integrator_utils.h"
+#include "voxblox/interpolator/interpolator.h"
 
 #define SQ(x) ((x) * (x))            // nbveplanner/include/nbveplanner/rrt.h:22
 #define CUBE(x) ((x) * (x) * (x))    // nbveplanner/include/nbveplanner/rrt.h:23
+
+namespace voxblox {
+// esdf_map.h pulls in Eigen::Ref / pybind conveniences; the two members the planner calls are cut out of esdf_map.cc
+// and compiled inside this skeleton, which only declares what they use.
+class EsdfMap {
+ public:
+  explicit EsdfMap(const Layer<EsdfVoxel>* layer) : interpolator_(layer) {}
+  bool getDistanceAndGradientAtPosition(const Eigen::Vector3d& position, double* distance, Eigen::Vector3d* gradient) const;
+  bool getDistanceAndGradientAtPosition(const Eigen::Vector3d& position, bool interpolate, double* distance,
+                                        Eigen::Vector3d* gradient) const;
+  Interpolator<EsdfVoxel> interpolator_;
+};
+#include "extract/esdf_map_cc_22_52.inc"
+}  // namespace voxblox
 
 namespace nbveplanner {
 
@@ -102,6 +119,7 @@ struct RefCtx {
   nbveplanner::Params params;
   nbveplanner::LowResManager low;
   nbveplanner::History history;
+  std::unique_ptr<voxblox::EsdfMap> esdf_map;
   nbveplanner::HighResManager high;
   nbveplanner::RrtTree tree;
 };
@@ -124,6 +142,7 @@ void* nbvr_create(float tsdf_voxel_size, int tsdf_vps, float esdf_voxel_size, in
   c->high.tsdf_layer_ = c->hires_tsdf.get();
   c->tree.manager_lowres_ = &c->low;
   c->tree.params_ = &c->params;
+  c->esdf_map.reset(new voxblox::EsdfMap(c->esdf.get()));
   c->history.manager_lowres_ = &c->low;
   c->history.params_ = &c->params;
   return c;
@@ -151,6 +170,19 @@ void nbvr_esdf_update(void* c_, size_t n, const int32_t* keys, const float* data
   for (size_t i = 0; i < n; ++i) {
     auto block = c->esdf->allocateBlockPtrByIndex(voxblox::BlockIndex(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]));
     for (size_t v = 0; v < nvox; ++v) block->getVoxelByLinearIndex(v).distance = data[i * nvox + v];
+  }
+}
+// ESDF blocks with explicit observed flags (EsdfVoxel::observed, voxel.h:21): observed[n][nvox] bytes
+void nbvr_esdf_update_observed(void* c_, size_t n, const int32_t* keys, const float* data, const uint8_t* observed) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  const size_t nvox = c->esdf->voxels_per_side() * c->esdf->voxels_per_side() * c->esdf->voxels_per_side();
+  for (size_t i = 0; i < n; ++i) {
+    auto block = c->esdf->allocateBlockPtrByIndex(voxblox::BlockIndex(keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]));
+    for (size_t v = 0; v < nvox; ++v) {
+      voxblox::EsdfVoxel& vox = block->getVoxelByLinearIndex(v);
+      vox.distance = data[i * nvox + v];
+      vox.observed = observed[i * nvox + v] != 0;
+    }
   }
 }
 void nbvr_tsdf_remove(void* c_, size_t n, const int32_t* keys) {
@@ -249,5 +281,17 @@ void nbvr_frontier_potential(void* c_, size_t n, const double* points, double* g
 int nbvr_voxel_status_at(void* c_, const double* p) {
   const nbveplanner::VoxelStatus s = static_cast<RefCtx*>(c_)->low.getVoxelStatus(nbveplanner::Point(p[0], p[1], p[2]));
   return s == nbveplanner::kUnknown ? 0 : (s == nbveplanner::kFree ? 1 : 2);
+}
+// EsdfMap::getDistanceAndGradientAtPosition (esdf_map.cc:22-52) per query, as History::refineVertexPosition calls it
+// (history.cpp:236): ok[i] = return value, distance[i], gradient[i][3] (written whatever the return value, as there).
+void nbvr_distance_and_gradient(void* c_, size_t n, const double* positions, uint8_t* ok, double* distance, double* gradient) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  for (size_t i = 0; i < n; ++i) {
+    double d = 0.0;
+    Eigen::Vector3d g = Eigen::Vector3d::Zero();
+    ok[i] = c->esdf_map->getDistanceAndGradientAtPosition(Eigen::Vector3d(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]), &d, &g) ? 1 : 0;
+    distance[i] = d;
+    gradient[3 * i] = g.x(); gradient[3 * i + 1] = g.y(); gradient[3 * i + 2] = g.z();
+  }
 }
 }  // extern "C"

@@ -257,3 +257,44 @@ def test_frontier_bfs_negative_zero_coordinates_match_reference():
     # observable in the reference's own result: the -0.0 start counts the unknown neighbour of the origin cell twice
     assert rr[0] != rr[1] and ro["frontier_voxels"][0] == ro["frontier_voxels"][1] + 1
 
+
+def _esdf_observed(m):
+    """EsdfVoxel::observed for a synthetic map: the voxels the TSDF observed (weight > 0), as the ESDF integrator sets it."""
+    return (m.tsdf[..., 1] > 0).astype(np.uint8)
+
+
+def _interp_queries(m, rng, n=4000):
+    vs = float(m.voxel_size)
+    lo, hi = np.array(m.cfg.bounds_min, float), np.array(m.cfg.bounds_max, float)
+    rand = rng.uniform(lo - 0.5, hi + 0.5, (n, 3))
+    centres = (rng.integers(0, 40, (n // 4, 3)) + 0.5) * np.float64(np.float32(vs))        # voxel centres: exact interpolation
+    faces = rng.integers(0, 40, (n // 4, 3)) * np.float64(np.float32(vs))                   # voxel faces / block corners
+    near = centres[: n // 8] + rng.choice([-1e-6, 1e-6, -1e-4, 1e-4], (n // 8, 3))          # either side of a centre
+    return np.concatenate([rand, centres, faces, near, [[0.0, 0.0, 0.0], [-0.0, 1.0, 1.0], lo, hi]])
+
+
+@pytest.mark.parametrize("which", ["tiny", "quarter"])
+def test_esdf_distance_and_gradient_match_reference_interpolator(tiny_map, which):
+    """EsdfMap::getDistanceAndGradientAtPosition (esdf_map.cc:22-52) -> Interpolator (interpolator_inl.h), the
+    reference's own lines compiled against the Eigen stand-in: success flag, distance and gradient -- the partial
+    gradient a failing call leaves behind included -- identical to the oracle's restatement on random queries, voxel
+    centres, voxel / block faces, points either side of a centre and points outside the map.  (The stand-in sums the
+    8-term products left to right; against a real Eigen build the values are only claimed within float tolerance.)"""
+    from nbv_exploration_planner_b200 import synth
+    if which == "tiny":
+        m = tiny_map
+    else:
+        m = synth.make_map(synth.SynthConfig("quarter", (-3, -2, 0), (9, 10, 3), 0.25, 3.0, 8, "pillars", 91, 92, (3.0, 4.0, 1.0), obs_radius=4.0,
+                                             traj_points=4, traj_step=2.5, vicinity=3.0))
+    obs = _esdf_observed(m)
+    o = ob.Oracle()
+    le = o.layer_create(1, m.voxel_size, m.vps)
+    o.layer_update_esdf_observed(le, m.keys, m.esdf, obs)
+    r = rb.Reference(m.voxel_size, m.vps)
+    r.esdf_update_observed(m.keys, m.esdf, obs)
+    q = _interp_queries(m, np.random.default_rng(17))
+    ro, rr = o.distance_and_gradient(le, q, threads=8), r.distance_and_gradient(q)
+    assert np.array_equal(ro["ok"], rr["ok"])
+    assert np.array_equal(ro["distance"], rr["distance"]) and np.array_equal(ro["gradient"], rr["gradient"])
+    assert 0.1 < ro["ok"].mean() < 0.95 and np.abs(ro["gradient"][ro["ok"] == 1]).max() > 0.5   # both outcomes, real gradients
+
