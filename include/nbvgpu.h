@@ -11,6 +11,8 @@
  *   HighResManager::checkMotion<T>        nbveplanner/include/nbveplanner/voxblox_manager.h:89-108
  *                                                                           -> nbvgpu_check_segments*, nbvgpu_check_motion
  *   History::bfs(point)                   nbveplanner/src/history.cpp:96-137 -> nbvgpu_frontier_potential
+ *   HighResManager::getDistanceAndGradientAtPosition   nbveplanner/src/voxblox_manager.cpp:143-148
+ *                                                                           -> nbvgpu_esdf_distance_gradient
  *   VoxbloxManager::getVoxelStatusByIndex nbveplanner/src/voxblox_manager.cpp:14-33 (map read side)
  *   voxblox::Layer<VoxelType> block hash  voxblox/voxblox/include/voxblox/core/layer.h:23-296,
  *                                         core/block_hash.h:20-31           -> nbvgpu_layer_* (GPU mirror)
@@ -216,6 +218,21 @@ int nbvgpu_check_segments_device(nbvgpu_ctx* ctx, int esdf_layer, double robot_r
 /* n = 1 shim: *free_out = checkMotion(start, end). */
 int nbvgpu_check_motion(nbvgpu_ctx* ctx, int esdf_layer, double robot_radius, const double start[3],
                         const double end[3], int* free_out);
+
+/* ---- ESDF interpolated distance and gradient -----------------------------
+ * HighResManager::getDistanceAndGradientAtPosition(pos, &distance, &grad) (nbveplanner/src/voxblox_manager.cpp:143-148,
+ * called by History::refineVertexPosition, history.cpp:235) = EsdfMap::getDistanceAndGradientAtPosition
+ * (voxblox/src/core/esdf_map.cc:22-52): trilinear interpolation over the eight observed voxels whose centres
+ * surround the position and a central-difference gradient from six more interpolations at +-voxel_size
+ * (voxblox/interpolator/interpolator_inl.h:47-77,160-330,447-474), in float.  ok[i] = the reference's return value;
+ * distance[i] / gradient[i][3] are written in every case, exactly as the reference leaves them (0 / the partial
+ * sums of a failing gradient).  The ESDF layer keeps EsdfVoxel::observed per voxel: bit 0 of the flags byte in
+ * NBVGPU_PACK_VOXBLOX payloads (block.cc:203-234); a NBVGPU_PACK_PLANAR voxel is observed unless its distance is NaN.
+ * Values: the reference sums its two 8-term float products inside Eigen; this library sums them left to right, so
+ * against a real Eigen build values agree to float rounding (a few ulp of the largest voxel distance), the ok flag
+ * and the choice of voxels exactly.  Host buffers. */
+int nbvgpu_esdf_distance_gradient(nbvgpu_ctx* ctx, int esdf_layer, size_t n, const double* positions /* [n][3] */,
+                                  uint8_t* ok /* [n] */, double* distance /* [n] */, double* gradient /* [n][3] */);
 
 /* ---- history-graph frontier potential ----------------------------------
  * History::bfs(point) (nbveplanner/src/history.cpp:96-137) as History::recalculatePotential calls it per

@@ -204,24 +204,38 @@ __global__ void k_scatter_tsdf(const void* __restrict__ payload, const int* __re
   if (active && (pair & 7) == 0) status[(size_t)slot * (nvox >> 4) + (pair >> 3)] = bits;
 }
 
-// ESDF payload -> float distance tile.  One thread per 4 voxels.  VOXBLOX = 2 x u32 per voxel
-// (distance bits, parent|flags: block.cc:203-234); the flags are not consulted by checkMotion.
+// ESDF payload -> float distance tile + 1 bit per voxel "observed" (EsdfVoxel::observed, voxel.h:21; the flag the
+// interpolator's isObservedVoxel reads).  One thread per 4 voxels, 8 threads per 32-voxel word of the bit tile.
+// VOXBLOX = 2 x u32 per voxel (distance bits, parent | flags with observed in bit 0: block.cc:203-234); the planar
+// convenience packing carries no flags: a voxel is observed unless its distance is NaN.  checkMotion reads the
+// distances only.
 template <int PACKING>
-__global__ void k_scatter_esdf(const void* __restrict__ payload, const int* __restrict__ slots, float* tiles, int nvox) {
+__global__ void k_scatter_esdf(const void* __restrict__ payload, const int* __restrict__ slots, float* tiles, uint32_t* observed, int nvox) {
   const int b = blockIdx.y;
   const int slot = slots[b];
   const int quad = blockIdx.x * blockDim.x + threadIdx.x;
   const int nquads = nvox >> 2;
-  if (quad >= nquads || slot < 0) return;
-  float4 v;
-  if (PACKING == 0) {
-    v = __ldg(reinterpret_cast<const float4*>(payload) + (size_t)b * nquads + quad);
-  } else {
-    const uint4* src = reinterpret_cast<const uint4*>(payload) + ((size_t)b * nquads + quad) * 2;
-    const uint4 a = __ldg(src), c = __ldg(src + 1);
-    v = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(c.x), __uint_as_float(c.z));
+  const bool active = quad < nquads && slot >= 0;
+  uint32_t bits = 0u;
+  if (active) {
+    float4 v;
+    if (PACKING == 0) {
+      v = __ldg(reinterpret_cast<const float4*>(payload) + (size_t)b * nquads + quad);
+      bits = (isnan(v.x) ? 0u : 1u) | (isnan(v.y) ? 0u : 2u) | (isnan(v.z) ? 0u : 4u) | (isnan(v.w) ? 0u : 8u);
+    } else {
+      const uint4* src = reinterpret_cast<const uint4*>(payload) + ((size_t)b * nquads + quad) * 2;
+      const uint4 a = __ldg(src), c = __ldg(src + 1);
+      v = make_float4(__uint_as_float(a.x), __uint_as_float(a.z), __uint_as_float(c.x), __uint_as_float(c.z));
+      bits = (a.y & 1u) | ((a.w & 1u) << 1) | ((c.y & 1u) << 2) | ((c.w & 1u) << 3);
+    }
+    reinterpret_cast<float4*>(tiles + (size_t)slot * nvox)[quad] = v;
   }
-  reinterpret_cast<float4*>(tiles + (size_t)slot * nvox)[quad] = v;
+  // layers have 4, 8, 16 or 32 voxels per side: whole 32-voxel words, 8 consecutive threads each
+  bits <<= (quad & 7) * 4;
+  bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+  bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+  bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
+  if (active && (quad & 7) == 0) observed[(size_t)slot * (nvox >> 5) + (quad >> 3)] = bits;
 }
 
 // Layer::getVoxelPtrByGlobalIndex (layer.h:215-239) + getVoxelStatusByIndex for test read-back.

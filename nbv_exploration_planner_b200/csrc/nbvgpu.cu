@@ -20,6 +20,7 @@
 #include "camera_host.h"
 #include "gain_kernels.cuh"
 #include "frontier_kernels.cuh"
+#include "interp_kernels.cuh"
 #include "map_mirror.cuh"
 #include "voxblox_io.h"
 
@@ -237,12 +238,12 @@ int apply_update_device(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const int32_t* 
       k_scatter_tsdf<1><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float2*)L->d_tiles, L->d_status, L->nvox);
   } else {
     const int per = L->nvox / 4;
-    const int tpb = per < 256 ? per : 256;
+    const int tpb = per < 256 ? ((per + 31) / 32) * 32 : 256;  // whole warps: the observed bits are combined by shuffles
     dim3 grid((per + tpb - 1) / tpb, (unsigned)n);
     if (packing == NBVGPU_PACK_PLANAR)
-      k_scatter_esdf<0><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float*)L->d_tiles, L->nvox);
+      k_scatter_esdf<0><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float*)L->d_tiles, L->d_status, L->nvox);
     else
-      k_scatter_esdf<1><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float*)L->d_tiles, L->nvox);
+      k_scatter_esdf<1><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float*)L->d_tiles, L->d_status, L->nvox);
   }
   ctx->stats.kernel_launches++;
   ctx->stats.blocks_uploaded += n;
@@ -606,6 +607,11 @@ int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, si
     const size_t sbytes = (size_t)(L->nvox / 16) * 4;
     ok = ok && cudaMalloc(&L->d_status, sbytes * (max_blocks + 1)) == cudaSuccess;
     ok = ok && cudaMemsetAsync((char*)L->d_status + sbytes * max_blocks, 0, sbytes, ctx->stream) == cudaSuccess;
+  } else {
+    // ESDF: the same array holds EsdfVoxel::observed, 1 bit per voxel (the interpolator needs it; checkMotion does not)
+    const size_t sbytes = (size_t)((L->nvox + 31) / 32) * 4;
+    ok = ok && cudaMalloc(&L->d_status, sbytes * (max_blocks + 1)) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(L->d_status, 0, sbytes * (max_blocks + 1), ctx->stream) == cudaSuccess;
   }
   ok = ok && cudaMalloc(&L->d_free_list, sizeof(int) * max_blocks) == cudaSuccess;
   ok = ok && cudaMalloc(&L->d_free_top, sizeof(int) * 2) == cudaSuccess;
@@ -1129,6 +1135,46 @@ int nbvgpu_check_motion(nbvgpu_ctx* ctx, int layer, double radius, const double 
   const int rc = nbvgpu_check_segments(ctx, layer, radius, 1, seg, &f);
   if (rc) return rc;
   *free_out = f;
+  return NBVGPU_OK;
+}
+
+// ---- EsdfMap::getDistanceAndGradientAtPosition (esdf_map.cc:22-52), batched ---------------------
+int nbvgpu_esdf_distance_gradient(nbvgpu_ctx* ctx, int layer, size_t n, const double* positions, uint8_t* ok, double* distance,
+                                  double* gradient) {
+  if (!ctx || (n && (!positions || !ok || !distance || !gradient))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_ESDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
+  if (n == 0) return NBVGPU_OK;
+  const double vs_inv = 1.0 / (double)L->voxel_size;
+  for (size_t i = 0; i < 3 * n; ++i)
+    if (!(std::fabs(positions[i] * vs_inv) < 4194000.0)) return fail(ctx, NBVGPU_ERR_RANGE, "position non-finite or out of range");
+  DeviceGuard guard(ctx->device);
+  const size_t in_bytes = n * 24, out_bytes = n * (1 + 8 + 24);
+  CK(ctx->h_io.reserve(in_bytes + out_bytes + 64, false));
+  CK(ctx->d_aux.reserve(in_bytes + out_bytes + 64));
+  char* h = ctx->h_io.as<char>();
+  char* d = ctx->d_aux.as<char>();
+  memcpy(h, positions, in_bytes);
+  CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  EsdfView E;
+  E.L = L->view();
+  E.voxel_size = L->voxel_size;
+  E.block_size = L->voxel_size * (float)L->vps;               // layer.h:39
+  E.block_size_inv = (float)(1.0 / (double)E.block_size);      // layer.h:41
+  E.voxel_size_inv = (float)(1.0 / (double)L->voxel_size);     // layer.h:37
+  E.vps = L->vps;
+  double* d_dist = reinterpret_cast<double*>(d + in_bytes);
+  double* d_grad = d_dist + n;
+  uint8_t* d_ok = reinterpret_cast<uint8_t*>(d_grad + 3 * n);
+  k_esdf_distance_gradient<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(E, reinterpret_cast<const double*>(d), (int)n, d_ok, d_dist, d_grad);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  CK(cudaMemcpyAsync(h + in_bytes, d + in_bytes, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(distance, h + in_bytes, n * 8);
+  memcpy(gradient, h + in_bytes + n * 8, n * 24);
+  memcpy(ok, h + in_bytes + n * 32, n);
   return NBVGPU_OK;
 }
 

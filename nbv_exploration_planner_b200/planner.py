@@ -279,6 +279,16 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_check_motion(self._h, layer, float(robot_radius), s, e, C.byref(out)))
         return bool(out.value)
 
+    # -- ESDF interpolation (EsdfMap::getDistanceAndGradientAtPosition, esdf_map.cc:22-52) -----
+    def esdf_distance_gradient(self, esdf_layer: int, positions) -> dict:
+        pos = np.ascontiguousarray(positions, np.float64).reshape(-1, 3)
+        n = len(pos)
+        ok = np.zeros(n, np.uint8)
+        dist = np.zeros(n)
+        grad = np.zeros((n, 3))
+        self._ck(self._L.nbvgpu_esdf_distance_gradient(self._h, esdf_layer, n, _vp(pos), _vp(ok), _vp(dist), _vp(grad)))
+        return {"ok": ok, "distance": dist, "gradient": grad}
+
     # -- history-graph frontier potential (History::bfs, history.cpp:96-137) -----------------
     def frontier_potential(self, tsdf_layer: int, points, max_distance: float = 6.0) -> dict:
         """potential gain and frontier-voxel count of each vertex position (the reference hard-codes 6.0 m)."""
@@ -404,6 +414,10 @@ class HighResManager:
 
     def checkMotionBatch(self, segments: np.ndarray) -> np.ndarray:
         return self.gpu.check_segments(self.layer, self.robot_radius, segments)
+
+    def getDistanceAndGradientAtPosition(self, pos):  # voxblox_manager.cpp:143-148 -> (ok, distance, gradient)
+        r = self.gpu.esdf_distance_gradient(self.layer, np.asarray(pos, float).reshape(1, 3))
+        return bool(r["ok"][0]), float(r["distance"][0]), r["gradient"][0]
 
 
 class History:
