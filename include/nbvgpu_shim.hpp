@@ -5,6 +5,7 @@
 //   double RrtTree::gain(Pose& state)                      nbveplanner/src/rrt.cpp:481
 //   bool   HighResManager::checkMotion<T>(start, end)      nbveplanner/include/nbveplanner/voxblox_manager.h:89
 //   double History::bfs(const Eigen::Vector3d& point)      nbveplanner/src/history.cpp:103
+//   bool   HighResManager::getDistanceAndGradientAtPosition(pos, &distance, &grad)   nbveplanner/src/voxblox_manager.cpp:143
 // and the bodies become one-line calls into libnbvgpu.so.  No Eigen / ROS / Voxblox headers are
 // needed here: `Pose` is anything indexable with [0..3] (Eigen::Vector4d), `Point` anything with
 // x(), y(), z() (Eigen::Vector3d), `Layer`/`Block` anything with the Voxblox accessors used below.
@@ -116,6 +117,20 @@ inline bool checkMotion(GpuMap& map, double robot_radius, const T& start, const 
   int free_seg = 0;
   check(map.ctx(), nbvgpu_check_motion(map.ctx(), map.esdf_layer(), robot_radius, a, b, &free_seg), "check_motion");
   return free_seg != 0;
+}
+
+/// bool HighResManager::getDistanceAndGradientAtPosition(const Point& pos, double* distance, Eigen::Vector3d* grad)
+/// (voxblox_manager.cpp:143-148 -> EsdfMap, esdf_map.cc:22-52): the outputs are written in every case, as there.
+template <class P, class G>
+inline bool getDistanceAndGradientAtPosition(GpuMap& map, const P& pos, double* distance, G* grad) {
+  const double p[3] = {pos.x(), pos.y(), pos.z()};
+  uint8_t ok = 0;
+  double g[3] = {0.0, 0.0, 0.0};
+  check(map.ctx(), nbvgpu_esdf_distance_gradient(map.ctx(), map.esdf_layer(), 1, p, &ok, distance, g), "esdf_distance_gradient");
+  (*grad)[0] = g[0];
+  (*grad)[1] = g[1];
+  (*grad)[2] = g[2];
+  return ok != 0;
 }
 
 /// double History::bfs(const Eigen::Vector3d& point) (history.cpp:103-137): the frontier potential of one vertex,

@@ -15,6 +15,7 @@ struct Point {
   double x() const { return v[0]; }
   double y() const { return v[1]; }
   double z() const { return v[2]; }
+  double& operator[](int i) { return v[i]; }
 };
 
 int main() {
@@ -29,8 +30,14 @@ int main() {
     double batch[2] = {0, 0};
     const double pts[6] = {1, 2, 1, 2, 2, 1};
     nbvgpu_shim::bfs_batch(map, 2, pts, batch);
-    std::printf("gpu gain=%.9g yaw=%.9g free=%d potential=%.9g\n", g, s[3], (int)free_seg, potential);
-    return (g > 0.0 && !free_seg && potential > 0.0 && batch[0] == potential && batch[1] == potential) ? 0 : 3;
+    double dist = -1.0;
+    Point grad{{9, 9, 9}};
+    const bool interp_ok = nbvgpu_shim::getDistanceAndGradientAtPosition(map, Point{{1, 2, 1}}, &dist, &grad);  // no block: false, outputs 0
+    std::printf("gpu gain=%.9g yaw=%.9g free=%d potential=%.9g interp=%d\n", g, s[3], (int)free_seg, potential, (int)interp_ok);
+    return (g > 0.0 && !free_seg && potential > 0.0 && batch[0] == potential && batch[1] == potential && !interp_ok && dist == 0.0 &&
+            grad.v[0] == 0.0)
+               ? 0
+               : 3;
   } catch (const std::exception& e) {
     std::printf("no-device: %s\n", e.what());
     return 42;

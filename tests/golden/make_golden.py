@@ -4,9 +4,10 @@ The reference has no build that works here (catkin / ROS) and holds no fixtures 
 8c).  The vectors are outputs of the CPU oracle (oracle/nbv_oracle.cc) on seeded synthetic inputs -- the oracle
 itself is pinned bit for bit against the reference's own hot-path sources compiled into oracle/_ref
 (tests/test_ref_pinning.py) -- and, where the reference's own code returns the quantity, outputs of that code
-(`frontier_golden.npz`: `reference_gain` comes from the reference's History::bfs).  They guard the oracle against
+(`frontier_golden.npz`: `reference_gain` comes from the reference's History::bfs; `interp_golden.npz`: `reference_*`
+come from the reference's interpolator, compiled against the Eigen stand-in -- see its summation-order caveat).  They guard the oracle against
 silent regressions and give the GPU tests fixtures that need neither the oracle nor /root/reference at run time.
-Re-run:  python tests/golden/make_golden.py [frontier]
+Re-run:  python tests/golden/make_golden.py [frontier | interp]
 """
 import os
 import sys
@@ -93,12 +94,44 @@ def golden_frontier(out):
     print("frontier golden:", len(pts), "vertices, frontier voxels", r["frontier_voxels"].tolist(), "reference gains recorded:", len(ref_gain) > 0)
 
 
+def golden_interp(out):
+    """EsdfMap::getDistanceAndGradientAtPosition (esdf_map.cc:22-52) on the tiny map with observed = "the TSDF saw this
+    voxel": random queries, voxel centres, faces; oracle outputs plus the reference interpolator's own (oracle/_ref)."""
+    from oracle import ref_binding as rb
+    m = synth.make_map("tiny")
+    obs = (m.tsdf[..., 1] > 0).astype(np.uint8)
+    o = Oracle()
+    le = o.layer_create(1, m.voxel_size, m.vps)
+    o.layer_update_esdf_observed(le, m.keys, m.esdf, obs)
+    rng = np.random.default_rng(31)
+    vs = float(np.float32(m.voxel_size))
+    lo, hi = np.array(m.cfg.bounds_min, float), np.array(m.cfg.bounds_max, float)
+    q = np.concatenate([rng.uniform(lo - 0.3, hi + 0.3, (600, 3)), (rng.integers(0, 40, (150, 3)) + 0.5) * vs, rng.integers(0, 40, (150, 3)) * vs,
+                        [[0.0, 0.0, 0.0], lo, hi, [100.0, 0.0, 0.0]]])
+    r = o.distance_and_gradient(le, q, threads=os.cpu_count())
+    ref_ok, ref_d, ref_g = np.zeros(0, np.uint8), np.zeros(0), np.zeros((0, 3))
+    if rb.available():
+        ref = rb.Reference(m.voxel_size, m.vps)
+        ref.esdf_update_observed(m.keys, m.esdf, obs)
+        rr = ref.distance_and_gradient(q)
+        assert np.array_equal(rr["ok"], r["ok"]) and np.array_equal(rr["distance"], r["distance"]) and np.array_equal(rr["gradient"], r["gradient"]), \
+            "oracle and reference disagree: do not write a golden file"
+        ref_ok, ref_d, ref_g = rr["ok"], rr["distance"], rr["gradient"]
+    np.savez_compressed(out, map_sha256=m.sha256(), positions=q, ok=r["ok"], distance=r["distance"], gradient=r["gradient"],
+                        reference_ok=ref_ok, reference_distance=ref_d, reference_gradient=ref_g)
+    print("interp golden:", len(q), "queries,", int(r["ok"].sum()), "succeed; reference outputs recorded:", len(ref_ok) > 0)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "frontier":
         golden_frontier(os.path.join(HERE, "frontier_golden.npz"))
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "interp":
+        golden_interp(os.path.join(HERE, "interp_golden.npz"))
         sys.exit(0)
     golden_cfg("cfg1", 100, os.path.join(HERE, "cfg1_golden.npz"))
     golden_cfg("tiny", 16, os.path.join(HERE, "tiny_golden.npz"))
     golden_rays(os.path.join(HERE, "rays_golden.npz"))
     golden_voxblox_file(os.path.join(HERE, "tiny_tsdf_esdf.voxblox"))
     golden_frontier(os.path.join(HERE, "frontier_golden.npz"))
+    golden_interp(os.path.join(HERE, "interp_golden.npz"))

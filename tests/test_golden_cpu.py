@@ -53,6 +53,21 @@ def test_frontier_golden(oracle_mod, tiny_map):
     assert len(g["reference_gain"]) == len(g["points"]) and np.array_equal(g["reference_gain"], g["gain"])
 
 
+def test_interp_golden(oracle_mod, tiny_map):
+    """ESDF interpolated distance / gradient on the tiny map: the oracle reproduces the committed vectors, which are also
+    the outputs of the reference's own interpolator (recorded when oracle/_ref was built at generation time)."""
+    g = np.load(os.path.join(GOLD, "interp_golden.npz"))
+    assert tiny_map.sha256() == str(g["map_sha256"])
+    o = oracle_mod.Oracle()
+    le = o.layer_create(1, tiny_map.voxel_size, tiny_map.vps)
+    o.layer_update_esdf_observed(le, tiny_map.keys, tiny_map.esdf, (tiny_map.tsdf[..., 1] > 0).astype(np.uint8))
+    r = o.distance_and_gradient(le, g["positions"], threads=4)
+    for k in ("ok", "distance", "gradient"):
+        assert np.array_equal(r[k], g[k]), k
+        assert np.array_equal(g["reference_" + k], g[k]), k
+    assert 100 < int(g["ok"].sum()) < len(g["ok"]) - 100
+
+
 def test_threaded_oracle_equals_single_thread(oracle_mod, tiny_map):
     o, lt, _ = load_oracle(oracle_mod, tiny_map, tiny_map.camera())
     pos = np.load(os.path.join(GOLD, "tiny_golden.npz"))["positions"]

@@ -69,6 +69,24 @@ def test_tiny_map_random_and_structured_queries(oracle_mod, tiny_map, packing):
     g.close()
 
 
+def test_against_committed_golden_vectors(tiny_map):
+    """No oracle at run time: tests/golden/interp_golden.npz (oracle outputs == the reference interpolator's own,
+    recorded when the file was generated)."""
+    import os
+    from nbv_exploration_planner_b200 import LAYER_ESDF, PACK_VOXBLOX, NbvGpu
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "interp_golden.npz"))
+    assert tiny_map.sha256() == str(gold["map_sha256"])
+    g = NbvGpu(0)
+    le = g.layer_create(LAYER_ESDF, tiny_map.voxel_size, tiny_map.vps, len(tiny_map.keys) + 8)
+    g.layer_update(le, tiny_map.keys, esdf_words(tiny_map.esdf, flags=_observed(tiny_map).astype(np.uint32)), PACK_VOXBLOX)
+    g.commit()
+    r = g.esdf_distance_gradient(le, gold["positions"])
+    for k in ("ok", "distance", "gradient"):
+        assert np.array_equal(r[k], gold[k]), k
+        assert np.array_equal(r[k], gold["reference_" + k]), k
+    g.close()
+
+
 def test_cfg1_map(oracle_mod, cfg1_map):
     o, le_o, g, le_g = _setup(oracle_mod, cfg1_map)
     ro, _ = _compare(o, le_o, g, le_g, _queries(cfg1_map, np.random.default_rng(29), 20000))
