@@ -20,12 +20,16 @@
 // reference's OWN SOURCE instead: oracle/_ref/libnbv_ref.so (oracle/Makefile `ref`, oracle/ref_wrap.cc)
 // compiles the reference's integrator_utils.cc and camera_model.cpp verbatim, its Voxblox core headers,
 // and the bodies of RrtTree::optimized_gain / gain, getVoxelStatusByIndex, checkCollisionWithRobotAtVoxel
-// and checkMotion cut out of rrt.cpp / voxblox_manager.{h,cpp} by line range, against stand-ins for the
+// and checkMotion cut out of rrt.cpp / voxblox_manager.{h,cpp} by line range, and -- for the widened rows --
+// LowResManager::getVoxelStatus, History::bfs (history.cpp:96-137), EsdfMap::getDistanceAndGradientAtPosition
+// (esdf_map.cc:22-52) with the interpolator headers and evaluation_utils.cc verbatim, against stand-ins for the
 // third-party headers only (oracle/ref_shim/).  tests/test_ref_pinning.py compares this file with that
 // library bit for bit (ray index sequences incl. the degenerate ones, index math, hash, per-yaw planes /
-// camera positions / far-plane points, gains and yaws, edge verdicts, voxel status, the cfg-1 goldens).
+// camera positions / far-plane points, gains and yaws, edge verdicts, voxel status, the cfg-1 goldens, flood-fill
+// gains incl. the -0.0 string quirk, interpolated distances and gradients incl. the partial sums of failures).
 // What stays an assumption is the arithmetic of the un-vendored, un-pinned third-party libraries (Eigen's
-// dot / normalized / quaternion evaluation order, minkindr's compose / inverse): it is restated once in
+// dot / normalized / quaternion evaluation order, the summation order of the interpolator's two fixed-size float
+// products, minkindr's compose / inverse): it is restated once in
 // the stand-ins and once in the "Eigen semantics" section below, as single switchable functions.
 //
 // Eigen / minkindr are third-party dependencies that are NOT vendored under /root/reference
