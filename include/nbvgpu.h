@@ -233,6 +233,10 @@ int nbvgpu_check_motion(nbvgpu_ctx* ctx, int esdf_layer, double robot_radius, co
  * and the choice of voxels exactly.  Host buffers. */
 int nbvgpu_esdf_distance_gradient(nbvgpu_ctx* ctx, int esdf_layer, size_t n, const double* positions /* [n][3] */,
                                   uint8_t* ok /* [n] */, double* distance /* [n] */, double* gradient /* [n][3] */);
+/* Same with device-resident buffers: stream-ordered on the context's stream, no copies, no synchronisation.  Positions are
+ * not validated by the host here: a non-finite or out-of-range position gives ok = 0 and zero outputs. */
+int nbvgpu_esdf_distance_gradient_device(nbvgpu_ctx* ctx, int esdf_layer, size_t n, const double* d_positions,
+                                         uint8_t* d_ok, double* d_distance, double* d_gradient);
 
 /* ---- history-graph frontier potential ----------------------------------
  * History::bfs(point) (nbveplanner/src/history.cpp:96-137) as History::recalculatePotential calls it per

@@ -35,8 +35,9 @@ __device__ __forceinline__ float esdf_voxel_centre(const EsdfView& E, int block,
 }
 __device__ __forceinline__ int esdf_grid_index(float v, float inv) { return (int)floorf(__fadd_rn(__fmul_rn(v, inv), 1e-6f)); }
 
-// Interpolator::getInterpDistance
-__device__ bool esdf_interp_distance(const EsdfView& E, float px, float py, float pz, float* distance) {
+// Interpolator::getInterpDistance.  Inlined seven times per query on purpose: ncu shows instruction-fetch stalls for
+// that, but the out-of-line version measured 18 % slower (0.300 vs 0.254 ms per million queries, device-resident).
+__device__ __forceinline__ bool esdf_interp_distance(const EsdfView& E, float px, float py, float pz, float* distance) {
   const float pos[3] = {px, py, pz};
   int b[3], v[3];
 #pragma unroll
@@ -119,6 +120,15 @@ __global__ void __launch_bounds__(128) k_esdf_distance_gradient(EsdfView E, cons
   if (i >= n) return;
   const float px = __double2float_rn(positions[3 * i]), py = __double2float_rn(positions[3 * i + 1]), pz = __double2float_rn(positions[3 * i + 2]);
   float d = 0.0f, g[3] = {0.0f, 0.0f, 0.0f};
+  // device-resident inputs are not validated by the host: a non-finite or out-of-range position fails like a position
+  // outside the map (the host entry point rejects such input with NBVGPU_ERR_RANGE instead)
+  const float lim = 4194000.0f * E.voxel_size;
+  if (!(fabsf(px) < lim) || !(fabsf(py) < lim) || !(fabsf(pz) < lim)) {
+    ok[i] = 0;
+    distance[i] = 0.0;
+    gradient[3 * i] = gradient[3 * i + 1] = gradient[3 * i + 2] = 0.0;
+    return;
+  }
   bool success = esdf_interp_distance(E, px, py, pz, &d);
   // getGradient: needs the block that contains the position, then six interpolations at +-voxel_size
   bool gok = probe_block(E.L, esdf_grid_index(px, E.block_size_inv), esdf_grid_index(py, E.block_size_inv), esdf_grid_index(pz, E.block_size_inv)) >= 0;

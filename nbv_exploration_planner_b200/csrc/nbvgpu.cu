@@ -1139,6 +1139,17 @@ int nbvgpu_check_motion(nbvgpu_ctx* ctx, int layer, double radius, const double 
 }
 
 // ---- EsdfMap::getDistanceAndGradientAtPosition (esdf_map.cc:22-52), batched ---------------------
+static EsdfView esdf_view_of(const LayerHost* L) {
+  EsdfView E;
+  E.L = L->view();
+  E.voxel_size = L->voxel_size;
+  E.block_size = L->voxel_size * (float)L->vps;               // layer.h:39
+  E.block_size_inv = (float)(1.0 / (double)E.block_size);      // layer.h:41
+  E.voxel_size_inv = (float)(1.0 / (double)L->voxel_size);     // layer.h:37
+  E.vps = L->vps;
+  return E;
+}
+
 int nbvgpu_esdf_distance_gradient(nbvgpu_ctx* ctx, int layer, size_t n, const double* positions, uint8_t* ok, double* distance,
                                   double* gradient) {
   if (!ctx || (n && (!positions || !ok || !distance || !gradient))) return NBVGPU_ERR_INVALID;
@@ -1157,13 +1168,7 @@ int nbvgpu_esdf_distance_gradient(nbvgpu_ctx* ctx, int layer, size_t n, const do
   char* d = ctx->d_aux.as<char>();
   memcpy(h, positions, in_bytes);
   CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  EsdfView E;
-  E.L = L->view();
-  E.voxel_size = L->voxel_size;
-  E.block_size = L->voxel_size * (float)L->vps;               // layer.h:39
-  E.block_size_inv = (float)(1.0 / (double)E.block_size);      // layer.h:41
-  E.voxel_size_inv = (float)(1.0 / (double)L->voxel_size);     // layer.h:37
-  E.vps = L->vps;
+  const EsdfView E = esdf_view_of(L);
   double* d_dist = reinterpret_cast<double*>(d + in_bytes);
   double* d_grad = d_dist + n;
   uint8_t* d_ok = reinterpret_cast<uint8_t*>(d_grad + 3 * n);
@@ -1175,6 +1180,22 @@ int nbvgpu_esdf_distance_gradient(nbvgpu_ctx* ctx, int layer, size_t n, const do
   memcpy(distance, h + in_bytes, n * 8);
   memcpy(gradient, h + in_bytes + n * 8, n * 24);
   memcpy(ok, h + in_bytes + n * 32, n);
+  return NBVGPU_OK;
+}
+
+// device-resident buffers, stream-ordered, no synchronisation
+int nbvgpu_esdf_distance_gradient_device(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_positions, uint8_t* d_ok, double* d_distance,
+                                         double* d_gradient) {
+  if (!ctx || (n && (!d_positions || !d_ok || !d_distance || !d_gradient))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_ESDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
+  if (n == 0) return NBVGPU_OK;
+  if (n > 0x7fffffffull) return fail(ctx, NBVGPU_ERR_INVALID, "too many queries for one call");
+  DeviceGuard guard(ctx->device);
+  k_esdf_distance_gradient<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(esdf_view_of(L), d_positions, (int)n, d_ok, d_distance, d_gradient);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
   return NBVGPU_OK;
 }
 

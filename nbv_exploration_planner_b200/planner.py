@@ -289,6 +289,10 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_esdf_distance_gradient(self._h, esdf_layer, n, _vp(pos), _vp(ok), _vp(dist), _vp(grad)))
         return {"ok": ok, "distance": dist, "gradient": grad}
 
+    def esdf_distance_gradient_device(self, esdf_layer: int, n: int, d_positions, d_ok, d_distance, d_gradient) -> None:
+        """device-resident buffers (anything _vp accepts: torch tensors, raw pointers); stream-ordered, no synchronisation"""
+        self._ck(self._L.nbvgpu_esdf_distance_gradient_device(self._h, esdf_layer, n, _vp(d_positions), _vp(d_ok), _vp(d_distance), _vp(d_gradient)))
+
     # -- history-graph frontier potential (History::bfs, history.cpp:96-137) -----------------
     def frontier_potential(self, tsdf_layer: int, points, max_distance: float = 6.0) -> dict:
         """potential gain and frontier-voxel count of each vertex position (the reference hard-codes 6.0 m)."""

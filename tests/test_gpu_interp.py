@@ -126,6 +126,30 @@ def test_linear_field_and_voxel_centres(oracle_mod):
     g.close()
 
 
+def test_device_pointer_entry_point(oracle_mod, tiny_map):
+    """nbvgpu_esdf_distance_gradient_device: torch tensors in HBM, stream-ordered; same results as the host entry point,
+    and non-finite / out-of-range positions (which the host entry point rejects) fail with zero outputs."""
+    import torch
+    o, le_o, g, le_g = _setup(oracle_mod, tiny_map)
+    q = _queries(tiny_map, np.random.default_rng(41), 3000)
+    want = g.esdf_distance_gradient(le_g, q)
+    stream = torch.cuda.Stream()
+    g.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        bad = np.array([[float("nan"), 0.0, 0.0], [float("inf"), 1.0, 1.0], [1e9, 0.0, 0.0]])
+        d_q = torch.from_numpy(np.concatenate([q, bad])).cuda()
+        n = d_q.shape[0]
+        d_ok = torch.full((n,), 7, dtype=torch.uint8, device="cuda")
+        d_dist = torch.full((n,), -1.0, dtype=torch.float64, device="cuda")
+        d_grad = torch.full((n, 3), -1.0, dtype=torch.float64, device="cuda")
+        g.esdf_distance_gradient_device(le_g, n, d_q, d_ok, d_dist, d_grad)
+        stream.synchronize()
+    ok, dist, grad = d_ok.cpu().numpy(), d_dist.cpu().numpy(), d_grad.cpu().numpy()
+    assert np.array_equal(ok[:-3], want["ok"]) and np.array_equal(dist[:-3], want["distance"]) and np.array_equal(grad[:-3], want["gradient"])
+    assert not ok[-3:].any() and not dist[-3:].any() and not grad[-3:].any()
+    g.close()
+
+
 def test_failures_and_errors(oracle_mod, tiny_map):
     from nbv_exploration_planner_b200 import LAYER_ESDF, LAYER_TSDF, NbvGpu, NbvGpuError
     o, le_o, g, le_g = _setup(oracle_mod, tiny_map)
