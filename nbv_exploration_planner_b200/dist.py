@@ -8,6 +8,9 @@ evaluation itself.  Two small exchanges surround it:
   * ``broadcast_blocks``  -- once per planning step rank 0 packs the changed blocks (keys + tile
     payload) into one device buffer and broadcasts it; every rank applies it with the same
     insert/scatter kernels (``nbvgpu_layer_update_device``), so the replicas stay identical.
+  * ``gather_sharded``    -- the widened rows (history-graph vertices for the frontier potential, positions for the
+    ESDF interpolation) shard the same way: every rank evaluates a contiguous block of the batch against its replica
+    and the per-item results are all-gathered back into batch order; again no collective on the evaluation itself.
   * ``gather_best``       -- each rank reduces its shard to one {score, global index, gain, yaw}
     record on the device (``nbvgpu_gain_eval_best_device``); the 32-byte records are all-gathered
     and every rank picks the winner with the reference's tie-break (first strict maximum in
@@ -80,6 +83,29 @@ def broadcast_blocks(keys: Optional[np.ndarray], payload: Optional[np.ndarray], 
     d_keys = buf[:, :3].contiguous().view(torch.int32)
     d_payload = buf[:, 3:].contiguous()
     return n, d_keys, d_payload
+
+
+def gather_sharded(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+    """All-gather per-item results of a batch that was split with ``shard_bounds``.
+
+    `local`: this rank's results, shape [hi - lo, ...] for (lo, hi) = shard_bounds(n_total, world, rank), on the device
+    the process group works on.  Returns the results of the whole batch in batch order, shape [n_total, ...], on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local
+    rank = dist.get_rank(group)
+    per = (n_total + world - 1) // world
+    lo, hi = shard_bounds(n_total, world, rank)
+    assert local.shape[0] == hi - lo, (local.shape, lo, hi)
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)   # equal-sized pieces
+    pad[: hi - lo] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    pieces = []
+    for r in range(world):
+        rlo, rhi = shard_bounds(n_total, world, r)
+        pieces.append(out[r * per: r * per + (rhi - rlo)])
+    return torch.cat(pieces, 0)
 
 
 def _pick(records) -> dict:

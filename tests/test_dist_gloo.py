@@ -128,6 +128,63 @@ def test_world_size_2_matches_single_process(oracle_mod):
     assert int(want[0]) >= 0
 
 
+def _worker_sharded(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nbv_exploration_planner_b200 import dist as nd
+    from nbv_exploration_planner_b200 import synth
+    from oracle.binding import Oracle
+    m = synth.make_map("tiny")          # every rank holds a replica (the broadcast itself is covered above)
+    cfg = m.cfg
+    o = Oracle()
+    lt = o.layer_create(0, cfg.voxel_size, cfg.vps)
+    le = o.layer_create(1, cfg.voxel_size, cfg.vps)
+    o.layer_update(lt, m.keys, m.tsdf)
+    o.layer_update_esdf_observed(le, m.keys, m.esdf, (m.tsdf[..., 1] > 0).astype(np.uint8))
+    o.set_camera(m.camera().as_dict())
+    pts = synth.make_candidates(cfg, 11, None).positions      # 11 over 2 ranks: uneven shards (6 + 5)
+    lo, hi = nd.shard_bounds(len(pts), world, rank)
+    f = o.frontier_potential(lt, pts[lo:hi], 6.0)
+    g = o.distance_and_gradient(le, pts[lo:hi])
+    gain = nd.gather_sharded(torch.from_numpy(f["gain"]), len(pts))
+    grad = nd.gather_sharded(torch.from_numpy(g["gradient"]), len(pts))          # a [n][3] result
+    ok = nd.gather_sharded(torch.from_numpy(g["ok"]), len(pts))
+    q.put((rank, gain.numpy(), grad.numpy(), ok.numpy()))
+    dist.destroy_process_group()
+
+
+def test_sharded_vertices_and_queries_gather_in_batch_order(oracle_mod):
+    """The widened rows shard like the candidates: world_size 2 over gloo, uneven shards, results back in batch order
+    on every rank and equal to the single-process evaluation (the oracle stands in for the GPU evaluator)."""
+    from nbv_exploration_planner_b200 import synth
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    m = synth.make_map("tiny")
+    o = oracle_mod.Oracle()
+    lt = o.layer_create(0, m.voxel_size, m.vps)
+    le = o.layer_create(1, m.voxel_size, m.vps)
+    o.layer_update(lt, m.keys, m.tsdf)
+    o.layer_update_esdf_observed(le, m.keys, m.esdf, (m.tsdf[..., 1] > 0).astype(np.uint8))
+    o.set_camera(m.camera().as_dict())
+    pts = synth.make_candidates(m.cfg, 11, None).positions
+    want_f = o.frontier_potential(lt, pts, 6.0)["gain"]
+    want_g = o.distance_and_gradient(le, pts)
+    for rank, gain, grad, ok in res:
+        assert np.array_equal(gain, want_f) and np.array_equal(grad, want_g["gradient"]) and np.array_equal(ok, want_g["ok"])
+    assert want_f.min() > 0 and len(set(want_f.tolist())) > 3 and np.ptp(want_g["gradient"], 0).max() > 0.1   # not a trivial gather
+
+
 def test_shard_bounds_cover_everything():
     from nbv_exploration_planner_b200.dist import shard_bounds
     for n in (0, 1, 7, 1000, 10001):
