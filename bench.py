@@ -40,7 +40,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2")
+    ap.add_argument("--config", default="cfg2", help="cfg1..cfg5 (BASELINE.json configurations; cfg2 is the headline), or one of the "
+                    "side measurements: frontier (History::bfs), interp (ESDF interpolation), shipped (the reference's shipped geometry)")
+    ap.add_argument("--map", default="cfg1", help="map of the frontier / interp side measurements")
     ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU (default: the config's)")
     ap.add_argument("--variant", type=int, default=0, help="gain kernel variant (A/B measurement)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the cpu_baseline sample (default 1000)")
@@ -612,6 +614,209 @@ def run_replay(args):
         dist.destroy_process_group()
 
 
+# ---- the widened rows and the reference's shipped geometry: one JSON line each --------------------
+# Host wall clock around the C-ABI call with host buffers (plus a device-resident figure for the interpolation); their
+# cpu_baseline legs time the reference's own code from oracle/_ref (one thread: the reference runs these on its planner
+# thread) and the oracle port on a bounded sample.  Not the headline metric: `python bench.py` without --config is that.
+def run_frontier(args):
+    """--config frontier: history-graph frontier potential, History::bfs (history.cpp:96-137); --candidates = vertices per call."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    n_items = args.candidates or 148
+    cpu_sample = 0 if args.no_cpu_baseline else (args.cpu_sample or 3)
+    import torch
+    from nbv_exploration_planner_b200 import LAYER_TSDF, NbvGpu, synth
+    m = synth.make_map(args.map)
+    cam = m.camera()
+    g = NbvGpu(0)
+    lt = g.layer_create(LAYER_TSDF, m.voxel_size, m.vps, len(m.keys) + 8)
+    g.layer_update(lt, m.keys, m.tsdf)
+    g.commit()
+    g.set_camera(cam)
+    pts = synth.make_candidates(m.cfg, n_items, None).positions
+    for _ in range(args.warmup):
+        r = g.frontier_potential(lt, pts, 6.0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = g.frontier_potential(lt, pts, 6.0)
+    dt = (time.perf_counter() - t0) / args.steps
+    one = []
+    for i in range(min(8, len(pts))):
+        t1 = time.perf_counter()
+        g.frontier_potential(lt, pts[i:i + 1], 6.0)
+        one.append(time.perf_counter() - t1)
+    out = {"metric": "history-graph vertices/s (frontier potential, History::bfs)", "value": len(pts) / dt, "unit": "vertices/s",
+           "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+           "timing": "host wall clock around the C-ABI call (host buffers in, host buffers out)",
+           "config": {"workload": f"{args.map} map, {len(pts)} vertices per call, max_distance {6.0} m, "
+                                  f"voxel {m.voxel_size} m", "map_blocks": int(len(m.keys))},
+           "visited_cells_per_vertex": float(r["visited"].mean()), "cells_per_s": float(r["visited"].sum()) / dt,
+           "single_vertex_latency_ms": float(np.median(one) * 1e3)}
+    # CPU side on a bounded sample: the reference's own code (1 thread) and the oracle port
+    k = min(cpu_sample, len(pts))
+    if k > 0:
+        from oracle import binding as ob, ref_binding as rb
+        o = ob.Oracle()
+        lo = o.layer_create(0, m.voxel_size, m.vps)
+        o.layer_update(lo, m.keys, m.tsdf)
+        o.set_camera(cam.as_dict())
+        t1 = time.perf_counter()
+        ro = o.frontier_potential(lo, pts[:k], 6.0, threads=1)
+        t_or = (time.perf_counter() - t1) / k
+        ok = bool(np.array_equal(ro["gain"], r["gain"][:k]) and np.array_equal(ro["cells_checksum"], r["cells_checksum"][:k]))
+        cpu = {"oracle_port_ms_per_vertex": t_or * 1e3, "sample": f"first {k} vertices, 1 thread", "gpu_equals_oracle_on_sample": ok}
+        if rb.available() and 6.0 == 6.0:
+            ref = rb.Reference(m.voxel_size, m.vps)
+            ref.tsdf_update(m.keys, m.tsdf)
+            ref.set_camera(cam.as_dict(), 0.4)
+            t1 = time.perf_counter()
+            rr = ref.frontier_potential(pts[:k])
+            t_ref = (time.perf_counter() - t1) / k
+            cpu.update({"kind": "reference", "reference_ms_per_vertex": t_ref * 1e3, "value": 1.0 / t_ref, "unit": "vertices/s", "cores": 1,
+                        "gpu_equals_reference_on_sample": bool(np.array_equal(rr, r["gain"][:k]))})
+        else:
+            cpu.update({"kind": "port", "value": 1.0 / t_or, "unit": "vertices/s", "cores": 1})
+        out["cpu_baseline"] = cpu
+    emit(out)
+    g.close()
+
+
+
+def run_interp(args):
+    """--config interp: ESDF interpolated distance + gradient, EsdfMap::getDistanceAndGradientAtPosition (esdf_map.cc:22-52);
+    --candidates = queries per call."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    n_items = args.candidates or 1000000
+    cpu_sample = 0 if args.no_cpu_baseline else (args.cpu_sample or 200000)
+    import torch
+    from nbv_exploration_planner_b200 import LAYER_ESDF, PACK_VOXBLOX, NbvGpu, synth
+    from voxblox_fixture import esdf_words
+    m = synth.make_map(args.map)
+    obs = (m.tsdf[..., 1] > 0).astype(np.uint8)
+    g = NbvGpu(0)
+    le = g.layer_create(LAYER_ESDF, m.voxel_size, m.vps, len(m.keys) + 8)
+    g.layer_update(le, m.keys, esdf_words(m.esdf, flags=obs.astype(np.uint32)), PACK_VOXBLOX)
+    g.commit()
+    rng = np.random.default_rng(5)
+    lo, hi = np.array(m.cfg.bounds_min, float), np.array(m.cfg.bounds_max, float)
+    q = rng.uniform(lo, hi, (n_items, 3))
+    for _ in range(args.warmup):
+        r = g.esdf_distance_gradient(le, q)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = g.esdf_distance_gradient(le, q)
+    dt = (time.perf_counter() - t0) / args.steps
+    t1 = time.perf_counter()
+    for i in range(200):
+        g.esdf_distance_gradient(le, q[i:i + 1])
+    one = (time.perf_counter() - t1) / 200
+    # inputs and outputs resident in HBM: nbvgpu_esdf_distance_gradient_device on an explicit stream, CUDA events
+    stream = torch.cuda.Stream()
+    g.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        d_q = torch.from_numpy(q).cuda()
+        d_ok = torch.empty(len(q), dtype=torch.uint8, device="cuda")
+        d_dist = torch.empty(len(q), dtype=torch.float64, device="cuda")
+        d_grad = torch.empty((len(q), 3), dtype=torch.float64, device="cuda")
+        for _ in range(args.warmup):
+            g.esdf_distance_gradient_device(le, len(q), d_q, d_ok, d_dist, d_grad)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            g.esdf_distance_gradient_device(le, len(q), d_q, d_ok, d_dist, d_grad)
+        e1.record()
+        stream.synchronize()
+        dev_ms = e0.elapsed_time(e1) / args.steps
+        same_dev = bool(np.array_equal(d_ok.cpu().numpy(), r["ok"]) and np.array_equal(d_dist.cpu().numpy(), r["distance"]))
+    g.set_stream(None)
+    out = {"metric": "ESDF interpolated distance+gradient queries/s (EsdfMap::getDistanceAndGradientAtPosition)", "value": len(q) / dt,
+           "unit": "queries/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+           "timing": "host wall clock around the C-ABI call (host buffers in, host buffers out)",
+           "config": {"workload": f"{args.map} map, {len(q)} uniform random positions inside the map bounds per call, voxel {m.voxel_size} m",
+                      "map_blocks": int(len(m.keys))},
+           "success_fraction": float(r["ok"].mean()), "single_query_latency_us": one * 1e6,
+           "device_resident": {"value": len(q) / (dev_ms * 1e-3), "unit": "queries/s", "ms_per_step": dev_ms,
+                               "timing": "CUDA events on the launching stream, buffers in HBM (nbvgpu_esdf_distance_gradient_device)",
+                               "equals_host_path": same_dev},
+           "h2d_bytes_per_step": len(q) * 24, "d2h_bytes_per_step": len(q) * 33}
+    k = min(cpu_sample, len(q))
+    if k > 0:
+        from oracle import binding as ob, ref_binding as rb
+        o = ob.Oracle()
+        lo_e = o.layer_create(1, m.voxel_size, m.vps)
+        o.layer_update_esdf_observed(lo_e, m.keys, m.esdf, obs)
+        t1 = time.perf_counter()
+        ro = o.distance_and_gradient(lo_e, q[:k], threads=1)
+        t_or = time.perf_counter() - t1
+        same = bool(np.array_equal(ro["ok"], r["ok"][:k]) and np.array_equal(ro["distance"], r["distance"][:k]) and
+                    np.array_equal(ro["gradient"], r["gradient"][:k]))
+        cpu = {"oracle_port_queries_per_s": k / t_or, "sample": f"first {k} queries, 1 thread", "gpu_equals_oracle_on_sample": same}
+        if rb.available():
+            ref = rb.Reference(m.voxel_size, m.vps)
+            ref.esdf_update_observed(m.keys, m.esdf, obs)
+            t1 = time.perf_counter()
+            rr = ref.distance_and_gradient(q[:k])
+            t_ref = time.perf_counter() - t1
+            cpu.update({"kind": "reference", "value": k / t_ref, "unit": "queries/s", "cores": 1,
+                        "note": "the reference's interpolator lines compiled against the Eigen stand-in (scalar products)",
+                        "gpu_equals_reference_on_sample": bool(np.array_equal(rr["ok"], r["ok"][:k]) and np.array_equal(rr["distance"], r["distance"][:k])
+                                                               and np.array_equal(rr["gradient"], r["gradient"][:k]))})
+        else:
+            cpu.update({"kind": "port", "value": k / t_or, "unit": "queries/s", "cores": 1})
+        out["cpu_baseline"] = cpu
+    emit(out)
+    g.close()
+
+
+
+def run_shipped(args):
+    """--config shipped: gain evaluation on the geometry of the reference's shipped indoor configuration
+    (resource/exploration_indoor.yaml, launch/voxblox_exploration_indoor.launch): 69 x 42 deg, 3.0 m range, 0.3 m voxels."""
+    n = args.candidates or 1000
+    import torch
+    from nbv_exploration_planner_b200 import LAYER_TSDF, NbvGpu, synth
+    cfg = synth.SynthConfig("shipped-indoor", (-4, -1, 0), (10, 14, 3), 0.3, 3.0, n, "pillars", 4001, 4002, (3.0, 6.0, 1.0), obs_radius=5.0,
+                            traj_points=8, traj_step=3.0, vicinity=6.0, hfov_deg=69.0, vfov_deg=42.0, pitch_deg=0.0, near_m=0.1)
+    m = synth.make_map(cfg)
+    cam = m.camera()
+    g = NbvGpu(0)
+    lt = g.layer_create(LAYER_TSDF, m.voxel_size, m.vps, len(m.keys) + 8)
+    g.layer_update(lt, m.keys, m.tsdf)
+    g.commit()
+    g.set_camera(cam)
+    pos = synth.make_candidates(cfg, n, None).positions
+    for _ in range(3):
+        r = g.gain_eval(lt, pos, steps=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(20):
+        r = g.gain_eval(lt, pos, steps=True)
+    dt = (time.perf_counter() - t0) / 20
+    out = {"metric": "candidate viewpoints/s, shipped indoor geometry", "value": n / dt, "unit": "viewpoints/s", "ms_per_step": dt * 1e3,
+           "timing": "host wall clock around nbvgpu_gain_eval (host buffers)", "n_candidates": n,
+           "voxel_steps_per_viewpoint": float(r["steps"].mean()), "voxel_steps_per_s": float(r["steps"].sum()) / dt,
+           "config": {"workload": "69x42 deg, 3.0 m range, 0.3 m voxels, 16^3 blocks, box (-4,-1,0)..(10,14,3), pillars world", "map_blocks": int(len(m.keys))}}
+    t1 = time.perf_counter()
+    for i in range(100):
+        g.gain_eval(lt, pos[i:i + 1])
+    out["single_candidate_latency_us"] = (time.perf_counter() - t1) / 100 * 1e6
+    from oracle import ref_binding as rb
+    if rb.available() and not args.no_cpu_baseline:
+        ref = rb.Reference(m.voxel_size, m.vps)
+        ref.tsdf_update(m.keys, m.tsdf)
+        ref.set_camera(cam.as_dict(), 0.4)
+        k = min(n, 200)
+        t1 = time.perf_counter()
+        rr = ref.gain_eval(pos[:k])
+        t_ref = time.perf_counter() - t1
+        out["cpu_baseline"] = {"kind": "reference", "value": k / t_ref, "unit": "viewpoints/s", "cores": 1, "sample": f"first {k} candidates, 1 thread",
+                               "gpu_equals_reference_on_sample": bool(np.array_equal(rr["gain"], r["gain"][:k]))}
+    emit(out)
+    g.close()
+
+
+
 def cpu_baseline(args, cfg, h_pos, h_seg):
     """The reference's CPU implementation timed on the host cores of this box on a bounded sample of the
     same workload: all threads and one thread (the reference itself plans on a single thread); the faster
@@ -648,5 +853,11 @@ if __name__ == "__main__":
         run_reference(a)
     elif a.config == "cfg5":
         run_replay(a)
+    elif a.config == "frontier":
+        run_frontier(a)
+    elif a.config == "interp":
+        run_interp(a)
+    elif a.config == "shipped":
+        run_shipped(a)
     else:
         run_ours(a)

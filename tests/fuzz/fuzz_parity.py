@@ -1,7 +1,7 @@
 """Randomised GPU-vs-oracle parity sweep for the gain / collision path: random cameras (FOVs, pitch, mount offset,
 near / far range), voxel sizes, worlds and exploration boxes; per-yaw counts, steps, yaw and gain must be identical
 for the default kernel and the cross-checking variant (whose mismatch counter must stay 0), edge verdicts identical.
-A tool, not part of the test suite (the oracle side takes a while):  python scripts/fuzz_parity.py [--cases 40] [--seed 1]"""
+Test infrastructure (it uses the oracle as the checker); not collected by pytest (the oracle side takes a while):  python tests/fuzz/fuzz_parity.py [--cases 40] [--seed 1]"""
 import argparse
 import os
 import sys
@@ -9,7 +9,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

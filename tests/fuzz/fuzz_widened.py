@@ -1,8 +1,8 @@
 """Randomised GPU-vs-oracle sweep for the widened rows: the history-graph frontier potential (History::bfs) and the ESDF
 interpolated distance / gradient, on random worlds, voxel sizes, exploration boxes, radii and start points (free, unknown,
 occupied, outside the box, on voxel faces, with -0.0 coordinates).  Frontier: count, gain, visited-set size and the per-cell
-coordinate checksum identical; interpolation: flag, distance, gradient identical.  A tool, not part of the test suite:
-python scripts/fuzz_widened.py [--cases 30] [--seed 1]"""
+coordinate checksum identical; interpolation: flag, distance, gradient identical.  Test infrastructure (it uses the oracle as the checker); not collected by pytest:
+python tests/fuzz/fuzz_widened.py [--cases 30] [--seed 1]"""
 import argparse
 import os
 import sys
@@ -10,7 +10,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 

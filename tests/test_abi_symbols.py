@@ -43,6 +43,12 @@ def test_no_cpu_fallback_without_device():
 
 
 def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py's baseline legs may touch oracle/: neither the package nor
+    anything under scripts/ does."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "scripts")):
+        for f in files:
+            txt = open(os.path.join(dirpath, f)).read()
+            assert "oracle" not in txt, f
     pkg = os.path.join(ROOT, "nbv_exploration_planner_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
