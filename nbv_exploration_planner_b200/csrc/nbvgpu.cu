@@ -292,8 +292,21 @@ int check_position_range(const nbvgpu_ctx* ctx, const LayerHost* L, size_t n, co
 
 template <int V, int LV, int MODE>
 cudaError_t launch_gain_as(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  // the opt-in limit is a property of the function (per device): raise it only when a launch needs more than any
+  // before it on that device -- a driver call per launch is a measurable part of a single-candidate evaluation
+  static std::mutex mu;
+  static std::map<int, size_t> granted;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = granted[dev];
+    if (smem > have) {
+      cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      have = smem;
+    }
+  }
   k_gain<V, LV, MODE><<<grid, kGainThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
@@ -931,19 +944,20 @@ int nbvgpu_gain_eval(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, do
   char* h = ctx->h_io.as<char>();
   memcpy(h, pos, n * 24);
   CK(ctx->d_pos.reserve(n * 24));
-  CK(ctx->d_gain.reserve(n * 8));
-  CK(ctx->d_yaw.reserve(n * 4));
-  CK(ctx->d_counts.reserve(n * 24));
-  CK(ctx->d_steps.reserve(n * 8));
+  // the small outputs share one device buffer laid out like the staging area, so that one copy brings back whatever
+  // was asked for: [gain n*8 | yaw n*8 (int32 in the first half) | counts n*24 | steps n*8]
+  CK(ctx->d_gain.reserve(n * 48));
+  char* d_out = ctx->d_gain.as<char>();
+  double* d_gain = reinterpret_cast<double*>(d_out);
+  int32_t* d_yaw = reinterpret_cast<int32_t*>(d_out + n * 8);
+  uint64_t* d_counts = reinterpret_cast<uint64_t*>(d_out + n * 16);
+  uint64_t* d_steps = reinterpret_cast<uint64_t*>(d_out + n * 40);
   if (per_yaw) CK(ctx->d_per_yaw.reserve(n * 1080 * sizeof(uint32_t)));
   CK(cudaMemcpyAsync(ctx->d_pos.p, h, n * 24, cudaMemcpyHostToDevice, ctx->stream));
-  const int rc = enqueue_gain(ctx, L, n, ctx->d_pos.as<double>(), ctx->d_gain.as<double>(), ctx->d_yaw.as<int32_t>(),
-                              counts ? ctx->d_counts.as<uint64_t>() : nullptr, nullptr, steps ? ctx->d_steps.as<uint64_t>() : nullptr);
+  const int rc = enqueue_gain(ctx, L, n, ctx->d_pos.as<double>(), d_gain, d_yaw, counts ? d_counts : nullptr, nullptr, steps ? d_steps : nullptr);
   if (rc) return rc;
-  CK(cudaMemcpyAsync(h + o_gain, ctx->d_gain.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (yaw_deg) CK(cudaMemcpyAsync(h + o_yaw, ctx->d_yaw.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  if (counts) CK(cudaMemcpyAsync(h + o_counts, ctx->d_counts.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
-  if (steps) CK(cudaMemcpyAsync(h + o_steps, ctx->d_steps.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  const size_t out_bytes = steps ? n * 48 : (counts ? n * 40 : n * 16);
+  CK(cudaMemcpyAsync(h + o_gain, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   if (per_yaw) CK(cudaMemcpyAsync(per_yaw, ctx->d_per_yaw.p, n * 1080 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   memcpy(gain, h + o_gain, n * 8);
