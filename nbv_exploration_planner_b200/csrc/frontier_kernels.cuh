@@ -284,14 +284,17 @@ struct VisitedDense {
   __device__ bool earlier(unsigned long long key, unsigned long long stamp) const { return seen_before(key, stamp); }
 };
 
+__device__ __forceinline__ int vis_index(const VisitedDense& v, unsigned long long key) { return v.index(key); }
+__device__ __forceinline__ int vis_index(const VisitedHash&, unsigned long long) { return -1; }  // never used: the hash set keeps handles
+
 constexpr int kFrontierThreads = 1024;
 // slot_eval codes
 constexpr int kSlotNone = -1, kSlotUnknown = -2;
 
 template <bool DENSE>
 __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const FrontierArgs a) {
-  __shared__ unsigned s_warp[32];
-  __shared__ unsigned s_run, s_total;
+  __shared__ unsigned s_warp[2][32];  // per-warp counts / offsets of the resolve scan, double-buffered by chunk parity
+  __shared__ unsigned s_total[2];
   __shared__ int s_err, s_split;
   __shared__ unsigned long long s_count, s_sum;
   extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -308,7 +311,10 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
   }
   FrontierEntry* cur = a.cur + (size_t)blockIdx.x * a.frontier_cap;
   FrontierEntry* next = a.next + (size_t)blockIdx.x * a.frontier_cap;
-  int* const slot_eval = a.slot_eval + (size_t)blockIdx.x * 6 * a.frontier_cap;
+  // per-slot outcome of the expand pass: the hash set keeps its entry handle (or a negative code); the dense set only a
+  // byte (0 nothing, 1 unknown neighbour, 2 free candidate) -- its handle is the grid index, recomputed from the key
+  typedef typename std::conditional<DENSE, signed char, int>::type SlotT;
+  SlotT* const slot_eval = reinterpret_cast<SlotT*>(a.slot_eval + (size_t)blockIdx.x * 6 * a.frontier_cap);
 
   for (int v = blockIdx.x; v < a.n; v += gridDim.x) {
     if (a.todo && !a.todo[v]) continue;
@@ -402,20 +408,20 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
             }
           }
         }
-        slot_eval[s] = ev;
+        slot_eval[s] = DENSE ? (SlotT)(ev >= 0 ? 2 : (ev == kSlotUnknown ? 1 : 0)) : (SlotT)ev;
       }
       __syncthreads();
       // ---- resolve in slot order: winners form the next frontier, unknown neighbours are counted
-      if (tid == 0) s_run = 0u;
-      __syncthreads();
-      for (unsigned base = 0; base < n_slots; base += blockDim.x) {
+      unsigned run = 0u;  // winners before this chunk: the same value in every thread
+      for (unsigned base = 0, par = 0; base < n_slots; base += blockDim.x, par ^= 1u) {
         const unsigned s = base + tid;
         bool win = false;
         double cx = 0, cy = 0, cz = 0;
         unsigned long long key = 0;
         if (s < n_slots) {
-          const int ev = slot_eval[s];
-          if (ev != kSlotNone) {
+          const int raw = slot_eval[s];
+          const bool is_free = DENSE ? raw == 2 : raw >= 0, is_unknown = DENSE ? raw == 1 : raw == kSlotUnknown;
+          if (is_free || is_unknown) {
             const FrontierEntry e = cur[s / 6u];
             const unsigned d = s % 6u;
             const int axis = (int)(d >> 1);
@@ -432,8 +438,8 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
             if (axis != 0 && e.x == 0.0) key &= ~(1ull << 57);
             if (axis != 1 && e.y == 0.0) key &= ~(1ull << 58);
             if (axis != 2 && e.z == 0.0) key &= ~(1ull << 59);
-            if (ev >= 0) {
-              win = vis.wins(ev, key, stamp0 | s);
+            if (is_free) {
+              win = vis.wins(DENSE ? vis_index(vis, key) : raw, key, stamp0 | s);
             } else if (!vis.earlier(key, stamp0 | s)) {
               ++my_count;  // unknown neighbour: counted unless an earlier slot of this level inserted this very key
             }
@@ -441,30 +447,31 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
         }
         // exclusive scan of `win` over the chunk, in slot order
         const unsigned ballot = __ballot_sync(0xffffffffu, win);
-        if (lane == 0) s_warp[warp] = __popc(ballot);
+        if (lane == 0) s_warp[par][warp] = __popc(ballot);
         __syncthreads();
         if (warp == 0) {
-          unsigned w = s_warp[lane];
+          unsigned w = s_warp[par][lane];
           unsigned incl = w;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += t;
           }
-          s_warp[lane] = incl - w;
-          if (lane == 31) s_total = incl;
+          s_warp[par][lane] = incl - w;
+          if (lane == 31) s_total[par] = incl;
         }
         __syncthreads();
         if (win) {
-          const unsigned pos = s_run + s_warp[warp] + __popc(ballot & ((1u << lane) - 1u));
+          const unsigned pos = run + s_warp[par][warp] + __popc(ballot & ((1u << lane) - 1u));
           if (pos < a.frontier_cap) next[pos] = FrontierEntry{cx, cy, cz, key};
           my_sum += cell_fingerprint(cx, cy, cz);
         }
-        __syncthreads();
-        if (tid == 0) s_run += s_total;
-        __syncthreads();
+        run += s_total[par];
+        // no barrier here: the next chunk writes the other half of the scratch, and its first barrier orders this
+        // chunk's reads before the writes of the chunk after that
       }
-      const unsigned n_next = s_run;
+      __syncthreads();
+      const unsigned n_next = run;
       if (n_next > a.frontier_cap) {
         if (tid == 0) s_err = 1;
       }
