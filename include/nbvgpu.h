@@ -263,6 +263,9 @@ int nbvgpu_debug_frontier_hash_redo(nbvgpu_ctx* ctx, uint64_t* count);
  * after an untimed warm-up pass, CUDA events on the context's stream.  Used by bench.py for the L2-normalised
  * roofline fraction; not part of the planner interface. */
 int nbvgpu_probe_l2_read_bandwidth(nbvgpu_ctx* ctx, size_t bytes, int iters, double* gb_per_s);
+/* Ray-sweep launches, since the context was created, that used the z-clipped dense shared-memory volume (fine-voxel layers
+ * whose unclipped volume does not fit; NBVGPU_NO_ZCLIP=1 in the environment disables the clipping); for tests. */
+int nbvgpu_debug_dense_clipped_launches(nbvgpu_ctx* ctx, uint64_t* count);
 /* Host-only helper for tests: round-half-even of |x| * 10^6, the integer behind "%f" / std::to_string(double),
  * exactly as the flood fill's cell keys compute it.  NBVGPU_ERR_RANGE for non-finite x or |x| >= 2^21. */
 int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude);

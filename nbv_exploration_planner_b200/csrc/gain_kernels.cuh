@@ -66,6 +66,9 @@ struct GainArgs {
   // candidate's voxel, and the common dimensions {16-voxel words along x, voxels along y, z}
   const int* vmin;    // [360 / yc][5]: lower corner x, y, z; words along x; voxels along y
   int vez, vwords;    // voxels along z (common); shared-memory words reserved for the volume
+  // z-clipped volume (fine voxels: the frustum reaches far below / above the exploration box, where nothing can count):
+  // a CTA keeps the rows of the box slab +- 3 voxels plus the rows its rays start in; zclip = 0: no clipping
+  int zclip, sz_lo, sz_hi, vez_alloc;  // start rows relative to the candidate's voxel; rows the host reserved memory for
   FilterConst F;
 };
 
@@ -323,7 +326,8 @@ __device__ __forceinline__ void dda_advance(float (&t)[3], const float (&dt)[3],
 //   * else the single-precision classifier in the camera frame, and the exact FP64 planes when that
 //     is within its margin.
 // ---------------------------------------------------------------------------------------------
-enum { kDense = 0, kGrid = 1, kProbe = 2 };
+enum { kDense = 0, kGrid = 1, kProbe = 2, kDenseClip = 3 };  // kDenseClip: kDense with the volume clipped in z (own instantiation,
+                                                                // so that the common dense kernel carries none of its code)
 
 inline size_t dense_smem_bytes(int yc, int gn, int nvol) {
   return (((size_t)nvol * 4 + 15) & ~(size_t)15) + gain_smem_bytes(yc, gn);
@@ -334,7 +338,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   constexpr bool kFilter = (VARIANT != 1);
   constexpr bool kStatusBits = (VARIANT == 0 || VARIANT == 2);
   constexpr bool kParanoid = (VARIANT == 2);
-  constexpr bool kIsDense = (MODE == kDense);
+  constexpr bool kIsDense = (MODE == kDense || MODE == kDenseClip);
+  constexpr bool kZClip = (MODE == kDenseClip);
   static_assert(!kIsDense || (LV == 4 && kStatusBits), "the dense volume copies 16-voxel status-tile words");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int yc = a.yc;
@@ -414,8 +419,21 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     x0 = dense_x0;
     vxw = a.vmin[5 * chunk + 3];
     vey = a.vmin[5 * chunk + 4];
-    nvol = vxw * vey * a.vez;
-    const int nrows = vey * a.vez;
+    int vez_c = a.vez;
+    if (kZClip) {
+      // rows that can be fetched: while a ray is inside the slab [gmin_z, gmax_z] (the walk stops at t_out, at most 2 voxels
+      // past it: margin 3), and between its start row and the slab when it starts outside
+      const int z_lo = max(z0, min(a.gmin[2] - 3, g0z + a.sz_lo));
+      const int z_hi = min(z0 + a.vez - 1, max(a.gmin[2] + (int)a.gspan[2] + 3, g0z + a.sz_hi));
+      z0 = z_lo;
+      vez_c = max(z_hi - z_lo + 1, 1);
+      if (vez_c > a.vez_alloc) {  // cannot happen: the host sized the memory from the candidates' own z-range
+        if (tid == 0) atomicAdd(a.totals + 3, 1ull);
+        vez_c = a.vez_alloc;
+      }
+    }
+    nvol = vxw * vey * vez_c;
+    const int nrows = vey * vez_c;
     int ry = tid % vey, rz = tid / vey;                             // row = rz * vey + ry
     const int dy = (int)blockDim.x % vey, dz = (int)blockDim.x / vey;  // row += blockDim.x
     for (int row = tid; row < nrows; row += blockDim.x) {
@@ -624,6 +642,12 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       return st | (st >> 1);  // 2 (occupied) -> 3
     };
     auto volume_code = [&]() -> unsigned {
+      if (kParanoid && tcur > t_out) {
+        // the default kernel has stopped here; this variant walks on to check that nothing inside the box follows, and
+        // must not read the (possibly z-clipped) volume for voxels the default kernel never fetches
+        if (in_box()) ++my_mismatch;
+        return 2u;
+      }
       uint32_t w;  // one word of the dense volume (always in range)
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((P >> 3) & ~3u));
       const unsigned code = __funnelshift_r(w, 0u, P) & 3u;

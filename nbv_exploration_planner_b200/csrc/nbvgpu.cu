@@ -138,6 +138,7 @@ struct nbvgpu_ctx {
   unsigned long long* d_totals = nullptr;  // rays, voxel steps, collision steps, classifier mismatches
   PinBuf h_io;                             // pinned staging for n-sized inputs / outputs
   DevBuf d_pos, d_per_yaw, d_gain, d_yaw, d_counts, d_steps, d_seg, d_free, d_aux, d_best;
+  DevBuf d_zrange;  // {min, max} voxel row of the candidates (z-clipped dense volume); NOT d_aux: callers keep live data there
   DevBuf d_fr_cells, d_fr_cur, d_fr_next, d_fr_slots, d_fr_io;  // History::bfs workspaces (nbvgpu_frontier_potential)
   unsigned long long stats_frontier_hash_redo = 0;              // vertices the dense visited set handed to the hash set
   nbvgpu_stats stats{};
@@ -150,11 +151,13 @@ struct nbvgpu_ctx {
     int vez = 0;
     long long vwords = 0;
     DevBuf d_vmin;
+    std::vector<int> h_vmin;  // host copy of the per-chunk table {min x, min y, min z, words along x, voxels along y}
   };
   std::map<int, DenseInfo> dense_info;  // per yaws-per-CTA, valid for (dense_gen, dense_vs)
   float dense_vs = 0.f;
   unsigned long long dense_gen = ~0ull, cam_gen = 0;
   int force_yc = 0;  // NBVGPU_YC environment override (experiments)
+  unsigned long long stats_dense_clipped = 0;  // ray-sweep launches that used the z-clipped dense volume (tests)
   int dense_budget = 55 * 1024;  // shared memory per CTA the dense volume path may use (NBVGPU_DENSE_KB)
   int smem_pad = 0;              // extra dynamic shared memory per CTA (NBVGPU_SMEM_PAD_KB; occupancy experiments)
   // optional CUDA-event timing of the ray-sweep kernel (nbvgpu_set_profiling)
@@ -318,6 +321,17 @@ cudaError_t launch_gain(const GainArgs& a, size_t smem, unsigned grid, cudaStrea
   return a.L.log2vps == 4 ? launch_gain_as<V, 4, kGrid>(a, smem, grid, s) : launch_gain_as<V, 0, kGrid>(a, smem, grid, s);
 }
 
+// min / max over the (valid) candidates of the voxel row that contains them: sizes the z-clipped dense volume
+__global__ void k_pos_zrange(const double* __restrict__ pos, const uint8_t* __restrict__ valid, int n, double vs_inv, int* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || (valid && !valid[i])) return;
+  const double z = pos[3 * i + 2] * vs_inv;
+  if (!(fabs(z) < 4194304.0)) return;  // such a candidate is skipped by the sweep as well
+  const int g = (int)floor(z);
+  atomicMin(out, g);
+  atomicMax(out + 1, g);
+}
+
 // Enqueue: ray sweep + best yaw for n resident positions.  d_per_yaw may be null (scratch used).
 int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, double* d_gain, int32_t* d_yaw_deg,
                  uint64_t* d_counts, uint32_t* d_per_yaw, uint64_t* d_steps, const uint8_t* d_valid = nullptr) {
@@ -404,6 +418,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
         std::vector<int> vmin((size_t)(360 / c) * 5);
         info.ok = nbvgpu_host::dense_volume_bounds(T, a.vs, c, vmin.data(), &info.vez, &info.vwords);
         if (info.ok) {
+          info.h_vmin = vmin;
           CK(info.d_vmin.reserve(vmin.size() * sizeof(int)));
           CK(cudaMemcpyAsync(info.d_vmin.p, vmin.data(), vmin.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
           CK(cudaStreamSynchronize(ctx->stream));  // vmin is a local vector
@@ -422,6 +437,60 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
         a.vez = di.vez;
         a.vwords = (int)di.vwords;
         break;
+      }
+    }
+  }
+  a.zclip = 0;
+  a.sz_lo = a.sz_hi = a.vez_alloc = 0;
+  if (!dense && (variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0 && getenv("NBVGPU_NO_ZCLIP") == nullptr) {
+    // Second chance for fine voxels: the volume did not fit because the frustum reaches far below / above the exploration
+    // box, where no voxel can count.  Clipped to the box slab (+- 3 voxels, plus the rows the rays start in) it may; how
+    // many rows that takes depends on the candidates' heights, so their z-range is read back first (one tiny kernel and
+    // one synchronise -- only on this path, i.e. only when the alternative is the slower slot-grid kernel).
+    CK(ctx->d_zrange.reserve(64));
+    int* d_zr = ctx->d_zrange.as<int>();
+    const int init[2] = {INT_MAX, INT_MIN};
+    CK(cudaMemcpyAsync(d_zr, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+    k_pos_zrange<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_pos, d_valid, (int)n, a.vs_inv, d_zr);
+    int zr[2] = {0, 0};
+    CK(cudaMemcpyAsync(zr, d_zr, sizeof zr, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.kernel_launches++;
+    if (zr[0] <= zr[1] && (long long)zr[1] - zr[0] <= 8192) {
+      // the camera's offset from the candidate is the same along z for every yaw (yaw turns about z)
+      const int sb = (int)std::floor(T.B[0][2] * a.vs_inv);
+      const int sz_lo = sb - 1, sz_hi = sb + 2;
+      const int bz_lo = a.gmin[2] - 3, bz_hi = a.gmin[2] + (int)a.gspan[2] + 3;
+      for (int c : kYc) {
+        if (c > yc) continue;
+        auto it = ctx->dense_info.find(c);
+        if (it == ctx->dense_info.end() || !it->second.ok || it->second.vez <= 0) continue;
+        const nbvgpu_ctx::DenseInfo& di = it->second;
+        const int chunks = 360 / c;
+        int ext = 1;
+        for (int g0 = zr[0]; g0 <= zr[1]; ++g0)
+          for (int ch = 0; ch < chunks; ++ch) {
+            const int z0 = g0 + di.h_vmin[5 * ch + 2];
+            const int lo = std::max(z0, std::min(bz_lo, g0 + sz_lo)), hi = std::min(z0 + di.vez - 1, std::max(bz_hi, g0 + sz_hi));
+            ext = std::max(ext, hi - lo + 1);
+          }
+        const long long words = (di.vwords / di.vez) * ext;
+        const size_t need = dense_smem_bytes(c, (int)gn, (int)words);
+        if (ext < di.vez && need <= (size_t)ctx->dense_budget && need <= (size_t)ctx->max_smem_optin) {
+          dense = true;
+          yc = c;
+          a.yc = c;
+          smem = need;
+          a.vmin = di.d_vmin.as<int>();
+          a.vez = di.vez;
+          a.vwords = (int)words;
+          a.zclip = 1;
+          a.sz_lo = sz_lo;
+          a.sz_hi = sz_hi;
+          a.vez_alloc = ext;
+          ctx->stats_dense_clipped++;
+          break;
+        }
       }
     }
   }
@@ -444,11 +513,17 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   const int mode = gdim > 0 ? kGrid : kProbe;
   switch (variant) {
     case 1: e = launch_gain<1>(a, smem, grid, ctx->stream, mode); break;
-    case 2: e = dense ? launch_gain_as<2, 4, kDense>(a, smem, grid, ctx->stream) : launch_gain<2>(a, smem, grid, ctx->stream, mode); break;
+    case 2:
+      e = dense ? (a.zclip ? launch_gain_as<2, 4, kDenseClip>(a, smem, grid, ctx->stream) : launch_gain_as<2, 4, kDense>(a, smem, grid, ctx->stream))
+                : launch_gain<2>(a, smem, grid, ctx->stream, mode);
+      break;
     case 3: e = launch_gain<3>(a, smem, grid, ctx->stream, mode); break;
     case 4: e = launch_gain<0>(a, smem, grid, ctx->stream, mode); break;
     case 5: e = launch_gain<2>(a, smem, grid, ctx->stream, mode); break;
-    default: e = dense ? launch_gain_as<0, 4, kDense>(a, smem, grid, ctx->stream) : launch_gain<0>(a, smem, grid, ctx->stream, mode); break;
+    default:
+      e = dense ? (a.zclip ? launch_gain_as<0, 4, kDenseClip>(a, smem, grid, ctx->stream) : launch_gain_as<0, 4, kDense>(a, smem, grid, ctx->stream))
+                : launch_gain<0>(a, smem, grid, ctx->stream, mode);
+      break;
   }
   if (ev1) cudaEventRecord(ev1, ctx->stream);
   CK(e);
@@ -561,7 +636,8 @@ void nbvgpu_destroy(nbvgpu_ctx* ctx) {
     ctx->h_io.release();
     for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
     for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
-                      &ctx->d_free, &ctx->d_aux, &ctx->d_best})
+                      &ctx->d_free, &ctx->d_aux, &ctx->d_best, &ctx->d_zrange, &ctx->d_fr_cells, &ctx->d_fr_cur, &ctx->d_fr_next,
+                      &ctx->d_fr_slots, &ctx->d_fr_io})
       b->release();
     for (auto& pr : ctx->prof_events) {
       cudaEventDestroy(pr.first);
@@ -1414,6 +1490,14 @@ int nbvgpu_probe_l2_read_bandwidth(nbvgpu_ctx* ctx, size_t bytes, int iters, dou
   cudaFree(sink);
   if (e != cudaSuccess || !(ms > 0.f)) return fail(ctx, NBVGPU_ERR_CUDA, "L2 probe failed");
   *gb_per_s = (double)n_vec * 16.0 * (double)iters / ((double)ms * 1e-3) / 1e9;
+  return NBVGPU_OK;
+}
+
+// Ray-sweep launches (since context creation) that used the z-clipped dense volume; for tests.
+int nbvgpu_debug_dense_clipped_launches(nbvgpu_ctx* ctx, uint64_t* out) {
+  if (!ctx || !out) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  *out = ctx->stats_dense_clipped;
   return NBVGPU_OK;
 }
 

@@ -311,6 +311,12 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_probe_l2_read_bandwidth(self._h, int(nbytes), int(iters), C.byref(out)))
         return float(out.value)
 
+    def dense_clipped_launches(self) -> int:
+        """ray-sweep launches that used the z-clipped dense volume (tests)."""
+        out = C.c_uint64(0)
+        self._ck(self._L.nbvgpu_debug_dense_clipped_launches(self._h, C.byref(out)))
+        return int(out.value)
+
     def frontier_hash_redo(self) -> int:
         """vertices the dense visited set of the flood fill handed back to the hash-keyed one (tests)."""
         out = C.c_uint64(0)

@@ -27,7 +27,7 @@ def main():
     t0 = time.time()
     for case in range(args.cases):
         vs = float(rng.choice([0.1, 0.15, 0.2, 0.25, 0.3, 0.4]))
-        far = float(rng.uniform(1.5, 5.0 if vs >= 0.15 else 3.5))
+        far = float(rng.uniform(1.5, 5.0))
         hfov = float(rng.choice([58.0, 69.0, 90.0, 110.0, 120.0]))
         vfov = float(rng.choice([42.0, 45.0, 60.0, 75.0]))
         pitch = float(rng.uniform(-25, 30))
