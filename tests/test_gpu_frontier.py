@@ -160,3 +160,22 @@ def test_hash_and_dense_visited_sets_agree(oracle_mod, tiny_map, monkeypatch):
         assert np.array_equal(dense[k], hashed[k])
     g.close()
 
+
+def test_context_destroy_releases_the_workspaces(tiny_map):
+    """The flood fill allocates per-CTA workspaces (visited sets, frontier arrays) inside the context: destroying the context
+    must give all of it back (it once did not)."""
+    import torch
+    from nbv_exploration_planner_b200 import synth
+    pts = synth.make_candidates(tiny_map.cfg, 64, None).positions
+    torch.cuda.synchronize()
+    free0 = None
+    for cycle in range(4):
+        g, lt, _ = load_gpu(tiny_map, tiny_map.camera())
+        g.frontier_potential(lt, pts, 6.0)
+        g.close()
+        torch.cuda.synchronize()
+        free = torch.cuda.mem_get_info()[0]
+        if cycle == 0:
+            free0 = free          # after the first cycle: whatever the driver keeps for itself is in place
+    assert free0 - free < 32 << 20, f"{(free0 - free) >> 20} MiB not returned after three more create / fill / destroy cycles"
+
