@@ -266,6 +266,11 @@ int nbvgpu_probe_l2_read_bandwidth(nbvgpu_ctx* ctx, size_t bytes, int iters, dou
 /* Ray-sweep launches, since the context was created, that used the z-clipped dense shared-memory volume (fine-voxel layers
  * whose unclipped volume does not fit; NBVGPU_NO_ZCLIP=1 in the environment disables the clipping); for tests. */
 int nbvgpu_debug_dense_clipped_launches(nbvgpu_ctx* ctx, uint64_t* count);
+/* Ray-sweep launches, since the context was created, that ran the best-yaw window scan in the last CTA of each candidate
+ * (batches of at most 64 candidates on the dense-volume sweep: a single-candidate nbvgpu_optimized_gain is then one kernel
+ * launch reading and writing mapped pinned host memory; NBVGPU_NO_FUSE=1 / NBVGPU_NO_SMALL_PATH=1 in the environment
+ * restore the two-launch / staged-copy paths); for tests. */
+int nbvgpu_debug_fused_launches(nbvgpu_ctx* ctx, uint64_t* count);
 /* Host-only helper for tests: round-half-even of |x| * 10^6, the integer behind "%f" / std::to_string(double),
  * exactly as the flood fill's cell keys compute it.  NBVGPU_ERR_RANGE for non-finite x or |x| >= 2^21. */
 int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude);

@@ -7,6 +7,7 @@
 //   k_best_yaw         best-yaw window scan                       nbveplanner/src/rrt.cpp:449-478
 //   k_score_best       node scoring / best node                   nbveplanner/src/rrt.cpp:220-246
 //   k_check_segments   HighResManager::checkMotion                nbveplanner/include/nbveplanner/voxblox_manager.h:89-108
+//   k_check_segments_warp   the same, one warp per segment (small batches)
 //   k_expand_sample    RrtTree::iterate front half (batched)      nbveplanner/src/rrt.cpp:172-212,223
 //
 // Work decomposition of k_gain: one CTA per (candidate position, chunk of `yc` consecutive
@@ -43,6 +44,19 @@ struct FilterConst {
   float m, mh, mv;  // margins (plain, scaled for the horizontal / vertical side planes)
 };
 
+// arguments of the best-yaw scan (best_yaw_warp below)
+struct BestYawArgs {
+  const uint32_t* per_yaw;  // [n][360][3]
+  double* gain;             // [n]
+  int32_t* yaw_deg;         // [n] or null
+  unsigned long long* counts;  // [n][3] or null
+  double g_unmapped, g_free, g_occupied;
+  double cube;
+  int half_hfov;
+  int sum_all;
+  int n;
+};
+
 struct GainArgs {
   LayerView L;
   const double* A;    // [360][24]
@@ -69,6 +83,11 @@ struct GainArgs {
   // z-clipped volume (fine voxels: the frustum reaches far below / above the exploration box, where nothing can count):
   // a CTA keeps the rows of the box slab +- 3 voxels plus the rows its rays start in; zclip = 0: no clipping
   int zclip, sz_lo, sz_hi, vez_alloc;  // start rows relative to the candidate's voxel; rows the host reserved memory for
+  // fused finish (k_gain<..., FUSE = true>, small batches): the last CTA of a candidate to arrive runs the window
+  // scan, so that a single-candidate evaluation is one launch.  arrive[v] counts CTAs and is reset by the last one.
+  BestYawArgs by;
+  int* arrive;
+  double pos1[3];     // the position of a single candidate passed by value (used when pos == nullptr)
   FilterConst F;
 };
 
@@ -333,7 +352,110 @@ inline size_t dense_smem_bytes(int yc, int gn, int nvol) {
   return (((size_t)nvol * 4 + 15) & ~(size_t)15) + gain_smem_bytes(yc, gn);
 }
 
-template <int VARIANT, int LV, int MODE>
+// ---------------------------------------------------------------------------------------------
+// Best yaw (rrt.cpp:449-478) / all-yaw sum (rrt.cpp:571-578).  One warp per candidate.
+// ---------------------------------------------------------------------------------------------
+// One warp, candidate v; vg: 360 doubles of shared memory owned by the warp.  The counts are read through L2
+// (__ldcg): in the fused sweep they were written by other CTAs of the same launch.
+__device__ __forceinline__ void best_yaw_warp(const BestYawArgs& a, int v, double* vg, int lane) {
+  const uint32_t* c = a.per_yaw + (size_t)v * 1080;
+  unsigned long long tu = 0, tf = 0, to = 0;
+  for (int j = lane; j < 360; j += 32) {
+    const uint32_t nu = __ldcg(c + 3 * j), nf = __ldcg(c + 3 * j + 1), no = __ldcg(c + 3 * j + 2);
+    // vertical_gain[j]: the running sum of rrt.cpp:436-443 in count form.
+    vg[j] = dadd(dadd(dmul((double)nu, a.g_unmapped), dmul((double)no, a.g_occupied)), dmul((double)nf, a.g_free));
+    tu += nu; tf += nf; to += no;
+  }
+  __syncwarp();
+  if (a.sum_all) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tu += __shfl_xor_sync(0xffffffffu, tu, o);
+      tf += __shfl_xor_sync(0xffffffffu, tf, o);
+      to += __shfl_xor_sync(0xffffffffu, to, o);
+    }
+    if (lane == 0) {
+      const double g = dadd(dadd(dmul((double)tu, a.g_unmapped), dmul((double)to, a.g_occupied)), dmul((double)tf, a.g_free));
+      a.gain[v] = dmul(g, a.cube);
+      if (a.yaw_deg) a.yaw_deg[v] = 0;
+      if (a.counts) { a.counts[3 * v] = tu; a.counts[3 * v + 1] = tf; a.counts[3 * v + 2] = to; }
+    }
+    return;
+  }
+  // 72 window centres, 5 degrees apart; each lane sums its windows in the reference's order.
+  double best = 0.0;
+  int best_c = 1 << 20;  // candidate ordinal; "none" sorts last
+  for (int cidx = lane; cidx < 72; cidx += 32) {
+    const int i = -180 + 5 * cidx;
+    double cur = 0.0;
+    int left = (i + 180) - a.half_hfov;
+    if (left < 0) {
+      for (int j = 360 + left; j < 360; ++j) cur = dadd(cur, vg[j]);
+      left = 0;
+    }
+    int right = (i + 180) + a.half_hfov;
+    if (right >= 360) {
+      for (int j = 0; j < right - 359; ++j) cur = dadd(cur, vg[j]);
+      right = 359;
+    }
+    for (int j = left; j <= right; ++j) cur = dadd(cur, vg[j]);
+    if (cur > best) { best = cur; best_c = cidx; }  // strict: first maximum of this lane
+  }
+  // Warp arg-max, ties -> lowest ordinal (= first strict maximum of the sequential scan).
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+  }
+  const int yaw = (best_c < 72) ? (-180 + 5 * best_c) : 0;  // max_gain_yaw starts at 0 (rrt.cpp:450)
+  if (a.counts) {
+    unsigned long long wu = 0, wf = 0, wo = 0;
+    for (int d = -a.half_hfov + lane; d <= a.half_hfov; d += 32) {
+      const int j = (((yaw + 180 + d) % 360) + 360) % 360;
+      wu += __ldcg(c + 3 * j); wf += __ldcg(c + 3 * j + 1); wo += __ldcg(c + 3 * j + 2);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      wu += __shfl_xor_sync(0xffffffffu, wu, o);
+      wf += __shfl_xor_sync(0xffffffffu, wf, o);
+      wo += __shfl_xor_sync(0xffffffffu, wo, o);
+    }
+    if (lane == 0) { a.counts[3 * v] = wu; a.counts[3 * v + 1] = wf; a.counts[3 * v + 2] = wo; }
+  }
+  if (lane == 0) {
+    a.gain[v] = dmul(best, a.cube);  // rrt.cpp:478
+    if (a.yaw_deg) a.yaw_deg[v] = yaw;
+  }
+}
+
+__global__ void __launch_bounds__(128) k_best_yaw(const BestYawArgs a) {
+  __shared__ double vg_all[4][360];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int v = blockIdx.x * 4 + warp;
+  if (v >= a.n) return;
+  best_yaw_warp(a, v, vg_all[warp], lane);
+}
+
+// Fused finish of k_gain<..., FUSE = true>: every CTA of candidate v arrives here after its per-yaw counts are written;
+// the last one runs the window scan on its first warp (the threadFenceReduction pattern: fence, count, fence, read
+// through L2) and resets the counter for the next launch.  `scratch`: 360 doubles of shared memory nobody uses any more.
+__device__ __forceinline__ void fused_best_yaw(const GainArgs& a, int v, int chunks, int tid, double* scratch) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.arrive + v, 1) == chunks - 1) ? 1 : 0;
+  __syncthreads();
+  if (s_last && tid < 32) {
+    __threadfence();
+    if (tid == 0) a.arrive[v] = 0;
+    best_yaw_warp(a.by, v, scratch, tid);
+  }
+}
+constexpr size_t kFusedScratchBytes = 360 * sizeof(double);  // the launch reserves at least this much dynamic shared memory
+
+// k_gain: the ray sweep described in the comment block above the MODE enum.
+template <int VARIANT, int LV, int MODE, bool FUSE = false>
 __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   constexpr bool kFilter = (VARIANT != 1);
   constexpr bool kStatusBits = (VARIANT == 0 || VARIANT == 2);
@@ -359,7 +481,9 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   const int vm = (1 << lv) - 1;
   const unsigned nvox = LV ? (1u << (3 * LV)) : (unsigned)a.L.nvox;
 
-  const double px = a.pos[3 * v], py = a.pos[3 * v + 1], pz = a.pos[3 * v + 2];
+  const bool by_value = FUSE && a.pos == nullptr;  // single candidate, position in the launch arguments
+  const double px = by_value ? a.pos1[0] : a.pos[3 * v], py = by_value ? a.pos1[1] : a.pos[3 * v + 1],
+               pz = by_value ? a.pos1[2] : a.pos[3 * v + 2];
   // Guard (the host entry points validate; device-resident inputs are caught here).
   const double lim = 4194304.0 - (double)a.reach_vox - 2.0;
   const bool bad = !(fabs(px * a.vs_inv) < lim) || !(fabs(py * a.vs_inv) < lim) || !(fabs(pz * a.vs_inv) < lim) ||
@@ -373,6 +497,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   if (bad) {
     for (int j = tid; j < yc; j += blockDim.x)
       for (int k = 0; k < 3; ++k) a.per_yaw[((size_t)v * 360 + chunk * yc + j) * 3 + k] = 0u;
+    if (FUSE) fused_best_yaw(a, v, chunks, tid, reinterpret_cast<double*>(smem_raw));
     return;
   }
   // Voxel containing the candidate position and the origin of the local block grid.
@@ -850,98 +975,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     atomicAdd(a.totals + 1, s_steps);
     if (kParanoid && s_mismatch) atomicAdd(a.totals + 3, (unsigned long long)s_mismatch);
   }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Best yaw (rrt.cpp:449-478) / all-yaw sum (rrt.cpp:571-578).  One warp per candidate.
-// ---------------------------------------------------------------------------------------------
-struct BestYawArgs {
-  const uint32_t* per_yaw;  // [n][360][3]
-  double* gain;             // [n]
-  int32_t* yaw_deg;         // [n] or null
-  unsigned long long* counts;  // [n][3] or null
-  double g_unmapped, g_free, g_occupied;
-  double cube;
-  int half_hfov;
-  int sum_all;
-  int n;
-};
-
-__global__ void __launch_bounds__(128) k_best_yaw(const BestYawArgs a) {
-  __shared__ double vg_all[4][360];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v = blockIdx.x * 4 + warp;
-  if (v >= a.n) return;
-  double* vg = vg_all[warp];
-  const uint32_t* c = a.per_yaw + (size_t)v * 1080;
-  unsigned long long tu = 0, tf = 0, to = 0;
-  for (int j = lane; j < 360; j += 32) {
-    const uint32_t nu = c[3 * j], nf = c[3 * j + 1], no = c[3 * j + 2];
-    // vertical_gain[j]: the running sum of rrt.cpp:436-443 in count form.
-    vg[j] = dadd(dadd(dmul((double)nu, a.g_unmapped), dmul((double)no, a.g_occupied)), dmul((double)nf, a.g_free));
-    tu += nu; tf += nf; to += no;
-  }
-  __syncwarp();
-  if (a.sum_all) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      tu += __shfl_xor_sync(0xffffffffu, tu, o);
-      tf += __shfl_xor_sync(0xffffffffu, tf, o);
-      to += __shfl_xor_sync(0xffffffffu, to, o);
-    }
-    if (lane == 0) {
-      const double g = dadd(dadd(dmul((double)tu, a.g_unmapped), dmul((double)to, a.g_occupied)), dmul((double)tf, a.g_free));
-      a.gain[v] = dmul(g, a.cube);
-      if (a.yaw_deg) a.yaw_deg[v] = 0;
-      if (a.counts) { a.counts[3 * v] = tu; a.counts[3 * v + 1] = tf; a.counts[3 * v + 2] = to; }
-    }
-    return;
-  }
-  // 72 window centres, 5 degrees apart; each lane sums its windows in the reference's order.
-  double best = 0.0;
-  int best_c = 1 << 20;  // candidate ordinal; "none" sorts last
-  for (int cidx = lane; cidx < 72; cidx += 32) {
-    const int i = -180 + 5 * cidx;
-    double cur = 0.0;
-    int left = (i + 180) - a.half_hfov;
-    if (left < 0) {
-      for (int j = 360 + left; j < 360; ++j) cur = dadd(cur, vg[j]);
-      left = 0;
-    }
-    int right = (i + 180) + a.half_hfov;
-    if (right >= 360) {
-      for (int j = 0; j < right - 359; ++j) cur = dadd(cur, vg[j]);
-      right = 359;
-    }
-    for (int j = left; j <= right; ++j) cur = dadd(cur, vg[j]);
-    if (cur > best) { best = cur; best_c = cidx; }  // strict: first maximum of this lane
-  }
-  // Warp arg-max, ties -> lowest ordinal (= first strict maximum of the sequential scan).
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
-    if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
-  }
-  const int yaw = (best_c < 72) ? (-180 + 5 * best_c) : 0;  // max_gain_yaw starts at 0 (rrt.cpp:450)
-  if (a.counts) {
-    unsigned long long wu = 0, wf = 0, wo = 0;
-    for (int d = -a.half_hfov + lane; d <= a.half_hfov; d += 32) {
-      const int j = (((yaw + 180 + d) % 360) + 360) % 360;
-      wu += c[3 * j]; wf += c[3 * j + 1]; wo += c[3 * j + 2];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      wu += __shfl_xor_sync(0xffffffffu, wu, o);
-      wf += __shfl_xor_sync(0xffffffffu, wf, o);
-      wo += __shfl_xor_sync(0xffffffffu, wo, o);
-    }
-    if (lane == 0) { a.counts[3 * v] = wu; a.counts[3 * v + 1] = wf; a.counts[3 * v + 2] = wo; }
-  }
-  if (lane == 0) {
-    a.gain[v] = dmul(best, a.cube);  // rrt.cpp:478
-    if (a.yaw_deg) a.yaw_deg[v] = yaw;
-  }
+  if (FUSE) fused_best_yaw(a, v, chunks, tid, reinterpret_cast<double*>(smem_raw));  // barrier inside: S.um is dead after it
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1081,8 +1115,45 @@ __global__ void k_expand_status(uint8_t* status, const uint8_t* __restrict__ edg
 }
 
 // ---------------------------------------------------------------------------------------------
-// HighResManager::checkMotion (voxblox_manager.h:89-108).  One thread per segment.
+// HighResManager::checkMotion (voxblox_manager.h:89-108).
 // ---------------------------------------------------------------------------------------------
+struct SegmentWalk {  // RayCaster state of one segment (integrator_utils.cc:127-179, float arithmetic)
+  int g[3], sg[3];
+  float t[3], dt[3];
+  int len;
+  bool ok;  // end points finite and in range
+};
+
+__device__ __forceinline__ void segment_setup(const double* s6, float voxel_size, SegmentWalk& w) {
+  w.len = 0;
+  w.ok = true;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float s = __fdiv_rn(__double2float_rn(s6[k]), voxel_size);      // :96-98 float division
+    const float e = __fdiv_rn(__double2float_rn(s6[3 + k]), voxel_size);
+    if (!(fabsf(s) < 4194304.0f) || !(fabsf(e) < 4194304.0f)) w.ok = false;  // non-finite / out of range
+    w.g[k] = (int)floorf(__fadd_rn(s, 1e-6f));
+    const int ei = (int)floorf(__fadd_rn(e, 1e-6f));
+    w.len += abs(ei - w.g[k]);
+    const float rr = __fsub_rn(e, s);
+    w.sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
+    const float shifted = __fsub_rn(s, (float)w.g[k]);
+    const float dist = __fsub_rn((float)max(0, w.sg[k]), shifted);
+    w.t[k] = __fdiv_rn(dist, rr);
+    w.dt[k] = __fdiv_rn((float)w.sg[k], rr);
+  }
+}
+
+__device__ __forceinline__ void segment_advance(SegmentWalk& w) {
+  const bool c1 = w.t[1] < w.t[0];
+  const float bm = c1 ? w.t[1] : w.t[0];
+  const bool c2 = w.t[2] < bm;
+  if (c2) { w.g[2] += w.sg[2]; w.t[2] = __fadd_rn(w.t[2], w.dt[2]); }
+  else if (c1) { w.g[1] += w.sg[1]; w.t[1] = __fadd_rn(w.t[1], w.dt[1]); }
+  else { w.g[0] += w.sg[0]; w.t[0] = __fadd_rn(w.t[0], w.dt[0]); }
+}
+
+// One thread per segment (large batches).
 __global__ void __launch_bounds__(128) k_check_segments(LayerView L, float voxel_size, double radius,
                                                         const double* __restrict__ seg, int n, uint8_t* is_free,
                                                         unsigned long long* totals) {
@@ -1090,45 +1161,23 @@ __global__ void __launch_bounds__(128) k_check_segments(LayerView L, float voxel
   unsigned long long steps = 0ull;
   if (i < n) {
     const int lv = L.log2vps, vm = (1 << lv) - 1;
-    int g[3], sg[3];
-    float t[3], dt[3];
-    int len = 0;
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const float s = __fdiv_rn(__double2float_rn(seg[6 * i + k]), voxel_size);      // :96-98 float division
-      const float e = __fdiv_rn(__double2float_rn(seg[6 * i + 3 + k]), voxel_size);
-      if (!(fabsf(s) < 4194304.0f) || !(fabsf(e) < 4194304.0f)) ok = false;          // non-finite / out of range
-      g[k] = (int)floorf(__fadd_rn(s, 1e-6f));
-      const int ei = (int)floorf(__fadd_rn(e, 1e-6f));
-      len += abs(ei - g[k]);
-      const float rr = __fsub_rn(e, s);
-      sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
-      const float shifted = __fsub_rn(s, (float)g[k]);
-      const float dist = __fsub_rn((float)max(0, sg[k]), shifted);
-      t[k] = __fdiv_rn(dist, rr);
-      dt[k] = __fdiv_rn((float)sg[k], rr);
-    }
-    bool free_seg = ok;
-    if (ok) {
+    SegmentWalk w;
+    segment_setup(seg + 6 * (size_t)i, voxel_size, w);
+    bool free_seg = w.ok;
+    if (w.ok) {
       int cbx = INT_MIN, cby = 0, cbz = 0, cslot = -1;
-      for (int step = 0; step <= len; ++step) {
+      for (int step = 0; step <= w.len; ++step) {
         ++steps;
-        const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
+        const int bx = w.g[0] >> lv, by = w.g[1] >> lv, bz = w.g[2] >> lv;
         if (bx != cbx || by != cby || bz != cbz) {
           cbx = bx; cby = by; cbz = bz;
           cslot = probe_block(L, bx, by, bz);
         }
         if (cslot < 0) { free_seg = false; break; }  // voxel == nullptr -> collision (voxblox_manager.cpp:125-127)
-        const int lin = (g[0] & vm) | ((g[1] & vm) << lv) | ((g[2] & vm) << (2 * lv));
+        const int lin = (w.g[0] & vm) | ((w.g[1] & vm) << lv) | ((w.g[2] & vm) << (2 * lv));
         const float d = __ldg(reinterpret_cast<const float*>(L.tiles) + (size_t)cslot * L.nvox + lin);
         if (radius >= (double)d) { free_seg = false; break; }  // :128
-        const bool c1 = t[1] < t[0];
-        const float bm = c1 ? t[1] : t[0];
-        const bool c2 = t[2] < bm;
-        if (c2) { g[2] += sg[2]; t[2] = __fadd_rn(t[2], dt[2]); }
-        else if (c1) { g[1] += sg[1]; t[1] = __fadd_rn(t[1], dt[1]); }
-        else { g[0] += sg[0]; t[0] = __fadd_rn(t[0], dt[0]); }
+        segment_advance(w);
       }
     }
     is_free[i] = free_seg ? 1 : 0;
@@ -1136,6 +1185,59 @@ __global__ void __launch_bounds__(128) k_check_segments(LayerView L, float voxel
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) steps += __shfl_xor_sync(0xffffffffu, steps, o);
   if ((threadIdx.x & 31) == 0 && steps) atomicAdd(totals + 2, steps);
+}
+
+// One warp per segment (small batches, where the latency of one call is what counts): the walk itself is cheap
+// arithmetic and sequential, the block probe and the distance load of each voxel are what takes time -- so every lane
+// runs the same walk, lane s keeps the voxel of step base + s, and the 32 voxels are then looked up at once.  The first
+// failing step decides, exactly as in the sequential loop (same flag, same count of executed steps).
+struct SegmentByValue { double v[6]; };  // a single segment passed in the launch arguments (seg == nullptr)
+
+__global__ void __launch_bounds__(128) k_check_segments_warp(LayerView L, float voxel_size, double radius,
+                                                             const double* __restrict__ seg, SegmentByValue one, int n,
+                                                             uint8_t* is_free, unsigned long long* totals) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const int lv = L.log2vps, vm = (1 << lv) - 1;
+  double s6[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s6[k] = seg ? seg[6 * (size_t)i + k] : one.v[k];
+  SegmentWalk w;
+  segment_setup(s6, voxel_size, w);
+  bool free_seg = w.ok;
+  unsigned long long steps = 0ull;
+  if (w.ok) {
+    for (int base = 0; base <= w.len; base += 32) {
+      const int cnt = min(32, w.len + 1 - base);
+      int mx = 0, my = 0, mz = 0;
+      for (int s = 0; s < cnt; ++s) {
+        if (lane == s) { mx = w.g[0]; my = w.g[1]; mz = w.g[2]; }
+        segment_advance(w);
+      }
+      bool fail = false;
+      if (lane < cnt) {
+        const int slot = probe_block(L, mx >> lv, my >> lv, mz >> lv);
+        if (slot < 0) {
+          fail = true;  // voxel == nullptr -> collision (voxblox_manager.cpp:125-127)
+        } else {
+          const int lin = (mx & vm) | ((my & vm) << lv) | ((mz & vm) << (2 * lv));
+          const float d = __ldg(reinterpret_cast<const float*>(L.tiles) + (size_t)slot * L.nvox + lin);
+          fail = radius >= (double)d;  // :128
+        }
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, fail);
+      if (m) {
+        steps += (unsigned)__ffs(m);
+        free_seg = false;
+        break;
+      }
+      steps += (unsigned)cnt;
+    }
+  }
+  if (lane == 0) {
+    is_free[i] = free_seg ? 1 : 0;
+    if (steps) atomicAdd(totals + 2, steps);
+  }
 }
 
 }  // namespace nbvgpu

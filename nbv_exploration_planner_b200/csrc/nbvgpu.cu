@@ -56,7 +56,7 @@ struct PinBuf {  // grow-only pinned host staging
     if (bytes <= cap) return cudaSuccess;
     size_t want = bytes + bytes / 2 + 4096;
     void* q = nullptr;
-    cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocMapped);  // kernels of the small-batch paths read / write it in place
     if (e != cudaSuccess) return e;
     if (p) {
       if (keep) memcpy(q, p, cap);
@@ -157,6 +157,10 @@ struct nbvgpu_ctx {
   float dense_vs = 0.f;
   unsigned long long dense_gen = ~0ull, cam_gen = 0;
   int force_yc = 0;  // NBVGPU_YC environment override (experiments)
+  DevBuf d_arrive;  // per-candidate CTA arrival counters of the fused sweep (zero between launches)
+  bool no_fuse = false;                        // NBVGPU_NO_FUSE: keep the two-launch path for small batches (experiments)
+  bool no_small = false;                       // NBVGPU_NO_SMALL_PATH: small batches go through the staged copies (experiments)
+  unsigned long long stats_fused = 0;          // ray-sweep launches that finished with the fused window scan (tests)
   unsigned long long stats_dense_clipped = 0;  // ray-sweep launches that used the z-clipped dense volume (tests)
   int dense_budget = 55 * 1024;  // shared memory per CTA the dense volume path may use (NBVGPU_DENSE_KB)
   int smem_pad = 0;              // extra dynamic shared memory per CTA (NBVGPU_SMEM_PAD_KB; occupancy experiments)
@@ -293,7 +297,12 @@ int check_position_range(const nbvgpu_ctx* ctx, const LayerHost* L, size_t n, co
   return NBVGPU_OK;
 }
 
-template <int V, int LV, int MODE>
+// Batches up to this size take the small-batch paths: inputs read and results written in place in mapped pinned host
+// memory (no copy operations in the stream) and, on the dense sweep, the window scan fused into the sweep's last CTA.
+constexpr size_t kFusedMaxCandidates = 64;
+constexpr size_t kSmallBatch = 64;
+
+template <int V, int LV, int MODE, bool FUSE = false>
 cudaError_t launch_gain_as(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
   // the opt-in limit is a property of the function (per device): raise it only when a launch needs more than any
   // before it on that device -- a driver call per launch is a measurable part of a single-candidate evaluation
@@ -305,12 +314,12 @@ cudaError_t launch_gain_as(const GainArgs& a, size_t smem, unsigned grid, cudaSt
     std::lock_guard<std::mutex> lk(mu);
     size_t& have = granted[dev];
     if (smem > have) {
-      cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV, MODE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       have = smem;
     }
   }
-  k_gain<V, LV, MODE><<<grid, kGainThreads, smem, s>>>(a);
+  k_gain<V, LV, MODE, FUSE><<<grid, kGainThreads, smem, s>>>(a);
   return cudaGetLastError();
 }
 // mode: kDense / kGrid / kProbe (gain_kernels.cuh).  16 voxels per side (the Voxblox default) gets
@@ -333,8 +342,11 @@ __global__ void k_pos_zrange(const double* __restrict__ pos, const uint8_t* __re
 }
 
 // Enqueue: ray sweep + best yaw for n resident positions.  d_per_yaw may be null (scratch used).
+// pos1 (host, 3 doubles, n == 1): passed to the fused kernel by value when that kernel is the one launched; d_pos must be
+// valid regardless (the other kernels read it).
 int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, double* d_gain, int32_t* d_yaw_deg,
-                 uint64_t* d_counts, uint32_t* d_per_yaw, uint64_t* d_steps, const uint8_t* d_valid = nullptr) {
+                 uint64_t* d_counts, uint32_t* d_per_yaw, uint64_t* d_steps, const uint8_t* d_valid = nullptr,
+                 const double* pos1 = nullptr) {
   if (n == 0) return NBVGPU_OK;
   if (n > (size_t)INT_MAX / 1080) return fail(ctx, NBVGPU_ERR_INVALID, "too many candidates in one call");
   if (!d_per_yaw) {
@@ -510,24 +522,6 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     ctx->prof_used++;
     CK(cudaEventRecord(ev0, ctx->stream));
   }
-  const int mode = gdim > 0 ? kGrid : kProbe;
-  switch (variant) {
-    case 1: e = launch_gain<1>(a, smem, grid, ctx->stream, mode); break;
-    case 2:
-      e = dense ? (a.zclip ? launch_gain_as<2, 4, kDenseClip>(a, smem, grid, ctx->stream) : launch_gain_as<2, 4, kDense>(a, smem, grid, ctx->stream))
-                : launch_gain<2>(a, smem, grid, ctx->stream, mode);
-      break;
-    case 3: e = launch_gain<3>(a, smem, grid, ctx->stream, mode); break;
-    case 4: e = launch_gain<0>(a, smem, grid, ctx->stream, mode); break;
-    case 5: e = launch_gain<2>(a, smem, grid, ctx->stream, mode); break;
-    default:
-      e = dense ? (a.zclip ? launch_gain_as<0, 4, kDenseClip>(a, smem, grid, ctx->stream) : launch_gain_as<0, 4, kDense>(a, smem, grid, ctx->stream))
-                : launch_gain<0>(a, smem, grid, ctx->stream, mode);
-      break;
-  }
-  if (ev1) cudaEventRecord(ev1, ctx->stream);
-  CK(e);
-  ctx->stats.kernel_launches++;
   BestYawArgs b;
   b.per_yaw = d_per_yaw;
   b.gain = d_gain;
@@ -540,14 +534,70 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   b.half_hfov = T.half_hfov;
   b.sum_all = ctx->cam.sum_all_yaws ? 1 : 0;
   b.n = (int)n;
+  // Small batches on the dense kernel: the window scan runs in the last CTA of each candidate (one launch instead of
+  // two -- what a single-candidate evaluation, the reference's own calling pattern, is made of).
+  const bool fused = dense && !a.zclip && n <= kFusedMaxCandidates && (variant == 0 || variant == 2) && !ctx->no_fuse;
+  a.by = b;
+  a.arrive = nullptr;
+  a.pos1[0] = a.pos1[1] = a.pos1[2] = 0.0;
+  if (fused) {
+    if (!ctx->d_arrive.p) {
+      CK(ctx->d_arrive.reserve(kFusedMaxCandidates * sizeof(int)));
+      CK(cudaMemsetAsync(ctx->d_arrive.p, 0, kFusedMaxCandidates * sizeof(int), ctx->stream));
+    }
+    a.arrive = ctx->d_arrive.as<int>();
+    if (pos1 && n == 1 && !d_valid) {
+      a.pos = nullptr;
+      for (int k = 0; k < 3; ++k) a.pos1[k] = pos1[k];
+    }
+    if (smem < kFusedScratchBytes + 16) smem = kFusedScratchBytes + 16;
+  }
+  const int mode = gdim > 0 ? kGrid : kProbe;
+  switch (variant) {
+    case 1: e = launch_gain<1>(a, smem, grid, ctx->stream, mode); break;
+    case 2:
+      e = fused ? launch_gain_as<2, 4, kDense, true>(a, smem, grid, ctx->stream)
+          : dense ? (a.zclip ? launch_gain_as<2, 4, kDenseClip>(a, smem, grid, ctx->stream) : launch_gain_as<2, 4, kDense>(a, smem, grid, ctx->stream))
+                  : launch_gain<2>(a, smem, grid, ctx->stream, mode);
+      break;
+    case 3: e = launch_gain<3>(a, smem, grid, ctx->stream, mode); break;
+    case 4: e = launch_gain<0>(a, smem, grid, ctx->stream, mode); break;
+    case 5: e = launch_gain<2>(a, smem, grid, ctx->stream, mode); break;
+    default:
+      e = fused ? launch_gain_as<0, 4, kDense, true>(a, smem, grid, ctx->stream)
+          : dense ? (a.zclip ? launch_gain_as<0, 4, kDenseClip>(a, smem, grid, ctx->stream) : launch_gain_as<0, 4, kDense>(a, smem, grid, ctx->stream))
+                  : launch_gain<0>(a, smem, grid, ctx->stream, mode);
+      break;
+  }
+  if (ev1) cudaEventRecord(ev1, ctx->stream);
+  CK(e);
+  ctx->stats.kernel_launches++;
+  if (fused) {
+    ctx->stats_fused++;
+    return NBVGPU_OK;
+  }
   k_best_yaw<<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(b);
   CK(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return NBVGPU_OK;
 }
 
-int enqueue_segments(nbvgpu_ctx* ctx, LayerHost* L, double radius, size_t n, const double* d_seg, uint8_t* d_free) {
+// seg1 (host, 6 doubles, n == 1): the segment travels in the launch arguments instead of being read from d_seg.
+int enqueue_segments(nbvgpu_ctx* ctx, LayerHost* L, double radius, size_t n, const double* d_seg, uint8_t* d_free,
+                     const double* seg1 = nullptr) {
   if (n == 0) return NBVGPU_OK;
+  if (n <= kSmallBatch && !ctx->no_small) {  // one warp per segment: the voxels of a segment are looked up 32 at a time
+    SegmentByValue one = {};
+    if (seg1 && n == 1) {
+      for (int k = 0; k < 6; ++k) one.v[k] = seg1[k];
+      d_seg = nullptr;
+    }
+    k_check_segments_warp<<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(L->view(), L->voxel_size, radius, d_seg, one, (int)n,
+                                                                           d_free, ctx->d_totals);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    return NBVGPU_OK;
+  }
   k_check_segments<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(L->view(), L->voxel_size, radius, d_seg, (int)n,
                                                                          d_free, ctx->d_totals);
   CK(cudaGetLastError());
@@ -606,6 +656,8 @@ int nbvgpu_create(int device, nbvgpu_ctx** out) {
   if (const char* e = std::getenv("NBVGPU_YC")) ctx->force_yc = std::atoi(e);
   if (const char* e = std::getenv("NBVGPU_DENSE_KB")) ctx->dense_budget = std::atoi(e) * 1024;
   if (const char* e = std::getenv("NBVGPU_SMEM_PAD_KB")) ctx->smem_pad = std::atoi(e) * 1024;
+  ctx->no_fuse = std::getenv("NBVGPU_NO_FUSE") != nullptr;
+  ctx->no_small = std::getenv("NBVGPU_NO_SMALL_PATH") != nullptr;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   DeviceGuard guard(device);
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -636,7 +688,7 @@ void nbvgpu_destroy(nbvgpu_ctx* ctx) {
     ctx->h_io.release();
     for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
     for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
-                      &ctx->d_free, &ctx->d_aux, &ctx->d_best, &ctx->d_zrange, &ctx->d_fr_cells, &ctx->d_fr_cur, &ctx->d_fr_next,
+                      &ctx->d_free, &ctx->d_aux, &ctx->d_best, &ctx->d_zrange, &ctx->d_arrive, &ctx->d_fr_cells, &ctx->d_fr_cur, &ctx->d_fr_next,
                       &ctx->d_fr_slots, &ctx->d_fr_io})
       b->release();
     for (auto& pr : ctx->prof_events) {
@@ -1028,6 +1080,20 @@ int nbvgpu_gain_eval(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, do
   int32_t* d_yaw = reinterpret_cast<int32_t*>(d_out + n * 8);
   uint64_t* d_counts = reinterpret_cast<uint64_t*>(d_out + n * 16);
   uint64_t* d_steps = reinterpret_cast<uint64_t*>(d_out + n * 40);
+  if (n <= kSmallBatch && !per_yaw && !steps && !ctx->no_small) {
+    // small batch: the kernels read the positions from and write the results to the staging area itself
+    char* hd = nullptr;
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&hd), h, 0));
+    const int rc = enqueue_gain(ctx, L, n, reinterpret_cast<const double*>(hd), reinterpret_cast<double*>(hd + o_gain),
+                                reinterpret_cast<int32_t*>(hd + o_yaw), counts ? reinterpret_cast<uint64_t*>(hd + o_counts) : nullptr,
+                                nullptr, nullptr, nullptr, n == 1 ? pos : nullptr);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(gain, h + o_gain, n * 8);
+    if (yaw_deg) memcpy(yaw_deg, h + o_yaw, n * 4);
+    if (counts) memcpy(counts, h + o_counts, n * 24);
+    return NBVGPU_OK;
+  }
   if (per_yaw) CK(ctx->d_per_yaw.reserve(n * 1080 * sizeof(uint32_t)));
   CK(cudaMemcpyAsync(ctx->d_pos.p, h, n * 24, cudaMemcpyHostToDevice, ctx->stream));
   const int rc = enqueue_gain(ctx, L, n, ctx->d_pos.as<double>(), d_gain, d_yaw, counts ? d_counts : nullptr, nullptr, steps ? d_steps : nullptr);
@@ -1209,6 +1275,16 @@ int nbvgpu_check_segments(nbvgpu_ctx* ctx, int layer, double radius, size_t n, c
   CK(ctx->d_free.reserve(n));
   char* h = ctx->h_io.as<char>();
   memcpy(h, seg, n * 48);
+  if (n <= kSmallBatch && !ctx->no_small) {  // small batch: end points read from, flags written to the staging area itself
+    char* hd = nullptr;
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&hd), h, 0));
+    const int rc = enqueue_segments(ctx, L, radius, n, reinterpret_cast<const double*>(hd), reinterpret_cast<uint8_t*>(hd + n * 48),
+                                    n == 1 ? seg : nullptr);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(is_free, h + n * 48, n);
+    return NBVGPU_OK;
+  }
   CK(cudaMemcpyAsync(ctx->d_seg.p, h, n * 48, cudaMemcpyHostToDevice, ctx->stream));
   const int rc = enqueue_segments(ctx, L, radius, n, ctx->d_seg.as<double>(), ctx->d_free.as<uint8_t>());
   if (rc) return rc;
@@ -1490,6 +1566,14 @@ int nbvgpu_probe_l2_read_bandwidth(nbvgpu_ctx* ctx, size_t bytes, int iters, dou
   cudaFree(sink);
   if (e != cudaSuccess || !(ms > 0.f)) return fail(ctx, NBVGPU_ERR_CUDA, "L2 probe failed");
   *gb_per_s = (double)n_vec * 16.0 * (double)iters / ((double)ms * 1e-3) / 1e9;
+  return NBVGPU_OK;
+}
+
+// Ray-sweep launches (since context creation) that ran the window scan in their last CTA (small batches); for tests.
+int nbvgpu_debug_fused_launches(nbvgpu_ctx* ctx, uint64_t* out) {
+  if (!ctx || !out) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  *out = ctx->stats_fused;
   return NBVGPU_OK;
 }
 

@@ -317,6 +317,12 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_debug_dense_clipped_launches(self._h, C.byref(out)))
         return int(out.value)
 
+    def fused_launches(self) -> int:
+        """ray-sweep launches that finished with the window scan fused into their last CTA (small batches; tests)."""
+        out = C.c_uint64(0)
+        self._ck(self._L.nbvgpu_debug_fused_launches(self._h, C.byref(out)))
+        return int(out.value)
+
     def frontier_hash_redo(self) -> int:
         """vertices the dense visited set of the flood fill handed back to the hash-keyed one (tests)."""
         out = C.c_uint64(0)
