@@ -44,7 +44,7 @@ struct FilterConst {
   float m, mh, mv;  // margins (plain, scaled for the horizontal / vertical side planes)
 };
 
-// arguments of the best-yaw scan (best_yaw_warp below)
+// arguments of the best-yaw scan (best_yaw_cta below)
 struct BestYawArgs {
   const uint32_t* per_yaw;  // [n][360][3]
   double* gain;             // [n]
@@ -353,21 +353,28 @@ inline size_t dense_smem_bytes(int yc, int gn, int nvol) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Best yaw (rrt.cpp:449-478) / all-yaw sum (rrt.cpp:571-578).  One warp per candidate.
+// Best yaw (rrt.cpp:449-478) / all-yaw sum (rrt.cpp:571-578).
 // ---------------------------------------------------------------------------------------------
-// One warp, candidate v; vg: 360 doubles of shared memory owned by the warp.  The counts are read through L2
-// (__ldcg): in the fused sweep they were written by other CTAs of the same launch.
-__device__ __forceinline__ void best_yaw_warp(const BestYawArgs& a, int v, double* vg, int lane) {
+// The whole CTA (a multiple of 32 threads, at least 96) works on candidate v; vg: 360 doubles of shared memory.  The
+// counts are read through L2 (__ldcg): in the fused sweep they were written by other CTAs of the same launch.  A window's
+// sum must keep the reference's order (floating-point addition), so it is one sequential chain -- but the 72 windows are
+// independent: one thread each.  Must be called by all threads of the CTA (barriers inside).
+__device__ __forceinline__ void best_yaw_cta(const BestYawArgs& a, int v, double* vg, int tid, int nthreads) {
+  __shared__ unsigned long long s_tot[3];
+  __shared__ double s_wbest[3];
+  __shared__ int s_wc[3];
+  const int lane = tid & 31, warp = tid >> 5;
   const uint32_t* c = a.per_yaw + (size_t)v * 1080;
   unsigned long long tu = 0, tf = 0, to = 0;
-  for (int j = lane; j < 360; j += 32) {
+  if (tid < 3) s_tot[tid] = 0ull;
+  for (int j = tid; j < 360; j += nthreads) {
     const uint32_t nu = __ldcg(c + 3 * j), nf = __ldcg(c + 3 * j + 1), no = __ldcg(c + 3 * j + 2);
     // vertical_gain[j]: the running sum of rrt.cpp:436-443 in count form.
     vg[j] = dadd(dadd(dmul((double)nu, a.g_unmapped), dmul((double)no, a.g_occupied)), dmul((double)nf, a.g_free));
     tu += nu; tf += nf; to += no;
   }
-  __syncwarp();
-  if (a.sum_all) {
+  __syncthreads();
+  if (a.sum_all) {  // RrtTree::gain: integer totals (exact in any order), one product at the end
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       tu += __shfl_xor_sync(0xffffffffu, tu, o);
@@ -375,6 +382,13 @@ __device__ __forceinline__ void best_yaw_warp(const BestYawArgs& a, int v, doubl
       to += __shfl_xor_sync(0xffffffffu, to, o);
     }
     if (lane == 0) {
+      atomicAdd(&s_tot[0], tu);
+      atomicAdd(&s_tot[1], tf);
+      atomicAdd(&s_tot[2], to);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      tu = s_tot[0]; tf = s_tot[1]; to = s_tot[2];
       const double g = dadd(dadd(dmul((double)tu, a.g_unmapped), dmul((double)to, a.g_occupied)), dmul((double)tf, a.g_free));
       a.gain[v] = dmul(g, a.cube);
       if (a.yaw_deg) a.yaw_deg[v] = 0;
@@ -382,11 +396,11 @@ __device__ __forceinline__ void best_yaw_warp(const BestYawArgs& a, int v, doubl
     }
     return;
   }
-  // 72 window centres, 5 degrees apart; each lane sums its windows in the reference's order.
+  // 72 window centres, 5 degrees apart; thread cidx sums its window in the reference's order.
   double best = 0.0;
   int best_c = 1 << 20;  // candidate ordinal; "none" sorts last
-  for (int cidx = lane; cidx < 72; cidx += 32) {
-    const int i = -180 + 5 * cidx;
+  if (tid < 72) {
+    const int i = -180 + 5 * tid;
     double cur = 0.0;
     int left = (i + 180) - a.half_hfov;
     if (left < 0) {
@@ -399,13 +413,26 @@ __device__ __forceinline__ void best_yaw_warp(const BestYawArgs& a, int v, doubl
       right = 359;
     }
     for (int j = left; j <= right; ++j) cur = dadd(cur, vg[j]);
-    if (cur > best) { best = cur; best_c = cidx; }  // strict: first maximum of this lane
+    if (cur > best) { best = cur; best_c = tid; }  // strict, against the initial 0.0 (rrt.cpp:449)
   }
-  // Warp arg-max, ties -> lowest ordinal (= first strict maximum of the sequential scan).
+  // arg-max, ties -> lowest ordinal (= the first strict maximum of the sequential scan)
+  if (warp < 3) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, best_c, o);
+      if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
+    }
+    if (lane == 0) { s_wbest[warp] = best; s_wc[warp] = best_c; }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  best = s_wbest[0];
+  best_c = s_wc[0];
+#pragma unroll
+  for (int w = 1; w < 3; ++w) {
+    const double ob = s_wbest[w];
+    const int oc = s_wc[w];
     if (ob > best || (ob == best && oc < best_c)) { best = ob; best_c = oc; }
   }
   const int yaw = (best_c < 72) ? (-180 + 5 * best_c) : 0;  // max_gain_yaw starts at 0 (rrt.cpp:450)
@@ -429,27 +456,25 @@ __device__ __forceinline__ void best_yaw_warp(const BestYawArgs& a, int v, doubl
   }
 }
 
+// One CTA per candidate.
 __global__ void __launch_bounds__(128) k_best_yaw(const BestYawArgs a) {
-  __shared__ double vg_all[4][360];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int v = blockIdx.x * 4 + warp;
-  if (v >= a.n) return;
-  best_yaw_warp(a, v, vg_all[warp], lane);
+  __shared__ double vg[360];
+  best_yaw_cta(a, (int)blockIdx.x, vg, (int)threadIdx.x, (int)blockDim.x);
 }
 
 // Fused finish of k_gain<..., FUSE = true>: every CTA of candidate v arrives here after its per-yaw counts are written;
-// the last one runs the window scan on its first warp (the threadFenceReduction pattern: fence, count, fence, read
-// through L2) and resets the counter for the next launch.  `scratch`: 360 doubles of shared memory nobody uses any more.
+// the last one runs the window scan (the threadFenceReduction pattern: fence, count, fence, read through L2) and resets
+// the counter for the next launch.  `scratch`: 360 doubles of shared memory nobody uses any more.
 __device__ __forceinline__ void fused_best_yaw(const GainArgs& a, int v, int chunks, int tid, double* scratch) {
   __shared__ int s_last;
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(a.arrive + v, 1) == chunks - 1) ? 1 : 0;
   __syncthreads();
-  if (s_last && tid < 32) {
+  if (s_last) {  // CTA-uniform
     __threadfence();
     if (tid == 0) a.arrive[v] = 0;
-    best_yaw_warp(a.by, v, scratch, tid);
+    best_yaw_cta(a.by, v, scratch, tid, (int)blockDim.x);
   }
 }
 constexpr size_t kFusedScratchBytes = 360 * sizeof(double);  // the launch reserves at least this much dynamic shared memory

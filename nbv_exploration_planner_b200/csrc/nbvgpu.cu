@@ -576,7 +576,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     ctx->stats_fused++;
     return NBVGPU_OK;
   }
-  k_best_yaw<<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(b);
+  k_best_yaw<<<(unsigned)n, 128, 0, ctx->stream>>>(b);
   CK(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return NBVGPU_OK;
