@@ -55,7 +55,19 @@ struct BestYawArgs {
   int half_hfov;
   int sum_all;
   int n;
+  // single-candidate host calls: after the results are written (to mapped host memory) the writing thread publishes
+  // `seq` at `done` (mapped host memory as well), which the host polls instead of synchronising the stream; else null
+  unsigned* done;
+  unsigned seq;
 };
+
+// Publish the completion ticket of a single-item host call: results first, system-wide fence, then the ticket.
+__device__ __forceinline__ void publish_done(unsigned* done, unsigned seq) {
+  if (done) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned*>(done) = seq;
+  }
+}
 
 struct GainArgs {
   LayerView L;
@@ -393,6 +405,7 @@ __device__ __forceinline__ void best_yaw_cta(const BestYawArgs& a, int v, double
       a.gain[v] = dmul(g, a.cube);
       if (a.yaw_deg) a.yaw_deg[v] = 0;
       if (a.counts) { a.counts[3 * v] = tu; a.counts[3 * v + 1] = tf; a.counts[3 * v + 2] = to; }
+      publish_done(a.done, a.seq);
     }
     return;
   }
@@ -453,6 +466,7 @@ __device__ __forceinline__ void best_yaw_cta(const BestYawArgs& a, int v, double
   if (lane == 0) {
     a.gain[v] = dmul(best, a.cube);  // rrt.cpp:478
     if (a.yaw_deg) a.yaw_deg[v] = yaw;
+    publish_done(a.done, a.seq);
   }
 }
 
@@ -1220,7 +1234,8 @@ struct SegmentByValue { double v[6]; };  // a single segment passed in the launc
 
 __global__ void __launch_bounds__(128) k_check_segments_warp(LayerView L, float voxel_size, double radius,
                                                              const double* __restrict__ seg, SegmentByValue one, int n,
-                                                             uint8_t* is_free, unsigned long long* totals) {
+                                                             uint8_t* is_free, unsigned long long* totals, unsigned* done,
+                                                             unsigned seq) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n) return;
   const int lv = L.log2vps, vm = (1 << lv) - 1;
@@ -1262,6 +1277,7 @@ __global__ void __launch_bounds__(128) k_check_segments_warp(LayerView L, float 
   if (lane == 0) {
     is_free[i] = free_seg ? 1 : 0;
     if (steps) atomicAdd(totals + 2, steps);
+    publish_done(done, seq);  // single-segment host calls only (see BestYawArgs::done)
   }
 }
 

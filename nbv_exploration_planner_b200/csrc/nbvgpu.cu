@@ -157,6 +157,13 @@ struct nbvgpu_ctx {
   float dense_vs = 0.f;
   unsigned long long dense_gen = ~0ull, cam_gen = 0;
   int force_yc = 0;  // NBVGPU_YC environment override (experiments)
+  // completion ticket of single-item host calls: the kernel's last writer stores the call's sequence number here (mapped
+  // pinned memory) and the host polls it -- a few microseconds sooner than the stream synchronise reports the same thing
+  unsigned* h_ticket = nullptr;
+  unsigned* d_ticket = nullptr;  // device-side address of h_ticket
+  unsigned ticket_seq = 0;
+  unsigned* want_ticket = nullptr;  // set by a host entry point around its enqueue: the kernel should publish ticket_seq
+  bool no_poll = false;             // NBVGPU_NO_POLL: always synchronise the stream (experiments)
   DevBuf d_arrive;  // per-candidate CTA arrival counters of the fused sweep (zero between launches)
   bool no_fuse = false;                        // NBVGPU_NO_FUSE: keep the two-launch path for small batches (experiments)
   bool no_small = false;                       // NBVGPU_NO_SMALL_PATH: small batches go through the staged copies (experiments)
@@ -339,6 +346,39 @@ __global__ void k_pos_zrange(const double* __restrict__ pos, const uint8_t* __re
   const int g = (int)floor(z);
   atomicMin(out, g);
   atomicMax(out + 1, g);
+}
+
+// Completion ticket of a single-item host call (see nbvgpu_ctx::h_ticket).  ticket_arm() before the enqueue makes the
+// kernel publish a fresh sequence number; ticket_wait() polls for it, looking at the stream every so often so that a failed
+// launch or kernel cannot hang the caller, and leaves the stream's own state to the next synchronising call.
+static int ticket_arm(nbvgpu_ctx* ctx) {
+  ctx->want_ticket = nullptr;
+  if (ctx->no_poll) return NBVGPU_OK;
+  if (!ctx->h_ticket) {
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&ctx->h_ticket), 64, cudaHostAllocMapped));
+    *ctx->h_ticket = 0u;
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&ctx->d_ticket), ctx->h_ticket, 0));
+  }
+  if (++ctx->ticket_seq == 0u) ctx->ticket_seq = 1u;
+  ctx->want_ticket = ctx->d_ticket;
+  return NBVGPU_OK;
+}
+static int ticket_wait(nbvgpu_ctx* ctx) {
+  unsigned* const armed = ctx->want_ticket;
+  ctx->want_ticket = nullptr;
+  if (armed) {
+    const volatile unsigned* f = ctx->h_ticket;
+    const unsigned seq = ctx->ticket_seq;
+    for (unsigned it = 1;; ++it) {
+      if (*f == seq) return NBVGPU_OK;
+      if ((it & 0xfffu) == 0u) {
+        const cudaError_t q = cudaStreamQuery(ctx->stream);
+        if (q != cudaErrorNotReady) break;  // finished (the ticket is then visible) or failed: let the synchronise say which
+      }
+    }
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  return NBVGPU_OK;
 }
 
 // Enqueue: ray sweep + best yaw for n resident positions.  d_per_yaw may be null (scratch used).
@@ -534,6 +574,8 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   b.half_hfov = T.half_hfov;
   b.sum_all = ctx->cam.sum_all_yaws ? 1 : 0;
   b.n = (int)n;
+  b.done = n == 1 ? ctx->want_ticket : nullptr;
+  b.seq = ctx->ticket_seq;
   // Small batches on the dense kernel: the window scan runs in the last CTA of each candidate (one launch instead of
   // two -- what a single-candidate evaluation, the reference's own calling pattern, is made of).
   const bool fused = dense && !a.zclip && n <= kFusedMaxCandidates && (variant == 0 || variant == 2) && !ctx->no_fuse;
@@ -593,7 +635,8 @@ int enqueue_segments(nbvgpu_ctx* ctx, LayerHost* L, double radius, size_t n, con
       d_seg = nullptr;
     }
     k_check_segments_warp<<<(unsigned)((n + 3) / 4), 128, 0, ctx->stream>>>(L->view(), L->voxel_size, radius, d_seg, one, (int)n,
-                                                                           d_free, ctx->d_totals);
+                                                                           d_free, ctx->d_totals, n == 1 ? ctx->want_ticket : nullptr,
+                                                                           ctx->ticket_seq);
     CK(cudaGetLastError());
     ctx->stats.kernel_launches++;
     return NBVGPU_OK;
@@ -658,6 +701,7 @@ int nbvgpu_create(int device, nbvgpu_ctx** out) {
   if (const char* e = std::getenv("NBVGPU_SMEM_PAD_KB")) ctx->smem_pad = std::atoi(e) * 1024;
   ctx->no_fuse = std::getenv("NBVGPU_NO_FUSE") != nullptr;
   ctx->no_small = std::getenv("NBVGPU_NO_SMALL_PATH") != nullptr;
+  ctx->no_poll = std::getenv("NBVGPU_NO_POLL") != nullptr;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   DeviceGuard guard(device);
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -686,6 +730,7 @@ void nbvgpu_destroy(nbvgpu_ctx* ctx) {
     cudaFree(ctx->d_cs);
     cudaFree(ctx->d_totals);
     ctx->h_io.release();
+    if (ctx->h_ticket) cudaFreeHost(ctx->h_ticket);
     for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
     for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
                       &ctx->d_free, &ctx->d_aux, &ctx->d_best, &ctx->d_zrange, &ctx->d_arrive, &ctx->d_fr_cells, &ctx->d_fr_cur, &ctx->d_fr_next,
@@ -1084,11 +1129,15 @@ int nbvgpu_gain_eval(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, do
     // small batch: the kernels read the positions from and write the results to the staging area itself
     char* hd = nullptr;
     CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&hd), h, 0));
+    if (n == 1 && ticket_arm(ctx)) return NBVGPU_ERR_CUDA;
     const int rc = enqueue_gain(ctx, L, n, reinterpret_cast<const double*>(hd), reinterpret_cast<double*>(hd + o_gain),
                                 reinterpret_cast<int32_t*>(hd + o_yaw), counts ? reinterpret_cast<uint64_t*>(hd + o_counts) : nullptr,
                                 nullptr, nullptr, nullptr, n == 1 ? pos : nullptr);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (rc) {
+      ctx->want_ticket = nullptr;
+      return rc;
+    }
+    if (ticket_wait(ctx)) return NBVGPU_ERR_CUDA;
     memcpy(gain, h + o_gain, n * 8);
     if (yaw_deg) memcpy(yaw_deg, h + o_yaw, n * 4);
     if (counts) memcpy(counts, h + o_counts, n * 24);
@@ -1278,10 +1327,14 @@ int nbvgpu_check_segments(nbvgpu_ctx* ctx, int layer, double radius, size_t n, c
   if (n <= kSmallBatch && !ctx->no_small) {  // small batch: end points read from, flags written to the staging area itself
     char* hd = nullptr;
     CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&hd), h, 0));
+    if (n == 1 && ticket_arm(ctx)) return NBVGPU_ERR_CUDA;
     const int rc = enqueue_segments(ctx, L, radius, n, reinterpret_cast<const double*>(hd), reinterpret_cast<uint8_t*>(hd + n * 48),
                                     n == 1 ? seg : nullptr);
-    if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (rc) {
+      ctx->want_ticket = nullptr;
+      return rc;
+    }
+    if (ticket_wait(ctx)) return NBVGPU_ERR_CUDA;
     memcpy(is_free, h + n * 48, n);
     return NBVGPU_OK;
   }

@@ -140,7 +140,7 @@ def test_long_segments_one_warp_each(oracle_mod):
     g.close()
 
 
-@pytest.mark.parametrize("env", ["NBVGPU_NO_FUSE", "NBVGPU_NO_SMALL_PATH"])
+@pytest.mark.parametrize("env", ["NBVGPU_NO_FUSE", "NBVGPU_NO_SMALL_PATH", "NBVGPU_NO_POLL"])
 def test_paths_switched_off_give_the_same_results(oracle_mod, env, monkeypatch):
     m, o, lt_o, le_o, g, lt_g, le_g, c = _setup(oracle_mod)
     pos = c.positions[:12]
