@@ -1386,8 +1386,27 @@ int nbvgpu_esdf_distance_gradient(nbvgpu_ctx* ctx, int layer, size_t n, const do
   char* h = ctx->h_io.as<char>();
   char* d = ctx->d_aux.as<char>();
   memcpy(h, positions, in_bytes);
-  CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
   const EsdfView E = esdf_view_of(L);
+  if (n <= kSmallBatch && !ctx->no_small) {
+    // small batch: eight lanes per query, inputs read from and results written to the staging area itself
+    char* hd = nullptr;
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&hd), h, 0));
+    double* m_dist = reinterpret_cast<double*>(hd + in_bytes);
+    if (n == 1 && ticket_arm(ctx)) return NBVGPU_ERR_CUDA;
+    k_esdf_distance_gradient_group<<<(unsigned)((n * 8 + 127) / 128), 128, 0, ctx->stream>>>(
+        E, reinterpret_cast<const double*>(hd), (int)n, reinterpret_cast<uint8_t*>(m_dist + 4 * n), m_dist, m_dist + n,
+        n == 1 ? ctx->want_ticket : nullptr, ctx->ticket_seq);
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) ctx->want_ticket = nullptr;
+    CK(le);
+    ctx->stats.kernel_launches++;
+    if (ticket_wait(ctx)) return NBVGPU_ERR_CUDA;
+    memcpy(distance, h + in_bytes, n * 8);
+    memcpy(gradient, h + in_bytes + n * 8, n * 24);
+    memcpy(ok, h + in_bytes + n * 32, n);
+    return NBVGPU_OK;
+  }
+  CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
   double* d_dist = reinterpret_cast<double*>(d + in_bytes);
   double* d_grad = d_dist + n;
   uint8_t* d_ok = reinterpret_cast<uint8_t*>(d_grad + 3 * n);
@@ -1412,7 +1431,11 @@ int nbvgpu_esdf_distance_gradient_device(nbvgpu_ctx* ctx, int layer, size_t n, c
   if (n == 0) return NBVGPU_OK;
   if (n > 0x7fffffffull) return fail(ctx, NBVGPU_ERR_INVALID, "too many queries for one call");
   DeviceGuard guard(ctx->device);
-  k_esdf_distance_gradient<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(esdf_view_of(L), d_positions, (int)n, d_ok, d_distance, d_gradient);
+  if (n <= kSmallBatch && !ctx->no_small)
+    k_esdf_distance_gradient_group<<<(unsigned)((n * 8 + 127) / 128), 128, 0, ctx->stream>>>(esdf_view_of(L), d_positions, (int)n, d_ok, d_distance,
+                                                                                            d_gradient, nullptr, 0u);
+  else
+    k_esdf_distance_gradient<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(esdf_view_of(L), d_positions, (int)n, d_ok, d_distance, d_gradient);
   CK(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return NBVGPU_OK;

@@ -163,3 +163,38 @@ def test_failures_and_errors(oracle_mod, tiny_map):
     with pytest.raises(NbvGpuError):
         g.esdf_distance_gradient(le_g, [[float("nan"), 0.0, 0.0]])
     g.close()
+
+
+def test_small_batches_eight_lanes_per_query(oracle_mod, tiny_map):
+    """Up to 64 queries per call run on eight lanes each (distance, six gradient samples, the gradient's block probe) with
+    mapped in-place I/O; one query per call also uses the completion ticket.  Same results as the one-thread kernel and
+    the oracle, including failing queries with their partial gradient sums, and out-of-range device-resident inputs."""
+    import torch
+    o, le_o, g, le_g = _setup(oracle_mod, tiny_map)
+    q = _queries(tiny_map, np.random.default_rng(59), 2000)
+    ro = o.distance_and_gradient(le_o, q, threads=8)
+    big = g.esdf_distance_gradient(le_g, q)
+    for k in ("ok", "distance", "gradient"):
+        assert np.array_equal(big[k], ro[k]), k
+    part = np.flatnonzero((ro["ok"] == 0) & (np.abs(ro["gradient"]).sum(axis=1) > 0))
+    assert len(part) > 0, "no query with a partially summed failing gradient in the sample"
+    at = 0
+    for n in (1, 1, 2, 7, 8, 9, 31, 64, 1, 33):
+        r = g.esdf_distance_gradient(le_g, q[at:at + n])
+        for k in ("ok", "distance", "gradient"):
+            assert np.array_equal(r[k], ro[k][at:at + n]), (k, n, at)
+        at += n
+    for i in list(part[:20]) + list(np.flatnonzero(ro["ok"] == 1)[:20]):
+        r = g.esdf_distance_gradient(le_g, q[i:i + 1])
+        assert r["ok"][0] == ro["ok"][i] and r["distance"][0] == ro["distance"][i] and np.array_equal(r["gradient"][0], ro["gradient"][i])
+    d_q = torch.from_numpy(np.concatenate([q[:9], [[float("nan"), 0.0, 0.0], [1e9, 0.0, 0.0]]])).cuda()
+    d_ok = torch.full((11,), 7, dtype=torch.uint8, device="cuda")
+    d_dist = torch.full((11,), -1.0, dtype=torch.float64, device="cuda")
+    d_grad = torch.full((11, 3), -1.0, dtype=torch.float64, device="cuda")
+    g.esdf_distance_gradient_device(le_g, 11, d_q, d_ok, d_dist, d_grad)
+    g.synchronize()
+    torch.cuda.synchronize()
+    assert np.array_equal(d_ok.cpu().numpy()[:9], ro["ok"][:9]) and np.array_equal(d_dist.cpu().numpy()[:9], ro["distance"][:9])
+    assert np.array_equal(d_grad.cpu().numpy()[:9], ro["gradient"][:9])
+    assert not d_ok.cpu().numpy()[9:].any() and not d_dist.cpu().numpy()[9:].any() and not d_grad.cpu().numpy()[9:].any()
+    g.close()
