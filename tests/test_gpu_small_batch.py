@@ -107,6 +107,36 @@ def test_check_segments_small_equals_large(oracle_mod):
     g.close()
 
 
+def test_interleaved_single_calls_stress(oracle_mod):
+    """400 single-item and small-batch calls of all three kinds back to back (arrival counters, completion tickets and the
+    shared staging area are reused call after call): every result equals the large-batch one."""
+    m, o, lt_o, le_o, g, lt_g, le_g, c = _setup(oracle_mod)
+    pos, seg = c.positions, c.segments
+    big = g.gain_eval(lt_g, pos, steps=False)
+    free = g.check_segments(le_g, m.cfg.robot_radius, seg)
+    q = np.random.default_rng(5).uniform(m.cfg.bounds_min, m.cfg.bounds_max, (200, 3))
+    interp = g.esdf_distance_gradient(le_g, q)
+    rng = np.random.default_rng(11)
+    for it in range(400):
+        kind = int(rng.integers(0, 4))
+        n = 1 if rng.random() < 0.6 else int(rng.integers(2, 65))
+        at = int(rng.integers(0, 200 - n + 1))
+        if kind == 0:
+            r = g.gain_eval(lt_g, pos[at:at + n], steps=False)
+            assert np.array_equal(r["gain"], big["gain"][at:at + n]) and np.array_equal(r["yaw_deg"], big["yaw_deg"][at:at + n]), (it, n, at)
+            assert np.array_equal(r["counts"], big["counts"][at:at + n])
+        elif kind == 1:
+            assert np.array_equal(g.check_segments(le_g, m.cfg.robot_radius, seg[at:at + n]), free[at:at + n]), (it, n, at)
+        elif kind == 2:
+            r = g.esdf_distance_gradient(le_g, q[at:at + n])
+            for k in ("ok", "distance", "gradient"):
+                assert np.array_equal(r[k], interp[k][at:at + n]), (it, k, n, at)
+        else:
+            st = np.array([*pos[at], 0.0])
+            assert g.optimized_gain(lt_g, st) == big["gain"][at] and st[3] == big["yaw_deg"][at] * np.pi / 180.0
+    g.close()
+
+
 def test_long_segments_one_warp_each(oracle_mod):
     """Segments far longer than 32 voxels, mostly through observed free space on a low radius (several rounds of 32
     look-ups before the first failing voxel), plus degenerate ones: flag and executed ESDF steps equal the oracle's."""
