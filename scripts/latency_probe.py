@@ -83,6 +83,7 @@ def main():
     ap.add_argument("--yc", default="0")
     ap.add_argument("--env", default="", help="comma-separated NBVGPU_* switches to set to 1, e.g. NBVGPU_NO_FUSE")
     ap.add_argument("--calls", type=int, default=200)
+    ap.add_argument("--cpp", action="store_true", help="also time the C++ drop-in loop (tests/cpp/shim_iterate_loop.cc): no Python in the loop")
     a = ap.parse_args()
     from nbv_exploration_planner_b200 import synth
     for e in filter(None, a.env.split(",")):
@@ -94,6 +95,18 @@ def main():
             os.environ.pop("NBVGPU_YC", None)
         print(json.dumps(probe("cfg2", "cfg2", a.calls)))
         print(json.dumps(probe("shipped", shipped_cfg(synth, 64), a.calls)))
+        if a.cpp:
+            import tempfile
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+            from cpp_dropin_fixture import build_loop_exe, run_case
+            with tempfile.TemporaryDirectory() as tmp:
+                exe = build_loop_exe(tmp)
+                for name, cfg in (("cfg2", "cfg2"), ("shipped", shipped_cfg(synth, 64))):
+                    m = synth.make_map(cfg)
+                    c = synth.make_candidates(m.cfg, 64, None)
+                    _, lat = run_case(exe, tmp, m, m.camera(), c, 4)
+                    print(json.dumps({"geometry": name, "caller": "C++ (include/nbvgpu_shim.hpp, tests/cpp/shim_iterate_loop.cc)",
+                                      "env": {k: v for k, v in os.environ.items() if k.startswith("NBVGPU_")}, **lat}))
 
 
 if __name__ == "__main__":
