@@ -110,6 +110,7 @@ struct FrontierArgs {
   unsigned frontier_cap;
   double vs;              // float voxel size widened (LowResManager::getResolution)
   double max_distance;
+  double max_d2;  // largest double x with sqrt_rn(x) <= max_distance
   double bmin[3], bmax[3];
   float block_size, block_size_inv, voxel_size_inv;
   int vps;
@@ -390,10 +391,15 @@ __global__ void __launch_bounds__(kFrontierThreads, 1) k_frontier_bfs(const Fron
           // visited.find(...) as of the previous levels (same-level arrivals are arbitrated below)
           const bool seen = vis.seen_before(key, stamp0);
           if (!seen) {
-            const double dx = __dsub_rn(cx, x0), dy = __dsub_rn(cy, y0), dz = __dsub_rn(cz, z0);
-            const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)));
-            if (nrm <= a.max_distance && cx >= a.bmin[0] && cx <= a.bmax[0] && cy >= a.bmin[1] && cy <= a.bmax[1] &&
-                cz >= a.bmin[2] && cz <= a.bmax[2]) {
+            // history.cpp:118-121: (candidate - point).norm() <= max_distance and inside the bounds.  The square root is
+            // correctly rounded and monotone, so norm <= max_distance  <=>  squared sum <= max_d2, the largest double whose
+            // root does not exceed max_distance (found by the host); the cheap bounds test goes first (both are pure).
+            bool near = cx >= a.bmin[0] && cx <= a.bmax[0] && cy >= a.bmin[1] && cy <= a.bmax[1] && cz >= a.bmin[2] && cz <= a.bmax[2];
+            if (near) {
+              const double dx = __dsub_rn(cx, x0), dy = __dsub_rn(cy, y0), dz = __dsub_rn(cz, z0);
+              near = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz)) <= a.max_d2;
+            }
+            if (near) {
               const unsigned st = status_at(a, cx, cy, cz);
               if (st == 0u) {
                 ev = kSlotUnknown;

@@ -1503,6 +1503,12 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double
     a.frontier_cap = (unsigned)frontier_cap;
     a.vs = vs;
     a.max_distance = max_distance;
+    {  // squared-distance threshold equivalent to sqrt(x) <= max_distance under round-to-nearest (see the kernel)
+      double t = max_distance * max_distance;
+      while (std::sqrt(t) > max_distance) t = std::nextafter(t, -INFINITY);
+      while (std::sqrt(std::nextafter(t, INFINITY)) <= max_distance) t = std::nextafter(t, INFINITY);
+      a.max_d2 = t;
+    }
     for (int k = 0; k < 3; ++k) {
       a.bmin[k] = ctx->cam.bbx_min[k];
       a.bmax[k] = ctx->cam.bbx_max[k];
