@@ -72,6 +72,18 @@ def main():
                     msg.append(f"variant {variant}: {k} differs")
             if not np.array_equal(fg, fo["free"]):
                 msg.append(f"variant {variant}: edge verdicts differ")
+            if variant in (0, 2):
+                # the single-item paths (mapped in-place I/O, fused window scan, completion ticket, one warp per segment)
+                rs = g.gain_eval(lt, pos, steps=False)
+                if not (np.array_equal(rs["gain"], ro["gain"]) and np.array_equal(rs["yaw_deg"], ro["yaw_deg"]) and np.array_equal(rs["counts"], ro["counts"])):
+                    msg.append(f"variant {variant}: small-batch gain differs")
+                for i in range(len(pos)):
+                    st = np.array([*pos[i], 0.0])
+                    if g.optimized_gain(lt, st) != ro["gain"][i] or st[3] != ro["yaw_deg"][i] * np.pi / 180.0:
+                        msg.append(f"variant {variant}: optimized_gain({i}) differs")
+                for i in range(len(c.segments)):
+                    if g.check_motion(le, cfg.robot_radius, c.segments[i, :3], c.segments[i, 3:]) != bool(fo["free"][i]):
+                        msg.append(f"variant {variant}: check_motion({i}) differs")
             if variant == 2 and g.classifier_mismatches() != 0:
                 msg.append(f"variant 2: {g.classifier_mismatches()} cross-check mismatches")
             g.close()
