@@ -371,6 +371,9 @@ static int ticket_wait(nbvgpu_ctx* ctx) {
     const unsigned seq = ctx->ticket_seq;
     for (unsigned it = 1;; ++it) {
       if (*f == seq) return NBVGPU_OK;
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();  // be polite to the sibling hyper-thread while spinning
+#endif
       if ((it & 0xfffu) == 0u) {
         const cudaError_t q = cudaStreamQuery(ctx->stream);
         if (q != cudaErrorNotReady) break;  // finished (the ticket is then visible) or failed: let the synchronise say which
