@@ -427,13 +427,26 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   a.unknown_slot = (int)L->max_blocks;
   int gdim = ((2 * a.reach_vox) >> L->log2vps) + 2;
   // yaws per CTA: enough CTAs to fill the machine for small batches, bigger chunks otherwise.
-  static const int kYc[] = {40, 20, 10, 8, 4};
+  // Candidate widths, widest first.  A CTA of `c` yaws walks rows * c rays in batches of 32 on 8 warps: with few rows
+  // per yaw (short range, coarse voxels: the reference's shipped indoor set-up has 8) forty yaws are only ten batches,
+  // which neither balances the warps nor pays for the per-CTA prologue, so wider chunks are allowed while forty yaws
+  // give fewer than two batches per warp (measured on that geometry: 2.71 M viewpoints/s at 40 yaws, 3.25 M at 120).
+  const nbvgpu_host::CameraTables& T = ctx->tab;
+  const double edge[3] = {T.A[0][4][0] - T.A[0][5][0], T.A[0][4][1] - T.A[0][5][1], T.A[0][4][2] - T.A[0][5][2]};
+  const double rows = std::ceil(std::sqrt(edge[0] * edge[0] + edge[1] * edge[1] + edge[2] * edge[2]) * a.vs_inv);  // rrt.cpp:384
+  const bool few_rows = rows * 40.0 < 16.0 * 32.0;
+  int kYc[10] = {120, 90, 72, 60, 40, 20, 10, 8, 4, 4};
   int yc = 40;
   for (int c : kYc) {
+    if (c > 40 && !few_rows) continue;
     yc = c;
     if (n * (size_t)(360 / c) >= (size_t)ctx->sm_count * 6) break;
   }
-  if (ctx->force_yc > 0 && 360 % ctx->force_yc == 0 && ctx->force_yc <= 120) yc = ctx->force_yc;
+  if (ctx->force_yc > 0 && 360 % ctx->force_yc == 0 && ctx->force_yc <= 120) {
+    yc = ctx->force_yc;
+    for (int i = 9; i > 0; --i) kYc[i] = kYc[i - 1];
+    kYc[0] = yc;
+  }
   size_t gn = (size_t)gdim * gdim * gdim;
   size_t smem = gain_smem_bytes(yc, (int)gn);
   if (smem > (size_t)ctx->max_smem_optin || smem > 96 * 1024) {  // fall back to direct hash probes
@@ -444,7 +457,6 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   a.gnx = a.gny = a.gnz = gdim;
   a.yc = yc;
   a.n = (int)n;
-  const nbvgpu_host::CameraTables& T = ctx->tab;
   for (int k = 0; k < 9; ++k) a.F.R[k] = T.R_CB[k];
   for (int k = 0; k < 3; ++k) a.F.t[k] = T.t_CB[k];
   a.F.th = T.th; a.F.tv = T.tv; a.F.nearp = T.near_f; a.F.farp = T.far_f;
