@@ -647,7 +647,10 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
   __syncthreads();
   const int n_rays = s_umax * yc;
   const int gbase = -((b0z * a.gny + b0y) * a.gnx + b0x);  // grid index of block (bx,by,bz) = (bz*gny + by)*gnx + bx + gbase
-  const int* const sgrid = S.grid;
+  // slot grid through its shared-window address (with gbase folded in), kept opaque like vol_s below: otherwise the
+  // window base is re-derived with four uniform-pipe instructions at every voxel
+  uint32_t grid_s = (uint32_t)__cvta_generic_to_shared(S.grid) + 4u * (unsigned)gbase;
+  asm volatile("mov.u32 %0, %0;" : "+r"(grid_s));
 
   // Offset of the candidate inside its voxel (classifier works relative to g0).
   const float noffx = -__double2float_rn(px - (double)g0x * a.vs);
@@ -685,6 +688,12 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
     int len = 0;
     float tlo = 0.0f, thi = 3.0e38f, tlo_v = 0.0f, t_out = 3.0e38f;
     float e3[3];
+    // Modes that test the exploration box per voxel (the dense volume has it baked in): a ray whose start and end voxels
+    // both lie at least two voxels inside the box never needs the test.  The walk moves axis k only towards the end voxel
+    // and takes len = sum |end - start| steps; it can overshoot an axis by one voxel at most (a second extra crossing
+    // lies 1 / |r_k| later in t, far beyond the accumulated rounding of the t's for the ranges admitted here), so every
+    // voxel it emits is within one voxel of the start / end bounding box.
+    bool ray_in = !kIsDense && a.reach_vox <= 256;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       const float sk = S.st[k * yc + j];
@@ -694,6 +703,9 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       g[k] = (int)floorf(__fadd_rn(sk, 1e-6f));
       const int ei = (int)floorf(__fadd_rn(ek, 1e-6f));
       len += abs(ei - g[k]);
+      if (!kIsDense)
+        ray_in = ray_in && a.gspan[k] >= 4u && (unsigned)(g[k] - a.gmin[k] - 2) <= a.gspan[k] - 4u &&
+                 (unsigned)(ei - a.gmin[k] - 2) <= a.gspan[k] - 4u;
       const float rr = __fsub_rn(ek, sk);
       sg[k] = (rr == 0.0f) ? 0 : (rr < 0.0f ? -1 : 1);
       const float shifted = __fsub_rn(sk, (float)g[k]);
@@ -774,8 +786,8 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
 
     // Exploration box on integer thresholds (exact); folded into the volume in dense mode.
     auto in_box = [&]() -> bool {
-      return (unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
-             (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2];
+      return ray_in || ((unsigned)(g[0] - a.gmin[0]) <= a.gspan[0] && (unsigned)(g[1] - a.gmin[1]) <= a.gspan[1] &&
+                        (unsigned)(g[2] - a.gmin[2]) <= a.gspan[2]);
     };
     // Voxel code of the current voxel as the map has it: 0 unknown, 1 free, 3 occupied (voxblox_manager.cpp:14-33);
     // the dense volume also answers 2 for voxels outside the exploration box.
@@ -783,7 +795,7 @@ __global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
       const int bx = g[0] >> lv, by = g[1] >> lv, bz = g[2] >> lv;
       int slot;
       if (MODE == kGrid) {
-        slot = sgrid[(bz * a.gny + by) * a.gnx + bx + gbase];
+        asm volatile("ld.shared.s32 %0, [%1];" : "=r"(slot) : "r"(grid_s + 4u * (unsigned)((bz * a.gny + by) * a.gnx + bx)));
       } else if (MODE == kProbe) {
         if (bx != cbx || by != cby || bz != cbz) {
           cbx = bx; cby = by; cbz = bz;
