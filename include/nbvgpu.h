@@ -271,6 +271,10 @@ int nbvgpu_debug_dense_clipped_launches(nbvgpu_ctx* ctx, uint64_t* count);
  * launch reading and writing mapped pinned host memory; NBVGPU_NO_FUSE=1 / NBVGPU_NO_SMALL_PATH=1 in the environment
  * restore the two-launch / staged-copy paths); for tests. */
 int nbvgpu_debug_fused_launches(nbvgpu_ctx* ctx, uint64_t* count);
+/* Ray-sweep launches, since the context was created, that ran as 512-thread CTAs (two per SM) because the dense
+ * shared-memory volume of a yaw chunk needs more than a quarter but at most half of an SM's shared memory (fine voxels
+ * under a tall exploration box; NBVGPU_NO_WIDE_CTA=1 in the environment keeps the slot-grid sweep instead); for tests. */
+int nbvgpu_debug_wide_cta_launches(nbvgpu_ctx* ctx, uint64_t* count);
 /* Host-only helper for tests: round-half-even of |x| * 10^6, the integer behind "%f" / std::to_string(double),
  * exactly as the flood fill's cell keys compute it.  NBVGPU_ERR_RANGE for non-finite x or |x| >= 2^21. */
 int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude);

@@ -494,8 +494,10 @@ __device__ __forceinline__ void fused_best_yaw(const GainArgs& a, int v, int chu
 constexpr size_t kFusedScratchBytes = 360 * sizeof(double);  // the launch reserves at least this much dynamic shared memory
 
 // k_gain: the ray sweep described in the comment block above the MODE enum.
-template <int VARIANT, int LV, int MODE, bool FUSE = false>
-__global__ void __launch_bounds__(kGainThreads, 4) k_gain(const GainArgs a) {
+// THREADS: 256 (4 CTAs per SM) everywhere except for dense volumes that need more than a quarter of an SM's shared
+// memory: those run as 512-thread CTAs, 2 per SM -- the same 32 warps per SM and 64 registers per thread.
+template <int VARIANT, int LV, int MODE, bool FUSE = false, int THREADS = kGainThreads>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs a) {
   constexpr bool kFilter = (VARIANT != 1);
   constexpr bool kStatusBits = (VARIANT == 0 || VARIANT == 2);
   constexpr bool kParanoid = (VARIANT == 2);

@@ -167,6 +167,8 @@ struct nbvgpu_ctx {
   DevBuf d_arrive;  // per-candidate CTA arrival counters of the fused sweep (zero between launches)
   bool no_fuse = false;                        // NBVGPU_NO_FUSE: keep the two-launch path for small batches (experiments)
   bool no_small = false;                       // NBVGPU_NO_SMALL_PATH: small batches go through the staged copies (experiments)
+  bool no_wide_cta = false;                    // NBVGPU_NO_WIDE_CTA: never use the 512-thread dense sweep (experiments)
+  unsigned long long stats_wide_cta = 0;       // ray-sweep launches with 512-thread CTAs and a half-SM dense volume (tests)
   unsigned long long stats_fused = 0;          // ray-sweep launches that finished with the fused window scan (tests)
   unsigned long long stats_dense_clipped = 0;  // ray-sweep launches that used the z-clipped dense volume (tests)
   int dense_budget = 55 * 1024;  // shared memory per CTA the dense volume path may use (NBVGPU_DENSE_KB)
@@ -309,7 +311,7 @@ int check_position_range(const nbvgpu_ctx* ctx, const LayerHost* L, size_t n, co
 constexpr size_t kFusedMaxCandidates = 64;
 constexpr size_t kSmallBatch = 64;
 
-template <int V, int LV, int MODE, bool FUSE = false>
+template <int V, int LV, int MODE, bool FUSE = false, int THREADS = kGainThreads>
 cudaError_t launch_gain_as(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
   // the opt-in limit is a property of the function (per device): raise it only when a launch needs more than any
   // before it on that device -- a driver call per launch is a measurable part of a single-candidate evaluation
@@ -321,12 +323,12 @@ cudaError_t launch_gain_as(const GainArgs& a, size_t smem, unsigned grid, cudaSt
     std::lock_guard<std::mutex> lk(mu);
     size_t& have = granted[dev];
     if (smem > have) {
-      cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV, MODE, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaError_t e = cudaFuncSetAttribute(k_gain<V, LV, MODE, FUSE, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       have = smem;
     }
   }
-  k_gain<V, LV, MODE, FUSE><<<grid, kGainThreads, smem, s>>>(a);
+  k_gain<V, LV, MODE, FUSE, THREADS><<<grid, THREADS, smem, s>>>(a);
   return cudaGetLastError();
 }
 // mode: kDense / kGrid / kProbe (gain_kernels.cuh).  16 voxels per side (the Voxblox default) gets
@@ -561,6 +563,30 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
       }
     }
   }
+  bool wide_cta = false;
+  if (!dense && (variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0 && !ctx->no_wide_cta) {
+    // Third chance: the volume fits half an SM's shared memory.  512-thread CTAs, two per SM, keep the 32 warps per SM of
+    // the normal configuration (measured on config 3, whose 0.10 m voxels need 60-85 KB per chunk).
+    const size_t budget = (size_t)std::min(ctx->max_smem_optin, 2 * ctx->dense_budget + 2048);
+    for (int c : kYc) {
+      if (c > yc) continue;
+      auto it = ctx->dense_info.find(c);
+      if (it == ctx->dense_info.end() || !it->second.ok || it->second.vwords >= (1 << 24)) continue;
+      const nbvgpu_ctx::DenseInfo& di = it->second;
+      const size_t need = dense_smem_bytes(c, (int)gn, (int)di.vwords);
+      if (need <= budget) {
+        dense = wide_cta = true;
+        yc = c;
+        a.yc = c;
+        smem = need;
+        a.vmin = di.d_vmin.as<int>();
+        a.vez = di.vez;
+        a.vwords = (int)di.vwords;
+        ctx->stats_wide_cta++;
+        break;
+      }
+    }
+  }
   const unsigned grid = (unsigned)(n * (size_t)(360 / yc));
   smem += (size_t)ctx->smem_pad;
   cudaError_t e;
@@ -593,7 +619,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   b.seq = ctx->ticket_seq;
   // Small batches on the dense kernel: the window scan runs in the last CTA of each candidate (one launch instead of
   // two -- what a single-candidate evaluation, the reference's own calling pattern, is made of).
-  const bool fused = dense && !a.zclip && n <= kFusedMaxCandidates && (variant == 0 || variant == 2) && !ctx->no_fuse;
+  const bool fused = dense && !a.zclip && !wide_cta && n <= kFusedMaxCandidates && (variant == 0 || variant == 2) && !ctx->no_fuse;
   a.by = b;
   a.arrive = nullptr;
   a.pos1[0] = a.pos1[1] = a.pos1[2] = 0.0;
@@ -614,6 +640,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     case 1: e = launch_gain<1>(a, smem, grid, ctx->stream, mode); break;
     case 2:
       e = fused ? launch_gain_as<2, 4, kDense, true>(a, smem, grid, ctx->stream)
+          : wide_cta ? launch_gain_as<2, 4, kDense, false, 512>(a, smem, grid, ctx->stream)
           : dense ? (a.zclip ? launch_gain_as<2, 4, kDenseClip>(a, smem, grid, ctx->stream) : launch_gain_as<2, 4, kDense>(a, smem, grid, ctx->stream))
                   : launch_gain<2>(a, smem, grid, ctx->stream, mode);
       break;
@@ -622,6 +649,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     case 5: e = launch_gain<2>(a, smem, grid, ctx->stream, mode); break;
     default:
       e = fused ? launch_gain_as<0, 4, kDense, true>(a, smem, grid, ctx->stream)
+          : wide_cta ? launch_gain_as<0, 4, kDense, false, 512>(a, smem, grid, ctx->stream)
           : dense ? (a.zclip ? launch_gain_as<0, 4, kDenseClip>(a, smem, grid, ctx->stream) : launch_gain_as<0, 4, kDense>(a, smem, grid, ctx->stream))
                   : launch_gain<0>(a, smem, grid, ctx->stream, mode);
       break;
@@ -717,6 +745,7 @@ int nbvgpu_create(int device, nbvgpu_ctx** out) {
   ctx->no_fuse = std::getenv("NBVGPU_NO_FUSE") != nullptr;
   ctx->no_small = std::getenv("NBVGPU_NO_SMALL_PATH") != nullptr;
   ctx->no_poll = std::getenv("NBVGPU_NO_POLL") != nullptr;
+  ctx->no_wide_cta = std::getenv("NBVGPU_NO_WIDE_CTA") != nullptr;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   DeviceGuard guard(device);
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -1663,6 +1692,14 @@ int nbvgpu_probe_l2_read_bandwidth(nbvgpu_ctx* ctx, size_t bytes, int iters, dou
   cudaFree(sink);
   if (e != cudaSuccess || !(ms > 0.f)) return fail(ctx, NBVGPU_ERR_CUDA, "L2 probe failed");
   *gb_per_s = (double)n_vec * 16.0 * (double)iters / ((double)ms * 1e-3) / 1e9;
+  return NBVGPU_OK;
+}
+
+// Ray-sweep launches (since context creation) that used 512-thread CTAs with a half-SM dense volume; for tests.
+int nbvgpu_debug_wide_cta_launches(nbvgpu_ctx* ctx, uint64_t* out) {
+  if (!ctx || !out) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  *out = ctx->stats_wide_cta;
   return NBVGPU_OK;
 }
 

@@ -323,6 +323,12 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_debug_fused_launches(self._h, C.byref(out)))
         return int(out.value)
 
+    def wide_cta_launches(self) -> int:
+        """ray-sweep launches that ran as 512-thread CTAs with a half-SM dense volume (tests)."""
+        out = C.c_uint64(0)
+        self._ck(self._L.nbvgpu_debug_wide_cta_launches(self._h, C.byref(out)))
+        return int(out.value)
+
     def frontier_hash_redo(self) -> int:
         """vertices the dense visited set of the flood fill handed back to the hash-keyed one (tests)."""
         out = C.c_uint64(0)

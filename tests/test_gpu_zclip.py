@@ -67,3 +67,33 @@ def test_expand_tree_with_clipped_volume(oracle_mod):
     _check(rg, ro)
     assert (ro["status"] == 2).sum() > 5
     g.close()
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+def test_tall_box_takes_the_half_sm_volume(oracle_mod, variant):
+    """Fine voxels under a TALL box (config 3's situation): nothing to clip in z, the volume of a yaw chunk needs more than
+    a quarter of an SM's shared memory and runs as 512-thread CTAs, two per SM.  Identical to the oracle; NBVGPU_NO_WIDE_CTA
+    (the slot-grid sweep on the same input) gives the same numbers."""
+    from nbv_exploration_planner_b200 import synth
+    cfg = synth.SynthConfig("fine-tall", (0, 0, 0), (14, 12, 8), 0.10, 5.0, 12, "office", 3201, 3202, (7.0, 6.0, 4.0), obs_radius=5.0,
+                            traj_points=5, traj_step=2.5, vicinity=4.0)
+    m = synth.make_map(cfg)
+    cam = m.camera()
+    o, lt_o, le_o = load_oracle(oracle_mod, m, cam)
+    g, lt_g, le_g = load_gpu(m, cam, variant)
+    c = synth.make_candidates(m.cfg, 12, None)
+    extra = np.array([[7.0, 6.0, 0.3], [7.0, 6.0, 7.8], [7.0, 6.0, -0.4], [3.0, 3.0, 4.0], [13.9, 11.9, 4.0], [7.0, 6.0, 12.0]])
+    pos = np.concatenate([c.positions, extra])
+    ro = o.gain_eval(lt_o, pos, per_yaw=True, threads=8)
+    rg = g.gain_eval(lt_g, pos, per_yaw=True, steps=True)           # 18 candidates: small batch, not fused (wide CTAs)
+    big = np.tile(pos, (8, 1))                                        # 144 candidates: large batch
+    rb = g.gain_eval(lt_g, big, per_yaw=True, steps=True)
+    assert g.wide_cta_launches() >= 2 and g.dense_clipped_launches() == 0 and g.fused_launches() == 0
+    for k in ("per_yaw", "steps", "yaw_deg", "gain"):
+        assert np.array_equal(rg[k], ro[k]), k
+        assert np.array_equal(rb[k], np.concatenate([ro[k]] * 8)), k
+    st = np.array([*pos[0], 0.0])
+    assert g.optimized_gain(lt_g, st) == ro["gain"][0] and st[3] == ro["yaw_deg"][0] * np.pi / 180.0
+    if variant == 2:
+        assert g.classifier_mismatches() == 0
+    g.close()
