@@ -468,7 +468,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   // Dense shared-memory status volume (MODE kDense) when the layer has 16^3 blocks and the volume of one
   // yaw chunk fits the budget that still allows 4 CTAs per SM: take the widest chunk that fits (narrower
   // chunks have smaller volumes), starting from the width chosen above.
-  bool dense = false;
+  bool dense = false, wide_cta = false;
   a.vmin = nullptr;
   a.vez = a.vwords = 0;
   if ((variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0) {
@@ -479,8 +479,8 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
       ctx->dense_gen = ctx->cam_gen;
       ctx->dense_vs = L->voxel_size;
     }
-    for (int c : kYc) {
-      if (c > yc) continue;
+    // volume bounds of a chunk width, computed once per camera / voxel size
+    auto info_for = [&](int c, const nbvgpu_ctx::DenseInfo** out) -> int {
       auto it = ctx->dense_info.find(c);
       if (it == ctx->dense_info.end()) {
         nbvgpu_ctx::DenseInfo info;
@@ -494,17 +494,45 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
         }
         it = ctx->dense_info.emplace(c, std::move(info)).first;
       }
-      const nbvgpu_ctx::DenseInfo& di = it->second;
+      *out = &it->second;
+      return NBVGPU_OK;
+    };
+    auto take = [&](int c, const nbvgpu_ctx::DenseInfo& di, size_t need) {
+      dense = true;
+      yc = c;
+      a.yc = c;
+      smem = need;
+      a.vmin = di.d_vmin.as<int>();
+      a.vez = di.vez;
+      a.vwords = (int)di.vwords;
+    };
+    // Large batches with many ray rows per yaw: 90 (or 72) yaws per 512-thread CTA, two CTAs per SM -- fewer prologues and
+    // end-of-CTA barriers for the same 32 warps per SM (config 2: 712 k against 694-697 k viewpoints/s with 40 yaws per
+    // 256-thread CTA; 60 / 72 / 120 yaws: 688 / 699 / 704 k).  Needs at least four waves of such CTAs.
+    if (!few_rows && ctx->force_yc <= 0 && !ctx->no_wide_cta && n * 4 >= (size_t)ctx->sm_count * 8) {
+      for (int c : {90, 72}) {
+        const nbvgpu_ctx::DenseInfo* di = nullptr;
+        if (info_for(c, &di)) return NBVGPU_ERR_CUDA;
+        if (!di->ok || di->vwords >= (1 << 24)) continue;
+        const size_t need = dense_smem_bytes(c, (int)gn, (int)di->vwords);
+        if (need <= (size_t)std::min(ctx->max_smem_optin, 2 * ctx->dense_budget + 2048)) {
+          take(c, *di, need);
+          wide_cta = true;
+          ctx->stats_wide_cta++;
+          break;
+        }
+      }
+    }
+    for (int c : kYc) {
+      if (dense) break;
+      if (c > yc) continue;
+      const nbvgpu_ctx::DenseInfo* dip = nullptr;
+      if (info_for(c, &dip)) return NBVGPU_ERR_CUDA;
+      const nbvgpu_ctx::DenseInfo& di = *dip;
       if (!di.ok || di.vwords >= (1 << 24)) continue;
       const size_t need = dense_smem_bytes(c, (int)gn, (int)di.vwords);
       if (need <= (size_t)ctx->dense_budget && need <= (size_t)ctx->max_smem_optin) {
-        dense = true;
-        yc = c;
-        a.yc = c;
-        smem = need;
-        a.vmin = di.d_vmin.as<int>();
-        a.vez = di.vez;
-        a.vwords = (int)di.vwords;
+        take(c, di, need);
         break;
       }
     }
@@ -563,7 +591,6 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
       }
     }
   }
-  bool wide_cta = false;
   if (!dense && (variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0 && !ctx->no_wide_cta) {
     // Third chance: the volume fits half an SM's shared memory.  512-thread CTAs, two per SM, keep the 32 warps per SM of
     // the normal configuration (measured on config 3, whose 0.10 m voxels need 60-85 KB per chunk).
