@@ -275,6 +275,10 @@ int nbvgpu_debug_fused_launches(nbvgpu_ctx* ctx, uint64_t* count);
  * shared-memory volume of a yaw chunk needs more than a quarter but at most half of an SM's shared memory (fine voxels
  * under a tall exploration box; NBVGPU_NO_WIDE_CTA=1 in the environment keeps the slot-grid sweep instead); for tests. */
 int nbvgpu_debug_wide_cta_launches(nbvgpu_ctx* ctx, uint64_t* count);
+/* Host-only helper for tests: the largest double x with sqrt(x) <= d (round to nearest).  The flood fill tests
+ * `squared distance <= threshold` instead of `(candidate - point).norm() <= max_distance` (history.cpp:118): the two are
+ * equivalent because the square root is monotone and correctly rounded.  NBVGPU_ERR_INVALID for negative or non-finite d. */
+int nbvgpu_debug_sqrt_threshold(double d, double* threshold);
 /* Host-only helper for tests: round-half-even of |x| * 10^6, the integer behind "%f" / std::to_string(double),
  * exactly as the flood fill's cell keys compute it.  NBVGPU_ERR_RANGE for non-finite x or |x| >= 2^21. */
 int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude);

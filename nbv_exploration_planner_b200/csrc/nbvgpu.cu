@@ -1513,6 +1513,15 @@ int nbvgpu_esdf_distance_gradient_device(nbvgpu_ctx* ctx, int layer, size_t n, c
 }
 
 // ---- History::bfs (history.cpp:96-137): frontier potential of history-graph vertices ---------
+// The largest double x with sqrt(x) <= d under round-to-nearest (d >= 0, finite): sqrt is monotone and correctly rounded,
+// so a comparison of a norm with d can be made on the squared sum instead.
+static double sqrt_le_threshold(double d) {
+  double t = d * d;
+  while (std::sqrt(t) > d) t = std::nextafter(t, -INFINITY);
+  while (std::sqrt(std::nextafter(t, INFINITY)) <= d) t = std::nextafter(t, INFINITY);
+  return t;
+}
+
 int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double* points, double max_distance, double* potential_gain,
                               uint64_t* frontier_voxels, uint64_t* visited_cells, uint64_t* cells_checksum) {
   if (!ctx || (n && (!points || !potential_gain))) return NBVGPU_ERR_INVALID;
@@ -1574,12 +1583,7 @@ int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double
     a.frontier_cap = (unsigned)frontier_cap;
     a.vs = vs;
     a.max_distance = max_distance;
-    {  // squared-distance threshold equivalent to sqrt(x) <= max_distance under round-to-nearest (see the kernel)
-      double t = max_distance * max_distance;
-      while (std::sqrt(t) > max_distance) t = std::nextafter(t, -INFINITY);
-      while (std::sqrt(std::nextafter(t, INFINITY)) <= max_distance) t = std::nextafter(t, INFINITY);
-      a.max_d2 = t;
-    }
+    a.max_d2 = sqrt_le_threshold(max_distance);  // sqrt(x) <= max_distance  <=>  x <= max_d2 (see the kernel)
     for (int k = 0; k < 3; ++k) {
       a.bmin[k] = ctx->cam.bbx_min[k];
       a.bmax[k] = ctx->cam.bbx_max[k];
@@ -1743,6 +1747,13 @@ int nbvgpu_debug_dense_clipped_launches(nbvgpu_ctx* ctx, uint64_t* out) {
   if (!ctx || !out) return NBVGPU_ERR_INVALID;
   std::lock_guard<std::mutex> lk(ctx->mu);
   *out = ctx->stats_dense_clipped;
+  return NBVGPU_OK;
+}
+
+// Host-only: the squared-distance threshold the flood fill compares against instead of taking a square root; for tests.
+int nbvgpu_debug_sqrt_threshold(double d, double* threshold) {
+  if (!threshold || !(d >= 0.0) || !std::isfinite(d)) return NBVGPU_ERR_INVALID;
+  *threshold = sqrt_le_threshold(d);
   return NBVGPU_OK;
 }
 

@@ -51,3 +51,32 @@ def test_out_of_range_is_reported():
     for x in (float("inf"), float("nan"), 2.0 ** 21, -3e6):
         rc, _ = _dec6(x)
         assert rc != 0
+
+
+def test_squared_distance_threshold_is_equivalent_to_the_norm_test():
+    """The flood fill compares the squared distance with the largest double whose correctly rounded square root does not
+    exceed max_distance instead of taking the root (history.cpp:118: (candidate - point).norm() <= max_distance).  Around
+    the threshold, and on random sums, both tests must agree for every value."""
+    rng = np.random.default_rng(9)
+    ds = np.concatenate([[0.0, 6.0, 1.0, 0.5, 2.0 ** 0.5, 1e-3, 123.456, 4499.0],
+                         rng.uniform(0.01, 50.0, 300), np.float64(np.float32(rng.uniform(0.1, 10.0, 100)))])
+    for d in ds:
+        t = C.c_double(0.0)
+        assert N.lib().nbvgpu_debug_sqrt_threshold(C.c_double(d), C.byref(t)) == N.OK
+        t = t.value
+        assert math.sqrt(t) <= d < math.sqrt(np.nextafter(t, np.inf))
+        x = t
+        for _ in range(40):                          # 40 doubles below ...
+            assert math.sqrt(x) <= d
+            x = float(np.nextafter(x, -np.inf))
+            if x < 0:
+                break
+        x = float(np.nextafter(t, np.inf))
+        for _ in range(40):                          # ... and above the threshold
+            assert not (math.sqrt(x) <= d)
+            x = float(np.nextafter(x, np.inf))
+        xs = rng.uniform(0.0, 2.0 * d * d + 1e-9, 2000)
+        assert np.array_equal(np.sqrt(xs) <= d, xs <= t)
+    bad = C.c_double(0.0)
+    for d in (-1.0, float("nan"), float("inf")):
+        assert N.lib().nbvgpu_debug_sqrt_threshold(C.c_double(d), C.byref(bad)) == N.ERR_INVALID
