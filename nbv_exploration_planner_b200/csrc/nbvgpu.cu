@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -372,7 +373,10 @@ static int ticket_wait(nbvgpu_ctx* ctx) {
     const volatile unsigned* f = ctx->h_ticket;
     const unsigned seq = ctx->ticket_seq;
     for (unsigned it = 1;; ++it) {
-      if (*f == seq) return NBVGPU_OK;
+      if (*f == seq) {
+        std::atomic_thread_fence(std::memory_order_acquire);  // the results were written before the ticket
+        return NBVGPU_OK;
+      }
 #if defined(__x86_64__) || defined(__i386__)
       __builtin_ia32_pause();  // be polite to the sibling hyper-thread while spinning
 #endif
