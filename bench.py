@@ -44,6 +44,8 @@ def parse_args():
                     "side measurements: frontier (History::bfs), interp (ESDF interpolation), shipped (the reference's shipped geometry)")
     ap.add_argument("--map", default="cfg1", help="map of the frontier / interp side measurements")
     ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU (default: the config's)")
+    ap.add_argument("--separate-calls", action="store_true",
+                    help="evaluate a step with nbvgpu_check_segments + nbvgpu_gain_eval_best instead of nbvgpu_evaluate_candidates")
     ap.add_argument("--variant", type=int, default=0, help="gain kernel variant (A/B measurement)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the cpu_baseline sample (default 1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -355,8 +357,12 @@ def run_ours(args):
     setup_s = time.perf_counter() - t_setup
 
     def step_device():
-        g.check_segments_device(le, cfg.robot_radius, n, d_seg, d_free)
-        g.gain_eval_best_device(lt, n, d_pos, d_pyaw, d_dist, d_free, v_max, dyaw_max, zero_gain, d_best, d_gain, d_yaw)
+        if args.separate_calls:   # the two entry points one after the other (identical results)
+            g.check_segments_device(le, cfg.robot_radius, n, d_seg, d_free)
+            g.gain_eval_best_device(lt, n, d_pos, d_pyaw, d_dist, d_free, v_max, dyaw_max, zero_gain, d_best, d_gain, d_yaw)
+        else:                     # one call: the edge check runs beside the ray sweep
+            g.evaluate_candidates_device(lt, le, cfg.robot_radius, n, d_pos, d_seg, d_pyaw, d_dist, v_max, dyaw_max, zero_gain,
+                                         d_free, d_best, d_gain, d_yaw)
         # every step ends with the winner known on the host (one 32 B record per rank)
         return nd.gather_best_raw(d_best, n_total)
 
@@ -399,8 +405,11 @@ def run_ours(args):
     e2e_steps = max(3, min(args.steps, 30))
 
     def step_host():
-        free = g.check_segments(le, cfg.robot_radius, h_seg)
-        r = g.gain_eval_best(lt, h_pos, h_pyaw, h_dist, free, v_max, dyaw_max, zero_gain)
+        if args.separate_calls:
+            free = g.check_segments(le, cfg.robot_radius, h_seg)
+            r = g.gain_eval_best(lt, h_pos, h_pyaw, h_dist, free, v_max, dyaw_max, zero_gain)
+        else:
+            r = g.evaluate_candidates(lt, le, cfg.robot_radius, h_pos, h_seg, h_pyaw, h_dist, v_max, dyaw_max, zero_gain)
         if world > 1:
             rec = torch.tensor([r["index"], r["score"], r["best_gain"], r["best_yaw"]], dtype=torch.float64, device=dev)
             return nd.gather_best(rec, lo)
@@ -416,8 +425,8 @@ def run_ours(args):
         step_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    h2d = n * (48 + 24 + 8 + 8 + 1)
-    d2h = n * (1 + 8 + 4) + 32
+    h2d = n * (48 + 24 + 8 + 8 + (1 if args.separate_calls else 0))   # segments, positions, parent yaw, distance (+ verdicts back up)
+    d2h = n * (1 + 8 + 4) + (32 if args.separate_calls else 64)       # verdicts, gain, yaw + the best record
 
     # ---- drop-in latency: one candidate through the n = 1 shims (what the unmodified iterate() would call)
     lat_us = None

@@ -183,6 +183,21 @@ int nbvgpu_gain_eval_best_device(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, cons
                                  double zero_gain, nbvgpu_best* d_best, double* d_gain,
                                  int32_t* d_yaw_deg);
 
+/* Edge check + gain + node scoring of n candidates in one call: what RrtTree::iterate does with a sample after the
+ * sampler (rrt.cpp:205-246) -- checkMotion on seg[i] = {start xyz, end xyz} (voxblox_manager.h:89-108), optimized_gain at
+ * pos[i], the score / best-node update -- i.e. nbvgpu_check_segments followed by nbvgpu_gain_eval_best with its verdicts,
+ * with identical results.  One call instead of two lets the edge check run beside the ray sweep (a side stream forked from
+ * and joined into the context's stream) and, for host buffers, saves a copy / synchronise round trip.  edge_free receives the
+ * per-candidate verdicts (required for the device variant, optional for the host variant); gain / yaw_deg may be NULL. */
+int nbvgpu_evaluate_candidates(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double robot_radius, size_t n,
+                               const double* pos, const double* seg, const double* parent_yaw, const double* distance,
+                               double v_max, double dyaw_max, double zero_gain, uint8_t* edge_free, nbvgpu_best* best,
+                               double* gain, int32_t* yaw_deg);
+int nbvgpu_evaluate_candidates_device(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double robot_radius, size_t n,
+                                      const double* d_pos, const double* d_seg, const double* d_parent_yaw,
+                                      const double* d_distance, double v_max, double dyaw_max, double zero_gain,
+                                      uint8_t* d_edge_free, nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg);
+
 /* ---- batched tree expansion ------------------------------------------------- */
 /* Parameters of RrtTree::iterate that are not in nbvgpu_camera (params.h:26-35,93,103; rrt.cpp:175). */
 typedef struct {

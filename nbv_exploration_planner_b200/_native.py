@@ -125,6 +125,10 @@ def lib() -> C.CDLL:
                                         C.POINTER(Best), vp, vp]
     L.nbvgpu_gain_eval_best_device.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, vp, vp, C.c_double, C.c_double,
                                                C.c_double, vp, vp, vp]
+    L.nbvgpu_evaluate_candidates.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_size_t, vp, vp, vp, vp, C.c_double, C.c_double,
+                                             C.c_double, vp, C.POINTER(Best), vp, vp]
+    L.nbvgpu_evaluate_candidates_device.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_size_t, vp, vp, vp, vp, C.c_double,
+                                                    C.c_double, C.c_double, vp, vp, vp, vp]
     L.nbvgpu_check_segments.argtypes = [vp, C.c_int, C.c_double, C.c_size_t, vp, vp]
     L.nbvgpu_check_segments_device.argtypes = [vp, C.c_int, C.c_double, C.c_size_t, vp, vp]
     L.nbvgpu_check_motion.argtypes = [vp, C.c_int, C.c_double, _f64p, _f64p, C.POINTER(C.c_int)]
@@ -174,5 +178,5 @@ ABI_SYMBOLS = [
     "nbvgpu_check_segments_device", "nbvgpu_check_motion", "nbvgpu_get_stats", "nbvgpu_set_kernel_variant",
     "nbvgpu_debug_classifier_mismatches", "nbvgpu_set_profiling", "nbvgpu_profile_collect",
     "nbvgpu_layer_load_voxblox_file", "nbvgpu_layer_apply_layer_msg", "nbvgpu_parse_blocks", "nbvgpu_expand_tree",
-    "nbvgpu_frontier_potential", "nbvgpu_esdf_distance_gradient", "nbvgpu_esdf_distance_gradient_device", "nbvgpu_debug_round_decimal6", "nbvgpu_debug_sqrt_threshold", "nbvgpu_debug_frontier_hash_redo", "nbvgpu_debug_dense_clipped_launches", "nbvgpu_debug_fused_launches", "nbvgpu_debug_wide_cta_launches", "nbvgpu_probe_l2_read_bandwidth",
+    "nbvgpu_frontier_potential", "nbvgpu_esdf_distance_gradient", "nbvgpu_esdf_distance_gradient_device", "nbvgpu_evaluate_candidates", "nbvgpu_evaluate_candidates_device", "nbvgpu_debug_round_decimal6", "nbvgpu_debug_sqrt_threshold", "nbvgpu_debug_frontier_hash_redo", "nbvgpu_debug_dense_clipped_launches", "nbvgpu_debug_fused_launches", "nbvgpu_debug_wide_cta_launches", "nbvgpu_probe_l2_read_bandwidth",
 ]

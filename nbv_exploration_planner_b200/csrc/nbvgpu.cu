@@ -168,6 +168,8 @@ struct nbvgpu_ctx {
   DevBuf d_arrive;  // per-candidate CTA arrival counters of the fused sweep (zero between launches)
   bool no_fuse = false;                        // NBVGPU_NO_FUSE: keep the two-launch path for small batches (experiments)
   bool no_small = false;                       // NBVGPU_NO_SMALL_PATH: small batches go through the staged copies (experiments)
+  cudaStream_t side_stream = nullptr;          // nbvgpu_evaluate_candidates*: the edge check runs beside the ray sweep
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool no_wide_cta = false;                    // NBVGPU_NO_WIDE_CTA: never use the 512-thread dense sweep (experiments)
   unsigned long long stats_wide_cta = 0;       // ray-sweep launches with 512-thread CTAs and a half-SM dense volume (tests)
   unsigned long long stats_fused = 0;          // ray-sweep launches that finished with the fused window scan (tests)
@@ -747,6 +749,50 @@ int best_device_nolock(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_pos
   return NBVGPU_OK;
 }
 
+// Edge check + gain + scoring of n resident candidates (the body of RrtTree::iterate after the sampler, rrt.cpp:205-246).
+// The edge check does not depend on the ray sweep, so it runs on a side stream forked from and joined back into the
+// context's stream: its kernel and launch gap disappear behind the sweep.
+int evaluate_device_nolock(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double radius, size_t n, const double* d_pos,
+                           const double* d_seg, const double* d_parent_yaw, const double* d_distance, double v_max,
+                           double dyaw_max, double zero_gain, uint8_t* d_edge_free, nbvgpu_best* d_best, double* d_gain,
+                           int32_t* d_yaw_deg) {
+  LayerHost* E = get_layer(ctx, esdf_layer, NBVGPU_LAYER_ESDF);
+  if (!E) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
+  DeviceGuard guard(ctx->device);
+  if (!ctx->side_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t main_stream = ctx->stream;
+  CK(cudaEventRecord(ctx->ev_fork, main_stream));
+  CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
+  ctx->stream = ctx->side_stream;
+  const int rs = enqueue_segments(ctx, E, radius, n, d_seg, d_edge_free);
+  ctx->stream = main_stream;
+  if (rs) return rs;
+  CK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
+  if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
+  LayerHost* L = get_layer(ctx, tsdf_layer, NBVGPU_LAYER_TSDF);
+  if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
+  if (!d_gain) {
+    CK(ctx->d_gain.reserve(n * 8 + 8));
+    d_gain = ctx->d_gain.as<double>();
+  }
+  if (!d_yaw_deg) {
+    CK(ctx->d_yaw.reserve(n * 4 + 4));
+    d_yaw_deg = ctx->d_yaw.as<int32_t>();
+  }
+  const int rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr);
+  CK(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));  // join also when the sweep could not be enqueued
+  if (rc) return rc;
+  k_score_best<<<1, 1024, 0, main_stream>>>(d_gain, d_yaw_deg, d_parent_yaw, d_distance, d_edge_free, (int)n, v_max, dyaw_max,
+                                            zero_gain, reinterpret_cast<BestRecord*>(d_best));
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  return NBVGPU_OK;
+}
+
 }  // namespace
 
 // =============================================================================================
@@ -806,6 +852,12 @@ void nbvgpu_destroy(nbvgpu_ctx* ctx) {
     cudaFree(ctx->d_totals);
     ctx->h_io.release();
     if (ctx->h_ticket) cudaFreeHost(ctx->h_ticket);
+    if (ctx->side_stream) {
+      cudaStreamSynchronize(ctx->side_stream);
+      cudaStreamDestroy(ctx->side_stream);
+    }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
     for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
                       &ctx->d_free, &ctx->d_aux, &ctx->d_best, &ctx->d_zrange, &ctx->d_arrive, &ctx->d_fr_cells, &ctx->d_fr_cur, &ctx->d_fr_next,
@@ -1288,6 +1340,62 @@ int nbvgpu_gain_eval_best(nbvgpu_ctx* ctx, int layer, size_t n, const double* po
   memcpy(best, hr, sizeof(nbvgpu_best));
   if (gain) memcpy(gain, hr + 64, n * 8);
   if (yaw_deg) memcpy(yaw_deg, hr + 64 + n * 8, n * 4);
+  return NBVGPU_OK;
+}
+
+// ---- edge check + gain + scoring in one call (rrt.cpp:205-246) ------------------------------------
+int nbvgpu_evaluate_candidates_device(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double robot_radius, size_t n,
+                                      const double* d_pos, const double* d_seg, const double* d_parent_yaw,
+                                      const double* d_distance, double v_max, double dyaw_max, double zero_gain,
+                                      uint8_t* d_edge_free, nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg) {
+  if (!ctx || !d_best || (n && (!d_pos || !d_seg || !d_parent_yaw || !d_distance || !d_edge_free))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  return evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, robot_radius, n, d_pos, d_seg, d_parent_yaw, d_distance, v_max,
+                                dyaw_max, zero_gain, d_edge_free, d_best, d_gain, d_yaw_deg);
+}
+
+int nbvgpu_evaluate_candidates(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double robot_radius, size_t n, const double* pos,
+                               const double* seg, const double* parent_yaw, const double* distance, double v_max,
+                               double dyaw_max, double zero_gain, uint8_t* edge_free, nbvgpu_best* best, double* gain,
+                               int32_t* yaw_deg) {
+  if (!ctx || !best || (n && (!pos || !seg || !parent_yaw || !distance))) return NBVGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  LayerHost* L = get_layer(ctx, tsdf_layer, NBVGPU_LAYER_TSDF);
+  LayerHost* E = get_layer(ctx, esdf_layer, NBVGPU_LAYER_ESDF);
+  if (!L || !E) return fail(ctx, NBVGPU_ERR_STATE, "needs a TSDF and an ESDF layer");
+  if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
+  if (check_position_range(ctx, L, n, pos)) return fail(ctx, NBVGPU_ERR_RANGE, "position non-finite or out of range");
+  const double vs_inv = 1.0 / (double)E->voxel_size;
+  for (size_t i = 0; i < 6 * n; ++i)
+    if (!(std::fabs(seg[i] * vs_inv) < 4194000.0)) return fail(ctx, NBVGPU_ERR_RANGE, "segment non-finite or out of range");
+  DeviceGuard guard(ctx->device);
+  // staging in: [pos n*24 | seg n*48 | parent n*8 | dist n*8]; device out: [best 64 | gain n*8 | yaw n*4 (padded to 8) | free n]
+  const size_t o_seg = n * 24, o_par = o_seg + n * 48, o_dist = o_par + n * 8, in_bytes = o_dist + n * 8;
+  const size_t r_gain = 64, r_yaw = r_gain + n * 8, r_free = r_yaw + ((n * 4 + 7) & ~(size_t)7), out_bytes = r_free + ((n + 7) & ~(size_t)7);
+  CK(ctx->h_io.reserve(in_bytes + out_bytes + 64, false));
+  CK(ctx->d_pos.reserve(in_bytes + 8));
+  CK(ctx->d_aux.reserve(out_bytes + 8));
+  char* h = ctx->h_io.as<char>();
+  char* d = ctx->d_pos.as<char>();
+  char* dr = ctx->d_aux.as<char>();
+  memcpy(h, pos, n * 24);
+  memcpy(h + o_seg, seg, n * 48);
+  memcpy(h + o_par, parent_yaw, n * 8);
+  memcpy(h + o_dist, distance, n * 8);
+  if (in_bytes) CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, robot_radius, n, reinterpret_cast<double*>(d),
+                                        reinterpret_cast<double*>(d + o_seg), reinterpret_cast<double*>(d + o_par),
+                                        reinterpret_cast<double*>(d + o_dist), v_max, dyaw_max, zero_gain,
+                                        reinterpret_cast<uint8_t*>(dr + r_free), reinterpret_cast<nbvgpu_best*>(dr),
+                                        reinterpret_cast<double*>(dr + r_gain), reinterpret_cast<int32_t*>(dr + r_yaw));
+  if (rc) return rc;
+  char* hr = h + in_bytes;
+  CK(cudaMemcpyAsync(hr, dr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(best, hr, sizeof(nbvgpu_best));
+  if (gain) memcpy(gain, hr + r_gain, n * 8);
+  if (yaw_deg) memcpy(yaw_deg, hr + r_yaw, n * 4);
+  if (edge_free) memcpy(edge_free, hr + r_free, n);
   return NBVGPU_OK;
 }
 

@@ -233,6 +233,32 @@ class NbvGpu:
                                                       _vp(d_edge_free), v_max, dyaw_max, zero_gain, _vp(d_best), _vp(d_gain),
                                                       _vp(d_yaw_deg)))
 
+    def evaluate_candidates(self, tsdf_layer: int, esdf_layer: int, robot_radius: float, pos, seg, parent_yaw, distance,
+                            v_max: float = 1.0, dyaw_max: float = 0.5, zero_gain: float = 0.0) -> dict:
+        """Edge check + gain + node scoring in one call (what ``RrtTree::iterate`` does with a sample after the sampler,
+        rrt.cpp:205-246): the same results as ``check_segments`` followed by ``gain_eval_best`` with its verdicts."""
+        pos = np.ascontiguousarray(pos, np.float64).reshape(-1, 3)
+        seg = np.ascontiguousarray(seg, np.float64).reshape(-1, 6)
+        n = len(pos)
+        if len(seg) != n:
+            raise ValueError("one segment per candidate")
+        parent_yaw = np.ascontiguousarray(parent_yaw, np.float64)
+        distance = np.ascontiguousarray(distance, np.float64)
+        best = N.Best()
+        gain, yaw, free = np.zeros(n, np.float64), np.zeros(n, np.int32), np.zeros(n, np.uint8)
+        self._ck(self._L.nbvgpu_evaluate_candidates(self._h, tsdf_layer, esdf_layer, float(robot_radius), n, _vp(pos), _vp(seg),
+                                                    _vp(parent_yaw), _vp(distance), v_max, dyaw_max, zero_gain, _vp(free),
+                                                    C.byref(best), _vp(gain), _vp(yaw)))
+        return {"index": best.index, "score": best.score, "best_gain": best.gain, "best_yaw": best.yaw, "gain": gain,
+                "yaw_deg": yaw, "free": free}
+
+    def evaluate_candidates_device(self, tsdf_layer: int, esdf_layer: int, robot_radius: float, n: int, d_pos, d_seg,
+                                   d_parent_yaw, d_distance, v_max, dyaw_max, zero_gain, d_edge_free, d_best, d_gain=None,
+                                   d_yaw_deg=None) -> None:
+        self._ck(self._L.nbvgpu_evaluate_candidates_device(self._h, tsdf_layer, esdf_layer, float(robot_radius), n, _vp(d_pos),
+                                                           _vp(d_seg), _vp(d_parent_yaw), _vp(d_distance), v_max, dyaw_max,
+                                                           zero_gain, _vp(d_edge_free), _vp(d_best), _vp(d_gain), _vp(d_yaw_deg)))
+
     def optimized_gain(self, layer: int, state: np.ndarray) -> float:
         """``double RrtTree::optimized_gain(Pose& state)``: returns the gain, writes ``state[3]``."""
         if not (isinstance(state, np.ndarray) and state.dtype == np.float64 and state.size >= 4 and state.flags.c_contiguous):

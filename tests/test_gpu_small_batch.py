@@ -186,3 +186,42 @@ def test_paths_switched_off_give_the_same_results(oracle_mod, env, monkeypatch):
     if env == "NBVGPU_NO_FUSE":
         assert g2.fused_launches() == 0
     g2.close()
+
+
+@pytest.mark.parametrize("n", [1, 10, 64, 65, 400])
+def test_evaluate_candidates_equals_the_two_calls(oracle_mod, n):
+    """nbvgpu_evaluate_candidates (edge check beside the ray sweep, one call) == nbvgpu_check_segments followed by
+    nbvgpu_gain_eval_best, host and device variants, small and large batches; verdicts and gains equal the oracle's."""
+    import torch
+    from nbv_exploration_planner_b200 import synth
+    m, o, lt_o, le_o, g, lt_g, le_g, c0 = _setup(oracle_mod)
+    c = synth.make_candidates(m.cfg, n, None)
+    pos, seg, dist = c.positions, c.segments, c.distance
+    pyaw = np.linspace(-3.0, 3.0, n)
+    ro = o.gain_eval(lt_o, pos, threads=8)
+    fo = o.check_segments(le_o, m.cfg.robot_radius, seg)["free"]
+    free = g.check_segments(le_g, m.cfg.robot_radius, seg)
+    two = g.gain_eval_best(lt_g, pos, pyaw, dist, free, 1.0, 0.5, 0.0)
+    for _ in range(2):
+        one = g.evaluate_candidates(lt_g, le_g, m.cfg.robot_radius, pos, seg, pyaw, dist, 1.0, 0.5, 0.0)
+        assert np.array_equal(one["free"], fo) and np.array_equal(one["gain"], ro["gain"]) and np.array_equal(one["yaw_deg"], ro["yaw_deg"])
+        for k in ("index", "score", "best_gain", "best_yaw"):
+            assert one[k] == two[k], k
+    d = lambda a, t: torch.from_numpy(np.ascontiguousarray(a, t)).cuda()
+    d_pos, d_seg, d_py, d_di = d(pos, np.float64), d(seg, np.float64), d(pyaw, np.float64), d(dist, np.float64)
+    d_free = torch.full((n,), 9, dtype=torch.uint8, device="cuda")
+    d_gain = torch.zeros(n, dtype=torch.float64, device="cuda")
+    d_yaw = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_best = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+    g.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        for _ in range(3):
+            g.evaluate_candidates_device(lt_g, le_g, m.cfg.robot_radius, n, d_pos, d_seg, d_py, d_di, 1.0, 0.5, 0.0, d_free, d_best,
+                                         d_gain, d_yaw)
+        stream.synchronize()
+    g.set_stream(None)
+    assert np.array_equal(d_free.cpu().numpy(), fo) and np.array_equal(d_gain.cpu().numpy(), ro["gain"])
+    rec = np.frombuffer(d_best.cpu().numpy().tobytes(), dtype=[("index", "<i8"), ("score", "<f8"), ("gain", "<f8"), ("yaw", "<f8")])[0]
+    assert rec["index"] == two["index"] and rec["score"] == two["score"] and rec["gain"] == two["best_gain"] and rec["yaw"] == two["best_yaw"]
+    g.close()
