@@ -55,3 +55,26 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "nbv_oracle" not in txt and "nbvo_" not in txt, f
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/nbvgpu.h must compile as C99 (no C++ in the signatures) and a C program must link
+    against the library; without a device the context constructor reports NBVGPU_ERR_NO_DEVICE."""
+    import subprocess
+    import torch
+    N.build()
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include <stdio.h>\n#include "nbvgpu.h"\n'
+                   "int main(void) {\n"
+                   "  nbvgpu_ctx* c = 0;\n"
+                   "  int rc = nbvgpu_create(0, &c);\n"
+                   '  printf("%s rc=%d\\n", nbvgpu_version(), rc);\n'
+                   "  if (rc == NBVGPU_OK) nbvgpu_destroy(c);\n"
+                   "  return rc == NBVGPU_OK ? 0 : (rc == NBVGPU_ERR_NO_DEVICE ? 42 : 1);\n"
+                   "}\n")
+    exe = str(tmp_path / "c_abi")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src),
+                           "-o", exe, "-L", N.CSRC, "-lnbvgpu", f"-Wl,-rpath,{N.CSRC}"])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert "sm_100a" in r.stdout
+    assert r.returncode == (0 if torch.cuda.is_available() else 42), r.stdout + r.stderr
