@@ -1,10 +1,12 @@
 // gain_kernels.cuh -- sm_100a kernels for the viewpoint-gain evaluator and its satellites.
 //
-//   k_gain<V,LV,MODE>  RrtTree::optimized_gain / gain ray sweep   nbveplanner/src/rrt.cpp:351-447, 481-571
+//   k_gain<V,LV,MODE,FUSE,THREADS>
+//                      RrtTree::optimized_gain / gain ray sweep   nbveplanner/src/rrt.cpp:351-447, 481-571
 //                      + CameraModel planes / in-view test        nbveplanner/src/camera_model.cpp:5-23,98-164,191-201
 //                      + voxblox RayCaster                        voxblox/src/integrator/integrator_utils.cc:111-179
 //                      + getVoxelStatusByIndex                    nbveplanner/src/voxblox_manager.cpp:14-33
 //   k_best_yaw         best-yaw window scan                       nbveplanner/src/rrt.cpp:449-478
+//                      (FUSE: run by the last CTA of a candidate inside k_gain, small batches)
 //   k_score_best       node scoring / best node                   nbveplanner/src/rrt.cpp:220-246
 //   k_check_segments   HighResManager::checkMotion                nbveplanner/include/nbveplanner/voxblox_manager.h:89-108
 //   k_check_segments_warp   the same, one warp per segment (small batches)
@@ -18,7 +20,10 @@
 // per lane; the 32 lanes of a warp take 32 consecutive yaws of the same ray row u, i.e. rays one
 // degree apart that stay within a voxel or two of each other: near-identical trip counts (little
 // divergence) and loads that fall into the same sectors.  Per-yaw counts are accumulated with
-// shared-memory atomics and written once per CTA.
+// shared-memory atomics and written once per CTA.  MODE selects how a voxel's status is found (dense 2-bit
+// shared-memory volume, slot grid + status tiles, direct hash probes), THREADS the CTA width (256: four
+// CTAs per SM; 512: two, for volumes of up to half an SM's shared memory and for 90-yaw chunks of large
+// batches); the host picks them per launch (csrc/nbvgpu.cu: enqueue_gain).
 //
 // Exactness: the DDA is a literal float transcription (IEEE division, inf/NaN semantics kept);
 // the exploration-box test is done on integer voxel thresholds (exactly equivalent, see
