@@ -84,6 +84,16 @@ def main():
                 for i in range(len(c.segments)):
                     if g.check_motion(le, cfg.robot_radius, c.segments[i, :3], c.segments[i, 3:]) != bool(fo["free"][i]):
                         msg.append(f"variant {variant}: check_motion({i}) differs")
+            if variant == 0:
+                # one call per planning step (edge check beside the sweep) against the two calls and the oracle
+                nc = len(c.positions)
+                py = np.linspace(-3.0, 3.0, nc)
+                two = g.gain_eval_best(lt, c.positions, py, c.distance, fg, 1.0, 0.5, 0.0)
+                one = g.evaluate_candidates(lt, le, cfg.robot_radius, c.positions, c.segments, py, c.distance, 1.0, 0.5, 0.0)
+                if not (np.array_equal(one["free"], fo["free"]) and np.array_equal(one["gain"], ro["gain"][:nc]) and
+                        np.array_equal(one["yaw_deg"], ro["yaw_deg"][:nc]) and
+                        all(one[k] == two[k] for k in ("index", "score", "best_gain", "best_yaw"))):
+                    msg.append("evaluate_candidates differs from the two calls / the oracle")
             if variant == 2 and g.classifier_mismatches() != 0:
                 msg.append(f"variant 2: {g.classifier_mismatches()} cross-check mismatches")
             g.close()
