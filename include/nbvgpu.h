@@ -74,6 +74,12 @@ typedef struct {
   double q_CB[4];            /* extrinsic T_C_B rotation, (w, x, y, z)           */
   double t_CB[3];            /* extrinsic T_C_B translation                      */
   double bbx_min[3], bbx_max[3]; /* exploration box, bbx/min*, bbx/max*          */
+  /* The reference adds one of these per counted voxel to a running double in ray / voxel order (rrt.cpp:436-443); this
+   * library counts voxels as integers and forms n_u*g_u + n_o*g_o + n_f*g_f once per yaw.  The two are bit-identical
+   * when every partial sum is exact -- the defaults (0, 0, 1) and any weights that are multiples of 2^-20 below 1024 --
+   * and agree to 1e-6 relative otherwise (north_star's tolerance for the floating-point gain; the counts stay exact,
+   * a best-yaw window or best node may differ on ties closer than that: tests/test_gpu_parity.py::
+   * test_non_default_gain_weights_within_tolerance). */
   double gain_free, gain_occupied, gain_unmapped;
   int32_t sum_all_yaws;      /* 0: optimized_gain (best yaw window); 1: gain() (sum of all yaws, yaw = 0) */
   int32_t reserved;

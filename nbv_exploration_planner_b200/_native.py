@@ -58,30 +58,21 @@ class Best(C.Structure):
     _fields_ = [("index", C.c_int64), ("score", C.c_double), ("gain", C.c_double), ("yaw", C.c_double)]
 
 
-def _sources_newer(target: str, names) -> bool:
-    if not os.path.exists(target):
-        return True
-    t = os.path.getmtime(target)
-    for n in names:
-        p = os.path.join(CSRC, n) if not os.path.isabs(n) else n
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    return False
-
-
 def build(force: bool = False, verbose: bool = False) -> None:
     """Compile libnbvgpu.so / libnbvsynth.so in-tree (nvcc -gencode arch=compute_100a,code=sm_100a)."""
-    hdr = os.path.join(_HERE, "..", "include", "nbvgpu.h")
-    gpu_stale = _sources_newer(LIB_PATH, ["nbvgpu.cu", "gain_kernels.cuh", "map_mirror.cuh", "camera_host.cc",
-                                          "camera_host.h", "voxblox_io.cc", "voxblox_io.h", hdr])
-    synth_stale = _sources_newer(SYNTH_PATH, ["synth_gen.cc"])
-    if not (force or gpu_stale or synth_stale):
-        return
+    # make decides what is stale (the Makefile lists every header of the library)
     args = ["make", "-C", CSRC]
     if force:
         args.append("-B")
     out = None if verbose else subprocess.DEVNULL
-    subprocess.check_call(args, stdout=out, stderr=None if verbose else subprocess.STDOUT)
+    # one builder at a time: the ranks of a torchrun launch all come through here
+    import fcntl
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            subprocess.check_call(args, stdout=out, stderr=None if verbose else subprocess.STDOUT)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 _lib = None

@@ -120,10 +120,12 @@ __global__ void k_remove_keys(HashEntry* table, uint32_t mask, uint32_t shift, c
   uint32_t idx = hash_key(bx, by, bz) >> shift;
   for (uint32_t p = 0; p <= mask; ++p) {
     HashEntry* e = table + idx;
-    const unsigned long long k = e->key;
+    const unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(&e->key);
     if (k == key) {
+      // claim the entry: a key listed twice in one batch (Layer::removeBlock of an absent block is a no-op in the
+      // reference, so callers may do that) is freed by exactly one thread
+      if (atomicCAS(&e->key, key, KEY_TOMB) != key) return;
       const int slot = e->slot;
-      e->key = KEY_TOMB;
       e->slot = -1;
       if (slot >= 0) {
         const int top = atomicAdd(free_top, 1);

@@ -11,12 +11,17 @@ from conftest import load_gpu, load_oracle
 pytestmark = pytest.mark.gpu
 
 
-def _subset_vs_oracle(o, lt_o, g, lt_g, pos, k, seed):
+def _subset_vs_oracle(o, lt_o, g, lt_g, pos, k, seed, base=None):
+    """`base`: the result of the FULL batch (the launch shape the bench times): its rows for the subset are compared with
+    the oracle as they are, and so is a re-run of the subset alone (a smaller batch, i.e. another launch shape)."""
     sel = np.random.default_rng(seed).choice(len(pos), size=min(k, len(pos)), replace=False)
     ro = o.gain_eval(lt_o, pos[sel], per_yaw=True, threads=16)
     rg = g.gain_eval(lt_g, pos[sel], per_yaw=True)
     assert np.array_equal(rg["per_yaw"], ro["per_yaw"]) and np.array_equal(rg["steps"], ro["steps"])
     assert np.array_equal(rg["yaw_deg"], ro["yaw_deg"]) and np.array_equal(rg["gain"], ro["gain"])
+    if base is not None:
+        for key in ("per_yaw", "steps", "yaw_deg", "gain"):
+            assert np.array_equal(base[key][sel], ro[key]), key
 
 
 def test_cfg2_1000_candidates(oracle_mod, cfg1_map):
@@ -30,6 +35,7 @@ def test_cfg2_1000_candidates(oracle_mod, cfg1_map):
     assert np.array_equal(g.check_segments(le_g, cfg.robot_radius, c.segments),
                           o.check_segments(le_o, cfg.robot_radius, c.segments, threads=16)["free"])
     base = g.gain_eval(lt_g, c.positions, per_yaw=True)
+    assert g.wide_cta_launches() >= 1              # the launch the bench times: 90 yaws per 512-thread CTA, dense volume
     for variant in (1, 2, 4):
         g.set_kernel_variant(variant)
         r = g.gain_eval(lt_g, c.positions, per_yaw=True)
@@ -37,7 +43,7 @@ def test_cfg2_1000_candidates(oracle_mod, cfg1_map):
             assert np.array_equal(r[k], base[k]), (variant, k)
     assert g.classifier_mismatches() == 0
     g.set_kernel_variant(0)
-    _subset_vs_oracle(o, lt_o, g, lt_g, c.positions, 96, 1)
+    _subset_vs_oracle(o, lt_o, g, lt_g, c.positions, 96, 1, base)
     # best viewpoint: device scoring == host replay of rrt.cpp:220-246 on the same gains
     best = g.gain_eval_best(lt_g, c.positions, np.zeros(1000), c.distance, None, 1.0, 0.5, 0.0)
     score = base["gain"] / np.maximum(base["yaw"] / 0.5, c.distance / 1.0)
@@ -47,7 +53,7 @@ def test_cfg2_1000_candidates(oracle_mod, cfg1_map):
 
 def test_cfg3_office_map_subset(oracle_mod):
     """BASELINE config 3 geometry (50x50x10 m office-like, 0.10 m voxels): 2,000 candidates on the GPU,
-    variants agree everywhere, 48 of them checked against the oracle."""
+    variants agree on 400, 200 rows of the full batch checked against the oracle."""
     from nbv_exploration_planner_b200 import synth
     m = synth.make_map("cfg3")
     cfg = m.cfg
@@ -56,6 +62,7 @@ def test_cfg3_office_map_subset(oracle_mod):
     g, lt_g, le_g = load_gpu(m, cam)
     c = synth.make_candidates(cfg, 2000, lambda s: g.check_segments(le_g, cfg.robot_radius, s))
     base = g.gain_eval(lt_g, c.positions, per_yaw=True)
+    assert g.wide_cta_launches() >= 1              # config 3's launch: half-SM dense volume in 512-thread CTAs
     assert base["steps"].mean() > 1.0e6            # ~1.65 M steps per viewpoint without occlusion
     for variant in (1, 5):
         g.set_kernel_variant(variant)
@@ -64,10 +71,46 @@ def test_cfg3_office_map_subset(oracle_mod):
             assert np.array_equal(r[k], base[k][:400]), (variant, k)
     assert g.classifier_mismatches() == 0
     g.set_kernel_variant(0)
-    _subset_vs_oracle(o, lt_o, g, lt_g, c.positions, 48, 2)
+    _subset_vs_oracle(o, lt_o, g, lt_g, c.positions, 200, 2, base)
     seg_sel = np.arange(0, 2000, 4)
     assert np.array_equal(g.check_segments(le_g, cfg.robot_radius, c.segments[seg_sel]),
                           o.check_segments(le_o, cfg.robot_radius, c.segments[seg_sel], threads=16)["free"])
+    g.close()
+
+
+def test_cfg4_full_size_map(oracle_mod):
+    """BASELINE config 4 at full size: the 100x100x20 m outdoor map at 0.05 m voxels (143 k blocks, 4.7 GB of TSDF tiles in
+    the mirror), 8 m range.  400 candidates in one batch (the slot-grid sweep: the volume of a yaw chunk is megabytes);
+    the rows of the four best and eight more candidates of that batch equal the oracle's, and the cross-checking variant
+    reports no mismatch on a 24-candidate batch."""
+    from nbv_exploration_planner_b200 import LAYER_TSDF, NbvGpu, synth
+    m = synth.make_map("cfg4")
+    cfg = m.cfg
+    cam = m.camera()
+    assert len(m.keys) > 100000
+    o = oracle_mod.Oracle()
+    lt_o = o.layer_create(0, m.voxel_size, m.vps)
+    o.layer_update(lt_o, m.keys, m.tsdf)
+    o.set_camera(cam.as_dict())
+    g = NbvGpu(0)
+    lt_g = g.layer_create(LAYER_TSDF, m.voxel_size, m.vps, len(m.keys) + 64)
+    for i in range(0, len(m.keys), 8192):          # bounded pinned staging
+        g.layer_update(lt_g, m.keys[i:i + 8192], m.tsdf[i:i + 8192])
+        g.commit()
+    assert g.layer_num_blocks(lt_g) == len(m.keys)
+    g.set_camera(cam)
+    pos = synth.make_candidates(cfg, 400, None).positions
+    base = g.gain_eval(lt_g, pos, per_yaw=True)
+    assert base["steps"].mean() > 1.0e7 and base["gain"].max() > 0
+    sel = np.unique(np.concatenate([np.argsort(base["gain"])[-4:], np.random.default_rng(4).choice(400, 8, replace=False)]))
+    ro = o.gain_eval(lt_o, pos[sel], per_yaw=True, threads=16)
+    for key in ("per_yaw", "steps", "yaw_deg", "gain"):
+        assert np.array_equal(base[key][sel], ro[key]), key
+    g.set_kernel_variant(5)
+    r5 = g.gain_eval(lt_g, pos[:24], per_yaw=True)
+    for key in ("per_yaw", "steps", "yaw_deg", "gain"):
+        assert np.array_equal(r5[key], base[key][:24]), key
+    assert g.classifier_mismatches() == 0
     g.close()
 
 

@@ -153,3 +153,32 @@ def test_device_resident_update_matches_host_update():
     vb, fb, sb = g.layer_read_voxels(lb, gi)
     assert fa.all() and fb.all() and np.array_equal(va, vb) and np.array_equal(sa, sb)
     g.close()
+
+
+def test_removing_a_block_twice_in_one_commit_frees_it_once():
+    """Layer::removeBlock on an already removed block is a no-op in the reference (layer.h:171-173), so one commit may
+    carry the same key twice (and keys that were never there): the block count drops once per block, every tile slot
+    stays unique, and a full refill of the pool still fits."""
+    from nbv_exploration_planner_b200 import LAYER_TSDF, NbvGpu
+    rng = np.random.default_rng(21)
+    keys, tsdf = _random_layer(rng, 64, 8)
+    g = NbvGpu(0)
+    lt = g.layer_create(LAYER_TSDF, 0.1, 8, 64)          # pool of exactly 64 tiles
+    g.layer_update(lt, keys, tsdf)
+    g.commit()
+    dup = np.concatenate([keys[:20], keys[:20], keys[5:15], [[999, 999, 999]]]).astype(np.int32)
+    g.layer_remove(lt, dup)
+    g.commit()
+    assert g.layer_num_blocks(lt) == 44
+    # refill: 20 new blocks must each get a tile of their own (a doubly freed slot would be handed out twice)
+    new_keys = (keys[:20] + np.array([200, 0, 0])).astype(np.int32)
+    new_tsdf = np.empty((20, 8 ** 3, 2), np.float32)
+    new_tsdf[..., 0] = np.arange(20, dtype=np.float32)[:, None] + 0.5
+    new_tsdf[..., 1] = 1.0
+    g.layer_update(lt, new_keys, new_tsdf)
+    g.commit()
+    assert g.layer_num_blocks(lt) == 64
+    vals, found, _ = g.layer_read_voxels(lt, _all_voxels(np.concatenate([keys[20:], new_keys]), 8))
+    assert found.all()
+    assert np.array_equal(vals.reshape(64, 8 ** 3, 2), np.concatenate([tsdf[20:], new_tsdf]))
+    g.close()

@@ -113,6 +113,29 @@ def test_gain_matches_reference_other_geometry(tiny_map):
     assert np.array_equal(ro["gain"], rr["gain"]) and np.array_equal(ro["yaw"], rr["yaw"])
 
 
+@pytest.mark.parametrize("which", ["cfg3-like", "cfg4-like"])
+def test_gain_matches_reference_at_fine_voxels(which):
+    """The geometries BASELINE configs 3 and 4 live on -- 0.10 m voxels / 5 m range (58 ray rows, ~1.2 M steps per
+    viewpoint) and 0.05 m voxels / 8 m range (185 rows, ~14 M steps) -- on small maps: the oracle equals the
+    reference's own optimized_gain (gain and state[3]) and checkMotion, bit for bit."""
+    from nbv_exploration_planner_b200 import synth
+    if which == "cfg3-like":
+        cfg = synth.SynthConfig("cfg3small", (0, 0, 0), (20, 20, 10), 0.10, 5.0, 8, "office", 1203, 2203, (7.5, 7.5, 1.5), obs_radius=6.0,
+                                traj_points=6, traj_step=4.0, vicinity=4.0)
+        n = 8
+    else:
+        cfg = synth.SynthConfig("cfg4small", (0, 0, 0), (16, 16, 6), 0.05, 8.0, 6, "pillars", 1204, 2204, (8.0, 8.0, 2.0), obs_radius=7.0,
+                                traj_points=3, traj_step=3.0, vicinity=2.0)
+        n = 4
+    m = synth.make_map(cfg)
+    o, lt, le, r = _both(m, m.camera(), cfg.robot_radius)
+    c = synth.make_candidates(cfg, n, None)
+    ro, rr = o.gain_eval(lt, c.positions, threads=8), r.gain_eval(c.positions)
+    assert np.array_equal(ro["gain"], rr["gain"]) and np.array_equal(ro["yaw"], rr["yaw"])
+    assert ro["gain"].max() > 0 and ro["steps"].min() > 1.0e6
+    assert np.array_equal(o.check_segments(le, cfg.robot_radius, c.segments)["free"], r.check_segments(c.segments))
+
+
 @pytest.mark.parametrize("sum_all", [0, 1])
 @pytest.mark.parametrize("state", ["unknown", "free", "occupied"])
 def test_rays_stuck_at_yaw_plus_minus_90_match_reference(state, sum_all):
