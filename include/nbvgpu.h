@@ -106,6 +106,34 @@ typedef struct {
 /* ---- context ---------------------------------------------------------------------------- */
 int nbvgpu_create(int device, nbvgpu_ctx** out);
 void nbvgpu_destroy(nbvgpu_ctx* ctx);
+
+/* ---- multi-GPU contexts (nbvgpu_config{n_gpus, device_ids}) ------------------------------------
+ * The path shards by candidates: every GPU keeps a replica of the map mirror and evaluates a contiguous block of
+ * ceil(n / world) candidates of each batch; nbvgpu_commit replicates the changed blocks with ONE ncclBroadcast per chunk
+ * of {descriptor table | payload} over NVLink; the per-shard best records come back through page-locked host memory that
+ * every GPU writes and every rank reads (no collective, no copy, no stream synchronisation per planning step).  NCCL is
+ * looked up at run time in the libnccl.so.2 the process already has (PyTorch's), else $NBVGPU_NCCL_LIB, else the system's.
+ *
+ * Two ways to build one -- the handle then goes through the SAME entry points as a single-GPU context:
+ *  nbvgpu_create_multi  one process drives n_gpus devices (what the reference's single C++ planner process needs:
+ *                       rrt.cpp:210-219, history.cpp:249,461,555 keep calling one handle).  device_ids may be NULL (0..n-1).
+ *  nbvgpu_create_rank   one process per GPU (torchrun / MPI style launches): rank 0 obtains an id with
+ *                       nbvgpu_group_unique_id (128 bytes) and hands it to the other ranks by whatever means the launcher has.
+ * Semantics on such a handle:
+ *  - layer_create, layer_clear, set_camera, set_kernel_variant, commit and the batch evaluators listed next are
+ *    COLLECTIVE in the one-process-per-GPU form: every rank makes the same calls in the same order;
+ *  - layer_update / layer_update_pinned / layer_remove stage on rank 0 (NBVGPU_ERR_STATE on other ranks);
+ *  - nbvgpu_evaluate_candidates and nbvgpu_gain_eval_best take the WHOLE batch on every rank, evaluate this process's
+ *    shard(s) and return the best node of the whole batch; per-candidate outputs are filled for the shards evaluated in
+ *    this process (all of them with nbvgpu_create_multi);
+ *  - nbvgpu_gain_eval / nbvgpu_check_segments shard large batches over the GPUs of this process;
+ *  - everything else (n = 1 shims, frontier, interpolation, tree expansion, read-back, _device variants) runs on this
+ *    process's first GPU: the map is replicated, so any replica answers. */
+int nbvgpu_create_multi(int n_gpus, const int* device_ids, nbvgpu_ctx** out);
+int nbvgpu_group_unique_id(uint8_t* id_out, size_t len /* >= 128 */);
+int nbvgpu_create_rank(int device, int rank, int world, const uint8_t* unique_id, size_t len, nbvgpu_ctx** out);
+/* rank of this process's first GPU, number of GPUs in the context, GPUs driven by this process (any may be NULL). */
+int nbvgpu_group_info(nbvgpu_ctx* ctx, int* rank, int* world, int* local_gpus);
 /* Use the caller's cudaStream_t (passed as void*) for all subsequent work; NULL restores the
  * library-owned stream (pass cudaStreamLegacy / cudaStreamPerThread to name the default streams). */
 int nbvgpu_set_stream(nbvgpu_ctx* ctx, void* cuda_stream);
@@ -123,13 +151,22 @@ int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int voxels_
  * to evaluations at the next nbvgpu_commit. keys = BlockIndex[n] (int32 x 3). */
 int nbvgpu_layer_update(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32_t* keys,
                         const void* payload, int packing);
-/* Same with device buffers (keys must be unique within the call); applied in stream order. */
+/* Same without the staging copy: `payload` must be page-locked host memory (cudaHostAlloc / cudaHostRegister) and must
+ * stay untouched until nbvgpu_commit has returned; the commit copies it to the GPU straight from there (the upload hook
+ * can serialise Layer::getAllUpdatedBlocks into such a buffer). */
+int nbvgpu_layer_update_pinned(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32_t* keys,
+                               const void* payload, int packing);
+/* Same with device buffers (single-GPU contexts); applied in stream order.  A key listed twice is written by either copy. */
 int nbvgpu_layer_update_device(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32_t* d_keys,
                                const void* d_payload, int packing);
 /* Layer::removeBlock (layer.h:171-173) / removeAllBlocks (:175). */
 int nbvgpu_layer_remove(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32_t* keys);
 int nbvgpu_layer_clear(nbvgpu_ctx* ctx, int layer);
-/* Publish staged updates/removals to the device snapshot (one H2D copy + scatter kernels). */
+/* Publish staged updates/removals of ALL layers to the device snapshot: removals in one small launch, then per chunk of at
+ * most 64 MiB of payload ($NBVGPU_CHUNK_MB) one device buffer {32-byte block descriptors | payload}, filled by host->device
+ * copies (of chunk k+1 while chunk k is applied), broadcast over NCCL in a multi-GPU context, and applied by ONE kernel
+ * (a CTA per block: hash insert-or-find, then the tile written with 128-bit stores).  Synchronous: returns after the
+ * snapshot is in place, NBVGPU_ERR_CAPACITY if a tile pool or table overflowed. */
 int nbvgpu_commit(nbvgpu_ctx* ctx);
 /* Layer::getNumberOfAllocatedBlocks (layer.h:205). */
 int nbvgpu_layer_num_blocks(nbvgpu_ctx* ctx, int layer, size_t* out);
@@ -177,7 +214,7 @@ int nbvgpu_optimized_gain(nbvgpu_ctx* ctx, int tsdf_layer, double state[4], doub
 /* Batched evaluation + node scoring (rrt.cpp:220-246): score = gain / max(dyaw / dyaw_max,
  * distance / v_max) with dyaw = yaw - parent_yaw wrapped once into (-pi, pi] (not abs'd, as in the
  * reference); best = first candidate with score > running best starting at zero_gain.
- * edge_free (may be NULL) masks candidates whose edge failed checkMotion.
+ * edge_free (may be NULL) masks candidates whose edge failed checkMotion: they are neither swept nor scored (gain = yaw = 0).
  * gain / yaw_deg (may be NULL) receive the per-candidate results as in nbvgpu_gain_eval. */
 int nbvgpu_gain_eval_best(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, const double* pos,
                           const double* parent_yaw, const double* distance, const uint8_t* edge_free,
@@ -192,8 +229,8 @@ int nbvgpu_gain_eval_best_device(nbvgpu_ctx* ctx, int tsdf_layer, size_t n, cons
 /* Edge check + gain + node scoring of n candidates in one call: what RrtTree::iterate does with a sample after the
  * sampler (rrt.cpp:205-246) -- checkMotion on seg[i] = {start xyz, end xyz} (voxblox_manager.h:89-108), optimized_gain at
  * pos[i], the score / best-node update -- i.e. nbvgpu_check_segments followed by nbvgpu_gain_eval_best with its verdicts,
- * with identical results.  One call instead of two lets the edge check run beside the ray sweep (a side stream forked from
- * and joined into the context's stream) and, for host buffers, saves a copy / synchronise round trip.  edge_free receives the
+ * with identical results.  As in the reference (rrt.cpp:210-216) a candidate whose edge collides is not swept: its gain and
+ * yaw read 0.  One call instead of two saves, for host buffers, a copy / synchronise round trip.  edge_free receives the
  * per-candidate verdicts (required for the device variant, optional for the host variant); gain / yaw_deg may be NULL. */
 int nbvgpu_evaluate_candidates(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double robot_radius, size_t n,
                                const double* pos, const double* seg, const double* parent_yaw, const double* distance,
@@ -203,6 +240,14 @@ int nbvgpu_evaluate_candidates_device(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_
                                       const double* d_pos, const double* d_seg, const double* d_parent_yaw,
                                       const double* d_distance, double v_max, double dyaw_max, double zero_gain,
                                       uint8_t* d_edge_free, nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg);
+/* One-process-per-GPU contexts, inputs already in this GPU's memory: this rank's shard -- n_local candidates whose first
+ * has global index index_offset -- is evaluated as above and its best record posted to the shared block; the call then
+ * waits for the records of every rank and returns the best node of the whole batch in HOST memory (*best).  Collective:
+ * every rank calls it once per batch, a rank without candidates with n_local = 0.  d_gain / d_yaw_deg may be NULL. */
+int nbvgpu_evaluate_shard_device(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double robot_radius, size_t n_local,
+                                 int64_t index_offset, const double* d_pos, const double* d_seg, const double* d_parent_yaw,
+                                 const double* d_distance, double v_max, double dyaw_max, double zero_gain,
+                                 uint8_t* d_edge_free, double* d_gain, int32_t* d_yaw_deg, nbvgpu_best* best);
 
 /* ---- batched tree expansion ------------------------------------------------- */
 /* Parameters of RrtTree::iterate that are not in nbvgpu_camera (params.h:26-35,93,103; rrt.cpp:175). */

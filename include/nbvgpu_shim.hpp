@@ -39,6 +39,14 @@ class GpuMap {
     check(ctx_, nbvgpu_layer_create(ctx_, NBVGPU_LAYER_TSDF, lowres_voxel_size, lowres_vps, lowres_max_blocks, &tsdf_), "layer_create");
     check(ctx_, nbvgpu_layer_create(ctx_, NBVGPU_LAYER_ESDF, hires_voxel_size, hires_vps, hires_max_blocks, &esdf_), "layer_create");
   }
+  /// The same on several GPUs of this box (nbvgpu_create_multi): the planner keeps ONE handle; batches are sharded over the
+  /// GPUs, every upload is replicated by an NCCL broadcast inside nbvgpu_commit.  n = 1 calls run on the first GPU.
+  GpuMap(const std::vector<int>& devices, float lowres_voxel_size, int lowres_vps, size_t lowres_max_blocks, float hires_voxel_size,
+         int hires_vps, size_t hires_max_blocks) {
+    check(nullptr, nbvgpu_create_multi((int)devices.size(), devices.data(), &ctx_), "nbvgpu_create_multi");
+    check(ctx_, nbvgpu_layer_create(ctx_, NBVGPU_LAYER_TSDF, lowres_voxel_size, lowres_vps, lowres_max_blocks, &tsdf_), "layer_create");
+    check(ctx_, nbvgpu_layer_create(ctx_, NBVGPU_LAYER_ESDF, hires_voxel_size, hires_vps, hires_max_blocks, &esdf_), "layer_create");
+  }
   ~GpuMap() { nbvgpu_destroy(ctx_); }
   GpuMap(const GpuMap&) = delete;
   GpuMap& operator=(const GpuMap&) = delete;
@@ -117,6 +125,20 @@ inline bool checkMotion(GpuMap& map, double robot_radius, const T& start, const 
   int free_seg = 0;
   check(map.ctx(), nbvgpu_check_motion(map.ctx(), map.esdf_layer(), robot_radius, a, b, &free_seg), "check_motion");
   return free_seg != 0;
+}
+
+/// The body of RrtTree::iterate after the sampler (rrt.cpp:205-246) for a whole batch of samples in one call: checkMotion on
+/// every edge, optimized_gain behind the free ones, node score against the parent's yaw / distance, first strict maximum
+/// over zero_gain.  pos[n][3], seg[n][6] (parent xyz, end point with overshoot), parent_yaw[n], distance[n]; outputs
+/// edge_free[n], gain[n], yaw_deg[n] (any may be null) and the best node.
+inline nbvgpu_best evaluateCandidates(GpuMap& map, double robot_radius, size_t n, const double* pos, const double* seg,
+                                      const double* parent_yaw, const double* distance, double v_max, double dyaw_max,
+                                      double zero_gain, uint8_t* edge_free, double* gain, int32_t* yaw_deg) {
+  nbvgpu_best best;
+  check(map.ctx(), nbvgpu_evaluate_candidates(map.ctx(), map.tsdf_layer(), map.esdf_layer(), robot_radius, n, pos, seg, parent_yaw,
+                                              distance, v_max, dyaw_max, zero_gain, edge_free, &best, gain, yaw_deg),
+        "evaluate_candidates");
+  return best;
 }
 
 /// bool HighResManager::getDistanceAndGradientAtPosition(const Point& pos, double* distance, Eigen::Vector3d* grad)

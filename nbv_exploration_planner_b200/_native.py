@@ -96,6 +96,13 @@ def lib() -> C.CDLL:
     L.nbvgpu_last_error.restype = C.c_char_p
     L.nbvgpu_last_error.argtypes = [vp]
     L.nbvgpu_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.nbvgpu_create_multi.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    L.nbvgpu_group_unique_id.argtypes = [vp, C.c_size_t]
+    L.nbvgpu_create_rank.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(vp)]
+    L.nbvgpu_group_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.nbvgpu_layer_update_pinned.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_int]
+    L.nbvgpu_evaluate_shard_device.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_size_t, C.c_int64, vp, vp, vp, vp, C.c_double,
+                                               C.c_double, C.c_double, vp, vp, vp, C.POINTER(Best)]
     L.nbvgpu_destroy.argtypes = [vp]
     L.nbvgpu_destroy.restype = None
     L.nbvgpu_set_stream.argtypes = [vp, vp]
@@ -161,7 +168,8 @@ def synth_lib() -> C.CDLL:
 
 # Every symbol include/nbvgpu.h declares (checked by tests/test_abi_symbols.py against the header).
 ABI_SYMBOLS = [
-    "nbvgpu_create", "nbvgpu_destroy", "nbvgpu_set_stream", "nbvgpu_synchronize", "nbvgpu_last_error", "nbvgpu_version",
+    "nbvgpu_create", "nbvgpu_create_multi", "nbvgpu_group_unique_id", "nbvgpu_create_rank", "nbvgpu_group_info",
+    "nbvgpu_layer_update_pinned", "nbvgpu_evaluate_shard_device", "nbvgpu_destroy", "nbvgpu_set_stream", "nbvgpu_synchronize", "nbvgpu_last_error", "nbvgpu_version",
     "nbvgpu_layer_create", "nbvgpu_layer_update", "nbvgpu_layer_update_device", "nbvgpu_layer_remove",
     "nbvgpu_layer_clear", "nbvgpu_commit", "nbvgpu_layer_num_blocks", "nbvgpu_layer_read_voxels",
     "nbvgpu_set_camera", "nbvgpu_gain_eval", "nbvgpu_gain_eval_device", "nbvgpu_optimized_gain",

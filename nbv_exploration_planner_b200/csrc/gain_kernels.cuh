@@ -1043,11 +1043,19 @@ struct BestRecord {
   long long index;
   double score, gain, yaw;
 };
+// Multi-GPU contexts: where the record of this GPU's shard is also posted -- a 64-byte slot in host memory that every rank
+// of the context can read (csrc/multi_gpu.h: BestSlot), index made global, the evaluation's sequence number stored last.
+struct BestPost {
+  void* slot;               // null: single-GPU context, nothing is posted
+  long long index_offset;   // first candidate of this GPU's shard
+  unsigned seq;
+};
 
 __global__ void __launch_bounds__(1024) k_score_best(const double* __restrict__ gain, const int32_t* __restrict__ yaw_deg,
                                                      const double* __restrict__ parent_yaw, const double* __restrict__ distance,
                                                      const uint8_t* __restrict__ edge_free, int n, double v_max, double dyaw_max,
-                                                     double zero_gain, BestRecord* out, double* score_out = nullptr) {
+                                                     double zero_gain, BestRecord* out, double* score_out = nullptr,
+                                                     const BestPost post = BestPost{nullptr, 0, 0u}) {
   __shared__ double s_score[32];
   __shared__ int s_idx[32];
   double best = zero_gain;
@@ -1087,11 +1095,20 @@ __global__ void __launch_bounds__(1024) k_score_best(const double* __restrict__ 
       if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
     }
     if (lane == 0) {
+      BestRecord r;
       if (best_i == INT_MAX) {
-        out->index = -1; out->score = zero_gain; out->gain = 0.0; out->yaw = 0.0;
+        r.index = -1; r.score = zero_gain; r.gain = 0.0; r.yaw = 0.0;
       } else {
-        out->index = best_i; out->score = best; out->gain = gain[best_i];
-        out->yaw = __ddiv_rn(dmul((double)yaw_deg[best_i], 3.14159265358979323846), 180.0);
+        r.index = best_i; r.score = best; r.gain = gain[best_i];
+        r.yaw = __ddiv_rn(dmul((double)yaw_deg[best_i], 3.14159265358979323846), 180.0);
+      }
+      if (out) *out = r;
+      if (post.slot) {  // record first, system-wide fence, then the ticket the hosts poll
+        volatile BestRecord* s = reinterpret_cast<volatile BestRecord*>(post.slot);
+        s->index = r.index >= 0 ? r.index + post.index_offset : -1;
+        s->score = r.score; s->gain = r.gain; s->yaw = r.yaw;
+        __threadfence_system();
+        *reinterpret_cast<volatile unsigned*>(reinterpret_cast<char*>(post.slot) + 32) = post.seq;
       }
     }
   }

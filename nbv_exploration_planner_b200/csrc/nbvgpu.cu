@@ -23,6 +23,7 @@
 #include "frontier_kernels.cuh"
 #include "interp_kernels.cuh"
 #include "map_mirror.cuh"
+#include "multi_gpu.h"
 #include "voxblox_io.h"
 
 using namespace nbvgpu;
@@ -57,7 +58,7 @@ struct PinBuf {  // grow-only pinned host staging
     if (bytes <= cap) return cudaSuccess;
     size_t want = bytes + bytes / 2 + 4096;
     void* q = nullptr;
-    cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocMapped);  // kernels of the small-batch paths read / write it in place
+    cudaError_t e = cudaHostAlloc(&q, want, cudaHostAllocMapped | cudaHostAllocPortable);  // kernels of the small-batch paths read / write it in place; every device of a multi-GPU context copies from it
     if (e != cudaSuccess) return e;
     if (p) {
       if (keep) memcpy(q, p, cap);
@@ -76,14 +77,6 @@ struct PinBuf {  // grow-only pinned host staging
   T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct KeyH {
-  int32_t x, y, z;
-  bool operator==(const KeyH& o) const { return x == o.x && y == o.y && z == o.z; }
-};
-struct KeyHHash {
-  size_t operator()(const KeyH& k) const { return (size_t)hash_key(k.x, k.y, k.z) ^ ((size_t)k.z << 32); }
-};
-
 struct LayerHost {
   int kind = 0;
   float voxel_size = 0.f;
@@ -94,17 +87,9 @@ struct LayerHost {
   void* d_tiles = nullptr;
   uint32_t* d_status = nullptr;
   int* d_free_list = nullptr;
-  int* d_free_top = nullptr;            // [0] free_top, [1] err
-  unsigned long long* d_nblocks = nullptr;
-  size_t n_blocks = 0;                  // as of the last commit
+  unsigned long long* d_state = nullptr;  // two words inside nbvgpu_ctx::d_lstate: live blocks | {free_top, err}
+  size_t n_blocks = 0;                    // as of the last commit
   size_t tombstones = 0;
-  // staged (uncommitted) operations
-  PinBuf h_keys, h_payload;             // updates
-  int pending_packing = -1;
-  size_t pending = 0;
-  std::unordered_map<KeyH, size_t, KeyHHash> pending_index;
-  std::vector<int32_t> pending_remove;
-  DevBuf d_keys, d_payload, d_slots;
   size_t payload_bytes_per_block(int packing) const {
     if (kind == NBVGPU_LAYER_TSDF) return (size_t)nvox * (packing == NBVGPU_PACK_PLANAR ? 8 : 12);
     return (size_t)nvox * (packing == NBVGPU_PACK_PLANAR ? 4 : 8);
@@ -120,16 +105,90 @@ struct LayerHost {
     v.nvox = nvox;
     return v;
   }
+  LayerDev dev() const {
+    LayerDev d;
+    d.table = d_table;
+    d.tiles = d_tiles;
+    d.status = d_status;
+    d.free_list = d_free_list;
+    d.state = d_state;
+    d.mask = cap - 1;
+    d.shift = 32 - log2cap;
+    d.nvox = nvox;
+    d.kind = kind;
+    return d;
+  }
+};
+
+// Staged (uncommitted) map operations: what nbvgpu_layer_update / _remove collected since the last nbvgpu_commit.  One
+// descriptor per block; payload bytes stay where they are until the commit copies them -- in the library's pinned arena
+// (nbvgpu_layer_update copies the caller's buffer there) or in the caller's own page-locked memory
+// (nbvgpu_layer_update_pinned).  Device offsets are assigned at staging time, so a commit is: descriptor table + payload
+// ranges -> one device buffer (-> one broadcast) -> one kernel.
+struct LKey {
+  int32_t layer, x, y, z;
+  bool operator==(const LKey& o) const { return layer == o.layer && x == o.x && y == o.y && z == o.z; }
+};
+struct LKeyHash {
+  size_t operator()(const LKey& k) const { return (size_t)hash_key(k.x, k.y, k.z) ^ ((size_t)k.z << 32) ^ ((size_t)k.layer << 48); }
+};
+struct UpdateStage {
+  struct Segment {
+    const char* host;  // caller's pinned memory, or null: arena + arena_off
+    size_t arena_off, bytes, dev_off;
+  };
+  std::vector<BlockDesc> descs;
+  std::vector<Segment> segs;
+  PinBuf arena;
+  size_t arena_used = 0, dev_bytes = 0;
+  std::unordered_map<LKey, size_t, LKeyHash> index;  // (layer, block) -> its latest descriptor
+  void add(int layer, const int32_t* key, int packing, int op, size_t payload_off) {
+    const LKey k{layer, key[0], key[1], key[2]};
+    auto it = index.find(k);
+    if (it != index.end()) descs[it->second].op = (int8_t)kOpSkip;  // last write wins; an update supersedes a staged removal and vice versa
+    BlockDesc d;
+    d.payload_off = payload_off;
+    d.key[0] = key[0]; d.key[1] = key[1]; d.key[2] = key[2];
+    d.layer = (int16_t)layer;
+    d.packing = (int8_t)packing;
+    d.op = (int8_t)op;
+    d.pad[0] = d.pad[1] = 0u;
+    index[k] = descs.size();
+    descs.push_back(d);
+  }
+  void drop_layer(int layer) {  // nbvgpu_layer_clear: forget what was staged for that layer
+    for (BlockDesc& d : descs)
+      if (d.layer == layer) d.op = (int8_t)kOpSkip;
+    for (auto it = index.begin(); it != index.end();) it = it->first.layer == layer ? index.erase(it) : std::next(it);
+  }
+  void clear() {
+    descs.clear();
+    segs.clear();
+    index.clear();
+    arena_used = dev_bytes = 0;
+  }
+  bool empty() const { return descs.empty(); }
 };
 
 }  // namespace
 
+struct Group;
 struct nbvgpu_ctx {
   int device = 0;
+  Group* group = nullptr;  // multi-GPU context: shared by its members; the public handle is member 0 of this process
+  int member = 0;          // index among the members in this process
   cudaStream_t own_stream = nullptr, stream = nullptr;
   std::mutex mu;
   std::string err;
   std::vector<LayerHost*> layers;
+  unsigned long long* d_lstate = nullptr;  // [kMaxLayers][2]: per layer live blocks | {free_top, err} (update kernels)
+  UpdateStage stage;                       // staged map operations (of the root rank in a multi-GPU context)
+  PinBuf h_table[2];                       // descriptor tables of the chunks in flight
+  DevBuf d_stage[2];                       // device staging of a commit: [descriptor table | payload bytes], double buffered
+  DevBuf d_utab;                           // descriptor table of nbvgpu_layer_update_device
+  cudaStream_t copy_stream = nullptr;      // host->device copies of chunk k+1 beside the broadcast / scatter of chunk k
+  cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_applied[2] = {nullptr, nullptr};
+  size_t chunk_bytes = 64u << 20;          // payload bytes per chunk of a large commit (NBVGPU_CHUNK_MB)
   bool cam_set = false;
   nbvgpu_camera cam{};
   nbvgpu_host::CameraTables tab{};
@@ -168,8 +227,6 @@ struct nbvgpu_ctx {
   DevBuf d_arrive;  // per-candidate CTA arrival counters of the fused sweep (zero between launches)
   bool no_fuse = false;                        // NBVGPU_NO_FUSE: keep the two-launch path for small batches (experiments)
   bool no_small = false;                       // NBVGPU_NO_SMALL_PATH: small batches go through the staged copies (experiments)
-  cudaStream_t side_stream = nullptr;          // nbvgpu_evaluate_candidates*: the edge check runs beside the ray sweep
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool no_wide_cta = false;                    // NBVGPU_NO_WIDE_CTA: never use the 512-thread dense sweep (experiments)
   unsigned long long stats_wide_cta = 0;       // ray-sweep launches with 512-thread CTAs and a half-SM dense volume (tests)
   unsigned long long stats_fused = 0;          // ray-sweep launches that finished with the fused window scan (tests)
@@ -180,6 +237,20 @@ struct nbvgpu_ctx {
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
   size_t prof_used = 0;
+};
+
+// A multi-GPU context (nbvgpu_create_multi: every GPU in this process; nbvgpu_create_rank: one GPU per process).  Rank r of
+// `world` evaluates the r-th contiguous block of a batch against its replica of the map.
+struct Group {
+  std::vector<nbvgpu_ctx*> local;  // members in this process; local[i] is rank rank0 + i
+  int world = 1, rank0 = 0;
+  bool multi_process = false;
+  std::vector<ncclComm_t> comms;   // one per local member
+  SharedMap shared;                // best-record slots + commit plan, readable by every rank, writable by every GPU
+  std::vector<SharedBlock*> d_shared;  // device-side address of `shared` per local member
+  unsigned long long eval_seq = 0, commit_seq = 0;
+  std::mutex mu;
+  std::string err;
 };
 
 namespace {
@@ -228,62 +299,36 @@ void free_layer(LayerHost* L) {
   cudaFree(L->d_tiles);
   cudaFree(L->d_status);
   cudaFree(L->d_free_list);
-  cudaFree(L->d_free_top);
-  cudaFree(L->d_nblocks);
-  L->h_keys.release();
-  L->h_payload.release();
-  L->d_keys.release();
-  L->d_payload.release();
-  L->d_slots.release();
   delete L;
 }
 
-// Apply n blocks whose keys / payload are already on the device (stream ordered).
-int apply_update_device(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const int32_t* d_keys, const void* d_payload, int packing) {
-  if (n == 0) return NBVGPU_OK;
-  CK(L->d_slots.reserve(n * sizeof(int)));
-  const int threads = 128;
-  k_insert_keys<<<(unsigned)((n + threads - 1) / threads), threads, 0, ctx->stream>>>(
-      L->d_table, L->cap - 1, 32 - L->log2cap, d_keys, (int)n, L->d_free_list, L->d_free_top, L->d_slots.as<int>(),
-      L->d_free_top + 1, L->d_nblocks);
-  ctx->stats.kernel_launches++;
-  if (L->kind == NBVGPU_LAYER_TSDF) {
-    const int per = L->nvox / 2;
-    const int tpb = per < 256 ? per : 256;
-    dim3 grid((per + tpb - 1) / tpb, (unsigned)n);
-    if (packing == NBVGPU_PACK_PLANAR)
-      k_scatter_tsdf<0><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float2*)L->d_tiles, L->d_status, L->nvox);
-    else
-      k_scatter_tsdf<1><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float2*)L->d_tiles, L->d_status, L->nvox);
-  } else {
-    const int per = L->nvox / 4;
-    const int tpb = per < 256 ? ((per + 31) / 32) * 32 : 256;  // whole warps: the observed bits are combined by shuffles
-    dim3 grid((per + tpb - 1) / tpb, (unsigned)n);
-    if (packing == NBVGPU_PACK_PLANAR)
-      k_scatter_esdf<0><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float*)L->d_tiles, L->d_status, L->nvox);
-    else
-      k_scatter_esdf<1><<<grid, tpb, 0, ctx->stream>>>(d_payload, L->d_slots.as<int>(), (float*)L->d_tiles, L->d_status, L->nvox);
-  }
-  ctx->stats.kernel_launches++;
-  ctx->stats.blocks_uploaded += n;
-  CK(cudaGetLastError());
-  return NBVGPU_OK;
+ApplyLayers apply_layers(const nbvgpu_ctx* ctx) {
+  ApplyLayers a;
+  memset(&a, 0, sizeof a);
+  for (size_t i = 0; i < ctx->layers.size() && i < (size_t)kMaxLayers; ++i)
+    if (ctx->layers[i]) a.L[i] = ctx->layers[i]->dev();
+  return a;
 }
 
-// Read back {n_blocks, err} of a layer (synchronises the stream).
-int sync_layer_state(nbvgpu_ctx* ctx, LayerHost* L) {
-  CK(ctx->h_io.reserve(64, false));
+// Read back {live blocks, err} of every layer (one small copy; synchronises the stream).  Returns the first capacity
+// error found and clears it on the device.
+int sync_layer_states(nbvgpu_ctx* ctx) {
+  CK(ctx->h_io.reserve(kMaxLayers * 16 + 64, false));
   unsigned long long* h = ctx->h_io.as<unsigned long long>();
-  CK(cudaMemcpyAsync(h, L->d_nblocks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaMemcpyAsync(h + 1, L->d_free_top, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaMemcpyAsync(h, ctx->d_lstate, kMaxLayers * 16, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  L->n_blocks = (size_t)h[0];
-  const int err = reinterpret_cast<int*>(h + 1)[1];
-  if (err) {
-    CK(cudaMemsetAsync(L->d_free_top + 1, 0, sizeof(int), ctx->stream));
-    return fail(ctx, NBVGPU_ERR_CAPACITY, (err & 1) ? "layer tile pool exhausted (max_blocks)" : "layer hash table full");
+  int rc = NBVGPU_OK;
+  for (size_t i = 0; i < ctx->layers.size(); ++i) {
+    LayerHost* L = ctx->layers[i];
+    if (!L) continue;
+    L->n_blocks = (size_t)h[2 * i];
+    const int err = reinterpret_cast<const int*>(h + 2 * i + 1)[1];
+    if (err) {
+      CK(cudaMemsetAsync(reinterpret_cast<char*>(L->d_state + 1) + 4, 0, sizeof(int), ctx->stream));
+      if (rc == NBVGPU_OK) rc = fail(ctx, NBVGPU_ERR_CAPACITY, (err & 1) ? "layer tile pool exhausted (max_blocks)" : "layer hash table full");
+    }
   }
-  return NBVGPU_OK;
+  return rc;
 }
 
 int rehash_if_needed(nbvgpu_ctx* ctx, LayerHost* L, size_t incoming) {
@@ -300,6 +345,163 @@ int rehash_if_needed(nbvgpu_ctx* ctx, LayerHost* L, size_t incoming) {
   return NBVGPU_OK;
 }
 
+// ---- commit: staged operations -> device ---------------------------------------------------------------------------
+// A commit walks the staged descriptors in order and cuts them into chunks of at most chunk_bytes of payload.  Per chunk:
+// descriptor table and payload ranges are copied into one device buffer [table | payload]; with several GPUs that buffer
+// is broadcast from the root (csrc/multi_gpu.h); k_apply_blocks inserts the blocks and writes their tiles.  Two device
+// buffers alternate, and from the second chunk on the copies run on their own stream, so the copy of chunk k+1 overlaps
+// the broadcast and scatter of chunk k.  Removals go first, in one small launch.
+struct ChunkPlan {
+  size_t first = 0, end = 0;      // descriptor range [first, end)
+  size_t lo = 0, hi = 0;          // payload byte range (staging offsets)
+  size_t n_update = 0;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Next chunk starting at descriptor `from`; false when nothing is left.
+bool next_chunk(const nbvgpu_ctx* ctx, const UpdateStage& st, size_t from, ChunkPlan* out) {
+  ChunkPlan c;
+  size_t i = from;
+  while (i < st.descs.size() && st.descs[i].op != kOpUpdate) ++i;
+  if (i >= st.descs.size()) return false;
+  c.first = i;
+  c.lo = (size_t)st.descs[i].payload_off;
+  for (; i < st.descs.size(); ++i) {
+    const BlockDesc& d = st.descs[i];
+    if (d.op != kOpUpdate) continue;
+    const LayerHost* L = ctx->layers[d.layer];
+    const size_t end = (size_t)d.payload_off + L->payload_bytes_per_block(d.packing);
+    if (c.n_update && end - c.lo > ctx->chunk_bytes) break;
+    c.hi = end;
+    c.n_update++;
+  }
+  c.end = i;
+  *out = c;
+  return true;
+}
+
+// Host part of a chunk on the rank that holds the staged data: descriptor table into pinned memory, then the copies.
+// dst layout: [table: align256(n * 32) | payload: hi - lo].  Returns the table bytes through *tb.
+int stage_chunk_h2d(nbvgpu_ctx* ctx, const UpdateStage& st, const ChunkPlan& c, int parity, cudaStream_t s, size_t* tb_out) {
+  const size_t tb = align_up(c.n_update * sizeof(BlockDesc), 256);
+  CK(ctx->h_table[parity].reserve(tb, false));
+  CK(ctx->d_stage[parity].reserve(tb + (c.hi - c.lo)));
+  BlockDesc* t = ctx->h_table[parity].as<BlockDesc>();
+  size_t k = 0;
+  for (size_t i = c.first; i < c.end; ++i) {
+    if (st.descs[i].op != kOpUpdate) continue;
+    t[k] = st.descs[i];
+    t[k].payload_off -= c.lo;
+    ++k;
+  }
+  char* d = ctx->d_stage[parity].as<char>();
+  CK(cudaMemcpyAsync(d, t, c.n_update * sizeof(BlockDesc), cudaMemcpyHostToDevice, s));
+  for (const UpdateStage::Segment& g : st.segs) {
+    const size_t lo = std::max(g.dev_off, c.lo), hi = std::min(g.dev_off + g.bytes, c.hi);
+    if (lo >= hi) continue;
+    const char* src = (g.host ? g.host : st.arena.as<char>() + g.arena_off) + (lo - g.dev_off);
+    CK(cudaMemcpyAsync(d + tb + (lo - c.lo), src, hi - lo, cudaMemcpyHostToDevice, s));
+    ctx->stats.bytes_uploaded += hi - lo;
+  }
+  ctx->stats.bytes_uploaded += c.n_update * sizeof(BlockDesc);
+  *tb_out = tb;
+  return NBVGPU_OK;
+}
+
+int launch_apply(nbvgpu_ctx* ctx, const BlockDesc* d_table, const char* d_payload, size_t n) {
+  if (n == 0) return NBVGPU_OK;
+  k_apply_blocks<<<(unsigned)n, kApplyThreads, 0, ctx->stream>>>(apply_layers(ctx), d_table, d_payload, (int)n);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  ctx->stats.blocks_uploaded += n;
+  return NBVGPU_OK;
+}
+
+int ensure_copy_stream(nbvgpu_ctx* ctx) {
+  if (ctx->copy_stream) return NBVGPU_OK;
+  CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CK(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ctx->ev_applied[i], cudaEventDisableTiming));
+  }
+  return NBVGPU_OK;
+}
+
+// Removals of a commit (device guard held): table of the kOpRemove descriptors -> k_apply_remove.
+int commit_removals(nbvgpu_ctx* ctx, const BlockDesc* d_table, size_t n) {
+  if (n == 0) return NBVGPU_OK;
+  k_apply_remove<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(apply_layers(ctx), d_table, (int)n);
+  CK(cudaGetLastError());
+  ctx->stats.kernel_launches++;
+  for (size_t i = 0; i < ctx->layers.size(); ++i)
+    if (ctx->layers[i]) ctx->layers[i]->tombstones += n;  // upper bound; only steers when the table is rebuilt
+  return NBVGPU_OK;
+}
+
+// Single-GPU commit of ctx->stage.
+int commit_single(nbvgpu_ctx* ctx) {
+  UpdateStage& st = ctx->stage;
+  if (st.empty()) return NBVGPU_OK;
+  // removals first
+  std::vector<BlockDesc> rm;
+  std::vector<size_t> incoming(ctx->layers.size(), 0);
+  for (const BlockDesc& d : st.descs) {
+    if (d.op == kOpRemove) rm.push_back(d);
+    if (d.op == kOpUpdate) incoming[d.layer]++;
+  }
+  if (!rm.empty()) {
+    CK(ctx->h_table[0].reserve(rm.size() * sizeof(BlockDesc), false));
+    CK(ctx->d_utab.reserve(rm.size() * sizeof(BlockDesc)));
+    memcpy(ctx->h_table[0].p, rm.data(), rm.size() * sizeof(BlockDesc));
+    CK(cudaMemcpyAsync(ctx->d_utab.p, ctx->h_table[0].p, rm.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, ctx->stream));
+    const int rc = commit_removals(ctx, ctx->d_utab.as<BlockDesc>(), rm.size());
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));  // h_table[0] is reused by the first chunk
+    ctx->stats.bytes_uploaded += rm.size() * sizeof(BlockDesc);
+  }
+  for (size_t i = 0; i < ctx->layers.size(); ++i)
+    if (ctx->layers[i] && incoming[i]) {
+      const int rc = rehash_if_needed(ctx, ctx->layers[i], incoming[i]);
+      if (rc) return rc;
+    }
+  ChunkPlan c, nxt;
+  bool have = next_chunk(ctx, st, 0, &c);
+  size_t k = 0;
+  while (have) {
+    const bool more = next_chunk(ctx, st, c.end, &nxt);
+    const int parity = (int)(k & 1);
+    size_t tb = 0;
+    if (k == 0 && !more) {  // the common case: everything fits one chunk, everything on the context's stream
+      const int rc = stage_chunk_h2d(ctx, st, c, 0, ctx->stream, &tb);
+      if (rc) return rc;
+    } else {
+      if (ensure_copy_stream(ctx)) return NBVGPU_ERR_CUDA;
+      if (k >= 2) {
+        CK(cudaEventSynchronize(ctx->ev_h2d[parity]));                      // the pinned table of chunk k-2 has been read
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_applied[parity], 0));  // the device buffer of chunk k-2 has been applied
+      } else if (k == 0) {
+        CK(cudaEventRecord(ctx->ev_applied[0], ctx->stream));               // order the copy stream after what is already enqueued
+        CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_applied[0], 0));
+      }
+      const int rc = stage_chunk_h2d(ctx, st, c, parity, ctx->copy_stream, &tb);
+      if (rc) return rc;
+      CK(cudaEventRecord(ctx->ev_h2d[parity], ctx->copy_stream));
+      CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[parity], 0));
+    }
+    const char* d = ctx->d_stage[parity].as<char>();
+    const int rc = launch_apply(ctx, reinterpret_cast<const BlockDesc*>(d), d + tb, c.n_update);
+    if (rc) return rc;
+    if (ctx->copy_stream && (k > 0 || more)) CK(cudaEventRecord(ctx->ev_applied[parity], ctx->stream));
+    c = nxt;
+    have = more;
+    ++k;
+  }
+  const int rc = sync_layer_states(ctx);  // also fences the staging memory (arena, caller's pinned buffers) for reuse
+  st.clear();
+  return rc;
+}
+
 int check_position_range(const nbvgpu_ctx* ctx, const LayerHost* L, size_t n, const double* pos) {
   const double vs_inv = 1.0 / (double)L->voxel_size;
   const double reach = std::ceil(ctx->tab.reach_m * vs_inv) + 4.0;
@@ -313,6 +515,9 @@ int check_position_range(const nbvgpu_ctx* ctx, const LayerHost* L, size_t n, co
 // memory (no copy operations in the stream) and, on the dense sweep, the window scan fused into the sweep's last CTA.
 constexpr size_t kFusedMaxCandidates = 64;
 constexpr size_t kSmallBatch = 64;
+// Edge checks up to this size run one warp per segment: the walk is a chain of dependent L2 round trips (block probe, then
+// distance) per voxel, which the warp issues 32 at a time; beyond it one thread per segment fills the machine anyway.
+constexpr size_t kWarpSegmentsMax = 32768;
 
 template <int V, int LV, int MODE, bool FUSE = false, int THREADS = kGainThreads>
 cudaError_t launch_gain_as(const GainArgs& a, size_t smem, unsigned grid, cudaStream_t s) {
@@ -704,7 +909,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
 int enqueue_segments(nbvgpu_ctx* ctx, LayerHost* L, double radius, size_t n, const double* d_seg, uint8_t* d_free,
                      const double* seg1 = nullptr) {
   if (n == 0) return NBVGPU_OK;
-  if (n <= kSmallBatch && !ctx->no_small) {  // one warp per segment: the voxels of a segment are looked up 32 at a time
+  if (n <= kWarpSegmentsMax && !ctx->no_small) {  // one warp per segment: the voxels of a segment are looked up 32 at a time
     SegmentByValue one = {};
     if (seg1 && n == 1) {
       for (int k = 0; k < 6; ++k) one.v[k] = seg1[k];
@@ -726,7 +931,7 @@ int enqueue_segments(nbvgpu_ctx* ctx, LayerHost* L, double radius, size_t n, con
 
 int best_device_nolock(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_pos, const double* d_parent_yaw,
                        const double* d_distance, const uint8_t* d_edge_free, double v_max, double dyaw_max, double zero_gain,
-                       nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg) {
+                       nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg, const BestPost post = BestPost{nullptr, 0, 0u}) {
   if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
@@ -739,42 +944,31 @@ int best_device_nolock(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_pos
     CK(ctx->d_yaw.reserve(n * 4 + 4));
     d_yaw_deg = ctx->d_yaw.as<int32_t>();
   }
-  const int rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr);
+  const int rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr, d_edge_free);  // rrt.cpp:210-216: no gain behind a colliding edge
   if (rc) return rc;
   static_assert(sizeof(BestRecord) == sizeof(nbvgpu_best), "record layout");
   k_score_best<<<1, 1024, 0, ctx->stream>>>(d_gain, d_yaw_deg, d_parent_yaw, d_distance, d_edge_free, (int)n, v_max, dyaw_max,
-                                            zero_gain, reinterpret_cast<BestRecord*>(d_best));
+                                            zero_gain, reinterpret_cast<BestRecord*>(d_best), nullptr, post);
   CK(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return NBVGPU_OK;
 }
 
-// Edge check + gain + scoring of n resident candidates (the body of RrtTree::iterate after the sampler, rrt.cpp:205-246).
-// The edge check does not depend on the ray sweep, so it runs on a side stream forked from and joined back into the
-// context's stream: its kernel and launch gap disappear behind the sweep.
+// Edge check + gain + scoring of n resident candidates (the body of RrtTree::iterate after the sampler, rrt.cpp:205-246), in
+// the reference's order: checkMotion first, and the gain only where the edge is free (rrt.cpp:210-216 returns before
+// optimized_gain when the edge collides) -- the verdicts are the sweep's `valid` mask, so a colliding candidate costs one
+// CTA-exit per yaw chunk instead of a ray sweep.  In a planner's unfiltered batches most samples collide (two thirds in the
+// config-5 replay); on the pre-filtered bench batches the edge check in front costs a few microseconds per step.
 int evaluate_device_nolock(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double radius, size_t n, const double* d_pos,
                            const double* d_seg, const double* d_parent_yaw, const double* d_distance, double v_max,
                            double dyaw_max, double zero_gain, uint8_t* d_edge_free, nbvgpu_best* d_best, double* d_gain,
-                           int32_t* d_yaw_deg) {
+                           int32_t* d_yaw_deg, const BestPost post = BestPost{nullptr, 0, 0u}) {
   LayerHost* E = get_layer(ctx, esdf_layer, NBVGPU_LAYER_ESDF);
   if (!E) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
-  DeviceGuard guard(ctx->device);
-  if (!ctx->side_stream) {
-    CK(cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-    CK(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
-  }
-  cudaStream_t main_stream = ctx->stream;
-  CK(cudaEventRecord(ctx->ev_fork, main_stream));
-  CK(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_fork, 0));
-  ctx->stream = ctx->side_stream;
-  const int rs = enqueue_segments(ctx, E, radius, n, d_seg, d_edge_free);
-  ctx->stream = main_stream;
-  if (rs) return rs;
-  CK(cudaEventRecord(ctx->ev_join, ctx->side_stream));
   if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
   LayerHost* L = get_layer(ctx, tsdf_layer, NBVGPU_LAYER_TSDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
+  DeviceGuard guard(ctx->device);
   if (!d_gain) {
     CK(ctx->d_gain.reserve(n * 8 + 8));
     d_gain = ctx->d_gain.as<double>();
@@ -783,14 +977,373 @@ int evaluate_device_nolock(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, doub
     CK(ctx->d_yaw.reserve(n * 4 + 4));
     d_yaw_deg = ctx->d_yaw.as<int32_t>();
   }
-  const int rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr);
-  CK(cudaStreamWaitEvent(main_stream, ctx->ev_join, 0));  // join also when the sweep could not be enqueued
+  unsigned* const ticket = ctx->want_ticket;  // a single-item call's ticket is published by the last kernel only
+  ctx->want_ticket = nullptr;
+  int rc = enqueue_segments(ctx, E, radius, n, d_seg, d_edge_free);
+  ctx->want_ticket = ticket;
   if (rc) return rc;
-  k_score_best<<<1, 1024, 0, main_stream>>>(d_gain, d_yaw_deg, d_parent_yaw, d_distance, d_edge_free, (int)n, v_max, dyaw_max,
-                                            zero_gain, reinterpret_cast<BestRecord*>(d_best));
+  rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr, d_edge_free);
+  if (rc) return rc;
+  k_score_best<<<1, 1024, 0, ctx->stream>>>(d_gain, d_yaw_deg, d_parent_yaw, d_distance, d_edge_free, (int)n, v_max, dyaw_max,
+                                            zero_gain, reinterpret_cast<BestRecord*>(d_best), nullptr, post);
   CK(cudaGetLastError());
   ctx->stats.kernel_launches++;
   return NBVGPU_OK;
+}
+
+// ---- host-buffer evaluation of one (shard of a) batch: enqueue now, collect later ---------------------------------------
+// Layout of the pinned staging area and of the device buffers:
+//   in : [pos n*24 | seg n*48 (when there is an edge check) | parent n*8 | dist n*8 | free n (when verdicts come from the caller)]
+//   out: [best 64 | gain n*8 | yaw n*4 (padded to 8) | free n]
+struct EvalLayout {
+  size_t n = 0, o_seg = 0, o_par = 0, o_dist = 0, o_free = 0, in_bytes = 0;
+  size_t r_gain = 64, r_yaw = 0, r_free = 0, out_bytes = 0;
+  bool with_seg = false, with_free = false;
+  EvalLayout(size_t n_, bool seg, bool free_in) : n(n_), with_seg(seg), with_free(free_in) {
+    o_seg = n * 24;
+    o_par = o_seg + (seg ? n * 48 : 0);
+    o_dist = o_par + n * 8;
+    o_free = o_dist + n * 8;
+    in_bytes = o_free + (free_in ? ((n + 7) & ~(size_t)7) : 0);
+    r_yaw = r_gain + n * 8;
+    r_free = r_yaw + ((n * 4 + 7) & ~(size_t)7);
+    out_bytes = r_free + ((n + 7) & ~(size_t)7);
+  }
+};
+
+// seg != null: edge check (on esdf_layer) + gain + scoring; seg == null: gain + scoring, masked by edge_free_in when given.
+// `outputs`: the per-candidate results are copied back (collected by evaluate_host_collect after the stream has been
+// synchronised); without them only the 32-byte best record travels -- into host memory when `post` names a slot.
+int evaluate_host_enqueue(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double radius, size_t n, const double* pos, const double* seg,
+                          const double* parent_yaw, const double* distance, const uint8_t* edge_free_in, double v_max, double dyaw_max,
+                          double zero_gain, bool outputs, const BestPost post) {
+  const EvalLayout lay(n, seg != nullptr, seg == nullptr && edge_free_in != nullptr);
+  DeviceGuard guard(ctx->device);
+  CK(ctx->h_io.reserve(lay.in_bytes + lay.out_bytes + 64, false));
+  CK(ctx->d_pos.reserve(lay.in_bytes + 8));
+  CK(ctx->d_aux.reserve(lay.out_bytes + 8));
+  char* h = ctx->h_io.as<char>();
+  char* d = ctx->d_pos.as<char>();
+  char* dr = ctx->d_aux.as<char>();
+  memcpy(h, pos, n * 24);
+  if (seg) memcpy(h + lay.o_seg, seg, n * 48);
+  memcpy(h + lay.o_par, parent_yaw, n * 8);
+  memcpy(h + lay.o_dist, distance, n * 8);
+  if (lay.with_free) memcpy(h + lay.o_free, edge_free_in, n);
+  if (lay.in_bytes) CK(cudaMemcpyAsync(d, h, lay.in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  int rc;
+  if (seg)
+    rc = evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, radius, n, reinterpret_cast<double*>(d), reinterpret_cast<double*>(d + lay.o_seg),
+                                reinterpret_cast<double*>(d + lay.o_par), reinterpret_cast<double*>(d + lay.o_dist), v_max, dyaw_max,
+                                zero_gain, reinterpret_cast<uint8_t*>(dr + lay.r_free), reinterpret_cast<nbvgpu_best*>(dr),
+                                reinterpret_cast<double*>(dr + lay.r_gain), reinterpret_cast<int32_t*>(dr + lay.r_yaw), post);
+  else
+    rc = best_device_nolock(ctx, tsdf_layer, n, reinterpret_cast<double*>(d), reinterpret_cast<double*>(d + lay.o_par),
+                            reinterpret_cast<double*>(d + lay.o_dist), lay.with_free ? reinterpret_cast<uint8_t*>(d + lay.o_free) : nullptr,
+                            v_max, dyaw_max, zero_gain, reinterpret_cast<nbvgpu_best*>(dr), reinterpret_cast<double*>(dr + lay.r_gain),
+                            reinterpret_cast<int32_t*>(dr + lay.r_yaw), post);
+  if (rc) return rc;
+  const size_t back = outputs ? (seg ? lay.out_bytes : lay.r_free) : (post.slot ? 0 : sizeof(nbvgpu_best));
+  if (back) CK(cudaMemcpyAsync(h + lay.in_bytes, dr, back, cudaMemcpyDeviceToHost, ctx->stream));
+  return NBVGPU_OK;
+}
+// After cudaStreamSynchronize: results of the last evaluate_host_enqueue of this context into the caller's arrays.
+void evaluate_host_collect(nbvgpu_ctx* ctx, size_t n, bool with_seg, bool with_free, uint8_t* edge_free, nbvgpu_best* best, double* gain,
+                           int32_t* yaw_deg) {
+  const EvalLayout lay(n, with_seg, with_free);
+  const char* hr = ctx->h_io.as<char>() + lay.in_bytes;
+  if (best) memcpy(best, hr, sizeof(nbvgpu_best));
+  if (gain) memcpy(gain, hr + lay.r_gain, n * 8);
+  if (yaw_deg) memcpy(yaw_deg, hr + lay.r_yaw, n * 4);
+  if (edge_free && with_seg) memcpy(edge_free, hr + lay.r_free, n);
+}
+
+// ---- multi-GPU contexts ---------------------------------------------------------------------------------------------
+// Contiguous blocks of ceil(n / world) candidates per rank (keeps tree-order locality).
+inline void shard_bounds(size_t n, int world, int rank, size_t* lo, size_t* hi) {
+  const size_t per = (n + (size_t)world - 1) / (size_t)world;
+  *lo = std::min(n, (size_t)rank * per);
+  *hi = std::min(n, *lo + per);
+}
+
+// The context whose staging area collects map updates: the context itself, or rank 0's member of a multi-GPU context
+// (null on the other ranks of a multi-process context: they receive the map through the broadcast).
+nbvgpu_ctx* stage_owner(nbvgpu_ctx* ctx) {
+  if (!ctx->group) return ctx;
+  return ctx->group->rank0 == 0 ? ctx->group->local[0] : nullptr;
+}
+
+int gfail(nbvgpu_ctx* ctx, int code, const std::string& msg) {
+  ctx->err = msg;
+  return code;
+}
+#define NCK(call)                                                                                              \
+  do {                                                                                                         \
+    ncclResult_t r_ = (call);                                                                                  \
+    if (r_ != ncclSuccess) return gfail(ctx, NBVGPU_ERR_CUDA, std::string(#call) + ": " + nccl().GetErrorString(r_)); \
+  } while (0)
+
+// nbvgpu_commit of a multi-GPU context.  Collective: every rank calls it; rank 0 holds the staged operations.
+//   root:   plan the chunks, publish the plan (other processes read it from the shared block), per chunk copy
+//           {table | payload} to its GPU (from the second chunk on beside the previous chunk's broadcast);
+//   all:    per chunk one ncclBroadcast of the device buffer from rank 0, then k_apply_blocks on every GPU.
+int group_commit(nbvgpu_ctx* ctx) {
+  Group* G = ctx->group;
+  std::lock_guard<std::mutex> glk(G->mu);
+  if (!nccl().ok) return gfail(ctx, NBVGPU_ERR_STATE, "NCCL unavailable: " + nccl().error);
+  nbvgpu_ctx* root = G->rank0 == 0 ? G->local[0] : nullptr;
+  SharedBlock* S = G->shared.host;
+  const unsigned long long seq = ++G->commit_seq;
+  std::vector<ChunkPlan> plans;
+  std::vector<BlockDesc> rm;
+  unsigned n_chunks = 0;
+  if (root) {
+    UpdateStage& st = root->stage;
+    unsigned incoming[kMaxLayers] = {0};
+    for (const BlockDesc& d : st.descs) {
+      if (d.op == kOpRemove) rm.push_back(d);
+      if (d.op == kOpUpdate) incoming[d.layer]++;
+    }
+    ChunkPlan c;
+    for (size_t from = 0; next_chunk(root, st, from, &c); from = c.end) plans.push_back(c);
+    if (plans.size() + 1 > (size_t)kMaxChunks) return gfail(ctx, NBVGPU_ERR_CAPACITY, "commit too large: commit more often or raise NBVGPU_CHUNK_MB");
+    // the plan may only be overwritten once every rank has read the previous one
+    if (G->multi_process && seq > 1) {
+      const bool ok = spin_until([&] {
+        for (int r = 0; r < G->world; ++r)
+          if (S->commit_ack[r].load(std::memory_order_acquire) < seq - 1) return false;
+        return true;
+      }, 120.0);
+      if (!ok) return gfail(ctx, NBVGPU_ERR_STATE, "a rank never joined the previous nbvgpu_commit");
+    }
+    unsigned k = 0;
+    if (!rm.empty()) {
+      ChunkInfo& ci = S->chunk[k++];
+      ci.table_bytes = (unsigned)align_up(rm.size() * sizeof(BlockDesc), 256);
+      ci.bytes = ci.table_bytes;
+      ci.n_update = 0;
+      ci.n_remove = (unsigned)rm.size();
+    }
+    for (const ChunkPlan& p : plans) {
+      ChunkInfo& ci = S->chunk[k++];
+      ci.table_bytes = (unsigned)align_up(p.n_update * sizeof(BlockDesc), 256);
+      ci.bytes = (unsigned long long)ci.table_bytes + (p.hi - p.lo);
+      ci.n_update = (unsigned)p.n_update;
+      ci.n_remove = 0;
+    }
+    S->n_chunks = n_chunks = k;
+    memcpy(S->incoming, incoming, sizeof incoming);
+    S->commit_seq.store(seq, std::memory_order_release);
+  } else {
+    const bool ok = spin_until([&] { return S->commit_seq.load(std::memory_order_acquire) >= seq; }, 600.0);
+    if (!ok) return gfail(ctx, NBVGPU_ERR_STATE, "rank 0 never called nbvgpu_commit");
+    n_chunks = S->n_chunks;
+  }
+  // the plan is copied out before the acknowledgement: rank 0 may overwrite the shared copy for the next commit afterwards
+  std::vector<ChunkInfo> info(S->chunk, S->chunk + n_chunks);
+  unsigned incoming[kMaxLayers];
+  memcpy(incoming, S->incoming, sizeof incoming);
+  for (size_t i = 0; i < G->local.size(); ++i) S->commit_ack[G->rank0 + (int)i].store(seq, std::memory_order_release);
+
+  int rc_all = NBVGPU_OK;
+  size_t plan_i = 0;
+  for (unsigned k = 0; k < n_chunks; ++k) {
+    const ChunkInfo ci = info[k];
+    const int parity = (int)(k & 1);
+    for (nbvgpu_ctx* m : G->local) {
+      std::lock_guard<std::mutex> lk(m->mu);
+      DeviceGuard guard(m->device);
+      if (m->d_stage[parity].reserve(ci.bytes) != cudaSuccess) return gfail(ctx, NBVGPU_ERR_CUDA, "device staging allocation failed");
+      if (k == 0)
+        for (size_t l = 0; l < m->layers.size(); ++l)
+          if (m->layers[l] && incoming[l]) {
+            const int rc = rehash_if_needed(m, m->layers[l], incoming[l]);
+            if (rc) return gfail(ctx, rc, m->err);
+          }
+    }
+    if (root) {
+      std::lock_guard<std::mutex> lk(root->mu);
+      DeviceGuard guard(root->device);
+      nbvgpu_ctx* ctx = root;  // CK reports into the root member
+      if (ci.n_remove) {
+        CK(root->h_table[parity].reserve(ci.table_bytes, false));
+        memcpy(root->h_table[parity].p, rm.data(), rm.size() * sizeof(BlockDesc));
+        CK(cudaMemcpyAsync(root->d_stage[parity].p, root->h_table[parity].p, rm.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, root->stream));
+        CK(cudaStreamSynchronize(root->stream));  // the pinned table is reused by the next chunk of the same parity
+      } else {
+        const ChunkPlan& p = plans[plan_i++];
+        size_t tb = 0;
+        if (n_chunks == 1 || (n_chunks == 2 && k == 1 && info[0].n_remove)) {
+          const int rc = stage_chunk_h2d(root, root->stage, p, parity, root->stream, &tb);
+          if (rc) return rc;
+        } else {
+          if (ensure_copy_stream(root)) return NBVGPU_ERR_CUDA;
+          if (k >= 2) {
+            CK(cudaEventSynchronize(root->ev_h2d[parity]));
+            CK(cudaStreamWaitEvent(root->copy_stream, root->ev_applied[parity], 0));
+          } else {
+            CK(cudaEventRecord(root->ev_applied[parity], root->stream));
+            CK(cudaStreamWaitEvent(root->copy_stream, root->ev_applied[parity], 0));
+          }
+          const int rc = stage_chunk_h2d(root, root->stage, p, parity, root->copy_stream, &tb);
+          if (rc) return rc;
+          CK(cudaEventRecord(root->ev_h2d[parity], root->copy_stream));
+          CK(cudaStreamWaitEvent(root->stream, root->ev_h2d[parity], 0));
+        }
+      }
+    }
+    // one broadcast of {table | payload} from rank 0 (NVLink); a single group call covers the GPUs of this process
+    if (G->world > 1) {
+      NCK(nccl().GroupStart());
+      for (size_t i = 0; i < G->local.size(); ++i) {
+        nbvgpu_ctx* m = G->local[i];
+        cudaSetDevice(m->device);
+        ncclResult_t r = nccl().Broadcast(m->d_stage[parity].p, m->d_stage[parity].p, ci.bytes, ncclUint8, 0, G->comms[i], m->stream);
+        if (r != ncclSuccess) {
+          nccl().GroupEnd();
+          return gfail(ctx, NBVGPU_ERR_CUDA, std::string("ncclBroadcast: ") + nccl().GetErrorString(r));
+        }
+      }
+      NCK(nccl().GroupEnd());
+    }
+    for (nbvgpu_ctx* m : G->local) {
+      std::lock_guard<std::mutex> lk(m->mu);
+      DeviceGuard guard(m->device);
+      const char* d = m->d_stage[parity].as<char>();
+      const int rc = ci.n_remove ? commit_removals(m, reinterpret_cast<const BlockDesc*>(d), ci.n_remove)
+                                 : launch_apply(m, reinterpret_cast<const BlockDesc*>(d), d + ci.table_bytes, ci.n_update);
+      if (rc) return gfail(ctx, rc, m->err);
+      if (m == root && root->copy_stream) cudaEventRecord(root->ev_applied[parity], root->stream);
+    }
+  }
+  for (nbvgpu_ctx* m : G->local) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    DeviceGuard guard(m->device);
+    const int rc = sync_layer_states(m);
+    if (rc && rc_all == NBVGPU_OK) rc_all = gfail(ctx, rc, m->err);
+  }
+  if (root) root->stage.clear();
+  return rc_all;
+}
+
+// Wait for the records of evaluation `seq` from every rank and pick the winner: highest score, lowest global index on
+// ties -- the reference's first strict maximum in candidate order (rrt.cpp:243-246).
+int group_collect_best(nbvgpu_ctx* ctx, unsigned seq, double zero_gain, nbvgpu_best* best) {
+  Group* G = ctx->group;
+  const BestSlot* slots = G->shared.host->best[seq & 1u];
+  int next = 0;  // ranks [0, next) have reported
+  const bool ok = spin_until([&] {
+    while (next < G->world && *reinterpret_cast<const volatile unsigned*>(&slots[next].ticket) == seq) ++next;
+    return next == G->world;
+  }, 120.0);
+  if (!ok) {
+    for (nbvgpu_ctx* m : G->local) {  // a failed kernel of our own explains it; otherwise a peer is missing
+      DeviceGuard guard(m->device);
+      const cudaError_t e = cudaStreamSynchronize(m->stream);
+      if (e != cudaSuccess) return gfail(ctx, NBVGPU_ERR_CUDA, std::string("evaluation failed: ") + cudaGetErrorString(e));
+    }
+    return gfail(ctx, NBVGPU_ERR_STATE, "rank " + std::to_string(next) + " never reported its shard (every rank must make the same calls)");
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  best->index = -1; best->score = zero_gain; best->gain = 0.0; best->yaw = 0.0;
+  for (int r = 0; r < G->world; ++r) {
+    const volatile BestSlot& s = slots[r];
+    if (s.index < 0) continue;
+    if (best->index < 0 || s.score > best->score || (s.score == best->score && s.index < best->index)) {
+      best->index = s.index; best->score = s.score; best->gain = s.gain; best->yaw = s.yaw;
+    }
+  }
+  return NBVGPU_OK;
+}
+
+// Host side of a rank whose shard is empty: the slot is written directly.
+void group_post_empty(Group* G, int rank, unsigned seq) {
+  BestSlot& s = G->shared.host->best[seq & 1u][rank];
+  s.index = -1; s.score = 0.0; s.gain = 0.0; s.yaw = 0.0;
+  std::atomic_thread_fence(std::memory_order_release);
+  *reinterpret_cast<volatile unsigned*>(&s.ticket) = seq;
+}
+
+// nbvgpu_evaluate_candidates / nbvgpu_gain_eval_best of a multi-GPU context: every rank takes its contiguous shard of the
+// n candidates (all GPUs of this process are launched before any is waited for), its scoring kernel posts the shard's best
+// record into the shared block, and the winner is picked from the world's records.  Per-candidate outputs are filled for
+// the shards evaluated in this process.
+int group_evaluate(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double radius, size_t n, const double* pos, const double* seg,
+                   const double* parent_yaw, const double* distance, const uint8_t* edge_free_in, double v_max, double dyaw_max,
+                   double zero_gain, uint8_t* edge_free, nbvgpu_best* best, double* gain, int32_t* yaw_deg) {
+  Group* G = ctx->group;
+  std::lock_guard<std::mutex> glk(G->mu);
+  nbvgpu_ctx* m0 = G->local[0];
+  {
+    std::lock_guard<std::mutex> lk(m0->mu);
+    LayerHost* L = get_layer(m0, tsdf_layer, NBVGPU_LAYER_TSDF);
+    if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
+    if (seg && !get_layer(m0, esdf_layer, NBVGPU_LAYER_ESDF)) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
+    if (!m0->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
+    if (check_position_range(m0, L, n, pos)) return fail(ctx, NBVGPU_ERR_RANGE, "position non-finite or out of range");
+    if (seg) {
+      const double vs_inv = 1.0 / (double)m0->layers[esdf_layer]->voxel_size;
+      for (size_t i = 0; i < 6 * n; ++i)
+        if (!(std::fabs(seg[i] * vs_inv) < 4194000.0)) return fail(ctx, NBVGPU_ERR_RANGE, "segment non-finite or out of range");
+    }
+  }
+  const unsigned seq = (unsigned)(++G->eval_seq);
+  const bool outputs = gain || yaw_deg || (edge_free && seg);
+  for (size_t i = 0; i < G->local.size(); ++i) {
+    nbvgpu_ctx* m = G->local[i];
+    const int rank = G->rank0 + (int)i;
+    size_t lo, hi;
+    shard_bounds(n, G->world, rank, &lo, &hi);
+    if (hi == lo) {
+      group_post_empty(G, rank, seq);
+      continue;
+    }
+    std::lock_guard<std::mutex> lk(m->mu);
+    const BestPost post{&G->d_shared[i]->best[seq & 1u][rank], (long long)lo, seq};
+    const int rc = evaluate_host_enqueue(m, tsdf_layer, esdf_layer, radius, hi - lo, pos + 3 * lo, seg ? seg + 6 * lo : nullptr,
+                                         parent_yaw + lo, distance + lo, edge_free_in ? edge_free_in + lo : nullptr, v_max, dyaw_max,
+                                         zero_gain, outputs, post);
+    if (rc) return gfail(ctx, rc, m->err);
+  }
+  if (outputs)
+    for (size_t i = 0; i < G->local.size(); ++i) {
+      nbvgpu_ctx* m = G->local[i];
+      size_t lo, hi;
+      shard_bounds(n, G->world, G->rank0 + (int)i, &lo, &hi);
+      if (hi == lo) continue;
+      std::lock_guard<std::mutex> lk(m->mu);
+      DeviceGuard guard(m->device);
+      if (cudaStreamSynchronize(m->stream) != cudaSuccess) return gfail(ctx, NBVGPU_ERR_CUDA, "evaluation failed on a member GPU");
+      evaluate_host_collect(m, hi - lo, seg != nullptr, seg == nullptr && edge_free_in != nullptr, edge_free ? edge_free + lo : nullptr, nullptr,
+                            gain ? gain + lo : nullptr, yaw_deg ? yaw_deg + lo : nullptr);
+    }
+  return group_collect_best(ctx, seq, zero_gain, best);
+}
+
+// Run f(member, lo, hi) for every local member's shard of n items on its own thread (entry points without a best record).
+template <class F>
+int group_fan_out(nbvgpu_ctx* ctx, size_t n, F f) {
+  Group* G = ctx->group;
+  std::vector<int> rcs(G->local.size(), NBVGPU_OK);
+  std::vector<std::thread> th;
+  for (size_t i = 0; i < G->local.size(); ++i) {
+    size_t lo, hi;
+    shard_bounds(n, G->world, G->rank0 + (int)i, &lo, &hi);
+    if (hi == lo) continue;
+    nbvgpu_ctx* m = G->local[i];
+    th.emplace_back([&, i, m, lo, hi] { rcs[i] = f(m, lo, hi); });
+  }
+  for (std::thread& t : th) t.join();
+  for (size_t i = 0; i < rcs.size(); ++i)
+    if (rcs[i]) return gfail(ctx, rcs[i], G->local[i]->err);
+  return NBVGPU_OK;
+}
+
+void destroy_group(Group* G) {
+  for (size_t i = 0; i < G->comms.size(); ++i)
+    if (G->comms[i] && nccl().ok) nccl().CommDestroy(G->comms[i]);
+  shared_release(&G->shared);
+  delete G;
 }
 
 }  // namespace
@@ -802,7 +1355,44 @@ extern "C" {
 
 const char* nbvgpu_version(void) { return "nbvgpu 0.1 (sm_100a)"; }
 
-int nbvgpu_create(int device, nbvgpu_ctx** out) {
+static void destroy_member(nbvgpu_ctx* ctx) {
+  if (!ctx) return;
+  {
+    DeviceGuard guard(ctx->device);
+    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
+    for (LayerHost* L : ctx->layers) free_layer(L);
+    cudaFree(ctx->d_A);
+    cudaFree(ctx->d_B);
+    cudaFree(ctx->d_cs);
+    cudaFree(ctx->d_totals);
+    cudaFree(ctx->d_lstate);
+    ctx->stage.arena.release();
+    for (int i = 0; i < 2; ++i) {
+      ctx->h_table[i].release();
+      ctx->d_stage[i].release();
+      if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+      if (ctx->ev_applied[i]) cudaEventDestroy(ctx->ev_applied[i]);
+    }
+    ctx->d_utab.release();
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    ctx->h_io.release();
+    if (ctx->h_ticket) cudaFreeHost(ctx->h_ticket);
+    for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
+    for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
+                      &ctx->d_free, &ctx->d_aux, &ctx->d_best, &ctx->d_zrange, &ctx->d_arrive, &ctx->d_fr_cells, &ctx->d_fr_cur, &ctx->d_fr_next,
+                      &ctx->d_fr_slots, &ctx->d_fr_io})
+      b->release();
+    for (auto& pr : ctx->prof_events) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  }
+  delete ctx;
+}
+
+
+static int create_member_impl(int device, nbvgpu_ctx** out) {
   if (!out) return NBVGPU_ERR_INVALID;
   *out = nullptr;
   int count = 0;
@@ -832,48 +1422,146 @@ int nbvgpu_create(int device, nbvgpu_ctx** out) {
   ok = ok && cudaMalloc(&ctx->d_cs, sizeof(float) * 360 * 2) == cudaSuccess;
   ok = ok && cudaMalloc(&ctx->d_totals, sizeof(unsigned long long) * 8) == cudaSuccess;
   ok = ok && cudaMemset(ctx->d_totals, 0, sizeof(unsigned long long) * 8) == cudaSuccess;
+  ok = ok && cudaMalloc(&ctx->d_lstate, kMaxLayers * 16) == cudaSuccess;
+  ok = ok && cudaMemset(ctx->d_lstate, 0, kMaxLayers * 16) == cudaSuccess;
+  if (const char* e = std::getenv("NBVGPU_CHUNK_MB")) ctx->chunk_bytes = (size_t)std::max(1, std::atoi(e)) << 20;
   if (!ok) {
-    nbvgpu_destroy(ctx);
+    destroy_member(ctx);
     return NBVGPU_ERR_CUDA;
   }
   *out = ctx;
   return NBVGPU_OK;
 }
 
+
+int nbvgpu_create(int device, nbvgpu_ctx** out) { return create_member_impl(device, out); }
+
 void nbvgpu_destroy(nbvgpu_ctx* ctx) {
   if (!ctx) return;
-  {
-    DeviceGuard guard(ctx->device);
-    if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    for (LayerHost* L : ctx->layers) free_layer(L);
-    cudaFree(ctx->d_A);
-    cudaFree(ctx->d_B);
-    cudaFree(ctx->d_cs);
-    cudaFree(ctx->d_totals);
-    ctx->h_io.release();
-    if (ctx->h_ticket) cudaFreeHost(ctx->h_ticket);
-    if (ctx->side_stream) {
-      cudaStreamSynchronize(ctx->side_stream);
-      cudaStreamDestroy(ctx->side_stream);
-    }
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-    for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
-    for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
-                      &ctx->d_free, &ctx->d_aux, &ctx->d_best, &ctx->d_zrange, &ctx->d_arrive, &ctx->d_fr_cells, &ctx->d_fr_cur, &ctx->d_fr_next,
-                      &ctx->d_fr_slots, &ctx->d_fr_io})
-      b->release();
-    for (auto& pr : ctx->prof_events) {
-      cudaEventDestroy(pr.first);
-      cudaEventDestroy(pr.second);
-    }
-    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+  Group* G = ctx->group;
+  if (!G) {
+    destroy_member(ctx);
+    return;
   }
-  delete ctx;
+  for (nbvgpu_ctx* m : G->local) {  // drain every GPU before the communicators go
+    DeviceGuard guard(m->device);
+    cudaStreamSynchronize(m->stream);
+  }
+  std::vector<nbvgpu_ctx*> members = G->local;
+  destroy_group(G);
+  for (nbvgpu_ctx* m : members) destroy_member(m);
+}
+
+// ---- multi-GPU contexts -------------------------------------------------------------------------------
+static int attach_shared_devices(nbvgpu_ctx* ctx, Group* G) {
+  G->d_shared.assign(G->local.size(), nullptr);
+  for (size_t i = 0; i < G->local.size(); ++i) {
+    DeviceGuard guard(G->local[i]->device);
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, G->shared.host, 0) != cudaSuccess) return fail(ctx, NBVGPU_ERR_CUDA, "cudaHostGetDevicePointer(shared block)");
+    G->d_shared[i] = reinterpret_cast<SharedBlock*>(d);
+  }
+  return NBVGPU_OK;
+}
+
+int nbvgpu_create_multi(int n_gpus, const int* device_ids, nbvgpu_ctx** out) {
+  if (!out || n_gpus < 1 || n_gpus > kMaxRanks) return NBVGPU_ERR_INVALID;
+  *out = nullptr;
+  Group* G = new Group();
+  G->world = n_gpus;
+  G->rank0 = 0;
+  std::vector<int> devs(n_gpus);
+  for (int i = 0; i < n_gpus; ++i) devs[i] = device_ids ? device_ids[i] : i;
+  auto bail = [&](int rc) {
+    std::vector<nbvgpu_ctx*> members = G->local;
+    destroy_group(G);
+    for (nbvgpu_ctx* m : members) destroy_member(m);
+    return rc;
+  };
+  for (int i = 0; i < n_gpus; ++i) {
+    for (int j = 0; j < i; ++j)
+      if (devs[j] == devs[i]) return bail(NBVGPU_ERR_INVALID);
+    nbvgpu_ctx* m = nullptr;
+    const int rc = create_member_impl(devs[i], &m);
+    if (rc) return bail(rc);
+    m->group = G;
+    m->member = i;
+    G->local.push_back(m);
+  }
+  nbvgpu_ctx* ctx = G->local[0];
+  if (shared_alloc_local(&G->shared, n_gpus) != cudaSuccess) return bail(NBVGPU_ERR_CUDA);
+  if (attach_shared_devices(ctx, G)) return bail(NBVGPU_ERR_CUDA);
+  if (n_gpus > 1) {
+    if (!nccl().ok) return bail(NBVGPU_ERR_STATE);
+    G->comms.assign(n_gpus, nullptr);
+    if (nccl().CommInitAll(G->comms.data(), n_gpus, devs.data()) != ncclSuccess) return bail(NBVGPU_ERR_CUDA);
+  }
+  *out = ctx;
+  return NBVGPU_OK;
+}
+
+int nbvgpu_group_unique_id(uint8_t* id_out, size_t len) {
+  if (!id_out || len < sizeof(ncclUniqueId)) return NBVGPU_ERR_INVALID;
+  if (!nccl().ok) return NBVGPU_ERR_STATE;
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) return NBVGPU_ERR_CUDA;
+  memset(id_out, 0, len);
+  memcpy(id_out, &id, sizeof id);
+  return NBVGPU_OK;
+}
+
+int nbvgpu_create_rank(int device, int rank, int world, const uint8_t* unique_id, size_t len, nbvgpu_ctx** out) {
+  if (!out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world || !unique_id || len < sizeof(ncclUniqueId)) return NBVGPU_ERR_INVALID;
+  *out = nullptr;
+  if (!nccl().ok) return NBVGPU_ERR_STATE;
+  nbvgpu_ctx* m = nullptr;
+  int rc = create_member_impl(device, &m);
+  if (rc) return rc;
+  Group* G = new Group();
+  G->world = world;
+  G->rank0 = rank;
+  G->multi_process = true;
+  G->local.push_back(m);
+  m->group = G;
+  auto bail = [&](int code) {
+    destroy_group(G);
+    destroy_member(m);
+    return code;
+  };
+  const std::string name = shared_name(unique_id, sizeof(ncclUniqueId));
+  std::string err;
+  if (rank == 0 && !shared_create(&G->shared, name, world, &err)) return bail(NBVGPU_ERR_STATE);
+  ncclUniqueId id;
+  memcpy(&id, unique_id, sizeof id);
+  G->comms.assign(1, nullptr);
+  {
+    DeviceGuard guard(device);
+    if (nccl().CommInitRank(&G->comms[0], world, id, rank) != ncclSuccess) return bail(NBVGPU_ERR_CUDA);  // synchronises the ranks
+    if (rank != 0 && !shared_open(&G->shared, name, &err)) return bail(NBVGPU_ERR_STATE);
+    if (shared_register(&G->shared) != cudaSuccess) return bail(NBVGPU_ERR_CUDA);
+  }
+  if (attach_shared_devices(m, G)) return bail(NBVGPU_ERR_CUDA);
+  if (rank == 0) {  // the name is only needed until everybody has mapped the segment
+    spin_until([&] { return G->shared.host->attached.load() >= (unsigned)world; }, 60.0);
+    shm_unlink(name.c_str());
+    G->shared.owner = false;
+  }
+  *out = m;
+  return NBVGPU_OK;
+}
+
+int nbvgpu_group_info(nbvgpu_ctx* ctx, int* rank, int* world, int* local_gpus) {
+  if (!ctx) return NBVGPU_ERR_INVALID;
+  if (rank) *rank = ctx->group ? ctx->group->rank0 : 0;
+  if (world) *world = ctx->group ? ctx->group->world : 1;
+  if (local_gpus) *local_gpus = ctx->group ? (int)ctx->group->local.size() : 1;
+  return NBVGPU_OK;
 }
 
 int nbvgpu_set_stream(nbvgpu_ctx* ctx, void* cuda_stream) {
   if (!ctx) return NBVGPU_ERR_INVALID;
+  if (ctx->group && ctx->group->local.size() > 1 && cuda_stream)
+    return fail(ctx, NBVGPU_ERR_STATE, "a context that spans several GPUs of one process keeps its own streams");
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard guard(ctx->device);
   CK(cudaStreamSynchronize(ctx->stream));
@@ -881,24 +1569,47 @@ int nbvgpu_set_stream(nbvgpu_ctx* ctx, void* cuda_stream) {
   return NBVGPU_OK;
 }
 
-int nbvgpu_synchronize(nbvgpu_ctx* ctx) {
-  if (!ctx) return NBVGPU_ERR_INVALID;
+static int synchronize_one(nbvgpu_ctx* ctx) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard guard(ctx->device);
   CK(cudaStreamSynchronize(ctx->stream));
+  return NBVGPU_OK;
+}
+int nbvgpu_synchronize(nbvgpu_ctx* ctx) {
+  if (!ctx) return NBVGPU_ERR_INVALID;
+  if (!ctx->group) return synchronize_one(ctx);
+  for (nbvgpu_ctx* m : ctx->group->local) {
+    const int rc = synchronize_one(m);
+    if (rc) return gfail(ctx, rc, m->err);
+  }
   return NBVGPU_OK;
 }
 
 const char* nbvgpu_last_error(nbvgpu_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 
 // ---- layers --------------------------------------------------------------------------------
+static int layer_create_one(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, size_t max_blocks, int* layer_out);
 int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, size_t max_blocks, int* layer_out) {
   if (!ctx || !layer_out) return NBVGPU_ERR_INVALID;
+  if (!ctx->group) return layer_create_one(ctx, kind, voxel_size, vps, max_blocks, layer_out);
+  int first = -1;
+  for (nbvgpu_ctx* m : ctx->group->local) {  // the same layer index on every GPU
+    int id = -1;
+    const int rc = layer_create_one(m, kind, voxel_size, vps, max_blocks, &id);
+    if (rc) return gfail(ctx, rc, m->err);
+    if (first < 0) first = id;
+    if (id != first) return fail(ctx, NBVGPU_ERR_STATE, "layer indices diverged between the GPUs of the context");
+  }
+  *layer_out = first;
+  return NBVGPU_OK;
+}
+static int layer_create_one(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, size_t max_blocks, int* layer_out) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (kind != NBVGPU_LAYER_TSDF && kind != NBVGPU_LAYER_ESDF) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer kind");
   if (!(voxel_size > 0.f) || !std::isfinite(voxel_size)) return fail(ctx, NBVGPU_ERR_INVALID, "bad voxel size");
   if (vps < 4 || vps > 32 || (vps & (vps - 1))) return fail(ctx, NBVGPU_ERR_INVALID, "voxels_per_side must be 4, 8, 16 or 32");
   if (max_blocks == 0 || max_blocks > (1u << 28)) return fail(ctx, NBVGPU_ERR_INVALID, "bad max_blocks");
+  if (ctx->layers.size() >= (size_t)kMaxLayers) return fail(ctx, NBVGPU_ERR_CAPACITY, "too many layers in one context");
   DeviceGuard guard(ctx->device);
   LayerHost* L = new LayerHost();
   L->kind = kind;
@@ -910,6 +1621,7 @@ int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, si
   L->log2cap = (uint32_t)ilog2(2 * (uint64_t)max_blocks);
   if (L->log2cap < 4) L->log2cap = 4;
   L->cap = 1u << L->log2cap;
+  L->d_state = ctx->d_lstate + 2 * ctx->layers.size();
   const size_t tile_bytes = (size_t)L->nvox * (kind == NBVGPU_LAYER_TSDF ? 8 : 4);
   bool ok = cudaMalloc(&L->d_table, (size_t)L->cap * sizeof(HashEntry)) == cudaSuccess;
   // one extra tile at index max_blocks stays zero: {distance 0, weight 0} / status "unknown", the
@@ -927,17 +1639,13 @@ int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, si
     ok = ok && cudaMemsetAsync(L->d_status, 0, sbytes * (max_blocks + 1), ctx->stream) == cudaSuccess;
   }
   ok = ok && cudaMalloc(&L->d_free_list, sizeof(int) * max_blocks) == cudaSuccess;
-  ok = ok && cudaMalloc(&L->d_free_top, sizeof(int) * 2) == cudaSuccess;
-  ok = ok && cudaMalloc(&L->d_nblocks, sizeof(unsigned long long)) == cudaSuccess;
-  ok = ok && cudaMemsetAsync(L->d_free_top, 0, sizeof(int) * 2, ctx->stream) == cudaSuccess;
   if (!ok) {
     cudaGetLastError();
     free_layer(L);
     return fail(ctx, NBVGPU_ERR_CUDA, "layer allocation failed");
   }
   const uint32_t nthreads = L->cap > (uint32_t)max_blocks ? L->cap : (uint32_t)max_blocks;
-  k_reset_table<<<(nthreads + 255) / 256, 256, 0, ctx->stream>>>(L->d_table, L->cap, L->d_free_list, (int)max_blocks,
-                                                                 L->d_free_top, L->d_nblocks);
+  k_reset_table<<<(nthreads + 255) / 256, 256, 0, ctx->stream>>>(L->d_table, L->cap, L->d_free_list, (int)max_blocks, L->d_state);
   ctx->stats.kernel_launches++;
   CK(cudaGetLastError());
   ctx->layers.push_back(L);
@@ -945,95 +1653,100 @@ int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, si
   return NBVGPU_OK;
 }
 
-int nbvgpu_layer_update(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* keys, const void* payload, int packing) {
-  if (!ctx || (n && (!keys || !payload))) return NBVGPU_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+// Stage n blocks; `pinned`: the payload stays in the caller's page-locked memory until the commit.
+static int stage_update(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* keys, const void* payload, int packing, bool pinned) {
   LayerHost* L = get_layer(ctx, layer, -1);
   if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
   if (packing != NBVGPU_PACK_PLANAR && packing != NBVGPU_PACK_VOXBLOX) return fail(ctx, NBVGPU_ERR_INVALID, "bad packing");
-  if (L->pending && L->pending_packing != packing)
-    return fail(ctx, NBVGPU_ERR_STATE, "mixed packings between commits (commit first)");
   for (size_t i = 0; i < 3 * n; ++i)
     if (keys[i] < -(1 << 20) || keys[i] >= (1 << 20)) return fail(ctx, NBVGPU_ERR_RANGE, "block index out of range");
+  if (n == 0) return NBVGPU_OK;
   DeviceGuard guard(ctx->device);
+  UpdateStage& st = ctx->stage;
   const size_t per = L->payload_bytes_per_block(packing);
-  L->pending_packing = packing;
-  CK(L->h_keys.reserve((L->pending + n) * 12, true));
-  CK(L->h_payload.reserve((L->pending + n) * per, true));
-  for (size_t i = 0; i < n; ++i) {
-    const KeyH k{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]};
-    size_t idx;
-    auto it = L->pending_index.find(k);
-    if (it != L->pending_index.end()) {
-      idx = it->second;  // last write wins
-    } else {
-      idx = L->pending++;
-      L->pending_index.emplace(k, idx);
-      memcpy(L->h_keys.as<int32_t>() + 3 * idx, keys + 3 * i, 12);
+  UpdateStage::Segment g;
+  g.bytes = n * per;
+  g.dev_off = align_up(st.dev_bytes, 256);
+  if (pinned) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, payload) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+      cudaGetLastError();
+      return fail(ctx, NBVGPU_ERR_INVALID, "nbvgpu_layer_update_pinned needs page-locked host memory (cudaHostAlloc / cudaHostRegister)");
     }
-    memcpy(L->h_payload.as<char>() + idx * per, reinterpret_cast<const char*>(payload) + i * per, per);
-    // an update after a staged removal of the same block supersedes the removal
-    for (size_t r = 0; r + 2 < L->pending_remove.size(); r += 3)
-      if (L->pending_remove[r] == k.x && L->pending_remove[r + 1] == k.y && L->pending_remove[r + 2] == k.z) {
-        L->pending_remove.erase(L->pending_remove.begin() + r, L->pending_remove.begin() + r + 3);
-        break;
-      }
+    g.host = reinterpret_cast<const char*>(payload);
+    g.arena_off = 0;
+  } else {
+    CK(st.arena.reserve(st.arena_used + g.bytes, true));
+    memcpy(st.arena.as<char>() + st.arena_used, payload, g.bytes);
+    g.host = nullptr;
+    g.arena_off = st.arena_used;
+    st.arena_used = align_up(st.arena_used + g.bytes, 256);
   }
+  st.segs.push_back(g);
+  st.dev_bytes = g.dev_off + g.bytes;
+  for (size_t i = 0; i < n; ++i) st.add(layer, keys + 3 * i, packing, kOpUpdate, g.dev_off + i * per);
   return NBVGPU_OK;
+}
+
+int nbvgpu_layer_update(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* keys, const void* payload, int packing) {
+  if (!ctx || (n && (!keys || !payload))) return NBVGPU_ERR_INVALID;
+  nbvgpu_ctx* r = stage_owner(ctx);
+  if (!r) return fail(ctx, NBVGPU_ERR_STATE, "map updates are staged on rank 0 of a multi-process context");
+  std::lock_guard<std::mutex> lk(r->mu);
+  return stage_update(r, layer, n, keys, payload, packing, false);
+}
+
+int nbvgpu_layer_update_pinned(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* keys, const void* payload, int packing) {
+  if (!ctx || (n && (!keys || !payload))) return NBVGPU_ERR_INVALID;
+  nbvgpu_ctx* r = stage_owner(ctx);
+  if (!r) return fail(ctx, NBVGPU_ERR_STATE, "map updates are staged on rank 0 of a multi-process context");
+  std::lock_guard<std::mutex> lk(r->mu);
+  return stage_update(r, layer, n, keys, payload, packing, true);
 }
 
 int nbvgpu_layer_update_device(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* d_keys, const void* d_payload, int packing) {
   if (!ctx || (n && (!d_keys || !d_payload))) return NBVGPU_ERR_INVALID;
+  if (ctx->group) return fail(ctx, NBVGPU_ERR_STATE, "device-resident updates address one GPU: use a single-GPU context");
   std::lock_guard<std::mutex> lk(ctx->mu);
   LayerHost* L = get_layer(ctx, layer, -1);
   if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
   if (packing != NBVGPU_PACK_PLANAR && packing != NBVGPU_PACK_VOXBLOX) return fail(ctx, NBVGPU_ERR_INVALID, "bad packing");
+  if (n == 0) return NBVGPU_OK;
+  if (n > (size_t)INT_MAX) return fail(ctx, NBVGPU_ERR_INVALID, "too many blocks in one call");
   DeviceGuard guard(ctx->device);
   int rc = rehash_if_needed(ctx, L, n);
   if (rc) return rc;
-  rc = apply_update_device(ctx, L, n, d_keys, d_payload, packing);
+  CK(ctx->d_utab.reserve(n * sizeof(BlockDesc)));
+  k_make_table<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(d_keys, (int)n, layer, packing,
+                                                                     (unsigned long long)L->payload_bytes_per_block(packing),
+                                                                     ctx->d_utab.as<BlockDesc>());
+  ctx->stats.kernel_launches++;
+  rc = launch_apply(ctx, ctx->d_utab.as<BlockDesc>(), reinterpret_cast<const char*>(d_payload), n);
   if (rc) return rc;
-  return sync_layer_state(ctx, L);
+  return sync_layer_states(ctx);
 }
 
 int nbvgpu_layer_remove(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* keys) {
   if (!ctx || (n && !keys)) return NBVGPU_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(ctx->mu);
-  LayerHost* L = get_layer(ctx, layer, -1);
-  if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
-  for (size_t i = 0; i < n; ++i) {
-    const KeyH k{keys[3 * i], keys[3 * i + 1], keys[3 * i + 2]};
-    auto it = L->pending_index.find(k);
-    if (it != L->pending_index.end()) {
-      // cancel the staged update: move the last staged block into its place
-      const size_t idx = it->second, last = L->pending - 1;
-      const size_t per = L->payload_bytes_per_block(L->pending_packing);
-      L->pending_index.erase(it);
-      if (idx != last) {
-        int32_t* hk = L->h_keys.as<int32_t>();
-        memcpy(hk + 3 * idx, hk + 3 * last, 12);
-        memcpy(L->h_payload.as<char>() + idx * per, L->h_payload.as<char>() + last * per, per);
-        L->pending_index[KeyH{hk[3 * idx], hk[3 * idx + 1], hk[3 * idx + 2]}] = idx;
-      }
-      L->pending--;
-    }
-    L->pending_remove.insert(L->pending_remove.end(), {k.x, k.y, k.z});
-  }
+  nbvgpu_ctx* r = stage_owner(ctx);
+  if (!r) return fail(ctx, NBVGPU_ERR_STATE, "map updates are staged on rank 0 of a multi-process context");
+  std::lock_guard<std::mutex> lk(r->mu);
+  LayerHost* L = get_layer(r, layer, -1);
+  if (!L) return fail(r, NBVGPU_ERR_INVALID, "bad layer");
+  for (size_t i = 0; i < 3 * n; ++i)
+    if (keys[i] < -(1 << 20) || keys[i] >= (1 << 20)) return fail(r, NBVGPU_ERR_RANGE, "block index out of range");
+  for (size_t i = 0; i < n; ++i) r->stage.add(layer, keys + 3 * i, 0, kOpRemove, 0);
   return NBVGPU_OK;
 }
 
-int nbvgpu_layer_clear(nbvgpu_ctx* ctx, int layer) {
-  if (!ctx) return NBVGPU_ERR_INVALID;
+static int layer_clear_one(nbvgpu_ctx* ctx, int layer) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   LayerHost* L = get_layer(ctx, layer, -1);
   if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
   DeviceGuard guard(ctx->device);
-  L->pending = 0;
-  L->pending_index.clear();
-  L->pending_remove.clear();
+  ctx->stage.drop_layer(layer);
   const uint32_t nthreads = L->cap > (uint32_t)L->max_blocks ? L->cap : (uint32_t)L->max_blocks;
-  k_reset_table<<<(nthreads + 255) / 256, 256, 0, ctx->stream>>>(L->d_table, L->cap, L->d_free_list, (int)L->max_blocks,
-                                                                 L->d_free_top, L->d_nblocks);
+  k_reset_table<<<(nthreads + 255) / 256, 256, 0, ctx->stream>>>(L->d_table, L->cap, L->d_free_list, (int)L->max_blocks, L->d_state);
   ctx->stats.kernel_launches++;
   CK(cudaGetLastError());
   L->n_blocks = 0;
@@ -1041,44 +1754,22 @@ int nbvgpu_layer_clear(nbvgpu_ctx* ctx, int layer) {
   return NBVGPU_OK;
 }
 
+int nbvgpu_layer_clear(nbvgpu_ctx* ctx, int layer) {
+  if (!ctx) return NBVGPU_ERR_INVALID;
+  if (!ctx->group) return layer_clear_one(ctx, layer);
+  for (nbvgpu_ctx* m : ctx->group->local) {
+    const int rc = layer_clear_one(m, layer);
+    if (rc) return rc;
+  }
+  return NBVGPU_OK;
+}
+
 int nbvgpu_commit(nbvgpu_ctx* ctx) {
   if (!ctx) return NBVGPU_ERR_INVALID;
+  if (ctx->group) return group_commit(ctx);
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard guard(ctx->device);
-  int rc_all = NBVGPU_OK;
-  for (LayerHost* L : ctx->layers) {
-    if (!L || (L->pending == 0 && L->pending_remove.empty())) continue;
-    const size_t nrem = L->pending_remove.size() / 3;
-    if (nrem) {
-      CK(L->d_keys.reserve(nrem * 12));
-      CK(cudaMemcpyAsync(L->d_keys.p, L->pending_remove.data(), nrem * 12, cudaMemcpyHostToDevice, ctx->stream));
-      k_remove_keys<<<(unsigned)((nrem + 127) / 128), 128, 0, ctx->stream>>>(L->d_table, L->cap - 1, 32 - L->log2cap,
-                                                                             L->d_keys.as<int32_t>(), (int)nrem, L->d_free_list,
-                                                                             L->d_free_top, L->d_nblocks);
-      ctx->stats.kernel_launches++;
-      CK(cudaStreamSynchronize(ctx->stream));  // pending_remove is pageable memory
-      L->tombstones += nrem;
-      L->pending_remove.clear();
-      ctx->stats.bytes_uploaded += nrem * 12;
-    }
-    if (L->pending) {
-      int rc = rehash_if_needed(ctx, L, L->pending);
-      if (rc) return rc;
-      const size_t per = L->payload_bytes_per_block(L->pending_packing);
-      CK(L->d_keys.reserve(L->pending * 12));
-      CK(L->d_payload.reserve(L->pending * per));
-      CK(cudaMemcpyAsync(L->d_keys.p, L->h_keys.p, L->pending * 12, cudaMemcpyHostToDevice, ctx->stream));
-      CK(cudaMemcpyAsync(L->d_payload.p, L->h_payload.p, L->pending * per, cudaMemcpyHostToDevice, ctx->stream));
-      ctx->stats.bytes_uploaded += L->pending * (12 + per);
-      rc = apply_update_device(ctx, L, L->pending, L->d_keys.as<int32_t>(), L->d_payload.p, L->pending_packing);
-      if (rc) return rc;
-      L->pending = 0;
-      L->pending_index.clear();
-    }
-    const int rc = sync_layer_state(ctx, L);  // also fences the pinned staging for reuse
-    if (rc) rc_all = rc;
-  }
-  return rc_all;
+  return commit_single(ctx);
 }
 
 int nbvgpu_layer_num_blocks(nbvgpu_ctx* ctx, int layer, size_t* out) {
@@ -1087,7 +1778,7 @@ int nbvgpu_layer_num_blocks(nbvgpu_ctx* ctx, int layer, size_t* out) {
   LayerHost* L = get_layer(ctx, layer, -1);
   if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
   DeviceGuard guard(ctx->device);
-  const int rc = sync_layer_state(ctx, L);
+  const int rc = sync_layer_states(ctx);
   *out = L->n_blocks;
   return rc;
 }
@@ -1198,8 +1889,17 @@ int nbvgpu_parse_blocks(int format, const uint8_t* buf, size_t len, int kind, fl
 }
 
 // ---- camera --------------------------------------------------------------------------------
+static int set_camera_one(nbvgpu_ctx* ctx, const nbvgpu_camera* cam);
 int nbvgpu_set_camera(nbvgpu_ctx* ctx, const nbvgpu_camera* cam) {
   if (!ctx || !cam) return NBVGPU_ERR_INVALID;
+  if (!ctx->group) return set_camera_one(ctx, cam);
+  for (nbvgpu_ctx* m : ctx->group->local) {
+    const int rc = set_camera_one(m, cam);
+    if (rc) return gfail(ctx, rc, m->err);
+  }
+  return NBVGPU_OK;
+}
+static int set_camera_one(nbvgpu_ctx* ctx, const nbvgpu_camera* cam) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   nbvgpu_host::CameraTables tab;
   if (!nbvgpu_host::build_camera_tables(*cam, &tab)) return fail(ctx, NBVGPU_ERR_INVALID, "invalid camera parameters");
@@ -1228,9 +1928,21 @@ int nbvgpu_gain_eval_device(nbvgpu_ctx* ctx, int layer, size_t n, const double* 
   return enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, d_counts, d_per_yaw, d_steps);
 }
 
+static int gain_eval_one(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, double* gain, int32_t* yaw_deg, uint64_t* counts,
+                         uint32_t* per_yaw, uint64_t* steps);
+// Batches this small stay on the first GPU of a multi-GPU context (the call is latency-, not throughput-bound).
+constexpr size_t kGroupMinBatch = 256;
 int nbvgpu_gain_eval(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, double* gain, int32_t* yaw_deg, uint64_t* counts,
                      uint32_t* per_yaw, uint64_t* steps) {
   if (!ctx || (n && (!pos || !gain))) return NBVGPU_ERR_INVALID;
+  if (!ctx->group || ctx->group->multi_process || n < kGroupMinBatch) return gain_eval_one(ctx, layer, n, pos, gain, yaw_deg, counts, per_yaw, steps);
+  return group_fan_out(ctx, n, [&](nbvgpu_ctx* m, size_t lo, size_t hi) {
+    return gain_eval_one(m, layer, hi - lo, pos + 3 * lo, gain + lo, yaw_deg ? yaw_deg + lo : nullptr, counts ? counts + 3 * lo : nullptr,
+                         per_yaw ? per_yaw + 1080 * lo : nullptr, steps ? steps + lo : nullptr);
+  });
+}
+static int gain_eval_one(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, double* gain, int32_t* yaw_deg, uint64_t* counts,
+                         uint32_t* per_yaw, uint64_t* steps) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
@@ -1307,39 +2019,20 @@ int nbvgpu_gain_eval_best(nbvgpu_ctx* ctx, int layer, size_t n, const double* po
                           const uint8_t* edge_free, double v_max, double dyaw_max, double zero_gain, nbvgpu_best* best,
                           double* gain, int32_t* yaw_deg) {
   if (!ctx || !best || (n && (!pos || !parent_yaw || !distance))) return NBVGPU_ERR_INVALID;
+  if (ctx->group)
+    return group_evaluate(ctx, layer, -1, 0.0, n, pos, nullptr, parent_yaw, distance, edge_free, v_max, dyaw_max, zero_gain, nullptr, best,
+                          gain, yaw_deg);
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
   if (check_position_range(ctx, L, n, pos)) return fail(ctx, NBVGPU_ERR_RANGE, "position non-finite or out of range");
   DeviceGuard guard(ctx->device);
-  // staging: [pos n*24 | parent n*8 | dist n*8 | free n (padded)] then results
-  const size_t o_par = n * 24, o_dist = o_par + n * 8, o_free = o_dist + n * 8, total = o_free + ((n + 7) & ~(size_t)7);
-  CK(ctx->h_io.reserve(total + n * 16 + 64, false));
-  CK(ctx->d_pos.reserve(total + 8));
-  CK(ctx->d_best.reserve(sizeof(nbvgpu_best)));
-  CK(ctx->d_gain.reserve(n * 8 + 8));
-  CK(ctx->d_yaw.reserve(n * 4 + 4));
-  char* h = ctx->h_io.as<char>();
-  memcpy(h, pos, n * 24);
-  memcpy(h + o_par, parent_yaw, n * 8);
-  memcpy(h + o_dist, distance, n * 8);
-  if (edge_free) memcpy(h + o_free, edge_free, n);
-  if (total) CK(cudaMemcpyAsync(ctx->d_pos.p, h, total, cudaMemcpyHostToDevice, ctx->stream));
-  char* d = ctx->d_pos.as<char>();
-  const int rc = best_device_nolock(ctx, layer, n, reinterpret_cast<double*>(d), reinterpret_cast<double*>(d + o_par),
-                                    reinterpret_cast<double*>(d + o_dist),
-                                    edge_free ? reinterpret_cast<uint8_t*>(d + o_free) : nullptr, v_max, dyaw_max, zero_gain,
-                                    ctx->d_best.as<nbvgpu_best>(), ctx->d_gain.as<double>(), ctx->d_yaw.as<int32_t>());
+  const int rc = evaluate_host_enqueue(ctx, layer, -1, 0.0, n, pos, nullptr, parent_yaw, distance, edge_free, v_max, dyaw_max, zero_gain,
+                                       gain || yaw_deg, BestPost{nullptr, 0, 0u});
   if (rc) return rc;
-  char* hr = h + total;  // results after the inputs
-  CK(cudaMemcpyAsync(hr, ctx->d_best.p, sizeof(nbvgpu_best), cudaMemcpyDeviceToHost, ctx->stream));
-  if (gain && n) CK(cudaMemcpyAsync(hr + 64, ctx->d_gain.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-  if (yaw_deg && n) CK(cudaMemcpyAsync(hr + 64 + n * 8, ctx->d_yaw.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  memcpy(best, hr, sizeof(nbvgpu_best));
-  if (gain) memcpy(gain, hr + 64, n * 8);
-  if (yaw_deg) memcpy(yaw_deg, hr + 64 + n * 8, n * 4);
+  evaluate_host_collect(ctx, n, false, edge_free != nullptr, nullptr, best, gain, yaw_deg);
   return NBVGPU_OK;
 }
 
@@ -1359,6 +2052,9 @@ int nbvgpu_evaluate_candidates(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, 
                                double dyaw_max, double zero_gain, uint8_t* edge_free, nbvgpu_best* best, double* gain,
                                int32_t* yaw_deg) {
   if (!ctx || !best || (n && (!pos || !seg || !parent_yaw || !distance))) return NBVGPU_ERR_INVALID;
+  if (ctx->group)
+    return group_evaluate(ctx, tsdf_layer, esdf_layer, robot_radius, n, pos, seg, parent_yaw, distance, nullptr, v_max, dyaw_max, zero_gain,
+                          edge_free, best, gain, yaw_deg);
   std::lock_guard<std::mutex> lk(ctx->mu);
   LayerHost* L = get_layer(ctx, tsdf_layer, NBVGPU_LAYER_TSDF);
   LayerHost* E = get_layer(ctx, esdf_layer, NBVGPU_LAYER_ESDF);
@@ -1369,34 +2065,37 @@ int nbvgpu_evaluate_candidates(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, 
   for (size_t i = 0; i < 6 * n; ++i)
     if (!(std::fabs(seg[i] * vs_inv) < 4194000.0)) return fail(ctx, NBVGPU_ERR_RANGE, "segment non-finite or out of range");
   DeviceGuard guard(ctx->device);
-  // staging in: [pos n*24 | seg n*48 | parent n*8 | dist n*8]; device out: [best 64 | gain n*8 | yaw n*4 (padded to 8) | free n]
-  const size_t o_seg = n * 24, o_par = o_seg + n * 48, o_dist = o_par + n * 8, in_bytes = o_dist + n * 8;
-  const size_t r_gain = 64, r_yaw = r_gain + n * 8, r_free = r_yaw + ((n * 4 + 7) & ~(size_t)7), out_bytes = r_free + ((n + 7) & ~(size_t)7);
-  CK(ctx->h_io.reserve(in_bytes + out_bytes + 64, false));
-  CK(ctx->d_pos.reserve(in_bytes + 8));
-  CK(ctx->d_aux.reserve(out_bytes + 8));
-  char* h = ctx->h_io.as<char>();
-  char* d = ctx->d_pos.as<char>();
-  char* dr = ctx->d_aux.as<char>();
-  memcpy(h, pos, n * 24);
-  memcpy(h + o_seg, seg, n * 48);
-  memcpy(h + o_par, parent_yaw, n * 8);
-  memcpy(h + o_dist, distance, n * 8);
-  if (in_bytes) CK(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  const int rc = evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, robot_radius, n, reinterpret_cast<double*>(d),
-                                        reinterpret_cast<double*>(d + o_seg), reinterpret_cast<double*>(d + o_par),
-                                        reinterpret_cast<double*>(d + o_dist), v_max, dyaw_max, zero_gain,
-                                        reinterpret_cast<uint8_t*>(dr + r_free), reinterpret_cast<nbvgpu_best*>(dr),
-                                        reinterpret_cast<double*>(dr + r_gain), reinterpret_cast<int32_t*>(dr + r_yaw));
+  const int rc = evaluate_host_enqueue(ctx, tsdf_layer, esdf_layer, robot_radius, n, pos, seg, parent_yaw, distance, nullptr, v_max, dyaw_max,
+                                       zero_gain, gain || yaw_deg || edge_free, BestPost{nullptr, 0, 0u});
   if (rc) return rc;
-  char* hr = h + in_bytes;
-  CK(cudaMemcpyAsync(hr, dr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
-  memcpy(best, hr, sizeof(nbvgpu_best));
-  if (gain) memcpy(gain, hr + r_gain, n * 8);
-  if (yaw_deg) memcpy(yaw_deg, hr + r_yaw, n * 4);
-  if (edge_free) memcpy(edge_free, hr + r_free, n);
+  evaluate_host_collect(ctx, n, true, false, edge_free, best, gain, yaw_deg);
   return NBVGPU_OK;
+}
+
+// A rank's shard of a batch that already sits in its GPU's memory (one process per GPU): n_local candidates starting at
+// global index index_offset.  Enqueues edge check + gain + scoring on this GPU, whose scoring kernel posts the shard's record
+// (global index) into the shared block; then waits for the records of EVERY rank and returns the batch's best node in host
+// memory.  Collective: every rank calls it once per batch (a rank with n_local == 0 too).
+int nbvgpu_evaluate_shard_device(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double robot_radius, size_t n_local, int64_t index_offset,
+                                 const double* d_pos, const double* d_seg, const double* d_parent_yaw, const double* d_distance,
+                                 double v_max, double dyaw_max, double zero_gain, uint8_t* d_edge_free, double* d_gain,
+                                 int32_t* d_yaw_deg, nbvgpu_best* best) {
+  if (!ctx || !best || (n_local && (!d_pos || !d_seg || !d_parent_yaw || !d_distance || !d_edge_free))) return NBVGPU_ERR_INVALID;
+  Group* G = ctx->group;
+  if (!G || G->local.size() != 1) return fail(ctx, NBVGPU_ERR_STATE, "needs a one-GPU-per-process context (nbvgpu_create_rank)");
+  std::lock_guard<std::mutex> glk(G->mu);
+  const unsigned seq = (unsigned)(++G->eval_seq);
+  if (n_local == 0) {
+    group_post_empty(G, G->rank0, seq);
+  } else {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const BestPost post{&G->d_shared[0]->best[seq & 1u][G->rank0], (long long)index_offset, seq};
+    const int rc = evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, robot_radius, n_local, d_pos, d_seg, d_parent_yaw, d_distance, v_max,
+                                          dyaw_max, zero_gain, d_edge_free, nullptr, d_gain, d_yaw_deg, post);
+    if (rc) return rc;
+  }
+  return group_collect_best(ctx, seq, zero_gain, best);
 }
 
 // ---- batched tree expansion ----------------------------------------------------------------
@@ -1492,8 +2191,13 @@ int nbvgpu_check_segments_device(nbvgpu_ctx* ctx, int layer, double radius, size
   return enqueue_segments(ctx, L, radius, n, d_seg, d_is_free);
 }
 
+static int check_segments_one(nbvgpu_ctx* ctx, int layer, double radius, size_t n, const double* seg, uint8_t* is_free);
 int nbvgpu_check_segments(nbvgpu_ctx* ctx, int layer, double radius, size_t n, const double* seg, uint8_t* is_free) {
   if (!ctx || (n && (!seg || !is_free))) return NBVGPU_ERR_INVALID;
+  if (!ctx->group || ctx->group->multi_process || n < 16 * kGroupMinBatch) return check_segments_one(ctx, layer, radius, n, seg, is_free);
+  return group_fan_out(ctx, n, [&](nbvgpu_ctx* m, size_t lo, size_t hi) { return check_segments_one(m, layer, radius, hi - lo, seg + 6 * lo, is_free + lo); });
+}
+static int check_segments_one(nbvgpu_ctx* ctx, int layer, double radius, size_t n, const double* seg, uint8_t* is_free) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_ESDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
@@ -1877,8 +2581,22 @@ int nbvgpu_debug_round_decimal6(double x, uint64_t* magnitude) {
 }
 
 // ---- introspection -------------------------------------------------------------------------
+static int get_stats_one(nbvgpu_ctx* ctx, nbvgpu_stats* out);
 int nbvgpu_get_stats(nbvgpu_ctx* ctx, nbvgpu_stats* out) {
   if (!ctx || !out) return NBVGPU_ERR_INVALID;
+  if (!ctx->group) return get_stats_one(ctx, out);
+  nbvgpu_stats sum{};
+  for (nbvgpu_ctx* m : ctx->group->local) {  // the GPUs of this process
+    nbvgpu_stats one{};
+    const int rc = get_stats_one(m, &one);
+    if (rc) return gfail(ctx, rc, m->err);
+    sum.rays += one.rays; sum.voxel_steps += one.voxel_steps; sum.collision_steps += one.collision_steps;
+    sum.blocks_uploaded += one.blocks_uploaded; sum.bytes_uploaded += one.bytes_uploaded; sum.kernel_launches += one.kernel_launches;
+  }
+  *out = sum;
+  return NBVGPU_OK;
+}
+static int get_stats_one(nbvgpu_ctx* ctx, nbvgpu_stats* out) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   DeviceGuard guard(ctx->device);
   unsigned long long t[8];
@@ -1930,6 +2648,13 @@ int nbvgpu_profile_collect(nbvgpu_ctx* ctx, double* gain_kernel_ms, uint64_t* la
 
 int nbvgpu_set_kernel_variant(nbvgpu_ctx* ctx, int variant) {
   if (!ctx || variant < 0 || variant > 5) return NBVGPU_ERR_INVALID;
+  if (ctx->group) {
+    for (nbvgpu_ctx* m : ctx->group->local) {
+      std::lock_guard<std::mutex> lk(m->mu);
+      m->variant = variant;
+    }
+    return NBVGPU_OK;
+  }
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->variant = variant;
   return NBVGPU_OK;

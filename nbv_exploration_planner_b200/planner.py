@@ -89,15 +89,57 @@ def _vp(a) -> Optional[C.c_void_p]:
 class NbvGpu:
     """One ``nbvgpu_ctx``: a GPU, its map-mirror layers, a camera and the evaluators."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, _handle=None):
         self._L = N.lib()
-        h = C.c_void_p()
-        rc = self._L.nbvgpu_create(device, C.byref(h))
-        if rc != 0:
-            raise N.NbvGpuError(rc, "nbvgpu_create failed (a B200 / sm_100 device is required; no CPU fallback)")
+        if _handle is None:
+            h = C.c_void_p()
+            rc = self._L.nbvgpu_create(device, C.byref(h))
+            if rc != 0:
+                raise N.NbvGpuError(rc, "nbvgpu_create failed (a B200 / sm_100 device is required; no CPU fallback)")
+        else:
+            h = _handle
         self._h = h
         self.device = device
         self.layers = {}
+
+    # -- multi-GPU contexts (SURVEY.md 8e): the same object, the same methods ------------------------
+    @classmethod
+    def multi(cls, device_ids: Sequence[int]) -> "NbvGpu":
+        """``nbvgpu_create_multi``: this process drives every GPU in ``device_ids``; batches are sharded over them,
+        ``commit`` replicates the map with one NCCL broadcast per chunk."""
+        L = N.lib()
+        ids = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+        h = C.c_void_p()
+        rc = L.nbvgpu_create_multi(len(device_ids), ids, C.byref(h))
+        if rc != 0:
+            raise N.NbvGpuError(rc, "nbvgpu_create_multi failed (B200 devices and NCCL are required; no CPU fallback)")
+        return cls(int(device_ids[0]), _handle=h)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        """``nbvgpu_group_unique_id``: 128 bytes rank 0 creates and every rank of a one-process-per-GPU context needs."""
+        L = N.lib()
+        buf = (C.c_uint8 * 128)()
+        rc = L.nbvgpu_group_unique_id(buf, 128)
+        if rc != 0:
+            raise N.NbvGpuError(rc, "nbvgpu_group_unique_id failed (NCCL is required)")
+        return bytes(buf)
+
+    @classmethod
+    def rank(cls, device: int, rank: int, world: int, unique_id: bytes) -> "NbvGpu":
+        """``nbvgpu_create_rank``: this process is rank ``rank`` of ``world`` and drives GPU ``device``."""
+        L = N.lib()
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id[:128])
+        h = C.c_void_p()
+        rc = L.nbvgpu_create_rank(device, rank, world, buf, 128, C.byref(h))
+        if rc != 0:
+            raise N.NbvGpuError(rc, "nbvgpu_create_rank failed (a B200 per rank and NCCL are required; no CPU fallback)")
+        return cls(device, _handle=h)
+
+    def group_info(self) -> dict:
+        r, w, l = C.c_int(0), C.c_int(1), C.c_int(1)
+        self._ck(self._L.nbvgpu_group_info(self._h, C.byref(r), C.byref(w), C.byref(l)))
+        return {"rank": r.value, "world": w.value, "local_gpus": l.value}
 
     # -- lifetime ---------------------------------------------------------------------------
     def close(self) -> None:
@@ -148,6 +190,13 @@ class NbvGpu:
             raise ValueError(f"payload has {payload.size} words, expected {per * len(keys)}")
         self._ck(self._L.nbvgpu_layer_update(self._h, layer, len(keys), _vp(keys), _vp(payload), packing))
 
+    def layer_update_pinned(self, layer: int, keys: np.ndarray, payload, packing: int = N.PACK_PLANAR) -> None:
+        """``nbvgpu_layer_update_pinned``: ``payload`` (a pinned torch tensor or anything with ``data_ptr`` / a page-locked
+        numpy array) is NOT copied: it must stay untouched until ``commit`` has returned."""
+        keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
+        self._pinned_keep = getattr(self, "_pinned_keep", []) + [payload]   # keep it alive until the commit
+        self._ck(self._L.nbvgpu_layer_update_pinned(self._h, layer, len(keys), _vp(keys), _vp(payload), packing))
+
     def layer_update_device(self, layer: int, n_blocks: int, d_keys, d_payload, packing: int = N.PACK_PLANAR) -> None:
         self._ck(self._L.nbvgpu_layer_update_device(self._h, layer, n_blocks, _vp(d_keys), _vp(d_payload), packing))
 
@@ -159,7 +208,10 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_layer_clear(self._h, layer))
 
     def commit(self) -> None:
-        self._ck(self._L.nbvgpu_commit(self._h))
+        try:
+            self._ck(self._L.nbvgpu_commit(self._h))
+        finally:
+            self._pinned_keep = []
 
     def layer_num_blocks(self, layer: int) -> int:
         out = C.c_size_t(0)
@@ -258,6 +310,17 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_evaluate_candidates_device(self._h, tsdf_layer, esdf_layer, float(robot_radius), n, _vp(d_pos),
                                                            _vp(d_seg), _vp(d_parent_yaw), _vp(d_distance), v_max, dyaw_max,
                                                            zero_gain, _vp(d_edge_free), _vp(d_best), _vp(d_gain), _vp(d_yaw_deg)))
+
+    def evaluate_shard_device(self, tsdf_layer: int, esdf_layer: int, robot_radius: float, n_local: int, index_offset: int, d_pos,
+                              d_seg, d_parent_yaw, d_distance, v_max, dyaw_max, zero_gain, d_edge_free, d_gain=None,
+                              d_yaw_deg=None) -> dict:
+        """``nbvgpu_evaluate_shard_device`` (one process per GPU): this rank's shard from device memory, the best node of
+        the WHOLE batch back in host memory -- no collective, no copy, no stream synchronisation."""
+        best = N.Best()
+        self._ck(self._L.nbvgpu_evaluate_shard_device(self._h, tsdf_layer, esdf_layer, float(robot_radius), n_local, index_offset,
+                                                      _vp(d_pos), _vp(d_seg), _vp(d_parent_yaw), _vp(d_distance), v_max, dyaw_max,
+                                                      zero_gain, _vp(d_edge_free), _vp(d_gain), _vp(d_yaw_deg), C.byref(best)))
+        return {"index": best.index, "score": best.score, "gain": best.gain, "yaw": best.yaw}
 
     def optimized_gain(self, layer: int, state: np.ndarray) -> float:
         """``double RrtTree::optimized_gain(Pose& state)``: returns the gain, writes ``state[3]``."""
