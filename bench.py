@@ -1,20 +1,23 @@
 #!/usr/bin/env python
 """bench.py -- viewpoint-gain hot path benchmark (BASELINE.json metric: candidate viewpoints/s).
 
-A "step" is one planning-step pass of the hot path over one batch of synthetic candidates:
-segment collision check of every tree edge (HighResManager::checkMotion), gain evaluation of every
-candidate (RrtTree::optimized_gain: 360-yaw ray sweep + best-yaw window), node scoring and
-best-candidate selection (rrt.cpp:220-246); with N > 1 ranks also the all-gather of the per-rank
-best records.  Workload at N = 1: BASELINE.json configs[1] ("cfg2": 20x20x5 m synthetic TSDF/ESDF,
-0.15 m voxels, 90x60 deg FOV, 5 m range, 1,000 candidates with their parent edges).  With N GPUs
-every rank evaluates its own 1,000 candidates on a replica of the map (weak scaling; the map is
-broadcast from rank 0 over NCCL during setup).
+A "step" is one planning-step pass of the hot path over one batch of synthetic candidates: segment collision check of
+every tree edge (HighResManager::checkMotion), gain evaluation behind every free edge (RrtTree::optimized_gain: 360-yaw ray
+sweep + best-yaw window), node scoring and best-candidate selection (rrt.cpp:220-246), with the best node of the WHOLE batch
+known on the host of every rank at the end of the step.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfgX]
+Workload (no flags): BASELINE.json configs[2] ("cfg3": 50x50x10 m office-like TSDF/ESDF, 0.10 m voxels, 90x60 deg FOV, 5 m
+range, 10,000 candidates with their parent edges) -- the 10k-candidate workload north_star's scaling target names; it fits
+one GPU.  STRONG scaling: with N GPUs the same 10,000 candidates are sharded inside libnbvgpu.so (one process per GPU,
+nbvgpu_create_rank), the map is replicated by nbvgpu_commit (page-locked H2D on rank 0 + ncclBroadcast).  `extra` carries
+configs[1] (cfg2) and configs[4] (cfg5, incremental replay) measured in the same run; `--config cfg4` measures configs[3]
+with the map replication inside every step.
 
-Prints ONE JSON line (rank 0).  `value` = candidates of all ranks / device time (CUDA events on the
-launching stream, max over ranks) with inputs resident in HBM; `e2e` = same through the host-buffer
-C ABI (H2D of the candidates and D2H of the results inside the timed region).
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfgX] [--extra cfgA,cfgB]
+
+Prints ONE JSON line (rank 0).  `value` = candidates of all ranks / device time (CUDA events on the launching stream around
+each step, max over ranks) with inputs resident in HBM; `e2e` = same through the host-buffer C ABI (H2D of the candidates and
+D2H of the results inside the timed region).
 """
 from __future__ import annotations
 
@@ -37,22 +40,27 @@ ALGO_BYTES_PER_STEP = 8.0  # one {distance, weight} pair per voxel-step (SURVEY.
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", help="cfg1..cfg5 (BASELINE.json configurations; cfg2 is the headline), or one of the "
-                    "side measurements: frontier (History::bfs), interp (ESDF interpolation), shipped (the reference's shipped geometry)")
+    ap.add_argument("--config", default="cfg3", help="cfg1..cfg5 (BASELINE.json configurations; cfg3, the 10,000-candidate workload, is the "
+                    "headline), or one of the side measurements: frontier (History::bfs), interp (ESDF interpolation), shipped "
+                    "(the reference's shipped geometry)")
+    ap.add_argument("--extra", default=None, help="comma-separated configurations measured as sub-records (default: cfg2,cfg5 with the "
+                    "default headline, none otherwise)")
+    ap.add_argument("--no-l2-probe", action="store_true")
     ap.add_argument("--map", default="cfg1", help="map of the frontier / interp side measurements")
     ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU (default: the config's)")
-    ap.add_argument("--separate-calls", action="store_true",
-                    help="evaluate a step with nbvgpu_check_segments + nbvgpu_gain_eval_best instead of nbvgpu_evaluate_candidates")
     ap.add_argument("--variant", type=int, default=0, help="gain kernel variant (A/B measurement)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="candidates in the cpu_baseline sample (default 1000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="", choices=["", "weak", "strong"], help="default: weak for cfg1/2, strong otherwise")
     ap.add_argument("--selfcheck", action="store_true", help="re-run one step with the plain FP64 kernel and compare")
     ap.add_argument("--traj-prefix", type=int, default=0, help="use only the first N trajectory points for the map")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.extra is None:
+        a.extra = "cfg2,cfg5" if (a.config == "cfg3" and not a.candidates and a.impl == "ours") else ""
+    return a
 
 
 def cpu_model() -> str:
@@ -89,16 +97,17 @@ def l2_info(g, achieved_gbs):
             "peak_source": "measured in this run: 64 MiB buffer, 128-bit L1-bypassing reads, best of 3"}
 
 
-def ncu_traffic_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the ray-sweep kernel from the committed ncu
-    capture (profiles/ncu_traffic.json, written by profiles/summarize_ncu.py), or None."""
+def ncu_traffic_per_launch(config):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the ray-sweep kernel for THIS configuration, from the committed
+    `ncu --set full` capture of the same launch shape (profiles/ncu_traffic.json: {"<cfg>": {"k_gain_dram_bytes_per_launch": ...}},
+    written by profiles/summarize_ncu.py), or None when that configuration has no capture."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get("k_gain_dram_bytes_per_launch")
-        except Exception:
-            return None
-    return None
+    try:
+        d = json.load(open(p))
+    except Exception:
+        return None
+    rec = d.get(config)
+    return rec.get("k_gain_dram_bytes_per_launch") if isinstance(rec, dict) else None
 
 
 class ClockSampler(threading.Thread):
@@ -212,39 +221,46 @@ class CpuReference:
 
 # ---------------------------------------------------------------------------------------------
 def run_reference(args):
-    """Reference arm: the reference's own CPU implementation of the path (oracle/_ref when the reference
-    compiled, else the oracle port) on the host cores, all threads, bounded sample per step."""
+    """Reference arm: the reference's own CPU implementation of the path (oracle/_ref when the reference compiled, else
+    the oracle port) on the host cores, all threads, on the SAME configuration and candidate set as the default arm, the
+    steps and warm-up steps asked for; each step a bounded sample of the candidates (a fixed prefix, stated as a fraction)
+    sized so that the whole run ends within a few minutes.  Throughput is per candidate, so the sample size does not bias it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from nbv_exploration_planner_b200 import synth
-    cfg = synth.CONFIGS[args.config]
-    m = synth.make_map(args.config)
+    name = args.config if args.config in synth.CONFIGS else "cfg3"
+    cfg = synth.CONFIGS[name]
+    m = synth.make_map(name)
     cam = m.camera()
     o, lt, le = load_oracle_ctx(m, cam)
     cores = os.cpu_count() or 1
-    n_total = args.candidates or cfg.n_candidates
+    strong = (args.scaling or ("weak" if name in ("cfg1", "cfg2") else "strong")) == "strong"
+    n_total = (args.candidates or cfg.n_candidates) * (1 if strong else max(1, args.gpus))
     c = synth.make_candidates(cfg, n_total, lambda s: o.check_segments(le, cfg.robot_radius, s, threads=cores)["free"])
     ref = CpuReference(m, cam, cfg, cores)
-    sample = min(n_total, max(cores * 8, 128))  # bounded per-step sample so that K steps end within minutes
+    # size the per-step sample from a first untimed pass: about 100 s for the whole run, at least one candidate per thread
+    probe = min(n_total, cores)
+    t_probe = ref.run(c.positions[:probe], c.segments[:probe])
+    n_steps_all = max(1, args.steps) + max(0, args.warmup)
+    sample = int(max(cores, min(n_total, 256, 100.0 / n_steps_all / max(t_probe / probe, 1e-6))))
     pos, seg = c.positions[:sample], c.segments[:sample]
     steps_per_vp = float(o.gain_eval(lt, pos, threads=cores)["steps"].mean())
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(max(0, args.warmup)):
         ref.run(pos, seg)
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, args.steps)
     total = sum(ref.run(pos, seg) for _ in range(steps))
     value = sample * steps / total
     out = {
         "impl": "reference", "metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64 frustum + f32 DDA + i64 voxel index", "data": "synthetic",
+        "steps": steps, "warmup": max(0, args.warmup), "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64 frustum + f32 DDA + i64 voxel index", "data": "synthetic",
         "voxel_steps_per_s": value * steps_per_vp,
-        "config": {"workload": f"{args.config}: {cfg.bounds_max[0]}x{cfg.bounds_max[1]}x{cfg.bounds_max[2]} m synthetic TSDF+ESDF, "
-                               f"{cfg.voxel_size} m voxels, {cfg.hfov_deg}x{cfg.vfov_deg} deg, {cfg.far_m} m range, "
-                               f"{n_total} candidates with ESDF edge check", "candidates_per_step": sample},
+        "config": {"workload": workload_text(cfg, name, n_total, n_total), "candidates_total": int(n_total), "candidates_per_step": sample,
+                   "fraction_of_candidates_per_step": sample / n_total, "map_blocks": int(len(m.keys))},
         "cpu_baseline": {"value": value, "unit": "viewpoints/s", "cores": cores, "cpu_model": cpu_model(), "kind": ref.kind,
-                         "sample": f"first {sample} of {n_total} candidates per step, {steps} steps, {cores} host threads "
-                                   f"(one reference planner instance per thread)"},
+                         "sample": f"first {sample} of {n_total} candidates per step ({100.0 * sample / n_total:.2f} %), {steps} steps, {cores} host "
+                                   f"threads (one reference planner instance per thread)"},
         "e2e": {"value": value, "unit": "viewpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(out)
@@ -257,137 +273,189 @@ def emit(obj):
 
 
 # ---------------------------------------------------------------------------------------------
-def replicate_map(g, lt, le, m, cfg, rank, world, dev, chunk_blocks=4096):
-    """Rank 0 holds the map on the host; every rank ends up with the same device replica: per chunk one
-    pinned H2D copy on rank 0, one NCCL broadcast of {keys | payload}, insert + scatter kernels on every
-    rank (nbvgpu_layer_update_device).  Returns (#blocks, device ms including H2D and broadcast)."""
+class Rig:
+    """The process's place in the launch (one process per GPU, RANK / LOCAL_RANK / WORLD_SIZE from torchrun) and the
+    plumbing torch.distributed provides around the library: the NCCL unique id and the candidate set travel through it
+    once per configuration; nothing on the per-step path does."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.stream = torch.cuda.Stream(device=self.dev)   # one explicit stream: torch events and the library's kernels
+        torch.cuda.set_stream(self.stream)
+        self.flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=self.dev)  # > 126 MB L2
+
+    def make_ctx(self):
+        """One GPU: a one-device multi context (the shared-block result path without NCCL); N ranks: nbvgpu_create_rank."""
+        from nbv_exploration_planner_b200 import dist as nd
+        return nd.create_context(self.local, self.stream.cuda_stream)
+
+    def bcast_int(self, v):
+        if self.world == 1:
+            return int(v)
+        t = self.torch.tensor([int(v)], dtype=self.torch.int64, device=self.dev)
+        self.dist.broadcast(t, 0)
+        return int(t.item())
+
+    def bcast_array(self, a, shape):
+        """float64 array of `shape` from rank 0 to every rank (numpy in, numpy out)."""
+        torch = self.torch
+        t = torch.from_numpy(np.ascontiguousarray(a, np.float64)).to(self.dev) if self.rank == 0 else torch.empty(shape, dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.broadcast(t, 0)
+        return t.cpu().numpy()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def reduce(self, values, op="max"):
+        torch = self.torch
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(x) for x in t.cpu()]
+
+    def close(self):
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def page_lock(a: np.ndarray):
+    """Page-lock a numpy array in place (cudaHostRegister) so that nbvgpu_layer_update_pinned can copy straight from it;
+    returns something to keep alive.  Falls back to a pinned copy."""
     import torch
-    import torch.distributed as dist
-
-    from nbv_exploration_planner_b200 import dist as nd
-    nvox = cfg.vps ** 3
-    hdr = torch.tensor([len(m.keys) if rank == 0 else 0], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(hdr, 0)
-    nb = int(hdr.item())
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for i in range(0, nb, chunk_blocks):
-        j = min(nb, i + chunk_blocks)
-        n_t, dk, dp = nd.broadcast_blocks(m.keys[i:j] if rank == 0 else None, m.tsdf[i:j] if rank == 0 else None, 2 * nvox, dev)
-        g.layer_update_device(lt, n_t, dk, dp)
-        n_e, dk2, dp2 = nd.broadcast_blocks(m.keys[i:j] if rank == 0 else None, m.esdf[i:j] if rank == 0 else None, nvox, dev)
-        g.layer_update_device(le, n_e, dk2, dp2)
-    e1.record()
-    torch.cuda.synchronize()
-    return nb, e0.elapsed_time(e1)
+    a = np.ascontiguousarray(a)
+    try:
+        rc = torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)
+        if int(rc) == 0:
+            return a, a
+    except Exception:
+        pass
+    t = torch.from_numpy(a).pin_memory()
+    return t, t
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+def shard(n, world, rank):
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
 
-    from nbv_exploration_planner_b200 import LAYER_ESDF, LAYER_TSDF, NbvGpu, synth
-    from nbv_exploration_planner_b200 import dist as nd
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+def workload_text(cfg, name, n_all, n_local):
+    return (f"{name}: {cfg.bounds_max[0]}x{cfg.bounds_max[1]}x{cfg.bounds_max[2]} m synthetic TSDF+ESDF, {cfg.voxel_size} m voxels, "
+            f"{cfg.vps}^3 blocks, {cfg.hfov_deg}x{cfg.vfov_deg} deg FOV, {cfg.far_m} m range, {int(n_all)} candidates "
+            f"({n_local} on this GPU) with ESDF edge check (radius {cfg.robot_radius:.4f} m, overshoot {cfg.overshoot} m)")
 
-    cfg = synth.CONFIGS[args.config]
-    strong = (args.scaling or ("weak" if args.config in ("cfg1", "cfg2") else "strong")) == "strong"
+
+def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline, include_replication=False):
+    """One BASELINE.json gain configuration (cfg1..cfg4): map on rank 0 -> nbvgpu_commit (pinned H2D + NCCL broadcast inside
+    the library) -> K timed planning steps.  A step = edge check of every candidate's parent edge, ray sweep behind the
+    free ones, node scoring, best node of the WHOLE batch known on the host of every rank.
+      value: shards resident in HBM (nbvgpu_evaluate_shard_device), CUDA events on the launching stream around each step --
+             the closing event is recorded after the call has returned, i.e. after the slowest rank's record arrived --,
+             L2 flushed between steps, max over ranks.
+      e2e:   the whole batch in host memory on every rank (nbvgpu_evaluate_candidates): shard H2D, results D2H, wall clock.
+    include_replication (config 4, "map broadcast cost included"): every step first clears the layers and replicates the
+    whole map again, in both legs."""
+    import hashlib
+    torch = rig.torch
+    from nbv_exploration_planner_b200 import LAYER_ESDF, LAYER_TSDF, synth
+    cfg = synth.CONFIGS[name]
+    world, rank, dev = rig.world, rig.rank, rig.dev
     n_total = (args.candidates or cfg.n_candidates) * (1 if strong else world)
-    g = NbvGpu(local)
-    # one explicit stream for everything: torch events, NCCL collectives and the library's kernels
-    work_stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(work_stream)
-    g.set_stream(work_stream.cuda_stream)
+    g = rig.make_ctx()
     g.set_kernel_variant(args.variant)
-
-    # ---- setup (untimed unless the config says otherwise): map on rank 0 -> NCCL broadcast -> replicas ----
     t_setup = time.perf_counter()
-    m = synth.make_map(args.config, traj_prefix=args.traj_prefix or None) if rank == 0 else None
-    hdr = torch.tensor([len(m.keys) if rank == 0 else 0], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.broadcast(hdr, 0)
-    nb_alloc = int(hdr.item())
-    lt = g.layer_create(LAYER_TSDF, cfg.voxel_size, cfg.vps, nb_alloc + 64)
-    le = g.layer_create(LAYER_ESDF, cfg.voxel_size, cfg.vps, nb_alloc + 64)
-    nb, map_broadcast_ms = replicate_map(g, lt, le, m, cfg, rank, world, dev)
-    cam = synth.camera_for(cfg)
-    g.set_camera(cam)
+    m = synth.make_map(name, traj_prefix=args.traj_prefix or None) if rank == 0 else None
+    nb = rig.bcast_int(len(m.keys) if rank == 0 else 0)
+    lt = g.layer_create(LAYER_TSDF, cfg.voxel_size, cfg.vps, nb + 64)
+    le = g.layer_create(LAYER_ESDF, cfg.voxel_size, cfg.vps, nb + 64)
+    keep = []
+    if rank == 0:
+        p_tsdf, k1 = page_lock(m.tsdf)
+        p_esdf, k2 = page_lock(m.esdf)
+        keep += [k1, k2]
+    map_bytes = nb * cfg.vps ** 3 * 12
 
+    def replicate():
+        """rank 0: stage the whole map from page-locked memory; all ranks: commit.  Returns wall ms (commit is synchronous)."""
+        t0 = time.perf_counter()
+        if rank == 0:
+            g.layer_update_pinned(lt, m.keys, p_tsdf)
+            g.layer_update_pinned(le, m.keys, p_esdf)
+        g.commit()
+        return (time.perf_counter() - t0) * 1e3
+
+    rig.barrier()
+    repl_ms = [replicate()]
+    g.set_camera(synth.camera_for(cfg))
     # candidates: grown on rank 0 with the GPU collision check as the acceptance test, then shared
     if rank == 0:
         c = synth.make_candidates(cfg, n_total, lambda s: g.check_segments(le, cfg.robot_radius, s))
         pack = np.concatenate([c.positions, c.segments, c.distance[:, None]], 1)
-    else:
-        pack = np.empty((n_total, 10))
-    import hashlib
-    inputs_sha = None
-    if rank == 0:
-        map_bytes = sum(int(np.asarray(a).nbytes) for a in (m.keys, m.tsdf, m.esdf) if a is not None)
+        mb = sum(int(np.asarray(a).nbytes) for a in (m.keys, m.tsdf, m.esdf))
         inputs_sha = {"candidates": hashlib.sha256(np.ascontiguousarray(pack).tobytes()).hexdigest(),
-                      "map": m.sha256() if map_bytes <= (1 << 30) else f"not hashed ({map_bytes >> 20} MiB)",
+                      "map": m.sha256() if mb <= (1 << 30) else f"not hashed ({mb >> 20} MiB)",
                       "seeds": {"map": cfg.seed_map, "candidates": cfg.seed_cand}}
-    pack_t = torch.from_numpy(pack).to(dev)
-    if world > 1:
-        dist.broadcast(pack_t, 0)
-    lo, hi = nd.shard_bounds(n_total, world, rank)
-    mine = pack_t[lo:hi].contiguous()
+    else:
+        pack, inputs_sha = None, None
+    pack = rig.bcast_array(pack, (n_total, 10))
+    lo, hi = shard(n_total, world, rank)
     n = hi - lo
-    d_pos = mine[:, 0:3].contiguous()
-    d_seg = mine[:, 3:9].contiguous()
-    d_dist = mine[:, 9].contiguous()
-    d_pyaw = torch.zeros(n, dtype=torch.float64, device=dev)   # flat candidate set: parents face yaw 0
-    d_free = torch.empty(n, dtype=torch.uint8, device=dev)
-    d_gain = torch.empty(n, dtype=torch.float64, device=dev)
-    d_yaw = torch.empty(n, dtype=torch.int32, device=dev)
-    d_best = torch.empty(32, dtype=torch.uint8, device=dev)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    h_pos, h_seg, h_dist = (np.ascontiguousarray(pack[:, 0:3]), np.ascontiguousarray(pack[:, 3:9]), np.ascontiguousarray(pack[:, 9]))
+    h_pyaw = np.zeros(n_total)                                  # flat candidate set: parents face yaw 0
+    d_pos = torch.from_numpy(h_pos[lo:hi].copy()).to(dev)
+    d_seg = torch.from_numpy(h_seg[lo:hi].copy()).to(dev)
+    d_dist = torch.from_numpy(h_dist[lo:hi].copy()).to(dev)
+    d_pyaw = torch.zeros(n, dtype=torch.float64, device=dev)
+    d_free = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    d_gain = torch.empty(max(n, 1), dtype=torch.float64, device=dev)
+    d_yaw = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
     v_max, dyaw_max, zero_gain = 1.0, 0.5, 0.0
     setup_s = time.perf_counter() - t_setup
 
+    def redo_map():
+        g.layer_clear(lt)
+        g.layer_clear(le)
+        return replicate()
+
     def step_device():
-        if args.separate_calls:   # the two entry points one after the other (identical results)
-            g.check_segments_device(le, cfg.robot_radius, n, d_seg, d_free)
-            g.gain_eval_best_device(lt, n, d_pos, d_pyaw, d_dist, d_free, v_max, dyaw_max, zero_gain, d_best, d_gain, d_yaw)
-        else:                     # one call: the edge check runs beside the ray sweep
-            g.evaluate_candidates_device(lt, le, cfg.robot_radius, n, d_pos, d_seg, d_pyaw, d_dist, v_max, dyaw_max, zero_gain,
-                                         d_free, d_best, d_gain, d_yaw)
-        # every step ends with the winner known on the host (one 32 B record per rank)
-        return nd.gather_best_raw(d_best, n_total)
+        if include_replication:
+            repl_ms.append(redo_map())
+        return g.evaluate_shard_device(lt, le, cfg.robot_radius, n, lo, d_pos, d_seg, d_pyaw, d_dist, v_max, dyaw_max, zero_gain,
+                                       d_free, d_gain, d_yaw)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step_device()
-    torch.cuda.synchronize()
-
+    rig.barrier()
     # ---- timed region: K steps, CUDA events on the launching stream, L2 flushed between steps ------
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(rig.local)
     st0 = g.stats()
     g.set_profiling(True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    repl_ms.clear()
+    rig.barrier()
     sampler.start()
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     winner = None
     for a, b in evs:
-        flush.zero_()
+        rig.flush.zero_()
         a.record()
         winner = step_device()
         b.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    rig.barrier()
     sampler.stop_flag = True
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     kern_ms, kern_launches = g.profile_collect()
@@ -397,40 +465,34 @@ def run_ours(args):
     vsteps = st1["voxel_steps"] - st0["voxel_steps"]
     rays = st1["rays"] - st0["rays"]
     csteps = st1["collision_steps"] - st0["collision_steps"]
+    repl_timed = list(repl_ms)
 
-    # ---- e2e: same step through the host-buffer C ABI (H2D + D2H inside) ---------------------------
-    h = mine.cpu().numpy()
-    h_pos, h_seg, h_dist = np.ascontiguousarray(h[:, 0:3]), np.ascontiguousarray(h[:, 3:9]), np.ascontiguousarray(h[:, 9])
-    h_pyaw = np.zeros(n)
-    e2e_steps = max(3, min(args.steps, 30))
+    # ---- e2e: the same step through the host-buffer C ABI (H2D of the shard + D2H of its results inside) ------------
+    e2e_steps = max(3, min(steps, 30))
 
     def step_host():
-        if args.separate_calls:
-            free = g.check_segments(le, cfg.robot_radius, h_seg)
-            r = g.gain_eval_best(lt, h_pos, h_pyaw, h_dist, free, v_max, dyaw_max, zero_gain)
-        else:
-            r = g.evaluate_candidates(lt, le, cfg.robot_radius, h_pos, h_seg, h_pyaw, h_dist, v_max, dyaw_max, zero_gain)
-        if world > 1:
-            rec = torch.tensor([r["index"], r["score"], r["best_gain"], r["best_yaw"]], dtype=torch.float64, device=dev)
-            return nd.gather_best(rec, lo)
-        return r
+        if include_replication:
+            redo_map()
+        return g.evaluate_candidates(lt, le, cfg.robot_radius, h_pos, h_seg, h_pyaw, h_dist, v_max, dyaw_max, zero_gain)
 
     for _ in range(2):
-        step_host()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+        r_host = step_host()
+    rig.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        step_host()
+        rig.flush.zero_()
+        r_host = step_host()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    h2d = n * (48 + 24 + 8 + 8 + (1 if args.separate_calls else 0))   # segments, positions, parent yaw, distance (+ verdicts back up)
-    d2h = n * (1 + 8 + 4) + (32 if args.separate_calls else 64)       # verdicts, gain, yaw + the best record
+    rig.barrier()
+    same = (r_host["index"], r_host["score"]) == (winner["index"], winner["score"]) and \
+        bool(np.array_equal(r_host["gain"][lo:hi], d_gain[:n].cpu().numpy()))
+    h2d = n * (48 + 24 + 8 + 8) + (map_bytes + nb * 64 if include_replication and rank == 0 else 0)
+    d2h = n * (1 + 8 + 4)          # verdicts, gain, yaw of the shard; the best records arrive by GPU stores into host memory
 
     # ---- drop-in latency: one candidate through the n = 1 shims (what the unmodified iterate() would call)
     lat_us = None
-    if rank == 0:
+    if rank == 0 and n > 0:
         st = np.array([h_pos[0, 0], h_pos[0, 1], h_pos[0, 2], 0.0])
         for _ in range(5):
             g.optimized_gain(lt, st)
@@ -441,101 +503,77 @@ def run_ours(args):
             g.check_motion(le, cfg.robot_radius, h_seg[0, :3], h_seg[0, 3:])
         lat_us = (time.perf_counter() - t1) / 50 * 1e6
 
-    # ---- optional full-size self-check: the plain FP64 transcription kernel must give the same result
     selfcheck = None
-    if args.selfcheck:
+    if args.selfcheck:   # the plain FP64 transcription kernel must give the same gains on the whole shard
         ref_gain, ref_yaw = d_gain.clone(), d_yaw.clone()
         g.set_kernel_variant(1)
-        step_device()
+        g.evaluate_shard_device(lt, le, cfg.robot_radius, n, lo, d_pos, d_seg, d_pyaw, d_dist, v_max, dyaw_max, zero_gain, d_free, d_gain, d_yaw)
         torch.cuda.synchronize()
         selfcheck = {"variant_1_equals_default": bool(torch.equal(ref_gain, d_gain) and torch.equal(ref_yaw, d_yaw)), "candidates": n}
         g.set_kernel_variant(args.variant)
 
-    # ---- reduce over ranks (max time) -----------------------------------------------------------
-    red = torch.tensor([dev_ms, e2e_s, kern_ms, map_broadcast_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(vsteps), float(rays), float(launches), float(n), float(csteps)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_s_max, kern_ms_max, bcast_ms_max = (float(x) for x in red.cpu())
-    vsteps_all, rays_all, launches_all, n_all, csteps_all = (float(x) for x in tot.cpu())
+    dev_ms_max, e2e_s_max, kern_ms_max, repl_max = rig.reduce([dev_ms, e2e_s, kern_ms, max(repl_timed) if repl_timed else repl_ms[0] if repl_ms else 0.0], "max")
+    vsteps_all, rays_all, launches_all, n_all, csteps_all, same_all = rig.reduce([vsteps, rays, launches, n, csteps, 0.0 if same else 1.0], "sum")
     clocks = sampler.summary()
-
+    out = None
     if rank == 0:
-        value = n_all * args.steps / (dev_ms_max * 1e-3)
+        value = n_all * steps / (dev_ms_max * 1e-3)
         peak, peak_src = measured_peaks()
-        # roofline of the dominant kernel (k_gain) on THIS rank: algorithmic bytes per launch / launch time
         steps_per_launch = vsteps / max(1, kern_launches)
         ach = steps_per_launch * ALGO_BYTES_PER_STEP / (kern_ms / max(1, kern_launches) * 1e-3) / 1e9
+        first_repl = repl_ms[0] if not repl_timed else float(np.median(repl_timed))
         out = {
-            "metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak",
-            "vs_baseline": None, "dtype": "f64 frustum planes + f32 DDA + i32 voxel index (bit-exact vs reference arithmetic)",
-            "data": "synthetic",
-            "config": {"workload": f"{args.config}: {cfg.bounds_max[0]}x{cfg.bounds_max[1]}x{cfg.bounds_max[2]} m synthetic TSDF+ESDF, "
-                                   f"{cfg.voxel_size} m voxels, {cfg.vps}^3 blocks, {cfg.hfov_deg}x{cfg.vfov_deg} deg FOV, "
-                                   f"{cfg.far_m} m range, {int(n_all)} candidates ({n} per GPU) with ESDF edge check "
-                                   f"(radius {cfg.robot_radius:.4f} m, overshoot {cfg.overshoot} m)",
-                       "candidates_total": int(n_all), "map_blocks": nb, "l2": "flushed between steps (256 MiB write)",
-                       "kernel_variant": args.variant, "parallelism": f"candidates sharded over {world} GPU(s), map replicated",
-                       "map_broadcast_ms_setup": bcast_ms_max, "setup_s": setup_s, "inputs_sha256": inputs_sha},
+            "metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": world, "steps": steps,
+            "warmup": max(warmup, 3), "ms_per_step": dev_ms_max / steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f64 frustum planes + f32 DDA + i32 voxel index (bit-exact vs reference arithmetic)", "data": "synthetic",
+            "config": {"workload": workload_text(cfg, name, n_all, n), "candidates_total": int(n_all), "map_blocks": nb,
+                       "l2": "flushed between steps (256 MiB write)", "kernel_variant": args.variant,
+                       "parallelism": f"candidates sharded over {world} GPU(s) inside libnbvgpu.so, map replicated by nbvgpu_commit "
+                                      f"(page-locked H2D on rank 0 + ncclBroadcast of {{descriptor table | payload}} per 64 MiB chunk); best "
+                                      f"records through GPU stores into shared host memory (no collective per step)",
+                       "map_replication": {"ms": first_repl, "bytes": map_bytes, "gb_per_s": map_bytes / (first_repl * 1e-3) / 1e9 if first_repl else None,
+                                           "inside_timed_steps": bool(include_replication)},
+                       "setup_s": setup_s, "inputs_sha256": inputs_sha},
             "rays_per_s": rays_all / (dev_ms_max * 1e-3), "voxel_steps_per_s": vsteps_all / (dev_ms_max * 1e-3),
-            "voxel_steps_per_viewpoint": vsteps_all / max(1.0, n_all * args.steps),
-            # every candidate comes with its parent edge (edges/s for config 2); ESDF voxel-steps of checkMotion
-            "edges_per_s": n_all * args.steps / (dev_ms_max * 1e-3), "collision_steps_per_s": csteps_all / (dev_ms_max * 1e-3),
-            "value_including_map_broadcast": n_all / ((dev_ms_max / args.steps + bcast_ms_max) * 1e-3),
+            "voxel_steps_per_viewpoint": vsteps_all / max(1.0, n_all * steps),
+            "edges_per_s": n_all * steps / (dev_ms_max * 1e-3), "collision_steps_per_s": csteps_all / (dev_ms_max * 1e-3),
             "e2e": {"value": n_all * e2e_steps / e2e_s_max, "unit": "viewpoints/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "equals_device_leg": same_all == 0.0,
+                    "l2": "flushed between steps"},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "kernel": "k_gain (ray sweep)", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": ncu_traffic_per_launch(), "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": ncu_traffic_per_launch(name), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": steps_per_launch * ALGO_BYTES_PER_STEP,
                          "avg_launch_ms": kern_ms / max(1, kern_launches),
                          "kernel_share_of_step": kern_ms / dev_ms if dev_ms > 0 else None,
-                         "l2": l2_info(g, ach),
-                         "note": "8 B per executed voxel-step (SURVEY.md 8d); the map is L2/L1 resident so real DRAM traffic is far lower"},
-            "clocks": clocks,
-            "best": winner,
+                         "l2": l2_info(g, ach) if not args.no_l2_probe else None,
+                         "note": "8 B per executed voxel-step (SURVEY.md 8d); the status tiles the sweep reads are L2/L1 resident, so real DRAM traffic is far lower"},
+            "clocks": clocks, "best": winner,
             "single_candidate_latency_us": lat_us,  # checkMotion + optimized_gain, n = 1, host buffers
         }
         if selfcheck is not None:
             out["selfcheck"] = selfcheck
-        if not args.no_cpu_baseline and world == 1:
-            out["cpu_baseline"] = cpu_baseline(args, cfg, h_pos, h_seg)
-        emit(out)
+        if with_cpu_baseline and not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(args, name, cfg, h_pos, h_seg)
     g.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return out
 
 
-# ---------------------------------------------------------------------------------------------
-def run_replay(args):
-    """BASELINE config 5: incremental exploration replay.  Each planning step marks the blocks that
-    intersect the observation sphere around the next trajectory point as changed, uploads them (rank 0
-    host -> device -> NCCL broadcast -> insert/scatter kernels on every rank), then checks and scores a
-    fresh set of candidates around the new position.  Everything per step is inside the timed region."""
-    import torch
-    import torch.distributed as dist
-
-    from nbv_exploration_planner_b200 import LAYER_ESDF, LAYER_TSDF, NbvGpu, synth
-    from nbv_exploration_planner_b200 import dist as nd
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-    cfg = synth.CONFIGS[args.config]
+def bench_replay(rig, args, name, steps):
+    """BASELINE config 5: incremental exploration replay.  Per planning step: the blocks within the observation sphere of
+    the next trajectory point change (rank 0 stages them from page-locked memory: TSDF + ESDF), nbvgpu_commit replicates them
+    (one H2D, one broadcast, one kernel), then a fresh UNFILTERED set of candidates around the new position is checked,
+    swept behind its free edges and scored, the whole batch in host memory on every rank (nbvgpu_evaluate_candidates).
+    Everything per step is inside the timed region (host wall clock, max over ranks); the map WRITER (block generation) and
+    the candidate sampler run before it."""
+    torch = rig.torch
+    from nbv_exploration_planner_b200 import LAYER_ESDF, LAYER_TSDF, synth
+    world, rank = rig.world, rig.rank
+    cfg = synth.CONFIGS[name]
     n_total = args.candidates or cfg.n_candidates
-    n_steps = min(args.steps, cfg.traj_points - 1)
-    g = NbvGpu(local)
-    ws = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(ws)
-    g.set_stream(ws.cuda_stream)
+    n_steps = min(steps, cfg.traj_points - 1)
+    g = rig.make_ctx()
     nvox = cfg.vps ** 3
     rng = np.random.Generator(np.random.MT19937(cfg.seed_map))
     objects = synth._world_objects(cfg, rng)
@@ -544,83 +582,118 @@ def run_replay(args):
     lt = g.layer_create(LAYER_TSDF, cfg.voxel_size, cfg.vps, len(all_keys) + 64)
     le = g.layer_create(LAYER_ESDF, cfg.voxel_size, cfg.vps, len(all_keys) + 64)
     g.set_camera(synth.camera_for(cfg))
-    # per-step changed blocks, generated up front on rank 0 (map *writing* is not the path being measured)
     updates = []
-    if rank == 0:
+    if rank == 0:   # per-step changed blocks in page-locked memory (map writing is not the path being measured)
         for k in range(n_steps + 1):
             keys = synth.blocks_touching(cfg.voxel_size, cfg.vps, traj[k:k + 1], cfg.obs_radius, cfg.bounds_min, cfg.bounds_max)
             tsdf, esdf = synth.generate_blocks(cfg, keys, objects, traj[:k + 1])
-            updates.append((keys, tsdf, esdf))
-    # candidate offsets around the current position (star-shaped expansion from the current pose)
+            updates.append((keys, torch.from_numpy(tsdf).pin_memory(), torch.from_numpy(esdf).pin_memory()))
+    # candidate offsets around the current position (star-shaped expansion from the current pose), per step, up front
     crng = np.random.Generator(np.random.MT19937(cfg.seed_cand))
     off = 2.0 * cfg.vicinity * (crng.random((4 * n_total, 3)) - 0.5)
     off = off[(off ** 2).sum(1) <= cfg.vicinity ** 2][:n_total]
     lo_b, hi_b = np.array(cfg.bounds_min, float) + 0.3, np.array(cfg.bounds_max, float) - 0.3
-    lo, hi = nd.shard_bounds(n_total, world, rank)
-
-    def apply_update(k):
-        keys, tsdf, esdf = updates[k] if rank == 0 else (None, None, None)
-        n_t, dk, dp = nd.broadcast_blocks(keys, tsdf, 2 * nvox, dev)
-        g.layer_update_device(lt, n_t, dk, dp)
-        n_e, dk2, dp2 = nd.broadcast_blocks(keys, esdf, nvox, dev)
-        g.layer_update_device(le, n_e, dk2, dp2)
-        return n_t
-
-    def plan(k):
+    cands = []
+    for k in range(n_steps + 1):
         p = traj[k]
-        pos = np.clip(p + off[lo:hi], lo_b, hi_b)
+        pos = np.clip(p + off, lo_b, hi_b)
         d = pos - p
         nrm = np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-9)
         seg = np.concatenate([np.broadcast_to(p, pos.shape), pos + d / nrm * cfg.overshoot], 1)
-        free = g.check_segments(le, cfg.robot_radius, seg)
-        r = g.gain_eval_best(lt, pos, np.zeros(len(pos)), nrm[:, 0], free, 1.0, 0.5, 0.0)
-        rec = torch.tensor([r["index"], r["score"], r["best_gain"], r["best_yaw"]], dtype=torch.float64, device=dev)
-        return nd.gather_best(rec, lo), int(free.sum())
+        cands.append((np.ascontiguousarray(pos), np.ascontiguousarray(seg), np.ascontiguousarray(nrm[:, 0])))
+    pyaw = np.zeros(n_total)
+    lo, hi = shard(n_total, world, rank)
+
+    def apply_update(k):
+        if rank == 0:
+            keys, pt, pe = updates[k]
+            g.layer_update_pinned(lt, keys, pt)
+            g.layer_update_pinned(le, keys, pe)
+        g.commit()
+        return len(updates[k][0]) if rank == 0 else 0
+
+    def plan(k):
+        pos, seg, dist = cands[k]
+        return g.evaluate_candidates(lt, le, cfg.robot_radius, pos, seg, pyaw, dist, 1.0, 0.5, 0.0)
 
     apply_update(0)
     plan(0)                                   # warm-up on the first pose
     st0 = g.stats()
-    sampler = ClockSampler(local)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    sampler = ClockSampler(rig.local)
+    rig.barrier()
     sampler.start()
     t0 = time.perf_counter()
     up_ms, blocks, nfree = 0.0, 0, 0
+    best = None
     for k in range(1, n_steps + 1):
         tu = time.perf_counter()
-        blocks += apply_update(k)
-        torch.cuda.synchronize()
+        blocks += apply_update(k)             # synchronous: returns when the snapshot is in place on this rank's GPU
         up_ms += (time.perf_counter() - tu) * 1e3
-        best, nf = plan(k)
-        nfree += nf
+        best = plan(k)
+        nfree += int(best["free"][lo:hi].sum())
     torch.cuda.synchronize()
     total_s = time.perf_counter() - t0
+    rig.barrier()
     sampler.stop_flag = True
     st1 = g.stats()
-    red = torch.tensor([total_s, up_ms], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(st1["voxel_steps"] - st0["voxel_steps"]), float(st1["kernel_launches"] - st0["kernel_launches"])],
-                       dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    total_s, up_ms = rig.reduce([total_s, up_ms], "max")
+    vsteps, launches, nfree, blocks, up_bytes = rig.reduce([st1["voxel_steps"] - st0["voxel_steps"], st1["kernel_launches"] - st0["kernel_launches"],
+                                                            nfree, blocks, st1["bytes_uploaded"] - st0["bytes_uploaded"]], "sum")
+    out = None
     if rank == 0:
-        total_s, up_ms = (float(x) for x in red.cpu())
-        vsteps, launches = (float(x) for x in tot.cpu())
         value = n_total * n_steps / total_s
-        emit({"metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": world, "steps": n_steps,
-              "warmup": 1, "ms_per_step": 1e3 * total_s / n_steps, "higher_is_better": True, "scaling": "strong",
-              "vs_baseline": None, "dtype": "f64 frustum planes + f32 DDA + i32 voxel index", "data": "synthetic",
-              "config": {"workload": f"{args.config}: incremental exploration replay, {n_steps} planning steps, per-step changed-block "
-                                     f"upload + {n_total} candidates, {cfg.voxel_size} m voxels, {cfg.far_m} m range",
-                         "blocks_uploaded_per_step": blocks / n_steps, "map_update_ms_per_step": up_ms / n_steps,
-                         "free_edges_per_step": nfree / n_steps, "timing": "wall clock over the whole replay, host buffers"},
-              "voxel_steps_per_s": vsteps / total_s, "gpu_launches": int(launches), "clocks": sampler.summary(),
-              "e2e": {"value": value, "unit": "viewpoints/s", "h2d_bytes_per_step": (hi - lo) * 89 + int(blocks / n_steps) * nvox * 12,
-                      "d2h_bytes_per_step": (hi - lo) * 13 + 32}, "best": best})
+        peak, _ = measured_peaks()
+        bpb = nvox * 12 + nvox // 4 + nvox // 8      # tile bytes written per (TSDF + ESDF) block: float2 + float tiles, status + observed bits
+        out = {"metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": world, "steps": n_steps,
+               "warmup": 1, "ms_per_step": 1e3 * total_s / n_steps, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "f64 frustum planes + f32 DDA + i32 voxel index", "data": "synthetic",
+               "config": {"workload": f"{name}: incremental exploration replay, {n_steps} planning steps, per-step changed-block "
+                                      f"commit + {n_total} unfiltered candidates, {cfg.voxel_size} m voxels, {cfg.far_m} m range",
+                          "blocks_uploaded_per_step": blocks / n_steps, "map_update_ms_per_step": up_ms / n_steps,
+                          "map_update_gb_per_s": (blocks / n_steps) * nvox * 12 / (up_ms / n_steps * 1e-3) / 1e9,
+                          "free_edges_per_step": nfree / n_steps,
+                          "note": "a candidate whose edge collides is not swept (rrt.cpp:210-216)",
+                          "timing": "host wall clock over the whole replay, host buffers, max over ranks"},
+               "voxel_steps_per_s": vsteps / total_s, "gpu_launches": int(launches), "clocks": sampler.summary(),
+               "update_kernel_bytes_written_per_step": (blocks / n_steps) * bpb,
+               "e2e": {"value": value, "unit": "viewpoints/s",
+                       "h2d_bytes_per_step": (hi - lo) * 88 + int(blocks / n_steps) * (nvox * 12 + 64),
+                       "d2h_bytes_per_step": (hi - lo) * 13},
+               "best": {k: best[k] for k in ("index", "score", "best_gain", "best_yaw")}}
     g.close()
-    if world > 1:
-        dist.destroy_process_group()
+    return out
+
+
+def run_ours(args):
+    """Headline: BASELINE.json configs[2] ("cfg3": 50x50x10 m office map, 0.10 m voxels, 10,000 candidates), STRONG scaling --
+    the workload north_star's scaling target names.  `extra` carries configs[1] (cfg2: 1,000 candidates, the largest
+    single-GPU configuration of round 1) and configs[4] (cfg5: the incremental replay) measured in the same process.
+    --config cfgN runs one configuration alone (cfg4: every step includes the map replication)."""
+    rig = Rig()
+    head = args.config
+    strong = (args.scaling or ("weak" if head in ("cfg1", "cfg2") else "strong")) == "strong"
+    if head == "cfg5":
+        out = bench_replay(rig, args, head, args.steps)
+    else:
+        out = bench_gain_config(rig, args, head, args.steps, args.warmup, strong, True, include_replication=(head == "cfg4"))
+    extras = [e for e in (args.extra.split(",") if args.extra else []) if e and e != head]
+    extra = {}
+    for e in extras:
+        sub = argparse.Namespace(**vars(args))
+        sub.candidates = 0
+        if e == "cfg5":
+            r = bench_replay(rig, sub, e, min(200, max(args.steps, 50)))
+        else:
+            r = bench_gain_config(rig, sub, e, min(args.steps, 20), args.warmup, True, False, include_replication=(e == "cfg4"))
+        if r is not None:
+            for k in ("dtype", "data", "higher_is_better", "vs_baseline", "metric", "unit"):
+                r.pop(k, None)
+            extra[e] = r
+    if rig.rank == 0:
+        if extra:
+            out["extra"] = extra
+        emit(out)
+    rig.close()
 
 
 # ---- the widened rows (SURVEY.md 8 f-3, f-4) and the reference's shipped geometry: one JSON line each --------------------
@@ -835,16 +908,16 @@ def run_shipped(args):
 
 
 
-def cpu_baseline(args, cfg, h_pos, h_seg):
+def cpu_baseline(args, name, cfg, h_pos, h_seg):
     """The reference's CPU implementation timed on the host cores of this box on a bounded sample of the
     same workload: all threads and one thread (the reference itself plans on a single thread); the faster
     oracle port is reported alongside."""
     from nbv_exploration_planner_b200 import synth
-    m = synth.make_map(args.config)
+    m = synth.make_map(name)
     cam = m.camera()
     cores = os.cpu_count() or 1
     ref = CpuReference(m, cam, cfg, cores)
-    sample = min(len(h_pos), args.cpu_sample or max(cores * 16, 256))
+    sample = min(len(h_pos), args.cpu_sample or max(cores * 8, 128))
     one = min(len(h_pos), 12)
     dt1 = ref.run(h_pos[:one], h_seg[:one], threads=1)
     dta = min(ref.run(h_pos[:sample], h_seg[:sample]) for _ in range(2))
@@ -869,8 +942,6 @@ if __name__ == "__main__":
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
-    elif a.config == "cfg5":
-        run_replay(a)
     elif a.config == "frontier":
         run_frontier(a)
     elif a.config == "interp":

@@ -1,20 +1,18 @@
-"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink on the GPU box,
-gloo in the CPU tests).
+"""Launch plumbing for one-process-per-GPU jobs (``torchrun``): ``torch.distributed`` around the library.
 
-The path shards by *candidates* (SURVEY.md 8e): every rank holds a replica of the map mirror and
-evaluates a contiguous block of the candidate list; there is no collective on the data path of the
-evaluation itself.  Two small exchanges surround it:
+The multi-GPU data path lives INSIDE ``libnbvgpu.so`` (include/nbvgpu.h, "multi-GPU contexts"): candidates sharded over the
+ranks, the map replicated by ``nbvgpu_commit`` with an NCCL broadcast of {descriptor table | payload}, the per-shard best
+records exchanged through GPU stores into shared host memory.  What is left for this module:
 
-  * ``broadcast_blocks``  -- once per planning step rank 0 packs the changed blocks (keys + tile
-    payload) into one device buffer and broadcasts it; every rank applies it with the same
-    insert/scatter kernels (``nbvgpu_layer_update_device``), so the replicas stay identical.
-  * ``gather_sharded``    -- the widened rows (history-graph vertices for the frontier potential, positions for the
-    ESDF interpolation) shard the same way: every rank evaluates a contiguous block of the batch against its replica
-    and the per-item results are all-gathered back into batch order; again no collective on the evaluation itself.
-  * ``gather_best``       -- each rank reduces its shard to one {score, global index, gain, yaw}
-    record on the device (``nbvgpu_gain_eval_best_device``); the 32-byte records are all-gathered
-    and every rank picks the winner with the reference's tie-break (first strict maximum in
-    candidate order, rrt.cpp:243-246).
+  * ``create_context``   -- hand the library's NCCL unique id from rank 0 to the other ranks (one 128-byte broadcast at start-up)
+    and return each rank's ``NbvGpu`` (``nbvgpu_create_rank``); with one rank, a one-device ``nbvgpu_create_multi`` context;
+  * ``shard_bounds``     -- the library's sharding rule, for callers that keep their shard in device memory
+    (``NbvGpu.evaluate_shard_device``);
+  * ``gather_sharded``   -- the widened rows (history-graph vertices for the frontier potential, positions for the ESDF
+    interpolation) shard the same way in a torch program: every rank evaluates a contiguous block of the batch against its
+    replica and the per-item results are all-gathered back into batch order;
+  * ``broadcast_blocks`` / ``gather_best*`` -- the torch-tensor forms of the two exchanges (round 1's data path; kept for
+    callers whose map updates or results already live in torch tensors, and exercised on CPU with gloo).
 """
 from __future__ import annotations
 
@@ -23,6 +21,25 @@ from typing import Optional, Tuple
 import numpy as np
 import torch
 import torch.distributed as dist
+
+
+def create_context(local_device: int, stream=None, group=None):
+    """This rank's ``NbvGpu`` of a multi-GPU context spanning the process group (or a one-device context without one)."""
+    from .planner import NbvGpu
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        g = NbvGpu.multi([local_device])
+    else:
+        rank = dist.get_rank(group)
+        dev = torch.device("cuda", local_device)
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(NbvGpu.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0, group=group)
+        g = NbvGpu.rank(local_device, rank, world, uid.cpu().numpy().tobytes())
+    if stream is not None:
+        g.set_stream(stream)
+    return g
 
 
 def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
@@ -53,6 +70,13 @@ def broadcast_blocks(keys: Optional[np.ndarray], payload: Optional[np.ndarray], 
     if rank == src:
         keys = np.ascontiguousarray(keys, np.int32).reshape(-1, 3)
         n = len(keys)
+        if len(np.unique(keys, axis=0)) != n:
+            raise ValueError("broadcast_blocks: a block index appears twice in one batch")
+        payload = np.ascontiguousarray(payload)
+        if payload.dtype != np.float32:      # PACK_VOXBLOX words: reinterpret the bits, never convert numerically
+            if payload.dtype.itemsize != 4:
+                raise ValueError("payload must be float32 or 32-bit words")
+            payload = payload.view(np.float32)
     else:
         n = 0
     if world > 1:

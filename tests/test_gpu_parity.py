@@ -268,7 +268,8 @@ def test_best_viewpoint_selection(oracle_mod, cfg1_map):
     assert best_i >= 0
     assert r["score"] == pytest.approx(best, rel=GAIN_RTOL)
     assert r["best_gain"] == ro["gain"][best_i] and r["best_yaw"] == ro["yaw"][best_i]
-    assert np.array_equal(r["gain"], ro["gain"]) and np.array_equal(r["yaw_deg"], ro["yaw_deg"])
+    # rrt.cpp:210-216: the gain is only evaluated behind a free edge
+    assert np.array_equal(r["gain"], np.where(free == 1, ro["gain"], 0.0)) and np.array_equal(r["yaw_deg"], np.where(free == 1, ro["yaw_deg"], 0))
     # nothing beats a huge zero_gain -> index -1
     r2 = g.gain_eval_best(lt_g, c.positions, parent_yaw, c.distance, free, v_max, dyaw_max, 1e30)
     assert r2["index"] == -1
