@@ -333,19 +333,27 @@ class Rig:
             self.dist.destroy_process_group()
 
 
-def page_lock(a: np.ndarray):
-    """Page-lock a numpy array in place (cudaHostRegister) so that nbvgpu_layer_update_pinned can copy straight from it;
-    returns something to keep alive.  Falls back to a pinned copy."""
-    import torch
-    a = np.ascontiguousarray(a)
-    try:
-        rc = torch.cuda.cudart().cudaHostRegister(a.ctypes.data, a.nbytes, 0)
-        if int(rc) == 0:
-            return a, a
-    except Exception:
-        pass
-    t = torch.from_numpy(a).pin_memory()
-    return t, t
+class PageLocked:
+    """A numpy array page-locked in place (cudaHostRegister) so that nbvgpu_layer_update_pinned can copy straight from it;
+    release() undoes the registration before the array may be freed (a pinned copy is the fallback)."""
+
+    def __init__(self, a: np.ndarray):
+        import torch
+        self.array = np.ascontiguousarray(a)
+        self.registered = False
+        self.buffer = self.array
+        try:
+            self.registered = int(torch.cuda.cudart().cudaHostRegister(self.array.ctypes.data, self.array.nbytes, 0)) == 0
+        except Exception:
+            self.registered = False
+        if not self.registered:
+            self.buffer = torch.from_numpy(self.array).pin_memory()
+
+    def release(self):
+        import torch
+        if self.registered:
+            torch.cuda.cudart().cudaHostUnregister(self.array.ctypes.data)
+            self.registered = False
 
 
 def shard(n, world, rank):
@@ -383,11 +391,10 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
     nb = rig.bcast_int(len(m.keys) if rank == 0 else 0)
     lt = g.layer_create(LAYER_TSDF, cfg.voxel_size, cfg.vps, nb + 64)
     le = g.layer_create(LAYER_ESDF, cfg.voxel_size, cfg.vps, nb + 64)
-    keep = []
+    locked = []
     if rank == 0:
-        p_tsdf, k1 = page_lock(m.tsdf)
-        p_esdf, k2 = page_lock(m.esdf)
-        keep += [k1, k2]
+        locked = [PageLocked(m.tsdf), PageLocked(m.esdf)]
+        p_tsdf, p_esdf = locked[0].buffer, locked[1].buffer
     map_bytes = nb * cfg.vps ** 3 * 12
 
     def replicate():
@@ -401,6 +408,7 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
 
     rig.barrier()
     repl_ms = [replicate()]
+    setup_repl_ms = repl_ms[0]
     g.set_camera(synth.camera_for(cfg))
     # candidates: grown on rank 0 with the GPU collision check as the acceptance test, then shared
     if rank == 0:
@@ -512,7 +520,8 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
         selfcheck = {"variant_1_equals_default": bool(torch.equal(ref_gain, d_gain) and torch.equal(ref_yaw, d_yaw)), "candidates": n}
         g.set_kernel_variant(args.variant)
 
-    dev_ms_max, e2e_s_max, kern_ms_max, repl_max = rig.reduce([dev_ms, e2e_s, kern_ms, max(repl_timed) if repl_timed else repl_ms[0] if repl_ms else 0.0], "max")
+    repl_med = float(np.median(repl_timed)) if repl_timed else setup_repl_ms
+    dev_ms_max, e2e_s_max, kern_ms_max, repl_max = rig.reduce([dev_ms, e2e_s, kern_ms, repl_med], "max")
     vsteps_all, rays_all, launches_all, n_all, csteps_all, same_all = rig.reduce([vsteps, rays, launches, n, csteps, 0.0 if same else 1.0], "sum")
     clocks = sampler.summary()
     out = None
@@ -521,7 +530,7 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
         peak, peak_src = measured_peaks()
         steps_per_launch = vsteps / max(1, kern_launches)
         ach = steps_per_launch * ALGO_BYTES_PER_STEP / (kern_ms / max(1, kern_launches) * 1e-3) / 1e9
-        first_repl = repl_ms[0] if not repl_timed else float(np.median(repl_timed))
+        first_repl = repl_max
         out = {
             "metric": "candidate viewpoints/s", "value": value, "unit": "viewpoints/s", "n_gpus": world, "steps": steps,
             "warmup": max(warmup, 3), "ms_per_step": dev_ms_max / steps, "higher_is_better": True,
@@ -557,6 +566,8 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
         if with_cpu_baseline and not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(args, name, cfg, h_pos, h_seg)
     g.close()
+    for pl in locked:
+        pl.release()
     return out
 
 
