@@ -259,6 +259,9 @@ typedef struct {
   double robot_radius;     /* system/robot_radius                                                   */
   double v_max, dyaw_max;  /* system/v_max, system/dyaw_max                                         */
   double zero_gain;        /* nbvep/gain/zero                                                       */
+  int32_t sequential;      /* 1: the reference's semantics -- sample i sees the nodes created by samples 0..i-1 of
+                              the batch (kd_insert3 at rrt.cpp:236) as parents; 0: parents are the given nodes only */
+  int32_t reserved;
 } nbvgpu_expand_params;
 /* One batched pass of the body of RrtTree::iterate (rrt.cpp:172-246) over n uniform triples u[n][3] in
  * [0,1) (the caller's RNG replaces the reference's clock-seeded mt19937): sample in the vicinity sphere,
@@ -266,9 +269,14 @@ typedef struct {
  * (node_state[n_nodes][4] = x y z yaw, node_distance[n_nodes]) as parent; clip to extension_range; edge +
  * overshoot through checkMotion; gain (optimized_gain / gain per the camera) for free edges; node score
  * against the parent's yaw and distance; best = first strict maximum over zero_gain in sample order.
- * Parents are existing nodes only: samples of one batch do not see each other (with n = 1 this is exactly
- * one iterate() call).  Per-sample outputs (any may be NULL): status 0 = sample rejected, 1 = edge collides,
- * 2 = node created; pos[n][3]; parent[n]; gain[n]; yaw[n] (radians); distance[n]; score[n]. */
+ * params->sequential = 1 is a faithful replay of n consecutive iterate() calls on the caller's stream of triples: the
+ * order-dependent front half (sample, nearest node among the given AND the already created nodes, clip, checkMotion,
+ * insert) runs sample by sample inside one CTA, the gains are batched, and each score uses its parent's chosen yaw even
+ * when the parent was created by the same call (rrt.cpp:225); parent[i] indexes the given nodes first, then the created
+ * nodes in creation order.  With sequential = 0 parents are the given nodes only (samples of one batch do not see each
+ * other; everything is batched; with n = 1 both modes are exactly one iterate() call).  Per-sample outputs (any may be
+ * NULL): status 0 = sample rejected, 1 = edge collides, 2 = node created; pos[n][3]; parent[n]; gain[n]; yaw[n] (radians);
+ * distance[n]; score[n]. */
 int nbvgpu_expand_tree(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, const nbvgpu_expand_params* params,
                        size_t n_nodes, const double* node_state, const double* node_distance, size_t n,
                        const double* uniforms, uint8_t* status, double* pos, int32_t* parent, double* gain, double* yaw,

@@ -49,7 +49,8 @@ class ExpandParams(C.Structure):
     """nbvgpu_expand_params."""
 
     _fields_ = [("root", C.c_double * 3), ("vicinity", C.c_double), ("extension_range", C.c_double), ("overshoot", C.c_double),
-                ("robot_radius", C.c_double), ("v_max", C.c_double), ("dyaw_max", C.c_double), ("zero_gain", C.c_double)]
+                ("robot_radius", C.c_double), ("v_max", C.c_double), ("dyaw_max", C.c_double), ("zero_gain", C.c_double),
+                ("sequential", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Best(C.Structure):

@@ -1135,35 +1135,33 @@ struct ExpandArgs {
   double* distance;             // [n]
 };
 
-__global__ void __launch_bounds__(128) k_expand_sample(const ExpandArgs a) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n) return;
-  double s[3];
+// rrt.cpp:176-185: the sample of triple i; false when it is rejected (outside the vicinity sphere or the exploration box).
+__device__ __forceinline__ bool expand_sample_point(const ExpandArgs& a, int i, double (&s)[3]) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) s[k] = dmul(dmul(2.0, a.vicinity), dsub(a.uniforms[3 * i + k], 0.5));  // :176-178
   bool ok = !(dadd(dadd(dmul(s[0], s[0]), dmul(s[1], s[1])), dmul(s[2], s[2])) > dmul(a.vicinity, a.vicinity));  // :179
 #pragma unroll
   for (int k = 0; k < 3; ++k) s[k] = dadd(s[k], a.root[k]);                                           // :182
-  ok = ok && s[0] >= a.bbx_min[0] && s[0] <= a.bbx_max[0] && s[1] >= a.bbx_min[1] && s[1] <= a.bbx_max[1] &&
-       s[2] >= a.bbx_min[2] && s[2] <= a.bbx_max[2];                                                  // :183-185
-  a.status[i] = ok ? 1 : 0;
-  if (!ok) {
-    for (int k = 0; k < 3; ++k) a.pos[3 * i + k] = 0.0;
-    for (int k = 0; k < 6; ++k) a.seg[6 * i + k] = 0.0;
-    a.parent[i] = -1;
-    a.parent_yaw[i] = 0.0;
-    a.distance[i] = 0.0;
-    return;
-  }
-  // kd_nearest3 (kdtree.c): squared distance accumulated x, y, z; first minimum
-  int best = 0;
-  double best_d = 0.0;
-  for (int j = 0; j < a.n_nodes; ++j) {
-    const double dx = dsub(a.node_state[4 * j], s[0]), dy = dsub(a.node_state[4 * j + 1], s[1]), dz = dsub(a.node_state[4 * j + 2], s[2]);
-    const double d = dadd(dadd(dadd(0.0, dmul(dx, dx)), dmul(dy, dy)), dmul(dz, dz));
-    if (j == 0 || d < best_d) { best_d = d; best = j; }
-  }
-  const D3 origin{a.node_state[4 * best], a.node_state[4 * best + 1], a.node_state[4 * best + 2]};
+  return ok && s[0] >= a.bbx_min[0] && s[0] <= a.bbx_max[0] && s[1] >= a.bbx_min[1] && s[1] <= a.bbx_max[1] &&
+         s[2] >= a.bbx_min[2] && s[2] <= a.bbx_max[2];                                                // :183-185
+}
+__device__ __forceinline__ void expand_write_rejected(const ExpandArgs& a, int i) {
+  a.status[i] = 0;
+  for (int k = 0; k < 3; ++k) a.pos[3 * i + k] = 0.0;
+  for (int k = 0; k < 6; ++k) a.seg[6 * i + k] = 0.0;
+  a.parent[i] = -1;
+  a.parent_yaw[i] = 0.0;
+  a.distance[i] = 0.0;
+}
+// kd_nearest3 (kdtree.c): squared distance accumulated x, y, z
+__device__ __forceinline__ double expand_dist2(const double* node, const double (&s)[3]) {
+  const double dx = dsub(node[0], s[0]), dy = dsub(node[1], s[1]), dz = dsub(node[2], s[2]);
+  return dadd(dadd(dadd(0.0, dmul(dx, dx)), dmul(dy, dy)), dmul(dz, dz));
+}
+// rrt.cpp:200-212,223: clip to extension_range, new state, edge with overshoot, Node::distance_; writes the per-sample outputs.
+__device__ __forceinline__ void expand_make_edge(const ExpandArgs& a, int i, const double (&s)[3], int best, const double* node_state,
+                                                 const double* node_distance, double (&ns_out)[3], double& dist_out) {
+  const D3 origin{node_state[4 * best], node_state[4 * best + 1], node_state[4 * best + 2]};
   D3 dir = d3sub(D3{s[0], s[1], s[2]}, origin);                                                       // :202-203
   if (__dsqrt_rn(d3dot(dir, dir)) > a.extension_range) {                                              // :204-206
     const D3 un = d3normalized(dir);
@@ -1176,8 +1174,31 @@ __global__ void __launch_bounds__(128) k_expand_sample(const ExpandArgs a) {
   a.seg[6 * i] = origin.x; a.seg[6 * i + 1] = origin.y; a.seg[6 * i + 2] = origin.z;
   a.seg[6 * i + 3] = end.x; a.seg[6 * i + 4] = end.y; a.seg[6 * i + 5] = end.z;
   a.parent[i] = best;
-  a.parent_yaw[i] = a.node_state[4 * best + 3];
-  a.distance[i] = dadd(a.node_distance[best], __dsqrt_rn(d3dot(dir, dir)));                           // :223
+  a.parent_yaw[i] = node_state[4 * best + 3];
+  dist_out = dadd(node_distance[best], __dsqrt_rn(d3dot(dir, dir)));                                  // :223
+  a.distance[i] = dist_out;
+  ns_out[0] = ns.x; ns_out[1] = ns.y; ns_out[2] = ns.z;
+}
+
+__global__ void __launch_bounds__(128) k_expand_sample(const ExpandArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  double s[3];
+  const bool ok = expand_sample_point(a, i, s);
+  a.status[i] = ok ? 1 : 0;
+  if (!ok) {
+    expand_write_rejected(a, i);
+    return;
+  }
+  // first minimum over the existing nodes
+  int best = 0;
+  double best_d = 0.0;
+  for (int j = 0; j < a.n_nodes; ++j) {
+    const double d = expand_dist2(a.node_state + 4 * j, s);
+    if (j == 0 || d < best_d) { best_d = d; best = j; }
+  }
+  double ns[3], dist;
+  expand_make_edge(a, i, s, best, a.node_state, a.node_distance, ns, dist);
 }
 
 // status 1 + free edge -> 2 (node created); valid[i] = (status == 2) for the gain / scoring kernels.
@@ -1268,16 +1289,10 @@ __global__ void __launch_bounds__(128) k_check_segments(LayerView L, float voxel
 // failing step decides, exactly as in the sequential loop (same flag, same count of executed steps).
 struct SegmentByValue { double v[6]; };  // a single segment passed in the launch arguments (seg == nullptr)
 
-__global__ void __launch_bounds__(128) k_check_segments_warp(LayerView L, float voxel_size, double radius,
-                                                             const double* __restrict__ seg, SegmentByValue one, int n,
-                                                             uint8_t* is_free, unsigned long long* totals, unsigned* done,
-                                                             unsigned seq) {
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= n) return;
+// Warp-collective checkMotion of one segment (all 32 lanes call it with the same s6): true = free; *steps = executed steps.
+__device__ __forceinline__ bool segment_free_warp(const LayerView& L, float voxel_size, double radius, const double (&s6)[6], int lane,
+                                                  unsigned long long* steps_out) {
   const int lv = L.log2vps, vm = (1 << lv) - 1;
-  double s6[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) s6[k] = seg ? seg[6 * (size_t)i + k] : one.v[k];
   SegmentWalk w;
   segment_setup(s6, voxel_size, w);
   bool free_seg = w.ok;
@@ -1310,10 +1325,135 @@ __global__ void __launch_bounds__(128) k_check_segments_warp(LayerView L, float 
       steps += (unsigned)cnt;
     }
   }
+  *steps_out = steps;
+  return free_seg;
+}
+
+__global__ void __launch_bounds__(128) k_check_segments_warp(LayerView L, float voxel_size, double radius,
+                                                             const double* __restrict__ seg, SegmentByValue one, int n,
+                                                             uint8_t* is_free, unsigned long long* totals, unsigned* done,
+                                                             unsigned seq) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= n) return;
+  double s6[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) s6[k] = seg ? seg[6 * (size_t)i + k] : one.v[k];
+  unsigned long long steps = 0ull;
+  const bool free_seg = segment_free_warp(L, voxel_size, radius, s6, lane, &steps);
   if (lane == 0) {
     is_free[i] = free_seg ? 1 : 0;
     if (steps) atomicAdd(totals + 2, steps);
     publish_done(done, seq);  // single-segment host calls only (see BestYawArgs::done)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// RrtTree::iterate's front half with the reference's SEQUENTIAL semantics (rrt.cpp:172-212,223,236): sample i finds its
+// parent among the given nodes AND the nodes created by samples 0..i-1 of the same batch, so the cheap, order-dependent
+// part -- sample, nearest node, clip, checkMotion, insert -- runs sample by sample inside ONE CTA (the nearest-node search
+// and the edge's voxel look-ups are what is parallel), and the expensive, order-independent part (the gains) is batched
+// afterwards.  all_state / all_dist hold the given nodes followed by room for n created ones; created_triple[k] = the sample
+// that created node n_nodes + k.
+// ---------------------------------------------------------------------------------------------
+struct ExpandSeqArgs {
+  ExpandArgs a;          // node_state / node_distance are unused here: all_state / all_dist carry the growing tree
+  LayerView E;           // ESDF layer of the edge check
+  float esdf_voxel_size;
+  double radius;
+  double* all_state;     // [(n_nodes + n)][4] x y z yaw (yaw of created nodes filled in by k_expand_parent_yaw)
+  double* all_dist;      // [n_nodes + n]
+  int* created_triple;   // [n]
+  int* n_created;        // [1]
+  uint8_t* valid;        // [n] 1 = node created
+  unsigned long long* totals;
+};
+constexpr int kExpandSeqThreads = 1024;
+
+__global__ void __launch_bounds__(kExpandSeqThreads) k_expand_sequential(const ExpandSeqArgs q) {
+  const ExpandArgs& a = q.a;
+  __shared__ double s_d[32];
+  __shared__ int s_j[32];
+  __shared__ int s_cnt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_cnt = 0;
+  __syncthreads();
+  unsigned long long my_steps = 0ull;
+  for (int i = 0; i < a.n; ++i) {
+    double s[3];
+    const bool ok = expand_sample_point(a, i, s);  // every thread computes the same sample: the branch is uniform
+    if (!ok) {
+      if (tid == 0) {
+        expand_write_rejected(a, i);
+        q.valid[i] = 0;
+      }
+      continue;
+    }
+    // nearest node, first minimum in node order (ties: lowest index)
+    const int total = a.n_nodes + s_cnt;
+    double best_d = 1.0e300;
+    int best = 0x7fffffff;
+    for (int j = tid; j < total; j += kExpandSeqThreads) {
+      const double d = expand_dist2(q.all_state + 4 * j, s);
+      if (d < best_d) { best_d = d; best = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, best_d, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, best, o);
+      if (od < best_d || (od == best_d && oj < best)) { best_d = od; best = oj; }
+    }
+    if (lane == 0) { s_d[warp] = best_d; s_j[warp] = best; }
+    __syncthreads();
+    if (warp == 0) {
+      best_d = s_d[lane];
+      best = s_j[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double od = __shfl_xor_sync(0xffffffffu, best_d, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best, o);
+        if (od < best_d || (od == best_d && oj < best)) { best_d = od; best = oj; }
+      }
+      if (best == 0x7fffffff) best = 0;  // every distance NaN (cannot happen for validated inputs): kd_nearest3 returns a node anyway
+      // edge + collision check + insertion by the first warp (lane 0 does the scalar arithmetic)
+      double ns[3] = {0.0, 0.0, 0.0}, dist = 0.0, s6[6];
+      if (lane == 0) expand_make_edge(a, i, s, best, q.all_state, q.all_dist, ns, dist);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 6; ++k) s6[k] = a.seg[6 * i + k];  // written by lane 0 just above
+      unsigned long long steps = 0ull;
+      const bool free_seg = segment_free_warp(q.E, q.esdf_voxel_size, q.radius, s6, lane, &steps);
+      if (lane == 0) {
+        my_steps += steps;
+        a.status[i] = free_seg ? 2 : 1;
+        q.valid[i] = free_seg ? 1 : 0;
+        if (free_seg) {  // kd_insert3 (rrt.cpp:236)
+          const int node = a.n_nodes + s_cnt;
+          q.all_state[4 * node] = ns[0]; q.all_state[4 * node + 1] = ns[1]; q.all_state[4 * node + 2] = ns[2]; q.all_state[4 * node + 3] = 0.0;
+          q.all_dist[node] = dist;
+          q.created_triple[s_cnt] = i;
+          s_cnt = s_cnt + 1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *q.n_created = s_cnt;
+    if (my_steps) atomicAdd(q.totals + 2, my_steps);
+  }
+}
+
+// After the gains: the yaw each created node chose (state[3] = max_gain_yaw * M_PI / 180.0, rrt.cpp:477) goes into the tree,
+// and every sample's parent_yaw is read from there -- the parent may be a node of the same batch (rrt.cpp:225).
+__global__ void k_expand_parent_yaw(const int32_t* __restrict__ yaw_deg, const int* __restrict__ created_triple, const int* __restrict__ n_created,
+                                    int n_nodes, double* all_state, const int32_t* __restrict__ parent, const uint8_t* __restrict__ valid,
+                                    double* parent_yaw, int n, int phase) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (phase == 0) {
+    if (i < *n_created)
+      all_state[4 * (n_nodes + i) + 3] = __ddiv_rn(dmul((double)yaw_deg[created_triple[i]], 3.14159265358979323846), 180.0);
+  } else if (i < n && valid[i]) {
+    parent_yaw[i] = all_state[4 * parent[i] + 3];
   }
 }
 

@@ -2120,12 +2120,16 @@ int nbvgpu_expand_tree(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, const nb
     best->index = -1; best->score = P->zero_gain; best->gain = 0.0; best->yaw = 0.0;
     return NBVGPU_OK;
   }
-  // device layout (doubles first): nodes [nn*4] | node_dist [nn] | u [n*3] | pos [n*3] | seg [n*6] | pyaw [n] | dist [n] |
-  //                                gain [n] | score [n] | best [4] | parent i32 [n] | yaw_deg i32 [n] | status [n] | free [n] | valid [n]
+  // device layout (doubles first): nodes [(nn+n)*4] | node_dist [nn+n] | u [n*3] | pos [n*3] | seg [n*6] | pyaw [n] | dist [n] |
+  //                                gain [n] | score [n] | best [4] | parent i32 [n] | yaw_deg i32 [n] | created i32 [n] | count i32 [2] |
+  //                                status [n] | free [n] | valid [n]
+  // (the node arrays have room for the n nodes a sequential pass may create)
   const size_t nn = n_nodes;
-  const size_t o_nd = nn * 4, o_u = o_nd + nn, o_pos = o_u + n * 3, o_seg = o_pos + n * 3, o_py = o_seg + n * 6, o_di = o_py + n,
+  const bool seq = P->sequential != 0;
+  const size_t o_nd = (nn + n) * 4, o_u = o_nd + (nn + n), o_pos = o_u + n * 3, o_seg = o_pos + n * 3, o_py = o_seg + n * 6, o_di = o_py + n,
                o_ga = o_di + n, o_sc = o_ga + n, o_be = o_sc + n, n_dbl = o_be + 4;
-  const size_t b_par = n_dbl * 8, b_yd = b_par + n * 4, b_st = b_yd + n * 4, b_fr = b_st + n, b_va = b_fr + n, total = b_va + n;
+  const size_t b_par = n_dbl * 8, b_yd = b_par + n * 4, b_cr = b_yd + n * 4, b_cn = b_cr + n * 4, b_st = b_cn + 8, b_fr = b_st + n,
+               b_va = b_fr + n, total = b_va + n;
   CK(ctx->d_aux.reserve(total + 64));
   CK(ctx->h_io.reserve(total + 64, false));
   char* d = ctx->d_aux.as<char>();
@@ -2134,7 +2138,9 @@ int nbvgpu_expand_tree(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, const nb
   memcpy(h, node_state, nn * 32);
   memcpy(h + o_nd * 8, node_distance, nn * 8);
   memcpy(h + o_u * 8, uniforms, n * 24);
-  CK(cudaMemcpyAsync(d, h, o_pos * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d, h, nn * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d + o_nd * 8, h + o_nd * 8, nn * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(d + o_u * 8, h + o_u * 8, n * 24, cudaMemcpyHostToDevice, ctx->stream));
   ExpandArgs a;
   for (int k = 0; k < 3; ++k) { a.root[k] = P->root[k]; a.bbx_min[k] = ctx->cam.bbx_min[k]; a.bbx_max[k] = ctx->cam.bbx_max[k]; }
   a.vicinity = P->vicinity; a.extension_range = P->extension_range; a.overshoot = P->overshoot;
@@ -2143,19 +2149,48 @@ int nbvgpu_expand_tree(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, const nb
   a.status = reinterpret_cast<uint8_t*>(d + b_st);
   a.pos = dd + o_pos; a.seg = dd + o_seg; a.parent = reinterpret_cast<int32_t*>(d + b_par);
   a.parent_yaw = dd + o_py; a.distance = dd + o_di;
-  k_expand_sample<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a);
-  CK(cudaGetLastError());
-  ctx->stats.kernel_launches++;
   uint8_t* d_free = reinterpret_cast<uint8_t*>(d + b_fr);
   uint8_t* d_valid = reinterpret_cast<uint8_t*>(d + b_va);
-  int rc = enqueue_segments(ctx, LE, P->robot_radius, n, a.seg, d_free);
-  if (rc) return rc;
-  k_expand_status<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a.status, d_free, d_valid, (int)n);
-  CK(cudaGetLastError());
-  ctx->stats.kernel_launches++;
   int32_t* d_yd = reinterpret_cast<int32_t*>(d + b_yd);
+  int* d_created = reinterpret_cast<int*>(d + b_cr);
+  int* d_count = reinterpret_cast<int*>(d + b_cn);
+  int rc;
+  if (seq) {
+    // the reference's sequential semantics: one CTA walks the samples in order (csrc/gain_kernels.cuh: k_expand_sequential)
+    ExpandSeqArgs q;
+    q.a = a;
+    q.E = LE->view();
+    q.esdf_voxel_size = LE->voxel_size;
+    q.radius = P->robot_radius;
+    q.all_state = dd;
+    q.all_dist = dd + o_nd;
+    q.created_triple = d_created;
+    q.n_created = d_count;
+    q.valid = d_valid;
+    q.totals = ctx->d_totals;
+    k_expand_sequential<<<1, kExpandSeqThreads, 0, ctx->stream>>>(q);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+  } else {
+    k_expand_sample<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    rc = enqueue_segments(ctx, LE, P->robot_radius, n, a.seg, d_free);
+    if (rc) return rc;
+    k_expand_status<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a.status, d_free, d_valid, (int)n);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+  }
   rc = enqueue_gain(ctx, LT, n, a.pos, dd + o_ga, d_yd, nullptr, nullptr, nullptr, d_valid);
   if (rc) return rc;
+  if (seq) {  // parents created by this very batch have their yaw only now (rrt.cpp:225 reads newParent->state_[3])
+    for (int phase = 0; phase < 2; ++phase) {
+      k_expand_parent_yaw<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_yd, d_created, d_count, (int)nn, dd, a.parent, d_valid, a.parent_yaw,
+                                                                              (int)n, phase);
+      CK(cudaGetLastError());
+      ctx->stats.kernel_launches++;
+    }
+  }
   static_assert(sizeof(BestRecord) == sizeof(nbvgpu_best), "record layout");
   k_score_best<<<1, 1024, 0, ctx->stream>>>(dd + o_ga, d_yd, a.parent_yaw, a.distance, d_valid, (int)n, P->v_max, P->dyaw_max,
                                             P->zero_gain, reinterpret_cast<BestRecord*>(dd + o_be), dd + o_sc);

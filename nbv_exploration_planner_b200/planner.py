@@ -331,9 +331,12 @@ class NbvGpu:
         return g.value
 
     # -- batched tree expansion --------------------------------------------------
-    def expand_tree(self, tsdf_layer: int, esdf_layer: int, params: dict, node_state, node_distance, uniforms) -> dict:
-        """One batched pass of the body of ``RrtTree::iterate`` (rrt.cpp:172-246) over uniform triples."""
+    def expand_tree(self, tsdf_layer: int, esdf_layer: int, params: dict, node_state, node_distance, uniforms,
+                    sequential: bool = False) -> dict:
+        """One batched pass of the body of ``RrtTree::iterate`` (rrt.cpp:172-246) over uniform triples; ``sequential``:
+        the reference's semantics (every sample sees the nodes created by the samples before it)."""
         P = N.ExpandParams()
+        P.sequential = 1 if sequential else 0
         P.root[:] = [float(v) for v in params["root"]]
         for k in ("vicinity", "extension_range", "overshoot", "robot_radius", "v_max", "dyaw_max", "zero_gain"):
             setattr(P, k, float(params[k]))

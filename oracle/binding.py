@@ -72,6 +72,7 @@ def lib():
                                        C.POINTER(C.c_double), C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_uint8),
                                        C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                        C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]
+        L.nbvo_expand_tree_seq.argtypes = L.nbvo_expand_tree.argtypes
         L.nbvo_cast_ray.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int64), C.c_size_t]
         L.nbvo_cast_ray.restype = C.c_size_t
         L.nbvo_yaw_frame.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double),
@@ -165,7 +166,10 @@ class Oracle:
             raise RuntimeError(f"oracle check_segments failed: {r}")
         return {"free": free, "steps": steps}
 
-    def expand_tree(self, tsdf_layer: int, esdf_layer: int, params: dict, node_state, node_distance, uniforms, threads: int = 1) -> dict:
+    def expand_tree(self, tsdf_layer: int, esdf_layer: int, params: dict, node_state, node_distance, uniforms, threads: int = 1,
+                    sequential: bool = False) -> dict:
+        """sequential: the reference's own semantics -- every sample sees the nodes created by the samples before it
+        (nbvo_expand_tree_seq); otherwise parents are the given nodes only."""
         P = OracleExpandParams()
         P.root[:] = [float(v) for v in params["root"]]
         for k in ("vicinity", "extension_range", "overshoot", "robot_radius", "v_max", "dyaw_max", "zero_gain"):
@@ -177,7 +181,8 @@ class Oracle:
         out = {"status": np.zeros(n, np.uint8), "pos": np.zeros((n, 3)), "parent": np.zeros(n, np.int32), "gain": np.zeros(n),
                "yaw": np.zeros(n), "distance": np.zeros(n), "score": np.zeros(n)}
         best = C.c_int64(-1)
-        r = self._l.nbvo_expand_tree(self._c, tsdf_layer, esdf_layer, C.byref(P), len(ns), _ptr(ns, C.c_double), _ptr(nd, C.c_double),
+        fn = self._l.nbvo_expand_tree_seq if sequential else self._l.nbvo_expand_tree
+        r = fn(self._c, tsdf_layer, esdf_layer, C.byref(P), len(ns), _ptr(ns, C.c_double), _ptr(nd, C.c_double),
                                      n, _ptr(u, C.c_double), _ptr(out["status"], C.c_uint8), _ptr(out["pos"], C.c_double),
                                      _ptr(out["parent"], C.c_int32), _ptr(out["gain"], C.c_double), _ptr(out["yaw"], C.c_double),
                                      _ptr(out["distance"], C.c_double), _ptr(out["score"], C.c_double), C.byref(best), threads)

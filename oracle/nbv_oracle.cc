@@ -890,6 +890,80 @@ int nbvo_expand_tree(void* c_, int tsdf_layer, int esdf_layer, const ExpandParam
   return 0;
 }
 
+// The same stream of triples with the reference's sequential semantics: every RrtTree::iterate() call (rrt.cpp:163-264)
+// sees the nodes the earlier calls inserted (kd_insert3 at :236), as nearest-parent candidates and -- through the parent's
+// chosen yaw, state_[3] -- in the score (:225).  parent[i] indexes the given nodes first, then the created nodes in creation
+// order.  Gains do not depend on other nodes, so they are evaluated in parallel between the two sequential passes.
+int nbvo_expand_tree_seq(void* c_, int tsdf_layer, int esdf_layer, const ExpandParams* P, size_t n_nodes, const double* node_state,
+                         const double* node_distance, size_t n, const double* uniforms, uint8_t* status, double* pos,
+                         int32_t* parent, double* gain, double* yaw, double* distance, double* score, int64_t* best_index,
+                         int n_threads) {
+  Ctx* c = static_cast<Ctx*>(c_);
+  if (!c->cam_set || n_nodes == 0) return -2;
+  const Layer& LT = *c->layers.at(tsdf_layer);
+  const Layer& LE = *c->layers.at(esdf_layer);
+  const Camera& cam = c->cam;
+  const bool sum_all = cam.sum_all_yaws != 0;
+  std::vector<double> nx(node_state, node_state + 4 * n_nodes), nd(node_distance, node_distance + n_nodes);
+  std::vector<size_t> created;  // triples that created a node, in order
+  for (size_t i = 0; i < n; ++i) {
+    status[i] = 0; parent[i] = -1; gain[i] = 0.0; yaw[i] = 0.0; distance[i] = 0.0; score[i] = 0.0;
+    pos[3 * i] = pos[3 * i + 1] = pos[3 * i + 2] = 0.0;
+    double s[3];
+    for (int k = 0; k < 3; ++k) s[k] = 2.0 * P->vicinity * (uniforms[3 * i + k] - 0.5);          // :176-178
+    if (s[0] * s[0] + s[1] * s[1] + s[2] * s[2] > P->vicinity * P->vicinity) continue;          // :179-180
+    for (int k = 0; k < 3; ++k) s[k] += P->root[k];                                             // :182
+    if (!(s[0] >= cam.bbx_min[0] && s[0] <= cam.bbx_max[0] && s[1] >= cam.bbx_min[1] && s[1] <= cam.bbx_max[1] &&
+          s[2] >= cam.bbx_min[2] && s[2] <= cam.bbx_max[2])) continue;                           // :183-185
+    const size_t total = nd.size();
+    size_t best = 0;                                                                            // :190-197
+    double best_d = 0.0;
+    for (size_t j = 0; j < total; ++j) {
+      double d = 0.0;
+      for (int k = 0; k < 3; ++k) { const double df = nx[4 * j + k] - s[k]; d += df * df; }
+      if (j == 0 || d < best_d) { best_d = d; best = j; }
+    }
+    const V3 origin{nx[4 * best], nx[4 * best + 1], nx[4 * best + 2]};
+    V3 dir{s[0] - origin.x, s[1] - origin.y, s[2] - origin.z};                                   // :202-203
+    if (norm(dir) > P->extension_range) dir = scale(P->extension_range, normalized(dir));       // :204-206
+    const V3 ns = add(origin, dir);                                                             // :207-209
+    const V3 un = normalized(dir);
+    const V3 end = add(add(dir, origin), V3{un.x * P->overshoot, un.y * P->overshoot, un.z * P->overshoot});  // :210-212
+    pos[3 * i] = ns.x; pos[3 * i + 1] = ns.y; pos[3 * i + 2] = ns.z;
+    parent[i] = (int32_t)best;
+    const double seg[6] = {origin.x, origin.y, origin.z, end.x, end.y, end.z};
+    status[i] = 1;
+    if (!check_motion(LE, P->robot_radius, seg, nullptr)) continue;
+    status[i] = 2;
+    distance[i] = nd[best] + norm(dir);                                                         // :223
+    nx.insert(nx.end(), {ns.x, ns.y, ns.z, 0.0});                                               // :236 (yaw filled in below)
+    nd.push_back(distance[i]);
+    created.push_back(i);
+  }
+  parallel_for(created.size(), n_threads, [&](size_t k) {
+    const size_t i = created[k];
+    GainOut o{};
+    const double p3[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+    eval_gain(c, LT, p3, sum_all, &o, nullptr);                                                 // :214-219
+    gain[i] = o.gain;
+    yaw[i] = o.yaw;
+  });
+  double bg = P->zero_gain;                                                                     // :243-246
+  int64_t bi = -1;
+  for (size_t k = 0; k < created.size(); ++k) {
+    const size_t i = created[k];
+    nx[4 * (n_nodes + k) + 3] = yaw[i];
+    double dy = yaw[i] - nx[4 * (size_t)parent[i] + 3];                                         // :225
+    if (dy > M_PI) dy -= 2.0 * M_PI;
+    if (dy < -M_PI) dy += 2.0 * M_PI;
+    const double ttr = std::max(dy / P->dyaw_max, distance[i] / P->v_max);                      // :232-233
+    score[i] = gain[i] / ttr;                                                                   // :234
+    if (score[i] > bg) { bg = score[i]; bi = (int64_t)i; }
+  }
+  *best_index = bi;
+  return 0;
+}
+
 // castRay (integrator_utils.h:133-143): returns the number of indices the
 // reference would emit; writes at most `cap` of them.
 size_t nbvo_cast_ray(const float* start, const float* end, int64_t* out, size_t cap) {

@@ -144,6 +144,31 @@ class Reference:
         self.L.nbvr_frontier_potential(self._c, len(pts), _p(pts, C.c_double), _p(gain, C.c_double))
         return gain
 
+    def iterate_stream(self, params: dict, node_state, node_distance, uniforms) -> dict:
+        """The reference's own RrtTree::iterate (rrt.cpp:163-264) with its own kd-tree, called until the stream of uniform
+        triples is used up (nbvr_iterate_stream); same outputs as the oracle's expand_tree(sequential=True)."""
+        ns = np.ascontiguousarray(node_state, np.float64).reshape(-1, 4)
+        nd = np.ascontiguousarray(node_distance, np.float64)
+        u = np.ascontiguousarray(uniforms, np.float64).reshape(-1, 3)
+        n = len(u)
+        out = {"status": np.zeros(n, np.uint8), "pos": np.zeros((n, 3)), "parent": np.zeros(n, np.int32), "gain": np.zeros(n),
+               "yaw": np.zeros(n), "distance": np.zeros(n), "score": np.zeros(n)}
+        best = C.c_int64(-1)
+        root = np.ascontiguousarray(params["root"], np.float64)
+        dp = C.POINTER(C.c_double)
+        f = self.L.nbvr_iterate_stream
+        f.argtypes = [C.c_void_p, dp] + [C.c_double] * 6 + [C.c_size_t, dp, dp, C.c_size_t, dp, C.POINTER(C.c_uint8), dp,
+                                                            C.POINTER(C.c_int32), dp, dp, dp, dp, C.POINTER(C.c_int64)]
+        rc = f(self._c, _p(root, C.c_double), float(params["vicinity"]), float(params["extension_range"]), float(params["overshoot"]),
+               float(params["v_max"]), float(params["dyaw_max"]), float(params["zero_gain"]), len(ns), _p(ns, C.c_double), _p(nd, C.c_double),
+               n, _p(u, C.c_double), _p(out["status"], C.c_uint8), _p(out["pos"], C.c_double), _p(out["parent"], C.c_int32),
+               _p(out["gain"], C.c_double), _p(out["yaw"], C.c_double), _p(out["distance"], C.c_double), _p(out["score"], C.c_double),
+               C.byref(best))
+        if rc != 0:
+            raise RuntimeError(f"nbvr_iterate_stream failed: {rc}")
+        out["best_index"] = best.value
+        return out
+
     def voxel_status_at(self, p) -> int:
         p = np.ascontiguousarray(p, np.float64)
         self.L.nbvr_voxel_status_at.argtypes = [C.c_void_p, C.POINTER(C.c_double)]

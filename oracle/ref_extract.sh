@@ -12,6 +12,7 @@ cut() {  # file first last out expected-first-line-fragment
     echo "reference changed: $1:$2 does not contain '$5'" >&2; exit 1
   fi
 }
+cut nbveplanner/src/rrt.cpp 163 264 rrt_cpp_163_264.inc 'void RrtTree::iterate() {'
 cut nbveplanner/src/rrt.cpp 351 479 rrt_cpp_351_479.inc 'double RrtTree::optimized_gain(Pose &state) {'
 cut nbveplanner/src/rrt.cpp 481 579 rrt_cpp_481_579.inc 'double RrtTree::gain(Pose &state) {'
 cut nbveplanner/src/voxblox_manager.cpp 14 33 voxblox_manager_cpp_14_33.inc 'VoxelStatus VoxbloxManager::getVoxelStatusByIndex('

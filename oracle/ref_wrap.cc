@@ -16,22 +16,31 @@
 //     HighResManager::checkCollisionWithRobotAtVoxel (:121-129), getResolution / getVoxelsPerSide
 //     (voxblox_manager.h:35-37), HighResManager::checkMotion<T> (voxblox_manager.h:89-108),
 //     LowResManager::getVoxelStatus (voxblox_manager.cpp:73-90), convertToString + History::bfs
-//     (history.cpp:96-137), EsdfMap::getDistanceAndGradientAtPosition (voxblox/src/core/esdf_map.cc:22-52);
+//     (history.cpp:96-137), EsdfMap::getDistanceAndGradientAtPosition (voxblox/src/core/esdf_map.cc:22-52),
+//     RrtTree::iterate (rrt.cpp:163-264) with the reference's own kd-tree (kdtree/src/kdtree.c, compiled as a file) --
+//     its clock-seeded std::mt19937 / std::uniform_real_distribution are replaced, by two #defines around the
+//     #include of that range, with a generator that replays the caller's stream of uniforms;
 //   * verbatim as well: voxblox/interpolator/interpolator{,_inl}.h (trilinear interpolation, central-difference
 //     gradient) and voxblox/src/utils/evaluation_utils.cc (isObservedVoxel);
 //   * NOT the reference's: the third-party headers it needs (Eigen, minkindr, glog, protoc output) --
 //     stand-ins under oracle/ref_shim/ restating their published semantics -- and this C glue.
 // Nothing from /root/reference is copied into the repository.
+#include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <fstream>
 #include <memory>
 #include <queue>
+#include <random>
+#include <unordered_map>
 #include <sstream>
 #include <string>
 #include <unordered_set>
 #include <vector>
 
+#include "kdtree.h"  // the reference's own kd-tree (kdtree/include/kdtree/kdtree.h)
 #include "nbveplanner/camera_model.h"
 #include "voxblox/core/layer.h"
 #include "voxblox/integrator/integrator_utils.h"
@@ -64,6 +73,8 @@ struct Params {  // the members of nbveplanner/params.h that the extracted bodie
   double gain_free_ = 0.0, gain_occupied_ = 0.0, gain_unmapped_ = 1.0;
   double robot_radius_ = 0.5;
   Point bbx_min_, bbx_max_;  // params.h: the exploration bounds History::bfs tests against
+  double extension_range_ = 1.0, dist_overshoot_ = 0.5, v_max_ = 1.0, dyaw_max_ = 0.5, zero_gain_ = 0.0;  // RrtTree::iterate
+  bool log_ = false;
 };
 
 class VoxbloxManager {
@@ -94,18 +105,74 @@ class History {
   Params* params_ = nullptr;
 };
 
+class Node {  // nbveplanner/include/nbveplanner/tree.h:17-32, constructor tree.cpp:5-12 (tree.h itself includes ROS headers)
+ public:
+  Pose state_;
+  Node* parent_ = nullptr;
+  std::vector<Node*> children_;
+  double num_unmapped_ = 0.0;
+  double time_to_reach_ = 0.0;
+  double gain_ = 0.0;
+  double distance_ = DBL_MAX;
+  int id_ = -1;
+};
+
 class RrtTree {
  public:
   double optimized_gain(Pose& state);
   double gain(Pose& state);
+  void iterate();
+  void publishNode(Node* node) { last_published_ = node; }  // rrt.cpp publishes an RViz marker here; the wrapper takes note
   VoxbloxManager* manager_lowres_ = nullptr;
+  HighResManager* manager_ = nullptr;
   Params* params_ = nullptr;
+  // TreeBase / RrtTree members iterate() touches (tree.h:34-47, rrt.h)
+  int counter_ = 0;
+  double bestGain_ = 0.0;
+  Node* bestNode_ = nullptr;
+  Node* rootNode_ = nullptr;
+  kdtree* kdTree_ = nullptr;
+  double root_vicinity_ = 0.0;
+  int g_ID_ = 0;
+  std::ofstream file_tree_;
+  Node* last_published_ = nullptr;
 };
 
 #include "extract/voxblox_manager_cpp_14_33.inc"
 #include "extract/voxblox_manager_cpp_121_129.inc"
 #include "extract/rrt_cpp_351_479.inc"
 #include "extract/rrt_cpp_481_579.inc"
+}  // namespace nbveplanner
+
+// RrtTree::iterate draws from a clock-seeded std::mt19937 through std::uniform_real_distribution (rrt.cpp:172-178).  For a
+// reproducible comparison the two names are redirected, for the lines of iterate() only, to a generator that hands out the
+// caller's uniforms in order and throws when the stream is exhausted.
+struct nbv_stream_end {};
+struct nbv_uniform_stream {
+  const double* u = nullptr;
+  size_t n = 0, next = 0;
+};
+static nbv_uniform_stream g_stream;
+namespace std {
+struct nbv_stream_rng {
+  template <class T>
+  explicit nbv_stream_rng(T) {}
+};
+template <class T>
+struct nbv_stream_dist {
+  nbv_stream_dist(T, T) {}
+  T operator()(nbv_stream_rng&) {
+    if (g_stream.next >= g_stream.n) throw nbv_stream_end{};
+    return g_stream.u[g_stream.next++];
+  }
+};
+}  // namespace std
+namespace nbveplanner {
+#define mt19937 nbv_stream_rng
+#define uniform_real_distribution nbv_stream_dist
+#include "extract/rrt_cpp_163_264.inc"
+#undef mt19937
+#undef uniform_real_distribution
 #include "extract/voxblox_manager_cpp_73_90.inc"
 #include "extract/history_cpp_96_137.inc"
 
@@ -141,6 +208,7 @@ void* nbvr_create(float tsdf_voxel_size, int tsdf_vps, float esdf_voxel_size, in
   c->hires_tsdf.reset(new voxblox::Layer<voxblox::TsdfVoxel>(esdf_voxel_size, esdf_vps));
   c->high.tsdf_layer_ = c->hires_tsdf.get();
   c->tree.manager_lowres_ = &c->low;
+  c->tree.manager_ = &c->high;
   c->tree.params_ = &c->params;
   c->esdf_map.reset(new voxblox::EsdfMap(c->esdf.get()));
   c->history.manager_lowres_ = &c->low;
@@ -216,6 +284,67 @@ void nbvr_gain_eval(void* c_, size_t n, const double* pos, int sum_all, double* 
     gain[i] = sum_all ? c->tree.gain(state) : c->tree.optimized_gain(state);
     yaw[i] = state[3];
   }
+}
+// RrtTree::iterate (rrt.cpp:163-264), called again and again on a tree that starts with the n_nodes given nodes (inserted
+// into the reference's kd-tree in order), drawing from the stream of n triples `uniforms` until it is used up.  Per triple:
+// status 0 = rejected by the sphere / bounds test, 1 = accepted but the edge collides (no node), 2 = node created; for
+// created nodes position, parent (index: given nodes first, then created nodes in creation order), num_unmapped_ (gain),
+// state_[3] (yaw), distance_, gain_ (score).  *best_index = triple of TreeBase::bestNode_ (-1: none above zero_gain).
+int nbvr_iterate_stream(void* c_, const double* root, double vicinity, double extension_range, double overshoot, double v_max,
+                        double dyaw_max, double zero_gain, size_t n_nodes, const double* node_state, const double* node_distance,
+                        size_t n, const double* uniforms, uint8_t* status, double* pos, int32_t* parent, double* gain, double* yaw,
+                        double* distance, double* score, int64_t* best_index) {
+  RefCtx* c = static_cast<RefCtx*>(c_);
+  nbveplanner::RrtTree& T = c->tree;
+  nbveplanner::Params& P = c->params;
+  P.extension_range_ = extension_range; P.dist_overshoot_ = overshoot; P.v_max_ = v_max; P.dyaw_max_ = dyaw_max; P.zero_gain_ = zero_gain;
+  T.root_vicinity_ = vicinity;
+  T.bestGain_ = zero_gain;  // TreeBase::TreeBase, tree.cpp:26
+  T.bestNode_ = nullptr;
+  T.counter_ = 0;
+  T.kdTree_ = kd_create(3);
+  std::vector<std::unique_ptr<nbveplanner::Node>> nodes;  // flat ownership (Node::~Node of the reference deletes children)
+  std::unordered_map<const nbveplanner::Node*, int64_t> index, triple_of;
+  nbveplanner::Node root_node;
+  root_node.state_ = nbveplanner::Pose(root[0], root[1], root[2], 0.0);
+  T.rootNode_ = &root_node;
+  for (size_t j = 0; j < n_nodes; ++j) {
+    nodes.emplace_back(new nbveplanner::Node);
+    nbveplanner::Node* nd = nodes.back().get();
+    nd->state_ = nbveplanner::Pose(node_state[4 * j], node_state[4 * j + 1], node_state[4 * j + 2], node_state[4 * j + 3]);
+    nd->distance_ = node_distance[j];
+    index[nd] = (int64_t)j;
+    kd_insert3(T.kdTree_, nd->state_.x(), nd->state_.y(), nd->state_.z(), nd);
+  }
+  for (size_t i = 0; i < n; ++i) { status[i] = 0; parent[i] = -1; gain[i] = yaw[i] = distance[i] = score[i] = 0.0; pos[3 * i] = pos[3 * i + 1] = pos[3 * i + 2] = 0.0; }
+  g_stream.u = uniforms; g_stream.n = 3 * n; g_stream.next = 0;
+  size_t created = 0;
+  try {
+    for (;;) {
+      T.last_published_ = nullptr;
+      T.iterate();
+      const size_t t = g_stream.next / 3 - 1;  // the triple that passed the sphere / bounds tests
+      if (T.last_published_) {
+        nbveplanner::Node* nd = T.last_published_;
+        nodes.emplace_back(nd);                 // iterate() allocated it with new
+        index[nd] = (int64_t)(n_nodes + created++);
+        triple_of[nd] = (int64_t)t;
+        status[t] = 2;
+        pos[3 * t] = nd->state_[0]; pos[3 * t + 1] = nd->state_[1]; pos[3 * t + 2] = nd->state_[2];
+        parent[t] = (int32_t)index.at(nd->parent_);
+        gain[t] = nd->num_unmapped_; yaw[t] = nd->state_[3]; distance[t] = nd->distance_; score[t] = nd->gain_;
+      } else {
+        status[t] = 1;
+      }
+    }
+  } catch (const nbv_stream_end&) {
+  }
+  *best_index = T.bestNode_ ? triple_of.at(T.bestNode_) : -1;
+  for (auto& nd : nodes) nd->children_.clear();
+  kd_free(T.kdTree_);
+  T.kdTree_ = nullptr;
+  T.rootNode_ = nullptr;
+  return 0;
 }
 void nbvr_check_segments(void* c_, size_t n, const double* seg, uint8_t* is_free) {
   RefCtx* c = static_cast<RefCtx*>(c_);

@@ -77,3 +77,40 @@ def test_expand_tree_sum_all_mode_and_edge_cases(oracle_mod, tiny_map):
     _check(g.expand_tree(lt_g, le_g, params, state, dist, u), o.expand_tree(lt_o, le_o, params, state, dist, u, threads=8))
     assert len(g.expand_tree(lt_g, le_g, params, state, dist, np.zeros((0, 3)))["status"]) == 0
     g.close()
+
+
+@pytest.mark.parametrize("which,n", [("tiny", 64), ("tiny", 400), ("cfg1", 300)])
+def test_sequential_expand_tree_matches_oracle(oracle_mod, tiny_map, cfg1_map, which, n):
+    """nbvgpu_expand_params.sequential = 1: n consecutive iterate() calls on one stream of triples -- every sample sees the
+    nodes the samples before it created (as parent, and through the parent's chosen yaw in its score).  Bit-equal to the
+    oracle's sequential restatement, which tests/test_ref_pinning.py pins against the reference's own rrt.cpp:163-264 with its
+    own kd-tree."""
+    m = tiny_map if which == "tiny" else cfg1_map
+    cfg = m.cfg
+    cam = m.camera()
+    o, lt_o, le_o = load_oracle(oracle_mod, m, cam)
+    g, lt_g, le_g = load_gpu(m, cam)
+    rng = np.random.default_rng(19 + n)
+    state, dist = _tree(cfg, o, le_o, lt_o, 6, rng)
+    params = {"root": cfg.root, "vicinity": cfg.vicinity, "extension_range": cfg.extension_range, "overshoot": cfg.overshoot,
+              "robot_radius": cfg.robot_radius, "v_max": 1.0, "dyaw_max": 0.75, "zero_gain": 0.0}
+    u = rng.random((n, 3))
+    ro = o.expand_tree(lt_o, le_o, params, state, dist, u, threads=16, sequential=True)
+    rg = g.expand_tree(lt_g, le_g, params, state, dist, u, sequential=True)
+    _check(rg, ro)
+    made = ro["status"] == 2
+    assert (ro["parent"][made] >= len(state)).sum() >= made.sum() // 3      # many parents were created by the same call
+    # scores of children of same-batch parents really use that parent's yaw
+    kids = np.nonzero(made & (ro["parent"] >= len(state)))[0]
+    created = np.nonzero(made)[0]
+    for i in kids[:10]:
+        p_triple = created[ro["parent"][i] - len(state)]
+        dy = ro["yaw"][i] - ro["yaw"][p_triple]
+        dy = dy - 2 * np.pi if dy > np.pi else (dy + 2 * np.pi if dy < -np.pi else dy)
+        assert rg["score"][i] == ro["gain"][i] / max(dy / 0.75, ro["distance"][i] / 1.0)
+    # the independent mode gives a different tree from the same stream; n = 1 is the same in both modes
+    ind = g.expand_tree(lt_g, le_g, params, state, dist, u)
+    assert not np.array_equal(ind["parent"], rg["parent"])
+    one_s, one_i = g.expand_tree(lt_g, le_g, params, state, dist, u[:1], sequential=True), g.expand_tree(lt_g, le_g, params, state, dist, u[:1])
+    _check(one_s, one_i)
+    g.close()

@@ -321,3 +321,32 @@ def test_esdf_distance_and_gradient_match_reference_interpolator(tiny_map, which
     assert np.array_equal(ro["distance"], rr["distance"]) and np.array_equal(ro["gradient"], rr["gradient"])
     assert 0.1 < ro["ok"].mean() < 0.95 and np.abs(ro["gradient"][ro["ok"] == 1]).max() > 0.5   # both outcomes, real gradients
 
+
+
+@pytest.mark.parametrize("which", ["tiny", "cfg1"])
+def test_sequential_tree_expansion_matches_reference_iterate(tiny_map, cfg1_map, which):
+    """RrtTree::iterate (rrt.cpp:163-264), the reference's own lines with its own kd-tree (kdtree.c), called until a stream of
+    uniform triples is used up -- only its clock-seeded RNG is replaced by that stream.  The oracle's sequential restatement
+    (nbvo_expand_tree_seq) must create the same nodes: which triples are rejected / collide / create a node, and for every
+    created node position, parent (among the given nodes AND the nodes created earlier in the stream), num_unmapped_,
+    state_[3], distance_, gain_; and the same bestNode_."""
+    m = tiny_map if which == "tiny" else cfg1_map
+    cfg = m.cfg
+    o, lt, le, r = _both(m, m.camera(), cfg.robot_radius)
+    P = {"root": cfg.root, "vicinity": cfg.vicinity, "extension_range": cfg.extension_range, "overshoot": cfg.overshoot,
+         "robot_radius": cfg.robot_radius, "v_max": 1.0, "dyaw_max": 0.5, "zero_gain": 0.0}
+    rng = np.random.default_rng(31)
+    nodes = np.array([[*cfg.root, 0.3], [cfg.root[0] + 0.5, cfg.root[1] - 0.2, cfg.root[2], -1.0]])
+    nd = np.array([0.0, 0.55])
+    u = rng.random((240 if which == "tiny" else 96, 3))
+    a = o.expand_tree(lt, le, P, nodes, nd, u, threads=8, sequential=True)
+    b = r.iterate_stream(P, nodes, nd, u)
+    assert np.array_equal(a["status"], b["status"]) and a["best_index"] == b["best_index"] and a["best_index"] >= 0
+    made = a["status"] == 2
+    for k in ("pos", "parent", "gain", "yaw", "distance", "score"):
+        assert np.array_equal(a[k][made], b[k][made]), k
+    assert made.sum() >= 20 and (a["status"] == 1).sum() >= 1 and (a["status"] == 0).sum() >= 1
+    assert (a["parent"][made] >= len(nodes)).sum() >= 10      # parents created earlier in the same stream
+    # and the independent mode differs: the intra-batch dependence is real
+    ind = o.expand_tree(lt, le, P, nodes, nd, u, threads=8, sequential=False)
+    assert not np.array_equal(ind["parent"][made], a["parent"][made])
