@@ -14,6 +14,7 @@
 #include <map>
 #include <atomic>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -177,6 +178,17 @@ struct nbvgpu_ctx {
   int device = 0;
   Group* group = nullptr;  // multi-GPU context: shared by its members; the public handle is member 0 of this process
   int member = 0;          // index among the members in this process
+  // Re-entrancy (gain_eval from the planner thread, check_segments from planner and history threads,
+  // layer_update / commit from the map thread).  Evaluators hold map_mu shared for the duration of their call and run on a
+  // LANE: the context itself when its mutex is free, else one of its lane contexts -- same device, same layers, camera
+  // tables and counters (shared pointers), own high-priority stream, own staging and scratch -- so a 12 us checkMotion from
+  // the history thread does not queue behind the planner thread's 26 ms gain batch.  What changes the snapshot (commit,
+  // layer_create / clear, set_camera, ...) takes map_mu exclusively: it waits for the evaluators in flight and they for it.
+  nbvgpu_ctx* owner = nullptr;       // lane contexts: the context they belong to (whose shared state they alias)
+  std::vector<nbvgpu_ctx*> lanes;    // extra lanes, created on demand (guarded by lane_mu)
+  std::mutex lane_mu, err_mu, stage_mu;
+  std::shared_mutex map_mu;
+  bool lane_async_work = false;      // a lane has un-synchronised work in flight (none of today's lane paths leaves any)
   cudaStream_t own_stream = nullptr, stream = nullptr;
   std::mutex mu;
   std::string err;
@@ -255,17 +267,24 @@ struct Group {
 
 namespace {
 
+// errors are reported on the public handle, whichever lane the call ran on
+void set_err(nbvgpu_ctx* ctx, const std::string& msg) {
+  if (!ctx) return;
+  nbvgpu_ctx* o = ctx->owner ? ctx->owner : ctx;
+  std::lock_guard<std::mutex> lk(o->err_mu);
+  o->err = msg;
+}
 #define CK(call)                                                                                   \
   do {                                                                                             \
     cudaError_t e_ = (call);                                                                       \
     if (e_ != cudaSuccess) {                                                                       \
-      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                               \
+      set_err(ctx, std::string(#call) + ": " + cudaGetErrorString(e_));                            \
       return NBVGPU_ERR_CUDA;                                                                      \
     }                                                                                              \
   } while (0)
 
 int fail(nbvgpu_ctx* ctx, int code, const char* msg) {
-  if (ctx) ctx->err = msg;
+  set_err(ctx, msg);
   return code;
 }
 
@@ -1074,7 +1093,7 @@ nbvgpu_ctx* stage_owner(nbvgpu_ctx* ctx) {
 }
 
 int gfail(nbvgpu_ctx* ctx, int code, const std::string& msg) {
-  ctx->err = msg;
+  set_err(ctx, msg);
   return code;
 }
 #define NCK(call)                                                                                              \
@@ -1090,8 +1109,12 @@ int gfail(nbvgpu_ctx* ctx, int code, const std::string& msg) {
 int group_commit(nbvgpu_ctx* ctx) {
   Group* G = ctx->group;
   std::lock_guard<std::mutex> glk(G->mu);
-  if (!nccl().ok) return gfail(ctx, NBVGPU_ERR_STATE, "NCCL unavailable: " + nccl().error);
+  if (G->world > 1 && !nccl().ok) return gfail(ctx, NBVGPU_ERR_STATE, "NCCL unavailable: " + nccl().error);
   nbvgpu_ctx* root = G->rank0 == 0 ? G->local[0] : nullptr;
+  std::vector<std::unique_lock<std::shared_mutex>> excl;  // no evaluator runs on any member (or its lanes) while the snapshot changes
+  for (nbvgpu_ctx* m : G->local) excl.emplace_back(m->map_mu);
+  std::unique_lock<std::mutex> stage_lock;
+  if (root) stage_lock = std::unique_lock<std::mutex>(root->stage_mu);
   SharedBlock* S = G->shared.host;
   const unsigned long long seq = ++G->commit_seq;
   std::vector<ChunkPlan> plans;
@@ -1274,8 +1297,15 @@ int group_evaluate(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double radiu
   Group* G = ctx->group;
   std::lock_guard<std::mutex> glk(G->mu);
   nbvgpu_ctx* m0 = G->local[0];
+  // every member is held for the whole call: its staging area carries this call's results until they are collected (a
+  // concurrent single call on the handle goes to a lane of the first member meanwhile)
+  std::vector<std::shared_lock<std::shared_mutex>> maps;
+  std::vector<std::unique_lock<std::mutex>> held;
+  for (nbvgpu_ctx* m : G->local) {
+    maps.emplace_back(m->map_mu);
+    held.emplace_back(m->mu);
+  }
   {
-    std::lock_guard<std::mutex> lk(m0->mu);
     LayerHost* L = get_layer(m0, tsdf_layer, NBVGPU_LAYER_TSDF);
     if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
     if (seg && !get_layer(m0, esdf_layer, NBVGPU_LAYER_ESDF)) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
@@ -1298,7 +1328,6 @@ int group_evaluate(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double radiu
       group_post_empty(G, rank, seq);
       continue;
     }
-    std::lock_guard<std::mutex> lk(m->mu);
     const BestPost post{&G->d_shared[i]->best[seq & 1u][rank], (long long)lo, seq};
     const int rc = evaluate_host_enqueue(m, tsdf_layer, esdf_layer, radius, hi - lo, pos + 3 * lo, seg ? seg + 6 * lo : nullptr,
                                          parent_yaw + lo, distance + lo, edge_free_in ? edge_free_in + lo : nullptr, v_max, dyaw_max,
@@ -1311,7 +1340,6 @@ int group_evaluate(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double radiu
       size_t lo, hi;
       shard_bounds(n, G->world, G->rank0 + (int)i, &lo, &hi);
       if (hi == lo) continue;
-      std::lock_guard<std::mutex> lk(m->mu);
       DeviceGuard guard(m->device);
       if (cudaStreamSynchronize(m->stream) != cudaSuccess) return gfail(ctx, NBVGPU_ERR_CUDA, "evaluation failed on a member GPU");
       evaluate_host_collect(m, hi - lo, seg != nullptr, seg == nullptr && edge_free_in != nullptr, edge_free ? edge_free + lo : nullptr, nullptr,
@@ -1357,15 +1385,19 @@ const char* nbvgpu_version(void) { return "nbvgpu 0.1 (sm_100a)"; }
 
 static void destroy_member(nbvgpu_ctx* ctx) {
   if (!ctx) return;
+  for (nbvgpu_ctx* lane : ctx->lanes) destroy_member(lane);
+  ctx->lanes.clear();
   {
     DeviceGuard guard(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    for (LayerHost* L : ctx->layers) free_layer(L);
-    cudaFree(ctx->d_A);
-    cudaFree(ctx->d_B);
-    cudaFree(ctx->d_cs);
-    cudaFree(ctx->d_totals);
-    cudaFree(ctx->d_lstate);
+    if (!ctx->owner) {  // a lane only borrows the layers, camera tables and counters of its owner
+      for (LayerHost* L : ctx->layers) free_layer(L);
+      cudaFree(ctx->d_A);
+      cudaFree(ctx->d_B);
+      cudaFree(ctx->d_cs);
+      cudaFree(ctx->d_totals);
+      cudaFree(ctx->d_lstate);
+    }
     ctx->stage.arena.release();
     for (int i = 0; i < 2; ++i) {
       ctx->h_table[i].release();
@@ -1435,6 +1467,88 @@ static int create_member_impl(int device, nbvgpu_ctx** out) {
 
 
 int nbvgpu_create(int device, nbvgpu_ctx** out) { return create_member_impl(device, out); }
+
+// ---- lanes ----------------------------------------------------------------------------------------------------------
+// What a lane shares with its owner; refreshed whenever the owner changes it (under the exclusive map lock).
+static void lane_refresh(const nbvgpu_ctx* P, nbvgpu_ctx* L) {
+  L->layers = P->layers;
+  L->cam_set = P->cam_set;
+  L->cam = P->cam;
+  L->tab = P->tab;
+  L->cam_gen = P->cam_gen;
+  L->variant = P->variant;
+}
+static void lanes_refresh(nbvgpu_ctx* P) {
+  std::lock_guard<std::mutex> lk(P->lane_mu);
+  for (nbvgpu_ctx* L : P->lanes) lane_refresh(P, L);
+}
+static nbvgpu_ctx* create_lane(nbvgpu_ctx* P) {
+  nbvgpu_ctx* L = new nbvgpu_ctx();
+  L->owner = P;
+  L->device = P->device;
+  L->sm_count = P->sm_count;
+  L->max_smem_optin = P->max_smem_optin;
+  L->force_yc = P->force_yc; L->dense_budget = P->dense_budget; L->smem_pad = P->smem_pad;
+  L->no_fuse = P->no_fuse; L->no_small = P->no_small; L->no_poll = P->no_poll; L->no_wide_cta = P->no_wide_cta;
+  L->d_A = P->d_A; L->d_B = P->d_B; L->d_cs = P->d_cs; L->d_totals = P->d_totals; L->d_lstate = P->d_lstate;
+  DeviceGuard guard(P->device);
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);  // hi = the numerically lowest value = the highest priority
+  if (cudaStreamCreateWithPriority(&L->own_stream, cudaStreamNonBlocking, hi) != cudaSuccess) {
+    cudaGetLastError();
+    delete L;
+    return nullptr;
+  }
+  L->stream = L->own_stream;
+  lane_refresh(P, L);
+  return L;
+}
+
+// An evaluator's hold on the context for the duration of one call: the snapshot (shared) and a lane (exclusive).
+struct Lease {
+  nbvgpu_ctx* ctx = nullptr;  // where the call runs: the context itself or one of its lanes (null: no lane could be made)
+  std::shared_lock<std::shared_mutex> map;
+  std::unique_lock<std::mutex> lk;
+  explicit Lease(nbvgpu_ctx* primary, bool may_use_lane = true) : map(primary->map_mu) {
+    lk = std::unique_lock<std::mutex>(primary->mu, std::try_to_lock);
+    if (lk.owns_lock()) {
+      ctx = primary;
+      return;
+    }
+    if (!may_use_lane || std::getenv("NBVGPU_NO_LANES")) {
+      lk.lock();
+      ctx = primary;
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> pool(primary->lane_mu);
+      for (nbvgpu_ctx* L : primary->lanes) {
+        lk = std::unique_lock<std::mutex>(L->mu, std::try_to_lock);
+        if (lk.owns_lock()) {
+          ctx = L;
+          return;
+        }
+      }
+      if (primary->lanes.size() < 8) {
+        nbvgpu_ctx* L = create_lane(primary);
+        if (L) {
+          primary->lanes.push_back(L);
+          lk = std::unique_lock<std::mutex>(L->mu);
+          ctx = L;
+          return;
+        }
+      }
+    }
+    lk = std::unique_lock<std::mutex>(primary->mu);  // the pool is exhausted: queue on the context itself
+    ctx = primary;
+  }
+};
+// A snapshot-changing call's hold: nobody evaluates meanwhile.
+struct Exclusive {
+  std::unique_lock<std::shared_mutex> map;
+  std::unique_lock<std::mutex> lk;
+  explicit Exclusive(nbvgpu_ctx* primary) : map(primary->map_mu), lk(primary->mu) {}
+};
 
 void nbvgpu_destroy(nbvgpu_ctx* ctx) {
   if (!ctx) return;
@@ -1562,7 +1676,7 @@ int nbvgpu_set_stream(nbvgpu_ctx* ctx, void* cuda_stream) {
   if (!ctx) return NBVGPU_ERR_INVALID;
   if (ctx->group && ctx->group->local.size() > 1 && cuda_stream)
     return fail(ctx, NBVGPU_ERR_STATE, "a context that spans several GPUs of one process keeps its own streams");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Exclusive ex(ctx);
   DeviceGuard guard(ctx->device);
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
@@ -1604,7 +1718,7 @@ int nbvgpu_layer_create(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, si
   return NBVGPU_OK;
 }
 static int layer_create_one(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps, size_t max_blocks, int* layer_out) {
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Exclusive ex(ctx);
   if (kind != NBVGPU_LAYER_TSDF && kind != NBVGPU_LAYER_ESDF) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer kind");
   if (!(voxel_size > 0.f) || !std::isfinite(voxel_size)) return fail(ctx, NBVGPU_ERR_INVALID, "bad voxel size");
   if (vps < 4 || vps > 32 || (vps & (vps - 1))) return fail(ctx, NBVGPU_ERR_INVALID, "voxels_per_side must be 4, 8, 16 or 32");
@@ -1650,6 +1764,7 @@ static int layer_create_one(nbvgpu_ctx* ctx, int kind, float voxel_size, int vps
   CK(cudaGetLastError());
   ctx->layers.push_back(L);
   *layer_out = (int)ctx->layers.size() - 1;
+  lanes_refresh(ctx);
   return NBVGPU_OK;
 }
 
@@ -1692,7 +1807,8 @@ int nbvgpu_layer_update(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* key
   if (!ctx || (n && (!keys || !payload))) return NBVGPU_ERR_INVALID;
   nbvgpu_ctx* r = stage_owner(ctx);
   if (!r) return fail(ctx, NBVGPU_ERR_STATE, "map updates are staged on rank 0 of a multi-process context");
-  std::lock_guard<std::mutex> lk(r->mu);
+  std::shared_lock<std::shared_mutex> sm(r->map_mu);  // staging runs beside the evaluators: it touches host memory only
+  std::lock_guard<std::mutex> lk(r->stage_mu);
   return stage_update(r, layer, n, keys, payload, packing, false);
 }
 
@@ -1700,14 +1816,15 @@ int nbvgpu_layer_update_pinned(nbvgpu_ctx* ctx, int layer, size_t n, const int32
   if (!ctx || (n && (!keys || !payload))) return NBVGPU_ERR_INVALID;
   nbvgpu_ctx* r = stage_owner(ctx);
   if (!r) return fail(ctx, NBVGPU_ERR_STATE, "map updates are staged on rank 0 of a multi-process context");
-  std::lock_guard<std::mutex> lk(r->mu);
+  std::shared_lock<std::shared_mutex> sm(r->map_mu);
+  std::lock_guard<std::mutex> lk(r->stage_mu);
   return stage_update(r, layer, n, keys, payload, packing, true);
 }
 
 int nbvgpu_layer_update_device(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* d_keys, const void* d_payload, int packing) {
   if (!ctx || (n && (!d_keys || !d_payload))) return NBVGPU_ERR_INVALID;
   if (ctx->group) return fail(ctx, NBVGPU_ERR_STATE, "device-resident updates address one GPU: use a single-GPU context");
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Exclusive ex(ctx);
   LayerHost* L = get_layer(ctx, layer, -1);
   if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
   if (packing != NBVGPU_PACK_PLANAR && packing != NBVGPU_PACK_VOXBLOX) return fail(ctx, NBVGPU_ERR_INVALID, "bad packing");
@@ -1730,7 +1847,8 @@ int nbvgpu_layer_remove(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* key
   if (!ctx || (n && !keys)) return NBVGPU_ERR_INVALID;
   nbvgpu_ctx* r = stage_owner(ctx);
   if (!r) return fail(ctx, NBVGPU_ERR_STATE, "map updates are staged on rank 0 of a multi-process context");
-  std::lock_guard<std::mutex> lk(r->mu);
+  std::shared_lock<std::shared_mutex> sm(r->map_mu);
+  std::lock_guard<std::mutex> lk(r->stage_mu);
   LayerHost* L = get_layer(r, layer, -1);
   if (!L) return fail(r, NBVGPU_ERR_INVALID, "bad layer");
   for (size_t i = 0; i < 3 * n; ++i)
@@ -1740,11 +1858,14 @@ int nbvgpu_layer_remove(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* key
 }
 
 static int layer_clear_one(nbvgpu_ctx* ctx, int layer) {
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Exclusive ex(ctx);
   LayerHost* L = get_layer(ctx, layer, -1);
   if (!L) return fail(ctx, NBVGPU_ERR_INVALID, "bad layer");
   DeviceGuard guard(ctx->device);
-  ctx->stage.drop_layer(layer);
+  {
+    std::lock_guard<std::mutex> sl(ctx->stage_mu);
+    ctx->stage.drop_layer(layer);
+  }
   const uint32_t nthreads = L->cap > (uint32_t)L->max_blocks ? L->cap : (uint32_t)L->max_blocks;
   k_reset_table<<<(nthreads + 255) / 256, 256, 0, ctx->stream>>>(L->d_table, L->cap, L->d_free_list, (int)L->max_blocks, L->d_state);
   ctx->stats.kernel_launches++;
@@ -1767,7 +1888,8 @@ int nbvgpu_layer_clear(nbvgpu_ctx* ctx, int layer) {
 int nbvgpu_commit(nbvgpu_ctx* ctx) {
   if (!ctx) return NBVGPU_ERR_INVALID;
   if (ctx->group) return group_commit(ctx);
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Exclusive ex(ctx);  // waits for the evaluators in flight; they wait for the new snapshot
+  std::lock_guard<std::mutex> sl(ctx->stage_mu);
   DeviceGuard guard(ctx->device);
   return commit_single(ctx);
 }
@@ -1900,7 +2022,7 @@ int nbvgpu_set_camera(nbvgpu_ctx* ctx, const nbvgpu_camera* cam) {
   return NBVGPU_OK;
 }
 static int set_camera_one(nbvgpu_ctx* ctx, const nbvgpu_camera* cam) {
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Exclusive ex(ctx);
   nbvgpu_host::CameraTables tab;
   if (!nbvgpu_host::build_camera_tables(*cam, &tab)) return fail(ctx, NBVGPU_ERR_INVALID, "invalid camera parameters");
   DeviceGuard guard(ctx->device);
@@ -1913,6 +2035,7 @@ static int set_camera_one(nbvgpu_ctx* ctx, const nbvgpu_camera* cam) {
   CK(cudaMemcpyAsync(ctx->d_cs, ctx->tab.cs, sizeof(ctx->tab.cs), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->cam_set = true;
+  lanes_refresh(ctx);
   return NBVGPU_OK;
 }
 
@@ -1943,7 +2066,8 @@ int nbvgpu_gain_eval(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, do
 }
 static int gain_eval_one(nbvgpu_ctx* ctx, int layer, size_t n, const double* pos, double* gain, int32_t* yaw_deg, uint64_t* counts,
                          uint32_t* per_yaw, uint64_t* steps) {
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Lease lease(ctx);
+  ctx = lease.ctx;
   if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
@@ -2022,7 +2146,8 @@ int nbvgpu_gain_eval_best(nbvgpu_ctx* ctx, int layer, size_t n, const double* po
   if (ctx->group)
     return group_evaluate(ctx, layer, -1, 0.0, n, pos, nullptr, parent_yaw, distance, edge_free, v_max, dyaw_max, zero_gain, nullptr, best,
                           gain, yaw_deg);
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Lease lease(ctx);
+  ctx = lease.ctx;
   if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
@@ -2055,7 +2180,8 @@ int nbvgpu_evaluate_candidates(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, 
   if (ctx->group)
     return group_evaluate(ctx, tsdf_layer, esdf_layer, robot_radius, n, pos, seg, parent_yaw, distance, nullptr, v_max, dyaw_max, zero_gain,
                           edge_free, best, gain, yaw_deg);
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Lease lease(ctx);
+  ctx = lease.ctx;
   LayerHost* L = get_layer(ctx, tsdf_layer, NBVGPU_LAYER_TSDF);
   LayerHost* E = get_layer(ctx, esdf_layer, NBVGPU_LAYER_ESDF);
   if (!L || !E) return fail(ctx, NBVGPU_ERR_STATE, "needs a TSDF and an ESDF layer");
@@ -2233,7 +2359,8 @@ int nbvgpu_check_segments(nbvgpu_ctx* ctx, int layer, double radius, size_t n, c
   return group_fan_out(ctx, n, [&](nbvgpu_ctx* m, size_t lo, size_t hi) { return check_segments_one(m, layer, radius, hi - lo, seg + 6 * lo, is_free + lo); });
 }
 static int check_segments_one(nbvgpu_ctx* ctx, int layer, double radius, size_t n, const double* seg, uint8_t* is_free) {
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Lease lease(ctx);
+  ctx = lease.ctx;
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_ESDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
   if (n == 0) return NBVGPU_OK;
@@ -2294,7 +2421,8 @@ static EsdfView esdf_view_of(const LayerHost* L) {
 int nbvgpu_esdf_distance_gradient(nbvgpu_ctx* ctx, int layer, size_t n, const double* positions, uint8_t* ok, double* distance,
                                   double* gradient) {
   if (!ctx || (n && (!positions || !ok || !distance || !gradient))) return NBVGPU_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Lease lease(ctx);
+  ctx = lease.ctx;
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_ESDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
   if (n == 0) return NBVGPU_OK;
@@ -2376,7 +2504,8 @@ static double sqrt_le_threshold(double d) {
 int nbvgpu_frontier_potential(nbvgpu_ctx* ctx, int layer, size_t n, const double* points, double max_distance, double* potential_gain,
                               uint64_t* frontier_voxels, uint64_t* visited_cells, uint64_t* cells_checksum) {
   if (!ctx || (n && (!points || !potential_gain))) return NBVGPU_ERR_INVALID;
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Lease lease(ctx);
+  ctx = lease.ctx;
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
   if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "set the camera first: its bounding box is the exploration bounds the flood fill respects");
@@ -2641,6 +2770,14 @@ static int get_stats_one(nbvgpu_ctx* ctx, nbvgpu_stats* out) {
   ctx->stats.voxel_steps = t[1];
   ctx->stats.collision_steps = t[2];
   *out = ctx->stats;
+  {  // host-side counters of the lanes (the device-side ones above are shared)
+    std::lock_guard<std::mutex> pool(ctx->lane_mu);
+    for (nbvgpu_ctx* L : ctx->lanes) {
+      out->kernel_launches += L->stats.kernel_launches;
+      out->blocks_uploaded += L->stats.blocks_uploaded;
+      out->bytes_uploaded += L->stats.bytes_uploaded;
+    }
+  }
   return NBVGPU_OK;
 }
 
@@ -2685,13 +2822,15 @@ int nbvgpu_set_kernel_variant(nbvgpu_ctx* ctx, int variant) {
   if (!ctx || variant < 0 || variant > 5) return NBVGPU_ERR_INVALID;
   if (ctx->group) {
     for (nbvgpu_ctx* m : ctx->group->local) {
-      std::lock_guard<std::mutex> lk(m->mu);
+      Exclusive ex(m);
       m->variant = variant;
+      lanes_refresh(m);
     }
     return NBVGPU_OK;
   }
-  std::lock_guard<std::mutex> lk(ctx->mu);
+  Exclusive ex(ctx);
   ctx->variant = variant;
+  lanes_refresh(ctx);
   return NBVGPU_OK;
 }
 

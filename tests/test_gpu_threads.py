@@ -104,3 +104,61 @@ def test_torch_stream_ordering(tiny_map):
         g.gain_eval_device(lt, 64, pos, gain)
         torch.cuda.synchronize()
     g.close()
+
+
+def test_check_motion_does_not_queue_behind_a_gain_batch(oracle_mod, cfg1_map):
+    """SURVEY.md 8b / history.cpp:249,461,555: the history thread calls checkMotion while the planner thread has a large gain
+    batch in flight.  The batch holds the context's own lane; the small call takes a lane context (own high-priority stream,
+    own staging) and must come back in tens of microseconds, not after the batch -- with the right answers on both sides."""
+    import time
+    from nbv_exploration_planner_b200 import synth
+    m, cfg = cfg1_map, synth.CONFIGS["cfg2"]
+    cam = m.camera()
+    from conftest import load_gpu
+    g, lt, le = load_gpu(m, cam)
+    o, lt_o, le_o = load_oracle(oracle_mod, m, cam)
+    big = synth.make_candidates(cfg, 10000, None).positions          # ~14 ms of ray sweep per call
+    c = synth.make_candidates(cfg, 64, None)
+    free_o = o.check_segments(le_o, cfg.robot_radius, c.segments)["free"]
+    gain_ref = g.gain_eval(lt, big[:2000])["gain"]
+    # idle latency of the single call
+    for i in range(20):
+        g.check_motion(le, cfg.robot_radius, c.segments[i, :3], c.segments[i, 3:])
+    idle = []
+    for i in range(200):
+        t0 = time.perf_counter()
+        g.check_motion(le, cfg.robot_radius, c.segments[i % 64, :3], c.segments[i % 64, 3:])
+        idle.append(time.perf_counter() - t0)
+    stop, errors, batch_ms = threading.Event(), [], []
+
+    def planner():
+        try:
+            while not stop.is_set():
+                t0 = time.perf_counter()
+                r = g.gain_eval(lt, big, steps=False)
+                batch_ms.append((time.perf_counter() - t0) * 1e3)
+                if not np.array_equal(r["gain"][:2000], gain_ref):
+                    errors.append(AssertionError("gain batch disturbed"))
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    th = threading.Thread(target=planner)
+    th.start()
+    time.sleep(0.05)                                                  # the batch loop is running
+    busy, wrong = [], 0
+    for i in range(400):
+        t0 = time.perf_counter()
+        f = g.check_motion(le, cfg.robot_radius, c.segments[i % 64, :3], c.segments[i % 64, 3:])
+        busy.append(time.perf_counter() - t0)
+        wrong += int(f != bool(free_o[i % 64]))
+        time.sleep(0.0005)
+    stop.set()
+    th.join()
+    assert not errors, errors
+    assert wrong == 0
+    med_idle, med_busy = np.median(idle) * 1e6, np.median(busy) * 1e6
+    print(f"check_motion latency: idle {med_idle:.1f} us, with a {np.median(batch_ms):.1f} ms gain batch in flight {med_busy:.1f} us "
+          f"(p90 {np.percentile(busy, 90) * 1e6:.1f} us), {len(batch_ms)} batches")
+    assert len(batch_ms) >= 5 and np.median(batch_ms) > 5.0           # there really was a long batch in flight
+    assert med_busy < 40.0, (med_idle, med_busy)                      # VERDICT r1 #7: < 40 us (a queued call would take milliseconds)
+    g.close()
