@@ -349,6 +349,11 @@ int nbvgpu_debug_fused_launches(nbvgpu_ctx* ctx, uint64_t* count);
  * shared-memory volume of a yaw chunk needs more than a quarter but at most half of an SM's shared memory (fine voxels
  * under a tall exploration box; NBVGPU_NO_WIDE_CTA=1 in the environment keeps the slot-grid sweep instead); for tests. */
 int nbvgpu_debug_wide_cta_launches(nbvgpu_ctx* ctx, uint64_t* count);
+/* Planning steps, since the context was created, that ran as ONE cudaGraphLaunch: nbvgpu_evaluate_candidates[_device],
+ * nbvgpu_evaluate_shard_device and nbvgpu_gain_eval_best run eagerly the first time a shape (sizes, buffers, layers, camera,
+ * parameters) is seen, are captured into a CUDA graph the second time and replayed from then on (copies of the host-buffer
+ * forms included); shapes that synchronise inside (the z-clipped volume) stay eager.  NBVGPU_NO_GRAPH=1 disables it. */
+int nbvgpu_debug_graph_replays(nbvgpu_ctx* ctx, uint64_t* count);
 /* Host-only helper for tests: the largest double x with sqrt(x) <= d (round to nearest).  The flood fill tests
  * `squared distance <= threshold` instead of `(candidate - point).norm() <= max_distance` (history.cpp:118): the two are
  * equivalent because the square root is monotone and correctly rounded.  NBVGPU_ERR_INVALID for negative or non-finite d. */

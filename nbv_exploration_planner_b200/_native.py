@@ -140,6 +140,7 @@ def lib() -> C.CDLL:
     L.nbvgpu_debug_dense_clipped_launches.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.nbvgpu_debug_fused_launches.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.nbvgpu_debug_wide_cta_launches.argtypes = [vp, C.POINTER(C.c_uint64)]
+    L.nbvgpu_debug_graph_replays.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.nbvgpu_probe_l2_read_bandwidth.argtypes = [vp, C.c_size_t, C.c_int, C.POINTER(C.c_double)]
     L.nbvgpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.nbvgpu_set_kernel_variant.argtypes = [vp, C.c_int]
@@ -178,5 +179,5 @@ ABI_SYMBOLS = [
     "nbvgpu_check_segments_device", "nbvgpu_check_motion", "nbvgpu_get_stats", "nbvgpu_set_kernel_variant",
     "nbvgpu_debug_classifier_mismatches", "nbvgpu_set_profiling", "nbvgpu_profile_collect",
     "nbvgpu_layer_load_voxblox_file", "nbvgpu_layer_apply_layer_msg", "nbvgpu_parse_blocks", "nbvgpu_expand_tree",
-    "nbvgpu_frontier_potential", "nbvgpu_esdf_distance_gradient", "nbvgpu_esdf_distance_gradient_device", "nbvgpu_evaluate_candidates", "nbvgpu_evaluate_candidates_device", "nbvgpu_debug_round_decimal6", "nbvgpu_debug_sqrt_threshold", "nbvgpu_debug_frontier_hash_redo", "nbvgpu_debug_dense_clipped_launches", "nbvgpu_debug_fused_launches", "nbvgpu_debug_wide_cta_launches", "nbvgpu_probe_l2_read_bandwidth",
+    "nbvgpu_frontier_potential", "nbvgpu_esdf_distance_gradient", "nbvgpu_esdf_distance_gradient_device", "nbvgpu_evaluate_candidates", "nbvgpu_evaluate_candidates_device", "nbvgpu_debug_round_decimal6", "nbvgpu_debug_sqrt_threshold", "nbvgpu_debug_frontier_hash_redo", "nbvgpu_debug_dense_clipped_launches", "nbvgpu_debug_fused_launches", "nbvgpu_debug_wide_cta_launches", "nbvgpu_debug_graph_replays", "nbvgpu_probe_l2_read_bandwidth",
 ]

@@ -1046,16 +1046,18 @@ struct BestRecord {
 // Multi-GPU contexts: where the record of this GPU's shard is also posted -- a 64-byte slot in host memory that every rank
 // of the context can read (csrc/multi_gpu.h: BestSlot), index made global, the evaluation's sequence number stored last.
 struct BestPost {
-  void* slot;               // null: single-GPU context, nothing is posted
+  void* slot;               // this rank's slot of parity 0 (null: single-GPU context, nothing is posted)
+  unsigned stride;          // bytes from there to its slot of parity 1: evaluation `seq` uses slot (seq & 1)
   long long index_offset;   // first candidate of this GPU's shard
-  unsigned seq;
+  const unsigned* seq_src;  // host word (mapped) holding the evaluation's sequence number: read by the kernel, so that a
+                            // captured graph of the step can be replayed without touching its kernel arguments
 };
 
 __global__ void __launch_bounds__(1024) k_score_best(const double* __restrict__ gain, const int32_t* __restrict__ yaw_deg,
                                                      const double* __restrict__ parent_yaw, const double* __restrict__ distance,
                                                      const uint8_t* __restrict__ edge_free, int n, double v_max, double dyaw_max,
                                                      double zero_gain, BestRecord* out, double* score_out = nullptr,
-                                                     const BestPost post = BestPost{nullptr, 0, 0u}) {
+                                                     const BestPost post = BestPost{nullptr, 0u, 0, nullptr}) {
   __shared__ double s_score[32];
   __shared__ int s_idx[32];
   double best = zero_gain;
@@ -1104,11 +1106,13 @@ __global__ void __launch_bounds__(1024) k_score_best(const double* __restrict__ 
       }
       if (out) *out = r;
       if (post.slot) {  // record first, system-wide fence, then the ticket the hosts poll
-        volatile BestRecord* s = reinterpret_cast<volatile BestRecord*>(post.slot);
+        const unsigned seq = *reinterpret_cast<const volatile unsigned*>(post.seq_src);
+        char* const slot = reinterpret_cast<char*>(post.slot) + (seq & 1u) * post.stride;
+        volatile BestRecord* s = reinterpret_cast<volatile BestRecord*>(slot);
         s->index = r.index >= 0 ? r.index + post.index_offset : -1;
         s->score = r.score; s->gain = r.gain; s->yaw = r.yaw;
         __threadfence_system();
-        *reinterpret_cast<volatile unsigned*>(reinterpret_cast<char*>(post.slot) + 32) = post.seq;
+        *reinterpret_cast<volatile unsigned*>(slot + 32) = seq;
       }
     }
   }

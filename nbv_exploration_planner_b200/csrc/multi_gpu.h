@@ -116,6 +116,7 @@ struct SharedBlock {
   unsigned pad0[13];
   BestSlot best[2][kMaxRanks];     // alternating by evaluation parity: a fast rank may start evaluation s+1 while a slow one
                                    // still reads the records of evaluation s
+  unsigned seq_in[kMaxRanks];      // written by each rank's host before it launches evaluation `seq`, read by its scoring kernel
   // commits
   alignas(64) std::atomic<unsigned long long> commit_seq;   // published by the root after the plan below is complete
   alignas(64) std::atomic<unsigned long long> commit_ack[kMaxRanks];  // last commit each rank has read the plan of

@@ -245,6 +245,23 @@ struct nbvgpu_ctx {
   unsigned long long stats_dense_clipped = 0;  // ray-sweep launches that used the z-clipped dense volume (tests)
   int dense_budget = 55 * 1024;  // shared memory per CTA the dense volume path may use (NBVGPU_DENSE_KB)
   int smem_pad = 0;              // extra dynamic shared memory per CTA (NBVGPU_SMEM_PAD_KB; occupancy experiments)
+  // CUDA graphs of the planning step (edge check -> ray sweep -> window scan -> scoring, with the copies of the host-buffer
+  // form): the first call with a given shape runs eagerly (allocations, caches, function attributes come into being), the
+  // second is captured, every later one is a single cudaGraphLaunch.  The key holds everything baked into the nodes.
+  struct StepGraph {
+    unsigned long long key[28];
+    int state = 0;  // 0 seen once (ran eagerly), 1 ready, 2 eager only (capture was refused)
+    cudaGraphExec_t exec = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;  // profiling: external event-record nodes around the sweep
+    bool timing_pending = false;
+    unsigned long long launches_per_replay = 0, last_use = 0;
+  };
+  std::vector<StepGraph> graphs;
+  bool capturing = false, no_graph = false;
+  cudaEvent_t cap_ev0 = nullptr, cap_ev1 = nullptr;  // the events of the graph being captured
+  unsigned long long graph_clock = 0, stats_graph_replays = 0;
+  double prof_graph_ms = 0.0;
+  unsigned long long prof_graph_n = 0;
   // optional CUDA-event timing of the ray-sweep kernel (nbvgpu_set_profiling)
   bool profiling = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
@@ -532,6 +549,7 @@ int check_position_range(const nbvgpu_ctx* ctx, const LayerHost* L, size_t n, co
 
 // Batches up to this size take the small-batch paths: inputs read and results written in place in mapped pinned host
 // memory (no copy operations in the stream) and, on the dense sweep, the window scan fused into the sweep's last CTA.
+constexpr int kErrEager = -100;  // internal: this step cannot be captured into a CUDA graph (it synchronises); run it eagerly
 constexpr size_t kFusedMaxCandidates = 64;
 constexpr size_t kSmallBatch = 64;
 // Edge checks up to this size run one warp per segment: the walk is a chain of dependent L2 round trips (block probe, then
@@ -703,6 +721,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   a.vez = a.vwords = 0;
   if ((variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0) {
     if (ctx->dense_gen != ctx->cam_gen || ctx->dense_vs != L->voxel_size) {
+      if (ctx->capturing) return kErrEager;
       CK(cudaStreamSynchronize(ctx->stream));  // cached tables may still be in use
       for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
       ctx->dense_info.clear();
@@ -713,6 +732,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     auto info_for = [&](int c, const nbvgpu_ctx::DenseInfo** out) -> int {
       auto it = ctx->dense_info.find(c);
       if (it == ctx->dense_info.end()) {
+        if (ctx->capturing) return kErrEager;  // builds a table and synchronises: not inside a stream capture
         nbvgpu_ctx::DenseInfo info;
         std::vector<int> vmin((size_t)(360 / c) * 5);
         info.ok = nbvgpu_host::dense_volume_bounds(T, a.vs, c, vmin.data(), &info.vez, &info.vwords);
@@ -742,7 +762,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     if (!few_rows && ctx->force_yc <= 0 && !ctx->no_wide_cta && n * 4 >= (size_t)ctx->sm_count * 8) {
       for (int c : {90, 72}) {
         const nbvgpu_ctx::DenseInfo* di = nullptr;
-        if (info_for(c, &di)) return NBVGPU_ERR_CUDA;
+        if (const int ri = info_for(c, &di)) return ri;
         if (!di->ok || di->vwords >= (1 << 24)) continue;
         const size_t need = dense_smem_bytes(c, (int)gn, (int)di->vwords);
         if (need <= (size_t)std::min(ctx->max_smem_optin, 2 * ctx->dense_budget + 2048)) {
@@ -757,7 +777,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
       if (dense) break;
       if (c > yc) continue;
       const nbvgpu_ctx::DenseInfo* dip = nullptr;
-      if (info_for(c, &dip)) return NBVGPU_ERR_CUDA;
+      if (const int ri = info_for(c, &dip)) return ri;
       const nbvgpu_ctx::DenseInfo& di = *dip;
       if (!di.ok || di.vwords >= (1 << 24)) continue;
       const size_t need = dense_smem_bytes(c, (int)gn, (int)di.vwords);
@@ -774,6 +794,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     // box, where no voxel can count.  Clipped to the box slab (+- 3 voxels, plus the rows the rays start in) it may; how
     // many rows that takes depends on the candidates' heights, so their z-range is read back first (one tiny kernel and
     // one synchronise -- only on this path, i.e. only when the alternative is the slower slot-grid kernel).
+    if (ctx->capturing) return kErrEager;
     CK(ctx->d_zrange.reserve(64));
     int* d_zr = ctx->d_zrange.as<int>();
     const int init[2] = {INT_MAX, INT_MIN};
@@ -848,7 +869,9 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   smem += (size_t)ctx->smem_pad;
   cudaError_t e;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  if (ctx->profiling) {
+  if (ctx->profiling && ctx->capturing) {
+    CK(cudaEventRecordWithFlags(ctx->cap_ev0, ctx->stream, cudaEventRecordExternal));  // an event-record NODE of the graph
+  } else if (ctx->profiling) {
     if (ctx->prof_used == ctx->prof_events.size()) {
       cudaEvent_t a0, a1;
       CK(cudaEventCreate(&a0));
@@ -912,6 +935,7 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
       break;
   }
   if (ev1) cudaEventRecord(ev1, ctx->stream);
+  if (ctx->profiling && ctx->capturing) cudaEventRecordWithFlags(ctx->cap_ev1, ctx->stream, cudaEventRecordExternal);
   CK(e);
   ctx->stats.kernel_launches++;
   if (fused) {
@@ -950,7 +974,7 @@ int enqueue_segments(nbvgpu_ctx* ctx, LayerHost* L, double radius, size_t n, con
 
 int best_device_nolock(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_pos, const double* d_parent_yaw,
                        const double* d_distance, const uint8_t* d_edge_free, double v_max, double dyaw_max, double zero_gain,
-                       nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg, const BestPost post = BestPost{nullptr, 0, 0u}) {
+                       nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg, const BestPost post = BestPost{nullptr, 0u, 0, nullptr}) {
   if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
   LayerHost* L = get_layer(ctx, layer, NBVGPU_LAYER_TSDF);
   if (!L) return fail(ctx, NBVGPU_ERR_STATE, "not a TSDF layer");
@@ -981,7 +1005,7 @@ int best_device_nolock(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_pos
 int evaluate_device_nolock(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double radius, size_t n, const double* d_pos,
                            const double* d_seg, const double* d_parent_yaw, const double* d_distance, double v_max,
                            double dyaw_max, double zero_gain, uint8_t* d_edge_free, nbvgpu_best* d_best, double* d_gain,
-                           int32_t* d_yaw_deg, const BestPost post = BestPost{nullptr, 0, 0u}) {
+                           int32_t* d_yaw_deg, const BestPost post = BestPost{nullptr, 0u, 0, nullptr}) {
   LayerHost* E = get_layer(ctx, esdf_layer, NBVGPU_LAYER_ESDF);
   if (!E) return fail(ctx, NBVGPU_ERR_STATE, "not an ESDF layer");
   if (!ctx->cam_set) return fail(ctx, NBVGPU_ERR_STATE, "camera not set");
@@ -1007,6 +1031,116 @@ int evaluate_device_nolock(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, doub
                                             zero_gain, reinterpret_cast<BestRecord*>(d_best), nullptr, post);
   CK(cudaGetLastError());
   ctx->stats.kernel_launches++;
+  return NBVGPU_OK;
+}
+
+// ---- CUDA graphs of the planning step --------------------------------------------------------------------------------
+struct StepKey {
+  unsigned long long v[28];
+  int n = 0;
+  StepKey() { memset(v, 0, sizeof v); }
+  void add(unsigned long long x) { if (n < 28) v[n++] = x; }
+  void add(const void* p) { add((unsigned long long)(uintptr_t)p); }
+  void add(double d) { unsigned long long x; memcpy(&x, &d, 8); add(x); }
+};
+// What every step bakes into its nodes beside its own arguments: stream, camera generation, kernel variant, profiling
+// mode, the layers' tables (a rehash replaces them) and the scratch buffers enqueue_gain uses.
+StepKey step_key_base(const nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer) {
+  StepKey k;
+  k.add((const void*)ctx->stream);
+  k.add(ctx->cam_gen);
+  k.add((unsigned long long)ctx->variant | ((unsigned long long)ctx->profiling << 8));
+  k.add((unsigned long long)(unsigned)tsdf_layer | ((unsigned long long)(unsigned)esdf_layer << 32));
+  const LayerHost* L = tsdf_layer >= 0 && tsdf_layer < (int)ctx->layers.size() ? ctx->layers[tsdf_layer] : nullptr;
+  const LayerHost* E = esdf_layer >= 0 && esdf_layer < (int)ctx->layers.size() ? ctx->layers[esdf_layer] : nullptr;
+  k.add(L ? (const void*)L->d_table : nullptr);
+  k.add(E ? (const void*)E->d_table : nullptr);
+  k.add(ctx->d_per_yaw.p);
+  k.add(ctx->d_gain.p);
+  k.add(ctx->d_yaw.p);
+  return k;
+}
+void destroy_step_graph(nbvgpu_ctx::StepGraph& g) {
+  if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (g.ev0) cudaEventDestroy(g.ev0);
+  if (g.ev1) cudaEventDestroy(g.ev1);
+  g.exec = nullptr;
+  g.ev0 = g.ev1 = nullptr;
+}
+// Accumulate the sweep time of a profiled graph's previous replay (its events are re-recorded by the next one).
+void harvest_graph_timing(nbvgpu_ctx* ctx, nbvgpu_ctx::StepGraph& g) {
+  if (!g.timing_pending) return;
+  g.timing_pending = false;
+  float ms = 0.f;
+  if (cudaEventSynchronize(g.ev1) == cudaSuccess && cudaEventElapsedTime(&ms, g.ev0, g.ev1) == cudaSuccess) {
+    ctx->prof_graph_ms += ms;
+    ctx->prof_graph_n++;
+  } else {
+    cudaGetLastError();
+  }
+}
+// Run the stream work of a step: eagerly the first time a key is seen, captured the second time, replayed afterwards.
+template <class F>
+int with_step_graph(nbvgpu_ctx* ctx, const StepKey& key, F enqueue) {
+  if (ctx->no_graph || ctx->capturing) return enqueue();
+  nbvgpu_ctx::StepGraph* g = nullptr;
+  for (nbvgpu_ctx::StepGraph& c : ctx->graphs)
+    if (memcmp(c.key, key.v, sizeof c.key) == 0) { g = &c; break; }
+  ++ctx->graph_clock;
+  if (!g) {
+    if (ctx->graphs.size() >= 16) {  // evict the least recently used
+      size_t victim = 0;
+      for (size_t i = 1; i < ctx->graphs.size(); ++i)
+        if (ctx->graphs[i].last_use < ctx->graphs[victim].last_use) victim = i;
+      harvest_graph_timing(ctx, ctx->graphs[victim]);
+      destroy_step_graph(ctx->graphs[victim]);
+      ctx->graphs.erase(ctx->graphs.begin() + victim);
+    }
+    nbvgpu_ctx::StepGraph fresh;
+    memcpy(fresh.key, key.v, sizeof fresh.key);
+    fresh.last_use = ctx->graph_clock;
+    ctx->graphs.push_back(fresh);
+    return enqueue();
+  }
+  g->last_use = ctx->graph_clock;
+  if (g->state == 2) return enqueue();
+  if (g->state == 0) {
+    if (ctx->profiling) {
+      if (cudaEventCreate(&g->ev0) != cudaSuccess || cudaEventCreate(&g->ev1) != cudaSuccess) { g->state = 2; cudaGetLastError(); return enqueue(); }
+      ctx->cap_ev0 = g->ev0;
+      ctx->cap_ev1 = g->ev1;
+    }
+    const unsigned long long launches0 = ctx->stats.kernel_launches;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      g->state = 2;
+      return enqueue();
+    }
+    ctx->capturing = true;
+    const int rc = enqueue();
+    ctx->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ee = cudaStreamEndCapture(ctx->stream, &graph);
+    cudaGraphExec_t exec = nullptr;
+    if (rc == NBVGPU_OK && ee == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+      g->exec = exec;
+      g->launches_per_replay = ctx->stats.kernel_launches - launches0;
+      ctx->stats.kernel_launches = launches0;  // nothing ran yet: the replay below counts
+      g->state = 1;
+      cudaGraphDestroy(graph);
+    } else {  // not capturable (a synchronising branch, an allocation, ...): this shape stays eager
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      ctx->stats.kernel_launches = launches0;
+      g->state = 2;
+      return enqueue();
+    }
+  }
+  if (g->ev0) harvest_graph_timing(ctx, *g);
+  CK(cudaGraphLaunch(g->exec, ctx->stream));
+  if (g->ev0) g->timing_pending = true;
+  ctx->stats.kernel_launches += g->launches_per_replay;
+  ctx->stats_graph_replays++;
   return NBVGPU_OK;
 }
 
@@ -1049,22 +1183,31 @@ int evaluate_host_enqueue(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, doubl
   memcpy(h + lay.o_par, parent_yaw, n * 8);
   memcpy(h + lay.o_dist, distance, n * 8);
   if (lay.with_free) memcpy(h + lay.o_free, edge_free_in, n);
-  if (lay.in_bytes) CK(cudaMemcpyAsync(d, h, lay.in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  int rc;
-  if (seg)
-    rc = evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, radius, n, reinterpret_cast<double*>(d), reinterpret_cast<double*>(d + lay.o_seg),
-                                reinterpret_cast<double*>(d + lay.o_par), reinterpret_cast<double*>(d + lay.o_dist), v_max, dyaw_max,
-                                zero_gain, reinterpret_cast<uint8_t*>(dr + lay.r_free), reinterpret_cast<nbvgpu_best*>(dr),
-                                reinterpret_cast<double*>(dr + lay.r_gain), reinterpret_cast<int32_t*>(dr + lay.r_yaw), post);
-  else
-    rc = best_device_nolock(ctx, tsdf_layer, n, reinterpret_cast<double*>(d), reinterpret_cast<double*>(d + lay.o_par),
-                            reinterpret_cast<double*>(d + lay.o_dist), lay.with_free ? reinterpret_cast<uint8_t*>(d + lay.o_free) : nullptr,
-                            v_max, dyaw_max, zero_gain, reinterpret_cast<nbvgpu_best*>(dr), reinterpret_cast<double*>(dr + lay.r_gain),
-                            reinterpret_cast<int32_t*>(dr + lay.r_yaw), post);
-  if (rc) return rc;
-  const size_t back = outputs ? (seg ? lay.out_bytes : lay.r_free) : (post.slot ? 0 : sizeof(nbvgpu_best));
-  if (back) CK(cudaMemcpyAsync(h + lay.in_bytes, dr, back, cudaMemcpyDeviceToHost, ctx->stream));
-  return NBVGPU_OK;
+  // everything from here on is stream work with fixed addresses: one CUDA graph per shape
+  StepKey key = step_key_base(ctx, tsdf_layer, seg ? esdf_layer : -1);
+  key.add((unsigned long long)n | ((unsigned long long)(seg != nullptr) << 40) | ((unsigned long long)lay.with_free << 41) |
+          ((unsigned long long)outputs << 42) | (1ull << 48));
+  key.add(h); key.add(d); key.add(dr);
+  key.add(radius); key.add(v_max); key.add(dyaw_max); key.add(zero_gain);
+  key.add(post.slot); key.add((unsigned long long)post.index_offset); key.add(post.seq_src);
+  return with_step_graph(ctx, key, [&]() -> int {
+    if (lay.in_bytes) CK(cudaMemcpyAsync(d, h, lay.in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    int rc;
+    if (seg)
+      rc = evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, radius, n, reinterpret_cast<double*>(d), reinterpret_cast<double*>(d + lay.o_seg),
+                                  reinterpret_cast<double*>(d + lay.o_par), reinterpret_cast<double*>(d + lay.o_dist), v_max, dyaw_max,
+                                  zero_gain, reinterpret_cast<uint8_t*>(dr + lay.r_free), reinterpret_cast<nbvgpu_best*>(dr),
+                                  reinterpret_cast<double*>(dr + lay.r_gain), reinterpret_cast<int32_t*>(dr + lay.r_yaw), post);
+    else
+      rc = best_device_nolock(ctx, tsdf_layer, n, reinterpret_cast<double*>(d), reinterpret_cast<double*>(d + lay.o_par),
+                              reinterpret_cast<double*>(d + lay.o_dist), lay.with_free ? reinterpret_cast<uint8_t*>(d + lay.o_free) : nullptr,
+                              v_max, dyaw_max, zero_gain, reinterpret_cast<nbvgpu_best*>(dr), reinterpret_cast<double*>(dr + lay.r_gain),
+                              reinterpret_cast<int32_t*>(dr + lay.r_yaw), post);
+    if (rc) return rc;
+    const size_t back = outputs ? (seg ? lay.out_bytes : lay.r_free) : (post.slot ? 0 : sizeof(nbvgpu_best));
+    if (back) CK(cudaMemcpyAsync(h + lay.in_bytes, dr, back, cudaMemcpyDeviceToHost, ctx->stream));
+    return NBVGPU_OK;
+  });
 }
 // After cudaStreamSynchronize: results of the last evaluate_host_enqueue of this context into the caller's arrays.
 void evaluate_host_collect(nbvgpu_ctx* ctx, size_t n, bool with_seg, bool with_free, uint8_t* edge_free, nbvgpu_best* best, double* gain,
@@ -1328,7 +1471,8 @@ int group_evaluate(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double radiu
       group_post_empty(G, rank, seq);
       continue;
     }
-    const BestPost post{&G->d_shared[i]->best[seq & 1u][rank], (long long)lo, seq};
+    G->shared.host->seq_in[rank] = seq;  // read by the scoring kernel (plain store: the launch that follows orders it)
+    const BestPost post{&G->d_shared[i]->best[0][rank], (unsigned)(sizeof(BestSlot) * kMaxRanks), (long long)lo, &G->d_shared[i]->seq_in[rank]};
     const int rc = evaluate_host_enqueue(m, tsdf_layer, esdf_layer, radius, hi - lo, pos + 3 * lo, seg ? seg + 6 * lo : nullptr,
                                          parent_yaw + lo, distance + lo, edge_free_in ? edge_free_in + lo : nullptr, v_max, dyaw_max,
                                          zero_gain, outputs, post);
@@ -1418,6 +1562,8 @@ static void destroy_member(nbvgpu_ctx* ctx) {
       cudaEventDestroy(pr.first);
       cudaEventDestroy(pr.second);
     }
+    for (nbvgpu_ctx::StepGraph& g : ctx->graphs) destroy_step_graph(g);
+    ctx->graphs.clear();
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   }
   delete ctx;
@@ -1445,6 +1591,7 @@ static int create_member_impl(int device, nbvgpu_ctx** out) {
   ctx->no_small = std::getenv("NBVGPU_NO_SMALL_PATH") != nullptr;
   ctx->no_poll = std::getenv("NBVGPU_NO_POLL") != nullptr;
   ctx->no_wide_cta = std::getenv("NBVGPU_NO_WIDE_CTA") != nullptr;
+  ctx->no_graph = std::getenv("NBVGPU_NO_GRAPH") != nullptr;
   ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
   DeviceGuard guard(device);
   bool ok = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -1490,6 +1637,7 @@ static nbvgpu_ctx* create_lane(nbvgpu_ctx* P) {
   L->max_smem_optin = P->max_smem_optin;
   L->force_yc = P->force_yc; L->dense_budget = P->dense_budget; L->smem_pad = P->smem_pad;
   L->no_fuse = P->no_fuse; L->no_small = P->no_small; L->no_poll = P->no_poll; L->no_wide_cta = P->no_wide_cta;
+  L->no_graph = P->no_graph;
   L->d_A = P->d_A; L->d_B = P->d_B; L->d_cs = P->d_cs; L->d_totals = P->d_totals; L->d_lstate = P->d_lstate;
   DeviceGuard guard(P->device);
   int lo = 0, hi = 0;
@@ -2154,7 +2302,7 @@ int nbvgpu_gain_eval_best(nbvgpu_ctx* ctx, int layer, size_t n, const double* po
   if (check_position_range(ctx, L, n, pos)) return fail(ctx, NBVGPU_ERR_RANGE, "position non-finite or out of range");
   DeviceGuard guard(ctx->device);
   const int rc = evaluate_host_enqueue(ctx, layer, -1, 0.0, n, pos, nullptr, parent_yaw, distance, edge_free, v_max, dyaw_max, zero_gain,
-                                       gain || yaw_deg, BestPost{nullptr, 0, 0u});
+                                       gain || yaw_deg, BestPost{nullptr, 0u, 0, nullptr});
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   evaluate_host_collect(ctx, n, false, edge_free != nullptr, nullptr, best, gain, yaw_deg);
@@ -2167,9 +2315,26 @@ int nbvgpu_evaluate_candidates_device(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_
                                       const double* d_distance, double v_max, double dyaw_max, double zero_gain,
                                       uint8_t* d_edge_free, nbvgpu_best* d_best, double* d_gain, int32_t* d_yaw_deg) {
   if (!ctx || !d_best || (n && (!d_pos || !d_seg || !d_parent_yaw || !d_distance || !d_edge_free))) return NBVGPU_ERR_INVALID;
+  std::shared_lock<std::shared_mutex> sm(ctx->map_mu);
   std::lock_guard<std::mutex> lk(ctx->mu);
-  return evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, robot_radius, n, d_pos, d_seg, d_parent_yaw, d_distance, v_max,
-                                dyaw_max, zero_gain, d_edge_free, d_best, d_gain, d_yaw_deg);
+  DeviceGuard guard(ctx->device);
+  if (!d_gain) {  // scratch outputs are part of the step's shape
+    CK(ctx->d_gain.reserve(n * 8 + 8));
+    d_gain = ctx->d_gain.as<double>();
+  }
+  if (!d_yaw_deg) {
+    CK(ctx->d_yaw.reserve(n * 4 + 4));
+    d_yaw_deg = ctx->d_yaw.as<int32_t>();
+  }
+  StepKey key = step_key_base(ctx, tsdf_layer, esdf_layer);
+  key.add((unsigned long long)n | (2ull << 48));
+  key.add(d_pos); key.add(d_seg); key.add(d_parent_yaw); key.add(d_distance); key.add(d_edge_free); key.add(d_best); key.add(d_gain);
+  key.add(d_yaw_deg);
+  key.add(robot_radius); key.add(v_max); key.add(dyaw_max); key.add(zero_gain);
+  return with_step_graph(ctx, key, [&]() -> int {
+    return evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, robot_radius, n, d_pos, d_seg, d_parent_yaw, d_distance, v_max, dyaw_max,
+                                  zero_gain, d_edge_free, d_best, d_gain, d_yaw_deg);
+  });
 }
 
 int nbvgpu_evaluate_candidates(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, double robot_radius, size_t n, const double* pos,
@@ -2192,7 +2357,7 @@ int nbvgpu_evaluate_candidates(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, 
     if (!(std::fabs(seg[i] * vs_inv) < 4194000.0)) return fail(ctx, NBVGPU_ERR_RANGE, "segment non-finite or out of range");
   DeviceGuard guard(ctx->device);
   const int rc = evaluate_host_enqueue(ctx, tsdf_layer, esdf_layer, robot_radius, n, pos, seg, parent_yaw, distance, nullptr, v_max, dyaw_max,
-                                       zero_gain, gain || yaw_deg || edge_free, BestPost{nullptr, 0, 0u});
+                                       zero_gain, gain || yaw_deg || edge_free, BestPost{nullptr, 0u, 0, nullptr});
   if (rc) return rc;
   CK(cudaStreamSynchronize(ctx->stream));
   evaluate_host_collect(ctx, n, true, false, edge_free, best, gain, yaw_deg);
@@ -2215,10 +2380,29 @@ int nbvgpu_evaluate_shard_device(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer
   if (n_local == 0) {
     group_post_empty(G, G->rank0, seq);
   } else {
+    std::shared_lock<std::shared_mutex> sm(ctx->map_mu);
     std::lock_guard<std::mutex> lk(ctx->mu);
-    const BestPost post{&G->d_shared[0]->best[seq & 1u][G->rank0], (long long)index_offset, seq};
-    const int rc = evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, robot_radius, n_local, d_pos, d_seg, d_parent_yaw, d_distance, v_max,
-                                          dyaw_max, zero_gain, d_edge_free, nullptr, d_gain, d_yaw_deg, post);
+    DeviceGuard guard(ctx->device);
+    G->shared.host->seq_in[G->rank0] = seq;
+    const BestPost post{&G->d_shared[0]->best[0][G->rank0], (unsigned)(sizeof(BestSlot) * kMaxRanks), (long long)index_offset,
+                        &G->d_shared[0]->seq_in[G->rank0]};
+    if (!d_gain) {
+      CK(ctx->d_gain.reserve(n_local * 8 + 8));
+      d_gain = ctx->d_gain.as<double>();
+    }
+    if (!d_yaw_deg) {
+      CK(ctx->d_yaw.reserve(n_local * 4 + 4));
+      d_yaw_deg = ctx->d_yaw.as<int32_t>();
+    }
+    StepKey key = step_key_base(ctx, tsdf_layer, esdf_layer);
+    key.add((unsigned long long)n_local | (3ull << 48));
+    key.add(d_pos); key.add(d_seg); key.add(d_parent_yaw); key.add(d_distance); key.add(d_edge_free); key.add(d_gain); key.add(d_yaw_deg);
+    key.add(robot_radius); key.add(v_max); key.add(dyaw_max); key.add(zero_gain);
+    key.add(post.slot); key.add((unsigned long long)post.index_offset); key.add(post.seq_src);
+    const int rc = with_step_graph(ctx, key, [&]() -> int {
+      return evaluate_device_nolock(ctx, tsdf_layer, esdf_layer, robot_radius, n_local, d_pos, d_seg, d_parent_yaw, d_distance, v_max, dyaw_max,
+                                    zero_gain, d_edge_free, nullptr, d_gain, d_yaw_deg, post);
+    });
     if (rc) return rc;
   }
   return group_collect_best(ctx, seq, zero_gain, best);
@@ -2722,6 +2906,19 @@ int nbvgpu_debug_fused_launches(nbvgpu_ctx* ctx, uint64_t* out) {
   return NBVGPU_OK;
 }
 
+// Planning steps (since context creation) that ran as a replay of their captured CUDA graph; for tests.
+int nbvgpu_debug_graph_replays(nbvgpu_ctx* ctx, uint64_t* out) {
+  if (!ctx || !out) return NBVGPU_ERR_INVALID;
+  unsigned long long total = 0;
+  std::vector<nbvgpu_ctx*> members = ctx->group ? ctx->group->local : std::vector<nbvgpu_ctx*>{ctx};
+  for (nbvgpu_ctx* m : members) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    total += m->stats_graph_replays;
+  }
+  *out = total;
+  return NBVGPU_OK;
+}
+
 // Ray-sweep launches (since context creation) that used the z-clipped dense volume; for tests.
 int nbvgpu_debug_dense_clipped_launches(nbvgpu_ctx* ctx, uint64_t* out) {
   if (!ctx || !out) return NBVGPU_ERR_INVALID;
@@ -2798,6 +2995,9 @@ int nbvgpu_set_profiling(nbvgpu_ctx* ctx, int enable) {
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->profiling = enable != 0;
   ctx->prof_used = 0;
+  for (nbvgpu_ctx::StepGraph& g : ctx->graphs) g.timing_pending = false;
+  ctx->prof_graph_ms = 0.0;
+  ctx->prof_graph_n = 0;
   return NBVGPU_OK;
 }
 
@@ -2812,9 +3012,12 @@ int nbvgpu_profile_collect(nbvgpu_ctx* ctx, double* gain_kernel_ms, uint64_t* la
     CK(cudaEventElapsedTime(&ms, ctx->prof_events[i].first, ctx->prof_events[i].second));
     total += ms;
   }
-  *gain_kernel_ms = total;
-  *launches = ctx->prof_used;
+  for (nbvgpu_ctx::StepGraph& g : ctx->graphs) harvest_graph_timing(ctx, g);  // replays of captured steps
+  *gain_kernel_ms = total + ctx->prof_graph_ms;
+  *launches = ctx->prof_used + ctx->prof_graph_n;
   ctx->prof_used = 0;
+  ctx->prof_graph_ms = 0.0;
+  ctx->prof_graph_n = 0;
   return NBVGPU_OK;
 }
 

@@ -421,6 +421,12 @@ class NbvGpu:
         self._ck(self._L.nbvgpu_debug_wide_cta_launches(self._h, C.byref(out)))
         return int(out.value)
 
+    def graph_replays(self) -> int:
+        """planning steps that ran as a replay of their captured CUDA graph (tests)."""
+        out = C.c_uint64(0)
+        self._ck(self._L.nbvgpu_debug_graph_replays(self._h, C.byref(out)))
+        return int(out.value)
+
     def frontier_hash_redo(self) -> int:
         """vertices the dense visited set of the flood fill handed back to the hash-keyed one (tests)."""
         out = C.c_uint64(0)

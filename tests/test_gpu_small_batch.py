@@ -227,3 +227,55 @@ def test_evaluate_candidates_equals_the_two_calls(oracle_mod, n):
     rec = np.frombuffer(d_best.cpu().numpy().tobytes(), dtype=[("index", "<i8"), ("score", "<f8"), ("gain", "<f8"), ("yaw", "<f8")])[0]
     assert rec["index"] == two["index"] and rec["score"] == two["score"] and rec["gain"] == two["best_gain"] and rec["yaw"] == two["best_yaw"]
     g.close()
+
+
+@pytest.mark.parametrize("n", [40, 700])
+def test_planning_step_graph_replays_equal_eager(oracle_mod, n, monkeypatch):
+    """The planning step as a CUDA graph: first call eager, second captured, then replays -- host-buffer and device-resident
+    forms, with profiling events inside the graph -- all bit-equal to the eager path (NBVGPU_NO_GRAPH=1) and to new inputs
+    written into the same buffers between replays."""
+    import torch
+    from nbv_exploration_planner_b200 import synth
+    m, o, lt_o, le_o, g, lt_g, le_g, c0 = _setup(oracle_mod)
+    c = synth.make_candidates(m.cfg, 2 * n, None)
+    pyaw = np.linspace(-3.0, 3.0, n)
+    sets = [(c.positions[:n], c.segments[:n], c.distance[:n]), (c.positions[n:], c.segments[n:], c.distance[n:])]
+    monkeypatch.setenv("NBVGPU_NO_GRAPH", "1")
+    ge, lt_e, le_e = _setup(oracle_mod)[4:7]
+    want = [ge.evaluate_candidates(lt_e, le_e, m.cfg.robot_radius, p, s, pyaw, d, 1.0, 0.5, 0.0) for p, s, d in sets]
+    assert ge.graph_replays() == 0
+    ge.close()
+    monkeypatch.delenv("NBVGPU_NO_GRAPH")
+    for rep in range(6):                      # host-buffer form: alternate the inputs, the shape stays
+        p, s, d = sets[rep % 2]
+        r = g.evaluate_candidates(lt_g, le_g, m.cfg.robot_radius, p, s, pyaw, d, 1.0, 0.5, 0.0)
+        w = want[rep % 2]
+        for k in ("index", "score", "best_gain", "best_yaw"):
+            assert r[k] == w[k], (rep, k)
+        for k in ("gain", "yaw_deg", "free"):
+            assert np.array_equal(r[k], w[k]), (rep, k)
+    assert g.graph_replays() >= 4
+    # device-resident form on a caller's stream, with the sweep's profiling events inside the graph
+    dv = lambda a, t: torch.from_numpy(np.ascontiguousarray(a, t)).cuda()
+    d_pos, d_seg, d_py, d_di = dv(sets[0][0], np.float64), dv(sets[0][1], np.float64), dv(pyaw, np.float64), dv(sets[0][2], np.float64)
+    d_free = torch.zeros(n, dtype=torch.uint8, device="cuda")
+    d_gain = torch.zeros(n, dtype=torch.float64, device="cuda")
+    d_yaw = torch.zeros(n, dtype=torch.int32, device="cuda")
+    d_best = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.Stream()
+    g.set_stream(stream.cuda_stream)
+    before = g.graph_replays()
+    g.set_profiling(True)
+    with torch.cuda.stream(stream):
+        for rep in range(6):
+            src = sets[rep % 2]
+            d_pos.copy_(dv(src[0], np.float64)); d_seg.copy_(dv(src[1], np.float64)); d_di.copy_(dv(src[2], np.float64))
+            g.evaluate_candidates_device(lt_g, le_g, m.cfg.robot_radius, n, d_pos, d_seg, d_py, d_di, 1.0, 0.5, 0.0, d_free, d_best, d_gain, d_yaw)
+            stream.synchronize()
+            assert np.array_equal(d_gain.cpu().numpy(), want[rep % 2]["gain"]) and np.array_equal(d_free.cpu().numpy(), want[rep % 2]["free"])
+    ms, launches = g.profile_collect()
+    g.set_profiling(False)
+    g.set_stream(None)
+    assert g.graph_replays() - before >= 4
+    assert launches == 6 and 0.0 < ms < 50.0, (ms, launches)      # every step's sweep was timed, replayed or not
+    g.close()
