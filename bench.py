@@ -562,6 +562,8 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
                          "algorithmic_bytes_per_launch": steps_per_launch * ALGO_BYTES_PER_STEP,
                          "avg_launch_ms": kern_ms / max(1, kern_launches),
                          "kernel_share_of_step": kern_ms / dev_ms if dev_ms > 0 else None,
+                         "step_minus_kernel_us": (dev_ms - kern_ms) / steps * 1e3,   # edge check, window scan, scoring, record to host, launch gaps
+                         "graph_replays": g.graph_replays(),
                          "l2": l2_info(g, ach) if not args.no_l2_probe else None,
                          "note": "8 B per executed voxel-step (SURVEY.md 8d); the status tiles the sweep reads are L2/L1 resident, so real DRAM traffic is far lower"},
             "clocks": clocks, "best": winner,

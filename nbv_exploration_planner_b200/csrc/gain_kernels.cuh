@@ -253,7 +253,7 @@ __device__ __forceinline__ void to_camera(const FilterConst& F, float vs_f, floa
 // ray parameter at which the next voxel is entered.  Written as predicated PTX: 6 compare/select + one
 // predicated add per carried quantity (HASP: bit address of the dense volume; HASSV: signed distance to
 // the open top/bottom plane).
-template <bool HASP, bool HASSV>
+template <bool HASP, bool HASSV, bool HASG = true>
 __device__ __forceinline__ void dda_advance(float (&t)[3], const float (&dt)[3], float& tcur, int (&g)[3], const int (&sg)[3],
                                             unsigned& P, int stx, int sty, int stz, float& sv, float d0, float d1, float d2) {
 #define NBV_DDA_SELECT                       \
@@ -266,7 +266,48 @@ __device__ __forceinline__ void dda_advance(float (&t)[3], const float (&dt)[3],
   "selp.f32 %3, %2, bm, m2;\n\t"             \
   "setp.geu.and.f32 m1, %2, bm, c1;\n\t"     \
   "setp.geu.and.f32 m0, %2, bm, !c1;\n\t"
-  if (HASP && HASSV) {
+  // Dense volume, voxel index not carried (rebuilt from P when a stretch ends).  Only used where t[0] cannot be NaN (rays without
+  // an x component end in the general loop), so the first minimum is a three-input min and two equality tests, and the bit
+  // address moves by ONE add of the selected stride.
+  if (HASP && !HASG && HASSV) {
+    asm("{\n\t"
+        ".reg .pred m0, m1, m2;\n\t"
+        ".reg .u32 st;\n\t"
+        ".reg .f32 ds;\n\t"
+        "min.f32 %3, %0, %1, %2;\n\t"
+        "setp.eq.f32 m0, %0, %3;\n\t"
+        "setp.eq.and.f32 m1, %1, %3, !m0;\n\t"
+        "setp.neu.and.f32 m2, %1, %3, !m0;\n\t"
+        "@m0 add.rn.f32 %0, %0, %6;\n\t"
+        "@m1 add.rn.f32 %1, %1, %7;\n\t"
+        "@m2 add.rn.f32 %2, %2, %8;\n\t"
+        "selp.b32 st, %10, %11, m1;\n\t"
+        "selp.b32 st, %9, st, m0;\n\t"
+        "add.s32 %4, %4, st;\n\t"
+        "selp.f32 ds, %13, %14, m1;\n\t"
+        "selp.f32 ds, %12, ds, m0;\n\t"
+        "add.rn.f32 %5, %5, ds;\n\t"
+        "}"
+        : "+f"(t[0]), "+f"(t[1]), "+f"(t[2]), "=&f"(tcur), "+r"(P), "+f"(sv)
+        : "f"(dt[0]), "f"(dt[1]), "f"(dt[2]), "r"(stx), "r"(sty), "r"(stz), "f"(d0), "f"(d1), "f"(d2));
+  } else if (HASP && !HASG) {
+    asm("{\n\t"
+        ".reg .pred m0, m1, m2;\n\t"
+        ".reg .u32 st;\n\t"
+        "min.f32 %3, %0, %1, %2;\n\t"
+        "setp.eq.f32 m0, %0, %3;\n\t"
+        "setp.eq.and.f32 m1, %1, %3, !m0;\n\t"
+        "setp.neu.and.f32 m2, %1, %3, !m0;\n\t"
+        "@m0 add.rn.f32 %0, %0, %5;\n\t"
+        "@m1 add.rn.f32 %1, %1, %6;\n\t"
+        "@m2 add.rn.f32 %2, %2, %7;\n\t"
+        "selp.b32 st, %9, %10, m1;\n\t"
+        "selp.b32 st, %8, st, m0;\n\t"
+        "add.s32 %4, %4, st;\n\t"
+        "}"
+        : "+f"(t[0]), "+f"(t[1]), "+f"(t[2]), "=&f"(tcur), "+r"(P)
+        : "f"(dt[0]), "f"(dt[1]), "f"(dt[2]), "r"(stx), "r"(sty), "r"(stz));
+  } else if (HASP && HASSV) {
     asm(NBV_DDA_SELECT
         "@m0 add.rn.f32 %0, %0, %9;\n\t"
         "@m1 add.rn.f32 %1, %1, %10;\n\t"
@@ -508,6 +549,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
   constexpr bool kParanoid = (VARIANT == 2);
   constexpr bool kIsDense = (MODE == kDense || MODE == kDenseClip);
   constexpr bool kZClip = (MODE == kDenseClip);
+  // The stretch loops of the dense kernel step the volume's bit address P only; the voxel index g is rebuilt from P when a
+  // stretch ends (the general loop needs it).  The cross-checking variant and the other modes carry g all the way.
+  constexpr bool kKeepG = !kIsDense || kParanoid;
   static_assert(!kIsDense || (LV == 4 && kStatusBits), "the dense volume copies 16-voxel status-tile words");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int yc = a.yc;
@@ -841,6 +885,33 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
       return code;
     };
 
+    // Voxel index from the bit address (dense kernel; once per stretch, two small integer divisions).
+    auto g_from_P = [&]() {
+      const unsigned rel = P - 8u * vol_s;
+      const unsigned wd = rel >> 5, row = wd / (unsigned)vxw, zz = row / (unsigned)vey;
+      g[0] = x0 + (int)((wd - row * (unsigned)vxw) * 16u + ((rel & 31u) >> 1));
+      g[1] = y0 + (int)(row - zz * (unsigned)vey);
+      g[2] = z0 + (int)zz;
+    };
+    // count_safe -- why the stretch loops need not test the RayCaster's step counter per voxel.  The walk ends after len + 1
+    // emissions, len = sum_k |end_k - start_k| (integrator_utils.cc:111-117,141-147).  Axis k crosses its j-th boundary at
+    // t_k(0) + j dt_k; its |delta_k|-th crossing and every later one lies beyond the end voxel, i.e. at t >= 1 -- except that
+    // the 1e-6 voxel nudge of getGridIndexFromPoint can hide one crossing from len, at t >= 1 - 1e-6 / |r_k|.  So while
+    // tcur < tB every step taken so far was one of the len counted ones and voxel number len has not been left, provided
+    // (a) 1 - tB exceeds the drift of the accumulated float t's (<= len * 2^-24 ~ 1.5e-5 at 250 steps; 1 - tB >= 1.8e-4 from
+    // the far-plane margin) and (b) no axis has 0 < |r_k| < 2e-6 / (1 - tB).  A ray that fails (b) -- almost parallel to a grid
+    // plane -- walks all its voxels in the general loop, which counts every step.
+    if (kFilter) {
+      const float room = 1.0f - tB;
+      bool risky = !(room > 1.0e-4f);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float ar = fabsf(dt[k]);  // = 1 / |r_k| (inf for r_k = 0: such an axis never steps)
+        risky = risky || (sg[k] != 0 && ar * 2.0e-6f > room);
+      }
+      if (risky) tlo = 3.0e38f;
+    }
+
     // A ray passes through up to three kinds of stretches, in this order: the general one (ray start; again at
     // the very end, where the far plane is open), a stretch where only the nearer of top/bottom is open (whole
     // rays in the rows that hug those planes), and the window in which every plane is sure.  One loop per
@@ -937,65 +1008,129 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
       //      distance is evaluated once on entry and then follows the walk with one add per step.  The n
       //      roundings of that sum are covered by widening the decision margin (|sv| <= reach + 1 m, so each is
       //      below 2^-24 * 1e5 * F.m); inside the margin the exact planes decide.
+      //      Neither this loop nor the window loop tests the RayCaster's step counter per voxel: while tcur < tB (< thi < 1,
+      //      the far plane cuts the ray's last stretch off) the ray cannot have emitted its len + 1 voxels -- see the
+      //      note at `count_safe` above; the counter is compared once when the loop is left.
       if (run && tcur < tB && !(tcur > tlo_v)) {
         float sv = fmaf(pa[0], (float)(g[0] - g0x), fmaf(pa[1], (float)(g[1] - g0y), fmaf(pa[2], (float)(g[2] - g0z), pc)));
         const float d0 = pa[0] * (float)sg[0], d1 = pa[1] * (float)sg[1], d2 = pa[2] * (float)sg[2];
         const float mi = F.m * (1.0f + 0.01f * (float)(len + 1));
+        unsigned last;
         do {
           bool fin = sv > 0.0f;
-          if (!(fabsf(sv) > mi)) fin = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);  // inside the margin (rare)
+          if (!(fabsf(sv) > mi)) {  // inside the margin (rare): the exact planes decide
+            if (!kKeepG) g_from_P();
+            fin = exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs);
+          }
           if (kParanoid && fin != exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs) && (kIsDense || in_box())) ++my_mismatch;
-          unsigned c = 0x10002u;  // code + 2^16, as in the window loop below
+          unsigned c = 2u;
           if (kIsDense) {
-            c = volume_code() | 0x10000u;
-            c = fin ? c : 0x10002u;
+            c = volume_code();
+            c = fin ? c : 2u;
           } else if (fin && in_box()) {
-            c = tile_code() | 0x10000u;
+            c = tile_code();
           }
-          if (c == 0x10003u) {
-            occ = 1u;
-            S1 += 0x10000u;
-            run = false;
-            break;
-          }
-          S1 += c;
+          // an occupied voxel ends the walk; it is accumulated and stepped past like any other (one exit test per voxel,
+          // at the bottom) and taken out again below
+          S1 += c + 0x10000u;
           S2 = c * c + S2;
-          if (kIsDense) dda_advance<true, true>(t, dt, tcur, g, sg, P, stx, sty, stz, sv, d0, d1, d2);
+          last = c;
+          if (kIsDense) dda_advance<true, true, kKeepG>(t, dt, tcur, g, sg, P, stx, sty, stz, sv, d0, d1, d2);
           else dda_advance<false, true>(t, dt, tcur, g, sg, P, 0, 0, 0, sv, d0, d1, d2);
+          if (kParanoid && last != 3u && !(S1 < walk_end) && tcur < tB && !(tcur > tlo_v)) ++my_mismatch;  // the counter would have ended the walk here
+        } while (last != 3u && (!kParanoid || S1 < walk_end) && tcur < tB && !(tcur > tlo_v));
+        if (last == 3u) {
+          occ = 1u;
+          S1 -= 3u;  // the step was executed, the voxel counts as occupied only
+          S2 -= 9u;
+          run = false;
+        } else {
           run = S1 < walk_end;
-        } while (run && tcur < tB && !(tcur > tlo_v));
+          if (!kKeepG) g_from_P();
+        }
       }
       __syncwarp();
       // ---- window: every plane is sure, the voxel counts unless it is outside the exploration box
-      if (run && tcur > tA && tcur < tB) {
+      if (kIsDense && !kParanoid) {
+        // The dense kernel's window loop, 74 % of all voxel-steps, written out as PTX so that it stays at the 22 instructions
+        // it needs per voxel: word address from the bit address P (2), load, first-minimum select of the RayCaster's t (6: a
+        // NaN in t[1] / t[2] never wins, one in t[0] always does -- Eigen's minCoeff), code = (word >> (P & 31)) & 3 (2), the
+        // stepping axis' t, and P by the axis' stride (6), S1 += code + 2^16 and S2 += code^2 (2), and ONE exit test: stop on
+        // an occupied voxel (code 3) or when the next voxel is entered at or beyond tB (3).  An occupied voxel is accumulated
+        // and stepped past like any other and taken out again below.
+        if (run && tcur > tA && tcur < tB) {
+          unsigned last;
+          asm volatile(
+              "{\n\t"
+              ".reg .pred m0, m1, m2, pn, pc;\n\t"
+              ".reg .u32 ad, wd;\n\t"
+              "NBVW_LOOP:\n\t"
+              "shr.u32 ad, %3, 3;\n\t"
+              "and.b32 ad, ad, 0xFFFFFFFC;\n\t"
+              "ld.shared.u32 wd, [ad];\n\t"
+              "min.f32 %6, %0, %1, %2;\n\t"               // t[0] is never NaN here (such rays end in the general loop)
+              "setp.eq.f32 m0, %0, %6;\n\t"               // first minimum: axis 0 on ties, then axis 1
+              "setp.eq.and.f32 m1, %1, %6, !m0;\n\t"
+              "setp.neu.and.f32 m2, %1, %6, !m0;\n\t"
+              "shf.r.wrap.b32 %7, wd, 0, %3;\n\t"
+              "and.b32 %7, %7, 3;\n\t"
+              "@m0 add.rn.f32 %0, %0, %8;\n\t"
+              "@m1 add.rn.f32 %1, %1, %9;\n\t"
+              "@m2 add.rn.f32 %2, %2, %10;\n\t"
+              "selp.b32 ad, %12, %13, m1;\n\t"
+              "selp.b32 ad, %11, ad, m0;\n\t"
+              "add.s32 %3, %3, ad;\n\t"
+              "add.u32 %4, %4, %7;\n\t"
+              "add.u32 %4, %4, 0x10000;\n\t"
+              "mad.lo.u32 %5, %7, %7, %5;\n\t"
+              "setp.ne.u32 pn, %7, 3;\n\t"
+              "setp.lt.and.f32 pc, %6, %14, pn;\n\t"
+              "@pc bra NBVW_LOOP;\n\t"
+              "}"
+              : "+f"(t[0]), "+f"(t[1]), "+f"(t[2]), "+r"(P), "+r"(S1), "+r"(S2), "+f"(tcur), "=&r"(last)
+              : "f"(dt[0]), "f"(dt[1]), "f"(dt[2]), "r"(stx), "r"(sty), "r"(stz), "f"(tB)
+              : "memory");
+          if (last == 3u) {  // the occupied voxel that stopped the ray: executed, not counted as anything else
+            occ = 1u;
+            S1 -= 3u;
+            S2 -= 9u;
+            run = false;
+          } else {
+            run = S1 < walk_end;
+            g_from_P();
+          }
+        }
+      } else if (run && tcur > tA && tcur < tB) {
+        unsigned last;
         do {
           if (kParanoid && (kIsDense || in_box()) && !exact_in_frustum(S.pl, yc, j, g[0], g[1], g[2], a.vs)) {
             if (in_box()) ++my_mismatch;
           }
-          // c = code + 2^16 (the walk counter's bit) in one logic op
-          unsigned c = 0x10002u;
+          unsigned c = 2u;
           if (kIsDense) {
             uint32_t w;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"((P >> 3) & ~3u));
-            asm("lop3.b32 %0, %1, 3, 0x10000, 0xEA;" : "=r"(c) : "r"(__funnelshift_r(w, 0u, P)));  // (x & 3) | 2^16
-            if (kParanoid && (c & 3u) != volume_code()) ++my_mismatch;  // volume_code() cross-checks against the tiles
+            c = __funnelshift_r(w, 0u, P) & 3u;
+            if (kParanoid && c != volume_code()) ++my_mismatch;  // volume_code() cross-checks against the tiles
           } else if (in_box()) {
-            c = tile_code() | 0x10000u;
+            c = tile_code();
           }
-          if (c == 0x10003u) {
-            occ = 1u;
-            S1 += 0x10000u;
-            run = false;
-            break;
-          }
-          // c^2 = code^2 + code * 2^17 (mod 2^32): the low 17 bits of S2 stay the sum of squares, the rest is
-          // masked off after the walk
-          S1 += c;
+          S1 += c + 0x10000u;  // one three-input add: the code and the walk counter's bit
           S2 = c * c + S2;
-          if (kIsDense) dda_advance<true, false>(t, dt, tcur, g, sg, P, stx, sty, stz, dummy_sv, 0.f, 0.f, 0.f);
+          last = c;
+          if (kIsDense) dda_advance<true, false, kKeepG>(t, dt, tcur, g, sg, P, stx, sty, stz, dummy_sv, 0.f, 0.f, 0.f);
           else dda_advance<false, false>(t, dt, tcur, g, sg, P, 0, 0, 0, dummy_sv, 0.f, 0.f, 0.f);
+          if (kParanoid && last != 3u && !(S1 < walk_end) && tcur < tB) ++my_mismatch;  // the counter would have ended the walk here
+        } while (last != 3u && (!kParanoid || S1 < walk_end) && tcur < tB);
+        if (last == 3u) {  // the occupied voxel that stopped the ray: executed, not counted as anything else
+          occ = 1u;
+          S1 -= 3u;
+          S2 -= 9u;
+          run = false;
+        } else {
           run = S1 < walk_end;
-        } while (run && tcur < tB);
+          if (!kKeepG) g_from_P();
+        }
       }
     }
     const unsigned walked = S1 >> 16;  // includes the occupied voxel that stopped the ray

@@ -789,7 +789,14 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
   }
   a.zclip = 0;
   a.sz_lo = a.sz_hi = a.vez_alloc = 0;
-  if (!dense && (variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0 && getenv("NBVGPU_NO_ZCLIP") == nullptr) {
+  // (worth its synchronisation only when the slab is thinner than the volume, so that EVERY candidate gains; under a tall box
+  // -- config 3: 100 rows of slab against 56 rows of volume -- only candidates next to the floor or the ceiling could, and a
+  // mixed batch is sized by its worst candidate anyway)
+  bool slab_thinner = false;
+  if (!dense && gdim > 0)
+    for (const auto& kv : ctx->dense_info)
+      if (kv.second.ok && kv.second.vez > 0 && (long long)a.gspan[2] + 7 < (long long)kv.second.vez) slab_thinner = true;
+  if (!dense && slab_thinner && (variant == 0 || variant == 2) && L->log2vps == 4 && gdim > 0 && getenv("NBVGPU_NO_ZCLIP") == nullptr) {
     // Second chance for fine voxels: the volume did not fit because the frustum reaches far below / above the exploration
     // box, where no voxel can count.  Clipped to the box slab (+- 3 voxels, plus the rows the rays start in) it may; how
     // many rows that takes depends on the candidates' heights, so their z-range is read back first (one tiny kernel and
