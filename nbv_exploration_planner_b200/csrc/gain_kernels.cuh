@@ -739,6 +739,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
     int len = 0;
     float tlo = 0.0f, thi = 3.0e38f, tlo_v = 0.0f, t_out = 3.0e38f;
     float e3[3];
+    int adl[3];  // |end voxel - start voxel| per axis
     // Modes that test the exploration box per voxel (the dense volume has it baked in): a ray whose start and end voxels
     // both lie at least two voxels inside the box never needs the test.  The walk moves axis k only towards the end voxel
     // and takes len = sum |end - start| steps; it can overshoot an axis by one voxel at most (a second extra crossing
@@ -753,7 +754,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
       e3[k] = ek;
       g[k] = (int)floorf(__fadd_rn(sk, 1e-6f));
       const int ei = (int)floorf(__fadd_rn(ek, 1e-6f));
-      len += abs(ei - g[k]);
+      adl[k] = abs(ei - g[k]);
+      len += adl[k];
       if (!kIsDense)
         ray_in = ray_in && a.gspan[k] >= 4u && (unsigned)(g[k] - a.gmin[k] - 2) <= a.gspan[k] - 4u &&
                  (unsigned)(ei - a.gmin[k] - 2) <= a.gspan[k] - 4u;
@@ -808,7 +810,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
       pa[2] = S.fp[(q + 2) * yc + j];
       pc = S.fp[(q + 3) * yc + j];
     }
-    const float tA = fmaxf(tlo, tlo_v), tB = fminf(thi, t_out);  // window in which every test is sure
+    const float tA = fmaxf(tlo, tlo_v);
+    float tB = fminf(thi, t_out);  // (tA, tB): the window in which every test is sure
     // dense volume: bit address of the start voxel (the shared-window byte address of the volume is folded
     // in: word address (P >> 3) & ~3, bit position P & 31; vol_s is 16-byte aligned) and per-axis strides
     unsigned P = 0u;
@@ -899,16 +902,29 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
     // the 1e-6 voxel nudge of getGridIndexFromPoint can hide one crossing from len, at t >= 1 - 1e-6 / |r_k|.  So while
     // tcur < tB every step taken so far was one of the len counted ones and voxel number len has not been left, provided
     // (a) 1 - tB exceeds the drift of the accumulated float t's (<= len * 2^-24 ~ 1.5e-5 at 250 steps; 1 - tB >= 1.8e-4 from
-    // the far-plane margin) and (b) no axis has 0 < |r_k| < 2e-6 / (1 - tB).  A ray that fails (b) -- almost parallel to a grid
-    // plane -- walks all its voxels in the general loop, which counts every step.
+    // the far-plane margin), (b) no axis has 0 < |r_k| < 2e-6 / (1 - tB) -- a ray that fails it, almost parallel to a grid
+    // plane, walks all its voxels in the general loop, which counts every step -- and (c) below.
     if (kFilter) {
       const float room = 1.0f - tB;
       bool risky = !(room > 1.0e-4f);
+      bool zero_axis = false;
+      float dmin = 3.0e38f, tstop = -1.0f;  // the densest stepping axis and the entry time of its third-last counted crossing
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const float ar = fabsf(dt[k]);  // = 1 / |r_k| (inf for r_k = 0: such an axis never steps)
+        const float ar = fabsf(dt[k]);  // = 1 / |r_k| (NaN for r_k = 0: such an axis never moves)
         risky = risky || (sg[k] != 0 && ar * 2.0e-6f > room);
+        zero_axis = zero_axis || sg[k] == 0;
+        if (sg[k] != 0 && ar < dmin) {
+          dmin = ar;
+          tstop = adl[k] >= 4 ? fmaf((float)adl[k] - 3.5f, dt[k], t[k]) : -1.0f;
+        }
       }
+      // (c) an axis WITHOUT a component (the integer yaws 0 / 180: no y; rows without z) starts at t = -inf when the start
+      // point is not on a voxel face: the RayCaster "steps" it once, by zero voxels, before it turns NaN for good
+      // (integrator_utils.cc:165-179), so such a ray emits its start voxel once more and ends up to two voxels short of its
+      // end voxel -- its counter can run out while tcur < tB.  Its stretches therefore end before the last three crossings
+      // of its densest axis; the general loop, which counts, walks the rest.
+      if (zero_axis) tB = fminf(tB, tstop);
       if (risky) tlo = 3.0e38f;
     }
 
