@@ -906,7 +906,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
     // plane, walks all its voxels in the general loop, which counts every step -- and (c) below.
     if (kFilter) {
       const float room = 1.0f - tB;
-      bool risky = !(room > 1.0e-4f);
+      bool risky = !(room > 1.0e-4f) || len > 250;  // (the window loop's packed accumulator holds 255 voxels)
       bool zero_axis = false;
       float dmin = 3.0e38f, tstop = -1.0f;  // the densest stepping axis and the entry time of its third-last counted crossing
 #pragma unroll
@@ -1075,7 +1075,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
         // an occupied voxel (code 3) or when the next voxel is entered at or beyond tB (3).  An occupied voxel is accumulated
         // and stepped past like any other and taken out again below.
         if (run && tcur > tA && tcur < tB) {
-          unsigned last;
+          // acc += (code + 1024)^2 = 2^20 + 2048 code + code^2 per voxel: voxels walked, sum of codes and sum of squared codes
+          // from ONE multiply-add (a stretch is at most 255 voxels: 2048 * 510 + 1020 < 2^20)
+          unsigned last, acc = 0u;
           asm volatile(
               "{\n\t"
               ".reg .pred m0, m1, m2, pn, pc;\n\t"
@@ -1084,29 +1086,29 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
               "shr.u32 ad, %3, 3;\n\t"
               "and.b32 ad, ad, 0xFFFFFFFC;\n\t"
               "ld.shared.u32 wd, [ad];\n\t"
-              "min.f32 %6, %0, %1, %2;\n\t"               // t[0] is never NaN here (such rays end in the general loop)
-              "setp.eq.f32 m0, %0, %6;\n\t"               // first minimum: axis 0 on ties, then axis 1
-              "setp.eq.and.f32 m1, %1, %6, !m0;\n\t"
-              "setp.neu.and.f32 m2, %1, %6, !m0;\n\t"
-              "shf.r.wrap.b32 %7, wd, 0, %3;\n\t"
-              "and.b32 %7, %7, 3;\n\t"
-              "@m0 add.rn.f32 %0, %0, %8;\n\t"
-              "@m1 add.rn.f32 %1, %1, %9;\n\t"
-              "@m2 add.rn.f32 %2, %2, %10;\n\t"
-              "selp.b32 ad, %12, %13, m1;\n\t"
-              "selp.b32 ad, %11, ad, m0;\n\t"
+              "min.f32 %5, %0, %1, %2;\n\t"               // t[0] is never NaN here (such rays end in the general loop)
+              "setp.eq.f32 m0, %0, %5;\n\t"               // first minimum: axis 0 on ties, then axis 1
+              "setp.eq.and.f32 m1, %1, %5, !m0;\n\t"
+              "setp.neu.and.f32 m2, %1, %5, !m0;\n\t"
+              "shf.r.wrap.b32 %6, wd, 0, %3;\n\t"
+              "lop3.b32 %6, %6, 3, %14, 0xEA;\n\t"        // (word >> (P & 31)) & 3 | 1024
+              "@m0 add.rn.f32 %0, %0, %7;\n\t"
+              "@m1 add.rn.f32 %1, %1, %8;\n\t"
+              "@m2 add.rn.f32 %2, %2, %9;\n\t"
+              "selp.b32 ad, %11, %12, m1;\n\t"
+              "selp.b32 ad, %10, ad, m0;\n\t"
               "add.s32 %3, %3, ad;\n\t"
-              "add.u32 %4, %4, %7;\n\t"
-              "add.u32 %4, %4, 0x10000;\n\t"
-              "mad.lo.u32 %5, %7, %7, %5;\n\t"
-              "setp.ne.u32 pn, %7, 3;\n\t"
-              "setp.lt.and.f32 pc, %6, %14, pn;\n\t"
+              "mad.lo.u32 %4, %6, %6, %4;\n\t"
+              "setp.ne.u32 pn, %6, 1027;\n\t"
+              "setp.lt.and.f32 pc, %5, %13, pn;\n\t"
               "@pc bra NBVW_LOOP;\n\t"
               "}"
-              : "+f"(t[0]), "+f"(t[1]), "+f"(t[2]), "+r"(P), "+r"(S1), "+r"(S2), "+f"(tcur), "=&r"(last)
-              : "f"(dt[0]), "f"(dt[1]), "f"(dt[2]), "r"(stx), "r"(sty), "r"(stz), "f"(tB)
+              : "+f"(t[0]), "+f"(t[1]), "+f"(t[2]), "+r"(P), "+r"(acc), "+f"(tcur), "=&r"(last)
+              : "f"(dt[0]), "f"(dt[1]), "f"(dt[2]), "r"(stx), "r"(sty), "r"(stz), "f"(tB), "r"(1024u)
               : "memory");
-          if (last == 3u) {  // the occupied voxel that stopped the ray: executed, not counted as anything else
+          S1 += ((acc >> 20) << 16) + ((acc >> 11) & 0x1FFu);
+          S2 += acc & 0x7FFu;
+          if (last == 1027u) {  // the occupied voxel that stopped the ray: executed, not counted as anything else
             occ = 1u;
             S1 -= 3u;
             S2 -= 9u;

@@ -85,13 +85,14 @@ def main():
                     if g.check_motion(le, cfg.robot_radius, c.segments[i, :3], c.segments[i, 3:]) != bool(fo["free"][i]):
                         msg.append(f"variant {variant}: check_motion({i}) differs")
             if variant == 0:
-                # one call per planning step (edge check beside the sweep) against the two calls and the oracle
+                # one call per planning step against the two calls and the oracle (no gain behind a colliding edge: rrt.cpp:210-216)
                 nc = len(c.positions)
                 py = np.linspace(-3.0, 3.0, nc)
                 two = g.gain_eval_best(lt, c.positions, py, c.distance, fg, 1.0, 0.5, 0.0)
                 one = g.evaluate_candidates(lt, le, cfg.robot_radius, c.positions, c.segments, py, c.distance, 1.0, 0.5, 0.0)
-                if not (np.array_equal(one["free"], fo["free"]) and np.array_equal(one["gain"], ro["gain"][:nc]) and
-                        np.array_equal(one["yaw_deg"], ro["yaw_deg"][:nc]) and
+                fr = fo["free"] == 1
+                if not (np.array_equal(one["free"], fo["free"]) and np.array_equal(one["gain"], np.where(fr, ro["gain"][:nc], 0.0)) and
+                        np.array_equal(one["yaw_deg"], np.where(fr, ro["yaw_deg"][:nc], 0)) and
                         all(one[k] == two[k] for k in ("index", "score", "best_gain", "best_yaw"))):
                     msg.append("evaluate_candidates differs from the two calls / the oracle")
             if variant == 2 and g.classifier_mismatches() != 0:
