@@ -1271,6 +1271,89 @@ __global__ void __launch_bounds__(1024) k_score_best(const double* __restrict__ 
   }
 }
 
+// Window scan and node scoring in one launch (large batches): CTA v finishes candidate v (best_yaw_cta), scores it
+// (rrt.cpp:220-234) and takes a ticket; the CTA that draws the last ticket reduces the n scores to the best node
+// (rrt.cpp:243-246: first strict maximum over zero_gain, lowest index on ties) and posts it.  A masked candidate scores -inf,
+// which never wins (strict comparison).
+struct ScoreArgs {
+  const double* parent_yaw;   // [n]
+  const double* distance;     // [n]
+  const uint8_t* edge_free;   // [n] or null
+  double v_max, dyaw_max, zero_gain;
+  double* score;              // [n] scratch
+  int* counter;               // zero between launches
+  BestRecord* out;            // device record or null
+  BestPost post;
+};
+__device__ __forceinline__ double node_score(double gain, int yaw_deg, double parent_yaw, double distance, double v_max, double dyaw_max) {
+  const double yaw = __ddiv_rn(dmul((double)yaw_deg, 3.14159265358979323846), 180.0);  // rrt.cpp:477
+  double dy = dsub(yaw, parent_yaw);                                                   // :225
+  if (dy > 3.14159265358979323846) dy = dsub(dy, dmul(2.0, 3.14159265358979323846));
+  if (dy < -3.14159265358979323846) dy = dadd(dy, dmul(2.0, 3.14159265358979323846));
+  const double ta = __ddiv_rn(dy, dyaw_max), tb = __ddiv_rn(distance, v_max);
+  const double time = (ta < tb) ? tb : ta;  // std::max (:232-233)
+  return __ddiv_rn(gain, time);             // :234
+}
+__global__ void __launch_bounds__(128) k_best_yaw_score(const BestYawArgs a, const ScoreArgs sc) {
+  __shared__ double vg[360];
+  __shared__ double s_score[4];
+  __shared__ int s_idx[4];
+  __shared__ int s_last;
+  const int v = (int)blockIdx.x, tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned seq = 0u;
+  if (tid == 32 && sc.post.slot) seq = *reinterpret_cast<const volatile unsigned*>(sc.post.seq_src);  // early: a round trip to host memory
+  best_yaw_cta(a, v, vg, tid, (int)blockDim.x);
+  __syncthreads();
+  if (tid == 0) {
+    const bool ok = !sc.edge_free || sc.edge_free[v];
+    sc.score[v] = ok ? node_score(a.gain[v], a.yaw_deg[v], sc.parent_yaw[v], sc.distance[v], sc.v_max, sc.dyaw_max) : -INFINITY;
+    __threadfence();
+    s_last = (atomicAdd(sc.counter, 1) == a.n - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (!s_last) return;  // CTA-uniform
+  __threadfence();
+  double best = sc.zero_gain;
+  int best_i = INT_MAX;
+  for (int i = tid; i < a.n; i += (int)blockDim.x) {
+    const double s = __ldcg(sc.score + i);
+    if (s > best) { best = s; best_i = i; }  // ascending i per thread: first strict maximum
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+    if (ob > best || (ob == best && oi < best_i)) { best = ob; best_i = oi; }
+  }
+  if (lane == 0) { s_score[warp] = best; s_idx[warp] = best_i; }
+  seq = __shfl_sync(0xffffffffu, seq, 0);  // warp 1 holds it in its lane 0
+  __syncthreads();
+  if (warp != 1) return;
+  if (lane == 0) {
+    best = s_score[0];
+    best_i = s_idx[0];
+    for (int w = 1; w < 4; ++w)
+      if (s_score[w] > best || (s_score[w] == best && s_idx[w] < best_i)) { best = s_score[w]; best_i = s_idx[w]; }
+    BestRecord r;
+    if (best_i == INT_MAX) {
+      r.index = -1; r.score = sc.zero_gain; r.gain = 0.0; r.yaw = 0.0;
+    } else {
+      r.index = best_i; r.score = best; r.gain = __ldcg(a.gain + best_i);
+      r.yaw = __ddiv_rn(dmul((double)__ldcg(a.yaw_deg + best_i), 3.14159265358979323846), 180.0);
+    }
+    if (sc.out) *sc.out = r;
+    *sc.counter = 0;
+    if (sc.post.slot) {  // record first, system-wide fence, then the ticket the hosts poll
+      char* const slot = reinterpret_cast<char*>(sc.post.slot) + (seq & 1u) * sc.post.stride;
+      volatile BestRecord* s = reinterpret_cast<volatile BestRecord*>(slot);
+      s->index = r.index >= 0 ? r.index + sc.post.index_offset : -1;
+      s->score = r.score; s->gain = r.gain; s->yaw = r.yaw;
+      __threadfence_system();
+      *reinterpret_cast<volatile unsigned*>(slot + 32) = seq;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Batched RrtTree::iterate front half (rrt.cpp:172-212,223): sample -> reject -> nearest parent ->
 // clip -> edge with overshoot.  One thread per uniform triple; FP64 in the reference's operation order.

@@ -210,6 +210,7 @@ struct nbvgpu_ctx {
   unsigned long long* d_totals = nullptr;  // rays, voxel steps, collision steps, classifier mismatches
   PinBuf h_io;                             // pinned staging for n-sized inputs / outputs
   DevBuf d_pos, d_per_yaw, d_gain, d_yaw, d_counts, d_steps, d_seg, d_free, d_aux, d_best;
+  DevBuf d_score, d_scores;  // ticket counter / per-candidate scores of the fused window-scan + scoring launch
   DevBuf d_zrange;  // {min, max} voxel row of the candidates (z-clipped dense volume); NOT d_aux: callers keep live data there
   DevBuf d_fr_cells, d_fr_cur, d_fr_next, d_fr_slots, d_fr_io;  // History::bfs workspaces (nbvgpu_frontier_potential)
   unsigned long long stats_frontier_hash_redo = 0;              // vertices the dense visited set handed to the hash set
@@ -639,7 +640,7 @@ static int ticket_wait(nbvgpu_ctx* ctx) {
 // valid regardless (the other kernels read it).
 int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, double* d_gain, int32_t* d_yaw_deg,
                  uint64_t* d_counts, uint32_t* d_per_yaw, uint64_t* d_steps, const uint8_t* d_valid = nullptr,
-                 const double* pos1 = nullptr) {
+                 const double* pos1 = nullptr, ScoreArgs* score = nullptr, bool* scored = nullptr) {
   if (n == 0) return NBVGPU_OK;
   if (n > (size_t)INT_MAX / 1080) return fail(ctx, NBVGPU_ERR_INVALID, "too many candidates in one call");
   if (!d_per_yaw) {
@@ -949,6 +950,20 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     ctx->stats_fused++;
     return NBVGPU_OK;
   }
+  if (score && d_yaw_deg) {  // window scan + node scoring + best node in one launch
+    if (!ctx->d_score.p) {
+      CK(ctx->d_score.reserve(64));
+      CK(cudaMemsetAsync(ctx->d_score.p, 0, 64, ctx->stream));
+    }
+    CK(ctx->d_scores.reserve(n * sizeof(double)));
+    score->score = ctx->d_scores.as<double>();
+    score->counter = ctx->d_score.as<int>();
+    k_best_yaw_score<<<(unsigned)n, 128, 0, ctx->stream>>>(b, *score);
+    CK(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    if (scored) *scored = true;
+    return NBVGPU_OK;
+  }
   k_best_yaw<<<(unsigned)n, 128, 0, ctx->stream>>>(b);
   CK(cudaGetLastError());
   ctx->stats.kernel_launches++;
@@ -994,9 +1009,13 @@ int best_device_nolock(nbvgpu_ctx* ctx, int layer, size_t n, const double* d_pos
     CK(ctx->d_yaw.reserve(n * 4 + 4));
     d_yaw_deg = ctx->d_yaw.as<int32_t>();
   }
-  const int rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr, d_edge_free);  // rrt.cpp:210-216: no gain behind a colliding edge
-  if (rc) return rc;
   static_assert(sizeof(BestRecord) == sizeof(nbvgpu_best), "record layout");
+  ScoreArgs sc{d_parent_yaw, d_distance, d_edge_free, v_max, dyaw_max, zero_gain, nullptr, nullptr, reinterpret_cast<BestRecord*>(d_best), post};
+  bool scored = false;
+  const int rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr, d_edge_free, nullptr, &sc,
+                              &scored);  // rrt.cpp:210-216: no gain behind a colliding edge
+  if (rc) return rc;
+  if (scored) return NBVGPU_OK;
   k_score_best<<<1, 1024, 0, ctx->stream>>>(d_gain, d_yaw_deg, d_parent_yaw, d_distance, d_edge_free, (int)n, v_max, dyaw_max,
                                             zero_gain, reinterpret_cast<BestRecord*>(d_best), nullptr, post);
   CK(cudaGetLastError());
@@ -1032,8 +1051,11 @@ int evaluate_device_nolock(nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer, doub
   int rc = enqueue_segments(ctx, E, radius, n, d_seg, d_edge_free);
   ctx->want_ticket = ticket;
   if (rc) return rc;
-  rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr, d_edge_free);
+  ScoreArgs sc{d_parent_yaw, d_distance, d_edge_free, v_max, dyaw_max, zero_gain, nullptr, nullptr, reinterpret_cast<BestRecord*>(d_best), post};
+  bool scored = false;
+  rc = enqueue_gain(ctx, L, n, d_pos, d_gain, d_yaw_deg, nullptr, nullptr, nullptr, d_edge_free, nullptr, &sc, &scored);
   if (rc) return rc;
+  if (scored) return NBVGPU_OK;
   k_score_best<<<1, 1024, 0, ctx->stream>>>(d_gain, d_yaw_deg, d_parent_yaw, d_distance, d_edge_free, (int)n, v_max, dyaw_max,
                                             zero_gain, reinterpret_cast<BestRecord*>(d_best), nullptr, post);
   CK(cudaGetLastError());
@@ -1065,6 +1087,7 @@ StepKey step_key_base(const nbvgpu_ctx* ctx, int tsdf_layer, int esdf_layer) {
   k.add(ctx->d_per_yaw.p);
   k.add(ctx->d_gain.p);
   k.add(ctx->d_yaw.p);
+  k.add(ctx->d_scores.p);
   return k;
 }
 void destroy_step_graph(nbvgpu_ctx::StepGraph& g) {
@@ -1562,7 +1585,7 @@ static void destroy_member(nbvgpu_ctx* ctx) {
     if (ctx->h_ticket) cudaFreeHost(ctx->h_ticket);
     for (auto& kv : ctx->dense_info) kv.second.d_vmin.release();
     for (DevBuf* b : {&ctx->d_pos, &ctx->d_per_yaw, &ctx->d_gain, &ctx->d_yaw, &ctx->d_counts, &ctx->d_steps, &ctx->d_seg,
-                      &ctx->d_free, &ctx->d_aux, &ctx->d_best, &ctx->d_zrange, &ctx->d_arrive, &ctx->d_fr_cells, &ctx->d_fr_cur, &ctx->d_fr_next,
+                      &ctx->d_free, &ctx->d_aux, &ctx->d_best, &ctx->d_zrange, &ctx->d_score, &ctx->d_scores, &ctx->d_arrive, &ctx->d_fr_cells, &ctx->d_fr_cur, &ctx->d_fr_next,
                       &ctx->d_fr_slots, &ctx->d_fr_io})
       b->release();
     for (auto& pr : ctx->prof_events) {
