@@ -10,8 +10,8 @@ Workload (no flags): BASELINE.json configs[2] ("cfg3": 50x50x10 m office-like TS
 range, 10,000 candidates with their parent edges) -- the 10k-candidate workload north_star's scaling target names; it fits
 one GPU.  STRONG scaling: with N GPUs the same 10,000 candidates are sharded inside libnbvgpu.so (one process per GPU,
 nbvgpu_create_rank), the map is replicated by nbvgpu_commit (page-locked H2D on rank 0 + ncclBroadcast).  `extra` carries
-configs[1] (cfg2) and configs[4] (cfg5, incremental replay) measured in the same run; `--config cfg4` measures configs[3]
-with the map replication inside every step.
+configs[1] (cfg2), configs[4] (cfg5, incremental replay) and configs[3] (cfg4: 100x100x20 m at 0.05 m, 8 m range, the 7 GB map
+replicated inside every one of its three steps) measured in the same run; `--config cfgN` measures one configuration alone.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfgX] [--extra cfgA,cfgB]
 
@@ -46,8 +46,8 @@ def parse_args():
     ap.add_argument("--config", default="cfg3", help="cfg1..cfg5 (BASELINE.json configurations; cfg3, the 10,000-candidate workload, is the "
                     "headline), or one of the side measurements: frontier (History::bfs), interp (ESDF interpolation), shipped "
                     "(the reference's shipped geometry)")
-    ap.add_argument("--extra", default=None, help="comma-separated configurations measured as sub-records (default: cfg2,cfg5 with the "
-                    "default headline, none otherwise)")
+    ap.add_argument("--extra", default=None, help="comma-separated configurations measured as sub-records (default: cfg2,cfg5,cfg4 with "
+                    "the default headline, none otherwise)")
     ap.add_argument("--no-l2-probe", action="store_true")
     ap.add_argument("--map", default="cfg1", help="map of the frontier / interp side measurements")
     ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU (default: the config's)")
@@ -59,7 +59,7 @@ def parse_args():
     ap.add_argument("--traj-prefix", type=int, default=0, help="use only the first N trajectory points for the map")
     a = ap.parse_args()
     if a.extra is None:
-        a.extra = "cfg2,cfg5" if (a.config == "cfg3" and not a.candidates and a.impl == "ours") else ""
+        a.extra = "cfg2,cfg5,cfg4" if (a.config == "cfg3" and not a.candidates and a.impl == "ours") else ""
     return a
 
 
@@ -703,7 +703,9 @@ def run_ours(args):
         if e == "cfg5":
             r = bench_replay(rig, sub, e, min(200, max(args.steps, 50)))
         else:
-            r = bench_gain_config(rig, sub, e, min(args.steps, 20), args.warmup, True, False, include_replication=(e == "cfg4"))
+            # config 4: 16.7 M voxel-steps per viewpoint and 7 GB of map replicated inside every step: three steps are enough
+            r = bench_gain_config(rig, sub, e, 3 if e == "cfg4" else min(args.steps, 20), 1 if e == "cfg4" else args.warmup, True, False,
+                                  include_replication=(e == "cfg4"))
         if r is not None:
             for k in ("dtype", "data", "higher_is_better", "vs_baseline", "metric", "unit"):
                 r.pop(k, None)

@@ -26,12 +26,17 @@
  *
  * Threading (mirrors the reference): gain_eval from the planner
  * thread, check_segments from planner and history threads, layer_update/commit
- * from the map (ROS spin) thread.  Every entry point is serialised on the
- * context by a mutex; work is ordered on one CUDA stream, so an evaluation always
- * sees the map as of the last nbvgpu_commit enqueued before it.
+ * from the map (ROS spin) thread -- concurrently.  The host-buffer evaluators are
+ * re-entrant: each holds the context's snapshot lock shared and runs on a lane of
+ * its own (the context's stream and staging when free, else a lane context with
+ * its own high-priority stream), so a checkMotion does not queue behind a gain
+ * batch.  layer_update / layer_remove only stage and run beside everything;
+ * commit, layer_create / clear, set_camera, set_stream and set_kernel_variant take
+ * the snapshot lock exclusively, so an evaluation sees the map exactly as of one
+ * commit.
  *
- * "_device" variants take DEVICE pointers (inputs already resident in HBM, e.g.
- * the result of an NCCL broadcast) and are asynchronous on the context stream.
+ * "_device" variants take DEVICE pointers (inputs already resident in HBM) and
+ * are asynchronous on the context's own stream (nbvgpu_set_stream).
  */
 #ifndef NBVGPU_H_
 #define NBVGPU_H_

@@ -1301,7 +1301,6 @@ __global__ void __launch_bounds__(128) k_best_yaw_score(const BestYawArgs a, con
   __shared__ int s_last;
   const int v = (int)blockIdx.x, tid = (int)threadIdx.x, lane = tid & 31, warp = tid >> 5;
   unsigned seq = 0u;
-  if (tid == 32 && sc.post.slot) seq = *reinterpret_cast<const volatile unsigned*>(sc.post.seq_src);  // early: a round trip to host memory
   best_yaw_cta(a, v, vg, tid, (int)blockDim.x);
   __syncthreads();
   if (tid == 0) {
@@ -1313,6 +1312,8 @@ __global__ void __launch_bounds__(128) k_best_yaw_score(const BestYawArgs a, con
   __syncthreads();
   if (!s_last) return;  // CTA-uniform
   __threadfence();
+  // the last CTA only: the evaluation's sequence number comes from host memory (one PCIe round trip, issued first)
+  if (tid == 32 && sc.post.slot) seq = *reinterpret_cast<const volatile unsigned*>(sc.post.seq_src);
   double best = sc.zero_gain;
   int best_i = INT_MAX;
   for (int i = tid; i < a.n; i += (int)blockDim.x) {

@@ -1,5 +1,7 @@
-"""Writes profiles/ncu_traffic.json (read by bench.py for roofline.traffic) from an `ncu --set full`
-capture of the ray-sweep kernel:  python profiles/summarize_ncu.py gpurun_out/r1_prof_gain.ncu-rep"""
+"""Merges one `ncu --set full` capture of the ray-sweep kernel into profiles/ncu_traffic.json, keyed by the BASELINE
+configuration it was taken on (bench.py reads roofline.traffic from there; a configuration without a capture reports null):
+    python profiles/summarize_ncu.py gpurun_out/r2_cfg3_prof.ncu-rep cfg3 "2000 of 10000 candidates per launch"
+dram bytes are per LAUNCH of the capture; `candidates_in_capture` lets bench.py scale them to its own launch size."""
 import csv
 import json
 import os
@@ -7,6 +9,8 @@ import subprocess
 import sys
 
 rep = sys.argv[1]
+config = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
+note = sys.argv[3] if len(sys.argv) > 3 else ""
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -37,6 +41,16 @@ out = {
     "warp_instructions": d["smsp__inst_executed.sum"][1],
     "threads_per_instruction": d["smsp__thread_inst_executed_per_inst_executed.ratio"][1],
 }
+out["note"] = note
+out["block_size"] = d["launch__block_size"][1]
+out["shared_mem_per_block_dynamic_kb"] = d["launch__shared_mem_per_block_dynamic"][1]
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "ncu_traffic.json")
-json.dump(out, open(path, "w"), indent=1)
+try:
+    allrec = json.load(open(path))
+    if "k_gain_dram_bytes_per_launch" in allrec:   # round-1 layout: a single record (cfg2)
+        allrec = {"cfg2_round1": allrec}
+except Exception:
+    allrec = {}
+allrec[config] = out
+json.dump(allrec, open(path, "w"), indent=1)
 print(json.dumps(out, indent=1))
