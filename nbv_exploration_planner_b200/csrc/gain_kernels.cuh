@@ -89,6 +89,8 @@ struct GainArgs {
   int gmin[3];
   unsigned gspan[3];
   int reach_vox;
+  int gz_lo;          // lower end of the slot grid along z, in voxels relative to the candidate's voxel (>= -reach_vox: the rays'
+                      // own z-extent, so that fine voxels do not pay for a cube of blocks the frustum never reaches)
   int unknown_slot;   // tile index of the all-unknown / zero tile (== max_blocks)
   int gnx, gny, gnz;  // local block grid dimensions
   int yc;             // yaws per CTA (divides 360)
@@ -592,7 +594,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
   }
   // Voxel containing the candidate position and the origin of the local block grid.
   const int g0x = (int)floor(px * a.vs_inv), g0y = (int)floor(py * a.vs_inv), g0z = (int)floor(pz * a.vs_inv);
-  const int b0x = (g0x - a.reach_vox) >> lv, b0y = (g0y - a.reach_vox) >> lv, b0z = (g0z - a.reach_vox) >> lv;
+  const int b0x = (g0x - a.reach_vox) >> lv, b0y = (g0y - a.reach_vox) >> lv, b0z = (g0z + a.gz_lo) >> lv;
 
   // (a) block-slot grid: one hash probe per reachable block; (b) per-yaw frames
   for (int i = tid; i < gn; i += blockDim.x) {
@@ -626,7 +628,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
   __syncthreads();
   for (int j = tid; j < yc; j += blockDim.x) atomicMax(&s_umax, S.um[j]);
 
-  // (c) dense status volume, one (y, z) row of Xw words per thread and iteration
+  // (c) dense status volume, filled strip by strip (see below)
   int x0 = 0, y0 = 0, z0 = 0, vxw = 0, vey = 0, nvol = 0;
   if (kIsDense) {
     y0 = g0y + a.vmin[5 * chunk + 1];
@@ -648,51 +650,51 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
       }
     }
     nvol = vxw * vey * vez_c;
-    const int nrows = vey * vez_c;
-    int ry = tid % vey, rz = tid / vey;                             // row = rz * vey + ry
-    const int dy = (int)blockDim.x % vey, dz = (int)blockDim.x / vey;  // row += blockDim.x
-    for (int row = tid; row < nrows; row += blockDim.x) {
-      const int gy = y0 + ry, gz = z0 + rz;
-      const bool row_in = (unsigned)(gy - a.gmin[1]) <= a.gspan[1] && (unsigned)(gz - a.gmin[2]) <= a.gspan[2];
-      const int iy = (gy >> 4) - b0y, iz = (gz >> 4) - b0z;
-      const bool row_grid = (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz;
-      const unsigned rowoff = (unsigned)(((gz & 15) << 4) | (gy & 15));
-      const int ix0 = (x0 >> 4) - b0x;
-      const int* const grow = S.grid + (iz * a.gny + iy) * a.gnx;
-      uint32_t* const vrow = vol + row * vxw;
-      // four words at a time: the status-tile loads of a group are issued before any is used
-      for (int wx0 = 0; wx0 < vxw; wx0 += 4) {
-        uint32_t om[4], word[4];
-        bool use[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int wx = wx0 + q;
-          om[q] = wx < vxw ? s_outm[wx] : 0xFFFFFFFFu;  // voxels of this word outside the exploration box along x
-          use[q] = row_in && om[q] != 0xFFFFFFFFu;
-          word[q] = 0u;
-          if (use[q]) {
-            const int ix = ix0 + wx;
-            int slot;
-            if (row_grid && (unsigned)ix < (unsigned)a.gnx) {
-              slot = grow[ix];
-            } else {
-              slot = probe_block(a.L, (x0 >> 4) + wx, gy >> 4, gz >> 4);
-              if (slot < 0) slot = a.unknown_slot;
-            }
-            word[q] = __ldg(a.L.status + ((unsigned)slot * 256u + rowoff));
-          }
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t w = word[q];
-          w |= (w >> 1) & 0x55555555u;  // tile status 2 (occupied) -> code 3
-          w = use[q] ? ((w & ~om[q]) | (om[q] & 0xAAAAAAAAu)) : 0xAAAAAAAAu;  // "skip" outside the box
-          if (wx0 + q < vxw) vrow[wx0 + q] = w;
+    // One item = one x word of up to 16 consecutive y rows that share a block (a "strip"): the box mask of the word, the z test and
+    // the block's tile slot are looked up once per strip, a row then costs one load of a status-tile word, four logic operations
+    // and one store (the loads of four rows are issued before any is used).
+    const int yb0 = y0 >> 4;
+    const int nyb = ((y0 + vey - 1) >> 4) - yb0 + 1;
+    const int nitems = vxw * nyb * vez_c;
+    for (int it = tid; it < nitems; it += blockDim.x) {
+      const int q = it / vxw, wx = it - q * vxw;
+      const int rz = q / nyb, yb = q - rz * nyb;
+      const int gz = z0 + rz;
+      const int ylo = max(y0, (yb0 + yb) << 4), yhi = min(y0 + vey - 1, ((yb0 + yb) << 4) + 15);
+      const uint32_t om = s_outm[wx];  // voxels of this word outside the exploration box along x
+      const bool use_col = (unsigned)(gz - a.gmin[2]) <= a.gspan[2] && om != 0xFFFFFFFFu;
+      int slot = a.unknown_slot;
+      if (use_col) {
+        const int ix = (x0 >> 4) - b0x + wx, iy = yb0 + yb - b0y, iz = (gz >> 4) - b0z;
+        if ((unsigned)ix < (unsigned)a.gnx && (unsigned)iy < (unsigned)a.gny && (unsigned)iz < (unsigned)a.gnz) {
+          slot = S.grid[(iz * a.gny + iy) * a.gnx + ix];
+        } else {
+          slot = probe_block(a.L, (x0 >> 4) + wx, yb0 + yb, gz >> 4);
+          if (slot < 0) slot = a.unknown_slot;
         }
       }
-      ry += dy;
-      rz += dz;
-      if (ry >= vey) { ry -= vey; ++rz; }
+      const uint32_t* const src = a.L.status + ((unsigned)slot * 256u + (unsigned)((gz & 15) << 4));
+      uint32_t* dst = vol + ((rz * vey + (ylo - y0)) * vxw + wx);
+      const int ylo_in = max(ylo, a.gmin[1]);  // rows of the strip inside the box along y: ylo_in .. yhi_in
+      const long long yhi_box = (long long)a.gmin[1] + (long long)a.gspan[1];
+      const int yhi_in = yhi_box < (long long)yhi ? (int)yhi_box : yhi;
+      for (int gy = ylo; gy <= yhi; gy += 4) {
+        uint32_t word[4];
+        bool use[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          use[r] = use_col && gy + r >= ylo_in && gy + r <= yhi_in;
+          word[r] = use[r] ? __ldg(src + ((gy + r) & 15)) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          uint32_t w = word[r];
+          w |= (w >> 1) & 0x55555555u;  // tile status 2 (occupied) -> code 3
+          w = use[r] ? ((w & ~om) | (om & 0xAAAAAAAAu)) : 0xAAAAAAAAu;  // "skip" outside the box
+          if (gy + r <= yhi) dst[r * vxw] = w;
+        }
+        dst += 4 * vxw;
+      }
     }
   }
   __syncthreads();
@@ -709,6 +711,7 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
   const float noffz = -__double2float_rn(pz - (double)g0z * a.vs);
   const FilterConst& F = a.F;
   const int stride_y = 32 * vxw, stride_z = 32 * vxw * vey;
+  const unsigned mg_xw = vxw > 1 ? 0xFFFFFFFFu / (unsigned)vxw + 1u : 0u, mg_ey = vey > 1 ? 0xFFFFFFFFu / (unsigned)vey + 1u : 0u;
   uint32_t vol_s = (uint32_t)__cvta_generic_to_shared(vol);
   asm volatile("mov.u32 %0, %0;" : "+r"(vol_s));  // opaque: keep the shared-window address in a register
 
@@ -726,6 +729,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
     // top rows first: with a floor-bounded exploration box the downward rows leave the box early, so the
     // short batches come last and the warps of a CTA finish closer together (order only; any order is exact)
     const int r = (((n_rays + 31) >> 5) << 5) - 32 - base + lane;
+    // (32 consecutive rows of one yaw per warp instead -- rays in one vertical plane -- were measured: 0.51 against 0.68 of the
+    // roofline on config 3, the lanes then differ in z and collide in the volume's banks)
     const int u = r / yc;
     const int j = r - u * yc;
     // The batch loop is warp-uniform; lanes without a ray (tail of the last batch, rows beyond this yaw's
@@ -891,7 +896,9 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
     // Voxel index from the bit address (dense kernel; once per stretch, two small integer divisions).
     auto g_from_P = [&]() {
       const unsigned rel = P - 8u * vol_s;
-      const unsigned wd = rel >> 5, row = wd / (unsigned)vxw, zz = row / (unsigned)vey;
+      // divisions by the chunk's row length / row count as multiplications by ceil(2^32 / d): exact while n * d < 2^32
+      // (word index < 2^24 and at most 32 words per row; row index * rows per slice < words * rows, checked on the host)
+      const unsigned wd = rel >> 5, row = __umulhi(wd, mg_xw), zz = vey > 1 ? __umulhi(row, mg_ey) : row;
       g[0] = x0 + (int)((wd - row * (unsigned)vxw) * 16u + ((rel & 31u) >> 1));
       g[1] = y0 + (int)(row - zz * (unsigned)vey);
       g[2] = z0 + (int)zz;
@@ -906,7 +913,8 @@ __global__ void __launch_bounds__(THREADS, 1024 / THREADS) k_gain(const GainArgs
     // plane, walks all its voxels in the general loop, which counts every step -- and (c) below.
     if (kFilter) {
       const float room = 1.0f - tB;
-      bool risky = !(room > 1.0e-4f) || len > 250;  // (the window loop's packed accumulator holds 255 voxels)
+      // (the dense window loop's packed accumulator holds 255 voxels; elsewhere the bound keeps the drift of note (a) at 6e-5)
+      bool risky = !(room > 1.0e-4f) || len > ((kIsDense && !kParanoid) ? 250 : 1000);
       bool zero_axis = false;
       float dmin = 3.0e38f, tstop = -1.0f;  // the densest stepping axis and the entry time of its third-last counted crossing
 #pragma unroll

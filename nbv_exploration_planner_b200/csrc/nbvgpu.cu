@@ -229,6 +229,10 @@ struct nbvgpu_ctx {
   std::map<int, DenseInfo> dense_info;  // per yaws-per-CTA, valid for (dense_gen, dense_vs)
   float dense_vs = 0.f;
   unsigned long long dense_gen = ~0ull, cam_gen = 0;
+  // z-extent of the rays relative to the candidate's voxel (slot grid height), valid for (camera generation, voxel size)
+  unsigned long long zext_gen = ~0ull;
+  float zext_vs = 0.0f;
+  int zext_lo = 0, zext_n = 0;  // zext_n == 0: unknown geometry, use the cube
   int force_yc = 0;  // NBVGPU_YC environment override (experiments)
   // completion ticket of single-item host calls: the kernel's last writer stores the call's sequence number here (mapped
   // pinned memory) and the host polls it -- a few microseconds sooner than the stream synchronise reports the same thing
@@ -698,14 +702,39 @@ int enqueue_gain(nbvgpu_ctx* ctx, LayerHost* L, size_t n, const double* d_pos, d
     for (int i = 9; i > 0; --i) kYc[i] = kYc[i - 1];
     kYc[0] = yc;
   }
-  size_t gn = (size_t)gdim * gdim * gdim;
+  // Along z the grid only spans the rays' own extent (the yaw turns about z, so it is the same for every yaw): with fine voxels
+  // and a long range the cube of blocks around the candidate is mostly above and below the frustum (config 4: 14 block layers
+  // instead of 25, 50 KB of shared memory per CTA instead of 77 KB, four CTAs per SM instead of two).
+  int gnz = gdim;
+  a.gz_lo = -a.reach_vox;
+  if (ctx->zext_gen != (unsigned long long)ctx->cam_gen || ctx->zext_vs != L->voxel_size) {
+    int ci[5], ez = 0;
+    long long words = 0;
+    ctx->zext_gen = (unsigned long long)ctx->cam_gen;
+    ctx->zext_vs = L->voxel_size;
+    ctx->zext_n = 0;
+    if (nbvgpu_host::dense_volume_bounds(ctx->tab, a.vs, 360, ci, &ez, &words) && ez > 0) {
+      ctx->zext_lo = ci[2];
+      ctx->zext_n = ez;
+    }
+  }
+  if (ctx->zext_n > 0 && std::getenv("NBVGPU_CUBE_GRID") == nullptr) {
+    const int lo = std::max(ctx->zext_lo, -a.reach_vox), hi = std::min(ctx->zext_lo + ctx->zext_n - 1, a.reach_vox);
+    const int nz = ((hi - lo) >> L->log2vps) + 2;
+    if (hi >= lo && nz < gdim) {
+      gnz = nz;
+      a.gz_lo = lo;
+    }
+  }
+  size_t gn = (size_t)gdim * gdim * gnz;
   size_t smem = gain_smem_bytes(yc, (int)gn);
   if (smem > (size_t)ctx->max_smem_optin || smem > 96 * 1024) {  // fall back to direct hash probes
-    gdim = 0;
+    gdim = gnz = 0;
     gn = 0;
     smem = gain_smem_bytes(yc, 0);
   }
-  a.gnx = a.gny = a.gnz = gdim;
+  a.gnx = a.gny = gdim;
+  a.gnz = gnz;
   a.yc = yc;
   a.n = (int)n;
   for (int k = 0; k < 9; ++k) a.F.R[k] = T.R_CB[k];
