@@ -328,6 +328,16 @@ class Rig:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
         return [float(x) for x in t.cpu()]
 
+    def gather(self, values):
+        """[world][len(values)] floats: every rank's values on every rank (diagnostics: per-rank step / kernel times)."""
+        torch = self.torch
+        t = torch.tensor([float(v) for v in values], dtype=torch.float64, device=self.dev)
+        if self.world == 1:
+            return [[float(x) for x in t.cpu()]]
+        out = torch.empty((self.world, len(values)), dtype=torch.float64, device=self.dev)
+        self.dist.all_gather_into_tensor(out, t)
+        return [[float(x) for x in row] for row in out.cpu()]
+
     def close(self):
         if self.world > 1:
             self.dist.destroy_process_group()
@@ -527,6 +537,7 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
     repl_med = float(np.median(repl_timed)) if repl_timed else setup_repl_ms
     dev_ms_max, e2e_s_max, kern_ms_max, repl_max = rig.reduce([dev_ms, e2e_s, kern_ms, repl_med], "max")
     vsteps_all, rays_all, launches_all, n_all, csteps_all, same_all = rig.reduce([vsteps, rays, launches, n, csteps, 0.0 if same else 1.0], "sum")
+    per_rank = rig.gather([dev_ms / steps, kern_ms / max(1, kern_launches), vsteps / max(1, kern_launches), n])
     clocks = sampler.summary()
     out = None
     if rank == 0:
@@ -567,6 +578,9 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
                          "l2": l2_info(g, ach) if not args.no_l2_probe else None,
                          "note": "8 B per executed voxel-step (SURVEY.md 8d); the status tiles the sweep reads are L2/L1 resident, so real DRAM traffic is far lower"},
             "clocks": clocks, "best": winner,
+            # per rank: device time per step (what the max is taken over), the sweep's own time per launch, voxel-steps and candidates
+            "per_rank": {"ms_per_step": [r[0] for r in per_rank], "sweep_ms": [r[1] for r in per_rank],
+                         "voxel_steps_per_launch": [r[2] for r in per_rank], "candidates": [int(r[3]) for r in per_rank]},
             "single_candidate_latency_us": lat_us,  # checkMotion + optimized_gain, n = 1, host buffers
         }
         if selfcheck is not None:
@@ -701,7 +715,7 @@ def run_ours(args):
         sub = argparse.Namespace(**vars(args))
         sub.candidates = 0
         if e == "cfg5":
-            r = bench_replay(rig, sub, e, min(200, max(args.steps, 50)))
+            r = bench_replay(rig, sub, e, 200)   # BASELINE configs[4]: the whole 200-pose trajectory (199 updates + evaluations)
         else:
             # config 4: 16.7 M voxel-steps per viewpoint and 7 GB of map replicated inside every step: three steps are enough
             r = bench_gain_config(rig, sub, e, 3 if e == "cfg4" else min(args.steps, 20), 1 if e == "cfg4" else args.warmup, True, False,

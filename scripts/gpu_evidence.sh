@@ -26,7 +26,7 @@ fi
 if has launches; then
   cmd="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-l2-probe --extra=cfg2"
   timeout 600 $cmd > $out/${tag}_launches_plain.json 2>&1 && \
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv $cmd > $out/${tag}_launches_ncu.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $out/${tag}_launches.csv $cmd > $out/${tag}_launches_ncu.log 2>&1
   echo "launches rc=$?"
 fi
 cap() {  # cap <name> <kernel regex> <skip> <bench args...>
@@ -36,8 +36,8 @@ cap() {  # cap <name> <kernel regex> <skip> <bench args...>
      python bench.py "$@" $short > $out/${tag}_${name}_ncu.log 2>&1
   echo "$name ncu rc=$?"
 }
-has ncu3 && cap k_gain_cfg3 '^k_gain' 3 --config cfg3 --candidates 2000 --steps 1 --warmup 3
+has ncu3 && cap k_gain_cfg3 '^k_gain' 3 --config cfg3 --steps 1 --warmup 3
 has ncu2 && cap k_gain_cfg2 '^k_gain' 3 --config cfg2 --steps 1 --warmup 3
-has ncu4 && cap k_gain_cfg4 '^k_gain' 1 --config cfg4 --candidates 148 --steps 1 --warmup 1
+has ncu4 && cap k_gain_cfg4 '^k_gain' 1 --config cfg4 --steps 1 --warmup 1
 has ncuup && cap k_apply_cfg3 '^k_apply_blocks' 1 --config cfg3 --candidates 500 --steps 1 --warmup 1
 ls -la $out | grep " ${tag}_" | awk '{print $5, $9}'
