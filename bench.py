@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--extra", default=None, help="comma-separated configurations measured as sub-records (default: cfg2,cfg5,cfg4 with "
                     "the default headline, none otherwise)")
     ap.add_argument("--no-l2-probe", action="store_true")
+    ap.add_argument("--no-shared-map", action="store_true", help="stage the map from rank 0's private page-locked memory (broadcast) "
+                    "instead of shared memory every GPU pulls its slice from")
     ap.add_argument("--map", default="cfg1", help="map of the frontier / interp side measurements")
     ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU (default: the config's)")
     ap.add_argument("--variant", type=int, default=0, help="gain kernel variant (A/B measurement)")
@@ -402,10 +404,31 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
     lt = g.layer_create(LAYER_TSDF, cfg.voxel_size, cfg.vps, nb + 64)
     le = g.layer_create(LAYER_ESDF, cfg.voxel_size, cfg.vps, nb + 64)
     locked = []
-    if rank == 0:
+    nvox = cfg.vps ** 3
+    map_bytes = nb * nvox * 12
+    # The map lives in memory every rank's GPU can read (nbvgpu_shared_alloc: collective; plain page-locked memory on one GPU):
+    # rank 0 -- the map's owner -- fills it, and a commit of that much data has every GPU pull its slice of each chunk over its
+    # own PCIe link before an all-gather over NVLink completes it.  --no-shared-map keeps the map in rank 0's private memory
+    # (one link + ncclBroadcast), for the A/B.
+    shared = None
+    use_shared = not args.no_shared_map
+    if use_shared and world > 1:   # across processes the memory is a POSIX shared-memory segment: it has to fit /dev/shm
+        try:
+            vfs = os.statvfs("/dev/shm")
+            use_shared = vfs.f_bavail * vfs.f_frsize > 1.25 * map_bytes
+        except OSError:
+            use_shared = False
+        use_shared = bool(rig.bcast_int(1 if use_shared else 0))
+    if use_shared:
+        shared = g.shared_alloc(map_bytes + 256)
+        if rank == 0:
+            p_tsdf = shared[:nb * nvox * 8].view(np.float32).reshape(m.tsdf.shape)
+            p_esdf = shared[nb * nvox * 8:nb * nvox * 12].view(np.float32).reshape(m.esdf.shape)
+            p_tsdf[...] = m.tsdf
+            p_esdf[...] = m.esdf
+    if shared is None and rank == 0:
         locked = [PageLocked(m.tsdf), PageLocked(m.esdf)]
         p_tsdf, p_esdf = locked[0].buffer, locked[1].buffer
-    map_bytes = nb * cfg.vps ** 3 * 12
 
     def replicate():
         """rank 0: stage the whole map from page-locked memory; all ranks: commit.  Returns wall ms (commit is synchronous)."""
@@ -538,6 +561,7 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
     dev_ms_max, e2e_s_max, kern_ms_max, repl_max = rig.reduce([dev_ms, e2e_s, kern_ms, repl_med], "max")
     vsteps_all, rays_all, launches_all, n_all, csteps_all, same_all = rig.reduce([vsteps, rays, launches, n, csteps, 0.0 if same else 1.0], "sum")
     per_rank = rig.gather([dev_ms / steps, kern_ms / max(1, kern_launches), vsteps / max(1, kern_launches), n])
+    pulled = g.pulled_chunks()
     clocks = sampler.summary()
     out = None
     if rank == 0:
@@ -554,12 +578,15 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
             "config": {"workload": workload_text(cfg, name, n_all, n), "candidates_total": int(n_all), "map_blocks": nb,
                        "l2": "flushed between steps (256 MiB write)", "kernel_variant": args.variant,
                        "parallelism": f"candidates sharded over {world} GPU(s) inside libnbvgpu.so, map replicated by nbvgpu_commit "
-                                      f"(page-locked H2D on rank 0 + ncclBroadcast of {{descriptor table | payload}} per 64 MiB chunk); best "
-                                      f"records through GPU stores into shared host memory (no collective per step)",
+                                      + (f"(the map lies in shared page-locked memory: per 64 MiB chunk every GPU copies 1/{world} over its own "
+                                         f"PCIe link, ncclAllGather over NVLink completes it; {pulled} chunks so far)" if pulled else
+                                         "(page-locked H2D on rank 0 + ncclBroadcast of {descriptor table | payload} per 64 MiB chunk)")
+                                      + "; best records through GPU stores into shared host memory (no collective per step)",
                        "map_replication": {"ms": first_repl, "bytes": map_bytes, "gb_per_s": map_bytes / (first_repl * 1e-3) / 1e9 if first_repl else None,
                                            "first_commit_ms": cold_repl_ms, "inside_timed_steps": bool(include_replication),
+                                           "pulled_chunks": pulled,
                                            "what": "host wall clock of layer_clear x2 excluded; rank 0 stages TSDF + ESDF from page-locked "
-                                                   "memory, every rank commits: H2D + ncclBroadcast + scatter kernel, max over ranks"},
+                                                   "memory, every rank commits: H2D (its slice when pulled) + NCCL + scatter kernel, max over ranks"},
                        "setup_s": setup_s, "inputs_sha256": inputs_sha},
             "rays_per_s": rays_all / (dev_ms_max * 1e-3), "voxel_steps_per_s": vsteps_all / (dev_ms_max * 1e-3),
             "voxel_steps_per_viewpoint": vsteps_all / max(1.0, n_all * steps),

@@ -161,6 +161,18 @@ int nbvgpu_layer_update(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32
  * can serialise Layer::getAllUpdatedBlocks into such a buffer). */
 int nbvgpu_layer_update_pinned(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32_t* keys,
                                const void* payload, int packing);
+/* Page-locked host memory that EVERY GPU of the context can read by DMA: portable cudaHostAlloc memory when one process drives
+ * the context (nbvgpu_create, nbvgpu_create_multi); in a one-process-per-GPU context (nbvgpu_create_rank) a POSIX shared-memory
+ * segment that every rank maps and page-locks -- there the call is COLLECTIVE: every rank makes it with the same size, in the same
+ * order, and gets its own mapping of the same bytes (rank 0, the map's owner, fills it).  Blocks staged out of such memory with
+ * nbvgpu_layer_update_pinned are replicated by a parallel pull when a commit chunk carries at least NBVGPU_PULL_MIN_MB (default 8)
+ * MiB of them: every GPU copies 1/world of the chunk over its own PCIe link and one ncclAllGather over NVLink completes the chunk
+ * on every GPU, instead of rank 0's link carrying everything in front of a broadcast (7 GB map of BASELINE configs[3] on 8 GPUs:
+ * see profiles/README.md).  This is where the reference's upload hook should serialise Layer::getAllUpdatedBlocks
+ * (voxblox/core/layer.h:194-203, block.cc:159-234) when the planner owns several GPUs.  nbvgpu_shared_free releases one allocation
+ * (not while blocks staged from it await their commit); nbvgpu_destroy releases the rest. */
+int nbvgpu_shared_alloc(nbvgpu_ctx* ctx, size_t bytes, void** ptr);
+int nbvgpu_shared_free(nbvgpu_ctx* ctx, void* ptr);
 /* Same with device buffers (single-GPU contexts); applied in stream order.  A key listed twice is written by either copy. */
 int nbvgpu_layer_update_device(nbvgpu_ctx* ctx, int layer, size_t n_blocks, const int32_t* d_keys,
                                const void* d_payload, int packing);
@@ -359,6 +371,9 @@ int nbvgpu_debug_wide_cta_launches(nbvgpu_ctx* ctx, uint64_t* count);
  * parameters) is seen, are captured into a CUDA graph the second time and replayed from then on (copies of the host-buffer
  * forms included); shapes that synchronise inside (the z-clipped volume) stay eager.  NBVGPU_NO_GRAPH=1 disables it. */
 int nbvgpu_debug_graph_replays(nbvgpu_ctx* ctx, uint64_t* count);
+/* Commit chunks of a multi-GPU context that were replicated by slice pull + all-gather (nbvgpu_shared_alloc) rather than
+ * by a broadcast from rank 0. */
+int nbvgpu_debug_pulled_chunks(nbvgpu_ctx* ctx, uint64_t* count);
 /* Host-only helper for tests: the largest double x with sqrt(x) <= d (round to nearest).  The flood fill tests
  * `squared distance <= threshold` instead of `(candidate - point).norm() <= max_distance` (history.cpp:118): the two are
  * equivalent because the square root is monotone and correctly rounded.  NBVGPU_ERR_INVALID for negative or non-finite d. */

@@ -102,6 +102,9 @@ def lib() -> C.CDLL:
     L.nbvgpu_create_rank.argtypes = [C.c_int, C.c_int, C.c_int, vp, C.c_size_t, C.POINTER(vp)]
     L.nbvgpu_group_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.nbvgpu_layer_update_pinned.argtypes = [vp, C.c_int, C.c_size_t, vp, vp, C.c_int]
+    L.nbvgpu_shared_alloc.argtypes = [vp, C.c_size_t, C.POINTER(vp)]
+    L.nbvgpu_shared_free.argtypes = [vp, vp]
+    L.nbvgpu_debug_pulled_chunks.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.nbvgpu_evaluate_shard_device.argtypes = [vp, C.c_int, C.c_int, C.c_double, C.c_size_t, C.c_int64, vp, vp, vp, vp, C.c_double,
                                                C.c_double, C.c_double, vp, vp, vp, C.POINTER(Best)]
     L.nbvgpu_destroy.argtypes = [vp]
@@ -180,4 +183,5 @@ ABI_SYMBOLS = [
     "nbvgpu_debug_classifier_mismatches", "nbvgpu_set_profiling", "nbvgpu_profile_collect",
     "nbvgpu_layer_load_voxblox_file", "nbvgpu_layer_apply_layer_msg", "nbvgpu_parse_blocks", "nbvgpu_expand_tree",
     "nbvgpu_frontier_potential", "nbvgpu_esdf_distance_gradient", "nbvgpu_esdf_distance_gradient_device", "nbvgpu_evaluate_candidates", "nbvgpu_evaluate_candidates_device", "nbvgpu_debug_round_decimal6", "nbvgpu_debug_sqrt_threshold", "nbvgpu_debug_frontier_hash_redo", "nbvgpu_debug_dense_clipped_launches", "nbvgpu_debug_fused_launches", "nbvgpu_debug_wide_cta_launches", "nbvgpu_debug_graph_replays", "nbvgpu_probe_l2_read_bandwidth",
+    "nbvgpu_shared_alloc", "nbvgpu_shared_free", "nbvgpu_debug_pulled_chunks",
 ]

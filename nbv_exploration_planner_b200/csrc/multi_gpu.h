@@ -4,7 +4,10 @@
 // The path shards by candidates: every GPU holds a replica of the map mirror and evaluates a contiguous
 // block of the batch.  Two exchanges surround it:
 //   * nbvgpu_commit: the root copies {descriptor table | payload} of the changed blocks to its GPU and ncclBroadcasts
-//     that one buffer over NVLink; every GPU then applies it with the same kernel (csrc/map_mirror.cuh);
+//     that one buffer over NVLink; every GPU then applies it with the same kernel (csrc/map_mirror.cuh).  Large chunks whose
+//     payload lies in memory every rank can read (nbvgpu_shared_alloc) are PULLED instead: every GPU copies 1/world of the
+//     payload over its own PCIe link and an ncclAllGather over NVLink completes the chunk on every GPU -- the host links of
+//     all GPUs work side by side instead of rank 0's alone;
 //   * the per-shard best {score, index, gain, yaw}: each GPU's scoring kernel stores its 32-byte record straight into
 //     host memory that every rank can read (page-locked + mapped: cudaHostAlloc in one process, a POSIX shared-memory
 //     segment registered with cudaHostRegister across processes), followed by a ticket; the host polls the tickets.
@@ -103,12 +106,23 @@ struct alignas(64) BestSlot {
 static_assert(sizeof(BestSlot) == 64, "slot layout");
 
 // What the root tells the other ranks about a commit (they cannot see its staging area).
+constexpr int kMaxPullSegs = 4;
+constexpr int kMaxArenas = 16;
+struct PullSeg {                 // a piece of a chunk's payload that lies in a shared arena (nbvgpu_shared_alloc)
+  unsigned arena, pad;
+  unsigned long long src_off;    // offset inside the arena
+  unsigned long long bytes;
+  unsigned long long dst_off;    // offset inside the chunk's payload
+};
 struct ChunkInfo {
-  unsigned long long bytes;  // table + payload bytes of the chunk (what is broadcast)
+  unsigned long long bytes;  // table + payload bytes of the chunk (what is broadcast; pulled chunks: table + world * slice)
   unsigned table_bytes;      // payload starts here
   unsigned n_update;         // descriptors to apply
   unsigned n_remove;         // > 0: the chunk is the commit's removal table (no payload)
-  unsigned pad;
+  unsigned n_seg;            // > 0: pulled chunk -- every rank copies its slice of these pieces, an all-gather does the rest
+  unsigned long long slice;  // payload bytes per rank of a pulled chunk (a multiple of 256)
+  unsigned long long payload;  // payload bytes of the chunk
+  PullSeg seg[kMaxPullSegs];
 };
 struct SharedBlock {
   unsigned magic, world;
@@ -122,6 +136,10 @@ struct SharedBlock {
   alignas(64) std::atomic<unsigned long long> commit_ack[kMaxRanks];  // last commit each rank has read the plan of
   unsigned n_chunks;
   unsigned incoming[16];           // blocks arriving per layer (steers the hash-table rebuild the same way on every rank)
+  // shared arenas (nbvgpu_shared_alloc across processes): the root creates segment number i and publishes its size, the others map it
+  alignas(64) std::atomic<unsigned> arena_created;            // segments created so far
+  unsigned long long arena_bytes[kMaxArenas];
+  std::atomic<unsigned> arena_attached[kMaxArenas];           // ranks that have mapped and page-locked segment i
   ChunkInfo chunk[kMaxChunks];
 };
 
@@ -228,6 +246,37 @@ inline void shared_release(SharedMap* m) {
     cudaFreeHost(m->host);
   }
   m->host = nullptr;
+}
+
+// A named POSIX shared-memory segment of `bytes` bytes: created (create = true) or opened and mapped; null on failure.
+inline void* shm_map_segment(const std::string& name, size_t bytes, bool create, std::string* err) {
+  int fd = -1;
+  if (create) {
+    shm_unlink(name.c_str());
+    fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd >= 0 && ftruncate(fd, (off_t)bytes) != 0) {
+      close(fd);
+      shm_unlink(name.c_str());
+      fd = -1;
+    }
+  } else {
+    for (int tries = 0; tries < 2000 && fd < 0; ++tries) {
+      fd = shm_open(name.c_str(), O_RDWR, 0600);
+      if (fd < 0) std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+  }
+  if (fd < 0) {
+    *err = std::string(create ? "shm_open(create)" : "shm_open") + " failed for " + name;
+    return nullptr;
+  }
+  void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (p == MAP_FAILED) {
+    if (create) shm_unlink(name.c_str());
+    *err = "mmap failed for " + name;
+    return nullptr;
+  }
+  return p;
 }
 
 // Spin until pred() holds; false after timeout_s seconds.

@@ -137,6 +137,8 @@ struct UpdateStage {
   struct Segment {
     const char* host;  // caller's pinned memory, or null: arena + arena_off
     size_t arena_off, bytes, dev_off;
+    int shared = -1;        // >= 0: `host` lies in shared arena number `shared` (nbvgpu_shared_alloc), at byte `shared_off`:
+    size_t shared_off = 0;  // every GPU of the context can copy from it
   };
   std::vector<BlockDesc> descs;
   std::vector<Segment> segs;
@@ -173,6 +175,14 @@ struct UpdateStage {
 
 }  // namespace
 
+// Host memory every GPU of a context can read by DMA (nbvgpu_shared_alloc): page-locked portable memory in one process, a POSIX
+// shared-memory segment mapped and page-locked by every rank across processes.
+struct SharedArena {
+  char* host = nullptr;
+  size_t bytes = 0;
+  bool posix = false, registered = false;
+};
+
 struct Group;
 struct nbvgpu_ctx {
   int device = 0;
@@ -195,6 +205,7 @@ struct nbvgpu_ctx {
   std::vector<LayerHost*> layers;
   unsigned long long* d_lstate = nullptr;  // [kMaxLayers][2]: per layer live blocks | {free_top, err} (update kernels)
   UpdateStage stage;                       // staged map operations (of the root rank in a multi-GPU context)
+  std::vector<SharedArena> arenas;         // nbvgpu_shared_alloc of a plain single-GPU context (a multi-GPU context keeps them in its Group)
   PinBuf h_table[2];                       // descriptor tables of the chunks in flight
   DevBuf d_stage[2];                       // device staging of a commit: [descriptor table | payload bytes], double buffered
   DevBuf d_utab;                           // descriptor table of nbvgpu_layer_update_device
@@ -283,6 +294,9 @@ struct Group {
   SharedMap shared;                // best-record slots + commit plan, readable by every rank, writable by every GPU
   std::vector<SharedBlock*> d_shared;  // device-side address of `shared` per local member
   unsigned long long eval_seq = 0, commit_seq = 0;
+  std::vector<SharedArena> arenas;  // same order and sizes on every rank (nbvgpu_shared_alloc is collective)
+  unsigned long long pulled_chunks = 0;  // commit chunks replicated by slice pull + all-gather (nbvgpu_debug_pulled_chunks)
+  size_t pull_min_bytes = 8u << 20; // chunks with at least this much payload in shared arenas are pulled (NBVGPU_PULL_MIN_MB)
   std::mutex mu;
   std::string err;
 };
@@ -1355,6 +1369,33 @@ int group_commit(nbvgpu_ctx* ctx) {
       ci.bytes = (unsigned long long)ci.table_bytes + (p.hi - p.lo);
       ci.n_update = (unsigned)p.n_update;
       ci.n_remove = 0;
+      ci.n_seg = 0;
+      ci.slice = 0;
+      ci.payload = p.hi - p.lo;
+      // A chunk whose payload lies in shared arenas is pulled: every GPU copies its slice over its own PCIe link.
+      if (G->world > 1 && ci.payload >= G->pull_min_bytes) {
+        unsigned ns = 0;
+        bool all_shared = true;
+        for (const UpdateStage::Segment& g : st.segs) {
+          const size_t lo = std::max(g.dev_off, p.lo), hi = std::min(g.dev_off + g.bytes, p.hi);
+          if (lo >= hi) continue;
+          if (g.shared < 0 || ns == (unsigned)kMaxPullSegs) {
+            all_shared = false;
+            break;
+          }
+          PullSeg& ps = ci.seg[ns++];
+          ps.arena = (unsigned)g.shared;
+          ps.pad = 0;
+          ps.src_off = g.shared_off + (lo - g.dev_off);
+          ps.bytes = hi - lo;
+          ps.dst_off = lo - p.lo;
+        }
+        if (all_shared && ns > 0) {
+          ci.n_seg = ns;
+          ci.slice = align_up((ci.payload + (size_t)G->world - 1) / (size_t)G->world, 256);
+          ci.bytes = (unsigned long long)ci.table_bytes + ci.slice * (unsigned long long)G->world;
+        }
+      }
     }
     S->n_chunks = n_chunks = k;
     memcpy(S->incoming, incoming, sizeof incoming);
@@ -1372,9 +1413,42 @@ int group_commit(nbvgpu_ctx* ctx) {
 
   int rc_all = NBVGPU_OK;
   size_t plan_i = 0;
+  // Host->device copies of chunk k run on the member's copy stream beside the collective and the scatter of chunk k - 1 (two
+  // staging buffers alternate); a commit of a single chunk uses the main stream.  copy_begin returns the stream to copy on.
+  const bool piped = !(n_chunks == 1 || (n_chunks == 2 && info[0].n_remove));
+  if (piped)
+    for (nbvgpu_ctx* m : G->local) {  // every member records when a staging buffer has been applied, whoever copies into it next
+      DeviceGuard guard(m->device);
+      if (ensure_copy_stream(m)) return gfail(ctx, NBVGPU_ERR_CUDA, m->err);
+    }
+  auto copy_begin = [&](nbvgpu_ctx* m, unsigned k, int parity, cudaStream_t* s) -> int {
+    nbvgpu_ctx* ctx = m;  // CK reports into the member
+    if (!piped) {
+      *s = m->stream;
+      return NBVGPU_OK;
+    }
+    if (ensure_copy_stream(m)) return NBVGPU_ERR_CUDA;
+    if (k >= 2) {
+      CK(cudaEventSynchronize(m->ev_h2d[parity]));                             // the pinned table of chunk k - 2 may be rewritten
+      CK(cudaStreamWaitEvent(m->copy_stream, m->ev_applied[parity], 0));      // its device buffer has been applied
+    } else {
+      CK(cudaEventRecord(m->ev_applied[parity], m->stream));
+      CK(cudaStreamWaitEvent(m->copy_stream, m->ev_applied[parity], 0));
+    }
+    *s = m->copy_stream;
+    return NBVGPU_OK;
+  };
+  auto copy_end = [&](nbvgpu_ctx* m, int parity) -> int {
+    nbvgpu_ctx* ctx = m;
+    if (!piped) return NBVGPU_OK;
+    CK(cudaEventRecord(m->ev_h2d[parity], m->copy_stream));
+    CK(cudaStreamWaitEvent(m->stream, m->ev_h2d[parity], 0));
+    return NBVGPU_OK;
+  };
   for (unsigned k = 0; k < n_chunks; ++k) {
     const ChunkInfo ci = info[k];
     const int parity = (int)(k & 1);
+    const bool pulled = ci.n_seg > 0;
     for (nbvgpu_ctx* m : G->local) {
       std::lock_guard<std::mutex> lk(m->mu);
       DeviceGuard guard(m->device);
@@ -1386,50 +1460,94 @@ int group_commit(nbvgpu_ctx* ctx) {
             if (rc) return gfail(ctx, rc, m->err);
           }
     }
-    if (root) {
-      std::lock_guard<std::mutex> lk(root->mu);
-      DeviceGuard guard(root->device);
-      nbvgpu_ctx* ctx = root;  // CK reports into the root member
-      if (ci.n_remove) {
-        CK(root->h_table[parity].reserve(ci.table_bytes, false));
-        memcpy(root->h_table[parity].p, rm.data(), rm.size() * sizeof(BlockDesc));
-        CK(cudaMemcpyAsync(root->d_stage[parity].p, root->h_table[parity].p, rm.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, root->stream));
-        CK(cudaStreamSynchronize(root->stream));  // the pinned table is reused by the next chunk of the same parity
-      } else {
-        const ChunkPlan& p = plans[plan_i++];
-        size_t tb = 0;
-        if (n_chunks == 1 || (n_chunks == 2 && k == 1 && info[0].n_remove)) {
-          const int rc = stage_chunk_h2d(root, root->stage, p, parity, root->stream, &tb);
-          if (rc) return rc;
-        } else {
-          if (ensure_copy_stream(root)) return NBVGPU_ERR_CUDA;
-          if (k >= 2) {
-            CK(cudaEventSynchronize(root->ev_h2d[parity]));
-            CK(cudaStreamWaitEvent(root->copy_stream, root->ev_applied[parity], 0));
-          } else {
-            CK(cudaEventRecord(root->ev_applied[parity], root->stream));
-            CK(cudaStreamWaitEvent(root->copy_stream, root->ev_applied[parity], 0));
+    if (pulled) {
+      // every member: its slice of the payload from the shared arenas; the root also the descriptor table
+      for (unsigned q = 0; q < ci.n_seg; ++q)
+        if (ci.seg[q].arena >= G->arenas.size() || !G->arenas[ci.seg[q].arena].host ||
+            ci.seg[q].src_off + ci.seg[q].bytes > G->arenas[ci.seg[q].arena].bytes)
+          return gfail(ctx, NBVGPU_ERR_STATE, "commit refers to a shared arena this rank has not mapped (nbvgpu_shared_alloc is collective)");
+      const ChunkPlan* p = root ? &plans[plan_i++] : nullptr;
+      for (size_t i = 0; i < G->local.size(); ++i) {
+        nbvgpu_ctx* m = G->local[i];
+        std::lock_guard<std::mutex> lk(m->mu);
+        DeviceGuard guard(m->device);
+        nbvgpu_ctx* ctx = m;
+        cudaStream_t cs = nullptr;
+        if (const int rc = copy_begin(m, k, parity, &cs)) return rc;
+        char* d = m->d_stage[parity].as<char>();
+        if (m == root) {
+          CK(m->h_table[parity].reserve(ci.table_bytes, false));
+          BlockDesc* t = m->h_table[parity].as<BlockDesc>();
+          size_t n = 0;
+          for (size_t j = p->first; j < p->end; ++j) {
+            if (root->stage.descs[j].op != kOpUpdate) continue;
+            t[n] = root->stage.descs[j];
+            t[n].payload_off -= p->lo;
+            ++n;
           }
-          const int rc = stage_chunk_h2d(root, root->stage, p, parity, root->copy_stream, &tb);
-          if (rc) return rc;
-          CK(cudaEventRecord(root->ev_h2d[parity], root->copy_stream));
-          CK(cudaStreamWaitEvent(root->stream, root->ev_h2d[parity], 0));
+          CK(cudaMemcpyAsync(d, t, n * sizeof(BlockDesc), cudaMemcpyHostToDevice, cs));
+          m->stats.bytes_uploaded += n * sizeof(BlockDesc);
         }
+        const size_t r = (size_t)(G->rank0 + (int)i);
+        const size_t s_lo = std::min((size_t)ci.payload, r * (size_t)ci.slice), s_hi = std::min((size_t)ci.payload, (r + 1) * (size_t)ci.slice);
+        for (unsigned q = 0; q < ci.n_seg; ++q) {
+          const PullSeg& ps = ci.seg[q];
+          const size_t lo = std::max(s_lo, (size_t)ps.dst_off), hi = std::min(s_hi, (size_t)(ps.dst_off + ps.bytes));
+          if (lo >= hi) continue;
+          CK(cudaMemcpyAsync(d + ci.table_bytes + lo, G->arenas[ps.arena].host + ps.src_off + (lo - ps.dst_off), hi - lo, cudaMemcpyHostToDevice, cs));
+          m->stats.bytes_uploaded += hi - lo;
+        }
+        if (const int rc = copy_end(m, parity)) return rc;
       }
-    }
-    // one broadcast of {table | payload} from rank 0 (NVLink); a single group call covers the GPUs of this process
-    if (G->world > 1) {
+      // the table from rank 0 and the slices from everybody, in one NCCL group over NVLink
       NCK(nccl().GroupStart());
       for (size_t i = 0; i < G->local.size(); ++i) {
         nbvgpu_ctx* m = G->local[i];
         cudaSetDevice(m->device);
-        ncclResult_t r = nccl().Broadcast(m->d_stage[parity].p, m->d_stage[parity].p, ci.bytes, ncclUint8, 0, G->comms[i], m->stream);
+        char* d = m->d_stage[parity].as<char>();
+        ncclResult_t r = nccl().Broadcast(d, d, ci.table_bytes, ncclUint8, 0, G->comms[i], m->stream);
+        if (r == ncclSuccess)
+          r = nccl().AllGather(d + ci.table_bytes + (size_t)(G->rank0 + (int)i) * ci.slice, d + ci.table_bytes, ci.slice, ncclUint8, G->comms[i], m->stream);
         if (r != ncclSuccess) {
           nccl().GroupEnd();
-          return gfail(ctx, NBVGPU_ERR_CUDA, std::string("ncclBroadcast: ") + nccl().GetErrorString(r));
+          return gfail(ctx, NBVGPU_ERR_CUDA, std::string("nccl (pulled chunk): ") + nccl().GetErrorString(r));
         }
       }
       NCK(nccl().GroupEnd());
+      G->pulled_chunks++;
+    } else {
+      if (root) {
+        std::lock_guard<std::mutex> lk(root->mu);
+        DeviceGuard guard(root->device);
+        nbvgpu_ctx* ctx = root;  // CK reports into the root member
+        if (ci.n_remove) {
+          CK(root->h_table[parity].reserve(ci.table_bytes, false));
+          memcpy(root->h_table[parity].p, rm.data(), rm.size() * sizeof(BlockDesc));
+          CK(cudaMemcpyAsync(root->d_stage[parity].p, root->h_table[parity].p, rm.size() * sizeof(BlockDesc), cudaMemcpyHostToDevice, root->stream));
+          CK(cudaStreamSynchronize(root->stream));  // the pinned table is reused by the next chunk of the same parity
+        } else {
+          const ChunkPlan& p = plans[plan_i++];
+          size_t tb = 0;
+          cudaStream_t cs = nullptr;
+          if (const int rc = copy_begin(root, k, parity, &cs)) return rc;
+          if (const int rc = stage_chunk_h2d(root, root->stage, p, parity, cs, &tb)) return rc;
+          if (const int rc = copy_end(root, parity)) return rc;
+        }
+      }
+      // one broadcast of {table | payload} from rank 0 (NVLink); a single group call covers the GPUs of this process
+      if (G->world > 1) {
+        NCK(nccl().GroupStart());
+        for (size_t i = 0; i < G->local.size(); ++i) {
+          nbvgpu_ctx* m = G->local[i];
+          cudaSetDevice(m->device);
+          ncclResult_t r = nccl().Broadcast(m->d_stage[parity].p, m->d_stage[parity].p, ci.bytes, ncclUint8, 0, G->comms[i], m->stream);
+          if (r != ncclSuccess) {
+            nccl().GroupEnd();
+            return gfail(ctx, NBVGPU_ERR_CUDA, std::string("ncclBroadcast: ") + nccl().GetErrorString(r));
+          }
+        }
+        NCK(nccl().GroupEnd());
+      }
     }
     for (nbvgpu_ctx* m : G->local) {
       std::lock_guard<std::mutex> lk(m->mu);
@@ -1438,7 +1556,7 @@ int group_commit(nbvgpu_ctx* ctx) {
       const int rc = ci.n_remove ? commit_removals(m, reinterpret_cast<const BlockDesc*>(d), ci.n_remove)
                                  : launch_apply(m, reinterpret_cast<const BlockDesc*>(d), d + ci.table_bytes, ci.n_update);
       if (rc) return gfail(ctx, rc, m->err);
-      if (m == root && root->copy_stream) cudaEventRecord(root->ev_applied[parity], root->stream);
+      if (m->copy_stream) cudaEventRecord(m->ev_applied[parity], m->stream);
     }
   }
   for (nbvgpu_ctx* m : G->local) {
@@ -1570,9 +1688,21 @@ int group_fan_out(nbvgpu_ctx* ctx, size_t n, F f) {
   return NBVGPU_OK;
 }
 
+void release_arena(SharedArena& a) {
+  if (!a.host) return;
+  if (a.posix) {
+    if (a.registered) cudaHostUnregister(a.host);
+    munmap(a.host, a.bytes);
+  } else {
+    cudaFreeHost(a.host);
+  }
+  a.host = nullptr;
+}
+
 void destroy_group(Group* G) {
   for (size_t i = 0; i < G->comms.size(); ++i)
     if (G->comms[i] && nccl().ok) nccl().CommDestroy(G->comms[i]);
+  for (SharedArena& a : G->arenas) release_arena(a);
   shared_release(&G->shared);
   delete G;
 }
@@ -1595,6 +1725,7 @@ static void destroy_member(nbvgpu_ctx* ctx) {
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
     if (!ctx->owner) {  // a lane only borrows the layers, camera tables and counters of its owner
       for (LayerHost* L : ctx->layers) free_layer(L);
+      for (SharedArena& a : ctx->arenas) release_arena(a);
       cudaFree(ctx->d_A);
       cudaFree(ctx->d_B);
       cudaFree(ctx->d_cs);
@@ -1791,6 +1922,7 @@ int nbvgpu_create_multi(int n_gpus, const int* device_ids, nbvgpu_ctx** out) {
   Group* G = new Group();
   G->world = n_gpus;
   G->rank0 = 0;
+  if (const char* e = std::getenv("NBVGPU_PULL_MIN_MB")) G->pull_min_bytes = (size_t)std::max(0, std::atoi(e)) << 20;
   std::vector<int> devs(n_gpus);
   for (int i = 0; i < n_gpus; ++i) devs[i] = device_ids ? device_ids[i] : i;
   auto bail = [&](int rc) {
@@ -1842,6 +1974,7 @@ int nbvgpu_create_rank(int device, int rank, int world, const uint8_t* unique_id
   G->world = world;
   G->rank0 = rank;
   G->multi_process = true;
+  if (const char* e = std::getenv("NBVGPU_PULL_MIN_MB")) G->pull_min_bytes = (size_t)std::max(0, std::atoi(e)) << 20;
   G->local.push_back(m);
   m->group = G;
   auto bail = [&](int code) {
@@ -1868,6 +2001,106 @@ int nbvgpu_create_rank(int device, int rank, int world, const uint8_t* unique_id
     G->shared.owner = false;
   }
   *out = m;
+  return NBVGPU_OK;
+}
+
+// ---- memory every GPU of the context can read (see include/nbvgpu.h) ------------------------------------------------------
+int nbvgpu_shared_alloc(nbvgpu_ctx* ctx, size_t bytes, void** ptr) {
+  if (!ctx || !ptr || bytes == 0) return NBVGPU_ERR_INVALID;
+  *ptr = nullptr;
+  Group* G = ctx->group;
+  SharedArena a;
+  a.bytes = bytes;
+  if (!G || !G->multi_process) {
+    DeviceGuard guard(ctx->device);
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, NBVGPU_ERR_CUDA, "cudaHostAlloc failed (nbvgpu_shared_alloc)");
+    }
+    a.host = reinterpret_cast<char*>(p);
+    if (G) {
+      std::lock_guard<std::mutex> lk(G->mu);
+      if (G->arenas.size() >= (size_t)kMaxArenas) {
+        cudaFreeHost(p);
+        return fail(ctx, NBVGPU_ERR_CAPACITY, "too many shared allocations");
+      }
+      G->arenas.push_back(a);
+    } else {
+      std::lock_guard<std::mutex> lk(ctx->stage_mu);
+      ctx->arenas.push_back(a);
+    }
+    *ptr = p;
+    return NBVGPU_OK;
+  }
+  // one process per GPU: segment number `id` of the job, created by rank 0, mapped and page-locked by every rank
+  std::lock_guard<std::mutex> lk(G->mu);
+  const size_t id = G->arenas.size();
+  if (id >= (size_t)kMaxArenas) return fail(ctx, NBVGPU_ERR_CAPACITY, "too many shared allocations");
+  SharedBlock* S = G->shared.host;
+  const std::string name = G->shared.name + "_a" + std::to_string(id);
+  std::string err;
+  void* p = nullptr;
+  if (G->rank0 == 0) {
+    p = shm_map_segment(name, bytes, true, &err);
+    if (!p) return fail(ctx, NBVGPU_ERR_STATE, err.c_str());
+    S->arena_bytes[id] = bytes;
+    S->arena_attached[id].store(0u);
+    S->arena_created.store((unsigned)id + 1u, std::memory_order_release);
+  } else {
+    if (!spin_until([&] { return S->arena_created.load(std::memory_order_acquire) > (unsigned)id; }, 600.0))
+      return fail(ctx, NBVGPU_ERR_STATE, "rank 0 never made the matching nbvgpu_shared_alloc call");
+    if (S->arena_bytes[id] != bytes) return fail(ctx, NBVGPU_ERR_INVALID, "nbvgpu_shared_alloc: sizes differ between the ranks");
+    p = shm_map_segment(name, bytes, false, &err);
+    if (!p) return fail(ctx, NBVGPU_ERR_STATE, err.c_str());
+  }
+  a.host = reinterpret_cast<char*>(p);
+  a.posix = true;
+  {
+    DeviceGuard guard(ctx->device);
+    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess) {
+      a.registered = true;
+    } else {
+      cudaGetLastError();
+      munmap(p, bytes);
+      if (G->rank0 == 0) shm_unlink(name.c_str());
+      return fail(ctx, NBVGPU_ERR_CUDA, "cudaHostRegister failed for the shared segment");
+    }
+  }
+  S->arena_attached[id].fetch_add(1u);
+  if (G->rank0 == 0) {  // the name is only needed until everybody has mapped the segment
+    spin_until([&] { return S->arena_attached[id].load() >= (unsigned)G->world; }, 600.0);
+    shm_unlink(name.c_str());
+  }
+  G->arenas.push_back(a);
+  *ptr = p;
+  return NBVGPU_OK;
+}
+
+int nbvgpu_shared_free(nbvgpu_ctx* ctx, void* ptr) {
+  if (!ctx || !ptr) return NBVGPU_ERR_INVALID;
+  Group* G = ctx->group;
+  std::vector<SharedArena>& arenas = G ? G->arenas : ctx->arenas;
+  nbvgpu_ctx* r = stage_owner(ctx);
+  std::unique_lock<std::mutex> slk;
+  if (r) slk = std::unique_lock<std::mutex>(r->stage_mu);
+  if (r)
+    for (const UpdateStage::Segment& g : r->stage.segs)
+      for (const SharedArena& a : arenas)
+        if (a.host == ptr && g.host >= a.host && g.host < a.host + a.bytes)
+          return fail(ctx, NBVGPU_ERR_STATE, "blocks staged from this memory have not been committed yet");
+  for (SharedArena& a : arenas)
+    if (a.host == ptr) {  // the slot stays (arena numbers are positions), its memory goes
+      DeviceGuard guard(ctx->device);
+      release_arena(a);
+      return NBVGPU_OK;
+    }
+  return fail(ctx, NBVGPU_ERR_INVALID, "not a pointer returned by nbvgpu_shared_alloc");
+}
+
+int nbvgpu_debug_pulled_chunks(nbvgpu_ctx* ctx, uint64_t* count) {
+  if (!ctx || !count) return NBVGPU_ERR_INVALID;
+  *count = ctx->group ? ctx->group->pulled_chunks : 0;
   return NBVGPU_OK;
 }
 
@@ -1997,6 +2230,12 @@ static int stage_update(nbvgpu_ctx* ctx, int layer, size_t n, const int32_t* key
     }
     g.host = reinterpret_cast<const char*>(payload);
     g.arena_off = 0;
+    const std::vector<SharedArena>& arenas = ctx->group ? ctx->group->arenas : ctx->arenas;
+    for (size_t a = 0; a < arenas.size(); ++a)
+      if (arenas[a].host && g.host >= arenas[a].host && g.host + g.bytes <= arenas[a].host + arenas[a].bytes) {
+        g.shared = (int)a;
+        g.shared_off = (size_t)(g.host - arenas[a].host);
+      }
   } else {
     CK(st.arena.reserve(st.arena_used + g.bytes, true));
     memcpy(st.arena.as<char>() + st.arena_used, payload, g.bytes);

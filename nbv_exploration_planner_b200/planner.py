@@ -197,6 +197,27 @@ class NbvGpu:
         self._pinned_keep = getattr(self, "_pinned_keep", []) + [payload]   # keep it alive until the commit
         self._ck(self._L.nbvgpu_layer_update_pinned(self._h, layer, len(keys), _vp(keys), _vp(payload), packing))
 
+    def shared_alloc(self, nbytes: int) -> np.ndarray:
+        """``nbvgpu_shared_alloc``: ``nbytes`` of page-locked host memory every GPU of the context can read, as a uint8 array
+        (view it as needed).  Collective in a one-process-per-GPU context: every rank calls it with the same size and gets its
+        own mapping of the same bytes.  Blocks staged from it (``layer_update_pinned``) are replicated by a parallel pull."""
+        p = C.c_void_p()
+        self._ck(self._L.nbvgpu_shared_alloc(self._h, int(nbytes), C.byref(p)))
+        buf = (C.c_uint8 * int(nbytes)).from_address(p.value)
+        a = np.frombuffer(buf, dtype=np.uint8)
+        self._shared = getattr(self, "_shared", {})
+        self._shared[a.ctypes.data] = p.value
+        return a
+
+    def shared_free(self, a: np.ndarray) -> None:
+        self._ck(self._L.nbvgpu_shared_free(self._h, C.c_void_p(self._shared[a.ctypes.data])))
+        del self._shared[a.ctypes.data]
+
+    def pulled_chunks(self) -> int:
+        out = C.c_uint64(0)
+        self._ck(self._L.nbvgpu_debug_pulled_chunks(self._h, C.byref(out)))
+        return int(out.value)
+
     def layer_update_device(self, layer: int, n_blocks: int, d_keys, d_payload, packing: int = N.PACK_PLANAR) -> None:
         self._ck(self._L.nbvgpu_layer_update_device(self._h, layer, n_blocks, _vp(d_keys), _vp(d_payload), packing))
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # usage (under gpurun --gpus N): scripts/scale_run.sh <N> <tag> [tests]
 # The default bench (config 3 strong scaling + config 2 / 5 / 4 sub-records) launched the way the driver launches it, one rank per
-# GPU; with `tests` also the multi-GPU hardware tests (N-GPU == 1-GPU == oracle, one process on all GPUs and one process per GPU).
+# GPU; with `tests` also the multi-GPU hardware tests (N-GPU == 1-GPU bit for bit, one process on all GPUs and one process per GPU).
 N=$1; tag=$2; shift 2
 mkdir -p gpurun_out
 if [ "${1:-}" = tests ]; then

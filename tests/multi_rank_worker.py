@@ -71,11 +71,29 @@ def main():
         b2 = g.evaluate_shard_device(lt, le, cfg.robot_radius, hi - lo, lo, d_pos, d_seg, d_py, d_di, 1.0, 0.5, 0.0, d_free, d_gain, d_yaw)
     g.synchronize()
     b3 = g.gain_eval_best(lt, c.positions, pyaw, c.distance, r["free"] if world == 1 else None, 1.0, 0.5, 0.0)
+    # the whole map again, this time out of memory every rank has mapped (nbvgpu_shared_alloc: collective): each GPU pulls its
+    # slice of every chunk over its own PCIe link, an all-gather completes the chunk (forced for these small chunks)
+    buf = g.shared_alloc(m.tsdf.nbytes + m.esdf.nbytes)
+    g.layer_clear(lt)
+    g.layer_clear(le)
+    if rank == 0:
+        t = buf[:m.tsdf.nbytes].view(m.tsdf.dtype).reshape(m.tsdf.shape)
+        e = buf[m.tsdf.nbytes:].view(m.esdf.dtype).reshape(m.esdf.shape)
+        t[...] = m.tsdf
+        e[...] = m.esdf
+        g.layer_update_pinned(lt, m.keys, t)
+        g.layer_update_pinned(le, m.keys, e)
+    g.commit()
+    assert g.layer_num_blocks(lt) == len(m.keys) and g.layer_num_blocks(le) == len(m.keys)
+    rp = g.evaluate_candidates(lt, le, cfg.robot_radius, c.positions, c.segments, pyaw, c.distance, 1.0, 0.5, 0.0)
+    pulled = g.pulled_chunks()
+    g.shared_free(buf)
     np.savez(out + f".{rank}.npz", lo=lo, hi=hi, gain=r["gain"][lo:hi], yaw=r["yaw_deg"][lo:hi], free=r["free"][lo:hi],
              best=np.array([r["index"], r["score"], r["best_gain"], r["best_yaw"]]),
              best_dev=np.array([b2["index"], b2["score"], b2["gain"], b2["yaw"]]),
              best_nomask=np.array([b3["index"], b3["score"], b3["best_gain"], b3["best_yaw"]]),
-             d_gain=d_gain.cpu().numpy(), d_yaw=d_yaw.cpu().numpy(), d_free=d_free.cpu().numpy())
+             d_gain=d_gain.cpu().numpy(), d_yaw=d_yaw.cpu().numpy(), d_free=d_free.cpu().numpy(),
+             gain_pulled=rp["gain"][lo:hi], free_pulled=rp["free"][lo:hi], pulled_chunks=pulled)
     g.close()
 
 

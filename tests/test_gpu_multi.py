@@ -129,6 +129,46 @@ def test_pinned_updates_equal_copied_updates(cfg1_map):
     g.close(); g1.close()
 
 
+@pytest.mark.parametrize("devices", [[0], "all"])
+def test_shared_arena_commit_pulls_slices(cfg1_map, devices, monkeypatch):
+    """nbvgpu_shared_alloc + nbvgpu_layer_update_pinned: with >= 2 GPUs every GPU copies its slice of each chunk and an
+    all-gather completes it (forced here for 1 MiB chunks); the mirrors answer like a plain single-GPU context's."""
+    from nbv_exploration_planner_b200 import LAYER_ESDF, LAYER_TSDF, NbvGpu, NbvGpuError, synth
+    if devices == "all":
+        if _n_gpus() < 2:
+            pytest.skip("needs >= 2 GPUs")
+        devices = list(range(_n_gpus()))
+    monkeypatch.setenv("NBVGPU_CHUNK_MB", "1")
+    monkeypatch.setenv("NBVGPU_PULL_MIN_MB", "0")
+    m, cfg = cfg1_map, synth.CONFIGS["cfg2"]
+    g = NbvGpu.multi(devices)
+    lt = g.layer_create(LAYER_TSDF, m.voxel_size, m.vps, len(m.keys) + 64)
+    le = g.layer_create(LAYER_ESDF, m.voxel_size, m.vps, len(m.keys) + 64)
+    buf = g.shared_alloc(m.tsdf.nbytes + m.esdf.nbytes + 512)
+    t = buf[:m.tsdf.nbytes].view(m.tsdf.dtype).reshape(m.tsdf.shape)
+    e = buf[m.tsdf.nbytes + 256:m.tsdf.nbytes + 256 + m.esdf.nbytes].view(m.esdf.dtype).reshape(m.esdf.shape)
+    t[...] = m.tsdf
+    e[...] = m.esdf
+    half = len(m.keys) // 2
+    g.layer_update_pinned(lt, m.keys[:half], t[:half])      # several pieces per chunk, and a piece that is not shared memory
+    g.layer_update_pinned(lt, m.keys[half:], t[half:])
+    g.layer_update_pinned(le, m.keys, e)
+    g.layer_update(le, m.keys[:2], m.esdf[:2])              # (copied into the library's own staging: that chunk is broadcast)
+    with pytest.raises(NbvGpuError):
+        g.shared_free(buf)                                  # staged blocks still point into it
+    g.commit()
+    assert g.layer_num_blocks(lt) == len(m.keys) and g.layer_num_blocks(le) == len(m.keys)
+    assert (g.pulled_chunks() > 0) == (len(devices) > 1)
+    g.shared_free(buf)
+    g.set_camera(m.camera())
+    c = synth.make_candidates(cfg, 600, None)
+    free1, r1 = _reference_results(m, cfg, c)
+    r = g.evaluate_candidates(lt, le, cfg.robot_radius, c.positions, c.segments, np.zeros(600), c.distance, 1.0, 0.5, 0.0)
+    assert np.array_equal(r["free"], free1) and np.array_equal(r["gain"], r1["gain"]) and np.array_equal(r["yaw_deg"], r1["yaw_deg"])
+    assert (r["index"], r["score"]) == (r1["index"], r1["score"])
+    g.close()
+
+
 def _run_ranks(tmp_path, world, n_cand):
     idfile, out = str(tmp_path / "uid.bin"), str(tmp_path / "res")
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multi_rank_worker.py"), str(r), str(world), idfile, out, str(n_cand)],
@@ -140,8 +180,9 @@ def _run_ranks(tmp_path, world, n_cand):
 
 
 @pytest.mark.parametrize("world", [1, "all"])
-def test_one_process_per_gpu_equals_single_gpu(cfg1_map, tmp_path, world):
+def test_one_process_per_gpu_equals_single_gpu(cfg1_map, tmp_path, world, monkeypatch):
     from nbv_exploration_planner_b200 import synth
+    monkeypatch.setenv("NBVGPU_PULL_MIN_MB", "0")   # the workers' last commit comes out of shared memory: pulled whatever its size
     if world == "all":
         if _n_gpus() < 2:
             pytest.skip("needs >= 2 GPUs")
@@ -158,6 +199,8 @@ def test_one_process_per_gpu_equals_single_gpu(cfg1_map, tmp_path, world):
         assert np.array_equal(z["gain"], r1["gain"][lo:hi]) and np.array_equal(z["d_gain"], r1["gain"][lo:hi])
         assert np.array_equal(z["yaw"], r1["yaw_deg"][lo:hi]) and np.array_equal(z["d_yaw"], r1["yaw_deg"][lo:hi])
         assert np.array_equal(z["best"], want_best) and np.array_equal(z["best_dev"], want_best)   # every rank knows the winner
+        assert np.array_equal(z["gain_pulled"], r1["gain"][lo:hi]) and np.array_equal(z["free_pulled"], free1[lo:hi])
+        assert (int(z["pulled_chunks"]) > 0) == (world > 1)
     assert sum(int(z["hi"]) - int(z["lo"]) for z in res) == n_cand
 
 
