@@ -419,8 +419,14 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
         except OSError:
             use_shared = False
         use_shared = bool(rig.bcast_int(1 if use_shared else 0))
+    shared_note = None
     if use_shared:
-        shared = g.shared_alloc(map_bytes + 256)
+        try:
+            shared = g.shared_alloc(map_bytes + 256)
+        except Exception as e:   # fails on every rank alike (the library agrees on it across ranks): private memory + broadcast then
+            shared_note = str(e)
+            print(f"bench: rank {rank}: {e}; the map stays in rank 0's private page-locked memory", file=sys.stderr)
+    if shared is not None:
         if rank == 0:
             p_tsdf = shared[:nb * nvox * 8].view(np.float32).reshape(m.tsdf.shape)
             p_esdf = shared[nb * nvox * 8:nb * nvox * 12].view(np.float32).reshape(m.esdf.shape)

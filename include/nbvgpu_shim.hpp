@@ -61,21 +61,35 @@ class GpuMap {
   /// (Layer::getAllUpdatedBlocks, layer.h:194-203) in the reference's own serialisation
   /// (Block::serializeToIntegers, block.cc:159-234), clear the bit, commit.  Needs the Voxblox
   /// headers, so it is only compiled inside the reference tree.
+  /// The blocks are serialised straight into memory every GPU of the context can read (nbvgpu_shared_alloc) and staged from there
+  /// without another copy (nbvgpu_layer_update_pinned): a single GPU copies them once, several GPUs each pull their slice of a
+  /// large upload over their own PCIe link before an all-gather over NVLink completes it (nbvgpu.h).
   template <class VoxelType>
   void uploadUpdatedBlocks(voxblox::Layer<VoxelType>* layer, int gpu_layer) {
     voxblox::BlockIndexList updated;
     layer->getAllUpdatedBlocks(voxblox::Update::kMap, &updated);
     std::vector<int32_t> keys;
-    std::vector<uint32_t> payload, one;
+    std::vector<uint32_t> one;
+    uint32_t* dst = nullptr;
+    size_t per = 0, n = 0;
     for (const voxblox::BlockIndex& bi : updated) {
       typename voxblox::Block<VoxelType>::Ptr block = layer->getBlockPtrByIndex(bi);
       if (!block) continue;
       block->serializeToIntegers(&one);
+      if (!dst) {  // every block of a layer serialises to the same number of words
+        per = one.size();
+        dst = stagingWords(per * updated.size());
+      }
+      if (one.size() != per) throw std::runtime_error("nbvgpu shim: blocks of one layer serialise to different sizes");
+      std::memcpy(dst + n * per, one.data(), per * sizeof(uint32_t));
       keys.insert(keys.end(), {bi.x(), bi.y(), bi.z()});
-      payload.insert(payload.end(), one.begin(), one.end());
+      ++n;
       block->updated().reset(voxblox::Update::kMap);
     }
-    if (!keys.empty()) uploadSerialized(gpu_layer, keys.size() / 3, keys.data(), payload.data());
+    if (n) {
+      check(ctx_, nbvgpu_layer_update_pinned(ctx_, gpu_layer, n, keys.data(), dst, NBVGPU_PACK_VOXBLOX), "layer_update_pinned");
+      check(ctx_, nbvgpu_commit(ctx_), "commit");
+    }
   }
 #endif
   /// Raw variant for callers that already hold serialised blocks (e.g. a voxblox_msgs/Layer message).
@@ -89,8 +103,21 @@ class GpuMap {
   }
 
  private:
+  /// Staging for the upload hook: one shared allocation, grown when an upload needs more (the commit has returned by then).
+  uint32_t* stagingWords(size_t words) {
+    const size_t need = words * sizeof(uint32_t);
+    if (need > staging_bytes_) {
+      if (staging_) check(ctx_, nbvgpu_shared_free(ctx_, staging_), "shared_free");
+      staging_ = nullptr;
+      staging_bytes_ = need + need / 2 + (1u << 20);
+      check(ctx_, nbvgpu_shared_alloc(ctx_, staging_bytes_, &staging_), "shared_alloc");
+    }
+    return static_cast<uint32_t*>(staging_);
+  }
   nbvgpu_ctx* ctx_ = nullptr;
   int tsdf_ = -1, esdf_ = -1;
+  void* staging_ = nullptr;
+  size_t staging_bytes_ = 0;
 };
 
 /// What nbvePlanner::setUpCamera (nbvep.cpp:40-61) configures, as plain numbers.

@@ -139,7 +139,8 @@ struct SharedBlock {
   // shared arenas (nbvgpu_shared_alloc across processes): the root creates segment number i and publishes its size, the others map it
   alignas(64) std::atomic<unsigned> arena_created;            // segments created so far
   unsigned long long arena_bytes[kMaxArenas];
-  std::atomic<unsigned> arena_attached[kMaxArenas];           // ranks that have mapped and page-locked segment i
+  std::atomic<unsigned> arena_attached[kMaxArenas];           // ranks that have mapped segment i and tried to page-lock it
+  std::atomic<unsigned> arena_failed[kMaxArenas];             // ... of which this many could not: then every rank gives the segment up
   ChunkInfo chunk[kMaxChunks];
 };
 

@@ -180,8 +180,13 @@ struct UpdateStage {
 struct SharedArena {
   char* host = nullptr;
   size_t bytes = 0;
-  bool posix = false, registered = false;
+  bool posix = false, registered = false;  // registered: the whole segment is page-locked (the owner's mapping)
+  // the other ranks of a one-process-per-GPU context page-lock only what they pull, when they first pull it, in granules of
+  // kArenaGranule bytes, each its own registration (a copy must not span two): 0 = not tried, 1 = locked, 2 = could not be locked
+  // (copied from as pageable memory: slower, still right)
+  std::vector<uint8_t> granule;
 };
+constexpr size_t kArenaGranule = 4u << 20;
 
 struct Group;
 struct nbvgpu_ctx {
@@ -1308,6 +1313,8 @@ nbvgpu_ctx* stage_owner(nbvgpu_ctx* ctx) {
   return ctx->group->rank0 == 0 ? ctx->group->local[0] : nullptr;
 }
 
+cudaError_t arena_copy_h2d(SharedArena& a, size_t lo, size_t hi, char* dst, cudaStream_t s);  // below, with the arenas' other housekeeping
+
 int gfail(nbvgpu_ctx* ctx, int code, const std::string& msg) {
   set_err(ctx, msg);
   return code;
@@ -1494,7 +1501,7 @@ int group_commit(nbvgpu_ctx* ctx) {
           const PullSeg& ps = ci.seg[q];
           const size_t lo = std::max(s_lo, (size_t)ps.dst_off), hi = std::min(s_hi, (size_t)(ps.dst_off + ps.bytes));
           if (lo >= hi) continue;
-          CK(cudaMemcpyAsync(d + ci.table_bytes + lo, G->arenas[ps.arena].host + ps.src_off + (lo - ps.dst_off), hi - lo, cudaMemcpyHostToDevice, cs));
+          CK(arena_copy_h2d(G->arenas[ps.arena], ps.src_off + (lo - ps.dst_off), ps.src_off + (hi - ps.dst_off), d + ci.table_bytes + lo, cs));
           m->stats.bytes_uploaded += hi - lo;
         }
         if (const int rc = copy_end(m, parity)) return rc;
@@ -1688,9 +1695,31 @@ int group_fan_out(nbvgpu_ctx* ctx, size_t n, F f) {
   return NBVGPU_OK;
 }
 
+// Host->device copy of [lo, hi) of a shared arena.  The owner's mapping (and a single process's allocation) is page-locked as a
+// whole; another rank's mapping is locked granule by granule as it is first read, and the copy is cut at the granule borders.
+cudaError_t arena_copy_h2d(SharedArena& a, size_t lo, size_t hi, char* dst, cudaStream_t s) {
+  if (lo >= hi) return cudaSuccess;
+  if (!a.posix || a.registered) return cudaMemcpyAsync(dst, a.host + lo, hi - lo, cudaMemcpyHostToDevice, s);
+  if (a.granule.empty()) a.granule.assign((a.bytes + kArenaGranule - 1) / kArenaGranule, 0);
+  for (size_t g = lo / kArenaGranule; g * kArenaGranule < hi; ++g) {
+    const size_t g_lo = g * kArenaGranule, g_hi = std::min(a.bytes, g_lo + kArenaGranule);
+    if (a.granule[g] == 0) {
+      a.granule[g] = cudaHostRegister(a.host + g_lo, g_hi - g_lo, cudaHostRegisterPortable) == cudaSuccess ? 1 : 2;
+      if (a.granule[g] == 2) cudaGetLastError();
+    }
+    const size_t c_lo = std::max(lo, g_lo), c_hi = std::min(hi, g_hi);
+    const cudaError_t e = cudaMemcpyAsync(dst + (c_lo - lo), a.host + c_lo, c_hi - c_lo, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
 void release_arena(SharedArena& a) {
   if (!a.host) return;
   if (a.posix) {
+    for (size_t g = 0; g < a.granule.size(); ++g)
+      if (a.granule[g] == 1) cudaHostUnregister(a.host + g * kArenaGranule);
+    a.granule.clear();
     if (a.registered) cudaHostUnregister(a.host);
     munmap(a.host, a.bytes);
   } else {
@@ -2046,6 +2075,7 @@ int nbvgpu_shared_alloc(nbvgpu_ctx* ctx, size_t bytes, void** ptr) {
     if (!p) return fail(ctx, NBVGPU_ERR_STATE, err.c_str());
     S->arena_bytes[id] = bytes;
     S->arena_attached[id].store(0u);
+    S->arena_failed[id].store(0u);
     S->arena_created.store((unsigned)id + 1u, std::memory_order_release);
   } else {
     if (!spin_until([&] { return S->arena_created.load(std::memory_order_acquire) > (unsigned)id; }, 600.0))
@@ -2056,21 +2086,30 @@ int nbvgpu_shared_alloc(nbvgpu_ctx* ctx, size_t bytes, void** ptr) {
   }
   a.host = reinterpret_cast<char*>(p);
   a.posix = true;
-  {
+  std::string reg_err;
+  if (G->rank0 == 0) {  // the owner page-locks all of it (it stages from anywhere in it); the others lock what they pull, when they pull it
     DeviceGuard guard(ctx->device);
-    if (cudaHostRegister(p, bytes, cudaHostRegisterPortable) == cudaSuccess) {
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaSuccess) {
       a.registered = true;
     } else {
       cudaGetLastError();
-      munmap(p, bytes);
-      if (G->rank0 == 0) shm_unlink(name.c_str());
-      return fail(ctx, NBVGPU_ERR_CUDA, "cudaHostRegister failed for the shared segment");
+      reg_err = cudaGetErrorString(e);
+      S->arena_failed[id].fetch_add(1u);
     }
   }
   S->arena_attached[id].fetch_add(1u);
-  if (G->rank0 == 0) {  // the name is only needed until everybody has mapped the segment
-    spin_until([&] { return S->arena_attached[id].load() >= (unsigned)G->world; }, 600.0);
-    shm_unlink(name.c_str());
+  // everybody waits for everybody: either all ranks hold the segment page-locked or none keeps it (the call fails on every
+  // rank alike, so that the callers can fall back together)
+  const bool all_in = spin_until([&] { return S->arena_attached[id].load() >= (unsigned)G->world; }, 600.0);
+  if (G->rank0 == 0) shm_unlink(name.c_str());  // the name was only needed until everybody had mapped the segment
+  const unsigned failed = S->arena_failed[id].load();
+  if (!all_in || failed) {
+    release_arena(a);
+    G->arenas.push_back(SharedArena());  // the number is used up on every rank
+    return fail(ctx, NBVGPU_ERR_CUDA,
+                (std::string("nbvgpu_shared_alloc: ") + (all_in ? std::string("rank 0 could not page-lock the shared segment") : std::string("a rank never joined")) +
+                 (reg_err.empty() ? "" : " (this rank: " + reg_err + ")")).c_str());
   }
   G->arenas.push_back(a);
   *ptr = p;

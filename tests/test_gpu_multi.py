@@ -173,7 +173,12 @@ def _run_ranks(tmp_path, world, n_cand):
     idfile, out = str(tmp_path / "uid.bin"), str(tmp_path / "res")
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multi_rank_worker.py"), str(r), str(world), idfile, out, str(n_cand)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
-    logs = [p.communicate(timeout=600)[0] for p in procs]
+    try:
+        logs = [p.communicate(timeout=240)[0] for p in procs]
+    except subprocess.TimeoutExpired:
+        for p in procs:
+            p.kill()
+        raise AssertionError("a rank hung:\n" + "\n".join((p.communicate()[0] or "")[-2000:] for p in procs))
     for p, log in zip(procs, logs):
         assert p.returncode == 0, log[-3000:]
     return [np.load(out + f".{r}.npz") for r in range(world)]
