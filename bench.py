@@ -584,9 +584,9 @@ def bench_gain_config(rig, args, name, steps, warmup, strong, with_cpu_baseline,
             "config": {"workload": workload_text(cfg, name, n_all, n), "candidates_total": int(n_all), "map_blocks": nb,
                        "l2": "flushed between steps (256 MiB write)", "kernel_variant": args.variant,
                        "parallelism": f"candidates sharded over {world} GPU(s) inside libnbvgpu.so, map replicated by nbvgpu_commit "
-                                      + (f"(the map lies in shared page-locked memory: per 64 MiB chunk every GPU copies 1/{world} over its own "
+                                      + (f"(the map lies in shared page-locked memory, nbvgpu_shared_alloc: per chunk every GPU copies 1/{world} over its own "
                                          f"PCIe link, ncclAllGather over NVLink completes it; {pulled} chunks so far)" if pulled else
-                                         "(page-locked H2D on rank 0 + ncclBroadcast of {descriptor table | payload} per 64 MiB chunk)")
+                                         "(page-locked H2D on rank 0 + ncclBroadcast of {descriptor table | payload} per chunk)")
                                       + "; best records through GPU stores into shared host memory (no collective per step)",
                        "map_replication": {"ms": first_repl, "bytes": map_bytes, "gb_per_s": map_bytes / (first_repl * 1e-3) / 1e9 if first_repl else None,
                                            "first_commit_ms": cold_repl_ms, "inside_timed_steps": bool(include_replication),

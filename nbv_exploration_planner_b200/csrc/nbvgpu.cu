@@ -1351,7 +1351,12 @@ int group_commit(nbvgpu_ctx* ctx) {
       if (d.op == kOpUpdate) incoming[d.layer]++;
     }
     ChunkPlan c;
+    // a commit of gigabytes on several GPUs goes in 256 MiB chunks unless NBVGPU_CHUNK_MB says otherwise: a chunk costs every
+    // rank a pair of NCCL calls and a turn of the staging buffers (config 4's 7 GB map on 2 GPUs: 96.8 -> 89.7 ms)
+    const size_t chunk_saved = root->chunk_bytes;
+    if (G->world > 1 && st.dev_bytes > ((size_t)1 << 30) && std::getenv("NBVGPU_CHUNK_MB") == nullptr) root->chunk_bytes = (size_t)256 << 20;
     for (size_t from = 0; next_chunk(root, st, from, &c); from = c.end) plans.push_back(c);
+    root->chunk_bytes = chunk_saved;
     if (plans.size() + 1 > (size_t)kMaxChunks) return gfail(ctx, NBVGPU_ERR_CAPACITY, "commit too large: commit more often or raise NBVGPU_CHUNK_MB");
     // the plan may only be overwritten once every rank has read the previous one
     if (G->multi_process && seq > 1) {

@@ -136,6 +136,37 @@ def test_long_range_fine_voxels(oracle_mod):
         g.close()
 
 
+def test_slot_grid_limited_to_the_rays_z_extent(oracle_mod, monkeypatch):
+    """Config 4's geometry on the slot-grid sweep: the grid spans only the block layers the rays reach (14 of 25), which is
+    what lets four CTAs share an SM.  Same results as with the full cube of blocks (NBVGPU_CUBE_GRID) and as the oracle, also
+    for candidates next to the floor and the ceiling of the map and for a camera pitched up."""
+    from nbv_exploration_planner_b200 import synth
+    for pitch in (15.0, -25.0):
+        cfg = synth.SynthConfig("cfg4grid", (0, 0, 0), (16, 16, 6), 0.05, 8.0, 8, "pillars", 1205, 2205, (8.0, 8.0, 2.0),
+                                obs_radius=7.0, traj_points=3, traj_step=3.0, vicinity=2.0, pitch_deg=pitch)
+        m = synth.make_map(cfg)
+        cam = m.camera()
+        c = synth.make_candidates(cfg, 8, None)
+        pos = c.positions.copy()
+        pos[0, 2], pos[1, 2] = 0.12, 5.9
+        o, lt_o, _ = load_oracle(oracle_mod, m, cam)
+        ro = o.gain_eval(lt_o, pos, per_yaw=True, threads=16)
+        res = {}
+        for cube in (False, True):
+            if cube:
+                monkeypatch.setenv("NBVGPU_CUBE_GRID", "1")
+            else:
+                monkeypatch.delenv("NBVGPU_CUBE_GRID", raising=False)
+            g, lt_g, _ = load_gpu(m, cam, 5)        # slot-grid sweep with every shortcut cross-checked
+            res[cube] = g.gain_eval(lt_g, pos, per_yaw=True)
+            assert g.classifier_mismatches() == 0
+            g.close()
+        monkeypatch.delenv("NBVGPU_CUBE_GRID", raising=False)
+        for k in ("per_yaw", "steps", "gain", "yaw_deg"):
+            assert np.array_equal(res[False][k], res[True][k]), k
+            assert np.array_equal(res[False][k], ro[k]), k
+
+
 def test_incremental_replay_tracks_oracle(oracle_mod):
     """BASELINE config 5 in miniature: per step upload only the changed blocks (sphere around the next
     trajectory point), drop some stale blocks, evaluate; the GPU mirror must track an oracle layer that
