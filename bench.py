@@ -127,9 +127,7 @@ class ClockSampler(threading.Thread):
         except Exception:
             self.nv = None
 
-    def run(self):
-        if self.nv is None:
-            return
+    def _sample(self):
         nv = self.nv
         names = {
             getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
@@ -138,18 +136,29 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
             getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
         }
-        while not self.stop_flag:
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.02)
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def run(self):
+        if self.nv is None:
+            return
+        while True:
+            # sparse on purpose (one rank per GPU: a step ends when the slowest rank's does, so whatever disturbs one rank's
+            # host thread disturbs every step): the first sample 5 ms into the timed region, then four per second
+            time.sleep(0.005 if not self.samples else 0.25)
+            if self.stop_flag:
+                break
+            self._sample()
 
     def summary(self):
+        if self.nv is not None and not self.samples:
+            self._sample()   # a timed region shorter than 5 ms: one sample right behind it
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),

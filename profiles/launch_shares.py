@@ -14,7 +14,7 @@ for name, grid, us in launch:
     t[0] += 1
     t[1] += us
 all_us = sum(t[1] for t in tot.values())
-print(f"launch list: ncu --metrics gpu__time_duration.sum --clock-control none -c 400 {cmd}")
+print(f"launch list: ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 {cmd}")
 print(f"{len(launch)} launches captured, {all_us / 1e3:.2f} ms of device time (cold-cache, serialised: shares, not absolutes)")
 for name, (n, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
     print(f"{name[:90]:45s} n={n:4d}  total {us / 1e3:9.3f} ms  avg {us / n:9.1f} us  share {100 * us / all_us:5.1f}%")
@@ -25,7 +25,7 @@ for name, grid, us in launch:
     if name.startswith("k_gain") and grid == big:
         cur = {"k_gain": us}
         steps.append(cur)
-    elif cur is not None and name.split("<")[0] in ("k_best_yaw", "k_score_best", "k_check_segments", "k_check_segments_warp"):
+    elif cur is not None and name.split("<")[0] in ("k_best_yaw", "k_best_yaw_score", "k_score_best", "k_check_segments", "k_check_segments_warp"):
         cur[name.split("<")[0]] = cur.get(name.split("<")[0], 0.0) + us
 if steps:
     keys = sorted({k for s in steps for k in s}, key=lambda k: -statistics.median(s.get(k, 0.0) for s in steps))
