@@ -170,7 +170,8 @@ int nbvgpu_layer_update_pinned(nbvgpu_ctx* ctx, int layer, size_t n_blocks, cons
  * on every GPU, instead of rank 0's link carrying everything in front of a broadcast (7 GB map of BASELINE configs[3] on 8 GPUs:
  * see profiles/README.md).  This is where the reference's upload hook should serialise Layer::getAllUpdatedBlocks
  * (voxblox/core/layer.h:194-203, block.cc:159-234) when the planner owns several GPUs.  nbvgpu_shared_free releases one allocation
- * (not while blocks staged from it await their commit); nbvgpu_destroy releases the rest. */
+ * (not while blocks staged from it await their commit; every rank that made the allocation frees it); nbvgpu_destroy releases the
+ * rest.  A context hands out at most 256 allocations over its lifetime. */
 int nbvgpu_shared_alloc(nbvgpu_ctx* ctx, size_t bytes, void** ptr);
 int nbvgpu_shared_free(nbvgpu_ctx* ctx, void* ptr);
 /* Same with device buffers (single-GPU contexts); applied in stream order.  A key listed twice is written by either copy. */

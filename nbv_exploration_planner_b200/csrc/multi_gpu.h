@@ -107,7 +107,7 @@ static_assert(sizeof(BestSlot) == 64, "slot layout");
 
 // What the root tells the other ranks about a commit (they cannot see its staging area).
 constexpr int kMaxPullSegs = 4;
-constexpr int kMaxArenas = 16;
+constexpr int kMaxArenas = 256;  // allocations per context lifetime (a freed number is not handed out again)
 struct PullSeg {                 // a piece of a chunk's payload that lies in a shared arena (nbvgpu_shared_alloc)
   unsigned arena, pad;
   unsigned long long src_off;    // offset inside the arena

@@ -1370,6 +1370,7 @@ int group_commit(nbvgpu_ctx* ctx) {
     unsigned k = 0;
     if (!rm.empty()) {
       ChunkInfo& ci = S->chunk[k++];
+      ci = ChunkInfo{};  // (the slot may hold a pulled chunk of the previous commit)
       ci.table_bytes = (unsigned)align_up(rm.size() * sizeof(BlockDesc), 256);
       ci.bytes = ci.table_bytes;
       ci.n_update = 0;
@@ -1377,6 +1378,7 @@ int group_commit(nbvgpu_ctx* ctx) {
     }
     for (const ChunkPlan& p : plans) {
       ChunkInfo& ci = S->chunk[k++];
+      ci = ChunkInfo{};
       ci.table_bytes = (unsigned)align_up(p.n_update * sizeof(BlockDesc), 256);
       ci.bytes = (unsigned long long)ci.table_bytes + (p.hi - p.lo);
       ci.n_update = (unsigned)p.n_update;
