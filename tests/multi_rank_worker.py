@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     import faulthandler
-    faulthandler.dump_traceback_later(int(os.environ.get("NBV_WORKER_TIMEOUT", "150")), exit=True)   # a rank that waits for a peer for ever says where, and goes away
+    faulthandler.dump_traceback_later(int(os.environ.get("NBV_WORKER_TIMEOUT", "300")), exit=True)   # a rank that waits for a peer for ever says where, and goes away
     rank, world, idfile, out, n_cand = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3], sys.argv[4], int(sys.argv[5])
     import torch
 

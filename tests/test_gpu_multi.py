@@ -174,7 +174,7 @@ def _run_ranks(tmp_path, world, n_cand):
     procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multi_rank_worker.py"), str(r), str(world), idfile, out, str(n_cand)],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
     try:
-        logs = [p.communicate(timeout=240)[0] for p in procs]
+        logs = [p.communicate(timeout=420)[0] for p in procs]
     except subprocess.TimeoutExpired:
         for p in procs:
             p.kill()
