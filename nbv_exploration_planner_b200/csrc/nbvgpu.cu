@@ -2055,8 +2055,11 @@ int nbvgpu_shared_alloc(nbvgpu_ctx* ctx, size_t bytes, void** ptr) {
       return fail(ctx, NBVGPU_ERR_CUDA, "cudaHostAlloc failed (nbvgpu_shared_alloc)");
     }
     a.host = reinterpret_cast<char*>(p);
-    if (G) {
+    if (G) {  // the list is written under the group's mutex AND the staging mutex (the commit holds both, staging the latter)
       std::lock_guard<std::mutex> lk(G->mu);
+      nbvgpu_ctx* r = stage_owner(ctx);
+      std::unique_lock<std::mutex> slk;
+      if (r) slk = std::unique_lock<std::mutex>(r->stage_mu);
       if (G->arenas.size() >= (size_t)kMaxArenas) {
         cudaFreeHost(p);
         return fail(ctx, NBVGPU_ERR_CAPACITY, "too many shared allocations");
@@ -2113,12 +2116,22 @@ int nbvgpu_shared_alloc(nbvgpu_ctx* ctx, size_t bytes, void** ptr) {
   const unsigned failed = S->arena_failed[id].load();
   if (!all_in || failed) {
     release_arena(a);
-    G->arenas.push_back(SharedArena());  // the number is used up on every rank
+    {
+      nbvgpu_ctx* r = stage_owner(ctx);
+      std::unique_lock<std::mutex> slk;
+      if (r) slk = std::unique_lock<std::mutex>(r->stage_mu);
+      G->arenas.push_back(SharedArena());  // the number is used up on every rank
+    }
     return fail(ctx, NBVGPU_ERR_CUDA,
                 (std::string("nbvgpu_shared_alloc: ") + (all_in ? std::string("rank 0 could not page-lock the shared segment") : std::string("a rank never joined")) +
                  (reg_err.empty() ? "" : " (this rank: " + reg_err + ")")).c_str());
   }
-  G->arenas.push_back(a);
+  {
+    nbvgpu_ctx* r = stage_owner(ctx);
+    std::unique_lock<std::mutex> slk;
+    if (r) slk = std::unique_lock<std::mutex>(r->stage_mu);
+    G->arenas.push_back(a);
+  }
   *ptr = p;
   return NBVGPU_OK;
 }
@@ -2127,6 +2140,8 @@ int nbvgpu_shared_free(nbvgpu_ctx* ctx, void* ptr) {
   if (!ctx || !ptr) return NBVGPU_ERR_INVALID;
   Group* G = ctx->group;
   std::vector<SharedArena>& arenas = G ? G->arenas : ctx->arenas;
+  std::unique_lock<std::mutex> glk;  // same order as the commit: the group's mutex, then the staging mutex
+  if (G) glk = std::unique_lock<std::mutex>(G->mu);
   nbvgpu_ctx* r = stage_owner(ctx);
   std::unique_lock<std::mutex> slk;
   if (r) slk = std::unique_lock<std::mutex>(r->stage_mu);
