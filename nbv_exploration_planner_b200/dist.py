@@ -49,6 +49,17 @@ def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
     return lo, min(n, lo + per)
 
 
+def pull_slice(payload_bytes: int, world: int, rank: int) -> Tuple[int, int, int]:
+    """The rule of a pulled commit chunk (csrc/nbvgpu.cu, group_commit): rank ``rank`` copies bytes [lo, hi) of the chunk's
+    payload over its own PCIe link into its slice of the staging buffer; slices are ``slice`` bytes apart (a multiple of 256, so
+    that the in-place all-gather of ``world`` x ``slice`` bytes lands every piece where the descriptors expect it).
+    Returns (lo, hi, slice)."""
+    per = (payload_bytes + world - 1) // world
+    sl = (per + 255) // 256 * 256
+    lo = min(payload_bytes, rank * sl)
+    return lo, min(payload_bytes, lo + sl), sl
+
+
 _PINNED = {}
 
 

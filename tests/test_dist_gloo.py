@@ -185,6 +185,52 @@ def test_sharded_vertices_and_queries_gather_in_batch_order(oracle_mod):
     assert want_f.min() > 0 and len(set(want_f.tolist())) > 3 and np.ptp(want_g["gradient"], 0).max() > 0.1   # not a trivial gather
 
 
+def _worker_pull(rank, world, port, q, payload_bytes):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from nbv_exploration_planner_b200 import dist as nd
+    # the "shared arena": every rank can read the same bytes (here: generates them), each copies only its slice
+    src = torch.from_numpy(np.random.default_rng(5).integers(0, 256, payload_bytes, dtype=np.uint8))
+    lo, hi, sl = nd.pull_slice(payload_bytes, world, rank)
+    stage = torch.zeros(world * sl, dtype=torch.uint8)
+    stage[rank * sl:rank * sl + (hi - lo)] = src[lo:hi]                     # the rank's own "PCIe pull"
+    parts = [torch.empty(sl, dtype=torch.uint8) for _ in range(world)]
+    dist.all_gather(parts, stage[rank * sl:(rank + 1) * sl].clone())        # the all-gather that completes the chunk
+    q.put((rank, bool(torch.equal(torch.cat(parts)[:payload_bytes], src)), lo, hi, sl))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("payload_bytes", [1, 255, 4096 * 12 * 3 + 17, 1 << 20])
+def test_pulled_chunk_slices_reassemble_the_payload(payload_bytes):
+    """A pulled commit chunk (every rank copies its slice, an all-gather completes it): world_size 2 over gloo rebuilds the
+    payload byte for byte with the library's slicing rule, including payloads smaller than a slice and ragged tails."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pull, args=(r, world, port, q, payload_bytes)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert all(ok for _, ok, *_ in res)
+    assert res[0][2] == 0 and res[-1][3] == payload_bytes and res[0][4] % 256 == 0
+
+
+def test_pull_slices_cover_the_payload():
+    from nbv_exploration_planner_b200.dist import pull_slice
+    for n in (0, 1, 256, 257, 7043678208, (64 << 20) + 3):
+        for w in (1, 2, 4, 8):
+            spans = [pull_slice(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] or (a[1] == n and b[0] == n) for a, b in zip(spans, spans[1:]))
+            assert all(hi - lo <= sl and sl % 256 == 0 and sl * w >= n for lo, hi, sl in spans)
+
+
 def test_shard_bounds_cover_everything():
     from nbv_exploration_planner_b200.dist import shard_bounds
     for n in (0, 1, 7, 1000, 10001):
